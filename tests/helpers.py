@@ -1,0 +1,77 @@
+# -*- coding: utf-8 -*-
+"""Shared test helpers: build oracle objects out of a golden fixture."""
+import os
+from datetime import datetime, timedelta
+
+import numpy as np
+
+from oracle import boundary as ob
+from oracle import isentropic as oi
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+S, SU, SV, U, V, MTG = oi.S, oi.SU, oi.SV, oi.U, oi.V, oi.MTG
+P = "air_pressure_on_interface_levels"
+EXN = "exner_function_on_interface_levels"
+H = "height_on_interface_levels"
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+class Topography:
+    """Time-growing topography, src/tasmania/domain/topography.py:L75-L81, L106-L116."""
+
+    def __init__(self, steady, grow_seconds):
+        self.steady = np.asarray(steady)
+        self.time = timedelta(seconds=grow_seconds)
+        self.fact = float(self.time.total_seconds() == 0.0)
+        self.profile = self.fact * self.steady
+
+    def update(self, elapsed):
+        if self.fact < 1.0:
+            self.fact = min(elapsed / self.time, 1.0)
+            self.profile = self.fact * self.steady
+
+    def __call__(self):
+        return self.profile
+
+
+def relerr(a, b):
+    """Norm-wise relative error max|a-b| / max|b| (0 if both vanish)."""
+    scale = float(np.max(np.abs(b)))
+    diff = float(np.max(np.abs(np.asarray(a) - np.asarray(b))))
+    return diff / scale if scale > 0 else diff
+
+
+def oracle_dry_run(fx, nsteps=None):
+    """Run the oracle dycore on a ``isen_dry_*`` fixture; returns (final dict, stage0 dict)."""
+    nx, ny, nz, nb, nr, nsteps_fx, damp_depth, damp_every = (int(v) for v in fx["dims"])
+    nsteps = nsteps or nsteps_fx
+    dx, dy, dz, pt, dt_s, eps, damp_max, topo_time = (float(v) for v in fx["params"])
+    scheme, flux = (str(v) for v in fx["scheme"])
+    grid = oi.Grid(nx, ny, nz, dx, dy, dz, fx["z_hl"], fx["z"])
+    hb = ob.Relaxed(nx, ny, nz, nb, nr)
+    names = (S, MTG, SU, U, SV, V, P, EXN, H)
+    state = {n: fx["init_" + n].copy() for n in names}
+    state["time"] = datetime(2000, 1, 1)
+    hb.reference_state = {n: state[n].copy() for n in names}
+    topo = Topography(fx["topo_steady"], topo_time)
+    dyc = oi.IsentropicDycore(grid, hb, topo, scheme=scheme, flux=flux, pt=pt, eps=eps,
+                              damp=True, damp_at_every_stage=bool(damp_every),
+                              damp_depth=damp_depth, damp_max=damp_max)
+    dt = timedelta(seconds=dt_s)
+    stage0 = None
+    for step in range(nsteps):
+        topo.update((step + 1) * dt)
+        out = dyc(state, {}, dt)
+        if step == 0:
+            stage0 = {n: dyc._stage_states[0][n].copy() if dyc.stages > 1 else out[n].copy()
+                      for n in (S, SU, U, SV, V)}
+        new = {n: out[n].copy() for n in (S, SU, U, SV, V)}
+        new["time"] = out["time"]
+        for n in (P, EXN, H, MTG):
+            new[n] = state[n].copy()
+        oi.refresh_diagnostics(grid, topo(), new[S], pt, new[P], new[EXN], new[MTG], new[H])
+        state = new
+    return state, stage0, (grid, hb, topo, dyc)

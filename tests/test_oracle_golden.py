@@ -1,0 +1,199 @@
+# -*- coding: utf-8 -*-
+"""Pin the oracle against fixtures produced by the reference's own numpy code
+(tests/golden/generate_golden.py).  Bit-exact: same numpy, same operation order."""
+import numpy as np
+import pytest
+
+from oracle import boundary as ob
+from oracle import dwarfs as od
+from oracle import isentropic as oi
+from oracle.fluxes import EXTENT
+from tests import helpers as hp
+
+SCHEMES = ("upwind", "centered", "third_order_upwind", "fifth_order_upwind")
+
+
+def eq(a, b):
+    np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("moist", (False, True))
+@pytest.mark.parametrize("tnd", (False, True))
+def test_k1_k2(stencils_golden, scheme, moist, tnd):
+    fx = stencils_golden
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    dt, dx, dy, eps = fx["scalars"]
+    e = EXTENT[scheme]
+    origin, domain = (e, e, 0), (nx - 2 * e, ny - 2 * e, nz)
+    shape = fx["s_now"].shape
+    tag = f"{scheme}_m{int(moist)}_t{int(tnd)}"
+    s_new = np.zeros(shape)
+    sq_new = [np.zeros(shape) for _ in range(3)]
+    kw = {}
+    if moist:
+        kw = dict(moist=True, sq_now=list(fx["sq_now"]), sq_int=list(fx["sq_int"]), sq_new=sq_new,
+                  q_tnd=list(fx["q_tnd"]) if tnd else (None, None, None))
+    oi.step_forward_euler(scheme, fx["s_now"], fx["s_int"], s_new, fx["u_int"], fx["v_int"],
+                          dt=dt, dx=dx, dy=dy, origin=origin, domain=domain,
+                          s_tnd=fx["s_tnd"] if tnd else None, **kw)
+    eq(s_new, fx[f"k1_{tag}_s_new"])
+    if moist:
+        eq(np.stack(sq_new), fx[f"k1_{tag}_sq_new"])
+        return
+    su_new, sv_new = np.zeros(shape), np.zeros(shape)
+    oi.step_forward_euler_momentum(
+        scheme, fx["s_now"], fx["s_new_in"], fx["u_int"], fx["v_int"], fx["su_now"], fx["su_int"],
+        su_new, fx["sv_now"], fx["sv_int"], sv_new, fx["mtg_now"], fx["mtg_new"], dt=dt, dx=dx,
+        dy=dy, eps=eps, origin=origin, domain=domain,
+        su_tnd=fx["su_tnd"] if tnd else None, sv_tnd=fx["sv_tnd"] if tnd else None)
+    eq(su_new, fx[f"k2_{tag}_su_new"])
+    eq(sv_new, fx[f"k2_{tag}_sv_new"])
+
+
+def test_k3_diagnostics(stencils_golden):
+    fx = stencils_golden
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    dz, pt, theta_s = fx["k3_scalars"]
+    shape = fx["k3_s"].shape
+    box = dict(origin=(0, 0, 0), domain=(nx, ny, nz + 1))
+    mtg = np.zeros(shape)
+    oi.montgomery(fx["k3_hs"], fx["k3_s"], mtg, dz=dz, pt=pt, theta_s=theta_s, **box)
+    eq(mtg, fx["k3_mtg"])
+    p, exn, mtg2, h = (np.zeros(shape) for _ in range(4))
+    oi.diagnostic_variables(fx["k3_theta"], fx["k3_hs"], fx["k3_s"], p, exn, mtg2, h, dz=dz, pt=pt,
+                            **box)
+    for a, n in ((p, "p"), (exn, "exn"), (mtg2, "mtg2"), (h, "h")):
+        eq(a, fx["k3_" + n])
+    h2 = np.zeros(shape)
+    oi.height(fx["k3_theta"], fx["k3_hs"], fx["k3_s"], h2, dz=dz, pt=pt, **box)
+    eq(h2, fx["k3_h2"])
+    rho, t = np.zeros(shape), np.zeros(shape)
+    oi.density_and_temperature(fx["k3_theta"], fx["k3_s"], exn, h, rho, t, origin=(0, 0, 0),
+                               domain=(nx, ny, nz))
+    eq(rho, fx["k3_rho"])
+    eq(t, fx["k3_t"])
+
+
+def test_k4_k7(stencils_golden):
+    fx = stencils_golden
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    shape = fx["s_now"].shape
+    u, v = np.zeros(shape), np.zeros(shape)
+    od.get_velocity_components(nx, ny, nz, fx["s_now"], fx["su_now"], fx["sv_now"], u, v)
+    eq(u, fx["k4_u"])
+    eq(v, fx["k4_v"])
+    du, dv = np.zeros(shape), np.zeros(shape)
+    od.momenta(fx["s_now"], fx["u_int"], fx["v_int"], du, dv, (0, 0, 0), (nx, ny, nz))
+    eq(du, fx["k4_du"])
+    eq(dv, fx["k4_dv"])
+    sq, q = np.zeros(shape), np.zeros(shape)
+    od.density(fx["s_now"], fx["k7_q"], sq, (0, 0, 0), (nx, ny, nz))
+    eq(sq, fx["k7_sq"])
+    od.mass_fraction(fx["s_now"], fx["k7_sq_in"], q, (0, 0, 0), (nx, ny, nz))
+    eq(q, fx["k7_q_out"])
+
+
+def test_k5_relaxed(stencils_golden):
+    fx = stencils_golden
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    gamma = ob.relaxed_gamma(nx, ny, nz, 3, 6)
+    eq(gamma, fx["k5_gamma"])
+    phi = fx["k5_phi"].copy()
+    ob.irelax(gamma, fx["k5_phi_ref"], phi, (0, 0, 0), (nx, ny, nz))
+    eq(phi, fx["k5_irelax"])
+    out = np.zeros_like(phi)
+    ob.relax(gamma, fx["k5_phi"], fx["k5_phi_ref"], out, (0, 0, 0), (nx + 1, ny, nz))
+    eq(out, fx["k5_relax"])
+
+
+def test_k6_rayleigh(stencils_golden):
+    fx = stencils_golden
+    shape = fx["k5_phi"].shape
+    depth, cmax, dt = fx["k6_params"]
+    r = od.rayleigh_coefficient(fx["k6_z"], fx["k6_zhl"][0], int(depth), cmax, shape[2])
+    rmat = np.zeros(shape)
+    rmat[...] = r[None, None, :]
+    eq(rmat, fx["k6_rmat"])
+    out = np.zeros(shape)
+    od.damping(fx["k5_phi"], fx["k5_phi_ref"], fx["s_now"], rmat, out, dt, (0, 0, 0), shape)
+    eq(out, fx["k6_out"])
+
+
+@pytest.mark.parametrize("order", (2, 4))
+def test_k8_diffusion(stencils_golden, order):
+    fx = stencils_golden
+    shape = fx["k5_phi"].shape
+    _, dx, dy, _ = fx["scalars"]
+    nb = order // 2
+    gamma = np.zeros(shape)
+    gamma[...] = od.vertical_profile(0.5, 1.0, 3, shape[2])[None, None, :]
+    eq(gamma, fx[f"k8_{order}_gamma"])
+    origin = (nb, nb, 0)
+    domain = (shape[0] - 2 * nb, shape[1] - 2 * nb, shape[2])
+    tnd = np.zeros(shape)
+    od.diffusion(order, fx["k5_phi"], gamma, tnd, dx, dy, True, origin, domain)
+    eq(tnd, fx[f"k8_{order}_tnd"])
+    acc = fx["k5_phi_ref"].copy()
+    od.diffusion(order, fx["k5_phi"], gamma, acc, dx, dy, False, origin, domain)
+    eq(acc, fx[f"k8_{order}_acc"])
+
+
+@pytest.mark.parametrize("order", (1, 2, 3))
+def test_k9_smoothing(stencils_golden, order):
+    fx = stencils_golden
+    shape = fx["k5_phi"].shape
+    gamma = np.zeros(shape)
+    gamma[...] = od.vertical_profile(0.03, 0.24, 3, shape[2])[None, None, :]
+    eq(gamma, fx[f"k9_{order}_gamma"])
+    out = np.zeros(shape)
+    od.horizontal_smoothing(order, fx["k5_phi"], gamma, out)
+    eq(out, fx[f"k9_{order}_out"])
+
+
+def test_k12_elementwise(stencils_golden):
+    fx = stencils_golden
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    a, b, c = fx["k12_a"], fx["k12_b"], fx["k12_c"]
+    box = (slice(1, nx - 1), slice(2, ny - 1), slice(0, nz))
+    E = od.ELEMENTWISE
+
+    def chk(name, val, base=None):
+        exp = np.zeros_like(a) if base is None else base.copy()
+        exp[box] = val
+        eq(exp, fx["k12_" + name])
+
+    chk("abs", E["abs"](a[box]))
+    chk("add", E["add"](a[box], b[box]))
+    chk("addsub", E["addsub"](a[box], b[box], c[box]))
+    chk("clip", E["clip"](a[box]))
+    chk("fma", E["fma"](a[box], b[box], 0.37))
+    chk("mul", E["mul"](a[box], b[box]))
+    chk("scale", E["scale"](a[box], -1.7))
+    chk("sub", E["sub"](a[box], b[box]))
+    chk("copy", a[box])
+    chk("copychange", -a[box])
+    chk("sts_rk2_0", E["sts_rk2_0"](a[box], b[box], c[box], 0.8))
+    chk("sts_rk3ws_0", E["sts_rk3ws_0"](a[box], b[box], c[box], 0.8))
+    chk("iabs", np.abs(a[box]), a)
+    chk("iadd", a[box] + b[box], a)
+    chk("iaddsub", a[box] + (b[box] - c[box]), a)
+    chk("iclip", np.where(a[box] > 0, a[box], 0), a)
+    chk("imul", a[box] * b[box], a)
+    chk("iscale", a[box] * 2.5, a)
+    chk("isub", a[box] - b[box], a)
+
+
+@pytest.mark.parametrize(
+    "case", ("isen_dry_rk3_5th", "isen_dry_rk3_3rd", "isen_dry_rk3_cen", "isen_dry_fe_upw")
+)
+def test_dry_dycore_orchestration(case):
+    """The oracle's restated orchestration vs. the reference's own classes driving the
+    reference's own ``stage_array_call_dry`` over several steps."""
+    fx = hp.load(case)
+    final, stage0, _ = hp.oracle_dry_run(fx)
+    nx, ny, nz = (int(v) for v in fx["dims"][:3])
+    for n in (hp.S, hp.SU, hp.SV, hp.U, hp.V):
+        eq(stage0[n][: nx + 1, : ny + 1, :nz], fx["stage0_" + n][: nx + 1, : ny + 1, :nz])
+    for n in (hp.S, hp.SU, hp.SV, hp.U, hp.V, hp.MTG, hp.P, hp.EXN, hp.H):
+        eq(final[n], fx["final_" + n])
