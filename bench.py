@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""Benchmark of the tasmania stencil hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+Workload (BASELINE.json): dry isentropic model, flow over an isolated Gaussian mountain,
+relaxed lateral boundaries (nb=3, nr=6), RK3WS + fifth-order upwind, Rayleigh damping
+(depth 15, max 5e-4), dt = 5 s, fp64.  Default size = the configuration the metric's target is
+quoted on: 1024x1024x64 per GPU (config 5; weak scaling over a 2-D decomposition), which also
+keeps every field (0.56 GB) far larger than the 126 MB L2, so no L2 flush is needed between
+timed steps.  ``--workload c2`` runs the 161x161x60 case of config 2 (L2-resident,
+launch-latency regime).
+
+One *step* = ``dycore.update_topography`` + one full RK3WS step (3 fused stages) + the
+``IsentropicDiagnostics`` refresh of p / exn / mtg / h.
+Metric: grid-point updates per second, Mpts*steps/s = nx*ny*nz*steps*N / seconds / 1e6.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from datetime import datetime, timedelta
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P, EXN, H = ("air_pressure_on_interface_levels", "exner_function_on_interface_levels",
+             "height_on_interface_levels")
+
+WORKLOADS = {
+    # name: (nx, ny, nz) per GPU
+    "c5": (1024, 1024, 64),
+    "c2": (161, 161, 60),
+    "small": (256, 256, 64),
+}
+# algorithmic HBM bytes per grid point (SURVEY.md section 8d / BASELINE.md section 4):
+# dry RK3WS step 3 x 112 B + diagnostics refresh 40 B
+BYTES_PER_POINT_STEP = 336 + 40
+BYTES_PER_POINT_STAGE = 112
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ workload set-up (host)
+def mountain_case(nx, ny, nz):
+    """BASELINE config 2/5 initial condition on an (nx, ny, nz) grid; returns (grid, numpy state).
+    Columns of the initial state are horizontally uniform (the mountain has not grown yet), so
+    one column is built with the reference formulas and broadcast."""
+    from tasmania_b200.grid import Grid, Topography, gaussian_profile, isentropic_state_from_brunt_vaisala
+
+    x = np.linspace(-176.0, 176.0, nx)
+    y = np.linspace(-176.0, 176.0, ny)
+    topo = Topography(gaussian_profile(x, y, 500.0, 50.0, 50.0), timedelta(seconds=1800))
+    grid = Grid((-176.0, 176.0), nx, (-176.0, 176.0), ny, (400.0, 280.0), nz, units_to_m=1e3,
+                topography=topo)
+    small = Grid((-176.0, 176.0), 3, (-176.0, 176.0), 3, (400.0, 280.0), nz, units_to_m=1e3)
+    col = isentropic_state_from_brunt_vaisala(small, 22.5, 0.0, 0.015)
+    state = {}
+    for name, a in col.items():
+        full = np.zeros((nx + 1, ny + 1, nz + 1))
+        mi = nx + 1 if "at_u_locations" in name else nx
+        mj = ny + 1 if "at_v_locations" in name else ny
+        full[:mi, :mj, :] = a[1, 1, :][None, None, :]
+        state[name] = full
+    return grid, state
+
+
+class DryRun:
+    """The timed loop on b200 storages."""
+
+    def __init__(self, nx, ny, nz, device_index=0):
+        import torch
+
+        import tasmania_b200 as tb
+        from tasmania_b200.boundary import Relaxed
+        from tasmania_b200.isentropic import (MTG, S, SU, SV, U, V, IsentropicDiagnostics,
+                                              IsentropicDynamicalCore)
+
+        self.tb, self.torch = tb, torch
+        self.names = (S, SU, SV, U, V, MTG)
+        self.out_names = (S, SU, U, SV, V)
+        self.S, self.MTG = S, MTG
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.grid, np_state = mountain_case(nx, ny, nz)
+        self.np_state = np_state
+        self.pt = float(np_state[P][0, 0, 0])
+        self.dt = timedelta(seconds=5)
+        self.hb = Relaxed(nx, ny, nz, 3, nr=6)
+        self.state = {n: tb.as_storage(v) for n, v in np_state.items()}
+        self.state["time"] = datetime(2000, 1, 1)
+        self.hb.reference_state = self.state
+        self.dyc = IsentropicDynamicalCore(
+            self.grid, self.hb, time_integration_scheme="rk3ws_si",
+            horizontal_flux_scheme="fifth_order_upwind",
+            time_integration_properties={"pt": self.pt, "eps": 0.5}, damp=True, damp_depth=15,
+            damp_max=5e-4)
+        assert self.dyc._fused
+        self.diag = IsentropicDiagnostics(self.grid)
+        self.spare = {n: tb.zeros(self.dyc.storage_shape) for n in self.out_names}
+        self.nstep = 0
+
+    def step(self):
+        """update_topography -> dycore -> diagnostics refresh; ping-pong the output buffers."""
+        self.nstep += 1
+        self.dyc.update_topography(self.nstep * self.dt)
+        out = self.dyc(self.state, {}, self.dt, out_state=self.spare)
+        new = {n: out[n] for n in self.out_names}
+        new["time"] = out["time"]
+        for n in (P, EXN, H, self.MTG):
+            new[n] = self.state[n]
+        self.spare = {n: self.state[n] for n in self.out_names}
+        self.diag.get_diagnostic_variables(new[self.S], self.pt, new[P], new[EXN], new[self.MTG], new[H])
+        self.state = new
+
+    # kernels of OUR library launched per step: 3 stages x (S, M, V) + topography scale (at
+    # most 2: dycore + diagnostics hold separate copies) + diagnostic_variables
+    def launches_per_step(self):
+        return 3 * 3 + 1 + 2
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_baseline(seconds_budget=20.0, grid=(161, 161, 60)):
+    """Time the numpy oracle (a port of the reference's numpy backend; the reference itself is
+    Python and cannot travel to the GPU box) on a bounded sample of the same workload: full
+    RK3WS steps of the same physics on a 161x161x60 grid (config 2 size), as many as fit the
+    budget (at least 1).  numpy element-wise code is single-threaded."""
+    from oracle import boundary as ob
+    from oracle import isentropic as oi
+
+    nx, ny, nz = grid
+    g, np_state = mountain_case(nx, ny, nz)
+    pt = float(np_state[P][0, 0, 0])
+    ogrid = oi.Grid(nx, ny, nz, g.dx, g.dy, g.dz, g.z_on_interface_levels, g.z)
+    ohb = ob.Relaxed(nx, ny, nz, 3, 6)
+    state = {n: v.copy() for n, v in np_state.items()}
+    state["time"] = datetime(2000, 1, 1)
+    ohb.reference_state = {n: v.copy() for n, v in np_state.items()}
+    topo = g.topography
+    dyc = oi.IsentropicDycore(ogrid, ohb, lambda: topo.profile, scheme="rk3ws_si",
+                              flux="fifth_order_upwind", pt=pt, eps=0.5, damp=True, damp_depth=15,
+                              damp_max=5e-4)
+    dt = timedelta(seconds=5)
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        topo.update((steps + 1) * dt)
+        out = dyc(state, {}, dt)
+        new = {n: out[n].copy() for n in (oi.S, oi.SU, oi.U, oi.SV, oi.V)}
+        new["time"] = out["time"]
+        for n in (P, EXN, H, oi.MTG):
+            new[n] = state[n]
+        oi.refresh_diagnostics(ogrid, topo.profile, new[oi.S], pt, new[P], new[EXN], new[oi.MTG], new[H])
+        state = new
+        steps += 1
+        if time.perf_counter() - t0 > seconds_budget or steps >= 50:
+            break
+    el = time.perf_counter() - t0
+    return {
+        "value": nx * ny * nz * steps / el / 1e6,
+        "unit": "Mpts*steps/s",
+        "cores": 1,
+        "kind": "port",
+        "sample": f"{steps} RK3WS steps (+diagnostics refresh) of the same dry isentropic workload on "
+                  f"{nx}x{ny}x{nz}, numpy oracle, 1 thread of {os.cpu_count()} host cores, "
+                  f"{el:.1f} s; the reference's gt4py CPU backends are not installable offline",
+    }, steps, el
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the numpy oracle port
+    (the reference is Python + absent on the GPU box; its numpy backend is what the oracle
+    restates and is pinned against).  Each 'step' is one RK3WS step on the bounded sample grid."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny, nz = WORKLOADS["c2"]
+    budget = 8.0 * max(1, args.steps)
+    base, steps, el = cpu_baseline(seconds_budget=min(120.0, budget), grid=(nx, ny, nz))
+    val = base["value"]
+    line = {
+        "impl": "reference", "metric": "grid-point updates/sec", "value": val,
+        "unit": "Mpts*steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+        "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "sample_grid": [nx, ny, nz]},
+        "cpu_baseline": base,
+        "e2e": {"value": val, "unit": "Mpts*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(key):
+    nx, ny, nz = WORKLOADS[key]
+    return (f"dry isentropic, gaussian mountain, relaxed BC nb=3 nr=6, RK3WS + fifth_order_upwind, "
+            f"{nx}x{ny}x{nz} per GPU, fp64")
+
+
+# ------------------------------------------------------------------ our arm
+def run_b200(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the b200 backend has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nx, ny, nz = WORKLOADS[args.workload]
+    if distributed:
+        from tasmania_b200.distributed import DecomposedDryRun
+
+        run = DecomposedDryRun(nx, ny, nz, rank, world)
+    else:
+        run = DryRun(nx, ny, nz, local_rank)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        run.step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        run.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if distributed:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    pts = nx * ny * nz
+    value = pts * args.steps * world / (ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (stage_m: the momentum step), timed live
+    roof = kernel_roofline(run, args) if not distributed else None
+    # ---- end to end through the public API with host buffers
+    e2e = end_to_end(run, args, world, barrier, distributed)
+
+    if rank == 0:
+        base = None
+        if world == 1 and not args.no_cpu_baseline:
+            base, _, _ = cpu_baseline()
+        line = {
+            "metric": "grid-point updates/sec", "value": value, "unit": "Mpts*steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "l2": "inputs larger than L2"
+                       if pts * 8 > 126e6 else "L2-resident grid (no flush: launch-latency regime)",
+                       "decomposition": getattr(run, "decomposition", "1x1")},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": run.launches_per_step() * args.steps,
+            "hbm_frac_step": BYTES_PER_POINT_STEP * pts / (ms / args.steps * 1e-3) / 1e9
+            / measured_peak_gbs()[0],
+        }
+        if roof is not None:
+            line["roofline"] = roof
+        if base is not None:
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(run, args):
+    """Achieved algorithmic GB/s of one fused RK stage (kernels S + M + V), CUDA events on the
+    launching stream around single stage calls inside a running time loop."""
+    import torch
+
+    dyc = run.dyc
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
+    orig = dyc._stage_fused
+    times = []
+
+    def timed(stage, state, timestep, out_state):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig(stage, state, timestep, out_state)
+        b.record()
+        times.append((a, b))
+
+    dyc._stage_fused = timed
+    for _ in range(max(2, min(args.steps, 5))):
+        run.step()
+    torch.cuda.synchronize()
+    dyc._stage_fused = orig
+    ms = [a.elapsed_time(b) for a, b in times]
+    avg = float(np.mean(ms))
+    pts = run.nx * run.ny * run.nz
+    achieved = BYTES_PER_POINT_STAGE * pts / (avg * 1e-3) / 1e9
+    peak, how = measured_peak_gbs()
+    return {"bound": "hbm", "kernel": "fused RK stage (stage_s + stage_m + stage_v kernels)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": how, "ms_per_launch": avg,
+            "algorithmic_bytes_per_launch": BYTES_PER_POINT_STAGE * pts}
+
+
+def end_to_end(run, args, world, barrier, distributed):
+    """Same metric through the public API with HOST buffers: every step copies the stage
+    inputs (s, su, sv, u, v, mtg) from pinned host memory to the device, runs the step, and
+    copies the stepped fields (s, su, sv, u, v) back to pinned host memory."""
+    import torch
+
+    if distributed and not hasattr(run, "state"):
+        return None
+    names_in = run.names
+    names_out = run.out_names
+    host_in = {n: torch.empty_like(run.state[n].t, device="cpu").pin_memory() for n in names_in}
+    for n in names_in:
+        host_in[n].copy_(run.state[n].t)
+    host_out = {n: torch.empty_like(run.state[n].t, device="cpu").pin_memory() for n in names_out}
+    steps = max(1, min(args.steps, 3))
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        for n in names_in:
+            run.state[n].t.copy_(host_in[n], non_blocking=True)
+        run.step()
+        for n in names_out:
+            host_out[n].copy_(run.state[n].t, non_blocking=True)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if distributed:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    nbytes = lambda d: int(sum(t.numel() * 8 for t in d.values()))  # noqa: E731
+    pts = run.nx * run.ny * run.nz
+    return {"value": pts * steps * world / (ms * 1e-3) / 1e6, "unit": "Mpts*steps/s",
+            "h2d_bytes_per_step": nbytes(host_in), "d2h_bytes_per_step": nbytes(host_out),
+            "steps": steps}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,233 @@
+/* tasmania_b200.h -- C ABI of libtasmania_b200.so
+ *
+ * B200-native (sm_100a, fp64) replacement for the stencils on tasmania's hot path
+ * (SURVEY.md section 8a, K1..K12).  tasmania is pure Python: the "FFI" these entry points
+ * replace is the call of a compiled stencil object,
+ *
+ *     stencil(**arrays, **scalars, origin=(i0,j0,k0), domain=(di,dj,dk), ...)
+ *
+ * returned by `StencilFactory.compile_stencil(name)`
+ * (reference: src/tasmania/framework/stencil.py:L273-L284, the numpy "compiler" being
+ * src/tasmania/framework/subclasses/stencil_compilers.py:L91-L99).  Each function below
+ * cites the reference stencil definition it stands in for; argument names follow the
+ * reference's keyword names.  The Python side (tasmania_b200/lib.py) binds them with ctypes
+ * and fills `tb200_field` from `__cuda_array_interface__`.
+ *
+ * Conventions
+ *  - every field is fp64 device memory, addressed with explicit element strides, so sliced
+ *    (non-contiguous) views are fine; the library never owns, frees or retains field memory;
+ *  - `origin`/`domain` have the reference's meaning (first point / number of points);
+ *  - optional fields are passed as NULL;
+ *  - kernels are enqueued on `stream` (a cudaStream_t; NULL = legacy default stream) and the
+ *    call returns immediately: no device synchronisation inside the library;
+ *  - return value 0 = success, otherwise an error code; `tb200_last_error()` gives the
+ *    thread-local message.  There is no CPU fallback: a call without a usable CUDA device
+ *    fails with TB200_ERR_CUDA.
+ */
+#ifndef TASMANIA_B200_H
+#define TASMANIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb200_field {
+  void *ptr;         /* device pointer to element (0,0,0), fp64 */
+  int64_t shape[3];  /* logical extents (ni, nj, nk) */
+  int64_t stride[3]; /* strides in ELEMENTS */
+} tb200_field;
+
+enum {
+  TB200_OK = 0,
+  TB200_ERR_ARG = 1,   /* bad argument (NULL field, box outside the storage, bad enum) */
+  TB200_ERR_CUDA = 2,  /* CUDA runtime error (message holds cudaGetErrorString) */
+  TB200_ERR_LAYOUT = 3 /* fused kernels need unit stride along i */
+};
+
+/* horizontal flux schemes: src/tasmania/isentropic/dynamics/subclasses/
+ * minimal_horizontal_fluxes/{upwind,centered,third_order_upwind,fifth_order_upwind}.py */
+enum {
+  TB200_FLUX_UPWIND = 0,
+  TB200_FLUX_CENTERED = 1,
+  TB200_FLUX_THIRD_ORDER_UPWIND = 2,
+  TB200_FLUX_FIFTH_ORDER_UPWIND = 3
+};
+
+/* element-wise stencils: src/tasmania/framework/subclasses/stencil_definitions/
+ * copy.py:L30-L41, math.py:L32-L124, algorithms.py:L60-L69 */
+enum {
+  TB200_EW_COPY = 0,        /* out = a                         */
+  TB200_EW_COPYCHANGE = 1,  /* out = -a                        */
+  TB200_EW_ABS = 2,         /* out = |a|                       */
+  TB200_EW_ADD = 3,         /* out = a + b                     */
+  TB200_EW_ADDSUB = 4,      /* out = a + b - c                 */
+  TB200_EW_CLIP = 5,        /* out = a > 0 ? a : 0             */
+  TB200_EW_FMA = 6,         /* out = a + f * b                 */
+  TB200_EW_MUL = 7,         /* out = a * b                     */
+  TB200_EW_SCALE = 8,       /* out = f * a                     */
+  TB200_EW_SUB = 9,         /* out = a - b                     */
+  TB200_EW_STS_RK2_0 = 10,  /* out = 0.5 * (a + b + f * c)     */
+  TB200_EW_STS_RK3WS_0 = 11,/* out = (2 a + b + f * c) / 3     */
+  TB200_EW_IADDSUB = 12,    /* out = a + (b - c)  (in-place `+=` form, math.py:L84-L88) */
+  TB200_EW_ISCALE = 13      /* out = a * f        (in-place `*=` form, math.py:L103-L106) */
+};
+
+const char *tb200_last_error(void);
+int tb200_version(void);
+/* number of visible CUDA devices, or a negative error code */
+int tb200_device_count(void);
+
+/* ---- K12 element-wise ------------------------------------------------------------- */
+int tb200_elementwise(int op, tb200_field *out, const tb200_field *a, const tb200_field *b,
+                      const tb200_field *c, double f, const int32_t origin[3],
+                      const int32_t domain[3], void *stream);
+
+/* ---- K5 lateral boundaries --------------------------------------------------------- */
+/* algorithms.py:L32-L43 (irelax; pass in_phi == NULL) and L46-L57 (relax) */
+int tb200_relax(const tb200_field *in_gamma, const tb200_field *in_phi,
+                const tb200_field *in_phi_ref, tb200_field *out_phi, const int32_t origin[3],
+                const int32_t domain[3], void *stream);
+/* Periodic.enforce_field, src/tasmania/domain/subclasses/horizontal_boundaries/
+ * periodic.py:L98-L122; nx, ny = physical sizes, mx, my = nx|nx+1, ny|ny+1 (staggering) */
+int tb200_periodic_enforce(tb200_field *field, int nx, int ny, int nb, int mx, int my,
+                           void *stream);
+/* Relaxed.set_outermost_layers_x / _y, relaxed.py:L161-L191; axis 0 -> x, 1 -> y */
+int tb200_set_outermost_layers(tb200_field *field, const tb200_field *field_ref, int axis,
+                               int mi, int mj, void *stream);
+
+/* ---- K6 Rayleigh damping: src/tasmania/dwarfs/subclasses/vertical_dampers/
+ * rayleigh.py:L90-L109 */
+int tb200_damping(const tb200_field *in_phi_now, const tb200_field *in_phi_new,
+                  const tb200_field *in_phi_ref, const tb200_field *in_rmat,
+                  tb200_field *out_phi, double dt, const int32_t origin[3],
+                  const int32_t domain[3], void *stream);
+
+/* ---- K4 / K7 diagnostics: src/tasmania/dwarfs/diagnostics.py:L175-L272, L400-L450 --- */
+int tb200_velocity(int axis, const tb200_field *in_d, const tb200_field *in_dw,
+                   tb200_field *out_w, int staggering, const int32_t origin[3],
+                   const int32_t domain[3], void *stream);
+int tb200_momenta(const tb200_field *in_d, const tb200_field *in_u, const tb200_field *in_v,
+                  tb200_field *out_du, tb200_field *out_dv, int staggering,
+                  const int32_t origin[3], const int32_t domain[3], void *stream);
+int tb200_density(const tb200_field *in_d, const tb200_field *in_q, tb200_field *out_dq,
+                  int clipping, const int32_t origin[3], const int32_t domain[3],
+                  void *stream);
+int tb200_mass_fraction(const tb200_field *in_d, const tb200_field *in_dq, tb200_field *out_q,
+                        int clipping, const int32_t origin[3], const int32_t domain[3],
+                        void *stream);
+
+/* ---- K8 diffusion: src/tasmania/dwarfs/subclasses/horizontal_diffusers/
+ * second_order.py:L92-L106, fourth_order.py:L92-L124 (+ set_output, generics.py:L38-L40).
+ * order = 2 | 4.  k runs over [origin[2], origin[2]+domain[2]); the reference's numpy
+ * definition ignores the k-range and processes every level of the storage -- the Python
+ * stencil wrapper passes the full k extent to reproduce that. */
+int tb200_diffusion(int order, const tb200_field *in_phi, const tb200_field *in_gamma,
+                    tb200_field *out_phi, double dx, double dy, int ow_out_phi,
+                    const int32_t origin[3], const int32_t domain[3], void *stream);
+
+/* ---- K9 smoothing: src/tasmania/dwarfs/subclasses/horizontal_smoothers/
+ * first_order.py:L113-L126, second_order.py:L113-L139, third_order.py:L113-L150.
+ * order = 1 | 2 | 3.  With rim_copy != 0 the four `copy` launches of
+ * HorizontalSmoothing.__call__ (first_order.py:L77-L110) are fused in: points of the
+ * (2*origin[0]+domain[0], 2*origin[1]+domain[1]) box -- the smoother's shape -- that lie
+ * outside [origin, origin+domain) are copied from in_phi. */
+int tb200_smoothing(int order, const tb200_field *in_phi, const tb200_field *in_gamma,
+                    tb200_field *out_phi, int rim_copy, const int32_t origin[3],
+                    const int32_t domain[3], void *stream);
+
+/* ---- K1 / K2 isentropic prognostic step: src/tasmania/isentropic/dynamics/subclasses/
+ * prognostics/utils.py:L43-L134 and L137-L204.  The moist tracers are passed as arrays of
+ * three field pointers (qv, qc, qr order); NULL arrays = dry. */
+int tb200_step_forward_euler(int flux_scheme, const tb200_field *s_now,
+                             const tb200_field *s_int, tb200_field *s_new,
+                             const tb200_field *u_int, const tb200_field *v_int,
+                             const tb200_field *s_tnd, const tb200_field *const *sq_now,
+                             const tb200_field *const *sq_int, tb200_field *const *sq_new,
+                             const tb200_field *const *q_tnd, double dt, double dx, double dy,
+                             const int32_t origin[3], const int32_t domain[3], void *stream);
+int tb200_step_forward_euler_momentum(
+    int flux_scheme, const tb200_field *s_now, const tb200_field *s_new,
+    const tb200_field *u_int, const tb200_field *v_int, const tb200_field *su_now,
+    const tb200_field *su_int, tb200_field *su_new, const tb200_field *sv_now,
+    const tb200_field *sv_int, tb200_field *sv_new, const tb200_field *mtg_now,
+    const tb200_field *mtg_new, const tb200_field *su_tnd, const tb200_field *sv_tnd,
+    double dt, double dx, double dy, double eps, const int32_t origin[3],
+    const int32_t domain[3], void *stream);
+
+/* ---- K3 column scans: src/tasmania/isentropic/dynamics/diagnostics.py
+ * montgomery L408-L438, diagnostic_variables L319-L360, height L472-L503,
+ * density_and_temperature L540-L570.  constants = {pref, rd, g, cp}.
+ * in_theta may be NULL for montgomery (theta_s is passed instead). */
+int tb200_montgomery(const tb200_field *in_hs, const tb200_field *in_s,
+                     tb200_field *inout_mtg, double dz, double pt, double theta_s,
+                     const double constants[4], const int32_t origin[3],
+                     const int32_t domain[3], void *stream);
+int tb200_diagnostic_variables(const tb200_field *in_theta, const tb200_field *in_hs,
+                               const tb200_field *in_s, tb200_field *inout_p,
+                               tb200_field *out_exn, tb200_field *inout_mtg,
+                               tb200_field *inout_h, double dz, double pt,
+                               const double constants[4], const int32_t origin[3],
+                               const int32_t domain[3], void *stream);
+int tb200_height(const tb200_field *in_theta, const tb200_field *in_hs,
+                 const tb200_field *in_s, tb200_field *inout_h, double dz, double pt,
+                 const double constants[4], const int32_t origin[3],
+                 const int32_t domain[3], void *stream);
+int tb200_density_and_temperature(const tb200_field *in_theta, const tb200_field *in_s,
+                                  const tb200_field *in_exn, const tb200_field *in_h,
+                                  tb200_field *out_rho, tb200_field *out_t, double cp,
+                                  const int32_t origin[3], const int32_t domain[3],
+                                  void *stream);
+
+/* ---- K10 Burgers: src/tasmania/burgers/dynamics/stepper.py:L188-L227 with the advection
+ * subroutines of burgers/dynamics/subclasses/advection/{first..sixth}_order.py;
+ * advection_order = 1..6 */
+int tb200_burgers_forward_euler(int advection_order, const tb200_field *in_u,
+                                const tb200_field *in_v, const tb200_field *in_u_tmp,
+                                const tb200_field *in_v_tmp, tb200_field *out_u,
+                                tb200_field *out_v, const tb200_field *in_u_tnd,
+                                const tb200_field *in_v_tnd, double dt, double dx, double dy,
+                                const int32_t origin[3], const int32_t domain[3],
+                                void *stream);
+
+/* ---- fused dry isentropic stage (the benchmark hot path) ---------------------------
+ * One RK stage of IsentropicDynamicalCore.stage_array_call_dry
+ * (src/tasmania/isentropic/dynamics/dycore.py:L641-L721) with the relaxed lateral boundary:
+ * K1 + irelax(s) + pressure/Exner/Montgomery scans + K2 + irelax(s, su, sv) + Rayleigh
+ * damping + velocity diagnosis + outermost layers, in three kernels.  All fields share one
+ * storage shape and have unit stride along i.  `scratch_exn`/`scratch_mtg` are caller-owned
+ * work storages of the same shape.  hs2d: topography, shape (>=nx, >=ny, 1).
+ * rmat1d / gamma2d: damping profile (1,1,nk) and relaxation coefficients (ni,nj,1) given as
+ * fields (strides pick the rank).  damp != 0 applies the damping in this stage. */
+typedef struct tb200_isentropic_stage {
+  int32_t nx, ny, nz, nb; /* numerical grid, boundary layers */
+  int32_t flux_scheme;
+  int32_t damp;
+  double dt;        /* stage time step [s] */
+  double dt_full;   /* full time step used by the damping [s] */
+  double dx, dy, dz, eps, pt, theta_s;
+  double constants[4]; /* pref, rd, g, cp */
+} tb200_isentropic_stage;
+
+int tb200_isentropic_stage_dry(
+    const tb200_isentropic_stage *cfg, const tb200_field *s_now, const tb200_field *su_now,
+    const tb200_field *sv_now, const tb200_field *mtg_now, const tb200_field *s_int,
+    const tb200_field *su_int, const tb200_field *sv_int, const tb200_field *u_int,
+    const tb200_field *v_int, tb200_field *s_new, tb200_field *su_new, tb200_field *sv_new,
+    tb200_field *u_new, tb200_field *v_new, const tb200_field *s_ref,
+    const tb200_field *su_ref, const tb200_field *sv_ref, const tb200_field *u_ref,
+    const tb200_field *v_ref, const tb200_field *gamma, const tb200_field *rmat,
+    const tb200_field *hs, tb200_field *scratch_exn, tb200_field *scratch_mtg, void *stream);
+
+/* ---- halo exchange support (2-D domain decomposition) ------------
+ * pack/unpack a box of a field into/from a contiguous buffer (i fastest). */
+int tb200_pack_box(const tb200_field *field, double *buffer, const int32_t origin[3],
+                   const int32_t domain[3], void *stream);
+int tb200_unpack_box(tb200_field *field, const double *buffer, const int32_t origin[3],
+                     const int32_t domain[3], void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TASMANIA_B200_H */

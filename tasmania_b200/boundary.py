@@ -1,0 +1,214 @@
+# -*- coding: utf-8 -*-
+"""Lateral boundary conditions on b200 storages (row K5 of SURVEY.md section 8a): the raw-field
+operations of the reference's ``HorizontalBoundary`` subclasses
+
+  Relaxed    src/tasmania/domain/subclasses/horizontal_boundaries/relaxed.py:L34-L247
+  Periodic   src/tasmania/domain/subclasses/horizontal_boundaries/periodic.py:L32-L122
+  Dirichlet  src/tasmania/domain/subclasses/horizontal_boundaries/dirichlet.py:L40-L160
+  enforce_raw  src/tasmania/domain/horizontal_boundary.py:L299-L344
+
+with the same method names.  Coefficients are built once on the host (numpy, O(nx ny)) and
+uploaded; every field operation is a CUDA kernel.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from tasmania_b200 import lib, storage
+from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
+
+
+def _extent(nx, ny, nz, name):
+    name = name or ""
+    mi = nx + 1 if ("at_u_locations" in name or "at_uv_locations" in name) else nx
+    mj = ny + 1 if ("at_v_locations" in name or "at_uv_locations" in name) else ny
+    mk = nz + 1 if "on_interface_levels" in name else nz
+    return mi, mj, mk
+
+
+class HorizontalBoundary(StencilFactory):
+    """Common part: sizes, the reference state (deep copies), ``enforce_raw``."""
+
+    type = None
+
+    def __init__(self, nx, ny, nz, nb, backend_options=None, storage_options=None):
+        super().__init__("b200", backend_options or BackendOptions(), storage_options or StorageOptions())
+        self.nx, self.ny, self.nz, self.nb = int(nx), int(ny), int(nz), int(nb)
+        self._ref_state = None
+
+    @property
+    def reference_state(self):
+        return self._ref_state if self._ref_state is not None else {}
+
+    @reference_state.setter
+    def reference_state(self, ref_state):
+        # deep copies, horizontal_boundary.py:L131-L144
+        self._ref_state = {}
+        for name, val in ref_state.items():
+            if name == "time":
+                self._ref_state[name] = val
+            else:
+                self._ref_state[name] = storage.as_storage(
+                    val, device=self.storage_options.device).copy()
+
+    @staticmethod
+    def factory(boundary_type, nx, ny, nz, nb, **kwargs):
+        classes = {"relaxed": Relaxed, "periodic": Periodic, "dirichlet": Dirichlet}
+        if boundary_type not in classes:
+            raise ValueError(f"unknown (or out-of-scope) horizontal boundary type {boundary_type!r}")
+        return classes[boundary_type](nx, ny, nz, nb, **kwargs)
+
+    def enforce_raw(self, state, field_properties=None):
+        """Only fields that have a reference value are touched (base-class behaviour)."""
+        ref = self.reference_state
+        for name in state:
+            if name == "time" or name not in ref:
+                continue
+            if field_properties is not None and name not in field_properties:
+                continue
+            self.enforce_field(state[name], field_name=name, time=state.get("time"))
+
+    def enforce_field(self, field, field_name=None, field_units=None, time=None):
+        raise NotImplementedError
+
+
+class Relaxed(HorizontalBoundary):
+    """Relaxed boundary conditions (``ni = nx``, ``nj = ny``)."""
+
+    type = "relaxed"
+
+    def __init__(self, nx, ny, nz, nb, nr=8, backend_options=None, storage_options=None,
+                 storage_shape=None):
+        assert nx > 1 and ny > 1
+        assert nr <= nx / 2 and nr <= ny / 2, "Depth of relaxation region cannot exceed n/2."
+        assert nr <= 8, "Depth of relaxation region cannot exceed 8."
+        assert nb <= nr, "Number of boundary layers cannot exceed depth of relaxation region."
+        super().__init__(nx, ny, nz, nb, backend_options, storage_options)
+        self.nr = nr
+        self.ni, self.nj = self.nx, self.ny
+        self._shape = tuple(storage_shape or (nx + 1, ny + 1, nz + 1))
+        self._allocate_coefficient_matrix()
+        self._stencil = self.compile_stencil("irelax")
+
+    def _allocate_coefficient_matrix(self):
+        """relaxed.py:L193-L247; gamma does not depend on k -> stored once as (ni, nj, 1)
+        and broadcast through a zero k-stride view (saves a 3-D storage the reference streams
+        on every call)."""
+        nx, ny, nb, nr = self.nx, self.ny, self.nb, self.nr
+        rel = np.array([1.0] + [1.0 - np.tanh(0.5 * m) for m in range(1, 8)])[:nr]
+        rel[:nb] = 1.0
+        rrel = rel[::-1]
+        g = np.zeros((self._shape[0], self._shape[1]))
+        corner = np.zeros((nr, nr))
+        for i in range(nr):
+            corner[i, i:] = rel[i]
+            corner[i:, i] = rel[i]
+        g[:nr, :nr] = corner
+        g[:nr, nr : ny - nr] = rel[:, None]
+        g[:nr, ny - nr : ny] = corner[:, ::-1]
+        g[nx - nr : nx, :nr] = corner[::-1, :]
+        g[nx - nr : nx, nr : ny - nr] = rrel[:, None]
+        g[nx - nr : nx, ny - nr : ny] = corner[::-1, ::-1]
+        g[nr : nx - nr, :nr] = rel[None, :]
+        g[nr : nx - nr, ny - nr : ny] = rrel[None, :]
+        g[nx : nx + 1, : ny + 1] = 1.0
+        g[: nx + 1, ny : ny + 1] = 1.0
+        g2d = storage.as_storage(g[:, :, None], device=self.storage_options.device)
+        self._gamma2d = g2d
+        # (ni, nj, nk) view with stride 0 along k
+        self._gamma = storage.B200Array(g2d.t.expand(-1, -1, self._shape[2]))
+
+    def enforce_field(self, field, field_name=None, field_units=None, time=None):
+        mi, mj, mk = _extent(self.nx, self.ny, self.nz, field_name)
+        self._stencil(in_gamma=self._gamma, in_phi_ref=self.reference_state[field_name],
+                      inout_phi=field, origin=(0, 0, 0), domain=(mi, mj, mk))
+
+    def _outermost(self, axis, field, field_name):
+        mi, mj, _ = _extent(self.nx, self.ny, self.nz, field_name)
+        lib.check(lib.load().tb200_set_outermost_layers(
+            lib.as_field(field), lib.as_field(self.reference_state[field_name]), axis, mi, mj,
+            lib.current_stream()), "tb200_set_outermost_layers")
+
+    def set_outermost_layers_x(self, field, field_name=None, field_units=None, time=None):
+        self._outermost(0, field, field_name)
+
+    def set_outermost_layers_y(self, field, field_name=None, field_units=None, time=None):
+        self._outermost(1, field, field_name)
+
+    def get_numerical_field(self, field, field_name=None):
+        return field
+
+    def get_physical_field(self, field, field_name=None):
+        return field
+
+
+class Periodic(HorizontalBoundary):
+    """Periodic conditions; fields live on the numerical grid ``(nx + 2 nb, ny + 2 nb)``."""
+
+    type = "periodic"
+
+    def __init__(self, nx, ny, nz, nb, backend_options=None, storage_options=None):
+        assert nx > 1 and ny > 1 and nb <= nx / 2 and nb <= ny / 2
+        super().__init__(nx, ny, nz, nb, backend_options, storage_options)
+        self.ni, self.nj = self.nx + 2 * nb, self.ny + 2 * nb
+
+    def enforce_field(self, field, field_name=None, field_units=None, time=None):
+        mx, my, _ = _extent(self.nx, self.ny, self.nz, field_name)
+        lib.check(lib.load().tb200_periodic_enforce(
+            lib.as_field(field), self.nx, self.ny, self.nb, mx, my, lib.current_stream()),
+            "tb200_periodic_enforce")
+
+    def get_numerical_field(self, field, field_name=None):
+        """periodic.py:L64-L96"""
+        nb = self.nb
+        mx, my, _ = _extent(self.nx, self.ny, self.nz, field_name)
+        src = storage.as_storage(field, device=self.storage_options.device)
+        shape = (src.shape[0] + 2 * nb, src.shape[1] + 2 * nb) + tuple(src.shape[2:])
+        trg = self.zeros(shape=shape)
+        trg[nb : mx + nb, nb : my + nb] = src[:mx, :my]
+        self.enforce_field(trg, field_name)
+        return trg
+
+    def get_physical_field(self, field, field_name=None):
+        return field[self.nb : -self.nb, self.nb : -self.nb]
+
+    def set_outermost_layers_x(self, field, field_name=None, field_units=None, time=None):
+        field[0, :] = field[-2, :]
+        field[-1, :] = field[1, :]
+
+    def set_outermost_layers_y(self, field, field_name=None, field_units=None, time=None):
+        field[:, 0] = field[:, -2]
+        field[:, -1] = field[:, 1]
+
+
+class Dirichlet(HorizontalBoundary):
+    """Dirichlet conditions: ``core(time, grid, slice_x, slice_y, field_name, field_units)``
+    provides the rim values.  As in the reference the core is host code (numpy) and the four
+    rim slabs are uploaded on every call (dirichlet.py:L98-L150)."""
+
+    type = "dirichlet"
+
+    def __init__(self, nx, ny, nz, nb, core=None, grid=None, backend_options=None,
+                 storage_options=None):
+        assert nx > 1 and ny > 1 and nb <= nx / 2 and nb <= ny / 2
+        super().__init__(nx, ny, nz, nb, backend_options, storage_options)
+        self.ni, self.nj = self.nx, self.ny
+        self.core, self.grid = core, grid
+
+    def enforce_field(self, field, field_name=None, field_units=None, time=None):
+        nb, core, g = self.nb, self.core, self.grid
+        mi, mj, _ = _extent(self.nx, self.ny, self.nz, field_name)
+        for sx, sy in (
+            (slice(0, nb), slice(0, mj)),
+            (slice(mi - nb, mi), slice(0, mj)),
+            (slice(nb, mi - nb), slice(0, nb)),
+            (slice(nb, mi - nb), slice(mj - nb, mj)),
+        ):
+            vals = np.asarray(core(time, g, sx, sy, field_name, field_units))
+            field[sx, sy, : vals.shape[2]] = vals
+
+    def get_numerical_field(self, field, field_name=None):
+        return field
+
+    def get_physical_field(self, field, field_name=None):
+        return field

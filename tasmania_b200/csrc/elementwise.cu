@@ -1,0 +1,307 @@
+// elementwise.cu -- point-wise stencils: K12 (copy/math/sts), K5 (relax), K6 (Rayleigh
+// damping), K4 (velocity, momenta), K7 (density, mass fraction), periodic / outermost-layer
+// copies and halo pack/unpack.  All are pure HBM streams (no reuse): one thread per point,
+// i along threadIdx.x for coalescing.
+#include <stdarg.h>
+
+#include "stencil_math.cuh"
+
+namespace tb200 {
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace tb200
+
+using namespace tb200;
+
+extern "C" const char *tb200_last_error(void) { return g_err; }
+extern "C" int tb200_version(void) { return 100; }
+extern "C" int tb200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return -TB200_ERR_CUDA;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------- K12
+template <int OP>
+__device__ __forceinline__ double ew(double a, double b, double c, double f) {
+  if (OP == TB200_EW_COPY) return a;
+  if (OP == TB200_EW_COPYCHANGE) return -a;
+  if (OP == TB200_EW_ABS) return fabs(a);
+  if (OP == TB200_EW_ADD) return a + b;
+  if (OP == TB200_EW_ADDSUB) return a + b - c;
+  if (OP == TB200_EW_CLIP) return a > 0.0 ? a : 0.0;
+  if (OP == TB200_EW_FMA) return a + f * b;
+  if (OP == TB200_EW_MUL) return a * b;
+  if (OP == TB200_EW_SCALE) return f * a;
+  if (OP == TB200_EW_SUB) return a - b;
+  if (OP == TB200_EW_STS_RK2_0) return 0.5 * (a + b + f * c);
+  if (OP == TB200_EW_STS_RK3WS_0) return (2.0 * a + b + f * c) / 3.0;
+  if (OP == TB200_EW_IADDSUB) return a + (b - c);
+  if (OP == TB200_EW_ISCALE) return a * f;
+  return 0.0;
+}
+
+template <int OP, int NIN>
+static int run_ew(View out, View a, View b, View c, double f, const int32_t o[3],
+                  const int32_t d[3], cudaStream_t st) {
+  const int i0 = o[0], j0 = o[1], k0 = o[2];
+  return launch_box("elementwise", d, st, [=] __device__(int i, int j, int k) {
+    i += i0; j += j0; k += k0;
+    const double va = a(i, j, k);
+    const double vb = NIN >= 2 ? b(i, j, k) : 0.0;
+    const double vc = NIN >= 3 ? c(i, j, k) : 0.0;
+    out(i, j, k) = ew<OP>(va, vb, vc, f);
+  });
+}
+
+extern "C" int tb200_elementwise(int op, tb200_field *out, const tb200_field *a,
+                                 const tb200_field *b, const tb200_field *c, double f,
+                                 const int32_t origin[3], const int32_t domain[3],
+                                 void *stream) {
+  View vo = view(out), va = view(a), vb = view(b), vc = view(c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TB200_REQUIRE(box_inside(vo, origin, domain), "elementwise: out box outside storage");
+  TB200_REQUIRE(box_inside(va, origin, domain), "elementwise: a box outside storage");
+#define EW1(OP) case OP: return run_ew<OP, 1>(vo, va, vb, vc, f, origin, domain, st)
+#define EW2(OP)                                                                        \
+  case OP:                                                                             \
+    TB200_REQUIRE(box_inside(vb, origin, domain), "elementwise: b box outside storage"); \
+    return run_ew<OP, 2>(vo, va, vb, vc, f, origin, domain, st)
+#define EW3(OP)                                                                        \
+  case OP:                                                                             \
+    TB200_REQUIRE(box_inside(vb, origin, domain), "elementwise: b box outside storage"); \
+    TB200_REQUIRE(box_inside(vc, origin, domain), "elementwise: c box outside storage"); \
+    return run_ew<OP, 3>(vo, va, vb, vc, f, origin, domain, st)
+  switch (op) {
+    EW1(TB200_EW_COPY);
+    EW1(TB200_EW_COPYCHANGE);
+    EW1(TB200_EW_ABS);
+    EW2(TB200_EW_ADD);
+    EW3(TB200_EW_ADDSUB);
+    EW1(TB200_EW_CLIP);
+    EW2(TB200_EW_FMA);
+    EW2(TB200_EW_MUL);
+    EW1(TB200_EW_SCALE);
+    EW2(TB200_EW_SUB);
+    EW3(TB200_EW_STS_RK2_0);
+    EW3(TB200_EW_STS_RK3WS_0);
+    EW3(TB200_EW_IADDSUB);
+    EW1(TB200_EW_ISCALE);
+    default:
+      set_error("elementwise: unknown op %d", op);
+      return TB200_ERR_ARG;
+  }
+}
+
+// ---------------------------------------------------------------------------- K5
+extern "C" int tb200_relax(const tb200_field *in_gamma, const tb200_field *in_phi,
+                           const tb200_field *in_phi_ref, tb200_field *out_phi,
+                           const int32_t origin[3], const int32_t domain[3], void *stream) {
+  View g = view(in_gamma), r = view(in_phi_ref), o = view(out_phi);
+  View p = in_phi ? view(in_phi) : o;  // irelax: in place
+  TB200_REQUIRE(box_inside(g, origin, domain), "relax: gamma box outside storage");
+  TB200_REQUIRE(box_inside(r, origin, domain), "relax: phi_ref box outside storage");
+  TB200_REQUIRE(box_inside(o, origin, domain), "relax: out box outside storage");
+  TB200_REQUIRE(box_inside(p, origin, domain), "relax: phi box outside storage");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  return launch_box("relax", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      o(i, j, k) = relax_point(g(i, j, k), p(i, j, k), r(i, j, k));
+                    });
+}
+
+// Periodic.enforce_field: x wrap on rows [nb, my+nb), then y wrap over [0, mi)
+extern "C" int tb200_periodic_enforce(tb200_field *field, int nx, int ny, int nb, int mx,
+                                      int my, void *stream) {
+  View f = view(field);
+  TB200_REQUIRE(f.ok(), "periodic_enforce: NULL field");
+  TB200_REQUIRE(nb > 0 && mx + 2 * nb <= f.n0 && my + 2 * nb <= f.n1,
+                "periodic_enforce: field smaller than (mx+2nb, my+2nb)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sx = (mx == nx) ? 1 : 2, sy = (my == ny) ? 1 : 2;
+  const int mi = mx + 2 * nb;
+  // pass 1: both x-ghost slabs, 2*nb points along i
+  {
+    const int32_t d[3] = {2 * nb, my, f.n2};
+    int rc = launch_box("periodic_x", d, st, [=] __device__(int i, int j, int k) {
+      j += nb;
+      if (i < nb) {
+        f(i, j, k) = f(nx - 1 + i, j, k);
+      } else {
+        const int g = i - nb;
+        f(mx + nb + g, j, k) = f(nb + sx + g, j, k);
+      }
+    });
+    if (rc) return rc;
+  }
+  // pass 2: both y-ghost slabs (reads rows written by nobody in this pass)
+  {
+    const int32_t d[3] = {mi, 2 * nb, f.n2};
+    return launch_box("periodic_y", d, st, [=] __device__(int i, int j, int k) {
+      if (j < nb) {
+        f(i, j, k) = f(i, ny - 1 + j, k);
+      } else {
+        const int g = j - nb;
+        f(i, my + nb + g, k) = f(i, nb + sy + g, k);
+      }
+    });
+  }
+}
+
+extern "C" int tb200_set_outermost_layers(tb200_field *field, const tb200_field *field_ref,
+                                          int axis, int mi, int mj, void *stream) {
+  View f = view(field), r = view(field_ref);
+  TB200_REQUIRE(f.ok() && r.ok(), "set_outermost_layers: NULL field");
+  TB200_REQUIRE(mi <= f.n0 && mj <= f.n1 && mi <= r.n0 && mj <= r.n1 && r.n2 >= f.n2,
+                "set_outermost_layers: extents outside storage");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (axis == 0) {  // rows 0 and mi-1, j in [0, mj), every k  (relaxed.py:L161-L175)
+    const int32_t d[3] = {2, mj, f.n2};
+    return launch_box("outermost_x", d, st, [=] __device__(int i, int j, int k) {
+      const int ii = i == 0 ? 0 : mi - 1;
+      f(ii, j, k) = r(ii, j, k);
+    });
+  }
+  const int32_t d[3] = {mi, 2, f.n2};  // relaxed.py:L177-L191
+  return launch_box("outermost_y", d, st, [=] __device__(int i, int j, int k) {
+    const int jj = j == 0 ? 0 : mj - 1;
+    f(i, jj, k) = r(i, jj, k);
+  });
+}
+
+// ---------------------------------------------------------------------------- K6
+extern "C" int tb200_damping(const tb200_field *in_phi_now, const tb200_field *in_phi_new,
+                             const tb200_field *in_phi_ref, const tb200_field *in_rmat,
+                             tb200_field *out_phi, double dt, const int32_t origin[3],
+                             const int32_t domain[3], void *stream) {
+  View now = view(in_phi_now), nw = view(in_phi_new), ref = view(in_phi_ref);
+  View rm = view(in_rmat), o = view(out_phi);
+  TB200_REQUIRE(box_inside(now, origin, domain) && box_inside(nw, origin, domain) &&
+                    box_inside(ref, origin, domain) && box_inside(rm, origin, domain) &&
+                    box_inside(o, origin, domain),
+                "damping: box outside storage");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  return launch_box("damping", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      o(i, j, k) =
+                          damp_point(now(i, j, k), nw(i, j, k), ref(i, j, k), rm(i, j, k), dt);
+                    });
+}
+
+// ---------------------------------------------------------------------------- K4
+extern "C" int tb200_velocity(int axis, const tb200_field *in_d, const tb200_field *in_dw,
+                              tb200_field *out_w, int staggering, const int32_t origin[3],
+                              const int32_t domain[3], void *stream) {
+  View d = view(in_d), dw = view(in_dw), w = view(out_w);
+  const int hi = (staggering && axis == 0) ? 1 : 0, hj = (staggering && axis == 1) ? 1 : 0;
+  TB200_REQUIRE(axis == 0 || axis == 1, "velocity: axis must be 0 or 1");
+  TB200_REQUIRE(box_inside(d, origin, domain, hi, 0, hj, 0) &&
+                    box_inside(dw, origin, domain, hi, 0, hj, 0) &&
+                    box_inside(w, origin, domain),
+                "velocity: box outside storage");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  return launch_box("velocity", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      if (staggering) {
+                        w(i, j, k) = (dw(i - hi, j - hj, k) + dw(i, j, k)) /
+                                     (d(i - hi, j - hj, k) + d(i, j, k));
+                      } else {
+                        w(i, j, k) = dw(i, j, k) / d(i, j, k);
+                      }
+                    });
+}
+
+extern "C" int tb200_momenta(const tb200_field *in_d, const tb200_field *in_u,
+                             const tb200_field *in_v, tb200_field *out_du,
+                             tb200_field *out_dv, int staggering, const int32_t origin[3],
+                             const int32_t domain[3], void *stream) {
+  View d = view(in_d), u = view(in_u), v = view(in_v), du = view(out_du), dv = view(out_dv);
+  const int h = staggering ? 1 : 0;
+  TB200_REQUIRE(box_inside(d, origin, domain) && box_inside(u, origin, domain, 0, h) &&
+                    box_inside(v, origin, domain, 0, 0, 0, h) &&
+                    box_inside(du, origin, domain) && box_inside(dv, origin, domain),
+                "momenta: box outside storage");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  return launch_box("momenta", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      if (staggering) {
+                        du(i, j, k) = 0.5 * d(i, j, k) * (u(i, j, k) + u(i + 1, j, k));
+                        dv(i, j, k) = 0.5 * d(i, j, k) * (v(i, j, k) + v(i, j + 1, k));
+                      } else {
+                        du(i, j, k) = d(i, j, k) * u(i, j, k);
+                        dv(i, j, k) = d(i, j, k) * v(i, j, k);
+                      }
+                    });
+}
+
+// ---------------------------------------------------------------------------- K7
+extern "C" int tb200_density(const tb200_field *in_d, const tb200_field *in_q,
+                             tb200_field *out_dq, int clipping, const int32_t origin[3],
+                             const int32_t domain[3], void *stream) {
+  View d = view(in_d), q = view(in_q), dq = view(out_dq);
+  TB200_REQUIRE(box_inside(d, origin, domain) && box_inside(q, origin, domain) &&
+                    box_inside(dq, origin, domain),
+                "density: box outside storage");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  return launch_box("density", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      const double x = d(i, j, k) * q(i, j, k);
+                      dq(i, j, k) = clipping ? (x > 0.0 ? x : 0.0) : x;
+                    });
+}
+
+extern "C" int tb200_mass_fraction(const tb200_field *in_d, const tb200_field *in_dq,
+                                   tb200_field *out_q, int clipping, const int32_t origin[3],
+                                   const int32_t domain[3], void *stream) {
+  View d = view(in_d), dq = view(in_dq), q = view(out_q);
+  TB200_REQUIRE(box_inside(d, origin, domain) && box_inside(dq, origin, domain) &&
+                    box_inside(q, origin, domain),
+                "mass_fraction: box outside storage");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  return launch_box("mass_fraction", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      const double x = dq(i, j, k) / d(i, j, k);
+                      q(i, j, k) = clipping ? (x > 0.0 ? x : 0.0) : x;
+                    });
+}
+
+// ---------------------------------------------------------------------------- halo boxes
+extern "C" int tb200_pack_box(const tb200_field *field, double *buffer,
+                              const int32_t origin[3], const int32_t domain[3], void *stream) {
+  View f = view(field);
+  TB200_REQUIRE(box_inside(f, origin, domain) && buffer, "pack_box: bad arguments");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  const long long di = domain[0], dj = domain[1];
+  return launch_box("pack_box", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      buffer[i + di * (j + dj * k)] = f(i + i0, j + j0, k + k0);
+                    });
+}
+
+extern "C" int tb200_unpack_box(tb200_field *field, const double *buffer,
+                                const int32_t origin[3], const int32_t domain[3],
+                                void *stream) {
+  View f = view(field);
+  TB200_REQUIRE(box_inside(f, origin, domain) && buffer, "unpack_box: bad arguments");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  const long long di = domain[0], dj = domain[1];
+  return launch_box("unpack_box", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      f(i + i0, j + j0, k + k0) = buffer[i + di * (j + dj * k)];
+                    });
+}

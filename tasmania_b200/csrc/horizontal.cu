@@ -1,0 +1,159 @@
+// horizontal.cu -- K8 horizontal diffusion (2nd / 4th order) and K9 horizontal smoothing
+// (1st..3rd order): cross-shaped (i, j) stencils, no coupling in k.
+//
+// Roofline: HBM.  Algorithmic bytes 16 B/point (read phi once, write the tendency once;
+// gamma is rank-1 in k by construction).  The tiled kernel stages a
+// (TX + 2H) x (TY + 2H) tile of phi in shared memory per k-level so every phi value is
+// fetched from L2/HBM once per CTA; threads keep i as the fast axis (coalesced 128-byte
+// rows), gamma comes through the read-only path.  Grid = (tiles_i, tiles_j, nk) is far
+// larger than 148 SMs x resident CTAs for the sizes of interest, so tail effects vanish.
+#include "stencil_math.cuh"
+
+using namespace tb200;
+
+namespace {
+
+// ---- point formulas ------------------------------------------------------------------
+// second_order.py:L101-L104
+__device__ __forceinline__ double lap2(double g, double c, double im1, double ip1, double jm1,
+                                       double jp1, double dx, double dy) {
+  return g * ((im1 - 2.0 * c + ip1) / (dx * dx) + (jm1 - 2.0 * c + jp1) / (dy * dy));
+}
+// fourth_order.py:L104-L122
+__device__ __forceinline__ double lap4(double g, double c, double im2, double im1, double ip1,
+                                       double ip2, double jm2, double jm1, double jp1,
+                                       double jp2, double dx, double dy) {
+  return g * ((-im2 + 16.0 * im1 - 30.0 * c + 16.0 * ip1 - ip2) / (12.0 * dx * dx) +
+              (-jm2 + 16.0 * jm1 - 30.0 * c + 16.0 * jp1 - jp2) / (12.0 * dy * dy));
+}
+
+constexpr int TX = 64, TY = 8;
+
+// Shared-memory tiled cross stencil.  OP: 2/4 = diffusion order, 11/12/13 = smoothing 1..3.
+template <int OP>
+struct Halo {
+  static constexpr int value = OP == 2 ? 1 : OP == 4 ? 2 : OP - 10;
+};
+
+template <int OP>
+__global__ void __launch_bounds__(TX *TY)
+    cross_kernel(View phi, View gam, View out, double dx, double dy, int overwrite, int rim,
+                 int i0, int j0, int k0, int di, int dj, int dk, int ri, int rj) {
+  constexpr int H = Halo<OP>::value;
+  constexpr int SX = TX + 2 * H, SY = TY + 2 * H;
+  __shared__ double tile[SY][SX + 1];
+
+  // with rim copy the launch covers the whole (ri, rj) box, otherwise [i0, i0+di) x ...
+  const int bi = rim ? 0 : i0, bj = rim ? 0 : j0;
+  const int ti = bi + blockIdx.x * TX, tj = bj + blockIdx.y * TY;  // tile origin
+  const int lim_i = rim ? ri : i0 + di, lim_j = rim ? rj : j0 + dj;
+  const int tid = threadIdx.y * TX + threadIdx.x;
+
+  for (int k = k0 + blockIdx.z; k < k0 + dk; k += gridDim.z) {
+    // cooperative, row-coalesced load of the tile + halo (clamped to the storage)
+    for (int t = tid; t < SX * SY; t += TX * TY) {
+      const int ly = t / SX, lx = t - ly * SX;
+      const int gi = ti + lx - H, gj = tj + ly - H;
+      double v = 0.0;
+      if (gi >= 0 && gi < phi.n0 && gj >= 0 && gj < phi.n1) v = phi.ld(gi, gj, k);
+      tile[ly][lx] = v;
+    }
+    __syncthreads();
+
+    const int i = ti + threadIdx.x, j = tj + threadIdx.y;
+    if (i < lim_i && j < lim_j) {
+      const int x = threadIdx.x + H, y = threadIdx.y + H;
+      const double c = tile[y][x];
+      const bool inside = i >= i0 && i < i0 + di && j >= j0 && j < j0 + dj;
+      if (inside) {
+        const double g = gam.ld(i, j, k);
+        double r;
+        if (OP == 2) {
+          r = lap2(g, c, tile[y][x - 1], tile[y][x + 1], tile[y - 1][x], tile[y + 1][x], dx, dy);
+        } else if (OP == 4) {
+          r = lap4(g, c, tile[y][x - 2], tile[y][x - 1], tile[y][x + 1], tile[y][x + 2],
+                   tile[y - 2][x], tile[y - 1][x], tile[y + 1][x], tile[y + 2][x], dx, dy);
+        } else if (OP == 11) {  // first_order.py:L124-L126
+          r = (1.0 - g) * c +
+              0.25 * g * (tile[y][x - 1] + tile[y][x + 1] + tile[y - 1][x] + tile[y + 1][x]);
+        } else if (OP == 12) {  // second_order.py:L126-L139
+          r = (1.0 - 0.75 * g) * c +
+              0.0625 * g *
+                  (-tile[y][x - 2] + 4.0 * tile[y][x - 1] - tile[y][x + 2] +
+                   4.0 * tile[y][x + 1] - tile[y - 2][x] + 4.0 * tile[y - 1][x] -
+                   tile[y + 2][x] + 4.0 * tile[y + 1][x]);
+        } else {  // third_order.py:L133-L150
+          r = (1.0 - 0.625 * g) * c +
+              0.015625 * g *
+                  (tile[y][x - 3] - 6.0 * tile[y][x - 2] + 15.0 * tile[y][x - 1] +
+                   tile[y][x + 3] - 6.0 * tile[y][x + 2] + 15.0 * tile[y][x + 1] +
+                   tile[y - 3][x] - 6.0 * tile[y - 2][x] + 15.0 * tile[y - 1][x] +
+                   tile[y + 3][x] - 6.0 * tile[y + 2][x] + 15.0 * tile[y + 1][x]);
+        }
+        if ((OP == 2 || OP == 4) && !overwrite) r = out(i, j, k) + r;  // generics.py:L38-L40
+        out(i, j, k) = r;
+      } else if (rim) {
+        out(i, j, k) = c;  // the four `copy` launches of HorizontalSmoothing.__call__
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int OP>
+int launch_cross(const char *what, View phi, View gam, View out, double dx, double dy,
+                 int overwrite, int rim, const int32_t o[3], const int32_t d[3],
+                 cudaStream_t st) {
+  // rim box = the smoother's shape: nb + (n - 2 nb) + nb points a side
+  const int ri = 2 * o[0] + d[0], rj = 2 * o[1] + d[1];
+  const int ei = rim ? ri : d[0], ej = rim ? rj : d[1];
+  if (ei <= 0 || ej <= 0 || d[2] <= 0) return TB200_OK;
+  dim3 block(TX, TY, 1);
+  dim3 grid((ei + TX - 1) / TX, (ej + TY - 1) / TY, d[2] > 65535 ? 65535 : d[2]);
+  cross_kernel<OP><<<grid, block, 0, st>>>(phi, gam, out, dx, dy, overwrite, rim, o[0], o[1],
+                                           o[2], d[0], d[1], d[2], ri, rj);
+  return check_launch(what);
+}
+
+}  // namespace
+
+extern "C" int tb200_diffusion(int order, const tb200_field *in_phi,
+                               const tb200_field *in_gamma, tb200_field *out_phi, double dx,
+                               double dy, int ow_out_phi, const int32_t origin[3],
+                               const int32_t domain[3], void *stream) {
+  View phi = view(in_phi), gam = view(in_gamma), out = view(out_phi);
+  TB200_REQUIRE(order == 2 || order == 4, "diffusion: order must be 2 or 4 (got %d)", order);
+  const int h = order / 2;
+  TB200_REQUIRE(box_inside(phi, origin, domain, h, h, h, h),
+                "diffusion: in_phi box + halo %d outside storage", h);
+  TB200_REQUIRE(box_inside(gam, origin, domain) && box_inside(out, origin, domain),
+                "diffusion: gamma/out box outside storage");
+  TB200_REQUIRE(phi.p != out.p, "diffusion: in_phi and out_phi must not alias");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (order == 2)
+    return launch_cross<2>("diffusion2", phi, gam, out, dx, dy, ow_out_phi, 0, origin, domain, st);
+  return launch_cross<4>("diffusion4", phi, gam, out, dx, dy, ow_out_phi, 0, origin, domain, st);
+}
+
+extern "C" int tb200_smoothing(int order, const tb200_field *in_phi,
+                               const tb200_field *in_gamma, tb200_field *out_phi,
+                               int rim_copy, const int32_t origin[3], const int32_t domain[3],
+                               void *stream) {
+  View phi = view(in_phi), gam = view(in_gamma), out = view(out_phi);
+  TB200_REQUIRE(order >= 1 && order <= 3, "smoothing: order must be 1..3 (got %d)", order);
+  const int h = order;
+  TB200_REQUIRE(box_inside(phi, origin, domain, h, h, h, h),
+                "smoothing: in_phi box + halo %d outside storage", h);
+  TB200_REQUIRE(box_inside(gam, origin, domain) && box_inside(out, origin, domain),
+                "smoothing: gamma/out box outside storage");
+  TB200_REQUIRE(phi.p != out.p, "smoothing: in_phi and out_phi must not alias");
+  TB200_REQUIRE(!rim_copy || (2 * origin[0] + domain[0] <= phi.n0 && 2 * origin[0] + domain[0] <= out.n0 &&
+                              2 * origin[1] + domain[1] <= phi.n1 && 2 * origin[1] + domain[1] <= out.n1),
+                "smoothing: rim box outside storage");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (order == 1)
+    return launch_cross<11>("smoothing1", phi, gam, out, 0, 0, 1, rim_copy, origin, domain, st);
+  if (order == 2)
+    return launch_cross<12>("smoothing2", phi, gam, out, 0, 0, 1, rim_copy, origin, domain, st);
+  return launch_cross<13>("smoothing3", phi, gam, out, 0, 0, 1, rim_copy, origin, domain, st);
+}

@@ -1,0 +1,313 @@
+// isentropic.cu -- stand-alone (per-stencil) kernels of the isentropic core:
+//   K1 step_forward_euler, K2 step_forward_euler_momentum  (prognostics/utils.py:L43-L204)
+//   K3 montgomery / diagnostic_variables / height / density_and_temperature
+//      (isentropic/dynamics/diagnostics.py:L319-L570)
+// These are the drop-in twins of the reference's registry entries; the benchmark path uses
+// the fused kernels of isentropic_fused.cu which share the point formulas.
+//
+// Roofline: HBM.  K1 dry: 40 B/pt, K2: 96 B/pt, K3 montgomery: 16 B/pt.
+// K3 runs one thread per (i, j) column with i along the warp, so every level is a
+// coalesced row access; the scans are sequential in k exactly as in the reference (no tree
+// reduction) to keep the summation order.
+#include "stencil_math.cuh"
+
+using namespace tb200;
+
+namespace {
+
+struct Tracers {
+  View now[3], in[3], out[3], tnd[3];
+  int n;
+};
+
+template <int SCHEME>
+int run_k1(View s_now, View s_int, View s_new, View u, View v, View s_tnd, Tracers tr,
+           double dt, double dx, double dy, const int32_t o[3], const int32_t d[3],
+           cudaStream_t st) {
+  const int i0 = o[0], j0 = o[1], k0 = o[2];
+  return launch_box("step_forward_euler", d, st, [=] __device__(int i, int j, int k) {
+    i += i0; j += j0; k += k0;
+    // utils.py:L95-L99
+    const double div = flux_divergence<SCHEME>(u, v, s_int, i, j, k, dx, dy);
+    const double tnd = s_tnd.ok() ? s_tnd(i, j, k) : 0.0;
+    s_new(i, j, k) = s_now(i, j, k) - dt * (div - tnd);
+    // utils.py:L101-L134
+    for (int t = 0; t < tr.n; ++t) {
+      const double dq = flux_divergence<SCHEME>(u, v, tr.in[t], i, j, k, dx, dy);
+      const double src = tr.tnd[t].ok() ? s_int(i, j, k) * tr.tnd[t](i, j, k) : 0.0;
+      tr.out[t](i, j, k) = tr.now[t](i, j, k) - dt * (dq - src);
+    }
+  });
+}
+
+template <int SCHEME>
+int run_k2(View s_now, View s_new, View u, View v, View su_now, View su_int, View su_new,
+           View sv_now, View sv_int, View sv_new, View mtg_now, View mtg_new, View su_tnd,
+           View sv_tnd, double dt, double dx, double dy, double eps, const int32_t o[3],
+           const int32_t d[3], cudaStream_t st) {
+  const int i0 = o[0], j0 = o[1], k0 = o[2];
+  return launch_box("step_forward_euler_momentum", d, st, [=] __device__(int i, int j, int k) {
+    i += i0; j += j0; k += k0;
+    const double sn = s_now(i, j, k), sw = s_new(i, j, k);
+    // utils.py:L191-L197
+    {
+      const double div = flux_divergence<SCHEME>(u, v, su_int, i, j, k, dx, dy);
+      const double pg_now =
+          (1.0 - eps) * sn * (mtg_now(i + 1, j, k) - mtg_now(i - 1, j, k)) / (2.0 * dx);
+      const double pg_new = eps * sw * (mtg_new(i + 1, j, k) - mtg_new(i - 1, j, k)) / (2.0 * dx);
+      const double tnd = su_tnd.ok() ? su_tnd(i, j, k) : 0.0;
+      su_new(i, j, k) = su_now(i, j, k) - dt * (div + pg_now + pg_new - tnd);
+    }
+    // utils.py:L198-L204
+    {
+      const double div = flux_divergence<SCHEME>(u, v, sv_int, i, j, k, dx, dy);
+      const double pg_now =
+          (1.0 - eps) * sn * (mtg_now(i, j + 1, k) - mtg_now(i, j - 1, k)) / (2.0 * dy);
+      const double pg_new = eps * sw * (mtg_new(i, j + 1, k) - mtg_new(i, j - 1, k)) / (2.0 * dy);
+      const double tnd = sv_tnd.ok() ? sv_tnd(i, j, k) : 0.0;
+      sv_new(i, j, k) = sv_now(i, j, k) - dt * (div + pg_now + pg_new - tnd);
+    }
+  });
+}
+
+int flux_extent(int scheme) {
+  switch (scheme) {
+    case TB200_FLUX_UPWIND:
+    case TB200_FLUX_CENTERED: return 1;
+    case TB200_FLUX_THIRD_ORDER_UPWIND: return 2;
+    case TB200_FLUX_FIFTH_ORDER_UPWIND: return 3;
+    default: return -1;
+  }
+}
+
+}  // namespace
+
+#define DISPATCH_SCHEME(scheme, CALL)                                              \
+  switch (scheme) {                                                                \
+    case TB200_FLUX_UPWIND: return CALL(TB200_FLUX_UPWIND);                        \
+    case TB200_FLUX_CENTERED: return CALL(TB200_FLUX_CENTERED);                    \
+    case TB200_FLUX_THIRD_ORDER_UPWIND: return CALL(TB200_FLUX_THIRD_ORDER_UPWIND); \
+    default: return CALL(TB200_FLUX_FIFTH_ORDER_UPWIND);                           \
+  }
+
+extern "C" int tb200_step_forward_euler(
+    int flux_scheme, const tb200_field *s_now, const tb200_field *s_int, tb200_field *s_new,
+    const tb200_field *u_int, const tb200_field *v_int, const tb200_field *s_tnd,
+    const tb200_field *const *sq_now, const tb200_field *const *sq_int,
+    tb200_field *const *sq_new, const tb200_field *const *q_tnd, double dt, double dx, double dy,
+    const int32_t origin[3], const int32_t domain[3], void *stream) {
+  const int e = flux_extent(flux_scheme);
+  TB200_REQUIRE(e > 0, "step_forward_euler: unknown flux scheme %d", flux_scheme);
+  View vs_now = view(s_now), vs_int = view(s_int), vs_new = view(s_new);
+  View vu = view(u_int), vv = view(v_int), vt = view(s_tnd);
+  TB200_REQUIRE(box_inside(vs_now, origin, domain) && box_inside(vs_new, origin, domain),
+                "step_forward_euler: s_now/s_new box outside storage");
+  TB200_REQUIRE(box_inside(vs_int, origin, domain, e, e, e, e),
+                "step_forward_euler: s_int box + extent %d outside storage", e);
+  TB200_REQUIRE(box_inside(vu, origin, domain, 0, 1) && box_inside(vv, origin, domain, 0, 0, 0, 1),
+                "step_forward_euler: u_int/v_int box outside storage");
+  TB200_REQUIRE(!vt.ok() || box_inside(vt, origin, domain), "step_forward_euler: s_tnd box");
+  TB200_REQUIRE(vs_int.p != vs_new.p, "step_forward_euler: s_int and s_new must not alias");
+  Tracers tr{};
+  if (sq_now != nullptr) {
+    TB200_REQUIRE(sq_int != nullptr && sq_new != nullptr, "step_forward_euler: tracer arrays");
+    tr.n = 3;
+    for (int t = 0; t < 3; ++t) {
+      tr.now[t] = view(sq_now[t]);
+      tr.in[t] = view(sq_int[t]);
+      tr.out[t] = view(sq_new[t]);
+      tr.tnd[t] = q_tnd ? view(q_tnd[t]) : View{};
+      TB200_REQUIRE(box_inside(tr.now[t], origin, domain) && box_inside(tr.out[t], origin, domain) &&
+                        box_inside(tr.in[t], origin, domain, e, e, e, e),
+                    "step_forward_euler: tracer %d box outside storage", t);
+      TB200_REQUIRE(!tr.tnd[t].ok() || box_inside(tr.tnd[t], origin, domain),
+                    "step_forward_euler: tracer tendency %d box outside storage", t);
+      TB200_REQUIRE(tr.in[t].p != tr.out[t].p, "step_forward_euler: tracer in/out alias");
+    }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define K1_CALL(S) run_k1<S>(vs_now, vs_int, vs_new, vu, vv, vt, tr, dt, dx, dy, origin, domain, st)
+  DISPATCH_SCHEME(flux_scheme, K1_CALL)
+}
+
+extern "C" int tb200_step_forward_euler_momentum(
+    int flux_scheme, const tb200_field *s_now, const tb200_field *s_new,
+    const tb200_field *u_int, const tb200_field *v_int, const tb200_field *su_now,
+    const tb200_field *su_int, tb200_field *su_new, const tb200_field *sv_now,
+    const tb200_field *sv_int, tb200_field *sv_new, const tb200_field *mtg_now,
+    const tb200_field *mtg_new, const tb200_field *su_tnd, const tb200_field *sv_tnd, double dt,
+    double dx, double dy, double eps, const int32_t origin[3], const int32_t domain[3],
+    void *stream) {
+  const int e = flux_extent(flux_scheme);
+  TB200_REQUIRE(e > 0, "step_forward_euler_momentum: unknown flux scheme %d", flux_scheme);
+  View a = view(s_now), b = view(s_new), vu = view(u_int), vv = view(v_int);
+  View un = view(su_now), ui = view(su_int), uo = view(su_new);
+  View vn = view(sv_now), vi = view(sv_int), vo = view(sv_new);
+  View mn = view(mtg_now), mw = view(mtg_new), tu = view(su_tnd), tv = view(sv_tnd);
+  TB200_REQUIRE(box_inside(a, origin, domain) && box_inside(b, origin, domain) &&
+                    box_inside(un, origin, domain) && box_inside(uo, origin, domain) &&
+                    box_inside(vn, origin, domain) && box_inside(vo, origin, domain),
+                "step_forward_euler_momentum: box outside storage");
+  TB200_REQUIRE(box_inside(ui, origin, domain, e, e, e, e) && box_inside(vi, origin, domain, e, e, e, e),
+                "step_forward_euler_momentum: su_int/sv_int box + extent outside storage");
+  TB200_REQUIRE(box_inside(mn, origin, domain, 1, 1, 1, 1) && box_inside(mw, origin, domain, 1, 1, 1, 1),
+                "step_forward_euler_momentum: mtg box + 1 outside storage");
+  TB200_REQUIRE(box_inside(vu, origin, domain, 0, 1) && box_inside(vv, origin, domain, 0, 0, 0, 1),
+                "step_forward_euler_momentum: u_int/v_int box outside storage");
+  TB200_REQUIRE((!tu.ok() || box_inside(tu, origin, domain)) && (!tv.ok() || box_inside(tv, origin, domain)),
+                "step_forward_euler_momentum: tendency box outside storage");
+  TB200_REQUIRE(ui.p != uo.p && vi.p != vo.p, "step_forward_euler_momentum: int/new alias");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define K2_CALL(S) \
+  run_k2<S>(a, b, vu, vv, un, ui, uo, vn, vi, vo, mn, mw, tu, tv, dt, dx, dy, eps, origin, domain, st)
+  DISPATCH_SCHEME(flux_scheme, K2_CALL)
+}
+
+// ---------------------------------------------------------------------------- K3
+// One thread per column.  WHAT: 0 montgomery, 1 diagnostic_variables (p, exn, mtg, h).
+// The Exner values of the column are parked in the output storages themselves between the
+// downward pressure scan and the upward scans, so no scratch is needed: for montgomery,
+// mtg[k-1] holds exn[k] until the upward scan overwrites it -- exactly the order in which
+// the values are consumed.
+template <int WHAT>
+static int run_k3(View theta, View hs, View s, View p, View exn, View mtg, View h, double dz,
+                  double pt, double theta_s, double pref, double rd, double g, double cp,
+                  const int32_t o[3], const int32_t d[3], cudaStream_t st) {
+  const int i0 = o[0], j0 = o[1], k0 = o[2], k1 = o[2] + d[2];
+  const double kappa = rd / cp;
+  return launch_columns("isentropic_diagnostics", d[0], d[1], st, [=] __device__(int i, int j) {
+    i += i0; j += j0;
+    // downward pressure scan, diagnostics.py:L339-L345 / L425-L431
+    double pk = pt;
+    for (int k = k0; k < k1; ++k) {
+      if (k > k0) pk = pk + g * dz * s(i, j, k - 1);
+      if (WHAT == 1) {
+        p(i, j, k) = pk;
+        exn(i, j, k) = cp * pow(pk / pref, kappa);
+      } else if (k > k0) {
+        mtg(i, j, k - 1) = cp * pow(pk / pref, kappa);  // park exn[k] in mtg[k-1]
+      }
+    }
+    // upward Montgomery scan, diagnostics.py:L347-L351 / L433-L438
+    const double th_s = WHAT == 1 ? theta(i, j, k1 - 1) : theta_s;
+    const double ex_s = WHAT == 1 ? exn(i, j, k1 - 1) : mtg(i, j, k1 - 2);
+    const double mtg_s = th_s * ex_s + g * hs(i, j, k1 - 1);
+    double m = mtg_s + 0.5 * dz * ex_s;
+    mtg(i, j, k1 - 2) = m;
+    for (int k = k1 - 3; k >= k0; --k) {
+      const double ex = WHAT == 1 ? exn(i, j, k + 1) : mtg(i, j, k);
+      m = m + dz * ex;
+      mtg(i, j, k) = m;
+    }
+    if (WHAT == 1) {
+      // upward height scan, diagnostics.py:L353-L360
+      double hk = hs(i, j, k1 - 1);
+      h(i, j, k1 - 1) = hk;
+      for (int k = k1 - 2; k >= k0; --k) {
+        const double pa = p(i, j, k), pb = p(i, j, k + 1);
+        hk = hk - rd * (theta(i, j, k) * exn(i, j, k) + theta(i, j, k + 1) * exn(i, j, k + 1)) *
+                      (pa - pb) / (cp * g * (pa + pb));
+        h(i, j, k) = hk;
+      }
+    }
+  });
+}
+
+extern "C" int tb200_montgomery(const tb200_field *in_hs, const tb200_field *in_s,
+                                tb200_field *inout_mtg, double dz, double pt, double theta_s,
+                                const double constants[4], const int32_t origin[3],
+                                const int32_t domain[3], void *stream) {
+  View hs = view(in_hs), s = view(in_s), mtg = view(inout_mtg);
+  TB200_REQUIRE(domain[2] >= 2, "montgomery: needs at least two interface levels");
+  TB200_REQUIRE(box_inside(hs, origin, domain) && box_inside(s, origin, domain) &&
+                    box_inside(mtg, origin, domain),
+                "montgomery: box outside storage");
+  TB200_REQUIRE(s.p != mtg.p, "montgomery: in_s and inout_mtg must not alias");
+  return run_k3<0>(View{}, hs, s, View{}, View{}, mtg, View{}, dz, pt, theta_s, constants[0],
+                   constants[1], constants[2], constants[3], origin, domain,
+                   static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tb200_diagnostic_variables(const tb200_field *in_theta, const tb200_field *in_hs,
+                                          const tb200_field *in_s, tb200_field *inout_p,
+                                          tb200_field *out_exn, tb200_field *inout_mtg,
+                                          tb200_field *inout_h, double dz, double pt,
+                                          const double constants[4], const int32_t origin[3],
+                                          const int32_t domain[3], void *stream) {
+  View th = view(in_theta), hs = view(in_hs), s = view(in_s);
+  View p = view(inout_p), exn = view(out_exn), mtg = view(inout_mtg), h = view(inout_h);
+  TB200_REQUIRE(domain[2] >= 2, "diagnostic_variables: needs at least two interface levels");
+  TB200_REQUIRE(box_inside(th, origin, domain) && box_inside(hs, origin, domain) &&
+                    box_inside(s, origin, domain) && box_inside(p, origin, domain) &&
+                    box_inside(exn, origin, domain) && box_inside(mtg, origin, domain) &&
+                    box_inside(h, origin, domain),
+                "diagnostic_variables: box outside storage");
+  return run_k3<1>(th, hs, s, p, exn, mtg, h, dz, pt, 0.0, constants[0], constants[1],
+                   constants[2], constants[3], origin, domain, static_cast<cudaStream_t>(stream));
+}
+
+// height: p and exn of the column are needed together on the way up.  The kernel walks down
+// once storing p[k] into inout_h[k] (h is pure output), then walks up keeping
+// (p[k+1], exn[k+1]) in registers and recomputing exn[k] = cp (p[k]/pref)^kappa from the
+// parked p[k] -- the same expression on the same operand, hence the same bits.
+extern "C" int tb200_height(const tb200_field *in_theta, const tb200_field *in_hs,
+                            const tb200_field *in_s, tb200_field *inout_h, double dz, double pt,
+                            const double constants[4], const int32_t origin[3],
+                            const int32_t domain[3], void *stream) {
+  View th = view(in_theta), hs = view(in_hs), s = view(in_s), h = view(inout_h);
+  TB200_REQUIRE(domain[2] >= 2, "height: needs at least two interface levels");
+  TB200_REQUIRE(box_inside(th, origin, domain) && box_inside(hs, origin, domain) &&
+                    box_inside(s, origin, domain) && box_inside(h, origin, domain),
+                "height: box outside storage");
+  TB200_REQUIRE(hs.p != h.p && s.p != h.p, "height: inputs must not alias inout_h");
+  const double pref = constants[0], rd = constants[1], g = constants[2], cp = constants[3];
+  const double kappa = rd / cp;
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2], k1 = origin[2] + domain[2];
+  return launch_columns("height", domain[0], domain[1], static_cast<cudaStream_t>(stream),
+                        [=] __device__(int i, int j) {
+                          i += i0; j += j0;
+                          double pk = pt;
+                          for (int k = k0; k < k1; ++k) {
+                            if (k > k0) pk = pk + g * dz * s(i, j, k - 1);
+                            if (k < k1 - 1) h(i, j, k) = pk;  // park p[k]
+                          }
+                          double pb = pk;  // p[k1-1]
+                          double eb = cp * pow(pb / pref, kappa);
+                          double hk = hs(i, j, k1 - 1);
+                          h(i, j, k1 - 1) = hk;
+                          for (int k = k1 - 2; k >= k0; --k) {
+                            const double pa = h(i, j, k);
+                            const double ea = cp * pow(pa / pref, kappa);
+                            hk = hk - rd * (th(i, j, k) * ea + th(i, j, k + 1) * eb) * (pa - pb) /
+                                          (cp * g * (pa + pb));
+                            h(i, j, k) = hk;
+                            pb = pa;
+                            eb = ea;
+                          }
+                        });
+}
+
+extern "C" int tb200_density_and_temperature(const tb200_field *in_theta,
+                                             const tb200_field *in_s, const tb200_field *in_exn,
+                                             const tb200_field *in_h, tb200_field *out_rho,
+                                             tb200_field *out_t, double cp,
+                                             const int32_t origin[3], const int32_t domain[3],
+                                             void *stream) {
+  View th = view(in_theta), s = view(in_s), exn = view(in_exn), h = view(in_h);
+  View rho = view(out_rho), t = view(out_t);
+  TB200_REQUIRE(box_inside(th, origin, domain, 0, 0, 0, 0, 0, 1) &&
+                    box_inside(exn, origin, domain, 0, 0, 0, 0, 0, 1) &&
+                    box_inside(h, origin, domain, 0, 0, 0, 0, 0, 1) &&
+                    box_inside(s, origin, domain) && box_inside(rho, origin, domain) &&
+                    box_inside(t, origin, domain),
+                "density_and_temperature: box outside storage");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  // diagnostics.py:L559-L570
+  return launch_box("density_and_temperature", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      const double ta = th(i, j, k), tb = th(i, j, k + 1);
+                      rho(i, j, k) = s(i, j, k) * (ta - tb) / (h(i, j, k) - h(i, j, k + 1));
+                      t(i, j, k) = 0.5 / cp * (ta * exn(i, j, k) + tb * exn(i, j, k + 1));
+                    });
+}

@@ -1,0 +1,170 @@
+// stencil_math.cuh -- point formulas shared by the stand-alone and the fused kernels.
+// Operation order follows the reference's numpy definitions exactly (file:line cited at
+// each formula); together with -fmad=false this makes the kernels bit-identical to numpy
+// apart from libm calls.
+#pragma once
+#include "common.cuh"
+
+namespace tb200 {
+
+// ------------------------------------------------------------------ horizontal fluxes
+// Face flux F(f) = w[f] * Phi(phi[f-e .. f+e-1]); `ph` points at phi[f], `st` is the stride
+// along the differenced axis.  SURVEY.md Appendix A "Flux-array offset".
+template <int SCHEME>
+struct Flux;
+
+template <>
+struct Flux<TB200_FLUX_UPWIND> {  // horizontal_fluxes/upwind.py:L32-L39
+  static constexpr int extent = 1;
+  __device__ __forceinline__ static double face(double w, const double *ph, long long st) {
+    return w * (w > 0.0 ? __ldg(ph - st) : __ldg(ph));
+  }
+  // from values phi[f-1], phi[f]
+  __device__ __forceinline__ static double face_v(double w, const double *v) {
+    return w * (w > 0.0 ? v[0] : v[1]);
+  }
+};
+
+template <>
+struct Flux<TB200_FLUX_CENTERED> {  // horizontal_fluxes/centered.py:L173-L202
+  static constexpr int extent = 1;
+  __device__ __forceinline__ static double face(double w, const double *ph, long long st) {
+    return w * 0.5 * (__ldg(ph - st) + __ldg(ph));
+  }
+  __device__ __forceinline__ static double face_v(double w, const double *v) {
+    return w * 0.5 * (v[0] + v[1]);
+  }
+};
+
+template <>
+struct Flux<TB200_FLUX_THIRD_ORDER_UPWIND> {  // horizontal_fluxes/third_order_upwind.py:L32-L55
+  static constexpr int extent = 2;
+  __device__ __forceinline__ static double eval(double w, double m2, double m1, double p0,
+                                                double p1) {
+    const double flux4 = w / 12.0 * (7.0 * (p0 + m1) - (p1 + m2));
+    return flux4 - fabs(w) / 12.0 * (3.0 * (p0 - m1) - (p1 - m2));
+  }
+  __device__ __forceinline__ static double face(double w, const double *ph, long long st) {
+    return eval(w, __ldg(ph - 2 * st), __ldg(ph - st), __ldg(ph), __ldg(ph + st));
+  }
+  // v[0..3] = phi[f-2 .. f+1]
+  __device__ __forceinline__ static double face_v(double w, const double *v) {
+    return eval(w, v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <>
+struct Flux<TB200_FLUX_FIFTH_ORDER_UPWIND> {  // horizontal_fluxes/fifth_order_upwind.py:L32-L75
+  static constexpr int extent = 3;
+  __device__ __forceinline__ static double eval(double w, double m3, double m2, double m1,
+                                                double p0, double p1, double p2) {
+    const double flux6 = w / 60.0 * (37.0 * (p0 + m1) - 8.0 * (p1 + m2) + (p2 + m3));
+    return flux6 - fabs(w) / 60.0 * (10.0 * (p0 - m1) - 5.0 * (p1 - m2) + (p2 - m3));
+  }
+  __device__ __forceinline__ static double face(double w, const double *ph, long long st) {
+    return eval(w, __ldg(ph - 3 * st), __ldg(ph - 2 * st), __ldg(ph - st), __ldg(ph),
+                __ldg(ph + st), __ldg(ph + 2 * st));
+  }
+  // v[0..5] = phi[f-3 .. f+2]
+  __device__ __forceinline__ static double face_v(double w, const double *v) {
+    return eval(w, v[0], v[1], v[2], v[3], v[4], v[5]);
+  }
+};
+
+// (Fx[i+1/2] - Fx[i-1/2]) / dx + (Fy[j+1/2] - Fy[j-1/2]) / dy at mass point (i, j, k),
+// prognostics/utils.py:L96-L99.  u, v are the staggered advecting velocities.
+template <int SCHEME>
+__device__ __forceinline__ double flux_divergence(const View &u, const View &v,
+                                                  const View &phi, int i, int j, int k,
+                                                  double dx, double dy) {
+  using F = Flux<SCHEME>;
+  const double *pc = phi.p + (i * phi.s0 + j * phi.s1 + k * phi.s2);
+  const double fxm = F::face(u.ld(i, j, k), pc, phi.s0);
+  const double fxp = F::face(u.ld(i + 1, j, k), pc + phi.s0, phi.s0);
+  const double fym = F::face(v.ld(i, j, k), pc, phi.s1);
+  const double fyp = F::face(v.ld(i, j + 1, k), pc + phi.s1, phi.s1);
+  return (fxp - fxm) / dx + (fyp - fym) / dy;
+}
+
+// ------------------------------------------------------------------ relaxation / damping
+// algorithms.py:L32-L43
+__device__ __forceinline__ double relax_point(double g, double phi, double ref) {
+  return g == 0.0 ? phi : (g == 1.0 ? ref : phi - g * (phi - ref));
+}
+
+// rayleigh.py:L104-L109: new - (dt * R) * (now - ref)
+__device__ __forceinline__ double damp_point(double now, double nw, double ref, double r,
+                                             double dt) {
+  return nw - dt * r * (now - ref);
+}
+
+// ------------------------------------------------------------------ Burgers advection
+// burgers/dynamics/subclasses/advection/{first..sixth}_order.py.  `a` is the advecting
+// velocity at the point, `q` points at the advected field at the point, `st` the stride
+// along the differenced axis, `dd` the grid spacing.
+template <int ORDER>
+struct Advection;
+
+template <>
+struct Advection<1> {  // first_order.py:L39-L58
+  static constexpr int extent = 1;
+  __device__ __forceinline__ static double term(double a, const double *q, long long st,
+                                                double dd) {
+    const double qm = __ldg(q - st), q0 = __ldg(q), qp = __ldg(q + st);
+    return a / (2.0 * dd) * (qp - qm) - fabs(a) / (2.0 * dd) * (qp - 2.0 * q0 + qm);
+  }
+};
+template <>
+struct Advection<2> {  // second_order.py:L37-L45
+  static constexpr int extent = 1;
+  __device__ __forceinline__ static double term(double a, const double *q, long long st,
+                                                double dd) {
+    return a / (2.0 * dd) * (__ldg(q + st) - __ldg(q - st));
+  }
+};
+template <>
+struct Advection<3> {  // third_order.py:L39-L65
+  static constexpr int extent = 2;
+  __device__ __forceinline__ static double term(double a, const double *q, long long st,
+                                                double dd) {
+    const double m2 = __ldg(q - 2 * st), m1 = __ldg(q - st), q0 = __ldg(q);
+    const double p1 = __ldg(q + st), p2 = __ldg(q + 2 * st);
+    return a / (12.0 * dd) * (8.0 * (p1 - m1) - (p2 - m2)) +
+           fabs(a) / (12.0 * dd) * (p2 + m2 - 4.0 * (p1 + m1) + 6.0 * q0);
+  }
+};
+template <>
+struct Advection<4> {  // fourth_order.py:L37-L61
+  static constexpr int extent = 2;
+  __device__ __forceinline__ static double term(double a, const double *q, long long st,
+                                                double dd) {
+    const double m2 = __ldg(q - 2 * st), m1 = __ldg(q - st);
+    const double p1 = __ldg(q + st), p2 = __ldg(q + 2 * st);
+    return a / (12.0 * dd) * (8.0 * (p1 - m1) - (p2 - m2));
+  }
+};
+template <>
+struct Advection<5> {  // fifth_order.py:L39-L86
+  static constexpr int extent = 3;
+  __device__ __forceinline__ static double term(double a, const double *q, long long st,
+                                                double dd) {
+    const double m3 = __ldg(q - 3 * st), m2 = __ldg(q - 2 * st), m1 = __ldg(q - st);
+    const double q0 = __ldg(q);
+    const double p1 = __ldg(q + st), p2 = __ldg(q + 2 * st), p3 = __ldg(q + 3 * st);
+    return a / (60.0 * dd) * (45.0 * (p1 - m1) - 9.0 * (p2 - m2) + (p3 - m3)) -
+           fabs(a) / (60.0 * dd) *
+               ((p3 + m3) - 6.0 * (p2 + m2) + 15.0 * (p1 + m1) - 20.0 * q0);
+  }
+};
+template <>
+struct Advection<6> {  // sixth_order.py:L37-L77
+  static constexpr int extent = 3;
+  __device__ __forceinline__ static double term(double a, const double *q, long long st,
+                                                double dd) {
+    const double m3 = __ldg(q - 3 * st), m2 = __ldg(q - 2 * st), m1 = __ldg(q - st);
+    const double p1 = __ldg(q + st), p2 = __ldg(q + 2 * st), p3 = __ldg(q + 3 * st);
+    return a / (60.0 * dd) * (45.0 * (p1 - m1) - 9.0 * (p2 - m2) + (p3 - m3));
+  }
+};
+
+}  // namespace tb200

@@ -1,0 +1,361 @@
+# -*- coding: utf-8 -*-
+"""The ``b200`` stencil definitions: one per reference stencil name on the hot path
+(SURVEY.md section 8a), with the reference's keyword names.  Each is a thin marshalling layer
+over one C-ABI entry point of ``libtasmania_b200.so``; the arithmetic lives in the CUDA
+kernels.  ``externals`` is the snapshot of ``BackendOptions.externals`` taken at
+``compile_stencil`` time and selects the kernel variant (flux scheme, ``moist``, constants).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from tasmania_b200 import lib
+from tasmania_b200.framework import stencil_definition, subroutine_definition
+
+_f = lib.as_field
+_i3 = lib.int3
+
+
+def _stream():
+    return lib.current_stream()
+
+
+def _call(name, *args):
+    lib.check(getattr(lib.load(), name)(*args), name)
+
+
+# ------------------------------------------------------------------ scheme descriptors
+class FluxScheme:
+    """What ``get_subroutine_definition('flux_dry' | 'flux_moist')`` returns for b200: a
+    descriptor the fused CUDA kernel is specialised on, standing in for
+    src/tasmania/isentropic/dynamics/subclasses/minimal_horizontal_fluxes/*.py."""
+
+    def __init__(self, name, extent, order):
+        self.name, self.extent, self.order = name, extent, order
+        self.code = lib.FLUX_SCHEMES[name]
+
+    def __repr__(self):
+        return f"FluxScheme({self.name!r})"
+
+
+FLUX = {
+    "upwind": FluxScheme("upwind", 1, 1),
+    "centered": FluxScheme("centered", 1, 2),
+    "third_order_upwind": FluxScheme("third_order_upwind", 2, 3),
+    "fifth_order_upwind": FluxScheme("fifth_order_upwind", 3, 5),
+}
+
+
+class AdvectionScheme:
+    """b200 descriptor of a Burgers advection subroutine
+    (src/tasmania/burgers/dynamics/subclasses/advection/*.py)."""
+
+    def __init__(self, name, order):
+        self.name, self.order, self.extent = name, order, (order + 1) // 2
+
+    def __repr__(self):
+        return f"AdvectionScheme({self.name!r})"
+
+
+ADVECTION = {
+    n: AdvectionScheme(n, o)
+    for o, n in enumerate(
+        ("first_order", "second_order", "third_order", "fourth_order", "fifth_order", "sixth_order"), 1
+    )
+}
+
+
+def _flux_code(externals):
+    d = externals.get("flux_dry")
+    if isinstance(d, FluxScheme):
+        return d.code
+    if isinstance(d, str):
+        return lib.FLUX_SCHEMES[d]
+    raise lib.B200Error("externals['flux_dry'] must be a tasmania_b200 FluxScheme descriptor")
+
+
+# ------------------------------------------------------------------ K12 element-wise
+def _ew(op, out, a, b=None, c=None, f=0.0, *, origin, domain):
+    _call("tb200_elementwise", lib.ELEMENTWISE_OPS[op], _f(out), _f(a), _f(b), _f(c), float(f),
+          _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("copy")
+def copy_b200(externals, *, src, dst, origin, domain):
+    _ew("copy", dst, src, origin=origin, domain=domain)
+
+
+@stencil_definition("copychange")
+def copychange_b200(externals, *, src, dst, origin, domain):
+    _ew("copychange", dst, src, origin=origin, domain=domain)
+
+
+@stencil_definition("abs")
+def abs_b200(externals, *, in_field, out_field, origin, domain):
+    _ew("abs", out_field, in_field, origin=origin, domain=domain)
+
+
+@stencil_definition("iabs")
+def iabs_b200(externals, *, inout_field, origin, domain):
+    _ew("abs", inout_field, inout_field, origin=origin, domain=domain)
+
+
+@stencil_definition("add")
+def add_b200(externals, *, in_a, in_b, out_c, origin, domain):
+    _ew("add", out_c, in_a, in_b, origin=origin, domain=domain)
+
+
+@stencil_definition("iadd")
+def iadd_b200(externals, *, inout_a, in_b, origin, domain):
+    _ew("add", inout_a, inout_a, in_b, origin=origin, domain=domain)
+
+
+@stencil_definition("addsub")
+def addsub_b200(externals, *, in_a, in_b, in_c, out_d, origin, domain):
+    _ew("addsub", out_d, in_a, in_b, in_c, origin=origin, domain=domain)
+
+
+@stencil_definition("iaddsub")
+def iaddsub_b200(externals, *, inout_a, in_b, in_c, origin, domain):
+    _ew("iaddsub", inout_a, inout_a, in_b, in_c, origin=origin, domain=domain)
+
+
+@stencil_definition("clip")
+def clip_b200(externals, *, in_field, out_field, origin, domain):
+    _ew("clip", out_field, in_field, origin=origin, domain=domain)
+
+
+@stencil_definition("iclip")
+def iclip_b200(externals, *, inout_field, origin, domain):
+    _ew("clip", inout_field, inout_field, origin=origin, domain=domain)
+
+
+@stencil_definition("fma")
+def fma_b200(externals, *, in_a, in_b, out_c, f, origin, domain):
+    _ew("fma", out_c, in_a, in_b, f=f, origin=origin, domain=domain)
+
+
+@stencil_definition("mul")
+def mul_b200(externals, *, in_a, in_b, out_c, origin, domain):
+    _ew("mul", out_c, in_a, in_b, origin=origin, domain=domain)
+
+
+@stencil_definition("imul")
+def imul_b200(externals, *, inout_a, in_b, origin, domain):
+    _ew("mul", inout_a, inout_a, in_b, origin=origin, domain=domain)
+
+
+@stencil_definition("scale")
+def scale_b200(externals, *, in_a, out_a, f, origin, domain):
+    _ew("scale", out_a, in_a, f=f, origin=origin, domain=domain)
+
+
+@stencil_definition("iscale")
+def iscale_b200(externals, *, inout_a, f, origin, domain):
+    _ew("iscale", inout_a, inout_a, f=f, origin=origin, domain=domain)
+
+
+@stencil_definition("sub")
+def sub_b200(externals, *, in_a, in_b, out_c, origin, domain):
+    _ew("sub", out_c, in_a, in_b, origin=origin, domain=domain)
+
+
+@stencil_definition("isub")
+def isub_b200(externals, *, inout_a, in_b, origin, domain):
+    _ew("sub", inout_a, inout_a, in_b, origin=origin, domain=domain)
+
+
+@stencil_definition("sts_rk2_0")
+def sts_rk2_0_b200(externals, *, in_field, in_field_prv, in_tnd, out_field, dt, origin, domain):
+    _ew("sts_rk2_0", out_field, in_field, in_field_prv, in_tnd, f=dt, origin=origin, domain=domain)
+
+
+@stencil_definition("sts_rk3ws_0")
+def sts_rk3ws_0_b200(externals, *, in_field, in_field_prv, in_tnd, out_field, dt, origin, domain):
+    _ew("sts_rk3ws_0", out_field, in_field, in_field_prv, in_tnd, f=dt, origin=origin, domain=domain)
+
+
+# ------------------------------------------------------------------ K5 relaxation
+@stencil_definition("irelax")
+def irelax_b200(externals, *, in_gamma, in_phi_ref, inout_phi, origin, domain):
+    _call("tb200_relax", _f(in_gamma), None, _f(in_phi_ref), _f(inout_phi), _i3(origin),
+          _i3(domain), _stream())
+
+
+@stencil_definition("relax")
+def relax_b200(externals, *, in_gamma, in_phi, in_phi_ref, out_phi, origin, domain):
+    _call("tb200_relax", _f(in_gamma), _f(in_phi), _f(in_phi_ref), _f(out_phi), _i3(origin),
+          _i3(domain), _stream())
+
+
+# ------------------------------------------------------------------ K6 damping
+@stencil_definition("damping")
+def damping_b200(externals, *, in_phi_now, in_phi_new, in_phi_ref, in_rmat, out_phi, dt, origin,
+                 domain):
+    _call("tb200_damping", _f(in_phi_now), _f(in_phi_new), _f(in_phi_ref), _f(in_rmat),
+          _f(out_phi), float(dt), _i3(origin), _i3(domain), _stream())
+
+
+# ------------------------------------------------------------------ K4 / K7 diagnostics
+@stencil_definition("velocity_x")
+def velocity_x_b200(externals, *, in_d, in_du, out_u, origin, domain):
+    _call("tb200_velocity", 0, _f(in_d), _f(in_du), _f(out_u), int(bool(externals.get("staggering", True))),
+          _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("velocity_y")
+def velocity_y_b200(externals, *, in_d, in_dv, out_v, origin, domain):
+    _call("tb200_velocity", 1, _f(in_d), _f(in_dv), _f(out_v), int(bool(externals.get("staggering", True))),
+          _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("momenta")
+def momenta_b200(externals, *, in_d, in_u, in_v, out_du, out_dv, origin, domain):
+    _call("tb200_momenta", _f(in_d), _f(in_u), _f(in_v), _f(out_du), _f(out_dv),
+          int(bool(externals.get("staggering", True))), _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("density")
+def density_b200(externals, *, in_d, in_q, out_dq, origin, domain):
+    _call("tb200_density", _f(in_d), _f(in_q), _f(out_dq), int(bool(externals.get("clipping", True))),
+          _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("mass_fraction")
+def mass_fraction_b200(externals, *, in_d, in_dq, out_q, origin, domain):
+    _call("tb200_mass_fraction", _f(in_d), _f(in_dq), _f(out_q),
+          int(bool(externals.get("clipping", True))), _i3(origin), _i3(domain), _stream())
+
+
+# ------------------------------------------------------------------ K8 / K9
+def _full_k(field, origin, domain):
+    # the reference's numpy diffusion ignores origin[2]/domain[2] and sweeps every level
+    # (fourth_order.py:L95-L124 index only i and j)
+    return (origin[0], origin[1], 0), (domain[0], domain[1], field.shape[2])
+
+
+@stencil_definition("diffusion")
+def diffusion_b200(externals, *, in_phi, in_gamma, out_phi, dx, dy, ow_out_phi, origin, domain):
+    order = externals.get("diffusion_order")
+    if order not in (2, 4):
+        raise lib.B200Error("externals['diffusion_order'] must be 2 or 4")
+    o, d = _full_k(in_phi, origin, domain)
+    _call("tb200_diffusion", order, _f(in_phi), _f(in_gamma), _f(out_phi), float(dx), float(dy),
+          int(bool(ow_out_phi)), _i3(o), _i3(d), _stream())
+
+
+@stencil_definition("smoothing")
+def smoothing_b200(externals, *, in_phi, in_gamma, out_phi, origin, domain):
+    order = externals.get("smoothing_order")
+    if order not in (1, 2, 3):
+        raise lib.B200Error("externals['smoothing_order'] must be 1, 2 or 3")
+    _call("tb200_smoothing", order, _f(in_phi), _f(in_gamma), _f(out_phi),
+          int(bool(externals.get("rim_copy", False))), _i3(origin), _i3(domain), _stream())
+
+
+# ------------------------------------------------------------------ K1 / K2
+def _field_array(fields):
+    """array of three ``tb200_field*`` (qv, qc, qr) or NULL"""
+    if fields is None or all(f is None for f in fields):
+        return None, None
+    keep = [_f(x) for x in fields]
+    arr = (lib.FieldP * 3)(*[C.pointer(k) if k is not None else None for k in keep])
+    return arr, keep
+
+
+@stencil_definition("step_forward_euler")
+def step_forward_euler_b200(
+    externals, *, s_now, s_int, s_new, u_int, v_int, su_int=None, sv_int=None, mtg_int=None,
+    sqv_now=None, sqv_int=None, sqv_new=None, sqc_now=None, sqc_int=None, sqc_new=None,
+    sqr_now=None, sqr_int=None, sqr_new=None, s_tnd=None, qv_tnd=None, qc_tnd=None, qr_tnd=None,
+    dt, dx, dy, origin, domain,
+):
+    moist = bool(externals.get("moist", False))
+    # RK3WS-SI passes a zero placeholder when a tendency is absent (rk3ws_si.py:L143); the
+    # *_tnd_on switches tell whether it is live
+    s_t = s_tnd if externals.get("s_tnd_on", s_tnd is not None) else None
+    now = ints = new = tnd = None
+    keep = []
+    if moist:
+        now, k1 = _field_array((sqv_now, sqc_now, sqr_now))
+        ints, k2 = _field_array((sqv_int, sqc_int, sqr_int))
+        new, k3 = _field_array((sqv_new, sqc_new, sqr_new))
+        q = [
+            t if externals.get(flag, t is not None) else None
+            for t, flag in ((qv_tnd, "qv_tnd_on"), (qc_tnd, "qc_tnd_on"), (qr_tnd, "qr_tnd_on"))
+        ]
+        tnd, k4 = _field_array(q)
+        keep = [k1, k2, k3, k4]
+    _call("tb200_step_forward_euler", _flux_code(externals), _f(s_now), _f(s_int), _f(s_new),
+          _f(u_int), _f(v_int), _f(s_t), now, ints, new, tnd, float(dt), float(dx), float(dy),
+          _i3(origin), _i3(domain), _stream())
+    del keep
+
+
+@stencil_definition("step_forward_euler_momentum")
+def step_forward_euler_momentum_b200(
+    externals, *, s_now, s_int=None, s_new, u_int, v_int, su_now, su_int, su_new, sv_now, sv_int,
+    sv_new, mtg_now, mtg_new, mtg_int=None, su_tnd=None, sv_tnd=None, dt, dx, dy, eps, origin,
+    domain,
+):
+    su_t = su_tnd if externals.get("su_tnd_on", su_tnd is not None) else None
+    sv_t = sv_tnd if externals.get("sv_tnd_on", sv_tnd is not None) else None
+    _call("tb200_step_forward_euler_momentum", _flux_code(externals), _f(s_now), _f(s_new),
+          _f(u_int), _f(v_int), _f(su_now), _f(su_int), _f(su_new), _f(sv_now), _f(sv_int),
+          _f(sv_new), _f(mtg_now), _f(mtg_new), _f(su_t), _f(sv_t), float(dt), float(dx),
+          float(dy), float(eps), _i3(origin), _i3(domain), _stream())
+
+
+# ------------------------------------------------------------------ K3
+def _constants(externals):
+    return lib.Double4(float(externals["pref"]), float(externals["rd"]), float(externals["g"]),
+                       float(externals["cp"]))
+
+
+@stencil_definition("montgomery")
+def montgomery_b200(externals, *, in_hs, in_s, inout_mtg, dz, pt, theta_s, origin, domain):
+    _call("tb200_montgomery", _f(in_hs), _f(in_s), _f(inout_mtg), float(dz), float(pt),
+          float(theta_s), _constants(externals), _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("diagnostic_variables")
+def diagnostic_variables_b200(externals, *, in_theta, in_hs, in_s, inout_p, out_exn, inout_mtg,
+                              inout_h, dz, pt, origin, domain):
+    _call("tb200_diagnostic_variables", _f(in_theta), _f(in_hs), _f(in_s), _f(inout_p),
+          _f(out_exn), _f(inout_mtg), _f(inout_h), float(dz), float(pt), _constants(externals),
+          _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("height")
+def height_b200(externals, *, in_theta, in_hs, in_s, inout_h, dz, pt, origin, domain):
+    _call("tb200_height", _f(in_theta), _f(in_hs), _f(in_s), _f(inout_h), float(dz), float(pt),
+          _constants(externals), _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("density_and_temperature")
+def density_and_temperature_b200(externals, *, in_theta, in_s, in_exn, in_h, out_rho, out_t,
+                                 origin, domain):
+    _call("tb200_density_and_temperature", _f(in_theta), _f(in_s), _f(in_exn), _f(in_h),
+          _f(out_rho), _f(out_t), float(externals["cp"]), _i3(origin), _i3(domain), _stream())
+
+
+# ------------------------------------------------------------------ K10 Burgers
+@stencil_definition("forward_euler")
+def burgers_forward_euler_b200(externals, *, in_u, in_v, in_u_tmp, in_v_tmp, out_u, out_v,
+                               in_u_tnd=None, in_v_tnd=None, dt, dx, dy, origin, domain):
+    adv = externals.get("advection")
+    order = adv.order if isinstance(adv, AdvectionScheme) else int(adv)
+    tu = in_u_tnd if externals.get("tnd_u", in_u_tnd is not None) else None
+    tv = in_v_tnd if externals.get("tnd_v", in_v_tnd is not None) else None
+    _call("tb200_burgers_forward_euler", order, _f(in_u), _f(in_v), _f(in_u_tmp), _f(in_v_tmp),
+          _f(out_u), _f(out_v), _f(tu), _f(tv), float(dt), float(dx), float(dy), _i3(origin),
+          _i3(domain), _stream())
+
+
+# subroutine descriptors: must *exist* for the backend (stencil.py:L379-L392)
+for _name, _scheme in FLUX.items():
+    subroutine_definition(f"flux_dry:{_name}")(_scheme)
+    subroutine_definition(f"flux_moist:{_name}")(_scheme)
+for _name, _scheme in ADVECTION.items():
+    subroutine_definition(f"advection:{_name}")(_scheme)
+subroutine_definition("set_output")("set_output")
