@@ -385,20 +385,27 @@ def end_to_end(run, args, world, barrier, distributed):
         return None
     names_in = run.names
     names_out = run.out_names
-    host_in = {n: torch.empty_like(run.state[n].t, device="cpu").pin_memory() for n in names_in}
+
+    def base(arr):
+        # the contiguous padded allocation behind a storage: host buffers mirror the device
+        # layout, so every copy is one plain cudaMemcpyAsync
+        t = arr.t
+        return t._base if t._base is not None else t
+
+    host_in = {n: torch.empty_like(base(run.state[n]), device="cpu").pin_memory() for n in names_in}
     for n in names_in:
-        host_in[n].copy_(run.state[n].t)
-    host_out = {n: torch.empty_like(run.state[n].t, device="cpu").pin_memory() for n in names_out}
+        host_in[n].copy_(base(run.state[n]))
+    host_out = {n: torch.empty_like(base(run.state[n]), device="cpu").pin_memory() for n in names_out}
     steps = max(1, min(args.steps, 3))
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):
         for n in names_in:
-            run.state[n].t.copy_(host_in[n], non_blocking=True)
+            base(run.state[n]).copy_(host_in[n], non_blocking=True)
         run.step()
         for n in names_out:
-            host_out[n].copy_(run.state[n].t, non_blocking=True)
+            host_out[n].copy_(base(run.state[n]), non_blocking=True)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)

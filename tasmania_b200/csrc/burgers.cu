@@ -16,15 +16,16 @@ int run(View u, View v, View ut, View vt, View ou, View ov, View tu, View tv, do
         double dx, double dy, const int32_t o[3], const int32_t d[3], cudaStream_t st) {
   using A = Advection<ORDER>;
   const int i0 = o[0], j0 = o[1], k0 = o[2];
+  const CDiv denx = make_cdiv(A::denominator(dx)), deny = make_cdiv(A::denominator(dy));
   return launch_box("burgers_forward_euler", d, st, [=] __device__(int i, int j, int k) {
     i += i0; j += j0; k += k0;
     const double *pu = ut.p + (i * ut.s0 + j * ut.s1 + k * ut.s2);
     const double *pv = vt.p + (i * vt.s0 + j * vt.s1 + k * vt.s2);
-    const double a = __ldg(pu), b = __ldg(pv);
-    const double adv_u_x = A::term(a, pu, ut.s0, dx);
-    const double adv_u_y = A::term(b, pu, ut.s1, dy);
-    const double adv_v_x = A::term(a, pv, vt.s0, dx);
-    const double adv_v_y = A::term(b, pv, vt.s1, dy);
+    const double a = __ldg(pu) / denx, b = __ldg(pv) / deny;
+    const double adv_u_x = A::term(a, pu, ut.s0);
+    const double adv_u_y = A::term(b, pu, ut.s1);
+    const double adv_v_x = A::term(a, pv, vt.s0);
+    const double adv_v_y = A::term(b, pv, vt.s1);
     // stepper.py:L219-L227
     if (tu.ok())
       ou(i, j, k) = u(i, j, k) - dt * (adv_u_x + adv_u_y - tu(i, j, k));

@@ -44,7 +44,7 @@ __device__ __forceinline__ double ew(double a, double b, double c, double f) {
   if (OP == TB200_EW_SCALE) return f * a;
   if (OP == TB200_EW_SUB) return a - b;
   if (OP == TB200_EW_STS_RK2_0) return 0.5 * (a + b + f * c);
-  if (OP == TB200_EW_STS_RK3WS_0) return (2.0 * a + b + f * c) / 3.0;
+  if (OP == TB200_EW_STS_RK3WS_0) return (2.0 * a + b + f * c) / CDiv{3.0, 1.0 / 3.0};
   if (OP == TB200_EW_IADDSUB) return a + (b - c);
   if (OP == TB200_EW_ISCALE) return a * f;
   return 0.0;

@@ -16,15 +16,17 @@ namespace {
 // ---- point formulas ------------------------------------------------------------------
 // second_order.py:L101-L104
 __device__ __forceinline__ double lap2(double g, double c, double im1, double ip1, double jm1,
-                                       double jp1, double dx, double dy) {
-  return g * ((im1 - 2.0 * c + ip1) / (dx * dx) + (jm1 - 2.0 * c + jp1) / (dy * dy));
+                                       double jp1, const CDiv &dx, const CDiv &dy) {
+  // dx, dy hold the full denominators dx*dx, dy*dy
+  return g * ((im1 - 2.0 * c + ip1) / dx + (jm1 - 2.0 * c + jp1) / dy);
 }
 // fourth_order.py:L104-L122
 __device__ __forceinline__ double lap4(double g, double c, double im2, double im1, double ip1,
                                        double ip2, double jm2, double jm1, double jp1,
-                                       double jp2, double dx, double dy) {
-  return g * ((-im2 + 16.0 * im1 - 30.0 * c + 16.0 * ip1 - ip2) / (12.0 * dx * dx) +
-              (-jm2 + 16.0 * jm1 - 30.0 * c + 16.0 * jp1 - jp2) / (12.0 * dy * dy));
+                                       double jp2, const CDiv &dx, const CDiv &dy) {
+  // dx, dy hold the full denominators 12*dx*dx, 12*dy*dy
+  return g * ((-im2 + 16.0 * im1 - 30.0 * c + 16.0 * ip1 - ip2) / dx +
+              (-jm2 + 16.0 * jm1 - 30.0 * c + 16.0 * jp1 - jp2) / dy);
 }
 
 constexpr int TX = 64, TY = 8;
@@ -37,7 +39,7 @@ struct Halo {
 
 template <int OP>
 __global__ void __launch_bounds__(TX *TY)
-    cross_kernel(View phi, View gam, View out, double dx, double dy, int overwrite, int rim,
+    cross_kernel(View phi, View gam, View out, CDiv dx, CDiv dy, int overwrite, int rim,
                  int i0, int j0, int k0, int di, int dj, int dk, int ri, int rj) {
   constexpr int H = Halo<OP>::value;
   constexpr int SX = TX + 2 * H, SY = TY + 2 * H;
@@ -110,7 +112,10 @@ int launch_cross(const char *what, View phi, View gam, View out, double dx, doub
   if (ei <= 0 || ej <= 0 || d[2] <= 0) return TB200_OK;
   dim3 block(TX, TY, 1);
   dim3 grid((ei + TX - 1) / TX, (ej + TY - 1) / TY, d[2] > 65535 ? 65535 : d[2]);
-  cross_kernel<OP><<<grid, block, 0, st>>>(phi, gam, out, dx, dy, overwrite, rim, o[0], o[1],
+  // full denominators, evaluated as the reference does: dx * dx and 12.0 * dx * dx
+  const CDiv cdx = make_cdiv(OP == 4 ? 12.0 * dx * dx : (OP == 2 ? dx * dx : 1.0));
+  const CDiv cdy = make_cdiv(OP == 4 ? 12.0 * dy * dy : (OP == 2 ? dy * dy : 1.0));
+  cross_kernel<OP><<<grid, block, 0, st>>>(phi, gam, out, cdx, cdy, overwrite, rim, o[0], o[1],
                                            o[2], d[0], d[1], d[2], ri, rj);
   return check_launch(what);
 }

@@ -25,15 +25,17 @@ int run_k1(View s_now, View s_int, View s_new, View u, View v, View s_tnd, Trace
            double dt, double dx, double dy, const int32_t o[3], const int32_t d[3],
            cudaStream_t st) {
   const int i0 = o[0], j0 = o[1], k0 = o[2];
+  const FluxConst fc = make_flux_const(dx, dy);
   return launch_box("step_forward_euler", d, st, [=] __device__(int i, int j, int k) {
     i += i0; j += j0; k += k0;
+    const FaceVel w = face_velocities<SCHEME>(u, v, i, j, k, fc);
     // utils.py:L95-L99
-    const double div = flux_divergence<SCHEME>(u, v, s_int, i, j, k, dx, dy);
+    const double div = flux_divergence<SCHEME>(w, s_int, i, j, k, fc);
     const double tnd = s_tnd.ok() ? s_tnd(i, j, k) : 0.0;
     s_new(i, j, k) = s_now(i, j, k) - dt * (div - tnd);
     // utils.py:L101-L134
     for (int t = 0; t < tr.n; ++t) {
-      const double dq = flux_divergence<SCHEME>(u, v, tr.in[t], i, j, k, dx, dy);
+      const double dq = flux_divergence<SCHEME>(w, tr.in[t], i, j, k, fc);
       const double src = tr.tnd[t].ok() ? s_int(i, j, k) * tr.tnd[t](i, j, k) : 0.0;
       tr.out[t](i, j, k) = tr.now[t](i, j, k) - dt * (dq - src);
     }
@@ -46,24 +48,27 @@ int run_k2(View s_now, View s_new, View u, View v, View su_now, View su_int, Vie
            View sv_tnd, double dt, double dx, double dy, double eps, const int32_t o[3],
            const int32_t d[3], cudaStream_t st) {
   const int i0 = o[0], j0 = o[1], k0 = o[2];
+  const FluxConst fc = make_flux_const(dx, dy);
+  const CDiv two_dx = make_cdiv(2.0 * dx), two_dy = make_cdiv(2.0 * dy);
   return launch_box("step_forward_euler_momentum", d, st, [=] __device__(int i, int j, int k) {
     i += i0; j += j0; k += k0;
+    const FaceVel w = face_velocities<SCHEME>(u, v, i, j, k, fc);
     const double sn = s_now(i, j, k), sw = s_new(i, j, k);
     // utils.py:L191-L197
     {
-      const double div = flux_divergence<SCHEME>(u, v, su_int, i, j, k, dx, dy);
+      const double div = flux_divergence<SCHEME>(w, su_int, i, j, k, fc);
       const double pg_now =
-          (1.0 - eps) * sn * (mtg_now(i + 1, j, k) - mtg_now(i - 1, j, k)) / (2.0 * dx);
-      const double pg_new = eps * sw * (mtg_new(i + 1, j, k) - mtg_new(i - 1, j, k)) / (2.0 * dx);
+          (1.0 - eps) * sn * (mtg_now(i + 1, j, k) - mtg_now(i - 1, j, k)) / two_dx;
+      const double pg_new = eps * sw * (mtg_new(i + 1, j, k) - mtg_new(i - 1, j, k)) / two_dx;
       const double tnd = su_tnd.ok() ? su_tnd(i, j, k) : 0.0;
       su_new(i, j, k) = su_now(i, j, k) - dt * (div + pg_now + pg_new - tnd);
     }
     // utils.py:L198-L204
     {
-      const double div = flux_divergence<SCHEME>(u, v, sv_int, i, j, k, dx, dy);
+      const double div = flux_divergence<SCHEME>(w, sv_int, i, j, k, fc);
       const double pg_now =
-          (1.0 - eps) * sn * (mtg_now(i, j + 1, k) - mtg_now(i, j - 1, k)) / (2.0 * dy);
-      const double pg_new = eps * sw * (mtg_new(i, j + 1, k) - mtg_new(i, j - 1, k)) / (2.0 * dy);
+          (1.0 - eps) * sn * (mtg_now(i, j + 1, k) - mtg_now(i, j - 1, k)) / two_dy;
+      const double pg_new = eps * sw * (mtg_new(i, j + 1, k) - mtg_new(i, j - 1, k)) / two_dy;
       const double tnd = sv_tnd.ok() ? sv_tnd(i, j, k) : 0.0;
       sv_new(i, j, k) = sv_now(i, j, k) - dt * (div + pg_now + pg_new - tnd);
     }
@@ -175,6 +180,7 @@ static int run_k3(View theta, View hs, View s, View p, View exn, View mtg, View 
                   const int32_t o[3], const int32_t d[3], cudaStream_t st) {
   const int i0 = o[0], j0 = o[1], k0 = o[2], k1 = o[2] + d[2];
   const double kappa = rd / cp;
+  const CDiv cpref = make_cdiv(pref);
   return launch_columns("isentropic_diagnostics", d[0], d[1], st, [=] __device__(int i, int j) {
     i += i0; j += j0;
     // downward pressure scan, diagnostics.py:L339-L345 / L425-L431
@@ -183,9 +189,9 @@ static int run_k3(View theta, View hs, View s, View p, View exn, View mtg, View 
       if (k > k0) pk = pk + g * dz * s(i, j, k - 1);
       if (WHAT == 1) {
         p(i, j, k) = pk;
-        exn(i, j, k) = cp * pow(pk / pref, kappa);
+        exn(i, j, k) = cp * pow(pk / cpref, kappa);
       } else if (k > k0) {
-        mtg(i, j, k - 1) = cp * pow(pk / pref, kappa);  // park exn[k] in mtg[k-1]
+        mtg(i, j, k - 1) = cp * pow(pk / cpref, kappa);  // park exn[k] in mtg[k-1]
       }
     }
     // upward Montgomery scan, diagnostics.py:L347-L351 / L433-L438
@@ -262,6 +268,7 @@ extern "C" int tb200_height(const tb200_field *in_theta, const tb200_field *in_h
   TB200_REQUIRE(hs.p != h.p && s.p != h.p, "height: inputs must not alias inout_h");
   const double pref = constants[0], rd = constants[1], g = constants[2], cp = constants[3];
   const double kappa = rd / cp;
+  const CDiv cpref = make_cdiv(pref);
   const int i0 = origin[0], j0 = origin[1], k0 = origin[2], k1 = origin[2] + domain[2];
   return launch_columns("height", domain[0], domain[1], static_cast<cudaStream_t>(stream),
                         [=] __device__(int i, int j) {
@@ -272,12 +279,12 @@ extern "C" int tb200_height(const tb200_field *in_theta, const tb200_field *in_h
                             if (k < k1 - 1) h(i, j, k) = pk;  // park p[k]
                           }
                           double pb = pk;  // p[k1-1]
-                          double eb = cp * pow(pb / pref, kappa);
+                          double eb = cp * pow(pb / cpref, kappa);
                           double hk = hs(i, j, k1 - 1);
                           h(i, j, k1 - 1) = hk;
                           for (int k = k1 - 2; k >= k0; --k) {
                             const double pa = h(i, j, k);
-                            const double ea = cp * pow(pa / pref, kappa);
+                            const double ea = cp * pow(pa / cpref, kappa);
                             hk = hk - rd * (th(i, j, k) * ea + th(i, j, k + 1) * eb) * (pa - pb) /
                                           (cp * g * (pa + pb));
                             h(i, j, k) = hk;

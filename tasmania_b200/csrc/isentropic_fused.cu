@@ -41,6 +41,8 @@ struct StageArgs {
   View gamma, rmat, hs, exn, mtg;
   int nx, ny, nz, nb, damp;
   double dt, dt_full, dx, dy, dz, eps, pt, theta_s, pref, rd, g, cp;
+  FluxConst fc;
+  CDiv two_dx, two_dy, cpref;
 };
 
 // ---------------------------------------------------------------- kernel S
@@ -59,7 +61,8 @@ __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
   for (int k = 0; k < a.nz; ++k) {
     double v;
     if (interior) {
-      const double div = flux_divergence<SCHEME>(a.u_int, a.v_int, a.s_int, i, j, k, a.dx, a.dy);
+      const FaceVel w = face_velocities<SCHEME>(a.u_int, a.v_int, i, j, k, a.fc);
+      const double div = flux_divergence<SCHEME>(w, a.s_int, i, j, k, a.fc);
       v = a.s_now.ld(i, j, k) - a.dt * (div - 0.0);
     } else {
       v = a.s_new(i, j, k);  // untouched by K1; the relaxation below decides
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
     if (gam != 0.0) v = relax_point(gam, v, a.s_ref.ld(i, j, k));
     a.s_new(i, j, k) = v;
     p = p + gdz * v;
-    a.exn(i, j, k) = a.cp * pow(p / a.pref, kappa);
+    a.exn(i, j, k) = a.cp * pow(p / a.cpref, kappa);
   }
   // upward sweep, diagnostics.py:L433-L438
   const double ex_s = a.exn(i, j, a.nz - 1);
@@ -98,21 +101,22 @@ __global__ void __launch_bounds__(256) stage_m_kernel(const StageArgs a) {
   const double su_now = need_now ? a.su_now.ld(i, j, k) : 0.0;
   const double sv_now = need_now ? a.sv_now.ld(i, j, k) : 0.0;
   if (interior) {
+    const FaceVel w = face_velocities<SCHEME>(a.u_int, a.v_int, i, j, k, a.fc);
     // prognostics/utils.py:L191-L204
     {
-      const double div = flux_divergence<SCHEME>(a.u_int, a.v_int, a.su_int, i, j, k, a.dx, a.dy);
+      const double div = flux_divergence<SCHEME>(w, a.su_int, i, j, k, a.fc);
       const double pg_now = (1.0 - a.eps) * s_now *
-                            (a.mtg_now.ld(i + 1, j, k) - a.mtg_now.ld(i - 1, j, k)) / (2.0 * a.dx);
+                            (a.mtg_now.ld(i + 1, j, k) - a.mtg_now.ld(i - 1, j, k)) / a.two_dx;
       const double pg_new =
-          a.eps * s * (a.mtg.ld(i + 1, j, k) - a.mtg.ld(i - 1, j, k)) / (2.0 * a.dx);
+          a.eps * s * (a.mtg.ld(i + 1, j, k) - a.mtg.ld(i - 1, j, k)) / a.two_dx;
       su = su_now - a.dt * (div + pg_now + pg_new - 0.0);
     }
     {
-      const double div = flux_divergence<SCHEME>(a.u_int, a.v_int, a.sv_int, i, j, k, a.dx, a.dy);
+      const double div = flux_divergence<SCHEME>(w, a.sv_int, i, j, k, a.fc);
       const double pg_now = (1.0 - a.eps) * s_now *
-                            (a.mtg_now.ld(i, j + 1, k) - a.mtg_now.ld(i, j - 1, k)) / (2.0 * a.dy);
+                            (a.mtg_now.ld(i, j + 1, k) - a.mtg_now.ld(i, j - 1, k)) / a.two_dy;
       const double pg_new =
-          a.eps * s * (a.mtg.ld(i, j + 1, k) - a.mtg.ld(i, j - 1, k)) / (2.0 * a.dy);
+          a.eps * s * (a.mtg.ld(i, j + 1, k) - a.mtg.ld(i, j - 1, k)) / a.two_dy;
       sv = sv_now - a.dt * (div + pg_now + pg_new - 0.0);
     }
   } else {
@@ -228,6 +232,10 @@ extern "C" int tb200_isentropic_stage_dry(
   a.eps = cfg->eps; a.pt = cfg->pt; a.theta_s = cfg->theta_s;
   a.pref = cfg->constants[0]; a.rd = cfg->constants[1]; a.g = cfg->constants[2];
   a.cp = cfg->constants[3];
+  a.fc = make_flux_const(a.dx, a.dy);
+  a.two_dx = make_cdiv(2.0 * a.dx);
+  a.two_dy = make_cdiv(2.0 * a.dy);
+  a.cpref = make_cdiv(a.pref);
 
   const int nx = a.nx, ny = a.ny, nz = a.nz;
   int e = -1;
