@@ -127,10 +127,10 @@ class DryRun:
         self.diag.get_diagnostic_variables(new[self.S], self.pt, new[P], new[EXN], new[self.MTG], new[H])
         self.state = new
 
-    # kernels of OUR library launched per step: 3 stages x (S, M, V) + topography scale (at
+    # kernels of OUR library launched per step: 3 stages x (S, MV) + topography scale (at
     # most 2: dycore + diagnostics hold separate copies) + diagnostic_variables
     def launches_per_step(self):
-        return 3 * 3 + 1 + 2
+        return 3 * 2 + 1 + 2
 
 
 # ------------------------------------------------------------------ clocks sampler

@@ -195,9 +195,9 @@ int tb200_burgers_forward_euler(int advection_order, const tb200_field *in_u,
  * One RK stage of IsentropicDynamicalCore.stage_array_call_dry
  * (src/tasmania/isentropic/dynamics/dycore.py:L641-L721) with the relaxed lateral boundary:
  * K1 + irelax(s) + pressure/Exner/Montgomery scans + K2 + irelax(s, su, sv) + Rayleigh
- * damping + velocity diagnosis + outermost layers, in three kernels.  All fields share one
- * storage shape and have unit stride along i.  `scratch_exn`/`scratch_mtg` are caller-owned
- * work storages of the same shape.  hs2d: topography, shape (>=nx, >=ny, 1).
+ * damping + velocity diagnosis + outermost layers, in two kernels.  All fields share one
+ * storage shape and have unit stride along i.  `scratch_exn`/`scratch_mtg`/`scratch_s` are
+ * caller-owned work storages of the same shape.  gamma must be 1 on the nb outermost rings.  hs2d: topography, shape (>=nx, >=ny, 1).
  * rmat1d / gamma2d: damping profile (1,1,nk) and relaxation coefficients (ni,nj,1) given as
  * fields (strides pick the rank).  damp != 0 applies the damping in this stage. */
 typedef struct tb200_isentropic_stage {
@@ -218,7 +218,8 @@ int tb200_isentropic_stage_dry(
     tb200_field *u_new, tb200_field *v_new, const tb200_field *s_ref,
     const tb200_field *su_ref, const tb200_field *sv_ref, const tb200_field *u_ref,
     const tb200_field *v_ref, const tb200_field *gamma, const tb200_field *rmat,
-    const tb200_field *hs, tb200_field *scratch_exn, tb200_field *scratch_mtg, void *stream);
+    const tb200_field *hs, tb200_field *scratch_exn, tb200_field *scratch_mtg,
+    tb200_field *scratch_s, void *stream);
 
 /* ---- halo exchange support (2-D domain decomposition) ------------
  * pack/unpack a box of a field into/from a contiguous buffer (i fastest). */

@@ -7,26 +7,23 @@
 //   -> Rayleigh damping (s, su, sv) -> velocity_x / velocity_y -> outermost layers of u, v.
 // The reference runs 13 full-domain passes for this; here:
 //
-//   kernel S  (one thread per column, marching in k)
-//       s_pre = irelax(K1(...))                      -> s_new
-//       p, exn by the downward scan on s_pre         -> scratch_exn   (exn at interface k+1)
-//       mtg_new by the upward scan                   -> scratch_mtg
-//   kernel M  (one thread per point)
-//       su, sv = irelax(K2(...)), s = irelax(s_pre), then Rayleigh damping on all three
-//   kernel V  (one thread per point)
-//       u, v from the final s, su, sv; outermost faces from the reference state.
+//   kernel S   (one thread per column, marching in k)
+//       s_pre = irelax(K1(...))                      -> scratch_s
+//       p by the downward scan on s_pre              -> scratch_exn  (pressure at interface k+1)
+//       exn = cp (p/pref)^kappa, mtg_new by the upward scan -> scratch_mtg
+//   kernel MV  (one warp per 30 columns x 64 rows of a level, marching in j)
+//       su, sv = irelax(K2(...)), s = irelax(s_pre), Rayleigh damping on all three,
+//       u, v from the final s, su, sv, outermost faces from the reference state.
 //
 // The vertical scans are inherently two sweeps (pressure top-down, Montgomery bottom-up) and
-// the momentum step needs mtg_new at i+-1 / j+-1, hence the kernel boundary between S and M;
-// V needs the *final* su/s at i-1 / j-1, hence the boundary between M and V.
+// the momentum step needs mtg_new at i+-1 / j+-1, hence the kernel boundary between S and MV.
 //
-// HBM traffic per point and stage (8-byte words): S reads s_now, s_int, u, v, writes s_new,
-// exn, re-reads exn (L2-resident for the CTA's columns at moderate sizes), writes mtg
-// = 7-8 words; M reads s_now, s_new, mtg_now, mtg_new, u, v, su_now, su_int, sv_now, sv_int,
-// writes s, su, sv = 13 words; V reads s, su, sv, writes u, v = 5 words.  Total ~25-26 words
-// = 200-208 B against the algorithmic minimum of 112 B; the relaxation
-// band and the damping layer add reads of the reference fields only where gamma != 0 or
-// R != 0.  All arithmetic follows the reference's operation order (see stencil_math.cuh).
+// HBM traffic per point and stage (8-byte words): S reads s_now, s_int, u, v, writes s_pre,
+// p, re-reads p, writes mtg = 8 words; MV reads s_now, s_pre, mtg_now, mtg_new, u, v, su_now,
+// su_int, sv_now, sv_int, writes s, su, sv, u, v = 15 words.  Total 23 words = 184 B against
+// the algorithmic minimum of 112 B; the relaxation band and the damping
+// layer add reads of the reference fields only where gamma != 0 or R != 0.  All arithmetic
+// follows the reference's operation order (see stencil_math.cuh).
 #include "stencil_math.cuh"
 
 using namespace tb200;
@@ -38,7 +35,7 @@ struct StageArgs {
   View s_int, su_int, sv_int, u_int, v_int;
   View s_new, su_new, sv_new, u_new, v_new;
   View s_ref, su_ref, sv_ref, u_ref, v_ref;
-  View gamma, rmat, hs, exn, mtg;
+  View gamma, rmat, hs, exn, mtg, spre;
   int nx, ny, nz, nb, damp;
   double dt, dt_full, dx, dy, dz, eps, pt, theta_s, pref, rd, g, cp;
   FluxConst fc;
@@ -46,6 +43,19 @@ struct StageArgs {
 };
 
 // ---------------------------------------------------------------- kernel S
+// Unit i-stride and 32-bit element offsets (a field has < 2^31 elements) keep the address
+// arithmetic off the critical path: one base pointer per field, immediate offsets along i.
+template <int SCHEME>
+__device__ __forceinline__ double div_unit(const FaceVel &w, const double *pc, int sj,
+                                           const FluxConst &c) {
+  using F = Flux<SCHEME>;
+  const double fxm = F::face(w.xm, pc, 1);
+  const double fxp = F::face(w.xp, pc + 1, 1);
+  const double fym = F::face(w.ym, pc, sj);
+  const double fyp = F::face(w.yp, pc + sj, sj);
+  return (fxp - fxm) / c.dx + (fyp - fym) / c.dy;
+}
+
 template <int SCHEME>
 __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,124 +65,292 @@ __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
   const double gam = a.gamma.ld(i, j, 0);
   const double kappa = a.rd / a.cp;
   const double gdz = a.g * a.dz;
+  using F = Flux<SCHEME>;
 
-  // downward sweep: step s, relax, integrate the pressure, park exn[k+1] in scratch_exn[k]
+  // downward sweep: step s, relax, integrate the pressure; p[k+1] is parked in the exn
+  // scratch (no libm call on this serial chain)
   double p = a.pt;
-  for (int k = 0; k < a.nz; ++k) {
-    double v;
+  {
+    const double *ps_int = a.s_int.p + (i + j * a.s_int.s1);
+    const double *ps_now = a.s_now.p + (i + j * a.s_now.s1);
+    const double *pu = a.u_int.p + (i + j * a.u_int.s1);
+    const double *pv = a.v_int.p + (i + j * a.v_int.s1);
+    const double *pref_ = a.s_ref.p + (i + j * a.s_ref.s1);
+    double *ps_new = a.spre.p + (i + j * a.spre.s1);
+    const double *ps_old = a.s_new.p + (i + j * a.s_new.s1);
+    double *pex = a.exn.p + (i + j * a.exn.s1);
+    const int sj = (int)a.s_int.s1, svj = (int)a.v_int.s1;
+#pragma unroll 2
+    for (int k = 0; k < a.nz; ++k) {
+      double v;
+      if (interior) {
+        const FaceVel w{F::prep(__ldg(pu), a.fc), F::prep(__ldg(pu + 1), a.fc),
+                        F::prep(__ldg(pv), a.fc), F::prep(__ldg(pv + svj), a.fc)};
+        const double div = div_unit<SCHEME>(w, ps_int, sj, a.fc);
+        v = __ldg(ps_now) - a.dt * (div - 0.0);
+      } else {
+        v = gam == 1.0 ? 0.0 : *ps_old;  // untouched by K1; the relaxation below decides
+      }
+      if (gam != 0.0) v = relax_point(gam, v, __ldg(pref_));
+      *ps_new = v;
+      p = p + gdz * v;
+      *pex = p;
+      ps_int += a.s_int.s2; ps_now += a.s_now.s2; pu += a.u_int.s2; pv += a.v_int.s2;
+      pref_ += a.s_ref.s2; ps_new += a.spre.s2; ps_old += a.s_new.s2; pex += a.exn.s2;
+    }
+  }
+  // upward sweep, diagnostics.py:L433-L438: exn[k+1] = cp (p[k+1] / pref)^kappa from the
+  // parked pressures -- the pow calls of different levels are independent of the cheap
+  // serial sum, so they pipeline
+  {
+    const double *pex = a.exn.p + (i + j * a.exn.s1 + (long long)(a.nz - 1) * a.exn.s2);
+    double *pm = a.mtg.p + (i + j * a.mtg.s1 + (long long)(a.nz - 1) * a.mtg.s2);
+    const double ex_s = a.cp * pow(*pex / a.cpref, kappa);
+    const double mtg_s = a.theta_s * ex_s + a.g * a.hs.ld(i, j, 0);
+    double m = mtg_s + 0.5 * a.dz * ex_s;
+    *pm = m;
+#pragma unroll 4
+    for (int k = a.nz - 2; k >= 0; --k) {
+      pex -= a.exn.s2;
+      pm -= a.mtg.s2;
+      m = m + a.dz * (a.cp * pow(*pex / a.cpref, kappa));
+      *pm = m;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- kernel MV
+// Momentum step + second relaxation + Rayleigh damping + velocity diagnosis in one pass.
+//
+// Work decomposition: one WARP owns 30 consecutive columns of one k-level and marches along
+// j over a strip of LJ rows.  Lanes 1..30 produce output; lane 0 re-computes the column to
+// the left (its final su, s feed lane 1's u) and lane 31 only contributes its left-face flux
+// to lane 30 -- so warps are fully autonomous: no shared memory, no block barrier.
+//   * y direction: each lane keeps a register window of the 2e rows of su_int / sv_int the
+//     next y-face needs (one new load per row instead of 2e+1) and carries the face flux
+//     F_y(j+1/2) over to the next row, so every y-face is evaluated once;
+//   * x direction: a lane evaluates only its LEFT face and receives the right one from
+//     lane+1 by shuffle, so every x-face is evaluated once (plus 2/32 redundancy); the x
+//     neighbours of the advected field come from L1 through immediate-offset loads;
+//   * the final (relaxed, damped) su, sv, s of the previous row / left lane stay in
+//     registers for the velocity diagnosis, hence no extra pass over the outputs.
+// A strip starts by re-computing row j0-1 (1/LJ redundancy) to seed those carries.
+// s_pre is read from its own scratch (written by kernel S) because halo lanes / rows read
+// points that belong to other warps, which may already have stored their final s.
+// Requirement: gamma == 1 on the nb outermost rings (true for the Relaxed boundary,
+// relaxed.py:L209-L211), so that the stale su/sv there never matter.
+constexpr int MV_COLS = 30;
+
+// First-touch (DRAM-latency) loads of one row, issued one row ahead of their use so that a
+// warp's arithmetic on row r overlaps its own memory traffic for row r+1.
+struct RowLoads {
+  double su_w, sv_w;  // su_int, sv_int at row r+E   (newest window entry)
+  double v_n;         // v_int at row r+1            (advects through the y-face r+1)
+  double u_c;         // u_int at row r              (advects through the left x-face)
+  double s_pre, s_now, su_now, sv_now;  // row r
+  double mn_p, mw_p;  // mtg_now, mtg_new at row r+1
+  double gam;         // relaxation coefficient at row r
+};
+
+// All 3-D fields of a fused stage share one geometry (unit i-stride, equal row and plane
+// strides -- what the b200 allocator produces for equal shapes; checked on the host), so one
+// 32-bit running BYTE offset addresses every field: loads compile to
+// [uniform base + offset + immediate] with no per-load integer arithmetic.
+__device__ __forceinline__ double ldo(const double *base, unsigned off) {
+  return __ldg(reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off));
+}
+__device__ __forceinline__ void sto(double *base, unsigned off, double v) {
+  *reinterpret_cast<double *>(reinterpret_cast<char *>(base) + off) = v;
+}
+__device__ __forceinline__ const double *ptr_at(const double *base, unsigned off) {
+  return reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off);
+}
+// pull a line towards L2 ahead of its use (no register, no stall)
+__device__ __forceinline__ void prefetch_l2(const double *base, unsigned off) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(base) + off));
+}
+
+template <int SCHEME, int LJ>
+__global__ void __launch_bounds__(128, 4) stage_mv_kernel(const StageArgs a) {
+  using F = Flux<SCHEME>;
+  constexpr int E = F::extent;
+  constexpr int NW = 2 * E;
+  const int lane = threadIdx.x & 31;
+  const int xw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (xw * MV_COLS >= a.nx) return;  // warp-uniform
+  const int c = xw * MV_COLS + lane - 1;
+  const int j0 = blockIdx.y * LJ;
+  const int jend = min(j0 + LJ, a.ny);
+  const int k = blockIdx.z;
+  const int nx = a.nx, ny = a.ny, nb = a.nb;
+
+  const bool out_lane = lane >= 1 && lane <= MV_COLS && c < nx;
+  const bool col_int = c >= nb && c < nx - nb;
+  // clamped columns: cc keeps every x-offset load inside the row, cm is the lane's own
+  // column whenever that exists (halo lanes beyond the domain only produce discarded values)
+  const int cc = min(max(c, E), nx - E);
+  const int cm = min(max(c, 0), nx - 1);
+
+  const unsigned row = (unsigned)a.s_now.s1 * 8u;         // bytes per row (all 3-D fields)
+  const unsigned plane = (unsigned)k * (unsigned)a.s_now.s2 * 8u;
+  const unsigned grow = (unsigned)a.gamma.s1 * 8u;
+
+  const double r_damp = a.damp ? a.rmat.ld(0, 0, k) : 0.0;
+  const double one_m_eps = 1.0 - a.eps;
+
+  const int r0 = j0 > 0 ? j0 - 1 : 0;  // first row computed (warm-up row unless j0 == 0)
+
+  // ---- prologue: windows for the y-face r0 (rows r0-E .. r0+E-1) and its flux
+  double wsu[NW], wsv[NW];
+#pragma unroll
+  for (int m = 0; m < NW; ++m) {
+    const unsigned o = plane + (unsigned)max(r0 - E + m, 0) * row + (unsigned)cc * 8u;
+    wsu[m] = ldo(a.su_int.p, o);
+    wsv[m] = ldo(a.sv_int.p, o);
+  }
+  // running byte offsets of row r (advanced by `row` per iteration)
+  unsigned o_cc = plane + (unsigned)r0 * row + (unsigned)cc * 8u;  // clamped column
+  unsigned o_cm = plane + (unsigned)r0 * row + (unsigned)cm * 8u;  // own column
+  unsigned o_g = (unsigned)r0 * grow + (unsigned)cm * 8u;          // gamma (2-D)
+  double fy_su, fy_sv;
+  {
+    const double vq = F::prep(ldo(a.v_int.p, o_cc), a.fc);
+    fy_su = F::eval_v(vq, wsu);
+    fy_sv = F::eval_v(vq, wsv);
+  }
+  // Montgomery window: row r-1 (row r+1 arrives with the row loads)
+  const unsigned o_m = plane + (unsigned)max(r0 - 1, 0) * row + (unsigned)cc * 8u;
+  double mn_m = ldo(a.mtg_now.p, o_m), mn_0 = ldo(a.mtg_now.p, o_cc);
+  double mw_m = ldo(a.mtg.p, o_m), mw_0 = ldo(a.mtg.p, o_cc);
+  double sv_prev = 0.0, s_prev = 0.0;
+
+  // rows up to jend + E are touched: inside the allocation because every field has at
+  // least one more plane than nz (checked on the host); the values only reach discarded
+  // boundary points
+  auto load_row = [&](unsigned occ, unsigned ocm, unsigned og) {
+    RowLoads L;
+    L.su_w = ldo(a.su_int.p, occ + E * row);
+    L.sv_w = ldo(a.sv_int.p, occ + E * row);
+    L.v_n = ldo(a.v_int.p, occ + row);
+    L.u_c = ldo(a.u_int.p, occ);
+    L.s_pre = ldo(a.spre.p, ocm);
+    L.s_now = ldo(a.s_now.p, ocm);
+    L.su_now = ldo(a.su_now.p, ocm);
+    L.sv_now = ldo(a.sv_now.p, ocm);
+    L.mn_p = ldo(a.mtg_now.p, occ + row);
+    L.mw_p = ldo(a.mtg.p, occ + row);
+    L.gam = ldo(a.gamma.p, og);
+    return L;
+  };
+
+  // DRAM -> L2 two rows further ahead, so the register loads above see L2 latency
+  auto prefetch_row = [&](unsigned occ, unsigned ocm) {
+    prefetch_l2(a.su_int.p, occ + E * row);
+    prefetch_l2(a.sv_int.p, occ + E * row);
+    prefetch_l2(a.v_int.p, occ + row);
+    prefetch_l2(a.u_int.p, occ);
+    prefetch_l2(a.spre.p, ocm);
+    prefetch_l2(a.s_now.p, ocm);
+    prefetch_l2(a.su_now.p, ocm);
+    prefetch_l2(a.sv_now.p, ocm);
+    prefetch_l2(a.mtg_now.p, occ + row);
+    prefetch_l2(a.mtg.p, occ + row);
+  };
+
+  RowLoads nxt = load_row(o_cc, o_cm, o_g);
+  for (int r = r0; r < jend; ++r) {
+    const RowLoads cur = nxt;
+    nxt = load_row(o_cc + row, o_cm + row, o_g + grow);  // in flight while row r is computed
+    if (r + 3 < jend) prefetch_row(o_cc + 3 * row, o_cm + 3 * row);
+
+    // ---- y-face r+1: shift the windows by one row, append row r+E
+#pragma unroll
+    for (int m = 0; m < NW - 1; ++m) {
+      wsu[m] = wsu[m + 1];
+      wsv[m] = wsv[m + 1];
+    }
+    wsu[NW - 1] = cur.su_w;
+    wsv[NW - 1] = cur.sv_w;
+    const double vq = F::prep(cur.v_n, a.fc);
+    const double fy_su_p = F::eval_v(vq, wsu);
+    const double fy_sv_p = F::eval_v(vq, wsv);
+
+    // ---- left x-face of column c at row r: phi[c-E .. c+E-1]; phi[c] is wsu[E-1]
+    // (the neighbours' lines entered L1 E rows ago as window loads)
+    const double uq = F::prep(cur.u_c, a.fc);
+    double xs[NW], ys[NW];
+    {
+      const double *psu = ptr_at(a.su_int.p, o_cc), *psv = ptr_at(a.sv_int.p, o_cc);
+#pragma unroll
+      for (int m = 0; m < NW; ++m) {
+        xs[m] = m == E ? wsu[E - 1] : __ldg(psu + (m - E));
+        ys[m] = m == E ? wsv[E - 1] : __ldg(psv + (m - E));
+      }
+    }
+    const double fx_su = F::eval_v(uq, xs);
+    const double fx_sv = F::eval_v(uq, ys);
+    const double fx_su_p = __shfl_down_sync(0xffffffffu, fx_su, 1);
+    const double fx_sv_p = __shfl_down_sync(0xffffffffu, fx_sv, 1);
+
+    // ---- point update (prognostics/utils.py:L191-L204)
+    const bool interior = col_int && r >= nb && r < ny - nb;
+    double s = cur.s_pre, su = 0.0, sv = 0.0;
     if (interior) {
-      const FaceVel w = face_velocities<SCHEME>(a.u_int, a.v_int, i, j, k, a.fc);
-      const double div = flux_divergence<SCHEME>(w, a.s_int, i, j, k, a.fc);
-      v = a.s_now.ld(i, j, k) - a.dt * (div - 0.0);
-    } else {
-      v = a.s_new(i, j, k);  // untouched by K1; the relaxation below decides
+      {
+        const double div = (fx_su_p - fx_su) / a.fc.dx + (fy_su_p - fy_su) / a.fc.dy;
+        const double *pmn = ptr_at(a.mtg_now.p, o_cc), *pmw = ptr_at(a.mtg.p, o_cc);
+        const double pg_now = one_m_eps * cur.s_now * (__ldg(pmn + 1) - __ldg(pmn - 1)) / a.two_dx;
+        const double pg_new = a.eps * s * (__ldg(pmw + 1) - __ldg(pmw - 1)) / a.two_dx;
+        su = cur.su_now - a.dt * (div + pg_now + pg_new - 0.0);
+      }
+      {
+        const double div = (fx_sv_p - fx_sv) / a.fc.dx + (fy_sv_p - fy_sv) / a.fc.dy;
+        const double pg_now = one_m_eps * cur.s_now * (cur.mn_p - mn_m) / a.two_dy;
+        const double pg_new = a.eps * s * (cur.mw_p - mw_m) / a.two_dy;
+        sv = cur.sv_now - a.dt * (div + pg_now + pg_new - 0.0);
+      }
     }
-    if (gam != 0.0) v = relax_point(gam, v, a.s_ref.ld(i, j, k));
-    a.s_new(i, j, k) = v;
-    p = p + gdz * v;
-    a.exn(i, j, k) = a.cp * pow(p / a.cpref, kappa);
-  }
-  // upward sweep, diagnostics.py:L433-L438
-  const double ex_s = a.exn(i, j, a.nz - 1);
-  const double mtg_s = a.theta_s * ex_s + a.g * a.hs.ld(i, j, 0);
-  double m = mtg_s + 0.5 * a.dz * ex_s;
-  a.mtg(i, j, a.nz - 1) = m;
-  for (int k = a.nz - 2; k >= 0; --k) {
-    m = m + a.dz * a.exn(i, j, k);
-    a.mtg(i, j, k) = m;
-  }
-}
+    const double gam = cur.gam;
+    double s_ref = 0.0, su_ref = 0.0, sv_ref = 0.0;
+    if (gam != 0.0 || r_damp != 0.0) {
+      s_ref = ldo(a.s_ref.p, o_cm);
+      su_ref = ldo(a.su_ref.p, o_cm);
+      sv_ref = ldo(a.sv_ref.p, o_cm);
+    }
+    if (!interior && gam != 1.0) {  // not reached with a Relaxed boundary (gamma == 1 there)
+      su = ldo(a.su_new.p, o_cm);
+      sv = ldo(a.sv_new.p, o_cm);
+    }
+    if (gam != 0.0) {  // hb.enforce_raw, dycore.py:L686
+      s = relax_point(gam, s, s_ref);
+      su = relax_point(gam, su, su_ref);
+      sv = relax_point(gam, sv, sv_ref);
+    }
+    if (r_damp != 0.0) {  // dycore.py:L694-L700
+      s = damp_point(cur.s_now, s, s_ref, r_damp, a.dt_full);
+      su = damp_point(cur.su_now, su, su_ref, r_damp, a.dt_full);
+      sv = damp_point(cur.sv_now, sv, sv_ref, r_damp, a.dt_full);
+    }
 
-// ---------------------------------------------------------------- kernel M
-template <int SCHEME>
-__global__ void __launch_bounds__(256) stage_m_kernel(const StageArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = blockIdx.z;
-  if (i >= a.nx || j >= a.ny) return;
-  const bool interior = i >= a.nb && i < a.nx - a.nb && j >= a.nb && j < a.ny - a.nb;
-  const double gam = a.gamma.ld(i, j, 0);
-  const double r = a.damp ? a.rmat.ld(0, 0, k) : 0.0;
-
-  double s = a.s_new(i, j, k);  // s_pre written by kernel S
-  double su, sv;
-  const bool need_now = interior || r != 0.0;
-  const double s_now = need_now ? a.s_now.ld(i, j, k) : 0.0;
-  const double su_now = need_now ? a.su_now.ld(i, j, k) : 0.0;
-  const double sv_now = need_now ? a.sv_now.ld(i, j, k) : 0.0;
-  if (interior) {
-    const FaceVel w = face_velocities<SCHEME>(a.u_int, a.v_int, i, j, k, a.fc);
-    // prognostics/utils.py:L191-L204
-    {
-      const double div = flux_divergence<SCHEME>(w, a.su_int, i, j, k, a.fc);
-      const double pg_now = (1.0 - a.eps) * s_now *
-                            (a.mtg_now.ld(i + 1, j, k) - a.mtg_now.ld(i - 1, j, k)) / a.two_dx;
-      const double pg_new =
-          a.eps * s * (a.mtg.ld(i + 1, j, k) - a.mtg.ld(i - 1, j, k)) / a.two_dx;
-      su = su_now - a.dt * (div + pg_now + pg_new - 0.0);
+    // ---- velocity diagnosis (dwarfs/diagnostics.py:L219-L272) and stores
+    const double su_l = __shfl_up_sync(0xffffffffu, su, 1);
+    const double s_l = __shfl_up_sync(0xffffffffu, s, 1);
+    if (out_lane && r >= j0) {
+      sto(a.s_new.p, o_cm, s);
+      sto(a.su_new.p, o_cm, su);
+      sto(a.sv_new.p, o_cm, sv);
+      sto(a.u_new.p, o_cm, c == 0 ? ldo(a.u_ref.p, o_cm) : (su_l + su) / (s_l + s));
+      if (c == nx - 1) sto(a.u_new.p, o_cm + 8u, ldo(a.u_ref.p, o_cm + 8u));  // relaxed.py:L161-L175
+      sto(a.v_new.p, o_cm, r == 0 ? ldo(a.v_ref.p, o_cm) : (sv_prev + sv) / (s_prev + s));
+      if (r == ny - 1) sto(a.v_new.p, o_cm + row, ldo(a.v_ref.p, o_cm + row));  // relaxed.py:L177-L191
     }
-    {
-      const double div = flux_divergence<SCHEME>(w, a.sv_int, i, j, k, a.fc);
-      const double pg_now = (1.0 - a.eps) * s_now *
-                            (a.mtg_now.ld(i, j + 1, k) - a.mtg_now.ld(i, j - 1, k)) / a.two_dy;
-      const double pg_new =
-          a.eps * s * (a.mtg.ld(i, j + 1, k) - a.mtg.ld(i, j - 1, k)) / a.two_dy;
-      sv = sv_now - a.dt * (div + pg_now + pg_new - 0.0);
-    }
-  } else {
-    su = a.su_new(i, j, k);
-    sv = a.sv_new(i, j, k);
-  }
-  const bool need_ref = gam != 0.0 || r != 0.0;
-  const double s_ref = need_ref ? a.s_ref.ld(i, j, k) : 0.0;
-  const double su_ref = need_ref ? a.su_ref.ld(i, j, k) : 0.0;
-  const double sv_ref = need_ref ? a.sv_ref.ld(i, j, k) : 0.0;
-  if (gam != 0.0) {  // hb.enforce_raw, dycore.py:L686
-    s = relax_point(gam, s, s_ref);
-    su = relax_point(gam, su, su_ref);
-    sv = relax_point(gam, sv, sv_ref);
-  }
-  if (r != 0.0) {  // dycore.py:L694-L700 (R == 0 leaves the value unchanged bit for bit)
-    s = damp_point(s_now, s, s_ref, r, a.dt_full);
-    su = damp_point(su_now, su, su_ref, r, a.dt_full);
-    sv = damp_point(sv_now, sv, sv_ref, r, a.dt_full);
-  }
-  a.s_new(i, j, k) = s;
-  a.su_new(i, j, k) = su;
-  a.sv_new(i, j, k) = sv;
-}
-
-// ---------------------------------------------------------------- kernel V
-__global__ void __launch_bounds__(256) stage_v_kernel(const StageArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = blockIdx.z;
-  if (i > a.nx || j > a.ny) return;
-  // dwarfs/diagnostics.py:L219-L272 + relaxed.py:L161-L191
-  const bool in_i = i < a.nx, in_j = j < a.ny;
-  double s = 0.0, su = 0.0, sv = 0.0;
-  if (in_i && in_j) {
-    s = a.s_new(i, j, k);
-    su = a.su_new(i, j, k);
-    sv = a.sv_new(i, j, k);
-  }
-  if (in_j) {
-    double u;
-    if (i == 0 || i == a.nx) {
-      u = a.u_ref.ld(i, j, k);
-    } else {
-      u = (a.su_new(i - 1, j, k) + su) / (a.s_new(i - 1, j, k) + s);
-    }
-    a.u_new(i, j, k) = u;
-  }
-  if (in_i) {
-    double v;
-    if (j == 0 || j == a.ny) {
-      v = a.v_ref.ld(i, j, k);
-    } else {
-      v = (a.sv_new(i, j - 1, k) + sv) / (a.s_new(i, j - 1, k) + s);
-    }
-    a.v_new(i, j, k) = v;
+    sv_prev = sv;
+    s_prev = s;
+    fy_su = fy_su_p;
+    fy_sv = fy_sv_p;
+    mn_m = mn_0; mn_0 = cur.mn_p;
+    mw_m = mw_0; mw_0 = cur.mw_p;
+    o_cc += row; o_cm += row; o_g += grow;
   }
 }
 
@@ -186,17 +364,12 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
     if (rc) return rc;
   }
   {
-    dim3 block(64, 4, 1);
-    dim3 grid((a.nx + 63) / 64, (a.ny + 3) / 4, a.nz);
-    stage_m_kernel<SCHEME><<<grid, block, 0, st>>>(a);
-    int rc = check_launch("isentropic_stage_dry/M");
-    if (rc) return rc;
-  }
-  {
-    dim3 block(64, 4, 1);
-    dim3 grid((a.nx + 1 + 63) / 64, (a.ny + 1 + 3) / 4, a.nz);
-    stage_v_kernel<<<grid, block, 0, st>>>(a);
-    return check_launch("isentropic_stage_dry/V");
+    constexpr int LJ = 64, WARPS = 4;
+    const int chunks = (a.nx + MV_COLS - 1) / MV_COLS;
+    dim3 block(32 * WARPS, 1, 1);
+    dim3 grid((chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
+    stage_mv_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
+    return check_launch("isentropic_stage_dry/MV");
   }
 }
 
@@ -214,7 +387,7 @@ extern "C" int tb200_isentropic_stage_dry(
     tb200_field *u_new, tb200_field *v_new, const tb200_field *s_ref, const tb200_field *su_ref,
     const tb200_field *sv_ref, const tb200_field *u_ref, const tb200_field *v_ref,
     const tb200_field *gamma, const tb200_field *rmat, const tb200_field *hs,
-    tb200_field *scratch_exn, tb200_field *scratch_mtg, void *stream) {
+    tb200_field *scratch_exn, tb200_field *scratch_mtg, tb200_field *scratch_s, void *stream) {
   TB200_REQUIRE(cfg != nullptr, "isentropic_stage_dry: NULL cfg");
   StageArgs a{};
   a.s_now = view(s_now); a.su_now = view(su_now); a.sv_now = view(sv_now);
@@ -226,7 +399,7 @@ extern "C" int tb200_isentropic_stage_dry(
   a.s_ref = view(s_ref); a.su_ref = view(su_ref); a.sv_ref = view(sv_ref);
   a.u_ref = view(u_ref); a.v_ref = view(v_ref);
   a.gamma = view(gamma); a.rmat = view(rmat); a.hs = view(hs);
-  a.exn = view(scratch_exn); a.mtg = view(scratch_mtg);
+  a.exn = view(scratch_exn); a.mtg = view(scratch_mtg); a.spre = view(scratch_s);
   a.nx = cfg->nx; a.ny = cfg->ny; a.nz = cfg->nz; a.nb = cfg->nb; a.damp = cfg->damp;
   a.dt = cfg->dt; a.dt_full = cfg->dt_full; a.dx = cfg->dx; a.dy = cfg->dy; a.dz = cfg->dz;
   a.eps = cfg->eps; a.pt = cfg->pt; a.theta_s = cfg->theta_s;
@@ -249,9 +422,20 @@ extern "C" int tb200_isentropic_stage_dry(
                 "isentropic_stage_dry: need nb >= extent and nx, ny >= 2 nb + 1");
   const View *mass[] = {&a.s_now, &a.su_now, &a.sv_now, &a.mtg_now, &a.s_int, &a.su_int,
                         &a.sv_int, &a.s_new,  &a.su_new, &a.sv_new,  &a.s_ref, &a.su_ref,
-                        &a.sv_ref, &a.exn,    &a.mtg};
+                        &a.sv_ref, &a.exn,    &a.mtg,    &a.spre};
   for (const View *v : mass)
     TB200_REQUIRE(covers(*v, nx, ny, nz), "isentropic_stage_dry: a mass-point field is NULL or too small");
+  {
+    const View *all[] = {&a.s_now, &a.su_now, &a.sv_now, &a.mtg_now, &a.s_int, &a.su_int, &a.sv_int,
+                         &a.u_int, &a.v_int, &a.s_new, &a.su_new, &a.sv_new, &a.u_new, &a.v_new,
+                         &a.s_ref, &a.su_ref, &a.sv_ref, &a.u_ref, &a.v_ref, &a.exn, &a.mtg, &a.spre};
+    for (const View *v : all) {
+      if (v->ok() && v->s0 != 1) {
+        set_error("isentropic_stage_dry: fields must have unit stride along i (b200 storage layout)");
+        return TB200_ERR_LAYOUT;
+      }
+    }
+  }
   TB200_REQUIRE(covers(a.u_int, nx + 1, ny, nz) && covers(a.u_new, nx + 1, ny, nz) &&
                     covers(a.u_ref, nx + 1, ny, nz),
                 "isentropic_stage_dry: u fields must cover (nx+1, ny, nz)");
@@ -264,6 +448,20 @@ extern "C" int tb200_isentropic_stage_dry(
   TB200_REQUIRE(a.s_new.p != a.s_int.p && a.su_new.p != a.su_int.p && a.sv_new.p != a.sv_int.p &&
                     a.s_new.p != a.s_now.p && a.u_new.p != a.u_int.p && a.v_new.p != a.v_int.p,
                 "isentropic_stage_dry: output fields must not alias the stage inputs");
+  {
+    const View *all[] = {&a.s_now, &a.su_now, &a.sv_now, &a.mtg_now, &a.s_int, &a.su_int, &a.sv_int,
+                         &a.u_int, &a.v_int, &a.s_new, &a.su_new, &a.sv_new, &a.u_new, &a.v_new,
+                         &a.s_ref, &a.su_ref, &a.sv_ref, &a.u_ref, &a.v_ref, &a.exn, &a.mtg, &a.spre};
+    for (const View *v : all) {
+      if (v->s1 != a.s_now.s1 || v->s2 != a.s_now.s2 || v->n2 < nz + 1 || v->n1 < ny + 1 ||
+          v->s2 < v->s1 * (ny + 1) || (long long)v->s2 * v->n2 * 8 >= (1LL << 32)) {
+        set_error("isentropic_stage_dry: all 3-D fields must share one geometry (equal row/plane "
+                  "strides, >= nz+1 planes of >= ny+1 rows, < 4 GiB) -- allocate them with the "
+                  "b200 allocator and one storage shape");
+        return TB200_ERR_LAYOUT;
+      }
+    }
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (cfg->flux_scheme) {
     case TB200_FLUX_UPWIND: return run_stage<TB200_FLUX_UPWIND>(a, st);

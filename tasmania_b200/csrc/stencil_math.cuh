@@ -32,6 +32,10 @@ struct Flux<TB200_FLUX_UPWIND> {  // horizontal_fluxes/upwind.py:L32-L39
   __device__ __forceinline__ static double face(double w, const double *ph, long long st) {
     return w * (w > 0.0 ? __ldg(ph - st) : __ldg(ph));
   }
+  // v[0 .. 2e-1] = phi[f-e .. f+e-1]
+  __device__ __forceinline__ static double eval_v(double w, const double *v) {
+    return w * (w > 0.0 ? v[0] : v[1]);
+  }
 };
 
 template <>
@@ -40,6 +44,9 @@ struct Flux<TB200_FLUX_CENTERED> {  // horizontal_fluxes/centered.py:L173-L202
   __device__ __forceinline__ static double prep(double w, const FluxConst &) { return w * 0.5; }
   __device__ __forceinline__ static double face(double wq, const double *ph, long long st) {
     return wq * (__ldg(ph - st) + __ldg(ph));
+  }
+  __device__ __forceinline__ static double eval_v(double wq, const double *v) {
+    return wq * (v[0] + v[1]);
   }
 };
 
@@ -55,6 +62,9 @@ struct Flux<TB200_FLUX_THIRD_ORDER_UPWIND> {  // horizontal_fluxes/third_order_u
   __device__ __forceinline__ static double face(double wq, const double *ph, long long st) {
     return eval(wq, __ldg(ph - 2 * st), __ldg(ph - st), __ldg(ph), __ldg(ph + st));
   }
+  __device__ __forceinline__ static double eval_v(double wq, const double *v) {
+    return eval(wq, v[0], v[1], v[2], v[3]);
+  }
 };
 
 template <>
@@ -69,6 +79,9 @@ struct Flux<TB200_FLUX_FIFTH_ORDER_UPWIND> {  // horizontal_fluxes/fifth_order_u
   __device__ __forceinline__ static double face(double wq, const double *ph, long long st) {
     return eval(wq, __ldg(ph - 3 * st), __ldg(ph - 2 * st), __ldg(ph - st), __ldg(ph),
                 __ldg(ph + st), __ldg(ph + 2 * st));
+  }
+  __device__ __forceinline__ static double eval_v(double wq, const double *v) {
+    return eval(wq, v[0], v[1], v[2], v[3], v[4], v[5]);
   }
 };
 

@@ -13,7 +13,7 @@ orchestration that stays in tasmania).  Two execution paths produce the same num
 * the *stencil* path issues one launch per reference stencil, exactly as the reference does
   (works for every boundary type, moist or dry);
 * the *fused* path (dry, relaxed boundary -- the benchmark configuration) runs a whole RK
-  stage in three kernels through ``tb200_isentropic_stage_dry``.
+  stage in two kernels through ``tb200_isentropic_stage_dry``.
 """
 from __future__ import annotations
 
@@ -331,7 +331,7 @@ class IsentropicDynamicalCore(StencilFactory):
         if stage == 0:
             pr._now = {n: state[n] for n in (S, MTG, SU, SV)}
         if self._scratch is None:
-            self._scratch = (self.zeros(shape=self.storage_shape), self.zeros(shape=self.storage_shape))
+            self._scratch = tuple(self.zeros(shape=self.storage_shape) for _ in range(3))
         dtr, dt = pr.substep(stage, timestep)
         cfg = lib.StageCfg()
         cfg.nx, cfg.ny, cfg.nz, cfg.nb = g.nx, g.ny, g.nz, hb.nb
@@ -352,7 +352,7 @@ class IsentropicDynamicalCore(StencilFactory):
             f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
             f(ref[S]), f(ref[SU]), f(ref[SV]), f(ref[U]), f(ref[V]),
             f(hb._gamma2d), f(rmat), f(pr._diagnostics._topo2d),
-            f(self._scratch[0]), f(self._scratch[1]), lib.current_stream())
+            f(self._scratch[0]), f(self._scratch[1]), f(self._scratch[2]), lib.current_stream())
         lib.check(rc, "tb200_isentropic_stage_dry")
         if "time" in state:
             out_state["time"] = state["time"] + dtr
