@@ -169,51 +169,79 @@ extern "C" int tb200_step_forward_euler_momentum(
 }
 
 // ---------------------------------------------------------------------------- K3
-// One thread per column.  WHAT: 0 montgomery, 1 diagnostic_variables (p, exn, mtg, h).
-// The Exner values of the column are parked in the output storages themselves between the
-// downward pressure scan and the upward scans, so no scratch is needed: for montgomery,
-// mtg[k-1] holds exn[k] until the upward scan overwrites it -- exactly the order in which
-// the values are consumed.
+// One thread per column (i along the warp: every level is a coalesced row access).
+// WHAT: 0 montgomery, 1 diagnostic_variables (p, exn, mtg, h).
+//
+// Two sweeps, both with running per-field pointers (one add per level, arbitrary strides):
+//   down: p[k] = p[k-1] + g dz s[k-1]  -- a serial chain of one multiply-add per level, no
+//         libm call; p is parked in its output storage (WHAT 1) or in mtg (WHAT 0);
+//   up:   exn[k] = cp (p[k]/pref)^kappa evaluated on the way up, where the calls for
+//         successive levels are independent of the cheap serial sums and pipeline;
+//         mtg and h are both accumulated in this single upward pass with (p, exn) of level
+//         k+1 carried in registers.
+// HBM traffic (WHAT 1): read s, write p, read p, write exn, mtg, h = 48 B/point.
 template <int WHAT>
 static int run_k3(View theta, View hs, View s, View p, View exn, View mtg, View h, double dz,
                   double pt, double theta_s, double pref, double rd, double g, double cp,
                   const int32_t o[3], const int32_t d[3], cudaStream_t st) {
-  const int i0 = o[0], j0 = o[1], k0 = o[2], k1 = o[2] + d[2];
+  const int i0 = o[0], j0 = o[1], k0 = o[2], nk = d[2];
   const double kappa = rd / cp;
   const CDiv cpref = make_cdiv(pref);
+  const double gdz = g * dz, cpg = cp * g;
+  View park = WHAT == 1 ? p : mtg;  // where the pressures wait for the upward sweep
   return launch_columns("isentropic_diagnostics", d[0], d[1], st, [=] __device__(int i, int j) {
     i += i0; j += j0;
-    // downward pressure scan, diagnostics.py:L339-L345 / L425-L431
+    // ---- downward pressure scan, diagnostics.py:L339-L342 / L425-L428
+    const double *ps = &s(i, j, k0);
+    double *pp = &park(i, j, k0);
     double pk = pt;
-    for (int k = k0; k < k1; ++k) {
-      if (k > k0) pk = pk + g * dz * s(i, j, k - 1);
-      if (WHAT == 1) {
-        p(i, j, k) = pk;
-        exn(i, j, k) = cp * pow(pk / cpref, kappa);
-      } else if (k > k0) {
-        mtg(i, j, k - 1) = cp * pow(pk / cpref, kappa);  // park exn[k] in mtg[k-1]
+    if (WHAT == 1) *pp = pk;  // montgomery never needs p[k0]
+    for (int k = 1; k < nk; ++k) {
+      pk = pk + gdz * *ps;
+      ps += s.s2;
+      // WHAT 0 parks p[k] in mtg[k-1]: the upward scan consumes it just before overwriting
+      if (WHAT == 1) pp += park.s2;
+      *pp = pk;
+      if (WHAT == 0) pp += park.s2;
+    }
+    // ---- upward sweep.  pb, eb = pressure and Exner function of level k+1
+    const int kt = k0 + nk - 1;
+    double pb = pk;
+    double eb = cp * pow_pos(pb / cpref, kappa);
+    const double th_s = WHAT == 1 ? theta(i, j, kt) : theta_s;
+    const double mtg_s = th_s * eb + g * hs(i, j, kt);  // L347 / L434
+    double m = mtg_s + 0.5 * dz * eb;
+    double *pm = &mtg(i, j, kt - 1);
+    if (WHAT == 0) {
+      *pm = m;
+      for (int k = kt - 2; k >= k0; --k) {
+        pm -= mtg.s2;
+        const double e = cp * pow_pos(*pm / cpref, kappa);  // exn[k+1] from the parked p[k+1]
+        m = m + dz * e;
+        *pm = m;
       }
-    }
-    // upward Montgomery scan, diagnostics.py:L347-L351 / L433-L438
-    const double th_s = WHAT == 1 ? theta(i, j, k1 - 1) : theta_s;
-    const double ex_s = WHAT == 1 ? exn(i, j, k1 - 1) : mtg(i, j, k1 - 2);
-    const double mtg_s = th_s * ex_s + g * hs(i, j, k1 - 1);
-    double m = mtg_s + 0.5 * dz * ex_s;
-    mtg(i, j, k1 - 2) = m;
-    for (int k = k1 - 3; k >= k0; --k) {
-      const double ex = WHAT == 1 ? exn(i, j, k + 1) : mtg(i, j, k);
-      m = m + dz * ex;
-      mtg(i, j, k) = m;
-    }
-    if (WHAT == 1) {
-      // upward height scan, diagnostics.py:L353-L360
-      double hk = hs(i, j, k1 - 1);
-      h(i, j, k1 - 1) = hk;
-      for (int k = k1 - 2; k >= k0; --k) {
-        const double pa = p(i, j, k), pb = p(i, j, k + 1);
-        hk = hk - rd * (theta(i, j, k) * exn(i, j, k) + theta(i, j, k + 1) * exn(i, j, k + 1)) *
-                      (pa - pb) / (cp * g * (pa + pb));
-        h(i, j, k) = hk;
+    } else {
+      const double *pth = &theta(i, j, kt);
+      double *pe = &exn(i, j, kt), *ph = &h(i, j, kt);
+      pp = &park(i, j, kt);
+      double thb = *pth;
+      double hk = hs(i, j, kt);  // L354
+      *pe = eb;
+      *ph = hk;
+      for (int k = kt - 1; k >= k0; --k) {
+        pp -= park.s2; pe -= exn.s2; ph -= h.s2; pth -= theta.s2;
+        const double pa = *pp;
+        const double ea = cp * pow_pos(pa / cpref, kappa);
+        const double tha = *pth;
+        *pe = ea;
+        // mtg[k] = mtg[k+1] + dz exn[k+1]; the first one (k = kt-1) is m itself
+        if (k < kt - 1) m = m + dz * eb;
+        *pm = m;
+        pm -= mtg.s2;
+        // L356-L360
+        hk = hk - rd * (tha * ea + thb * eb) * (pa - pb) / (cpg * (pa + pb));
+        *ph = hk;
+        pb = pa; eb = ea; thb = tha;
       }
     }
   });
@@ -279,12 +307,12 @@ extern "C" int tb200_height(const tb200_field *in_theta, const tb200_field *in_h
                             if (k < k1 - 1) h(i, j, k) = pk;  // park p[k]
                           }
                           double pb = pk;  // p[k1-1]
-                          double eb = cp * pow(pb / cpref, kappa);
+                          double eb = cp * pow_pos(pb / cpref, kappa);
                           double hk = hs(i, j, k1 - 1);
                           h(i, j, k1 - 1) = hk;
                           for (int k = k1 - 2; k >= k0; --k) {
                             const double pa = h(i, j, k);
-                            const double ea = cp * pow(pa / cpref, kappa);
+                            const double ea = cp * pow_pos(pa / cpref, kappa);
                             hk = hk - rd * (th(i, j, k) * ea + th(i, j, k + 1) * eb) * (pa - pb) /
                                           (cp * g * (pa + pb));
                             h(i, j, k) = hk;

@@ -42,6 +42,24 @@ struct StageArgs {
   CDiv two_dx, two_dy, cpref;
 };
 
+// All 3-D fields of a fused stage share one geometry (unit i-stride, equal row and plane
+// strides -- what the b200 allocator produces for equal shapes; checked on the host), so one
+// 32-bit running BYTE offset addresses every field: loads compile to
+// [uniform base + offset + immediate] with no per-load integer arithmetic.
+__device__ __forceinline__ double ldo(const double *base, unsigned off) {
+  return __ldg(reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off));
+}
+__device__ __forceinline__ void sto(double *base, unsigned off, double v) {
+  *reinterpret_cast<double *>(reinterpret_cast<char *>(base) + off) = v;
+}
+__device__ __forceinline__ const double *ptr_at(const double *base, unsigned off) {
+  return reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off);
+}
+// pull a line towards L2 ahead of its use (no register, no stall)
+__device__ __forceinline__ void prefetch_l2(const double *base, unsigned off) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(base) + off));
+}
+
 // ---------------------------------------------------------------- kernel S
 // Unit i-stride and 32-bit element offsets (a field has < 2^31 elements) keep the address
 // arithmetic off the critical path: one base pointer per field, immediate offsets along i.
@@ -80,9 +98,19 @@ __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
     const double *ps_old = a.s_new.p + (i + j * a.s_new.s1);
     double *pex = a.exn.p + (i + j * a.exn.s1);
     const int sj = (int)a.s_int.s1, svj = (int)a.v_int.s1;
+    const long long s2 = a.s_int.s2;  // plane stride (shared by all 3-D fields)
 #pragma unroll 2
     for (int k = 0; k < a.nz; ++k) {
       double v;
+      if (interior && k + 2 < a.nz) {  // DRAM -> L2 two levels ahead
+        prefetch_l2(ps_int + 2 * s2, 0);
+        prefetch_l2(ps_int + 2 * s2 - 3 * sj, 0);
+        prefetch_l2(ps_int + 2 * s2 + 3 * sj, 0);
+        prefetch_l2(ps_now + 2 * s2, 0);
+        prefetch_l2(pu + 2 * s2, 0);
+        prefetch_l2(pv + 2 * s2, 0);
+        prefetch_l2(pv + 2 * s2 + svj, 0);
+      }
       if (interior) {
         const FaceVel w{F::prep(__ldg(pu), a.fc), F::prep(__ldg(pu + 1), a.fc),
                         F::prep(__ldg(pv), a.fc), F::prep(__ldg(pv + svj), a.fc)};
@@ -105,7 +133,7 @@ __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
   {
     const double *pex = a.exn.p + (i + j * a.exn.s1 + (long long)(a.nz - 1) * a.exn.s2);
     double *pm = a.mtg.p + (i + j * a.mtg.s1 + (long long)(a.nz - 1) * a.mtg.s2);
-    const double ex_s = a.cp * pow(*pex / a.cpref, kappa);
+    const double ex_s = a.cp * pow_pos(*pex / a.cpref, kappa);
     const double mtg_s = a.theta_s * ex_s + a.g * a.hs.ld(i, j, 0);
     double m = mtg_s + 0.5 * a.dz * ex_s;
     *pm = m;
@@ -113,7 +141,7 @@ __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
     for (int k = a.nz - 2; k >= 0; --k) {
       pex -= a.exn.s2;
       pm -= a.mtg.s2;
-      m = m + a.dz * (a.cp * pow(*pex / a.cpref, kappa));
+      m = m + a.dz * (a.cp * pow_pos(*pex / a.cpref, kappa));
       *pm = m;
     }
   }
@@ -151,24 +179,6 @@ struct RowLoads {
   double mn_p, mw_p;  // mtg_now, mtg_new at row r+1
   double gam;         // relaxation coefficient at row r
 };
-
-// All 3-D fields of a fused stage share one geometry (unit i-stride, equal row and plane
-// strides -- what the b200 allocator produces for equal shapes; checked on the host), so one
-// 32-bit running BYTE offset addresses every field: loads compile to
-// [uniform base + offset + immediate] with no per-load integer arithmetic.
-__device__ __forceinline__ double ldo(const double *base, unsigned off) {
-  return __ldg(reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off));
-}
-__device__ __forceinline__ void sto(double *base, unsigned off, double v) {
-  *reinterpret_cast<double *>(reinterpret_cast<char *>(base) + off) = v;
-}
-__device__ __forceinline__ const double *ptr_at(const double *base, unsigned off) {
-  return reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off);
-}
-// pull a line towards L2 ahead of its use (no register, no stall)
-__device__ __forceinline__ void prefetch_l2(const double *base, unsigned off) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(base) + off));
-}
 
 template <int SCHEME, int LJ>
 __global__ void __launch_bounds__(128, 4) stage_mv_kernel(const StageArgs a) {

@@ -111,6 +111,17 @@ __device__ __forceinline__ double flux_divergence(const FaceVel &w, const View &
   return (fxp - fxm) / c.dx + (fyp - fym) / c.dy;
 }
 
+// ------------------------------------------------------------------ Exner function
+// exn = cp (p / pref)^kappa (isentropic/dynamics/diagnostics.py:L345).  For the positive
+// arguments met here x^kappa = exp2(kappa * log2(x)); CUDA's log2 and exp2 are 1-ulp
+// functions, which bounds the result's error by ~2 ulp -- the bound CUDA documents for its
+// own pow -- at less than half the instructions (pow spends most of its time on sign /
+// integer-exponent / infinity special cases).  The reference's glibc pow is < 1 ulp, so either
+// way the last bit may differ; parity tests hold K3 to 1e-13 and the 100-step run to 1e-12.
+__device__ __forceinline__ double pow_pos(double x, double kappa) {
+  return exp2(kappa * log2(x));
+}
+
 // ------------------------------------------------------------------ relaxation / damping
 // algorithms.py:L32-L43
 __device__ __forceinline__ double relax_point(double g, double phi, double ref) {
