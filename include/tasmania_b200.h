@@ -78,6 +78,9 @@ const char *tb200_last_error(void);
 int tb200_version(void);
 /* number of visible CUDA devices, or a negative error code */
 int tb200_device_count(void);
+/* kernels this library has launched since it was loaded (every successful launch counts;
+ * bench.py reports the difference over its timed region as `gpu_launches`) */
+long long tb200_launch_count(void);
 
 /* ---- K12 element-wise ------------------------------------------------------------- */
 int tb200_elementwise(int op, tb200_field *out, const tb200_field *a, const tb200_field *b,
@@ -227,6 +230,13 @@ int tb200_pack_box(const tb200_field *field, double *buffer, const int32_t origi
                    const int32_t domain[3], void *stream);
 int tb200_unpack_box(tb200_field *field, const double *buffer, const int32_t origin[3],
                      const int32_t domain[3], void *stream);
+/* the same box of `nfields` (<= TB200_HALO_MAX_FIELDS) fields in ONE launch; message layout
+ * [field][k][j][i], i fastest.  One side of a halo exchange = one pack + one unpack. */
+#define TB200_HALO_MAX_FIELDS 8
+int tb200_halo_pack(const tb200_field *const *fields, int nfields, double *buffer,
+                    const int32_t origin[3], const int32_t domain[3], void *stream);
+int tb200_halo_unpack(const tb200_field *const *fields, int nfields, const double *buffer,
+                      const int32_t origin[3], const int32_t domain[3], void *stream);
 
 #ifdef __cplusplus
 }

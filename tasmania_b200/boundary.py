@@ -72,15 +72,41 @@ class HorizontalBoundary(StencilFactory):
         raise NotImplementedError
 
 
+def relaxed_gamma_window(global_extent, offset, shape, rel):
+    """The relaxation coefficients of relaxed.py:L193-L247 on a window of the global grid, in
+    closed form: a point of ring ``m = min(i, j, NX-1-i, NY-1-j)`` gets ``rel[m]`` (corners take
+    the coefficient of the outer ring), the interior 0, and the extra staggered row / column
+    ``i == NX`` / ``j == NY`` gets 1.  Identical to the block-wise construction (checked in
+    tests/test_distributed_cpu.py)."""
+    nxg, nyg = global_extent
+    nr = len(rel)
+    i = np.arange(shape[0])[:, None] + offset[0]
+    j = np.arange(shape[1])[None, :] + offset[1]
+    ring = np.minimum(np.minimum(i, nxg - 1 - i), np.minimum(j, nyg - 1 - j))
+    inside = (i < nxg) & (j < nyg)
+    relx = np.concatenate((np.asarray(rel, dtype=float), [0.0]))
+    g = relx[np.clip(ring, 0, nr)]
+    g = np.where(inside, g, 0.0)
+    g = np.where(((i == nxg) & (j <= nyg)) | ((j == nyg) & (i <= nxg)), 1.0, g)
+    return g
+
+
 class Relaxed(HorizontalBoundary):
     """Relaxed boundary conditions (``ni = nx``, ``nj = ny``)."""
 
     type = "relaxed"
 
     def __init__(self, nx, ny, nz, nb, nr=8, backend_options=None, storage_options=None,
-                 storage_shape=None):
+                 storage_shape=None, global_extent=None, offset=(0, 0)):
+        """``global_extent=(NX, NY)`` and ``offset=(i0, j0)`` describe a sub-domain of a 2-D
+        decomposed grid (tasmania_b200.distributed): the object then handles the local
+        ``nx x ny`` window whose point (0, 0) is the global point (i0, j0), with the relaxation
+        coefficients of the *global* boundary."""
         assert nx > 1 and ny > 1
-        assert nr <= nx / 2 and nr <= ny / 2, "Depth of relaxation region cannot exceed n/2."
+        self._global = tuple(global_extent) if global_extent is not None else (int(nx), int(ny))
+        self._offset = (int(offset[0]), int(offset[1]))
+        nxg, nyg = self._global
+        assert nr <= nxg / 2 and nr <= nyg / 2, "Depth of relaxation region cannot exceed n/2."
         assert nr <= 8, "Depth of relaxation region cannot exceed 8."
         assert nb <= nr, "Number of boundary layers cannot exceed depth of relaxation region."
         super().__init__(nx, ny, nz, nb, backend_options, storage_options)
@@ -97,6 +123,12 @@ class Relaxed(HorizontalBoundary):
         nx, ny, nb, nr = self.nx, self.ny, self.nb, self.nr
         rel = np.array([1.0] + [1.0 - np.tanh(0.5 * m) for m in range(1, 8)])[:nr]
         rel[:nb] = 1.0
+        if self._global != (nx, ny) or self._offset != (0, 0):
+            g = relaxed_gamma_window(self._global, self._offset, self._shape[:2], rel)
+            g2d = storage.as_storage(g[:, :, None], device=self.storage_options.device)
+            self._gamma2d = g2d
+            self._gamma = storage.B200Array(g2d.t.expand(-1, -1, self._shape[2]))
+            return
         rrel = rel[::-1]
         g = np.zeros((self._shape[0], self._shape[1]))
         corner = np.zeros((nr, nr))

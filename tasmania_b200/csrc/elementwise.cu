@@ -4,6 +4,8 @@
 // i along threadIdx.x for coalescing.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "stencil_math.cuh"
 
 namespace tb200 {
@@ -14,11 +16,14 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace tb200
 
 using namespace tb200;
 
 extern "C" const char *tb200_last_error(void) { return g_err; }
+extern "C" long long tb200_launch_count(void) { return g_launches.load(); }
 extern "C" int tb200_version(void) { return 100; }
 extern "C" int tb200_device_count(void) {
   int n = 0;

@@ -1,0 +1,428 @@
+# -*- coding: utf-8 -*-
+"""2-D (x, y) domain decomposition of the isentropic dynamical core over the GPUs of one box
+(SURVEY.md section 8e).  The reference has no distributed code at all; this is the part
+``north_star`` adds.
+
+Layout.  The global numerical grid ``NX x NY`` is cut into ``px x py`` blocks, one process (one
+GPU) per block, x fastest in the rank order.  A rank's *local* grid is its owned block plus a
+halo of ``HALO = nb + 1 = 4`` columns / rows on every side that has a neighbour (no halo on
+physical boundaries, where the global relaxed boundary applies through the global relaxation
+coefficients, cf. ``boundary.Relaxed(global_extent=..., offset=...)``).  The vertical is never
+split: the column scans stay local.
+
+Why ``nb + 1``.  A fused RK stage (isentropic_fused.cu) is: step s -> column scans -> momentum
+step, and the momentum step reads the *new* Montgomery potential at i+-1 / j+-1.  Instead of a
+second exchange in the middle of the stage, every rank also steps s (and scans the column) on
+the first halo ring, which needs the stage inputs on ``nb`` more rings: one exchange of
+``s, su, sv, u, v`` (width 4) per stage, none for the Montgomery potential.  Because that ring's
+s-step reads the stage input on corner points, the exchange is done in two phases -- x faces
+first, then y faces *including* the freshly received x halos -- which fills the corners without
+diagonal messages.  Afterwards the velocity components on the two faces that separate owned
+points from halo points are re-diagnosed locally (``tb200_velocity`` on a one-face box): the
+fused kernel computed them from not-yet-exchanged momenta.
+
+Every owned point sees bit-identical inputs and executes the same operations as in a single
+-device run, so the decomposed result equals the single-device result **bitwise** -- the test
+in tests/test_gpu_distributed.py (in-process sub-domains on one GPU) and the world_size-2
+``gloo`` test of the exchange logic in tests/test_distributed_cpu.py.
+
+Transport.  One pack kernel per side and phase gathers the slab of all five fields into one
+message (``tb200_halo_pack``); messages travel with ``torch.distributed`` point-to-point ops
+(NCCL over NVLink / NVSwitch on the GPUs, grouped per phase); one unpack kernel per side
+scatters them.  There is no global reduction on the path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from datetime import datetime, timedelta
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from tasmania_b200 import lib, storage
+
+HALO = 4  # nb (fifth-order upwind: 3) + 1, see the module docstring
+
+
+def process_grid(world: int):
+    """1, 2, 4, 8 ranks -> 1x1, 2x1, 2x2, 4x2; otherwise the most
+    square factorisation with px >= py."""
+    py = int(np.floor(np.sqrt(world)))
+    while world % py:
+        py -= 1
+    return world // py, py
+
+
+def _split(n: int, parts: int):
+    """Even split of n points over `parts` blocks (the first n % parts blocks get one more)."""
+    base, rem = divmod(n, parts)
+    edges = [0]
+    for p in range(parts):
+        edges.append(edges[-1] + base + (1 if p < rem else 0))
+    return edges
+
+
+@dataclass
+class Side:
+    """One neighbour of one phase: where the outgoing slab is read and the incoming one lands
+    (local indices, (i0, j0) + (di, dj))."""
+
+    name: str
+    neighbour: int
+    send_origin: tuple
+    recv_origin: tuple
+    extent: tuple
+
+
+class Decomposition:
+    """Index bookkeeping of the block decomposition (pure Python, shared by every backend)."""
+
+    def __init__(self, nx_global: int, ny_global: int, px: int, py: int, halo: int = HALO):
+        self.NX, self.NY, self.px, self.py, self.halo = nx_global, ny_global, px, py, halo
+        self.xe, self.ye = _split(nx_global, px), _split(ny_global, py)
+        for e in (self.xe, self.ye):
+            if len(e) > 2:
+                assert min(b - a for a, b in zip(e[:-1], e[1:])) >= 2 * halo, \
+                    "blocks must be at least 2 * halo points wide"
+
+    @property
+    def world(self):
+        return self.px * self.py
+
+    def coords(self, rank):
+        return rank % self.px, rank // self.px
+
+    def rank_of(self, cx, cy):
+        if 0 <= cx < self.px and 0 <= cy < self.py:
+            return cy * self.px + cx
+        return None
+
+    def owned(self, rank):
+        cx, cy = self.coords(rank)
+        return self.xe[cx], self.xe[cx + 1], self.ye[cy], self.ye[cy + 1]
+
+    def halos(self, rank):
+        """(west, east, south, north) halo widths: `halo` towards a neighbour, 0 at a physical
+        boundary."""
+        cx, cy = self.coords(rank)
+        h = self.halo
+        return (h if cx > 0 else 0, h if cx < self.px - 1 else 0,
+                h if cy > 0 else 0, h if cy < self.py - 1 else 0)
+
+    def local(self, rank):
+        """Global index range covered by the local grid: (i0, i1, j0, j1)."""
+        i0, i1, j0, j1 = self.owned(rank)
+        hw, he, hs, hn = self.halos(rank)
+        return i0 - hw, i1 + he, j0 - hs, j1 + hn
+
+    def local_shape(self, rank):
+        i0, i1, j0, j1 = self.local(rank)
+        return i1 - i0, j1 - j0
+
+    def sides(self, rank, phase) -> List[Side]:
+        """Phase 0: x faces over all local rows; phase 1: y faces over all local columns."""
+        cx, cy = self.coords(rank)
+        nxl, nyl = self.local_shape(rank)
+        hw, he, hs, hn = self.halos(rank)
+        h = self.halo
+        out = []
+        if phase == 0:
+            if hw:
+                out.append(Side("west", self.rank_of(cx - 1, cy), (hw, 0), (0, 0), (h, nyl)))
+            if he:
+                out.append(Side("east", self.rank_of(cx + 1, cy), (nxl - he - h, 0), (nxl - he, 0),
+                                (h, nyl)))
+        else:
+            if hs:
+                out.append(Side("south", self.rank_of(cx, cy - 1), (0, hs), (0, 0), (nxl, h)))
+            if hn:
+                out.append(Side("north", self.rank_of(cx, cy + 1), (0, nyl - hn - h), (0, nyl - hn),
+                                (nxl, h)))
+        return out
+
+    def seam_faces(self, rank):
+        """Staggered faces between an owned and a halo point, whose velocity must be
+        re-diagnosed after the exchange: ([u face columns], [v face rows]), local indices."""
+        nxl, nyl = self.local_shape(rank)
+        hw, he, hs, hn = self.halos(rank)
+        return ([hw] if hw else []) + ([nxl - he] if he else []), \
+               ([hs] if hs else []) + ([nyl - hn] if hn else [])
+
+
+# ------------------------------------------------------------------ pack / unpack
+def _field_ptrs(fields):
+    keep = [lib.as_field(f) for f in fields]
+    import ctypes as C
+
+    arr = (lib.FieldP * len(keep))(*[C.pointer(k) for k in keep])
+    return arr, keep
+
+
+def _pack(fields, buf, origin, extent, nz):
+    if buf.is_cuda:
+        arr, keep = _field_ptrs(fields)
+        lib.check(lib.load().tb200_halo_pack(arr, len(fields), buf.data_ptr(),
+                                             lib.int3((origin[0], origin[1], 0)),
+                                             lib.int3((extent[0], extent[1], nz)),
+                                             lib.current_stream()), "tb200_halo_pack")
+        del keep
+    else:  # host tensors: only the exchange-logic tests (gloo) come here
+        i0, j0 = origin
+        di, dj = extent
+        view = buf.view(len(fields), nz, dj, di)
+        for n, f in enumerate(fields):
+            view[n].copy_(f.t[i0:i0 + di, j0:j0 + dj, :nz].permute(2, 1, 0))
+
+
+def _unpack(fields, buf, origin, extent, nz):
+    if buf.is_cuda:
+        arr, keep = _field_ptrs(fields)
+        lib.check(lib.load().tb200_halo_unpack(arr, len(fields), buf.data_ptr(),
+                                               lib.int3((origin[0], origin[1], 0)),
+                                               lib.int3((extent[0], extent[1], nz)),
+                                               lib.current_stream()), "tb200_halo_unpack")
+        del keep
+    else:
+        i0, j0 = origin
+        di, dj = extent
+        view = buf.view(len(fields), nz, dj, di)
+        for n, f in enumerate(fields):
+            f.t[i0:i0 + di, j0:j0 + dj, :nz].copy_(view[n].permute(2, 1, 0))
+
+
+class HaloExchange:
+    """The per-rank halo exchange of ``nfields`` fields: persistent message buffers, the
+    two-phase plan and the three steps (pack, transfer, unpack) of each phase.  ``transfer``
+    is either ``torch.distributed`` point-to-point (``exchange``) or done by the caller for
+    in-process sub-domains (``exchange_in_process``)."""
+
+    def __init__(self, decomp: Decomposition, rank: int, nz: int, nfields: int, device):
+        self.decomp, self.rank, self.nz, self.nfields = decomp, rank, nz, nfields
+        self.plan = [decomp.sides(rank, 0), decomp.sides(rank, 1)]
+        self.send, self.recv = {}, {}
+        for phase in self.plan:
+            for s in phase:
+                n = nfields * nz * s.extent[0] * s.extent[1]
+                self.send[s.name] = torch.empty(n, dtype=torch.float64, device=device)
+                self.recv[s.name] = torch.empty(n, dtype=torch.float64, device=device)
+        self.bytes_per_exchange = 8 * sum(b.numel() for b in self.send.values())
+
+    def pack(self, phase, fields):
+        for s in self.plan[phase]:
+            _pack(fields, self.send[s.name], s.send_origin, s.extent, self.nz)
+
+    def unpack(self, phase, fields):
+        for s in self.plan[phase]:
+            _unpack(fields, self.recv[s.name], s.recv_origin, s.extent, self.nz)
+
+    def transfer(self, phase):
+        import torch.distributed as dist
+
+        ops = []
+        for s in self.plan[phase]:
+            ops.append(dist.P2POp(dist.isend, self.send[s.name], s.neighbour))
+            ops.append(dist.P2POp(dist.irecv, self.recv[s.name], s.neighbour))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def exchange(self, fields: Sequence):
+        assert len(fields) == self.nfields
+        for phase in (0, 1):
+            self.pack(phase, fields)
+            self.transfer(phase)
+            self.unpack(phase, fields)
+
+
+_OPPOSITE = {"west": "east", "east": "west", "south": "north", "north": "south"}
+
+
+def exchange_in_process(exchangers: Sequence[HaloExchange], fields_per_rank: Sequence[Sequence]):
+    """All sub-domains live in this process (one GPU): a rank's outgoing message is unpacked
+    straight from the neighbour's send buffer."""
+    for phase in (0, 1):
+        for ex, fields in zip(exchangers, fields_per_rank):
+            ex.pack(phase, fields)
+        for ex, fields in zip(exchangers, fields_per_rank):
+            for s in ex.plan[phase]:
+                src = exchangers[s.neighbour].send[_OPPOSITE[s.name]]
+                _unpack(fields, src, s.recv_origin, s.extent, ex.nz)
+
+
+# ------------------------------------------------------------------ the decomposed dry core
+P, EXN, H = ("air_pressure_on_interface_levels", "exner_function_on_interface_levels",
+             "height_on_interface_levels")
+
+
+class SubdomainDryCore:
+    """One rank's share of the dry mountain-flow problem (BASELINE configs 2 / 5): local grid,
+    local window of the global topography / relaxation coefficients / initial state, the fused
+    dynamical core on it, and the per-stage halo exchange + seam-face velocity fix-up."""
+
+    def __init__(self, decomp: Decomposition, rank: int, nz: int, *, domain_x=(-176.0, 176.0),
+                 domain_y=(-176.0, 176.0), nb=3, nr=6, flux="fifth_order_upwind",
+                 scheme="rk3ws_si", damp_depth=15, damp_max=5e-4, dt_seconds=5.0,
+                 mountain=(500.0, 50.0, 50.0), topo_seconds=1800.0, device=None):
+        import tasmania_b200 as tb
+        from tasmania_b200.boundary import Relaxed
+        from tasmania_b200.grid import (Grid, Topography, gaussian_profile,
+                                        isentropic_state_from_brunt_vaisala)
+        from tasmania_b200.isentropic import (MTG, S, SU, SV, U, V, IsentropicDiagnostics,
+                                              IsentropicDynamicalCore)
+
+        assert decomp.halo >= nb + 1 or decomp.world == 1
+        self.decomp, self.rank, self.nz = decomp, rank, nz
+        self.names = (S, SU, SV, U, V, MTG)
+        self.out_names = (S, SU, U, SV, V)
+        self.S, self.SU, self.SV, self.U, self.V, self.MTG = S, SU, SV, U, V, MTG
+        NX, NY = decomp.NX, decomp.NY
+        gi0, gi1, gj0, gj1 = decomp.local(rank)
+        nx, ny = gi1 - gi0, gj1 - gj0
+        self.nx, self.ny = nx, ny
+        self.owned_points = (decomp.owned(rank)[1] - decomp.owned(rank)[0]) * \
+                            (decomp.owned(rank)[3] - decomp.owned(rank)[2]) * nz
+        # global axes (native units: km), local windows of them
+        xg = np.linspace(domain_x[0], domain_x[1], NX)
+        yg = np.linspace(domain_y[0], domain_y[1], NY)
+        full = Grid(domain_x, NX, domain_y, NY, (400.0, 280.0), nz, units_to_m=1e3)
+        steady = gaussian_profile(xg[gi0:gi1], yg[gj0:gj1], mountain[0], mountain[1], mountain[2],
+                                  center_x=0.5 * (xg[0] + xg[-1]), center_y=0.5 * (yg[0] + yg[-1]))
+        grid = Grid((xg[gi0], xg[gi1 - 1]), nx, (yg[gj0], yg[gj1 - 1]), ny, (400.0, 280.0), nz,
+                    units_to_m=1e3, x=xg[gi0:gi1], y=yg[gj0:gj1],
+                    topography=Topography(steady, timedelta(seconds=topo_seconds)))
+        # grid spacings are those of the GLOBAL grid, bit for bit
+        grid.dx_native, grid.dy_native, grid.dx, grid.dy = full.dx_native, full.dy_native, full.dx, full.dy
+        self.grid = grid
+        # horizontally uniform initial state: one column, broadcast
+        small = Grid(domain_x, 3, domain_y, 3, (400.0, 280.0), nz, units_to_m=1e3)
+        col = isentropic_state_from_brunt_vaisala(small, 22.5, 0.0, 0.015)
+        self.pt = float(col[P][0, 0, 0])
+        so = tb.StorageOptions(device=device)
+        state = {}
+        for name, a in col.items():
+            arr = np.zeros((nx + 1, ny + 1, nz + 1))
+            # staggered extents in GLOBAL terms: the extra face exists on the last block only
+            mi = min(nx + 1, (NX + 1 if "at_u_locations" in name else NX) - gi0)
+            mj = min(ny + 1, (NY + 1 if "at_v_locations" in name else NY) - gj0)
+            arr[:mi, :mj, :] = a[1, 1, :][None, None, :]
+            state[name] = tb.as_storage(arr, device=device)
+        state["time"] = datetime(2000, 1, 1)
+        self.state = state
+        self.dt = timedelta(seconds=dt_seconds)
+        self.hb = Relaxed(nx, ny, nz, nb, nr=nr, storage_options=so, global_extent=(NX, NY),
+                          offset=(gi0, gj0))
+        self.hb.reference_state = state
+        self.dyc = IsentropicDynamicalCore(
+            grid, self.hb, time_integration_scheme=scheme, horizontal_flux_scheme=flux,
+            time_integration_properties={"pt": self.pt, "eps": 0.5}, damp=True,
+            damp_depth=damp_depth, damp_max=damp_max, storage_options=so)
+        assert self.dyc._fused
+        self.diag = IsentropicDiagnostics(grid, storage_options=so)
+        self.spare = {n: tb.zeros(self.dyc.storage_shape, device=device) for n in self.out_names}
+        dev = state[S].t.device
+        self.halo = HaloExchange(decomp, rank, nz, 5, dev)
+        self.u_faces, self.v_faces = decomp.seam_faces(rank)
+        self.nstep = 0
+
+    # ---- pieces of a step (driven stage by stage so that sub-domains can interleave)
+    def exchange_fields(self, out):
+        return [out[n] for n in (self.S, self.SU, self.SV, self.U, self.V)]
+
+    def fix_seam_velocities(self, out):
+        """u on the faces between owned and halo columns, v likewise in y, from the exchanged
+        s, su, sv (dwarfs/diagnostics.py:L219-L272, same formula as the fused kernel)."""
+        vc = self.dyc._velocity_components
+        for i in self.u_faces:
+            vc._stencil_diagnosing_velocity_x(in_d=out[self.S], in_du=out[self.SU], out_u=out[self.U],
+                                              origin=(i, 0, 0), domain=(1, self.ny, self.nz))
+        for j in self.v_faces:
+            vc._stencil_diagnosing_velocity_y(in_d=out[self.S], in_dv=out[self.SV], out_v=out[self.V],
+                                              origin=(0, j, 0), domain=(self.nx, 1, self.nz))
+
+    def begin_step(self):
+        self.nstep += 1
+        self.dyc.update_topography(self.nstep * self.dt)
+        return self.dyc.stages_iter(self.state, {}, self.dt, out_state=self.spare)
+
+    def end_step(self, out):
+        new = {n: out[n] for n in self.out_names}
+        new["time"] = out["time"]
+        for n in (P, EXN, H, self.MTG):
+            new[n] = self.state[n]
+        self.spare = {n: self.state[n] for n in self.out_names}
+        self.diag.get_diagnostic_variables(new[self.S], self.pt, new[P], new[EXN], new[self.MTG], new[H])
+        self.state = new
+
+    def owned_numpy(self, name):
+        """The owned block of a field on the host (for gathering / comparing)."""
+        hw, he, hs, hn = self.decomp.halos(self.rank)
+        a = storage.to_numpy(self.state[name])
+        return a[hw:self.nx - he, hs:self.ny - hn, :self.nz]
+
+
+class DecomposedDryRun:
+    """The timed loop of ``bench.py`` on N GPUs: one ``SubdomainDryCore`` per process,
+    ``torch.distributed`` (NCCL) halo exchange after every RK stage.  Weak scaling: every rank
+    owns ``nx x ny x nz`` points; the global domain grows with the process grid so that the
+    grid spacing -- and with it the physics per point -- stays (almost exactly) the same."""
+
+    def __init__(self, nx, ny, nz, rank, world, device=None):
+        px, py = process_grid(world)
+        self.decomposition = f"{px}x{py}"
+        self.decomp = Decomposition(nx * px, ny * py, px, py)
+        self.sub = SubdomainDryCore(self.decomp, rank, nz, domain_x=(-176.0 * px, 176.0 * px),
+                                    domain_y=(-176.0 * py, 176.0 * py), device=device)
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.names, self.out_names = self.sub.names, self.sub.out_names
+        self.dyc = self.sub.dyc
+        self.dyc.after_stage = self._after_stage
+
+    def _after_stage(self, stage, out):
+        self.sub.halo.exchange(self.sub.exchange_fields(out))
+        self.sub.fix_seam_velocities(out)
+
+    @property
+    def state(self):
+        return self.sub.state
+
+    def step(self):
+        out = None
+        for _, out in self.sub.begin_step():
+            pass
+        self.sub.end_step(out)
+
+
+class InProcessDecomposedRun:
+    """All sub-domains of a decomposition in ONE process on one device -- the bitwise-parity
+    harness of the decomposition (and a way to run a decomposed case without several GPUs)."""
+
+    def __init__(self, nx_global, ny_global, nz, px, py, device=None, **kwargs):
+        self.decomp = Decomposition(nx_global, ny_global, px, py)
+        self.subs = [SubdomainDryCore(self.decomp, r, nz, device=device, **kwargs)
+                     for r in range(px * py)]
+
+    def step(self):
+        iters = [s.begin_step() for s in self.subs]
+        outs = [None] * len(self.subs)
+        for _ in range(self.subs[0].dyc.stages):
+            for r, it in enumerate(iters):
+                outs[r] = next(it)[1]
+            exchange_in_process([s.halo for s in self.subs],
+                                [s.exchange_fields(o) for s, o in zip(self.subs, outs)])
+            for s, o in zip(self.subs, outs):
+                s.fix_seam_velocities(o)
+        for it in iters:  # exhaust the generators (sets the time label)
+            for _ in it:
+                pass
+        for s, o in zip(self.subs, outs):
+            s.end_step(o)
+
+    def gather(self, name):
+        """Assemble the global field from the owned blocks."""
+        d = self.decomp
+        out = np.zeros((d.NX, d.NY, self.subs[0].nz))
+        for s in self.subs:
+            i0, i1, j0, j1 = d.owned(s.rank)
+            out[i0:i1, j0:j1, :] = s.owned_numpy(name)
+        return out

@@ -273,6 +273,9 @@ class IsentropicDynamicalCore(StencilFactory):
         self._s_now = self._su_now = self._sv_now = None
         self._ref = None
         self._scratch = None
+        # hook run after every stage on that stage's output fields (halo exchange of a
+        # decomposed run); None on a single device
+        self.after_stage = None
 
     @property
     def stages(self):
@@ -358,7 +361,11 @@ class IsentropicDynamicalCore(StencilFactory):
             out_state["time"] = state["time"] + dtr
 
     # ---- framework/dycore.py:L383-L462
-    def __call__(self, state, tendencies, timestep, out_state=None):
+    def stages_iter(self, state, tendencies, timestep, out_state=None):
+        """Generator over the stages of one time step: each ``next()`` runs one stage and
+        yields ``(stage, stage_output_dict)``.  A domain-decomposed run advances all its
+        sub-domains stage by stage and exchanges halos in between
+        (tasmania_b200.distributed); ``__call__`` simply exhausts it."""
         if self._raw_stage_states is None:
             self._raw_stage_states = [self.allocate_stage_outputs() for _ in range(self.stages - 1)]
         out_state = out_state if out_state is not None else {}
@@ -370,7 +377,15 @@ class IsentropicDynamicalCore(StencilFactory):
         for stage in range(self.stages):
             # each stage sees its own dict (the moist path adds sq* entries to it)
             self.stage_array_call(stage, dict(cur), tendencies or {}, timestep, outs[stage])
+            if self.after_stage is not None:
+                self.after_stage(stage, outs[stage])
+            if stage == self.stages - 1 and "time" in state:
+                out_state["time"] = state["time"] + timestep
+            yield stage, outs[stage]
             cur = outs[stage]
-        if "time" in state:
-            out_state["time"] = state["time"] + timestep
-        return out_state
+
+    def __call__(self, state, tendencies, timestep, out_state=None):
+        out = None
+        for _, out in self.stages_iter(state, tendencies, timestep, out_state):
+            pass
+        return out

@@ -76,6 +76,8 @@ SIGNATURES = {
     "tb200_isentropic_stage_dry": [C.POINTER(StageCfg)] + [_F] * 25 + [_V],
     "tb200_pack_box": [_F, C.c_void_p, _I3, _I3, _V],
     "tb200_unpack_box": [_F, C.c_void_p, _I3, _I3, _V],
+    "tb200_halo_pack": [_FPP, _I, C.c_void_p, _I3, _I3, _V],
+    "tb200_halo_unpack": [_FPP, _I, C.c_void_p, _I3, _I3, _V],
 }
 
 _lib = None
@@ -100,6 +102,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.tb200_last_error.argtypes = []
     lib.tb200_version.restype = C.c_int
     lib.tb200_device_count.restype = C.c_int
+    lib.tb200_launch_count.restype = C.c_longlong
+    lib.tb200_launch_count.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -109,7 +113,13 @@ def load(build_if_missing: bool = True) -> C.CDLL:
 
 
 def exported_symbols():
-    return ["tb200_last_error", "tb200_version", "tb200_device_count", *SIGNATURES]
+    return ["tb200_last_error", "tb200_version", "tb200_device_count", "tb200_launch_count",
+            *SIGNATURES]
+
+
+def launch_count() -> int:
+    """Kernels launched by the library so far (``tb200_launch_count``)."""
+    return int(load().tb200_launch_count())
 
 
 def check(rc: int, what: str) -> None:
