@@ -1,0 +1,234 @@
+# -*- coding: utf-8 -*-
+"""Registration of the ``b200`` backend into tasmania's own registries.
+
+    import tasmania            # the reference package, unmodified
+    import tasmania_b200.plugin
+    tasmania_b200.plugin.install()
+    dycore = IsentropicDynamicalCore(domain, ..., backend="b200", ...)
+
+After ``install()`` every ``StencilFactory`` of tasmania resolves ``backend="b200"`` like any
+built-in backend:
+
+* allocators ``zeros / ones / empty / as_storage`` (src/tasmania/framework/allocators.py:L40-L181)
+  return ``B200Array`` device storages; ``as_storage("numpy", data=<B200Array>)`` (what
+  ``to_numpy`` calls, framework/generic_functions.py:L35-L36) copies back to the host;
+* ``stencil_compiler`` / ``subroutine_compiler`` (framework/stencil.py:L137-L204) get a b200
+  entry: the stencil compiler snapshots ``backend_options.externals`` and swallows unused
+  keyword arguments exactly like ``compiler_numpy`` + ``wrap``
+  (framework/subclasses/stencil_compilers.py:L49-L99);
+* the class-less stencils (``copy``, the ``math`` family, ``irelax``/``relax``, ``sts_rk*_0``,
+  ``step_forward_euler[_momentum]``) are registered globally through
+  ``StencilDefinition.register(handle, backend="b200", stencil=...)``
+  (framework/stencil.py:L112-L130);
+* the class-scoped ones (``diffusion``, ``smoothing``, ``damping``, ``montgomery``, ...; several
+  classes define the same stencil name and only the per-instance registry tells them apart,
+  framework/stencil.py:L460-L469) are attached to the reference classes as static methods
+  tagged with ``tasmania.framework.tag.stencil_definition(backend="b200", stencil=...)``
+  (framework/tag.py:L68-L80), before any instance is built;
+* the flux / advection / sedimentation-flux *subroutines* only have to exist for the backend
+  (``get_subroutine_definition``, framework/stencil.py:L379-L392): a fused CUDA kernel never
+  calls them, so a descriptor function carrying the scheme is registered and travels to the
+  b200 stencil through ``externals`` (e.g. rk3ws_si.py:L249-L264).
+
+Nothing here computes: every definition marshals its arguments into one C-ABI call of
+``libtasmania_b200.so`` (tasmania_b200/stencils.py).  No multi-backend dispatch, no CPU
+fallback: a stencil without a b200 definition raises ``FactoryRegistryError`` as for any other
+backend.
+"""
+from __future__ import annotations
+
+import importlib
+import inspect
+
+import numpy as np
+
+from tasmania_b200 import framework as fw
+from tasmania_b200 import stencils as st
+from tasmania_b200 import storage
+
+BACKEND = fw.BACKEND
+_installed = False
+
+
+# ------------------------------------------------------------------ allocators
+def _dtype(storage_options):
+    return getattr(storage_options, "dtype", None) or np.float64
+
+
+def _device(storage_options):
+    return getattr(storage_options, "device", None) or storage.DEFAULT_DEVICE_OVERRIDE
+
+
+def zeros_b200(shape, *, storage_options=None):
+    return storage.zeros(shape, dtype=_dtype(storage_options), device=_device(storage_options))
+
+
+def ones_b200(shape, *, storage_options=None):
+    return storage.ones(shape, dtype=_dtype(storage_options), device=_device(storage_options))
+
+
+def empty_b200(shape, *, storage_options=None):
+    return storage.empty(shape, dtype=_dtype(storage_options), device=_device(storage_options))
+
+
+def as_storage_b200(data, *, storage_options=None):
+    return storage.as_storage(data, device=_device(storage_options))
+
+
+def subroutine_compiler_b200(definition, *, backend_options=None):
+    """Subroutines are descriptors for b200: nothing to compile."""
+    return definition
+
+
+# ------------------------------------------------------------------ descriptors as functions
+def _descriptor(scheme, name):
+    """``_fill_registry`` only collects functions / methods (framework/stencil.py:L460-L469),
+    so a scheme descriptor is wrapped in a function object that carries it."""
+
+    def subroutine(*args, **kwargs):
+        raise RuntimeError(
+            f"'{name}' is a descriptor for the b200 backend: the scheme is evaluated inside the "
+            "fused CUDA kernels, never as a separate subroutine")
+
+    subroutine.__name__ = f"{name}_b200"
+    subroutine.tb200_scheme = scheme
+    return subroutine
+
+
+def _order_bound(definition, key, value, name):
+    """A class-scoped b200 definition with the class's order baked into the externals."""
+
+    def bound(externals, **kwargs):
+        ext = dict(externals)
+        ext[key] = value
+        return definition(ext, **kwargs)
+
+    bound.__name__ = name
+    bound.__signature__ = inspect.signature(definition)
+    return bound
+
+
+# (module, class, stencil name, b200 definition)
+def _class_scoped_stencils():
+    dv = "tasmania.isentropic.dynamics.diagnostics"
+    dw = "tasmania.dwarfs.diagnostics"
+    hd = "tasmania.dwarfs.subclasses.horizontal_diffusers"
+    hs = "tasmania.dwarfs.subclasses.horizontal_smoothers"
+    out = [
+        (dv, "IsentropicDiagnostics", "diagnostic_variables", st.diagnostic_variables_b200),
+        (dv, "IsentropicDiagnostics", "montgomery", st.montgomery_b200),
+        (dv, "IsentropicDiagnostics", "height", st.height_b200),
+        (dv, "IsentropicDiagnostics", "density_and_temperature", st.density_and_temperature_b200),
+        (dw, "HorizontalVelocity", "momenta", st.momenta_b200),
+        (dw, "HorizontalVelocity", "velocity_x", st.velocity_x_b200),
+        (dw, "HorizontalVelocity", "velocity_y", st.velocity_y_b200),
+        (dw, "WaterConstituent", "density", st.density_b200),
+        (dw, "WaterConstituent", "mass_fraction", st.mass_fraction_b200),
+        (hd + ".second_order", "SecondOrder", "diffusion",
+         _order_bound(st.diffusion_b200, "diffusion_order", 2, "diffusion_second_order_b200")),
+        (hd + ".fourth_order", "FourthOrder", "diffusion",
+         _order_bound(st.diffusion_b200, "diffusion_order", 4, "diffusion_fourth_order_b200")),
+        (hs + ".first_order", "FirstOrder", "smoothing",
+         _order_bound(st.smoothing_b200, "smoothing_order", 1, "smoothing_first_order_b200")),
+        (hs + ".second_order", "SecondOrder", "smoothing",
+         _order_bound(st.smoothing_b200, "smoothing_order", 2, "smoothing_second_order_b200")),
+        (hs + ".third_order", "ThirdOrder", "smoothing",
+         _order_bound(st.smoothing_b200, "smoothing_order", 3, "smoothing_third_order_b200")),
+        ("tasmania.dwarfs.subclasses.vertical_dampers.rayleigh", "Rayleigh", "damping",
+         st.damping_b200),
+        ("tasmania.burgers.dynamics.stepper", "BurgersStepper", "forward_euler",
+         st.burgers_forward_euler_b200),
+    ]
+    out += [(m, c, s, getattr(st, d)) for (m, c, s, d) in st.KESSLER_CLASS_STENCILS]
+    return out
+
+
+def _class_scoped_subroutines():
+    mf = "tasmania.isentropic.dynamics.subclasses.minimal_horizontal_fluxes"
+    ff = "tasmania.isentropic.dynamics.subclasses.horizontal_fluxes"
+    ad = "tasmania.burgers.dynamics.subclasses.advection"
+    out = []
+    for mod, cls, scheme in (("upwind", "Upwind", "upwind"), ("centered", "Centered", "centered"),
+                             ("third_order_upwind", "ThirdOrderUpwind", "third_order_upwind"),
+                             ("fifth_order_upwind", "FifthOrderUpwind", "fifth_order_upwind")):
+        for pkg in (mf, ff):
+            for name in ("flux_dry", "flux_moist"):
+                out.append((f"{pkg}.{mod}", cls, name, _descriptor(st.FLUX[scheme], name)))
+    for mod, cls in (("first_order", "FirstOrder"), ("second_order", "SecondOrder"),
+                     ("third_order", "ThirdOrder"), ("fourth_order", "FourthOrder"),
+                     ("fifth_order", "FifthOrder"), ("sixth_order", "SixthOrder")):
+        out.append((f"{ad}.{mod}", cls, "advection", _descriptor(st.ADVECTION[mod], "advection")))
+    sf = "tasmania.physics.microphysics.sedimentation_fluxes"
+    for mod, cls, order in (("first_order", "FirstOrderUpwind", 1), ("second_order", "SecondOrderUpwind", 2)):
+        out.append((f"{sf}.{mod}", cls, "flux", _descriptor(st.SedimentationFluxScheme(order), "flux")))
+    return out
+
+
+GLOBAL_STENCILS = (
+    "copy", "copychange", "abs", "iabs", "add", "iadd", "addsub", "iaddsub", "clip", "iclip", "fma",
+    "mul", "imul", "scale", "iscale", "sub", "isub", "sts_rk2_0", "sts_rk3ws_0", "irelax", "relax",
+    "step_forward_euler", "step_forward_euler_momentum",
+)
+
+
+def install(strict: bool = False) -> dict:
+    """Register the b200 backend into the importable ``tasmania`` package.  Returns a report
+    ``{"global": [...], "class_scoped": [...], "skipped": [...]}``; with ``strict`` a reference
+    class that cannot be imported raises instead of being skipped (sub-packages pulling
+    optional dependencies may be unavailable)."""
+    global _installed
+    from tasmania.framework import allocators as ta
+    from tasmania.framework import stencil as ts
+    from tasmania.framework import tag as tt
+
+    report = {"global": [], "class_scoped": [], "skipped": []}
+    if _installed:
+        return report
+
+    # 1. allocators
+    ta.zeros.register(zeros_b200, backend=BACKEND)
+    ta.ones.register(ones_b200, backend=BACKEND)
+    ta.empty.register(empty_b200, backend=BACKEND)
+    ta.as_storage.register(as_storage_b200, backend=BACKEND)
+    try:  # to_numpy(<B200Array>): an overload of the reference's singledispatch converter
+        from tasmania.framework.subclasses.allocators.as_storage_numpy import as_storage_numpy
+
+        @as_storage_numpy.register
+        def _(data: storage.B200Array, *, storage_options=None):
+            return data.to_numpy()
+    except Exception as exc:  # pragma: no cover - depends on optional deps of the reference
+        if strict:
+            raise
+        report["skipped"].append(("as_storage_numpy", repr(exc)))
+
+    # 2. compilers
+    ts.StencilCompiler.register(fw.compiler_b200, backend=BACKEND)
+    ts.SubroutineCompiler.register(subroutine_compiler_b200, backend=BACKEND)
+
+    # 3. class-less stencils and subroutines
+    for name in GLOBAL_STENCILS:
+        ts.StencilDefinition.register(fw.get_stencil_definition(name), backend=BACKEND, stencil=name)
+        report["global"].append(name)
+    ts.SubroutineDefinition.register(_descriptor("set_output", "set_output"), backend=BACKEND,
+                                     stencil="set_output")
+
+    # 4. class-scoped definitions: tagged static methods on the reference classes
+    def attach(modname, clsname, stencil, fn, tagger):
+        try:
+            cls = getattr(importlib.import_module(modname), clsname)
+        except Exception as exc:
+            if strict:
+                raise
+            report["skipped"].append((f"{modname}.{clsname}:{stencil}", repr(exc)))
+            return
+        tagged = tagger(backend=BACKEND, stencil=stencil)(fn)
+        setattr(cls, f"_{stencil}_b200", staticmethod(tagged))
+        report["class_scoped"].append(f"{clsname}:{stencil}")
+
+    for modname, clsname, stencil, fn in _class_scoped_stencils():
+        attach(modname, clsname, stencil, fn, tt.stencil_definition)
+    for modname, clsname, stencil, fn in _class_scoped_subroutines():
+        attach(modname, clsname, stencil, fn, tt.subroutine_definition)
+
+    _installed = True
+    return report

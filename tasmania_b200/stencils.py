@@ -65,8 +65,36 @@ ADVECTION = {
 }
 
 
+class SedimentationFluxScheme:
+    """b200 descriptor of a sedimentation flux subroutine
+    (src/tasmania/physics/microphysics/sedimentation_fluxes/{first,second}_order.py)."""
+
+    def __init__(self, order):
+        self.order = int(order)
+        self.nb = self.order  # number of upstream levels (first_order.py:L33, second_order.py:L33)
+
+    def __repr__(self):
+        return f"SedimentationFluxScheme(order={self.order})"
+
+
+# class-scoped Kessler stencils for tasmania_b200.plugin: (module, class, stencil, definition name)
+KESSLER_CLASS_STENCILS = []
+
+
+def _scheme_of(obj):
+    """A descriptor, or the function object the plugin wraps it in (plugin._descriptor)."""
+    return getattr(obj, "tb200_scheme", obj)
+
+
+def framework_definition(name):
+    """The registered b200 definition of a stencil name."""
+    from tasmania_b200.framework import get_stencil_definition
+
+    return get_stencil_definition(name)
+
+
 def _flux_code(externals):
-    d = externals.get("flux_dry")
+    d = _scheme_of(externals.get("flux_dry"))
     if isinstance(d, FluxScheme):
         return d.code
     if isinstance(d, str):
@@ -343,7 +371,7 @@ def density_and_temperature_b200(externals, *, in_theta, in_s, in_exn, in_h, out
 @stencil_definition("forward_euler")
 def burgers_forward_euler_b200(externals, *, in_u, in_v, in_u_tmp, in_v_tmp, out_u, out_v,
                                in_u_tnd=None, in_v_tnd=None, dt, dx, dy, origin, domain):
-    adv = externals.get("advection")
+    adv = _scheme_of(externals.get("advection"))
     order = adv.order if isinstance(adv, AdvectionScheme) else int(adv)
     tu = in_u_tnd if externals.get("tnd_u", in_u_tnd is not None) else None
     tv = in_v_tnd if externals.get("tnd_v", in_v_tnd is not None) else None

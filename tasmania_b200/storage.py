@@ -25,12 +25,18 @@ import torch
 
 ROW_ALIGN = 16  # doubles -> 128 bytes
 
+# Host-side tests of the storage wrapper / the tasmania plugin (no GPU in the build container)
+# set this to "cpu"; the product never does, and kernels refuse host memory (lib.as_field).
+DEFAULT_DEVICE_OVERRIDE = None
+
 
 def _round_up(n: int, m: int) -> int:
     return ((n + m - 1) // m) * m
 
 
 def default_device() -> torch.device:
+    if DEFAULT_DEVICE_OVERRIDE is not None:
+        return torch.device(DEFAULT_DEVICE_OVERRIDE)
     if not torch.cuda.is_available():
         raise RuntimeError(
             "the b200 backend needs a CUDA device (there is no CPU fallback); pass "

@@ -1,0 +1,112 @@
+# -*- coding: utf-8 -*-
+"""Run by tests/test_plugin_reference.py in a subprocess (the reference loader patches
+sys.modules).  Loads the UNMODIFIED reference from /root/reference through
+tests/golden/refload.py, installs the b200 plugin into its registries and drives the
+reference's own classes with backend="b200" as far as the CPU container allows: everything
+up to (not including) the kernel launches, with storages on the host."""
+import inspect
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+import refload  # noqa: E402
+
+refload.install_framework()
+
+from tasmania_b200 import plugin, storage  # noqa: E402
+from tasmania_b200 import stencils as st  # noqa: E402
+
+storage.DEFAULT_DEVICE_OVERRIDE = "cpu"  # no GPU here: exercise registration + storages only
+report = plugin.install()
+
+from tasmania.framework import allocators as ta  # noqa: E402
+from tasmania.framework import stencil as ts  # noqa: E402
+from tasmania.framework.generic_functions import to_numpy  # noqa: E402
+from tasmania.framework.options import BackendOptions, StorageOptions  # noqa: E402
+from tasmania.utils.exceptions import FactoryRegistryError  # noqa: E402
+
+# ---- allocators and conversions through the reference's own entry points
+z = ta.zeros("b200", shape=(5, 4, 3), storage_options=StorageOptions())
+assert isinstance(z, storage.B200Array) and z.shape == (5, 4, 3) and z.dtype == np.float64
+o = ta.ones("b200", shape=(2, 2, 2))
+assert to_numpy(o).sum() == 8.0 and isinstance(to_numpy(o), np.ndarray)
+a = ta.as_storage("b200", data=np.arange(24.0).reshape(2, 3, 4))
+assert isinstance(a, storage.B200Array) and np.array_equal(to_numpy(a), np.arange(24.0).reshape(2, 3, 4))
+
+# ---- global stencils resolve to the b200 definitions, compile through the b200 compiler
+for name in plugin.GLOBAL_STENCILS:
+    assert ts.StencilDefinition("b200", name) is st.framework_definition(name), name
+compiled = ts.StencilCompiler("irelax", "b200", backend_options=BackendOptions())
+assert callable(compiled) and compiled.externals == {}
+try:
+    ts.StencilDefinition("b200", "thomas")  # out of scope: must fail like any unknown backend
+    raise SystemExit("thomas should not be registered for b200")
+except FactoryRegistryError:
+    pass
+
+# ---- class-scoped definitions on the reference's classes
+must = {"IsentropicDiagnostics:montgomery", "IsentropicDiagnostics:diagnostic_variables",
+        "HorizontalVelocity:velocity_x", "WaterConstituent:density", "FourthOrder:diffusion",
+        "SecondOrder:smoothing", "Rayleigh:damping", "BurgersStepper:forward_euler",
+        "FifthOrderUpwind:flux_dry", "ThirdOrder:advection"}
+missing = must - set(report["class_scoped"])
+assert not missing, (missing, report["skipped"])
+
+from tasmania.dwarfs.horizontal_diffusion import HorizontalDiffusion  # noqa: E402
+from tasmania.dwarfs.subclasses.horizontal_diffusers import fourth_order, second_order  # noqa: E402,F401
+
+hd = HorizontalDiffusion.factory("fourth_order", (12, 11, 6), 1.0, 1.0, 0.5, 1.0, 3, backend="b200",
+                                 backend_options=BackendOptions(), storage_options=StorageOptions())
+assert isinstance(hd._gamma, storage.B200Array)           # allocated by the b200 allocator
+g = to_numpy(hd._gamma)
+assert g.shape == (12, 11, 6) and g[0, 0, 0] > g[0, 0, 5] == 0.5   # broadcast assignment worked
+assert hd.get_stencil_definition("diffusion").__name__ == "diffusion_fourth_order_b200"
+assert callable(hd._stencil)
+
+from tasmania.isentropic.dynamics.subclasses.minimal_horizontal_fluxes.fifth_order_upwind import (  # noqa: E402
+    FifthOrderUpwind)
+
+hf = FifthOrderUpwind(backend="b200")
+d = hf.get_subroutine_definition("flux_dry")
+assert d.tb200_scheme is st.FLUX["fifth_order_upwind"] and hf.extent == 3
+# what RK3WSSI._stencils_initialize does (rk3ws_si.py:L249-L264) -> the b200 K1 compiles
+bo = BackendOptions()
+bo.externals = {"extent": hf.extent, "flux_dry": d, "flux_moist": hf.get_subroutine_definition("flux_moist"),
+                "moist": False, "s_tnd_on": False}
+k1 = ts.StencilCompiler("step_forward_euler", "b200", backend_options=bo)
+assert st._flux_code(k1.externals) == 3
+bo.externals = {}  # the compiler snapshots: later overwrites must not leak in
+assert st._flux_code(k1.externals) == 3
+
+# ---- keyword names: every argument of the reference's numpy definition is accepted by ours
+import importlib  # noqa: E402
+
+checked = 0
+for modname, clsname, stencil, fn in plugin._class_scoped_stencils():
+    try:
+        cls = getattr(importlib.import_module(modname), clsname)
+    except Exception:
+        continue
+    ref_def = None
+    for _, h in inspect.getmembers(cls, predicate=inspect.isfunction):
+        tag = getattr(h, "__tasmania__", None)
+        if tag and tag.get("function") == "stencil_definition":
+            backends, stencils = tag.get("backend"), tag.get("stencil")
+            backends = [backends] if isinstance(backends, str) else backends
+            stencils = [stencils] if isinstance(stencils, str) else stencils
+            if "numpy" in backends and stencil in stencils and not getattr(h, "__isabstractmethod__", False):
+                ref_def = h
+    assert ref_def is not None, (clsname, stencil)
+    ours = set(inspect.signature(fn).parameters) - {"externals"}
+    theirs = set(inspect.signature(ref_def).parameters)
+    assert theirs <= ours, (clsname, stencil, sorted(theirs - ours))
+    checked += 1
+assert checked >= 14, checked
+print("PLUGIN-OK", len(report["global"]), len(report["class_scoped"]), len(report["skipped"]))
+for s in report["skipped"]:
+    print("skipped:", s)

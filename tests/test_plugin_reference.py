@@ -1,0 +1,20 @@
+# -*- coding: utf-8 -*-
+"""The b200 plugin against the UNMODIFIED reference (only where /root/reference is mounted,
+i.e. in the build container; skipped on the GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("TASMANIA_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
+                    reason="reference tree not mounted")
+def test_plugin_registers_into_the_reference():
+    res = subprocess.run([sys.executable, os.path.join(HERE, "plugin_check.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "PLUGIN-OK" in res.stdout
