@@ -194,6 +194,52 @@ int tb200_burgers_forward_euler(int advection_order, const tb200_field *in_u,
                                 const int32_t origin[3], const int32_t domain[3],
                                 void *stream);
 
+/* ---- K11 Kessler microphysics: src/tasmania/physics/microphysics/kessler.py
+ * kessler L307-L376, saturation (diagnostic) L661-L714, saturation (prognostic) L981-L1032,
+ * fall_velocity L1183-L1203, sedimentation L1339-L1370 (+ sedimentation_fluxes/{first,second}
+ * _order.py), accumulated_precipitation microphysics/utils.py:L283-L305.
+ * `flags`: the compile-time externals and the `ow_*` (set_output overwrite) switches. */
+enum {
+  TB200_KESSLER_P_ON_INTERFACES = 1,  /* air_pressure_on_interface_levels: p, exn averaged k, k+1 */
+  TB200_KESSLER_RAIN_EVAPORATION = 2,
+  TB200_KESSLER_OW_QC = 4,
+  TB200_KESSLER_OW_QR = 8,
+  TB200_KESSLER_OW_QV = 16,
+  TB200_KESSLER_OW_THETA = 32
+};
+int tb200_kessler(const tb200_field *in_rho, const tb200_field *in_p, const tb200_field *in_t,
+                  const tb200_field *in_exn, const tb200_field *in_qc, const tb200_field *in_qr,
+                  const tb200_field *in_qv, tb200_field *out_qc_tnd, tb200_field *out_qr_tnd,
+                  tb200_field *out_qv_tnd, tb200_field *out_theta_tnd, double a, double k1,
+                  double k2, double beta, double lhvw, uint32_t flags, const int32_t origin[3],
+                  const int32_t domain[3], void *stream);
+int tb200_saturation_diagnostic(const tb200_field *in_p, const tb200_field *in_t,
+                                const tb200_field *in_exn, const tb200_field *in_qv,
+                                const tb200_field *in_qc, tb200_field *out_qv,
+                                tb200_field *out_qc, tb200_field *out_t, tb200_field *tnd_theta,
+                                double dt, double beta, double lhvw, double cp, double rv,
+                                uint32_t flags, const int32_t origin[3],
+                                const int32_t domain[3], void *stream);
+int tb200_saturation_prognostic(const tb200_field *in_p, const tb200_field *in_t,
+                                const tb200_field *in_exn, const tb200_field *in_qv,
+                                const tb200_field *in_qc, tb200_field *tnd_qv,
+                                tb200_field *tnd_qc, tb200_field *tnd_theta, double sr,
+                                double beta, double lhvw, double cp, double rv, uint32_t flags,
+                                const int32_t origin[3], const int32_t domain[3], void *stream);
+int tb200_fall_velocity(const tb200_field *in_rho, const tb200_field *in_rho_s,
+                        const tb200_field *in_qr, tb200_field *out_vt, const int32_t origin[3],
+                        const int32_t domain[3], void *stream);
+/* order = 1 | 2: first / second order upwind sedimentation flux (sflux_extent = order) */
+int tb200_sedimentation(int order, const tb200_field *in_rho, const tb200_field *in_h,
+                        const tb200_field *in_qr, const tb200_field *in_vt,
+                        tb200_field *out_tnd_qr, int ow_out_tnd_qr, const int32_t origin[3],
+                        const int32_t domain[3], void *stream);
+int tb200_accumulated_precipitation(const tb200_field *in_rho, const tb200_field *in_qr,
+                                    const tb200_field *in_vt, const tb200_field *in_accprec,
+                                    tb200_field *out_prec, tb200_field *out_accprec, double dt,
+                                    double rhow, const int32_t origin[3],
+                                    const int32_t domain[3], void *stream);
+
 /* ---- fused dry isentropic stage (the benchmark hot path) ---------------------------
  * One RK stage of IsentropicDynamicalCore.stage_array_call_dry
  * (src/tasmania/isentropic/dynamics/dycore.py:L641-L721) with the relaxed lateral boundary:

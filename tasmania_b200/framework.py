@@ -169,12 +169,18 @@ class StencilFactory:
     def storage_options(self) -> StorageOptions:
         return self._storage_options
 
+    # class-scoped definitions: several classes define the same stencil name ("saturation",
+    # "diffusion", ...) and the per-instance registry tells them apart
+    # (framework/stencil.py:L460-L469); here a class maps name -> registered b200 name
+    class_stencils: dict = {}
+
     def compile_stencil(self, stencil: str, backend: Optional[str] = None, *,
                         backend_options: Optional[BackendOptions] = None) -> Callable:
-        return compile_stencil(stencil, backend, backend_options=backend_options or self.backend_options)
+        return compiler_b200(self.get_stencil_definition(stencil, backend),
+                             backend_options=backend_options or self.backend_options)
 
     def get_stencil_definition(self, stencil, backend=None):
-        return get_stencil_definition(stencil, backend)
+        return get_stencil_definition(self.class_stencils.get(stencil, stencil), backend)
 
     def get_subroutine_definition(self, stencil, backend=None):
         return get_subroutine_definition(stencil, backend)

@@ -76,9 +76,18 @@ SIGNATURES = {
     "tb200_isentropic_stage_dry": [C.POINTER(StageCfg)] + [_F] * 25 + [_V],
     "tb200_pack_box": [_F, C.c_void_p, _I3, _I3, _V],
     "tb200_unpack_box": [_F, C.c_void_p, _I3, _I3, _V],
+    "tb200_kessler": [_F] * 11 + [_D] * 5 + [C.c_uint32, _I3, _I3, _V],
+    "tb200_saturation_diagnostic": [_F] * 9 + [_D] * 5 + [C.c_uint32, _I3, _I3, _V],
+    "tb200_saturation_prognostic": [_F] * 8 + [_D] * 5 + [C.c_uint32, _I3, _I3, _V],
+    "tb200_fall_velocity": [_F] * 4 + [_I3, _I3, _V],
+    "tb200_sedimentation": [_I] + [_F] * 5 + [_I, _I3, _I3, _V],
+    "tb200_accumulated_precipitation": [_F] * 6 + [_D, _D, _I3, _I3, _V],
     "tb200_halo_pack": [_FPP, _I, C.c_void_p, _I3, _I3, _V],
     "tb200_halo_unpack": [_FPP, _I, C.c_void_p, _I3, _I3, _V],
 }
+
+KESSLER_FLAGS = {"p_on_interfaces": 1, "rain_evaporation": 2, "ow_qc": 4, "ow_qr": 8, "ow_qv": 16,
+                 "ow_theta": 32}
 
 _lib = None
 

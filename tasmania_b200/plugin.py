@@ -159,8 +159,9 @@ def _class_scoped_subroutines():
                      ("fifth_order", "FifthOrder"), ("sixth_order", "SixthOrder")):
         out.append((f"{ad}.{mod}", cls, "advection", _descriptor(st.ADVECTION[mod], "advection")))
     sf = "tasmania.physics.microphysics.sedimentation_fluxes"
-    for mod, cls, order in (("first_order", "FirstOrderUpwind", 1), ("second_order", "SecondOrderUpwind", 2)):
-        out.append((f"{sf}.{mod}", cls, "flux", _descriptor(st.SedimentationFluxScheme(order), "flux")))
+    for mod, cls, name in (("first_order", "FirstOrderUpwind", "first_order_upwind"),
+                           ("second_order", "SecondOrderUpwind", "second_order_upwind")):
+        out.append((f"{sf}.{mod}", cls, "flux", _descriptor(st.SEDIMENTATION_FLUX[name], "flux")))
     return out
 
 

@@ -380,10 +380,95 @@ def burgers_forward_euler_b200(externals, *, in_u, in_v, in_u_tmp, in_v_tmp, out
           _i3(domain), _stream())
 
 
+# ------------------------------------------------------------------ K11 Kessler
+def _kflags(externals, **ow):
+    fl = lib.KESSLER_FLAGS
+    v = 0
+    if externals.get("air_pressure_on_interface_levels", True):
+        v |= fl["p_on_interfaces"]
+    if externals.get("rain_evaporation", True):
+        v |= fl["rain_evaporation"]
+    for key, on in ow.items():
+        if on:
+            v |= fl[key]
+    return v
+
+
+@stencil_definition("kessler")
+def kessler_b200(externals, *, in_rho, in_p, in_t, in_exn, in_qc, in_qr, in_qv, out_qc_tnd,
+                 out_qr_tnd, out_qv_tnd=None, out_theta_tnd=None, a, k1, k2, ow_out_qc_tnd,
+                 ow_out_qr_tnd, ow_out_qv_tnd=True, ow_out_theta_tnd=True, origin, domain):
+    flags = _kflags(externals, ow_qc=ow_out_qc_tnd, ow_qr=ow_out_qr_tnd, ow_qv=ow_out_qv_tnd,
+                    ow_theta=ow_out_theta_tnd)
+    _call("tb200_kessler", _f(in_rho), _f(in_p), _f(in_t), _f(in_exn), _f(in_qc), _f(in_qr),
+          _f(in_qv), _f(out_qc_tnd), _f(out_qr_tnd), _f(out_qv_tnd), _f(out_theta_tnd), float(a),
+          float(k1), float(k2), float(externals["beta"]), float(externals["lhvw"]), flags,
+          _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("saturation_diagnostic")
+def saturation_diagnostic_b200(externals, *, in_p, in_t, in_exn, in_qv, in_qc, out_qv, out_qc,
+                               out_t, tnd_theta, dt, ow_tnd_theta, origin, domain):
+    flags = _kflags(externals, ow_theta=ow_tnd_theta)
+    _call("tb200_saturation_diagnostic", _f(in_p), _f(in_t), _f(in_exn), _f(in_qv), _f(in_qc),
+          _f(out_qv), _f(out_qc), _f(out_t), _f(tnd_theta), float(dt), float(externals["beta"]),
+          float(externals["lhvw"]), float(externals["cp"]), float(externals["rv"]), flags,
+          _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("saturation_prognostic")
+def saturation_prognostic_b200(externals, *, in_p, in_t, in_exn, in_qv, in_qc, tnd_qv, tnd_qc,
+                               tnd_theta, sr, ow_tnd_qv, ow_tnd_qc, ow_tnd_theta, origin, domain):
+    flags = _kflags(externals, ow_qv=ow_tnd_qv, ow_qc=ow_tnd_qc, ow_theta=ow_tnd_theta)
+    _call("tb200_saturation_prognostic", _f(in_p), _f(in_t), _f(in_exn), _f(in_qv), _f(in_qc),
+          _f(tnd_qv), _f(tnd_qc), _f(tnd_theta), float(sr), float(externals["beta"]),
+          float(externals["lhvw"]), float(externals["cp"]), float(externals["rv"]), flags,
+          _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("fall_velocity")
+def fall_velocity_b200(externals, *, in_rho, in_rho_s, in_qr, out_vt, origin, domain):
+    _call("tb200_fall_velocity", _f(in_rho), _f(in_rho_s), _f(in_qr), _f(out_vt), _i3(origin),
+          _i3(domain), _stream())
+
+
+@stencil_definition("sedimentation")
+def sedimentation_b200(externals, *, in_rho, in_h, in_qr, in_vt, out_tnd_qr, ow_out_tnd_qr, origin,
+                       domain):
+    sflux = _scheme_of(externals.get("sflux"))
+    order = sflux.order if isinstance(sflux, SedimentationFluxScheme) else int(externals["sflux_extent"])
+    _call("tb200_sedimentation", order, _f(in_rho), _f(in_h), _f(in_qr), _f(in_vt), _f(out_tnd_qr),
+          int(bool(ow_out_tnd_qr)), _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("accumulated_precipitation")
+def accumulated_precipitation_b200(externals, *, in_rho, in_qr, in_vt, in_accprec, out_prec,
+                                   out_accprec, dt, origin, domain):
+    _call("tb200_accumulated_precipitation", _f(in_rho), _f(in_qr), _f(in_vt), _f(in_accprec),
+          _f(out_prec), _f(out_accprec), float(dt), float(externals["rhow"]), _i3(origin),
+          _i3(domain), _stream())
+
+
+_KE = "tasmania.physics.microphysics.kessler"
+KESSLER_CLASS_STENCILS += [
+    (_KE, "KesslerMicrophysics", "kessler", "kessler_b200"),
+    (_KE, "KesslerSaturationAdjustmentDiagnostic", "saturation", "saturation_diagnostic_b200"),
+    (_KE, "KesslerSaturationAdjustmentPrognostic", "saturation", "saturation_prognostic_b200"),
+    (_KE, "KesslerFallVelocity", "fall_velocity", "fall_velocity_b200"),
+    (_KE, "KesslerSedimentation", "sedimentation", "sedimentation_b200"),
+    ("tasmania.physics.microphysics.utils", "Precipitation", "accumulated_precipitation",
+     "accumulated_precipitation_b200"),
+]
+SEDIMENTATION_FLUX = {"first_order_upwind": SedimentationFluxScheme(1),
+                      "second_order_upwind": SedimentationFluxScheme(2)}
+
+
 # subroutine descriptors: must *exist* for the backend (stencil.py:L379-L392)
 for _name, _scheme in FLUX.items():
     subroutine_definition(f"flux_dry:{_name}")(_scheme)
     subroutine_definition(f"flux_moist:{_name}")(_scheme)
 for _name, _scheme in ADVECTION.items():
     subroutine_definition(f"advection:{_name}")(_scheme)
+for _name, _scheme in SEDIMENTATION_FLUX.items():
+    subroutine_definition(f"flux:{_name}")(_scheme)
 subroutine_definition("set_output")("set_output")

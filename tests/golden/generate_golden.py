@@ -296,6 +296,112 @@ def gen_stencils():
     save("stencils", dims=np.array([nx, ny, nz]), **out)
 
 
+
+# ============================================================================ Kessler (K11)
+def gen_kessler():
+    """K11: kessler, saturation (diagnostic + prognostic), fall_velocity, sedimentation
+    (first / second order upwind flux), accumulated_precipitation -- the reference's numpy
+    stencil definitions of src/tasmania/physics/microphysics/{kessler,utils}.py with the
+    externals their classes inject (kessler.py:L183-L190, L554-L562, L1283-L1287,
+    utils.py:L205-L207)."""
+    rng = np.random.default_rng(20261019)
+    nx, ny, nz = 13, 11, 8
+    shape = (nx + 1, ny + 1, nz + 1)
+    out = {}
+    rd, rv, cp, lhvw, pref, rhow = 287.05, 461.52, 1004.0, 2.5e6, 1.0e5, 1.0e3
+    beta = rd / rv
+
+    # a physically plausible column: pressure increasing with k, height decreasing
+    p_hl = np.zeros(shape)
+    p_hl[...] = np.linspace(1.5e4, 1.0e5, nz + 1)[None, None, :] * rng.uniform(0.97, 1.03, size=shape)
+    exn_hl = cp * (p_hl / pref) ** (rd / cp)
+    p_ml, exn_ml = rng.uniform(2e4, 9.5e4, size=shape), rng.uniform(600, 1000, size=shape)
+    t = rng.uniform(215.0, 305.0, size=shape)
+    rho = rng.uniform(0.15, 1.3, size=shape)
+    qv = rng.uniform(0.0, 0.02, size=shape)
+    qc = rng.uniform(0.0, 3e-3, size=shape)
+    qr = rng.uniform(-5e-4, 3e-3, size=shape)   # negatives and zeros exercise the where() branches
+    qr[::3, ::2, ::2] = 0.0
+    h_hl = np.zeros(shape)
+    h_hl[...] = np.linspace(1.6e4, 0.0, nz + 1)[None, None, :] + rng.uniform(-150, 150, size=shape)
+    vt_in = rng.uniform(0.0, 9.0, size=shape)
+    accprec = rng.uniform(0.0, 4.0, size=(nx + 1, ny + 1, 1))
+    prev = {n: rng.uniform(-1e-5, 1e-5, size=shape) for n in ("qc", "qr", "qv", "theta")}
+    a, k1, k2, dt, sr = 1.0e-3, 1.0e-3, 2.2, 7.5, 0.025
+    out.update(p_hl=p_hl, exn_hl=exn_hl, p_ml=p_ml, exn_ml=exn_ml, t=t, rho=rho, qv=qv, qc=qc,
+               qr=qr, h_hl=h_hl, vt_in=vt_in, accprec=accprec,
+               prev_qc=prev["qc"], prev_qr=prev["qr"], prev_qv=prev["qv"], prev_theta=prev["theta"],
+               scalars=np.array([a, k1, k2, dt, sr, rd, rv, cp, lhvw, rhow]))
+
+    gen = refload.load("tasmania.framework.subclasses.subroutine_definitions.generics")
+    ke = refload.load("tasmania.physics.microphysics.kessler")
+    ut = refload.load("tasmania.physics.microphysics.utils")
+    box = dict(origin=(0, 0, 0), domain=(nx, ny, nz))
+
+    # ---- kessler
+    for apoil in (True, False):
+        for evap in (True, False):
+            for ow in (True, False):
+                ext = {"air_pressure_on_interface_levels": apoil, "beta": beta, "e": np.exp(1),
+                       "lhvw": lhvw, "rain_evaporation": evap, "set_output": gen.set_output_numpy}
+                st = refload.numpy_stencil(ke.KesslerMicrophysics._kessler_numpy, ext)
+                o = {n: (np.zeros(shape) if ow else prev[n].copy()) for n in prev}
+                st(in_rho=rho, in_p=p_hl if apoil else p_ml, in_t=t,
+                   in_exn=exn_hl if apoil else exn_ml, in_qc=qc, in_qr=qr, in_qv=qv,
+                   out_qc_tnd=o["qc"], out_qr_tnd=o["qr"], out_qv_tnd=o["qv"],
+                   out_theta_tnd=o["theta"], a=a, k1=k1, k2=k2, ow_out_qc_tnd=ow,
+                   ow_out_qr_tnd=ow, ow_out_qv_tnd=ow, ow_out_theta_tnd=ow, **box)
+                tag = f"kessler_p{int(apoil)}_e{int(evap)}_o{int(ow)}"
+                for n in o:
+                    out[f"{tag}_{n}"] = o[n]
+
+    # ---- saturation adjustment
+    for apoil in (True, False):
+        ext = {"air_pressure_on_interface_levels": apoil, "beta": beta, "cp": cp, "e": np.exp(1),
+               "lhvw": lhvw, "rv": rv, "set_output": gen.set_output_numpy}
+        pp, ee = (p_hl, exn_hl) if apoil else (p_ml, exn_ml)
+        for ow in (True, False):
+            st = refload.numpy_stencil(ke.KesslerSaturationAdjustmentDiagnostic._saturation_diagnostic_numpy, ext)
+            o_qv, o_qc, o_t = np.zeros(shape), np.zeros(shape), np.zeros(shape)
+            tnd = np.zeros(shape) if ow else prev["theta"].copy()
+            st(in_p=pp, in_t=t, in_exn=ee, in_qv=qv, in_qc=qc, out_qv=o_qv, out_qc=o_qc, out_t=o_t,
+               tnd_theta=tnd, dt=dt, ow_tnd_theta=ow, **box)
+            tag = f"satd_p{int(apoil)}_o{int(ow)}"
+            out.update({f"{tag}_qv": o_qv, f"{tag}_qc": o_qc, f"{tag}_t": o_t, f"{tag}_theta": tnd})
+            st = refload.numpy_stencil(ke.KesslerSaturationAdjustmentPrognostic._saturation_prognostic_numpy, ext)
+            o = {n: (np.zeros(shape) if ow else prev[n].copy()) for n in ("qv", "qc", "theta")}
+            st(in_p=pp, in_t=t, in_exn=ee, in_qv=qv, in_qc=qc, tnd_qv=o["qv"], tnd_qc=o["qc"],
+               tnd_theta=o["theta"], sr=sr, ow_tnd_qv=ow, ow_tnd_qc=ow, ow_tnd_theta=ow, **box)
+            tag = f"satp_p{int(apoil)}_o{int(ow)}"
+            out.update({f"{tag}_{n}": o[n] for n in o})
+
+    # ---- fall velocity (array_call copies the surface density slab first, kessler.py:L1169)
+    rho_s = np.zeros(shape)
+    rho_s[:nx, :ny, :nz] = rho[:nx, :ny, nz - 1 : nz]
+    vt = np.zeros(shape)
+    ke.KesslerFallVelocity._fall_velocity_numpy(in_rho=rho, in_rho_s=rho_s, in_qr=qr, out_vt=vt, **box)
+    out.update(fall_rho_s=rho_s, fall_vt=vt)
+
+    # ---- sedimentation
+    for order, mod, cls in ((1, "first_order", "FirstOrderUpwind"), (2, "second_order", "SecondOrderUpwind")):
+        sf = getattr(refload.load("tasmania.physics.microphysics.sedimentation_fluxes." + mod), cls)
+        for ow in (True, False):
+            ext = {"set_output": gen.set_output_numpy, "sflux": sf.call_numpy, "sflux_extent": sf.nb}
+            st = refload.numpy_stencil(ke.KesslerSedimentation._sedimentation_numpy, ext)
+            tnd = rng.uniform(-1, 1, size=shape) if ow else prev["qr"].copy()
+            st(in_rho=rho, in_h=h_hl, in_qr=qr, in_vt=vt_in, out_tnd_qr=tnd, ow_out_tnd_qr=ow, **box)
+            out[f"sed_{order}_o{int(ow)}"] = tnd
+
+    # ---- accumulated precipitation on the surface slabs (utils.py:L262-L281)
+    st = refload.numpy_stencil(ut.Precipitation._accumulated_precipitation_numpy, {"rhow": rhow})
+    prec, acc = np.zeros((nx + 1, ny + 1, 1)), np.zeros((nx + 1, ny + 1, 1))
+    st(in_rho=rho[:, :, nz - 1 : nz], in_qr=qr[:, :, nz - 1 : nz], in_vt=vt_in[:, :, nz - 1 : nz],
+       in_accprec=accprec[:, :, :1], out_prec=prec[:, :, :1], out_accprec=acc[:, :, :1], dt=dt,
+       origin=(0, 0, 0), domain=(nx, ny, 1))
+    out.update(prec=prec, acc=acc)
+
+    save("kessler", dims=np.array([nx, ny, nz]), **out)
+
 # ============================================================================ isentropic
 def _make_domain(nx, ny, nz, hb_type, nb, hb_kwargs, topo_time=1800.0, xlim=(-176, 176),
                  topo=True):
@@ -433,6 +539,7 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
 
 CASES = {
     "stencils": gen_stencils,
+    "kessler": gen_kessler,
     "isen_dry_rk3_5th": lambda: gen_isentropic_dry(
         "isen_dry_rk3_5th", 25, 21, 8, "rk3ws_si", "fifth_order_upwind", 3, 6, 6, 5.0),
     "isen_dry_rk3_3rd": lambda: gen_isentropic_dry(

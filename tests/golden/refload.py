@@ -24,6 +24,7 @@ No reference source is copied: the reference code is executed where it lies.
 """
 from __future__ import annotations
 
+import abc
 import importlib
 import importlib.abc
 import importlib.machinery
@@ -42,7 +43,7 @@ def available() -> bool:
 
 
 # --------------------------------------------------------------------------- stubs
-class _AnyMeta(type):
+class _AnyMeta(abc.ABCMeta):
     def __getattr__(cls, name):
         if name.startswith("__"):
             raise AttributeError(name)

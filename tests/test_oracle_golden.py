@@ -197,3 +197,18 @@ def test_dry_dycore_orchestration(case):
         eq(stage0[n][: nx + 1, : ny + 1, :nz], fx["stage0_" + n][: nx + 1, : ny + 1, :nz])
     for n in (hp.S, hp.SU, hp.SV, hp.U, hp.V, hp.MTG, hp.P, hp.EXN, hp.H):
         eq(final[n], fx["final_" + n])
+
+
+# ------------------------------------------------------------------ K11 Kessler
+def test_kessler_family_bitwise():
+    """Every K11 stencil of the oracle against the reference's own numpy definitions
+    (tests/golden/kessler.npz), bit for bit."""
+    from oracle import microphysics as om
+    from tests.kessler_cases import cases
+
+    fx = hp.load("kessler")
+    n = 0
+    for tag, name, got, want in cases(fx, om, lambda a: np.array(a, copy=True), np.asarray, np.zeros):
+        np.testing.assert_array_equal(got, want, err_msg=f"{tag}:{name}")
+        n += 1
+    assert n >= 60
