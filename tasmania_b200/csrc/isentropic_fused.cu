@@ -24,41 +24,14 @@
 // the algorithmic minimum of 112 B; the relaxation band and the damping
 // layer add reads of the reference fields only where gamma != 0 or R != 0.  All arithmetic
 // follows the reference's operation order (see stencil_math.cuh).
-#include "stencil_math.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "stage.cuh"
 
 using namespace tb200;
 
 namespace {
-
-struct StageArgs {
-  View s_now, su_now, sv_now, mtg_now;
-  View s_int, su_int, sv_int, u_int, v_int;
-  View s_new, su_new, sv_new, u_new, v_new;
-  View s_ref, su_ref, sv_ref, u_ref, v_ref;
-  View gamma, rmat, hs, exn, mtg, spre;
-  int nx, ny, nz, nb, damp;
-  double dt, dt_full, dx, dy, dz, eps, pt, theta_s, pref, rd, g, cp;
-  FluxConst fc;
-  CDiv two_dx, two_dy, cpref;
-};
-
-// All 3-D fields of a fused stage share one geometry (unit i-stride, equal row and plane
-// strides -- what the b200 allocator produces for equal shapes; checked on the host), so one
-// 32-bit running BYTE offset addresses every field: loads compile to
-// [uniform base + offset + immediate] with no per-load integer arithmetic.
-__device__ __forceinline__ double ldo(const double *base, unsigned off) {
-  return __ldg(reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off));
-}
-__device__ __forceinline__ void sto(double *base, unsigned off, double v) {
-  *reinterpret_cast<double *>(reinterpret_cast<char *>(base) + off) = v;
-}
-__device__ __forceinline__ const double *ptr_at(const double *base, unsigned off) {
-  return reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off);
-}
-// pull a line towards L2 ahead of its use (no register, no stall)
-__device__ __forceinline__ void prefetch_l2(const double *base, unsigned off) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(base) + off));
-}
 
 // ---------------------------------------------------------------- kernel S
 // Unit i-stride and 32-bit element offsets (a field has < 2^31 elements) keep the address
@@ -143,6 +116,179 @@ __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
       pm -= a.mtg.s2;
       m = m + a.dz * (a.cp * pow_pos(*pex / a.cpref, kappa));
       *pm = m;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- kernels A and B
+// Kernel S above couples two things with opposite needs: the s-step is a halo-3 horizontal
+// stencil (wants (i, j) marching with shared faces and parallelism over k), the scans are serial
+// in k (want one thread per column).  Splitting them:
+//
+//   kernel A  (one warp per 31 columns x LJ rows of ONE level, marching in j like kernel MV)
+//       s_pre = irelax(K1(...)) -> scratch_s.  Every face flux is evaluated once (x faces shared
+//       by shuffle, y faces carried to the next row, s_int rows in a register window), and the
+//       launch has nz-fold more parallelism than one thread per column.
+//   kernel B  (one thread per column)
+//       reads the column of s_pre into registers in one go (nz independent loads in flight per
+//       thread), runs the pressure prefix sum, the Exner function and the Montgomery suffix sum
+//       out of registers and writes mtg_new: no parking of p in memory.
+//
+// HBM traffic: A reads s_now, s_int, u, v and writes s_pre (5 words), B reads s_pre and writes
+// mtg (2 words): 7 words against the 8 of kernel S, with ~35 fewer fp64 instructions per point.
+// Arithmetic and results are bit-identical to kernel S.
+constexpr int A_COLS = 31;
+
+template <int SCHEME, int LJ>
+__global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
+  using F = Flux<SCHEME>;
+  constexpr int E = F::extent;
+  constexpr int NW = 2 * E;
+  const int lane = threadIdx.x & 31;
+  const int xw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (xw * A_COLS >= a.nx) return;  // warp-uniform
+  const int c = xw * A_COLS + lane;  // lanes 0..30 own a column, lane 31 lends its left face
+  const int j0 = blockIdx.y * LJ;
+  const int jend = min(j0 + LJ, a.ny);
+  const int k = blockIdx.z;
+  const int nx = a.nx, ny = a.ny, nb = a.nb;
+
+  const bool out_lane = lane < A_COLS && c < nx;
+  const bool col_int = c >= nb && c < nx - nb;
+  const int cc = min(max(c, E), nx - E);  // keeps every x-offset load inside the row
+  const int cm = min(c, nx - 1);          // own column (lanes beyond the domain are discarded)
+
+  const unsigned row = (unsigned)a.s_now.s1 * 8u;
+  const unsigned plane = (unsigned)k * (unsigned)a.s_now.s2 * 8u;
+  const unsigned grow = (unsigned)a.gamma.s1 * 8u;
+
+  // window for the y-face j0 (rows j0-E .. j0+E-1) and its flux
+  double ws[NW];
+#pragma unroll
+  for (int m = 0; m < NW; ++m)
+    ws[m] = ldo(a.s_int.p, plane + (unsigned)max(j0 - E + m, 0) * row + (unsigned)cc * 8u);
+  unsigned o_cc = plane + (unsigned)j0 * row + (unsigned)cc * 8u;
+  unsigned o_cm = plane + (unsigned)j0 * row + (unsigned)cm * 8u;
+  unsigned o_g = (unsigned)j0 * grow + (unsigned)cm * 8u;
+  double fy = F::eval_v(F::prep(ldo(a.v_int.p, o_cc), a.fc), ws);
+
+  struct Row {
+    double s_w, v_n, u_c, s_now, gam;
+  };
+  auto load_row = [&](unsigned occ, unsigned ocm, unsigned og) {
+    Row L;
+    L.s_w = ldo(a.s_int.p, occ + E * row);
+    L.v_n = ldo(a.v_int.p, occ + row);
+    L.u_c = ldo(a.u_int.p, occ);
+    L.s_now = ldo(a.s_now.p, ocm);
+    L.gam = ldo(a.gamma.p, og);
+    return L;
+  };
+  Row nxt = load_row(o_cc, o_cm, o_g);
+  for (int r = j0; r < jend; ++r) {
+    const Row cur = nxt;
+    nxt = load_row(o_cc + row, o_cm + row, o_g + grow);
+    if (r + 4 < jend) {  // DRAM -> L2 a few rows ahead
+      prefetch_l2(a.s_int.p, o_cc + (E + 4) * row);
+      prefetch_l2(a.v_int.p, o_cc + 5 * row);
+      prefetch_l2(a.u_int.p, o_cc + 4 * row);
+      prefetch_l2(a.s_now.p, o_cm + 4 * row);
+    }
+#pragma unroll
+    for (int m = 0; m < NW - 1; ++m) ws[m] = ws[m + 1];
+    ws[NW - 1] = cur.s_w;
+    const double fy_p = F::eval_v(F::prep(cur.v_n, a.fc), ws);
+    double xs[NW];
+    {
+      const double *ps = ptr_at(a.s_int.p, o_cc);
+#pragma unroll
+      for (int m = 0; m < NW; ++m) xs[m] = m == E ? ws[E - 1] : __ldg(ps + (m - E));
+    }
+    const double fx = F::eval_v(F::prep(cur.u_c, a.fc), xs);
+    const double fx_p = __shfl_down_sync(0xffffffffu, fx, 1);
+
+    const bool interior = col_int && r >= nb && r < ny - nb;
+    const double gam = cur.gam;
+    double v;
+    if (interior) {  // prognostics/utils.py:L95-L99
+      const double div = (fx_p - fx) / a.fc.dx + (fy_p - fy) / a.fc.dy;
+      v = cur.s_now - a.dt * (div - 0.0);
+    } else {
+      v = gam == 1.0 ? 0.0 : ldo(a.s_new.p, o_cm);  // untouched by K1; the relaxation decides
+    }
+    if (gam != 0.0) v = relax_point(gam, v, ldo(a.s_ref.p, o_cm));  // rk3ws_si.py:L184-L189
+    if (out_lane) sto(a.spre.p, o_cm, v);
+    fy = fy_p;
+    o_cc += row; o_cm += row; o_g += grow;
+  }
+}
+
+// The Exner function of four levels as ONE real call: kernel B is unrolled over the levels, so
+// an inlined copy of log2 / exp2 per level would not fit the instruction cache, and four
+// independent evaluations per call give the fp64 pipe the instruction-level parallelism that a
+// single dependent polynomial chain lacks.
+struct D4 {
+  double a, b, c, d;
+};
+__device__ __noinline__ D4 exner4(D4 x, double kappa, double cp) {
+  D4 r;
+  r.a = cp * pow_pos(x.a, kappa);
+  r.b = cp * pow_pos(x.b, kappa);
+  r.c = cp * pow_pos(x.c, kappa);
+  r.d = cp * pow_pos(x.d, kappa);
+  return r;
+}
+
+template <int NZC>
+__global__ void __launch_bounds__(128) stage_b_kernel(const StageArgs a) {
+  static_assert(NZC % 4 == 0, "levels are processed four at a time");
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= a.nx || j >= a.ny) return;
+  const int nz = a.nz;
+  const double kappa = a.rd / a.cp;
+  const double gdz = a.g * a.dz;
+  double e[NZC];
+  {
+    const double *ps = a.spre.p + (i + j * a.spre.s1);
+    const long long s2 = a.spre.s2;
+#pragma unroll
+    for (int k = 0; k < NZC; ++k) e[k] = k < nz ? __ldg(ps + k * s2) : 0.0;
+  }
+  // pressure at interface k+1 over the reference pressure (diagnostics.py:L425-L428, L431),
+  // kept in place of s_pre; levels beyond nz get 1 (their Exner value is never used)
+  double p = a.pt;
+#pragma unroll
+  for (int k = 0; k < NZC; ++k) {
+    if (k < nz) {
+      p = p + gdz * e[k];
+      e[k] = p / a.cpref;
+    } else {
+      e[k] = 1.0;
+    }
+  }
+  // Exner function of every interface, four levels per call
+#pragma unroll
+  for (int k = 0; k < NZC; k += 4) {
+    if (k < nz) {
+      const D4 r = exner4(D4{e[k], e[k + 1], e[k + 2], e[k + 3]}, kappa, a.cp);
+      e[k] = r.a; e[k + 1] = r.b; e[k + 2] = r.c; e[k + 3] = r.d;
+    }
+  }
+  // upward sweep, diagnostics.py:L433-L438
+  double *pm = a.mtg.p + (i + j * a.mtg.s1);
+  const long long m2 = a.mtg.s2;
+  double m = 0.0;
+#pragma unroll
+  for (int k = NZC - 1; k >= 0; --k) {
+    if (k == nz - 1) {
+      const double ex_s = e[k];
+      const double mtg_s = a.theta_s * ex_s + a.g * a.hs.ld(i, j, 0);
+      m = mtg_s + 0.5 * a.dz * ex_s;
+      pm[k * m2] = m;
+    } else if (k < nz - 1) {
+      m = m + a.dz * e[k];
+      pm[k * m2] = m;
     }
   }
 }
@@ -364,14 +510,61 @@ __global__ void __launch_bounds__(128, 4) stage_mv_kernel(const StageArgs a) {
   }
 }
 
+// TB200_STAGE_IMPL=tma selects the TMA / shared-memory-ring momentum kernel of
+// isentropic_tma.cu instead of the register-window kernel below.  Both give bit-identical
+// results; on B200 the register-window kernel is currently the faster one (1.94 ms vs 2.16 ms
+// per launch at 1024x1024x64), hence the default.
+int stage_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("TB200_STAGE_IMPL");
+    impl = (e != nullptr && strcmp(e, "tma") == 0) ? 1 : 0;
+  }
+  return impl;
+}
+
+// TB200_S_IMPL=column selects the thread-per-column kernel S instead of kernels A + B
+int s_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("TB200_S_IMPL");
+    impl = (e != nullptr && strcmp(e, "column") == 0) ? 0 : 1;
+  }
+  return impl;
+}
+
 template <int SCHEME>
 int run_stage(const StageArgs &a, cudaStream_t st) {
-  {
+  if (s_impl() != 0 && a.nz <= 64) {
+    {
+      constexpr int LJ = 64, WARPS = 4;
+      const int chunks = (a.nx + A_COLS - 1) / A_COLS;
+      dim3 block(32 * WARPS, 1, 1);
+      dim3 grid((chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
+      stage_a_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
+      int rc = check_launch("isentropic_stage_dry/A");
+      if (rc) return rc;
+    }
+    {
+      dim3 block(32, 4, 1);
+      dim3 grid((a.nx + 31) / 32, (a.ny + 3) / 4, 1);
+      if (a.nz <= 32)
+        stage_b_kernel<32><<<grid, block, 0, st>>>(a);
+      else
+        stage_b_kernel<64><<<grid, block, 0, st>>>(a);
+      int rc = check_launch("isentropic_stage_dry/B");
+      if (rc) return rc;
+    }
+  } else {
     dim3 block(32, 4, 1);
     dim3 grid((a.nx + 31) / 32, (a.ny + 3) / 4, 1);
     stage_s_kernel<SCHEME><<<grid, block, 0, st>>>(a);
     int rc = check_launch("isentropic_stage_dry/S");
     if (rc) return rc;
+  }
+  if (stage_impl() != 0) {  // TMA row pipeline (default); -1 = not covered -> register windows
+    const int rc = launch_stage_c(a, SCHEME, st);
+    if (rc >= 0) return rc;
   }
   {
     constexpr int LJ = 64, WARPS = 4;
