@@ -341,37 +341,68 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# algorithmic HBM bytes per grid point of each kernel of the fused stage (every distinct array
+# read once, every output written once) and their DRAM traffic per launch at
+# 1024x1024x64 from the ncu --set full captures under profiles/ (dram__bytes_read + write)
+KERNEL_BYTES_PER_POINT = {"s_step (stage_a_kernel)": 40, "column_scan (stage_b_kernel)": 16,
+                          "momentum (stage_mv_kernel)": 120}
+NCU_TRAFFIC_C5 = {"s_step (stage_a_kernel)": 2.37e9, "column_scan (stage_b_kernel)": 1.03e9,
+                  "momentum (stage_mv_kernel)": 8.05e9}
+
+
 def kernel_roofline(run, args):
-    """Achieved algorithmic GB/s of one fused RK stage (kernels S + M + V), CUDA events on the
-    launching stream around single stage calls inside a running time loop."""
+    """Roofline of the dominant kernel (the momentum kernel) and of the whole fused RK stage,
+    from CUDA events recorded by the library on the launching stream around each kernel
+    (tb200_stage_profile) inside a running time loop."""
+    import ctypes as C
+
     import torch
 
+    from tasmania_b200 import lib as tblib
+
+    handle = tblib.load()
     dyc = run.dyc
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
     orig = dyc._stage_fused
-    times = []
+    samples = []
 
     def timed(stage, state, timestep, out_state):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
         orig(stage, state, timestep, out_state)
-        b.record()
-        times.append((a, b))
+        ms = (C.c_double * 3)()
+        tblib.check(handle.tb200_stage_profile_read(ms), "tb200_stage_profile_read")
+        samples.append(tuple(ms))
 
+    tblib.check(handle.tb200_stage_profile(1), "tb200_stage_profile")
     dyc._stage_fused = timed
     for _ in range(max(2, min(args.steps, 5))):
         run.step()
     torch.cuda.synchronize()
     dyc._stage_fused = orig
-    ms = [a.elapsed_time(b) for a, b in times]
-    avg = float(np.mean(ms))
+    tblib.check(handle.tb200_stage_profile(0), "tb200_stage_profile")
+    t = np.mean(np.array(samples), axis=0)  # ms: s-step, scan, momentum
     pts = run.nx * run.ny * run.nz
-    achieved = BYTES_PER_POINT_STAGE * pts / (avg * 1e-3) / 1e9
     peak, how = measured_peak_gbs()
-    return {"bound": "hbm", "kernel": "fused RK stage (stage_s + stage_m + stage_v kernels)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": how, "ms_per_launch": avg,
-            "algorithmic_bytes_per_launch": BYTES_PER_POINT_STAGE * pts}
+    names = list(KERNEL_BYTES_PER_POINT)
+    kernels = {}
+    for n, ms in zip(names, t):
+        if ms > 0:
+            gbs = KERNEL_BYTES_PER_POINT[n] * pts / (ms * 1e-3) / 1e9
+            kernels[n] = {"ms_per_launch": float(ms), "achieved": gbs, "frac": gbs / peak,
+                          "algorithmic_bytes_per_launch": KERNEL_BYTES_PER_POINT[n] * pts}
+    dom = names[int(np.argmax(t))]
+    stage_ms = float(np.sum(t))
+    stage_gbs = BYTES_PER_POINT_STAGE * pts / (stage_ms * 1e-3) / 1e9
+    c5 = (run.nx, run.ny, run.nz) == WORKLOADS["c5"]
+    return {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved"], "peak": peak,
+            "unit": "GB/s", "frac": kernels[dom]["frac"],
+            "traffic": NCU_TRAFFIC_C5[dom] if c5 else None,
+            "traffic_source": "ncu --set full capture of the same command, profiles/ (per launch)"
+            if c5 else None,
+            "peak_source": how, "ms_per_launch": kernels[dom]["ms_per_launch"],
+            "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"],
+            "kernels": kernels,
+            "fused_stage": {"ms": stage_ms, "algorithmic_bytes": BYTES_PER_POINT_STAGE * pts,
+                            "achieved": stage_gbs, "frac": stage_gbs / peak,
+                            "note": "112 B/pt (SURVEY.md 8d) over the three kernels of one RK stage"}}
 
 
 def end_to_end(run, args, world, barrier, distributed):
@@ -414,7 +445,7 @@ def end_to_end(run, args, world, barrier, distributed):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    nbytes = lambda d: int(sum(t.numel() * 8 for t in d.values()))  # noqa: E731
+    nbytes = lambda d: int(sum(t.numel() * 8 for t in d.values())) * world  # noqa: E731  (whole job)
     pts = run.nx * run.ny * run.nz
     return {"value": pts * steps * world / (ms * 1e-3) / 1e6, "unit": "Mpts*steps/s",
             "h2d_bytes_per_step": nbytes(host_in), "d2h_bytes_per_step": nbytes(host_out),

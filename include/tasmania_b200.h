@@ -270,6 +270,13 @@ int tb200_isentropic_stage_dry(
     const tb200_field *hs, tb200_field *scratch_exn, tb200_field *scratch_mtg,
     tb200_field *scratch_s, void *stream);
 
+/* Per-kernel timing of the fused stage for the roofline report: with profiling enabled every
+ * tb200_isentropic_stage_dry call records CUDA events on its stream around its kernels;
+ * tb200_stage_profile_read waits for the last call and returns the durations [ms] of
+ * {s-step kernel (A, or S), column-scan kernel (B; 0 when S does both), momentum kernel}. */
+int tb200_stage_profile(int enable);
+int tb200_stage_profile_read(double ms[3]);
+
 /* ---- halo exchange support (2-D domain decomposition) ------------
  * pack/unpack a box of a field into/from a contiguous buffer (i fastest). */
 int tb200_pack_box(const tb200_field *field, double *buffer, const int32_t origin[3],

@@ -533,8 +533,20 @@ int s_impl() {
   return impl;
 }
 
+// optional per-kernel timing of the last stage call (tb200_stage_profile): four events on the
+// launching stream around the (up to) three kernels
+struct StageProfile {
+  bool on = false, recorded = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+} g_prof;
+
+void prof_mark(int n, cudaStream_t st) {
+  if (g_prof.on) cudaEventRecord(g_prof.ev[n], st);
+}
+
 template <int SCHEME>
 int run_stage(const StageArgs &a, cudaStream_t st) {
+  prof_mark(0, st);
   if (s_impl() != 0 && a.nz <= 64) {
     {
       constexpr int LJ = 64, WARPS = 4;
@@ -544,6 +556,7 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
       stage_a_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
       int rc = check_launch("isentropic_stage_dry/A");
       if (rc) return rc;
+      prof_mark(1, st);
     }
     {
       dim3 block(32, 4, 1);
@@ -561,10 +574,16 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
     stage_s_kernel<SCHEME><<<grid, block, 0, st>>>(a);
     int rc = check_launch("isentropic_stage_dry/S");
     if (rc) return rc;
+    prof_mark(1, st);
   }
-  if (stage_impl() != 0) {  // TMA row pipeline (default); -1 = not covered -> register windows
+  prof_mark(2, st);
+  if (stage_impl() != 0) {  // TMA shared-memory-ring kernel; -1 = not covered -> register windows
     const int rc = launch_stage_c(a, SCHEME, st);
-    if (rc >= 0) return rc;
+    if (rc >= 0) {
+      prof_mark(3, st);
+      g_prof.recorded = g_prof.on;
+      return rc;
+    }
   }
   {
     constexpr int LJ = 64, WARPS = 4;
@@ -572,7 +591,10 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
     dim3 block(32 * WARPS, 1, 1);
     dim3 grid((chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
     stage_mv_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
-    return check_launch("isentropic_stage_dry/MV");
+    const int rc = check_launch("isentropic_stage_dry/MV");
+    prof_mark(3, st);
+    g_prof.recorded = g_prof.on;
+    return rc;
   }
 }
 
@@ -581,6 +603,34 @@ bool covers(const View &v, int ni, int nj, int nk) {
 }
 
 }  // namespace
+
+extern "C" int tb200_stage_profile(int enable) {
+  if (enable && g_prof.ev[0] == nullptr) {
+    for (auto &e : g_prof.ev) {
+      if (cudaEventCreate(&e) != cudaSuccess) {
+        set_error("stage_profile: %s", cudaGetErrorString(cudaGetLastError()));
+        return TB200_ERR_CUDA;
+      }
+    }
+  }
+  g_prof.on = enable != 0;
+  g_prof.recorded = false;
+  return TB200_OK;
+}
+
+extern "C" int tb200_stage_profile_read(double ms[3]) {
+  TB200_REQUIRE(ms != nullptr && g_prof.recorded, "stage_profile_read: no profiled stage call yet");
+  if (cudaEventSynchronize(g_prof.ev[3]) != cudaSuccess) {
+    set_error("stage_profile_read: %s", cudaGetErrorString(cudaGetLastError()));
+    return TB200_ERR_CUDA;
+  }
+  for (int n = 0; n < 3; ++n) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, g_prof.ev[n], g_prof.ev[n + 1]);
+    ms[n] = t;
+  }
+  return TB200_OK;
+}
 
 extern "C" int tb200_isentropic_stage_dry(
     const tb200_isentropic_stage *cfg, const tb200_field *s_now, const tb200_field *su_now,

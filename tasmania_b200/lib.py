@@ -74,6 +74,8 @@ SIGNATURES = {
     "tb200_density_and_temperature": [_F] * 6 + [_D, _I3, _I3, _V],
     "tb200_burgers_forward_euler": [_I] + [_F] * 8 + [_D, _D, _D, _I3, _I3, _V],
     "tb200_isentropic_stage_dry": [C.POINTER(StageCfg)] + [_F] * 25 + [_V],
+    "tb200_stage_profile": [_I],
+    "tb200_stage_profile_read": [C.POINTER(C.c_double)],
     "tb200_pack_box": [_F, C.c_void_p, _I3, _I3, _V],
     "tb200_unpack_box": [_F, C.c_void_p, _I3, _I3, _V],
     "tb200_kessler": [_F] * 11 + [_D] * 5 + [C.c_uint32, _I3, _I3, _V],
