@@ -431,7 +431,7 @@ def _make_domain(nx, ny, nz, hb_type, nb, hb_kwargs, topo_time=1800.0, xlim=(-17
 
 
 def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, damp_depth=4,
-                       damp_every=True, topo_time=60.0):
+                       damp_every=True, topo_time=60.0, moist=False):
     """Dry isentropic dycore driven through the reference's OWN classes: real Domain /
     Relaxed / RK3WSSI|ForwardEulerSI / IsentropicDiagnostics / Rayleigh / HorizontalVelocity
     and the real ``IsentropicDynamicalCore.stage_array_call_dry``, chained as
@@ -445,6 +445,20 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
         g, datetime(2000, 1, 1), da(22.5, "m s^-1"), da(0.0, "m s^-1"), da(0.015, "s^-1"),
         moist=False, backend="numpy", storage_shape=shape,
     )
+    if moist:
+        # seeded, smooth water species (the moist state builder needs the meteo utilities; the
+        # dycore only sees arrays): qv decaying with height, patches of cloud and rain water
+        rng = np.random.default_rng(20261020)
+        ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+        bump = np.exp(-(((ii - 0.45 * nx) / (0.2 * nx)) ** 2) - ((jj - 0.5 * ny) / (0.25 * ny)) ** 2)
+        qv = 8e-3 * (kk + 1.0) / (nz + 1.0) * (1.0 + 0.3 * bump) * rng.uniform(0.95, 1.05, size=shape)
+        qc = 1e-3 * bump * (kk > nz // 2) * rng.uniform(0.5, 1.0, size=shape)
+        qr = 5e-4 * bump * (kk > nz // 3) * rng.uniform(0.0, 1.0, size=shape)
+        for key, arr in ((MFWV, qv), (MFCW, qc), (MFPW, qr)):
+            arr[nx:, :, :] = 0.0
+            arr[:, ny:, :] = 0.0
+            arr[:, :, nz:] = 0.0
+            state[key] = DataArray(arr, attrs={"units": "g g^-1"})
     hb = d.horizontal_boundary
     hb.reference_state = state
 
@@ -477,7 +491,7 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
     pt = float(state[P].data[0, 0, 0])
     bo, so = opts.BackendOptions, opts.StorageOptions
     P_ = prog.IsentropicPrognostic.factory(
-        scheme, flux, d, False, backend="numpy", backend_options=bo(), storage_shape=shape,
+        scheme, flux, d, moist, backend="numpy", backend_options=bo(), storage_shape=shape,
         storage_options=so(), pt=da(pt, "Pa"), eps=0.5,
     )
     damper = vd.VerticalDamping.factory(
@@ -488,8 +502,13 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
                                 storage_options=so())
     diags = idiag.IsentropicDiagnostics(g, backend="numpy", backend_options=bo(),
                                         storage_shape=shape, storage_options=so())
-    outnames = (S, SU, U, SV, V)
+    outnames = (S, SU, U, SV, V) + ((MFWV, MFCW, MFPW) if moist else ())
+    wc = dd.WaterConstituent(g, clipping=True, backend="numpy", backend_options=bo(),
+                             storage_options=so()) if moist else None
     fake = types.SimpleNamespace(
+        _water_constituent=wc,
+        **({f"_{q}_{t}": np.zeros(shape) for q in ("sqv", "sqc", "sqr") for t in ("now", "int", "new")}
+           if moist else {}),
         horizontal_boundary=hb,
         output_properties={k: {"units": state[k].attrs["units"]} for k in outnames},
         _damp=True, _damp_at_every_stage=damp_every, stages=P_.stages, _prognostic=P_,
@@ -497,7 +516,9 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
         _s_ref=np.zeros(shape), _su_ref=np.zeros(shape), _sv_ref=np.zeros(shape),
         _s_now=None, _su_now=None, _sv_now=None,
     )
-    innames = (S, MTG, SU, U, SV, V)
+    innames = (S, MTG, SU, U, SV, V) + ((MFWV, MFCW, MFPW) if moist else ())
+    stage_call = (dyc.IsentropicDynamicalCore.stage_array_call_moist if moist
+                  else dyc.IsentropicDynamicalCore.stage_array_call_dry)
     cur = {k: state[k].data.copy() for k in innames}
     cur["time"] = state["time"]
     extra = {k: state[k].data.copy() for k in (P, EXN, H)}
@@ -509,9 +530,7 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
         g.update_topography((step + 1) * dt)
         st_in = cur
         for stage in range(P_.stages):
-            dyc.IsentropicDynamicalCore.stage_array_call_dry(
-                fake, stage, st_in, {}, dt, stage_outs[stage]
-            )
+            stage_call(fake, stage, st_in, {}, dt, stage_outs[stage])
             st_in = dict(stage_outs[stage])
             st_in.setdefault(MTG, cur[MTG])
             if step == 0 and stage == 0:
@@ -548,6 +567,11 @@ CASES = {
         "isen_dry_rk3_cen", 17, 15, 5, "rk3ws_si", "centered", 1, 4, 3, 4.0, damp_every=False),
     "isen_dry_fe_upw": lambda: gen_isentropic_dry(
         "isen_dry_fe_upw", 16, 18, 5, "forward_euler_si", "upwind", 1, 3, 4, 3.0),
+    "isen_moist_rk3_5th": lambda: gen_isentropic_dry(
+        "isen_moist_rk3_5th", 23, 19, 8, "rk3ws_si", "fifth_order_upwind", 3, 6, 4, 5.0, moist=True),
+    "isen_moist_fe_3rd": lambda: gen_isentropic_dry(
+        "isen_moist_fe_3rd", 17, 21, 6, "forward_euler_si", "third_order_upwind", 2, 5, 3, 4.0,
+        moist=True),
 }
 
 

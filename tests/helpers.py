@@ -52,12 +52,14 @@ def oracle_dry_run(fx, nsteps=None):
     scheme, flux = (str(v) for v in fx["scheme"])
     grid = oi.Grid(nx, ny, nz, dx, dy, dz, fx["z_hl"], fx["z"])
     hb = ob.Relaxed(nx, ny, nz, nb, nr)
-    names = (S, MTG, SU, U, SV, V, P, EXN, H)
+    moist = ("init_" + oi.MFWV) in fx.files
+    qnames = (oi.MFWV, oi.MFCW, oi.MFPW) if moist else ()
+    names = (S, MTG, SU, U, SV, V, P, EXN, H) + qnames
     state = {n: fx["init_" + n].copy() for n in names}
     state["time"] = datetime(2000, 1, 1)
     hb.reference_state = {n: state[n].copy() for n in names}
     topo = Topography(fx["topo_steady"], topo_time)
-    dyc = oi.IsentropicDycore(grid, hb, topo, scheme=scheme, flux=flux, pt=pt, eps=eps,
+    dyc = oi.IsentropicDycore(grid, hb, topo, moist=moist, scheme=scheme, flux=flux, pt=pt, eps=eps,
                               damp=True, damp_at_every_stage=bool(damp_every),
                               damp_depth=damp_depth, damp_max=damp_max)
     dt = timedelta(seconds=dt_s)
@@ -67,8 +69,8 @@ def oracle_dry_run(fx, nsteps=None):
         out = dyc(state, {}, dt)
         if step == 0:
             stage0 = {n: dyc._stage_states[0][n].copy() if dyc.stages > 1 else out[n].copy()
-                      for n in (S, SU, U, SV, V)}
-        new = {n: out[n].copy() for n in (S, SU, U, SV, V)}
+                      for n in (S, SU, U, SV, V) + qnames}
+        new = {n: out[n].copy() for n in (S, SU, U, SV, V) + qnames}
         new["time"] = out["time"]
         for n in (P, EXN, H, MTG):
             new[n] = state[n].copy()

@@ -199,6 +199,21 @@ def test_dry_dycore_orchestration(case):
         eq(final[n], fx["final_" + n])
 
 
+@pytest.mark.parametrize("case", ("isen_moist_rk3_5th", "isen_moist_fe_3rd"))
+def test_moist_dycore_orchestration(case):
+    """Moist stage (tracer densities -> K1 with tracers -> mass fractions -> boundary -> damping
+    -> velocities) against the reference's own ``stage_array_call_moist``."""
+    fx = hp.load(case)
+    final, stage0, _ = hp.oracle_dry_run(fx)
+    nx, ny, nz = (int(v) for v in fx["dims"][:3])
+    qn = (oi.MFWV, oi.MFCW, oi.MFPW)
+    for n in (hp.S, hp.SU, hp.SV, hp.U, hp.V) + qn:
+        eq(stage0[n][: nx + 1, : ny + 1, :nz], fx["stage0_" + n][: nx + 1, : ny + 1, :nz])
+    for n in (hp.S, hp.SU, hp.SV, hp.U, hp.V, hp.MTG, hp.P, hp.EXN, hp.H) + qn:
+        eq(final[n], fx["final_" + n])
+    assert np.abs(final[oi.MFCW]).max() > 0 and np.abs(final[oi.MFPW]).max() > 0
+
+
 # ------------------------------------------------------------------ K11 Kessler
 def test_kessler_family_bitwise():
     """Every K11 stencil of the oracle against the reference's own numpy definitions
