@@ -257,6 +257,13 @@ typedef struct tb200_isentropic_stage {
   double dt_full;   /* full time step used by the damping [s] */
   double dx, dy, dz, eps, pt, theta_s;
   double constants[4]; /* pref, rd, g, cp */
+  /* Splitting a stage for communication/computation overlap (2-D domain decomposition):
+   * part 0 = the whole stage; part 1 = everything except the interior blocks of the momentum
+   * kernel, i.e. all results a neighbour's halo needs; part 2 = those interior blocks.
+   * rim[4] = number of owned columns / rows next to the (west, east, south, north) edge that
+   * must be final after part 1 (0 for an edge without a neighbour). */
+  int32_t part;
+  int32_t rim[4];
 } tb200_isentropic_stage;
 
 int tb200_isentropic_stage_dry(

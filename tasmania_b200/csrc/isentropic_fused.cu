@@ -332,10 +332,10 @@ __global__ void __launch_bounds__(128, 4) stage_mv_kernel(const StageArgs a) {
   constexpr int E = F::extent;
   constexpr int NW = 2 * E;
   const int lane = threadIdx.x & 31;
-  const int xw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int xw = (blockIdx.x + a.bx0) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (xw * MV_COLS >= a.nx) return;  // warp-uniform
   const int c = xw * MV_COLS + lane - 1;
-  const int j0 = blockIdx.y * LJ;
+  const int j0 = (blockIdx.y + a.by0) * LJ;
   const int jend = min(j0 + LJ, a.ny);
   const int k = blockIdx.z;
   const int nx = a.nx, ny = a.ny, nb = a.nb;
@@ -544,8 +544,47 @@ void prof_mark(int n, cudaStream_t st) {
   if (g_prof.on) cudaEventRecord(g_prof.ev[n], st);
 }
 
+// The momentum kernel over a rectangle of its block grid.
+template <int SCHEME, int LJ, int WARPS>
+int launch_mv_rect(StageArgs a, int bx0, int bx1, int by0, int by1, cudaStream_t st) {
+  if (bx1 <= bx0 || by1 <= by0) return TB200_OK;
+  a.bx0 = bx0;
+  a.by0 = by0;
+  dim3 block(32 * WARPS, 1, 1);
+  dim3 grid(bx1 - bx0, by1 - by0, a.nz);
+  stage_mv_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
+  return check_launch("isentropic_stage_dry/MV");
+}
+
+// part 0: the whole block grid; part 1: the blocks holding the a.rim columns / rows next to an
+// edge with a neighbour (south and north strips over all columns, west and east blocks over the
+// remaining strips); part 2: the interior rectangle.
+template <int SCHEME, int LJ, int WARPS>
+int launch_mv_part(const StageArgs &a, int gx, int gy, cudaStream_t st) {
+  if (a.part == 0) return launch_mv_rect<SCHEME, LJ, WARPS>(a, 0, gx, 0, gy, st);
+  const int cols = WARPS * MV_COLS;
+  // first interior block after the west rim / first east-rim block, likewise for the strips
+  int xw = a.rim[0] > 0 ? (a.rim[0] + cols - 1) / cols : 0;
+  int xe = a.rim[1] > 0 ? (a.nx - a.rim[1]) / cols : gx;
+  int ys = a.rim[2] > 0 ? (a.rim[2] + LJ - 1) / LJ : 0;
+  int yn = a.rim[3] > 0 ? (a.ny - a.rim[3]) / LJ : gy;
+  xe = max(min(xe, gx), xw);
+  yn = max(min(yn, gy), ys);
+  if (a.part == 2) return launch_mv_rect<SCHEME, LJ, WARPS>(a, xw, xe, ys, yn, st);
+  int rc = launch_mv_rect<SCHEME, LJ, WARPS>(a, 0, gx, 0, ys, st);
+  if (!rc) rc = launch_mv_rect<SCHEME, LJ, WARPS>(a, 0, gx, yn, gy, st);
+  if (!rc) rc = launch_mv_rect<SCHEME, LJ, WARPS>(a, 0, xw, ys, yn, st);
+  if (!rc) rc = launch_mv_rect<SCHEME, LJ, WARPS>(a, xe, gx, ys, yn, st);
+  return rc;
+}
+
 template <int SCHEME>
 int run_stage(const StageArgs &a, cudaStream_t st) {
+  if (a.part == 2) {  // the s-step and the scans ran with part 1
+    constexpr int LJ = 64, WARPS = 4;
+    const int chunks = (a.nx + MV_COLS - 1) / MV_COLS;
+    return launch_mv_part<SCHEME, LJ, WARPS>(a, (chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, st);
+  }
   prof_mark(0, st);
   if (s_impl() != 0 && a.nz <= 64) {
     {
@@ -577,7 +616,7 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
     prof_mark(1, st);
   }
   prof_mark(2, st);
-  if (stage_impl() != 0) {  // TMA shared-memory-ring kernel; -1 = not covered -> register windows
+  if (stage_impl() != 0 && a.part == 0) {  // TMA shared-memory-ring kernel; -1 = not covered
     const int rc = launch_stage_c(a, SCHEME, st);
     if (rc >= 0) {
       prof_mark(3, st);
@@ -588,10 +627,8 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
   {
     constexpr int LJ = 64, WARPS = 4;
     const int chunks = (a.nx + MV_COLS - 1) / MV_COLS;
-    dim3 block(32 * WARPS, 1, 1);
-    dim3 grid((chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
-    stage_mv_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
-    const int rc = check_launch("isentropic_stage_dry/MV");
+    const int gx = (chunks + WARPS - 1) / WARPS, gy = (a.ny + LJ - 1) / LJ;
+    const int rc = launch_mv_part<SCHEME, LJ, WARPS>(a, gx, gy, st);
     prof_mark(3, st);
     g_prof.recorded = g_prof.on;
     return rc;
@@ -654,6 +691,9 @@ extern "C" int tb200_isentropic_stage_dry(
   a.gamma = view(gamma); a.rmat = view(rmat); a.hs = view(hs);
   a.exn = view(scratch_exn); a.mtg = view(scratch_mtg); a.spre = view(scratch_s);
   a.nx = cfg->nx; a.ny = cfg->ny; a.nz = cfg->nz; a.nb = cfg->nb; a.damp = cfg->damp;
+  a.part = cfg->part;
+  for (int n = 0; n < 4; ++n) a.rim[n] = cfg->rim[n];
+  TB200_REQUIRE(a.part >= 0 && a.part <= 2, "isentropic_stage_dry: part must be 0, 1 or 2");
   a.dt = cfg->dt; a.dt_full = cfg->dt_full; a.dx = cfg->dx; a.dy = cfg->dy; a.dz = cfg->dz;
   a.eps = cfg->eps; a.pt = cfg->pt; a.theta_s = cfg->theta_s;
   a.pref = cfg->constants[0]; a.rd = cfg->constants[1]; a.g = cfg->constants[2];

@@ -13,6 +13,8 @@ struct StageArgs {
   View s_ref, su_ref, sv_ref, u_ref, v_ref;
   View gamma, rmat, hs, exn, mtg, spre;
   int nx, ny, nz, nb, damp;
+  int bx0, by0;    // block offsets of a partial launch of the momentum kernel
+  int part, rim[4];  // tb200_isentropic_stage.part / .rim
   double dt, dt_full, dx, dy, dz, eps, pt, theta_s, pref, rd, g, cp;
   FluxConst fc;
   CDiv two_dx, two_dy, cpref;

@@ -33,6 +33,7 @@ scatters them.  There is no global reduction on the path.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from datetime import datetime, timedelta
 from typing import List, Optional, Sequence
@@ -361,13 +362,54 @@ class SubdomainDryCore:
         return a[hw:self.nx - he, hs:self.ny - hn, :self.nz]
 
 
+class Overlap:
+    """Runs the halo exchange of a stage on a side stream, under the interior blocks of the
+    momentum kernel (IsentropicDynamicalCore.stage_array_call drives it):
+
+        main stream   A, B, MV(rim blocks) | MV(interior blocks) ............ | next stage
+        side stream                        | pack, send/recv, unpack, seam fix-up |
+
+    ``rim`` = local columns / rows next to each edge with a neighbour that must be final before
+    the exchange starts: the halo itself plus the ``halo`` owned points the neighbour receives.
+    """
+
+    def __init__(self, sub):
+        self.sub = sub
+        hw, he, hs, hn = sub.decomp.halos(sub.rank)
+        h = sub.decomp.halo
+        self.rim = tuple(x + h if x else 0 for x in (hw, he, hs, hn))
+        self.side = torch.cuda.Stream()
+        self.rim_done = torch.cuda.Event()
+        self.exchanged = torch.cuda.Event()
+        self.events = None  # optional (start, end) timing events of the exchanges
+
+    def after_rim(self, stage, out):
+        main = torch.cuda.current_stream()
+        self.rim_done.record(main)
+        self.side.wait_event(self.rim_done)
+        with torch.cuda.stream(self.side):
+            if self.events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            self.sub.halo.exchange(self.sub.exchange_fields(out))
+            self.sub.fix_seam_velocities(out)
+            if self.events is not None:
+                e1.record()
+                self.events.append((e0, e1))
+            self.exchanged.record(self.side)
+
+    def after_interior(self, stage, out):
+        # whatever comes next on the main stream reads the exchanged halos
+        torch.cuda.current_stream().wait_event(self.exchanged)
+
+
 class DecomposedDryRun:
     """The timed loop of ``bench.py`` on N GPUs: one ``SubdomainDryCore`` per process,
     ``torch.distributed`` (NCCL) halo exchange after every RK stage.  Weak scaling: every rank
     owns ``nx x ny x nz`` points; the global domain grows with the process grid so that the
     grid spacing -- and with it the physics per point -- stays (almost exactly) the same."""
 
-    def __init__(self, nx, ny, nz, rank, world, device=None):
+    def __init__(self, nx, ny, nz, rank, world, device=None, overlap=False):
         px, py = process_grid(world)
         self.decomposition = f"{px}x{py}"
         self.decomp = Decomposition(nx * px, ny * py, px, py)
@@ -376,11 +418,29 @@ class DecomposedDryRun:
         self.nx, self.ny, self.nz = nx, ny, nz
         self.names, self.out_names = self.sub.names, self.sub.out_names
         self.dyc = self.sub.dyc
-        self.dyc.after_stage = self._after_stage
+        self.exchange_events = None  # set to [] to time the exchanges with CUDA events
+        self.overlap = Overlap(self.sub) if (overlap and world > 1) else None
+        if self.overlap is not None:
+            self.dyc.overlap = self.overlap
+        else:
+            self.dyc.after_stage = self._after_stage
 
     def _after_stage(self, stage, out):
+        if os.environ.get("TB200_SKIP_EXCHANGE"):  # timing experiments only: results are wrong
+            return
+        if self.exchange_events is not None:  # optional device timing of the exchange
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         self.sub.halo.exchange(self.sub.exchange_fields(out))
         self.sub.fix_seam_velocities(out)
+        if self.exchange_events is not None:
+            e1.record()
+            self.exchange_events.append((e0, e1))
+
+    def exchange_ms(self):
+        """Mean device time of one halo exchange + seam fix-up (after a synchronize)."""
+        ev = (self.overlap.events if self.overlap is not None else self.exchange_events) or []
+        return float(np.mean([a.elapsed_time(b) for a, b in ev])) if ev else None
 
     @property
     def state(self):

@@ -276,6 +276,8 @@ class IsentropicDynamicalCore(StencilFactory):
         # hook run after every stage on that stage's output fields (halo exchange of a
         # decomposed run); None on a single device
         self.after_stage = None
+        # overlap controller of a decomposed run (tasmania_b200.distributed.Overlap) or None
+        self.overlap = None
 
     @property
     def stages(self):
@@ -304,7 +306,16 @@ class IsentropicDynamicalCore(StencilFactory):
                         "Reference state not set in the object handling the horizontal boundary "
                         "conditions, but needed by the wave absorber.") from None
         if self._fused and not tendencies:
-            return self._stage_fused(stage, state, timestep, out_state)
+            if self.overlap is None:
+                return self._stage_fused(stage, state, timestep, out_state)
+            # communication / computation overlap of a decomposed run: everything a neighbour
+            # needs first, then the halo exchange (started by the hook on its own stream) runs
+            # under the interior blocks of the momentum kernel
+            self._stage_fused(stage, state, timestep, out_state, part=1, rim=self.overlap.rim)
+            self.overlap.after_rim(stage, out_state)
+            self._stage_fused(stage, state, timestep, out_state, part=2, rim=self.overlap.rim)
+            self.overlap.after_interior(stage, out_state)
+            return None
         if self._moist:
             wc = self._water_constituent
             tag = "now" if stage == 0 else "int"
@@ -329,7 +340,7 @@ class IsentropicDynamicalCore(StencilFactory):
         hb.set_outermost_layers_y(out_state[V], field_name=V, time=out_state.get("time"))
 
     # ---- the fused stage: three kernels
-    def _stage_fused(self, stage, state, timestep, out_state):
+    def _stage_fused(self, stage, state, timestep, out_state, part=0, rim=(0, 0, 0, 0)):
         g, hb, pr = self.grid, self.horizontal_boundary, self._prognostic
         if stage == 0:
             pr._now = {n: state[n] for n in (S, MTG, SU, SV)}
@@ -345,6 +356,8 @@ class IsentropicDynamicalCore(StencilFactory):
         cfg.pt, cfg.theta_s = pr._pt, float(g.z_on_interface_levels[-1])
         rpc = pr._diagnostics.rpc
         cfg.constants[:] = [rpc["pref"], rpc["rd"], rpc["g"], rpc["cp"]]
+        cfg.part = part
+        cfg.rim[:] = list(rim)
         pr._diagnostics._set_topography()
         ref, now = hb.reference_state, pr._now
         f = lib.as_field
@@ -357,7 +370,7 @@ class IsentropicDynamicalCore(StencilFactory):
             f(hb._gamma2d), f(rmat), f(pr._diagnostics._topo2d),
             f(self._scratch[0]), f(self._scratch[1]), f(self._scratch[2]), lib.current_stream())
         lib.check(rc, "tb200_isentropic_stage_dry")
-        if "time" in state:
+        if "time" in state and part != 1:
             out_state["time"] = state["time"] + dtr
 
     # ---- framework/dycore.py:L383-L462

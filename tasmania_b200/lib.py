@@ -39,6 +39,7 @@ class StageCfg(C.Structure):
         ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double), ("eps", C.c_double),
         ("pt", C.c_double), ("theta_s", C.c_double),
         ("constants", C.c_double * 4),
+        ("part", C.c_int32), ("rim", C.c_int32 * 4),
     ]
 
 

@@ -59,3 +59,26 @@ def test_halo_pack_unpack_roundtrip():
         np.testing.assert_array_equal(out[10:14, 1:16, :nz], src[n][3:7, 2:17, :nz])
         out[10:14, 1:16, :nz] = 0.0
         assert not out.any()
+
+
+def test_two_rank_nccl_run_equals_single_device_bitwise():
+    """Real multi-process run (torchrun, NCCL) when the box has >= 2 GPUs: tests/mgpu_check.py
+    compares every rank's owned block with the single-domain run, with and without
+    communication / computation overlap."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for port, extra in ((29531, []), (29532, ["--overlap"])):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port),
+               os.path.join(root, "tests", "mgpu_check.py"), *extra]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+        assert res.returncode == 0 and "MGPU-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
