@@ -303,6 +303,8 @@ def run_b200(args):
     barrier()
     launches = tblib.launch_count() - launches0  # kernels of libtasmania_b200.so, this rank
     ms = ev0.elapsed_time(ev1)
+    if os.environ.get("TB200_DEBUG_RANKS"):
+        print(f"[rank {rank}] {ms / args.steps:.3f} ms/step on its own clock", file=sys.stderr, flush=True)
     if distributed:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,7 +329,11 @@ def run_b200(args):
         if run.overlap is not None:
             run.overlap.events = None
     # ---- roofline of the dominant kernel (stage_m: the momentum step), timed live
-    roof = kernel_roofline(run, args) if not distributed else None
+    roof = kernel_roofline(run, args) if (not distributed or os.environ.get("TB200_DEBUG_RANKS")) else None
+    if distributed and roof is not None:
+        print(f"[rank {rank}] kernels " + str({k.split()[0]: round(v["ms_per_launch"], 3)
+                                                for k, v in roof["kernels"].items()}), file=sys.stderr, flush=True)
+        roof = None
     # ---- end to end through the public API with host buffers
     e2e = end_to_end(run, args, world, barrier, distributed)
 

@@ -544,6 +544,287 @@ void prof_mark(int n, cudaStream_t st) {
   if (g_prof.on) cudaEventRecord(g_prof.ev[n], st);
 }
 
+// ---------------------------------------------------------------- kernel MV, ring version
+// Same decomposition and arithmetic as stage_mv_kernel (one warp = 30 columns x LJ rows of one
+// level, marching in j), but the rotating state lives in WARP-PRIVATE shared-memory rings
+// instead of register windows: each row of su_int / sv_int (and mtg_now / mtg_new) is loaded
+// once with coalesced LDGs, stored into the warp's ring (lanes 0..4 add the five halo columns)
+// and every stencil neighbour -- the six rows of the y stencil, the x neighbours, the Montgomery
+// cross -- is then an LDS at an immediate offset from ONE per-row base.  The rings are mirrored
+// (a row stored at slot s < W-1 is also stored at s + R) so that W consecutive rows are always
+// contiguous: no modulo per access.  This removes the ~100 register moves and most of the
+// address arithmetic per row of the register-window kernel; warps stay autonomous (one
+// __syncwarp per row, no block barrier).
+constexpr int RW = 38;                    // ring row: columns c_0-3 .. c_0+33 (+1 pad)
+constexpr int SU_RING = 8, SU_MIRROR = 5; // y stencil spans up to 6 rows
+constexpr int MT_RING = 4, MT_MIRROR = 2; // Montgomery rows r-1, r, r+1
+constexpr int SU_ROWS = SU_RING + SU_MIRROR, MT_ROWS = MT_RING + MT_MIRROR;
+constexpr int WARP_DOUBLES = (2 * SU_ROWS + 2 * MT_ROWS) * RW;
+
+struct RingLoads {   // values on their way into the rings (row r+E of su/sv, row r+1 of mtg)
+  double su, sv, mn, mw;      // own column
+  double hsu, hsv, hmn, hmw;  // halo column of lanes 0..4
+};
+struct OwnLoads {    // own-column values without reuse, requested one row ahead
+  double v_n, u_c, s_pre, s_now, su_now, sv_now, gam;
+};
+
+template <int SCHEME, int LJ>
+__global__ void __launch_bounds__(128, 4) stage_mv_ring_kernel(const StageArgs a) {
+  using F = Flux<SCHEME>;
+  constexpr int E = F::extent;
+  constexpr int NW = 2 * E;
+  extern __shared__ double ring_smem[];
+  const int lane = threadIdx.x & 31;
+  const int xw = (blockIdx.x + a.bx0) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (xw * MV_COLS >= a.nx) return;  // warp-uniform (no block-wide barrier in this kernel)
+  double *r_su = ring_smem + (threadIdx.x >> 5) * WARP_DOUBLES;
+  double *r_sv = r_su + SU_ROWS * RW;
+  double *r_mn = r_sv + SU_ROWS * RW;
+  double *r_mw = r_mn + MT_ROWS * RW;
+  const int c = xw * MV_COLS + lane - 1;
+  const int j0 = (blockIdx.y + a.by0) * LJ;
+  const int jend = min(j0 + LJ, a.ny);
+  const int k = blockIdx.z;
+  const int nx = a.nx, ny = a.ny, nb = a.nb;
+
+  const bool out_lane = lane >= 1 && lane <= MV_COLS && c < nx;
+  const bool col_int = c >= nb && c < nx - nb;
+  const int cm = min(max(c, 0), nx - 1);  // own column, clamped into the row
+  // halo column of lanes 0..4: ring columns 0, 1, 2 (left of lane 0) and 35, 36 (right of lane 31)
+  const bool halo_lane = lane < 5;
+  const int th = lane < 3 ? lane : 32 + lane;                       // ring column of the halo value
+  const int ch = min(max(xw * MV_COLS - 1 - 3 + th, 0), nx - 1);     // its grid column, clamped
+  const int t = lane + 3;                                            // ring column of the own value
+
+  const unsigned row = (unsigned)a.s_now.s1 * 8u;
+  const unsigned plane = (unsigned)k * (unsigned)a.s_now.s2 * 8u;
+  const unsigned grow = (unsigned)a.gamma.s1 * 8u;
+  const double r_damp = a.damp ? a.rmat.ld(0, 0, k) : 0.0;
+  const double one_m_eps = 1.0 - a.eps;
+  const int r0 = j0 > 0 ? j0 - 1 : 0;  // first row computed (warm-up row unless j0 == 0)
+
+  // ring slots: su / sv row rho sits at slot (rho - (r0 - E)) & 7, mtg row rho at (rho - (r0 - 1)) & 3
+  auto put_su = [&](int q, double vsu, double vsv, double hsu, double hsv) {
+    const int s = q & (SU_RING - 1);
+    r_su[s * RW + t] = vsu;
+    r_sv[s * RW + t] = vsv;
+    if (halo_lane) {
+      r_su[s * RW + th] = hsu;
+      r_sv[s * RW + th] = hsv;
+    }
+    if (s < SU_MIRROR) {
+      r_su[(s + SU_RING) * RW + t] = vsu;
+      r_sv[(s + SU_RING) * RW + t] = vsv;
+      if (halo_lane) {
+        r_su[(s + SU_RING) * RW + th] = hsu;
+        r_sv[(s + SU_RING) * RW + th] = hsv;
+      }
+    }
+  };
+  auto put_mt = [&](int q, double vmn, double vmw, double hmn, double hmw) {
+    const int s = q & (MT_RING - 1);
+    r_mn[s * RW + t] = vmn;
+    r_mw[s * RW + t] = vmw;
+    if (halo_lane) {
+      r_mn[s * RW + th] = hmn;
+      r_mw[s * RW + th] = hmw;
+    }
+    if (s < MT_MIRROR) {
+      r_mn[(s + MT_RING) * RW + t] = vmn;
+      r_mw[(s + MT_RING) * RW + t] = vmw;
+      if (halo_lane) {
+        r_mn[(s + MT_RING) * RW + th] = hmn;
+        r_mw[(s + MT_RING) * RW + th] = hmw;
+      }
+    }
+  };
+
+  // ---- prologue: su / sv rows r0-E .. r0+E-1 (ring rows 0 .. 2E-1), mtg rows r0-1, r0
+  const unsigned col_o = (unsigned)cm * 8u, col_h = (unsigned)ch * 8u;
+#pragma unroll
+  for (int m = 0; m < NW; ++m) {
+    const unsigned o = plane + (unsigned)max(r0 - E + m, 0) * row;
+    put_su(m, ldo(a.su_int.p, o + col_o), ldo(a.sv_int.p, o + col_o),
+           halo_lane ? ldo(a.su_int.p, o + col_h) : 0.0, halo_lane ? ldo(a.sv_int.p, o + col_h) : 0.0);
+  }
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const unsigned o = plane + (unsigned)max(r0 - 1 + m, 0) * row;
+    put_mt(m, ldo(a.mtg_now.p, o + col_o), ldo(a.mtg.p, o + col_o),
+           halo_lane ? ldo(a.mtg_now.p, o + col_h) : 0.0, halo_lane ? ldo(a.mtg.p, o + col_h) : 0.0);
+  }
+  unsigned o_c = plane + (unsigned)r0 * row + col_o;  // own column, row r
+  unsigned o_h = plane + (unsigned)r0 * row + col_h;  // halo column, row r
+  unsigned o_g = (unsigned)r0 * grow + col_o;         // gamma (2-D)
+  __syncwarp();
+  double fy_su, fy_sv;
+  {
+    double ysu[NW], ysv[NW];
+#pragma unroll
+    for (int m = 0; m < NW; ++m) {
+      ysu[m] = r_su[m * RW + t];
+      ysv[m] = r_sv[m * RW + t];
+    }
+    const double vq = F::prep(ldo(a.v_int.p, o_c), a.fc);
+    fy_su = F::eval_v(vq, ysu);
+    fy_sv = F::eval_v(vq, ysv);
+  }
+  double sv_prev = 0.0, s_prev = 0.0;
+
+  // rows up to jend + E are touched: inside the allocation (>= nz + 1 planes, checked on the host)
+  auto load_ring = [&](unsigned oc, unsigned oh) {
+    RingLoads L;
+    L.su = ldo(a.su_int.p, oc + E * row);
+    L.sv = ldo(a.sv_int.p, oc + E * row);
+    L.mn = ldo(a.mtg_now.p, oc + row);
+    L.mw = ldo(a.mtg.p, oc + row);
+    L.hsu = L.hsv = L.hmn = L.hmw = 0.0;
+    if (halo_lane) {
+      L.hsu = ldo(a.su_int.p, oh + E * row);
+      L.hsv = ldo(a.sv_int.p, oh + E * row);
+      L.hmn = ldo(a.mtg_now.p, oh + row);
+      L.hmw = ldo(a.mtg.p, oh + row);
+    }
+    return L;
+  };
+  auto load_own = [&](unsigned oc, unsigned og) {
+    OwnLoads L;
+    L.v_n = ldo(a.v_int.p, oc + row);
+    L.u_c = ldo(a.u_int.p, oc);
+    L.s_pre = ldo(a.spre.p, oc);
+    L.s_now = ldo(a.s_now.p, oc);
+    L.su_now = ldo(a.su_now.p, oc);
+    L.sv_now = ldo(a.sv_now.p, oc);
+    L.gam = ldo(a.gamma.p, og);
+    return L;
+  };
+  auto prefetch_row = [&](unsigned oc) {
+    prefetch_l2(a.su_int.p, oc + E * row);
+    prefetch_l2(a.sv_int.p, oc + E * row);
+    prefetch_l2(a.v_int.p, oc + row);
+    prefetch_l2(a.u_int.p, oc);
+    prefetch_l2(a.spre.p, oc);
+    prefetch_l2(a.s_now.p, oc);
+    prefetch_l2(a.su_now.p, oc);
+    prefetch_l2(a.sv_now.p, oc);
+    prefetch_l2(a.mtg_now.p, oc + row);
+    prefetch_l2(a.mtg.p, oc + row);
+  };
+
+  RingLoads pend = load_ring(o_c, o_h);  // rows r0+E / r0+1: stored at the top of iteration r0
+  OwnLoads nxt = load_own(o_c, o_g);
+  for (int r = r0; r < jend; ++r) {
+    const int q = r - r0;
+    // ---- the rows requested during the previous iteration enter the rings ...
+    put_su(q + NW, pend.su, pend.sv, pend.hsu, pend.hsv);
+    put_mt(q + 2, pend.mn, pend.mw, pend.hmn, pend.hmw);
+    // ... and the next ones are requested (in flight while row r is computed)
+    pend = load_ring(o_c + row, o_h + row);
+    const OwnLoads cur = nxt;
+    nxt = load_own(o_c + row, o_g + grow);
+    if (r + 3 < jend) prefetch_row(o_c + 3 * row);
+    __syncwarp();
+
+    // ---- one base per ring and row: every neighbour below is an immediate offset from it
+    const double *bsu = r_su + ((q + 1) & (SU_RING - 1)) * RW + t;  // rows r-E+1 .. r+E
+    const double *bsv = bsu + SU_ROWS * RW;
+    const double *bmn = r_mn + (q & (MT_RING - 1)) * RW + t;        // rows r-1, r, r+1
+    const double *bmw = bmn + MT_ROWS * RW;
+
+    // ---- y-face r+1
+    double ysu[NW], ysv[NW];
+#pragma unroll
+    for (int m = 0; m < NW; ++m) {
+      ysu[m] = bsu[m * RW];
+      ysv[m] = bsv[m * RW];
+    }
+    const double vq = F::prep(cur.v_n, a.fc);
+    const double fy_su_p = F::eval_v(vq, ysu);
+    const double fy_sv_p = F::eval_v(vq, ysv);
+
+    // ---- left x-face of column c at row r (window entry E-1): phi[c-E .. c+E-1]
+    const double uq = F::prep(cur.u_c, a.fc);
+    double xs[NW], ys[NW];
+#pragma unroll
+    for (int m = 0; m < NW; ++m) {
+      xs[m] = m == E ? ysu[E - 1] : bsu[(E - 1) * RW + (m - E)];
+      ys[m] = m == E ? ysv[E - 1] : bsv[(E - 1) * RW + (m - E)];
+    }
+    const double fx_su = F::eval_v(uq, xs);
+    const double fx_sv = F::eval_v(uq, ys);
+    const double fx_su_p = __shfl_down_sync(0xffffffffu, fx_su, 1);
+    const double fx_sv_p = __shfl_down_sync(0xffffffffu, fx_sv, 1);
+
+    // ---- point update (prognostics/utils.py:L191-L204)
+    const bool interior = col_int && r >= nb && r < ny - nb;
+    double s = cur.s_pre, su = 0.0, sv = 0.0;
+    if (interior) {
+      {
+        const double div = (fx_su_p - fx_su) / a.fc.dx + (fy_su_p - fy_su) / a.fc.dy;
+        const double pg_now = one_m_eps * cur.s_now * (bmn[RW + 1] - bmn[RW - 1]) / a.two_dx;
+        const double pg_new = a.eps * s * (bmw[RW + 1] - bmw[RW - 1]) / a.two_dx;
+        su = cur.su_now - a.dt * (div + pg_now + pg_new - 0.0);
+      }
+      {
+        const double div = (fx_sv_p - fx_sv) / a.fc.dx + (fy_sv_p - fy_sv) / a.fc.dy;
+        const double pg_now = one_m_eps * cur.s_now * (bmn[2 * RW] - bmn[0]) / a.two_dy;
+        const double pg_new = a.eps * s * (bmw[2 * RW] - bmw[0]) / a.two_dy;
+        sv = cur.sv_now - a.dt * (div + pg_now + pg_new - 0.0);
+      }
+    }
+    const double gam = cur.gam;
+    double s_ref = 0.0, su_ref = 0.0, sv_ref = 0.0;
+    if (gam != 0.0 || r_damp != 0.0) {
+      s_ref = ldo(a.s_ref.p, o_c);
+      su_ref = ldo(a.su_ref.p, o_c);
+      sv_ref = ldo(a.sv_ref.p, o_c);
+    }
+    if (!interior && gam != 1.0) {  // not reached with a Relaxed boundary (gamma == 1 there)
+      su = ldo(a.su_new.p, o_c);
+      sv = ldo(a.sv_new.p, o_c);
+    }
+    if (gam != 0.0) {  // hb.enforce_raw, dycore.py:L686
+      s = relax_point(gam, s, s_ref);
+      su = relax_point(gam, su, su_ref);
+      sv = relax_point(gam, sv, sv_ref);
+    }
+    if (r_damp != 0.0) {  // dycore.py:L694-L700
+      s = damp_point(cur.s_now, s, s_ref, r_damp, a.dt_full);
+      su = damp_point(cur.su_now, su, su_ref, r_damp, a.dt_full);
+      sv = damp_point(cur.sv_now, sv, sv_ref, r_damp, a.dt_full);
+    }
+
+    // ---- velocity diagnosis (dwarfs/diagnostics.py:L219-L272) and stores
+    const double su_l = __shfl_up_sync(0xffffffffu, su, 1);
+    const double s_l = __shfl_up_sync(0xffffffffu, s, 1);
+    if (out_lane && r >= j0) {
+      sto(a.s_new.p, o_c, s);
+      sto(a.su_new.p, o_c, su);
+      sto(a.sv_new.p, o_c, sv);
+      sto(a.u_new.p, o_c, c == 0 ? ldo(a.u_ref.p, o_c) : (su_l + su) / (s_l + s));
+      if (c == nx - 1) sto(a.u_new.p, o_c + 8u, ldo(a.u_ref.p, o_c + 8u));  // relaxed.py:L161-L175
+      sto(a.v_new.p, o_c, r == 0 ? ldo(a.v_ref.p, o_c) : (sv_prev + sv) / (s_prev + s));
+      if (r == ny - 1) sto(a.v_new.p, o_c + row, ldo(a.v_ref.p, o_c + row));  // relaxed.py:L177-L191
+    }
+    sv_prev = sv;
+    s_prev = s;
+    fy_su = fy_su_p;
+    fy_sv = fy_sv_p;
+    o_c += row; o_h += row; o_g += grow;
+  }
+}
+
+// TB200_MV_IMPL=window selects the register-window momentum kernel instead of the ring one
+int mv_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("TB200_MV_IMPL");
+    impl = (e != nullptr && strcmp(e, "window") == 0) ? 0 : 1;
+  }
+  return impl;
+}
+
 // The momentum kernel over a rectangle of its block grid.
 template <int SCHEME, int LJ, int WARPS>
 int launch_mv_rect(StageArgs a, int bx0, int bx1, int by0, int by1, cudaStream_t st) {
@@ -552,6 +833,10 @@ int launch_mv_rect(StageArgs a, int bx0, int bx1, int by0, int by1, cudaStream_t
   a.by0 = by0;
   dim3 block(32 * WARPS, 1, 1);
   dim3 grid(bx1 - bx0, by1 - by0, a.nz);
+  if (mv_impl() != 0) {
+    stage_mv_ring_kernel<SCHEME, LJ><<<grid, block, WARPS * WARP_DOUBLES * sizeof(double), st>>>(a);
+    return check_launch("isentropic_stage_dry/MV(ring)");
+  }
   stage_mv_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
   return check_launch("isentropic_stage_dry/MV");
 }
