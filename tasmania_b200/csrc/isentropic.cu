@@ -247,6 +247,100 @@ static int run_k3(View theta, View hs, View s, View p, View exn, View mtg, View 
   });
 }
 
+// diagnostic_variables for columns of at most 64 layers: the column of pressures stays in
+// registers between the two sweeps (read s, write p, exn, mtg, h = 40 B/point, the algorithmic
+// minimum; the generic kernel above parks p in memory and reads it back), and the Exner
+// function is evaluated eight interfaces per call with interleaved chains (pow_pos_n<8>).
+// Same operations in the same order as run_k3<1>, hence the same bits.
+struct E8 {
+  double v[8];
+};
+__device__ __noinline__ E8 exner8_diag(E8 x, double kappa, double cp) {
+  E8 r;
+  pow_pos_n<8>(x.v, kappa, r.v);
+#pragma unroll
+  for (int n = 0; n < 8; ++n) r.v[n] = cp * r.v[n];
+  return r;
+}
+
+struct DiagArgs {
+  View theta, hs, s, p, exn, mtg, h;
+  double dz, pt, rd, g, cp, kappa;
+  CDiv cpref;
+  int i0, j0, k0, di, dj, n;  // n = number of layers = interface levels - 1
+};
+
+template <bool EXACT>
+__global__ void __launch_bounds__(128, 2) diag_column_kernel(const DiagArgs a) {
+  constexpr int NC = 64;
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jj = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ii >= a.di || jj >= a.dj) return;
+  const int i = ii + a.i0, j = jj + a.j0, k0 = a.k0;
+  const int n = EXACT ? NC : a.n;
+  const double gdz = a.g * a.dz, cpg = a.cp * a.g;
+  double pr[NC];  // pr[l] = pressure at interface k0 + l + 1
+  {
+    const double *ps = &a.s(i, j, k0);
+#pragma unroll
+    for (int l = 0; l < NC; ++l) pr[l] = l < n ? __ldg(ps + l * a.s.s2) : 0.0;
+  }
+  // ---- downward pressure scan, diagnostics.py:L339-L342
+  {
+    double *pp = &a.p(i, j, k0);
+    double pk = a.pt;
+    *pp = pk;
+#pragma unroll
+    for (int l = 0; l < NC; ++l) {
+      if (l < n) {
+        pk = pk + gdz * pr[l];
+        pr[l] = pk;
+        pp[(l + 1) * a.p.s2] = pk;
+      }
+    }
+  }
+  // ---- upward sweep, diagnostics.py:L345-L360; (pb, eb, thb) belong to interface k + 1
+  const int kt = k0 + n;
+  double pb = 0.0, eb = 0.0, thb = 0.0, m = 0.0, hk = 0.0;
+  double *pe = &a.exn(i, j, k0), *pm = &a.mtg(i, j, k0), *ph = &a.h(i, j, k0);
+  const double *pth = &a.theta(i, j, k0);
+  auto interface = [&](int l1, double pa, double ea) {  // interface k0 + l1, l1 < n
+    const double tha = __ldg(pth + l1 * a.theta.s2);
+    pe[l1 * a.exn.s2] = ea;
+    if (l1 < n - 1) m = m + a.dz * eb;  // mtg[k] = mtg[k+1] + dz exn[k+1]
+    pm[l1 * a.mtg.s2] = m;
+    hk = hk - a.rd * (tha * ea + thb * eb) * (pa - pb) / (cpg * (pa + pb));
+    ph[l1 * a.h.s2] = hk;
+    pb = pa; eb = ea; thb = tha;
+  };
+#pragma unroll
+  for (int q = NC / 8 - 1; q >= 0; --q) {
+    if (8 * q < n) {
+      E8 x;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) x.v[c] = 8 * q + c < n ? pr[8 * q + c] / a.cpref : 1.0;
+      const E8 ex = exner8_diag(x, a.kappa, a.cp);
+#pragma unroll
+      for (int c = 7; c >= 0; --c) {
+        const int l = 8 * q + c;  // interface k0 + l + 1
+        if (l == n - 1) {         // the lowest interface starts the sweep
+          pb = pr[l];
+          eb = ex.v[c];
+          thb = __ldg(pth + n * a.theta.s2);
+          hk = a.hs(i, j, kt);
+          const double mtg_s = thb * eb + a.g * hk;  // L347
+          m = mtg_s + 0.5 * a.dz * eb;
+          pe[n * a.exn.s2] = eb;
+          ph[n * a.h.s2] = hk;  // L354
+        } else if (l < n - 1) {
+          interface(l + 1, pr[l], ex.v[c]);
+        }
+      }
+    }
+  }
+  interface(0, a.pt, a.cp * pow_pos(a.pt / a.cpref, a.kappa));
+}
+
 extern "C" int tb200_montgomery(const tb200_field *in_hs, const tb200_field *in_s,
                                 tb200_field *inout_mtg, double dz, double pt, double theta_s,
                                 const double constants[4], const int32_t origin[3],
@@ -276,6 +370,18 @@ extern "C" int tb200_diagnostic_variables(const tb200_field *in_theta, const tb2
                     box_inside(exn, origin, domain) && box_inside(mtg, origin, domain) &&
                     box_inside(h, origin, domain),
                 "diagnostic_variables: box outside storage");
+  if (domain[2] - 1 <= 64 && domain[0] > 0 && domain[1] > 0) {  // register-resident columns
+    DiagArgs a{th, hs, s, p, exn, mtg, h, dz, pt, constants[1], constants[2], constants[3],
+               constants[1] / constants[3], make_cdiv(constants[0]), origin[0], origin[1], origin[2],
+               domain[0], domain[1], domain[2] - 1};
+    dim3 block(32, 4, 1);
+    dim3 grid((domain[0] + 31) / 32, (domain[1] + 3) / 4, 1);
+    if (a.n == 64)
+      diag_column_kernel<true><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    else
+      diag_column_kernel<false><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("diagnostic_variables");
+  }
   return run_k3<1>(th, hs, s, p, exn, mtg, h, dz, pt, 0.0, constants[0], constants[1],
                    constants[2], constants[3], origin, domain, static_cast<cudaStream_t>(stream));
 }

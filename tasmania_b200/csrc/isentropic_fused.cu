@@ -224,28 +224,39 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
 }
 
 // The Exner function of four levels as ONE real call: kernel B is unrolled over the levels, so
-// an inlined copy of log2 / exp2 per level would not fit the instruction cache, and four
-// independent evaluations per call give the fp64 pipe the instruction-level parallelism that a
-// single dependent polynomial chain lacks.
+// an inlined copy of the power per level would not fit the instruction cache, and the four
+// evaluations are interleaved instruction by instruction (pow_pos_n), which gives the fp64 pipe
+// the instruction-level parallelism that a single dependent polynomial chain lacks.
 struct D4 {
   double a, b, c, d;
 };
 __device__ __noinline__ D4 exner4(D4 x, double kappa, double cp) {
-  D4 r;
-  r.a = cp * pow_pos(x.a, kappa);
-  r.b = cp * pow_pos(x.b, kappa);
-  r.c = cp * pow_pos(x.c, kappa);
-  r.d = cp * pow_pos(x.d, kappa);
+  const double xs[4] = {x.a, x.b, x.c, x.d};
+  double r[4];
+  pow_pos_n<4>(xs, kappa, r);
+  return D4{cp * r[0], cp * r[1], cp * r[2], cp * r[3]};
+}
+// eight levels per call: with two resident warps per scheduler (kernel B keeps a column in
+// registers) eight interleaved chains cover the 8-cycle DFMA latency from within one warp
+struct D8 {
+  double v[8];
+};
+__device__ __noinline__ D8 exner8(D8 x, double kappa, double cp) {
+  D8 r;
+  pow_pos_n<8>(x.v, kappa, r.v);
+#pragma unroll
+  for (int n = 0; n < 8; ++n) r.v[n] = cp * r.v[n];
   return r;
 }
 
-template <int NZC>
-__global__ void __launch_bounds__(128) stage_b_kernel(const StageArgs a) {
-  static_assert(NZC % 4 == 0, "levels are processed four at a time");
+// EXACT: nz == NZC, known at compile time (no per-level range checks in the unrolled code)
+template <int NZC, bool EXACT>
+__global__ void __launch_bounds__(128, 2) stage_b_kernel(const StageArgs a) {
+  static_assert(NZC % 8 == 0, "levels are processed eight at a time");
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= a.nx || j >= a.ny) return;
-  const int nz = a.nz;
+  const int nz = EXACT ? NZC : a.nz;
   const double kappa = a.rd / a.cp;
   const double gdz = a.g * a.dz;
   double e[NZC];
@@ -267,12 +278,16 @@ __global__ void __launch_bounds__(128) stage_b_kernel(const StageArgs a) {
       e[k] = 1.0;
     }
   }
-  // Exner function of every interface, four levels per call
+  // Exner function of every interface, eight levels per call
 #pragma unroll
-  for (int k = 0; k < NZC; k += 4) {
+  for (int k = 0; k < NZC; k += 8) {
     if (k < nz) {
-      const D4 r = exner4(D4{e[k], e[k + 1], e[k + 2], e[k + 3]}, kappa, a.cp);
-      e[k] = r.a; e[k + 1] = r.b; e[k + 2] = r.c; e[k + 3] = r.d;
+      D8 x;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) x.v[n] = e[k + n];
+      const D8 r = exner8(x, kappa, a.cp);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) e[k + n] = r.v[n];
     }
   }
   // upward sweep, diagnostics.py:L433-L438
@@ -885,10 +900,12 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
     {
       dim3 block(32, 4, 1);
       dim3 grid((a.nx + 31) / 32, (a.ny + 3) / 4, 1);
-      if (a.nz <= 32)
-        stage_b_kernel<32><<<grid, block, 0, st>>>(a);
+      if (a.nz == 64)
+        stage_b_kernel<64, true><<<grid, block, 0, st>>>(a);
+      else if (a.nz <= 32)
+        stage_b_kernel<32, false><<<grid, block, 0, st>>>(a);
       else
-        stage_b_kernel<64><<<grid, block, 0, st>>>(a);
+        stage_b_kernel<64, false><<<grid, block, 0, st>>>(a);
       int rc = check_launch("isentropic_stage_dry/B");
       if (rc) return rc;
     }

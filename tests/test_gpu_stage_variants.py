@@ -1,8 +1,8 @@
 # -*- coding: utf-8 -*-
 """The fused stage has interchangeable kernels (selected per process by environment
-variables, read once): the s-step + scans as kernel S (thread per column) or kernels A + B, the
-momentum step as the register-window kernel or the TMA / shared-memory-ring kernel.  Every
-combination must give bit-identical fields."""
+variables, read once): the s-step + scans as kernel S (thread per column) or kernels A + B,
+the momentum step as the register-window kernel, the shared-memory-ring kernel or the TMA
+kernel.  Every combination must give bit-identical fields."""
 import hashlib
 import os
 import subprocess
@@ -19,7 +19,8 @@ import hashlib, sys
 sys.path.insert(0, %r)
 import numpy as np
 from tasmania_b200.distributed import InProcessDecomposedRun
-run = InProcessDecomposedRun(131, 77, 12, 1, 1, damp_depth=5, topo_seconds=15.0, flux=sys.argv[1])
+nz = int(sys.argv[2])
+run = InProcessDecomposedRun(131, 77, nz, 1, 1, damp_depth=5, topo_seconds=15.0, flux=sys.argv[1])
 for _ in range(3):
     run.step()
 h = hashlib.sha256()
@@ -32,10 +33,10 @@ print("DIGEST", h.hexdigest())
 """ % ROOT
 
 
-def _digest(flux, **env):
+def _digest(flux, nz=12, **env):
     e = dict(os.environ)
     e.update(env)
-    res = subprocess.run([sys.executable, "-c", SCRIPT, flux], capture_output=True, text=True,
+    res = subprocess.run([sys.executable, "-c", SCRIPT, flux, str(nz)], capture_output=True, text=True,
                          env=e, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     return [l for l in res.stdout.splitlines() if l.startswith("DIGEST")][0]
@@ -47,3 +48,12 @@ def test_stage_kernel_variants_are_bitwise_identical(flux):
     assert _digest(flux, TB200_S_IMPL="column") == ref
     assert _digest(flux, TB200_STAGE_IMPL="tma") == ref
     assert _digest(flux, TB200_S_IMPL="column", TB200_STAGE_IMPL="tma") == ref
+    assert _digest(flux, TB200_MV_IMPL="window") == ref
+
+
+@pytest.mark.parametrize("nz", [64, 60, 37, 5])
+def test_scan_kernel_variants_are_bitwise_identical(nz):
+    """Kernels A + B (register-resident columns: full, ragged and short ones) vs the former
+    kernel S (thread per column, pressures parked in memory)."""
+    ref = _digest("fifth_order_upwind", nz)
+    assert _digest("fifth_order_upwind", nz, TB200_S_IMPL="column") == ref
