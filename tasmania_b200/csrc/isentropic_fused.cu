@@ -223,21 +223,11 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
   }
 }
 
-// The Exner function of four levels as ONE real call: kernel B is unrolled over the levels, so
-// an inlined copy of the power per level would not fit the instruction cache, and the four
-// evaluations are interleaved instruction by instruction (pow_pos_n), which gives the fp64 pipe
-// the instruction-level parallelism that a single dependent polynomial chain lacks.
-struct D4 {
-  double a, b, c, d;
-};
-__device__ __noinline__ D4 exner4(D4 x, double kappa, double cp) {
-  const double xs[4] = {x.a, x.b, x.c, x.d};
-  double r[4];
-  pow_pos_n<4>(xs, kappa, r);
-  return D4{cp * r[0], cp * r[1], cp * r[2], cp * r[3]};
-}
-// eight levels per call: with two resident warps per scheduler (kernel B keeps a column in
-// registers) eight interleaved chains cover the 8-cycle DFMA latency from within one warp
+// The Exner function of eight levels as ONE real call: kernel B is unrolled over the levels, so
+// an inlined copy of the power per level would not fit the instruction cache, and the eight
+// evaluations are interleaved instruction by instruction (pow_pos_n): with two resident warps
+// per scheduler (kernel B keeps a column in registers) eight interleaved chains cover the
+// 8-cycle DFMA latency from within one warp (experiments/fp64_latency.cu).
 struct D8 {
   double v[8];
 };
@@ -830,26 +820,439 @@ __global__ void __launch_bounds__(128, 4) stage_mv_ring_kernel(const StageArgs a
   }
 }
 
-// TB200_MV_IMPL=window selects the register-window momentum kernel instead of the ring one
+// ---------------------------------------------------------------- kernel MV, two columns per lane
+// The ring kernel above still issues ~445 instructions per warp-row of 30 points, of which only
+// 141 are fp64: every global access costs two integer instructions (64-bit address formation;
+// sm_100a has no [uniform base + 32-bit offset] global addressing), every neighbour one LDS and
+// every shared face one shuffle.  Here
+//   * a lane owns TWO adjacent columns (c0 even, c1 = c0 + 1): all global accesses are 16-byte
+//     LDG.128 / STG.128 (half the address arithmetic per point), the y-window and the
+//     x-neighbours are LDS.128, the face between c0 and c1 needs no shuffle, and a warp carries
+//     two independent dependency chains through every formula;
+//   * the rows with reuse (su_int, sv_int, mtg_now, mtg_new) go global -> shared memory with
+//     cp.async (LDGSTS, 16 bytes per lane, no staging registers, no STS), one row ahead;
+//   * the reference fields of the relaxation band / damping layer are requested one row ahead
+//     like every other own-column value (their DRAM latency used to sit on every row there).
+// One warp = 64 columns of one level, 60 of them owned (lanes 1..30); lane 0 recomputes the two
+// columns to the left (their final s, su feed lane 1's u), lane 31 lends its left face.  A
+// block = WX x WY warps (WX side by side, WY strips of LJ rows).
+// Ring row: grid columns c_first-6 .. c_first+65 (72 doubles, 16-byte aligned pairs); su / sv
+// rings of 8 rows, mtg rings of 4 rows, slot = row & 7 / & 3 relative to the strip.
+// Arithmetic and results are bit-identical to the other momentum kernels.
+// Requirements (checked on the host, else the ring kernel runs): 16-byte aligned bases, even
+// row / plane pitches, row pitch >= nx + 1.
+constexpr int MV2_COLS = 60;
+constexpr int RW2 = 72;
+constexpr int SU_RING2 = 8, MT_RING2 = 4;
+constexpr int REF_RING2 = 2;  // rows r (in use) and r+1 (in flight) of s_ref, su_ref, sv_ref
+constexpr int WARP_DOUBLES2 = (2 * SU_RING2 + 2 * MT_RING2) * RW2 + 3 * REF_RING2 * 64;
+constexpr int MV2_WX = 2, MV2_WY = 2;
+constexpr int MV2_PF = 2;  // rows of DRAM -> L2 prefetch ahead of the loads (measured: 0 -> 2.00 ms, 2 -> 1.79, 3 -> 1.82, 6 -> 2.22)
+
+__device__ __forceinline__ double2 ldo2(const double *base, unsigned off) {
+  return __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + off));
+}
+__device__ __forceinline__ void sto2(double *base, unsigned off, double2 v) {
+  *reinterpret_cast<double2 *>(reinterpret_cast<char *>(base) + off) = v;
+}
+__device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+// 16 bytes global -> shared, asynchronously (LDGSTS, L2 only)
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const double *base, unsigned off) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst),
+               "l"(reinterpret_cast<const char *>(base) + off)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct OwnLoads2 {
+  double2 v_n, u_c, s_pre, s_now, su_now, sv_now;
+};
+
+template <int SCHEME, int LJ>
+__global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(const StageArgs a) {
+  using F = Flux<SCHEME>;
+  constexpr int E = F::extent;
+  constexpr int NW = 2 * E;
+  extern __shared__ __align__(16) double ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int xw = (blockIdx.x + a.bx0) * MV2_WX + warp % MV2_WX;
+  const int j0 = ((blockIdx.y + a.by0) * MV2_WY + warp / MV2_WX) * LJ;
+  if (xw * MV2_COLS >= a.nx || j0 >= a.ny) return;  // warp-uniform (no block-wide barrier in this kernel)
+  double *r_su = ring_smem + warp * WARP_DOUBLES2;
+  const int c0 = xw * MV2_COLS + 2 * lane - 2;  // first of the lane's two columns (even)
+  const int jend = min(j0 + LJ, a.ny);
+  const int k = blockIdx.z;
+  const int nx = a.nx, ny = a.ny, nb = a.nb;
+
+  const bool own_lane = lane >= 1 && lane <= MV2_COLS / 2;
+  const bool out0 = own_lane && c0 < nx, out1 = own_lane && c0 + 1 < nx;
+  const bool col_int0 = c0 >= nb && c0 < nx - nb, col_int1 = c0 + 1 >= nb && c0 + 1 < nx - nb;
+  const int pmax = (nx - 1) & ~1;        // last pair start inside the row
+  const int cm = min(max(c0, 0), pmax);  // own pair, clamped into the row
+  // halo pairs of lanes 0, 1 (ring columns 0-1, 2-3) and 2 (ring columns 68-69)
+  const bool halo_lane = lane < 3;
+  const int th = lane < 2 ? 2 * lane : 68;
+  const int ch = min(max(xw * MV2_COLS - 6 + th, 0), pmax);
+  const int t = 2 * lane + 4;  // ring column of c0
+
+  const unsigned row = (unsigned)a.s_now.s1 * 8u;
+  const unsigned plane = (unsigned)k * (unsigned)a.s_now.s2 * 8u;
+  const unsigned grow = (unsigned)a.gamma.s1 * 8u;
+  const double r_damp = a.damp ? a.rmat.ld(0, 0, k) : 0.0;
+  const double one_m_eps = 1.0 - a.eps;
+  const int r0 = j0 > 0 ? j0 - 1 : 0;  // first row computed (warm-up row unless j0 == 0)
+  const double2 zero2 = make_double2(0.0, 0.0);
+
+  // shared-memory byte addresses of this lane's own / halo entry of ring row 0
+  constexpr unsigned SLOT = RW2 * 8u;                       // bytes per ring row
+  constexpr unsigned SV_OFF = SU_RING2 * SLOT;              // sv ring relative to su ring
+  constexpr unsigned MN_OFF = 2 * SU_RING2 * SLOT;          // mtg_now ring
+  constexpr unsigned MW_OFF = MN_OFF + MT_RING2 * SLOT;     // mtg_new ring
+  const unsigned sm_own = (unsigned)__cvta_generic_to_shared(r_su + t);
+  const unsigned sm_halo = (unsigned)__cvta_generic_to_shared(r_su + th);
+  // reference fields: [stream][slot][64 columns] behind the rings, own pair at 2 * lane
+  const double *w_ref = r_su + (2 * SU_RING2 + 2 * MT_RING2) * RW2 + 2 * lane;
+  const unsigned sm_ref = (unsigned)__cvta_generic_to_shared(w_ref);
+  const unsigned col_o = (unsigned)cm * 8u, col_h = (unsigned)ch * 8u;
+
+  // grid row rr of su_int / sv_int -> ring slot q_su & 7; of mtg_now / mtg_new -> slot q_mt & 3
+  auto fetch_su = [&](int q_su, int rr) {
+    const unsigned o = plane + (unsigned)max(rr, 0) * row, d = (unsigned)(q_su & (SU_RING2 - 1)) * SLOT;
+    cp_async16(sm_own + d, a.su_int.p, o + col_o);
+    cp_async16(sm_own + d + SV_OFF, a.sv_int.p, o + col_o);
+    if (halo_lane) {
+      cp_async16(sm_halo + d, a.su_int.p, o + col_h);
+      cp_async16(sm_halo + d + SV_OFF, a.sv_int.p, o + col_h);
+    }
+  };
+  auto fetch_mt = [&](int q_mt, int rr) {
+    const unsigned o = plane + (unsigned)max(rr, 0) * row, d = (unsigned)(q_mt & (MT_RING2 - 1)) * SLOT;
+    cp_async16(sm_own + d + MN_OFF, a.mtg_now.p, o + col_o);
+    cp_async16(sm_own + d + MW_OFF, a.mtg.p, o + col_o);
+    if (halo_lane) {
+      cp_async16(sm_halo + d + MN_OFF, a.mtg_now.p, o + col_h);
+      cp_async16(sm_halo + d + MW_OFF, a.mtg.p, o + col_h);
+    }
+  };
+
+  // ---- prologue: su / sv rows r0-E .. r0+E-1 (slots 0 .. 2E-1), mtg rows r0-1, r0 (slots 0, 1),
+  // then the rows the first iteration waits for (r0+E -> slot 2E, r0+1 -> slot 2) as the
+  // youngest group.  Rows up to jend + E are touched: inside the allocation (>= nz + 1 planes,
+  // checked on the host).
+#pragma unroll
+  for (int m = 0; m < NW; ++m) fetch_su(m, r0 - E + m);
+  fetch_mt(0, r0 - 1);
+  fetch_mt(1, r0);
+  cp_async_commit();
+  unsigned o_c = plane + (unsigned)r0 * row + col_o;  // own pair, row r
+
+  auto load_own = [&](unsigned oc) {
+    OwnLoads2 L;
+    L.v_n = ldo2(a.v_int.p, oc + row);
+    L.u_c = ldo2(a.u_int.p, oc);
+    L.s_pre = ldo2(a.spre.p, oc);
+    L.s_now = ldo2(a.s_now.p, oc);
+    L.su_now = ldo2(a.su_now.p, oc);
+    L.sv_now = ldo2(a.sv_now.p, oc);
+    return L;
+  };
+  // The reference fields of the relaxation band / damping layer are requested one row ahead of
+  // their use like everything else (cp.async into a two-row ring; the relaxation coefficients
+  // run two rows ahead to decide where).  Row rr -> slot rr & 1.
+  auto fetch_ref = [&](int rr, unsigned oc, double2 gam) {
+    if (gam.x != 0.0 || gam.y != 0.0 || r_damp != 0.0) {
+      const unsigned d = sm_ref + (unsigned)(rr & 1) * 512u;
+      cp_async16(d, a.s_ref.p, oc);
+      cp_async16(d + REF_RING2 * 512u, a.su_ref.p, oc);
+      cp_async16(d + 2 * REF_RING2 * 512u, a.sv_ref.p, oc);
+    }
+  };
+  auto load_gamma = [&](int rr) {  // rows beyond the domain repeat the last one (never used)
+    return ldo2(a.gamma.p, (unsigned)min(rr, ny - 1) * grow + col_o);
+  };
+  double2 gam_a = load_gamma(r0), gam_b = load_gamma(r0 + 1);  // rows r and r+1
+  const double2 v_first = ldo2(a.v_int.p, o_c);
+  OwnLoads2 nxt = load_own(o_c);
+  fetch_su(NW, r0 + E);
+  fetch_mt(2, r0 + 1);
+  fetch_ref(r0, o_c, gam_a);
+  cp_async_commit();
+
+  cp_async_wait<1>();
+  __syncwarp();
+  double fy_su0, fy_su1, fy_sv0, fy_sv1;
+  {
+    double ysu0[NW], ysu1[NW], ysv0[NW], ysv1[NW];
+#pragma unroll
+    for (int m = 0; m < NW; ++m) {
+      const double2 vu = lds2(r_su + m * RW2 + t), vv = lds2(r_su + (SU_RING2 + m) * RW2 + t);
+      ysu0[m] = vu.x; ysu1[m] = vu.y; ysv0[m] = vv.x; ysv1[m] = vv.y;
+    }
+    const double vq0 = F::prep(v_first.x, a.fc), vq1 = F::prep(v_first.y, a.fc);
+    fy_su0 = F::eval_v(vq0, ysu0); fy_su1 = F::eval_v(vq1, ysu1);
+    fy_sv0 = F::eval_v(vq0, ysv0); fy_sv1 = F::eval_v(vq1, ysv1);
+  }
+  double sv_prev0 = 0.0, sv_prev1 = 0.0, s_prev0 = 0.0, s_prev1 = 0.0;
+
+  // DRAM -> L2 MV2_PF rows ahead with two instructions per row for all ten streams: lane
+  // 10 l + f takes the 128-byte lines 2 l and 2 l + 1 of stream f (the warp's 70 columns of a
+  // row span at most six lines)
+  const double *pf_base;
+  unsigned pf_off;
+  {
+    const int f = lane % 10, line = lane / 10;
+    const double *bases[10] = {a.su_int.p, a.sv_int.p, a.v_int.p, a.u_int.p,  a.spre.p,
+                               a.s_now.p,  a.su_now.p, a.sv_now.p, a.mtg_now.p, a.mtg.p};
+    const int ahead[10] = {E, E, 1, 0, 0, 0, 0, 0, 1, 1};
+    pf_base = bases[0];
+    int ah = 0;
+#pragma unroll
+    for (int n = 0; n < 10; ++n)
+      if (f == n) {
+        pf_base = bases[n];
+        ah = ahead[n];
+      }
+    const int cfirst = max(xw * MV2_COLS - 6, 0);
+    pf_off = plane + (unsigned)(r0 + MV2_PF + ah) * row + (unsigned)((cfirst * 8 & ~127) + 256 * line);
+  }
+
+  const double *w_su = r_su + t;  // this lane's entry of su ring row 0
+  for (int r = r0; r < jend; ++r) {
+    const int q = r - r0;
+    // rows r+E / r+1, requested one iteration ago, have landed; all lanes are done with row r-1
+    cp_async_wait<0>();
+    __syncwarp();
+    fetch_su(q + NW + 1, r + E + 1);
+    fetch_mt(q + 3, r + 2);
+    fetch_ref(r + 1, o_c + row, gam_b);
+    cp_async_commit();
+    const OwnLoads2 cur = nxt;
+    nxt = load_own(o_c + row);
+    const double2 gam_c = load_gamma(r + 2);
+    if (r + MV2_PF < jend) {
+      prefetch_l2(pf_base, pf_off);
+      if (lane < 30) prefetch_l2(pf_base, pf_off + 128u);
+    }
+    pf_off += row;
+
+    // ---- y-faces r+1 of both columns: rows r-E+1 .. r+E sit in slots (q + 1 + m) & 7
+    double ysu0[NW], ysu1[NW], ysv0[NW], ysv1[NW];
+    const double *row_r = w_su;  // ring row of grid row r
+#pragma unroll
+    for (int m = 0; m < NW; ++m) {
+      const double *pr = w_su + ((q + 1 + m) & (SU_RING2 - 1)) * RW2;
+      if (m == E - 1) row_r = pr;
+      const double2 vu = lds2(pr), vv = lds2(pr + SU_RING2 * RW2);
+      ysu0[m] = vu.x; ysu1[m] = vu.y; ysv0[m] = vv.x; ysv1[m] = vv.y;
+    }
+    const double vq0 = F::prep(cur.v_n.x, a.fc), vq1 = F::prep(cur.v_n.y, a.fc);
+    const double fy_su0_p = F::eval_v(vq0, ysu0), fy_su1_p = F::eval_v(vq1, ysu1);
+    const double fy_sv0_p = F::eval_v(vq0, ysv0), fy_sv1_p = F::eval_v(vq1, ysv1);
+
+    // ---- x-faces at row r: left face of c0, face between c0 and c1; the right face of c1 is
+    // the left face of the next lane's c0.  lsu[n] = su_int[c0 - E + n]
+    const double uq0 = F::prep(cur.u_c.x, a.fc), uq1 = F::prep(cur.u_c.y, a.fc);
+    double lsu[NW + 1], lsv[NW + 1];
+    {
+      const double *psu = row_r, *psv = row_r + SU_RING2 * RW2;
+#pragma unroll
+      for (int po = -4; po <= 2; po += 2) {  // aligned pairs (po, po + 1) around the own pair (0, 1)
+        if (po == 0) continue;
+        const bool need0 = po >= -E && po <= E, need1 = po + 1 >= -E && po + 1 <= E;
+        if (need0 && need1) {
+          const double2 vu = lds2(psu + po), vv = lds2(psv + po);
+          lsu[po + E] = vu.x; lsu[po + 1 + E] = vu.y;
+          lsv[po + E] = vv.x; lsv[po + 1 + E] = vv.y;
+        } else if (need0) {
+          lsu[po + E] = psu[po]; lsv[po + E] = psv[po];
+        } else if (need1) {
+          lsu[po + 1 + E] = psu[po + 1]; lsv[po + 1 + E] = psv[po + 1];
+        }
+      }
+      lsu[E] = ysu0[E - 1]; lsu[E + 1] = ysu1[E - 1];
+      lsv[E] = ysv0[E - 1]; lsv[E + 1] = ysv1[E - 1];
+    }
+    const double fx_su0 = F::eval_v(uq0, lsu), fx_su1 = F::eval_v(uq1, lsu + 1);
+    const double fx_sv0 = F::eval_v(uq0, lsv), fx_sv1 = F::eval_v(uq1, lsv + 1);
+    const double fx_su2 = __shfl_down_sync(0xffffffffu, fx_su0, 1);
+    const double fx_sv2 = __shfl_down_sync(0xffffffffu, fx_sv0, 1);
+
+    // ---- point updates (prognostics/utils.py:L191-L204)
+    const bool row_int = r >= nb && r < ny - nb;
+    const bool int0 = col_int0 && row_int, int1 = col_int1 && row_int;
+    double s0 = cur.s_pre.x, s1 = cur.s_pre.y, su0 = 0.0, su1 = 0.0, sv0 = 0.0, sv1 = 0.0;
+    if (int0 || int1) {
+      // Montgomery potential: rows r-1, r, r+1 in slots (q + m) & 3
+      const double *bm_m = w_su + (2 * SU_RING2 + (q & (MT_RING2 - 1))) * RW2;
+      const double *bm_c = w_su + (2 * SU_RING2 + ((q + 1) & (MT_RING2 - 1))) * RW2;
+      const double *bm_p = w_su + (2 * SU_RING2 + ((q + 2) & (MT_RING2 - 1))) * RW2;
+      constexpr int MW = MT_RING2 * RW2;  // mtg_new relative to mtg_now
+      const double2 mn_c = lds2(bm_c), mw_c = lds2(bm_c + MW);
+      const double2 mn_m = lds2(bm_m), mw_m = lds2(bm_m + MW);
+      const double2 mn_p = lds2(bm_p), mw_p = lds2(bm_p + MW);
+      const double mn_l = bm_c[-1], mw_l = bm_c[MW - 1], mn_r = bm_c[2], mw_r = bm_c[MW + 2];
+      {
+        const double div = (fx_su1 - fx_su0) / a.fc.dx + (fy_su0_p - fy_su0) / a.fc.dy;
+        const double pg_now = one_m_eps * cur.s_now.x * (mn_c.y - mn_l) / a.two_dx;
+        const double pg_new = a.eps * s0 * (mw_c.y - mw_l) / a.two_dx;
+        su0 = cur.su_now.x - a.dt * (div + pg_now + pg_new - 0.0);
+      }
+      {
+        const double div = (fx_su2 - fx_su1) / a.fc.dx + (fy_su1_p - fy_su1) / a.fc.dy;
+        const double pg_now = one_m_eps * cur.s_now.y * (mn_r - mn_c.x) / a.two_dx;
+        const double pg_new = a.eps * s1 * (mw_r - mw_c.x) / a.two_dx;
+        su1 = cur.su_now.y - a.dt * (div + pg_now + pg_new - 0.0);
+      }
+      {
+        const double div = (fx_sv1 - fx_sv0) / a.fc.dx + (fy_sv0_p - fy_sv0) / a.fc.dy;
+        const double pg_now = one_m_eps * cur.s_now.x * (mn_p.x - mn_m.x) / a.two_dy;
+        const double pg_new = a.eps * s0 * (mw_p.x - mw_m.x) / a.two_dy;
+        sv0 = cur.sv_now.x - a.dt * (div + pg_now + pg_new - 0.0);
+      }
+      {
+        const double div = (fx_sv2 - fx_sv1) / a.fc.dx + (fy_sv1_p - fy_sv1) / a.fc.dy;
+        const double pg_now = one_m_eps * cur.s_now.y * (mn_p.y - mn_m.y) / a.two_dy;
+        const double pg_new = a.eps * s1 * (mw_p.y - mw_m.y) / a.two_dy;
+        sv1 = cur.sv_now.y - a.dt * (div + pg_now + pg_new - 0.0);
+      }
+      if (!int0) { su0 = 0.0; sv0 = 0.0; }
+      if (!int1) { su1 = 0.0; sv1 = 0.0; }
+    }
+    const double gam0 = gam_a.x, gam1 = gam_a.y;
+    double2 s_ref = zero2, su_ref = zero2, sv_ref = zero2;
+    if (gam0 != 0.0 || gam1 != 0.0 || r_damp != 0.0) {
+      const double *pr = w_ref + (r & 1) * 64;
+      s_ref = lds2(pr);
+      su_ref = lds2(pr + REF_RING2 * 64);
+      sv_ref = lds2(pr + 2 * REF_RING2 * 64);
+    }
+    if ((!int0 && gam0 != 1.0) || (!int1 && gam1 != 1.0)) {  // not reached with a Relaxed boundary
+      const double2 ou = ldo2(a.su_new.p, o_c), ov = ldo2(a.sv_new.p, o_c);
+      if (!int0 && gam0 != 1.0) { su0 = ou.x; sv0 = ov.x; }
+      if (!int1 && gam1 != 1.0) { su1 = ou.y; sv1 = ov.y; }
+    }
+    if (gam0 != 0.0) {  // hb.enforce_raw, dycore.py:L686
+      s0 = relax_point(gam0, s0, s_ref.x);
+      su0 = relax_point(gam0, su0, su_ref.x);
+      sv0 = relax_point(gam0, sv0, sv_ref.x);
+    }
+    if (gam1 != 0.0) {
+      s1 = relax_point(gam1, s1, s_ref.y);
+      su1 = relax_point(gam1, su1, su_ref.y);
+      sv1 = relax_point(gam1, sv1, sv_ref.y);
+    }
+    if (r_damp != 0.0) {  // dycore.py:L694-L700
+      s0 = damp_point(cur.s_now.x, s0, s_ref.x, r_damp, a.dt_full);
+      su0 = damp_point(cur.su_now.x, su0, su_ref.x, r_damp, a.dt_full);
+      sv0 = damp_point(cur.sv_now.x, sv0, sv_ref.x, r_damp, a.dt_full);
+      s1 = damp_point(cur.s_now.y, s1, s_ref.y, r_damp, a.dt_full);
+      su1 = damp_point(cur.su_now.y, su1, su_ref.y, r_damp, a.dt_full);
+      sv1 = damp_point(cur.sv_now.y, sv1, sv_ref.y, r_damp, a.dt_full);
+    }
+
+    // ---- velocity diagnosis (dwarfs/diagnostics.py:L219-L272) and stores
+    const double su_l = __shfl_up_sync(0xffffffffu, su1, 1);
+    const double s_l = __shfl_up_sync(0xffffffffu, s1, 1);
+    if (out0 && r >= j0) {
+      const int c1 = c0 + 1;
+      const double u0 = c0 == 0 ? ldo(a.u_ref.p, o_c) : (su_l + su0) / (s_l + s0);
+      double v0, v1;
+      if (r == 0) {
+        const double2 vr = ldo2(a.v_ref.p, o_c);
+        v0 = vr.x; v1 = vr.y;
+      } else {
+        v0 = (sv_prev0 + sv0) / (s_prev0 + s0);
+        v1 = (sv_prev1 + sv1) / (s_prev1 + s1);
+      }
+      if (out1) {
+        const double u1 = (su0 + su1) / (s0 + s1);
+        sto2(a.s_new.p, o_c, make_double2(s0, s1));
+        sto2(a.su_new.p, o_c, make_double2(su0, su1));
+        sto2(a.sv_new.p, o_c, make_double2(sv0, sv1));
+        sto2(a.u_new.p, o_c, make_double2(u0, u1));
+        sto2(a.v_new.p, o_c, make_double2(v0, v1));
+        if (c1 == nx - 1) sto(a.u_new.p, o_c + 16u, ldo(a.u_ref.p, o_c + 16u));  // relaxed.py:L161-L175
+        if (r == ny - 1) sto2(a.v_new.p, o_c + row, ldo2(a.v_ref.p, o_c + row));  // relaxed.py:L177-L191
+      } else {  // c0 is the last column of an odd-sized row
+        sto(a.s_new.p, o_c, s0);
+        sto(a.su_new.p, o_c, su0);
+        sto(a.sv_new.p, o_c, sv0);
+        sto(a.u_new.p, o_c, u0);
+        sto(a.v_new.p, o_c, v0);
+        sto(a.u_new.p, o_c + 8u, ldo(a.u_ref.p, o_c + 8u));
+        if (r == ny - 1) sto(a.v_new.p, o_c + row, ldo(a.v_ref.p, o_c + row));
+      }
+    }
+    sv_prev0 = sv0; sv_prev1 = sv1;
+    s_prev0 = s0; s_prev1 = s1;
+    fy_su0 = fy_su0_p; fy_su1 = fy_su1_p;
+    fy_sv0 = fy_sv0_p; fy_sv1 = fy_sv1_p;
+    gam_a = gam_b; gam_b = gam_c;
+    o_c += row;
+  }
+  cp_async_wait<0>();  // nothing may still be in flight into this block's shared memory
+}
+
+// TB200_MV_IMPL selects the momentum kernel: "window" (register windows), "ring" (warp-private
+// shared-memory rings, one column per lane) or, by default, the two-columns-per-lane ring kernel
 int mv_impl() {
   static int impl = -1;
   if (impl < 0) {
     const char *e = getenv("TB200_MV_IMPL");
-    impl = (e != nullptr && strcmp(e, "window") == 0) ? 0 : 1;
+    impl = e == nullptr ? 2 : strcmp(e, "window") == 0 ? 0 : strcmp(e, "ring") == 0 ? 1 : 2;
   }
   return impl;
 }
 
+// the two-column kernel moves 16-byte pairs: aligned bases, even pitches, one spare column
+bool mv2_ok(const StageArgs &a) {
+  const View *all[] = {&a.s_now, &a.su_now, &a.sv_now, &a.mtg_now, &a.su_int, &a.sv_int, &a.u_int,
+                       &a.v_int, &a.s_new, &a.su_new, &a.sv_new, &a.u_new, &a.v_new, &a.s_ref,
+                       &a.su_ref, &a.sv_ref, &a.u_ref, &a.v_ref, &a.mtg, &a.spre, &a.gamma};
+  for (const View *v : all)
+    if ((reinterpret_cast<uintptr_t>(v->p) & 15) != 0 || (v->s1 & 1) != 0 || (v->s2 & 1) != 0 ||
+        v->s1 < a.nx + 1)
+      return false;
+  return true;
+}
+
+struct MvGeom {
+  int impl, wx, wy, cols;  // kernel, warps per block along x / along y, owned columns per warp
+};
+MvGeom mv_geom(const StageArgs &a) {
+  int impl = mv_impl();
+  if (impl == 2 && !mv2_ok(a)) impl = 1;
+  return impl == 2 ? MvGeom{2, MV2_WX, MV2_WY, MV2_COLS} : MvGeom{impl, 4, 1, MV_COLS};
+}
+
 // The momentum kernel over a rectangle of its block grid.
-template <int SCHEME, int LJ, int WARPS>
-int launch_mv_rect(StageArgs a, int bx0, int bx1, int by0, int by1, cudaStream_t st) {
+template <int SCHEME, int LJ>
+int launch_mv_rect(StageArgs a, const MvGeom &g, int bx0, int bx1, int by0, int by1, cudaStream_t st) {
   if (bx1 <= bx0 || by1 <= by0) return TB200_OK;
   a.bx0 = bx0;
   a.by0 = by0;
-  dim3 block(32 * WARPS, 1, 1);
+  dim3 block(32 * g.wx * g.wy, 1, 1);
   dim3 grid(bx1 - bx0, by1 - by0, a.nz);
-  if (mv_impl() != 0) {
-    stage_mv_ring_kernel<SCHEME, LJ><<<grid, block, WARPS * WARP_DOUBLES * sizeof(double), st>>>(a);
+  if (g.impl == 2) {
+    const size_t smem = (size_t)g.wx * g.wy * WARP_DOUBLES2 * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(stage_mv2_kernel<SCHEME, LJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem) != cudaSuccess) {
+        set_error("isentropic_stage_dry/MV2: %s", cudaGetErrorString(cudaGetLastError()));
+        return TB200_ERR_CUDA;
+      }
+      configured = true;
+    }
+    stage_mv2_kernel<SCHEME, LJ><<<grid, block, smem, st>>>(a);
+    return check_launch("isentropic_stage_dry/MV(2 columns)");
+  }
+  if (g.impl == 1) {
+    stage_mv_ring_kernel<SCHEME, LJ><<<grid, block, g.wx * WARP_DOUBLES * sizeof(double), st>>>(a);
     return check_launch("isentropic_stage_dry/MV(ring)");
   }
   stage_mv_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
@@ -859,32 +1262,30 @@ int launch_mv_rect(StageArgs a, int bx0, int bx1, int by0, int by1, cudaStream_t
 // part 0: the whole block grid; part 1: the blocks holding the a.rim columns / rows next to an
 // edge with a neighbour (south and north strips over all columns, west and east blocks over the
 // remaining strips); part 2: the interior rectangle.
-template <int SCHEME, int LJ, int WARPS>
-int launch_mv_part(const StageArgs &a, int gx, int gy, cudaStream_t st) {
-  if (a.part == 0) return launch_mv_rect<SCHEME, LJ, WARPS>(a, 0, gx, 0, gy, st);
-  const int cols = WARPS * MV_COLS;
+template <int SCHEME, int LJ>
+int launch_mv_part(const StageArgs &a, cudaStream_t st) {
+  const MvGeom g = mv_geom(a);
+  const int cols = g.wx * g.cols, rows = g.wy * LJ;  // columns / rows per block
+  const int gx = (a.nx + cols - 1) / cols, gy = (a.ny + rows - 1) / rows;
+  if (a.part == 0) return launch_mv_rect<SCHEME, LJ>(a, g, 0, gx, 0, gy, st);
   // first interior block after the west rim / first east-rim block, likewise for the strips
   int xw = a.rim[0] > 0 ? (a.rim[0] + cols - 1) / cols : 0;
   int xe = a.rim[1] > 0 ? (a.nx - a.rim[1]) / cols : gx;
-  int ys = a.rim[2] > 0 ? (a.rim[2] + LJ - 1) / LJ : 0;
-  int yn = a.rim[3] > 0 ? (a.ny - a.rim[3]) / LJ : gy;
+  int ys = a.rim[2] > 0 ? (a.rim[2] + rows - 1) / rows : 0;
+  int yn = a.rim[3] > 0 ? (a.ny - a.rim[3]) / rows : gy;
   xe = max(min(xe, gx), xw);
   yn = max(min(yn, gy), ys);
-  if (a.part == 2) return launch_mv_rect<SCHEME, LJ, WARPS>(a, xw, xe, ys, yn, st);
-  int rc = launch_mv_rect<SCHEME, LJ, WARPS>(a, 0, gx, 0, ys, st);
-  if (!rc) rc = launch_mv_rect<SCHEME, LJ, WARPS>(a, 0, gx, yn, gy, st);
-  if (!rc) rc = launch_mv_rect<SCHEME, LJ, WARPS>(a, 0, xw, ys, yn, st);
-  if (!rc) rc = launch_mv_rect<SCHEME, LJ, WARPS>(a, xe, gx, ys, yn, st);
+  if (a.part == 2) return launch_mv_rect<SCHEME, LJ>(a, g, xw, xe, ys, yn, st);
+  int rc = launch_mv_rect<SCHEME, LJ>(a, g, 0, gx, 0, ys, st);
+  if (!rc) rc = launch_mv_rect<SCHEME, LJ>(a, g, 0, gx, yn, gy, st);
+  if (!rc) rc = launch_mv_rect<SCHEME, LJ>(a, g, 0, xw, ys, yn, st);
+  if (!rc) rc = launch_mv_rect<SCHEME, LJ>(a, g, xe, gx, ys, yn, st);
   return rc;
 }
 
 template <int SCHEME>
 int run_stage(const StageArgs &a, cudaStream_t st) {
-  if (a.part == 2) {  // the s-step and the scans ran with part 1
-    constexpr int LJ = 64, WARPS = 4;
-    const int chunks = (a.nx + MV_COLS - 1) / MV_COLS;
-    return launch_mv_part<SCHEME, LJ, WARPS>(a, (chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, st);
-  }
+  if (a.part == 2) return launch_mv_part<SCHEME, 64>(a, st);  // the s-step and the scans ran with part 1
   prof_mark(0, st);
   if (s_impl() != 0 && a.nz <= 64) {
     {
@@ -927,10 +1328,7 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
     }
   }
   {
-    constexpr int LJ = 64, WARPS = 4;
-    const int chunks = (a.nx + MV_COLS - 1) / MV_COLS;
-    const int gx = (chunks + WARPS - 1) / WARPS, gy = (a.ny + LJ - 1) / LJ;
-    const int rc = launch_mv_part<SCHEME, LJ, WARPS>(a, gx, gy, st);
+    const int rc = launch_mv_part<SCHEME, 64>(a, st);
     prof_mark(3, st);
     g_prof.recorded = g_prof.on;
     return rc;

@@ -1,8 +1,8 @@
 # -*- coding: utf-8 -*-
 """The fused stage has interchangeable kernels (selected per process by environment
 variables, read once): the s-step + scans as kernel S (thread per column) or kernels A + B,
-the momentum step as the register-window kernel, the shared-memory-ring kernel or the TMA
-kernel.  Every combination must give bit-identical fields."""
+the momentum step as the register-window kernel, the shared-memory-ring kernels (one or two
+columns per lane) or the TMA kernel.  Every combination must give bit-identical fields."""
 import hashlib
 import os
 import subprocess
@@ -49,6 +49,7 @@ def test_stage_kernel_variants_are_bitwise_identical(flux):
     assert _digest(flux, TB200_STAGE_IMPL="tma") == ref
     assert _digest(flux, TB200_S_IMPL="column", TB200_STAGE_IMPL="tma") == ref
     assert _digest(flux, TB200_MV_IMPL="window") == ref
+    assert _digest(flux, TB200_MV_IMPL="ring") == ref
 
 
 @pytest.mark.parametrize("nz", [64, 60, 37, 5])
