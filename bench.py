@@ -384,7 +384,7 @@ def run_b200(args):
 KERNEL_BYTES_PER_POINT = {"s_step (stage_a_kernel)": 40, "column_scan (stage_b_kernel)": 16,
                           "momentum (stage_mv2_kernel)": 120}
 NCU_TRAFFIC_C5 = {"s_step (stage_a_kernel)": 2.96e9, "column_scan (stage_b_kernel)": 1.03e9,
-                  "momentum (stage_mv2_kernel)": 10.16e9}
+                  "momentum (stage_mv2_kernel)": 9.41e9}  # MV: 8.51 GB at stage 0 (now == int), 9.86 GB at stages 1, 2
 
 
 def kernel_roofline(run, args):
