@@ -240,6 +240,23 @@ int tb200_accumulated_precipitation(const tb200_field *in_rho, const tb200_field
                                     double rhow, const int32_t origin[3],
                                     const int32_t domain[3], void *stream);
 
+/* ---- vertical advection: IsentropicVerticalAdvection._stencil
+ * src/tasmania/isentropic/physics/vertical_advection.py:L271-L386 with the minimal vertical flux
+ * schemes of src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/ (flux_scheme =
+ * TB200_FLUX_*).  staggered_w: in_w lives on the interface levels (externals["staggering"]), else
+ * it is averaged onto them.  in_q* / out_q* NULL = dry.  overwrite_flags: bit f = ow_out_<field f>
+ * for the fields (s, su, sv, qv, qc, qr); as in the reference's set_output, an overwritten output
+ * is zero everywhere outside the levels [origin[2] + extent, origin[2] + domain[2] - extent) of the
+ * box, i.e. the WHOLE output storage is written. */
+int tb200_vertical_advection(int flux_scheme, int staggered_w, const tb200_field *in_w,
+                             const tb200_field *in_s, const tb200_field *in_su,
+                             const tb200_field *in_sv, tb200_field *out_s, tb200_field *out_su,
+                             tb200_field *out_sv, const tb200_field *in_qv,
+                             const tb200_field *in_qc, const tb200_field *in_qr,
+                             tb200_field *out_qv, tb200_field *out_qc, tb200_field *out_qr,
+                             double dz, uint32_t overwrite_flags, const int32_t origin[3],
+                             const int32_t domain[3], void *stream);
+
 /* ---- fused dry isentropic stage (the benchmark hot path) ---------------------------
  * One RK stage of IsentropicDynamicalCore.stage_array_call_dry
  * (src/tasmania/isentropic/dynamics/dycore.py:L641-L721) with the relaxed lateral boundary:

@@ -21,4 +21,5 @@ Operation order is kept exactly as in the reference (``u / 60.0 * (...)``, divid
 kernels are compared to this oracle at 1e-12 relative.
 """
 
-from oracle import boundary, burgers, dwarfs, fluxes, isentropic, microphysics  # noqa: F401
+from oracle import (boundary, burgers, dwarfs, fluxes, isentropic, microphysics,  # noqa: F401
+                    vertical_advection)

@@ -1,0 +1,72 @@
+# -*- coding: utf-8 -*-
+"""Oracle (test infrastructure): vertical advection of the isentropic model, SURVEY.md 8f-1.
+
+Follows src/tasmania/isentropic/physics/vertical_advection.py:L271-L386 (numpy definition of
+``IsentropicVerticalAdvection._stencil``) and the flux formulas of
+src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/{upwind.py:L31-L33,
+centered.py:L28-L30, third_order_upwind.py:L31-L38, fifth_order_upwind.py:L31-L42}.
+Pinned bit for bit on tests/golden/vertical_advection.npz (the reference's own code run in place).
+"""
+import numpy as np
+
+EXTENT = {"upwind": 1, "centered": 1, "third_order_upwind": 2, "fifth_order_upwind": 3}
+
+
+def vertical_flux(scheme, w, phi):
+    """Flux through the interfaces e .. n - e of a column with n levels (``phi``: n levels,
+    ``w``: n + 1 interfaces, third axis); interface K separates the levels K - 1 and K."""
+    n = phi.shape[2]
+    e = EXTENT[scheme]
+    K = np.arange(e, n - e + 1)
+
+    def lev(off):
+        return phi[:, :, K + off]
+
+    wk = w[:, :, K]
+    if scheme == "upwind":
+        return wk * np.where(wk > 0.0, lev(0), lev(-1))
+    if scheme == "centered":
+        return wk * 0.5 * (lev(0) + lev(-1))
+    if scheme == "third_order_upwind":
+        return wk / 12.0 * (7.0 * (lev(-1) + lev(0)) - (lev(-2) + lev(1))) - np.abs(wk) / 12.0 * (
+            3.0 * (lev(-1) - lev(0)) - (lev(-2) - lev(1)))
+    if scheme == "fifth_order_upwind":
+        return wk / 60.0 * (
+            37.0 * (lev(-1) + lev(0)) - 8.0 * (lev(-2) + lev(1)) + (lev(-3) + lev(2))
+        ) - np.abs(wk) / 60.0 * (
+            10.0 * (lev(-1) - lev(0)) - 5.0 * (lev(-2) - lev(1)) + (lev(-3) - lev(2)))
+    raise ValueError(scheme)
+
+
+def _set_output(lhs, rhs, overwrite):  # generics.py:L38-L40: on the WHOLE storage
+    lhs[...] = rhs if overwrite else lhs + rhs
+
+
+def vertical_advection(scheme, staggered, in_w, in_s, in_su, in_sv, out_s, out_su, out_sv, *,
+                       dz, ow_out_s, ow_out_su, ow_out_sv, origin, domain, in_qv=None, in_qc=None,
+                       in_qr=None, out_qv=None, out_qc=None, out_qr=None, ow_out_qv=True,
+                       ow_out_qc=True, ow_out_qr=True):
+    i = slice(origin[0], origin[0] + domain[0])
+    j = slice(origin[1], origin[1] + domain[1])
+    kb, ke = origin[2], origin[2] + domain[2]
+    e = EXTENT[scheme]
+    if staggered:  # L305-L306
+        w = in_w
+    else:  # L307-L320: averaged onto the inner interfaces, zero on the outermost two
+        w = np.zeros(tuple(max(a, b) for a, b in zip(in_w.shape, (0, 0, ke + 1))), dtype=in_w.dtype)
+        w[i, j, kb + 1:ke] = 0.5 * (in_w[i, j, kb + 1:ke] + in_w[i, j, kb:ke - 1])
+    wcol = w[i, j, kb:ke + 1]
+
+    def tendency(phi, denom):
+        f = vertical_flux(scheme, wcol, phi)
+        tmp = np.zeros_like(in_s)
+        tmp[i, j, kb + e:ke - e] = (f[:, :, 1:] - f[:, :, :-1]) / denom
+        return tmp
+
+    for src, out, ow in ((in_s, out_s, ow_out_s), (in_su, out_su, ow_out_su), (in_sv, out_sv, ow_out_sv)):
+        _set_output(out, tendency(src[i, j, kb:ke], dz), ow)  # L341-L353
+    if in_qv is not None:  # L322-L329, L355-L385
+        s_in = in_s[i, j, kb + e:ke - e]
+        for q, out, ow in ((in_qv, out_qv, ow_out_qv), (in_qc, out_qc, ow_out_qc), (in_qr, out_qr, ow_out_qr)):
+            sq = in_s[i, j, kb:ke] * q[i, j, kb:ke]
+            _set_output(out, tendency(sq, s_in * dz), ow)

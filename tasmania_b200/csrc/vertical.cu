@@ -1,0 +1,189 @@
+// vertical.cu -- vertical advection of the isentropic model.
+//
+// Reference (numpy definitions):
+//   src/tasmania/isentropic/physics/vertical_advection.py:L271-L386   IsentropicVerticalAdvection
+//   src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/upwind.py:L31-L33,
+//   centered.py:L28-L30, third_order_upwind.py:L31-L38, fifth_order_upwind.py:L31-L42
+//
+// tendency[k] = (F[k+1] - F[k]) / dz for k in [k0 + e, k0 + nk - e), F[K] the flux through
+// interface K (between levels K-1 and K) of s, su, sv (and of s q for the water species, whose
+// tendency is further divided by s); zero elsewhere.  The vertical velocity w either lives on
+// the interfaces or is averaged onto them from the main levels.  One thread per point, i along
+// the warp; a thread evaluates the two fluxes of its level (each interface flux is evaluated by
+// the two levels it separates: the kernel stays a pure stream of 4 + 3 (7 + 6 moist) fields).
+// The reference's set_output works on WHOLE storages (generics.py:L38-L40): with `overwrite` the
+// output is zero outside the computed levels -- and outside the box -- so the kernel covers the
+// full output storage.  Operation order is the reference's: bit-identical results.
+#include "stencil_math.cuh"
+
+using namespace tb200;
+
+namespace {
+
+template <int SCHEME>
+struct VFlux;
+
+template <>
+struct VFlux<TB200_FLUX_UPWIND> {  // upwind.py:L31-L33
+  static constexpr int extent = 1;
+  template <class Phi>
+  __device__ __forceinline__ static double eval(double w, Phi phi, int K, const FluxConst &) {
+    return w * (w > 0.0 ? phi(K) : phi(K - 1));
+  }
+};
+template <>
+struct VFlux<TB200_FLUX_CENTERED> {  // centered.py:L28-L30
+  static constexpr int extent = 1;
+  template <class Phi>
+  __device__ __forceinline__ static double eval(double w, Phi phi, int K, const FluxConst &) {
+    return w * 0.5 * (phi(K) + phi(K - 1));
+  }
+};
+template <>
+struct VFlux<TB200_FLUX_THIRD_ORDER_UPWIND> {  // third_order_upwind.py:L31-L38
+  static constexpr int extent = 2;
+  template <class Phi>
+  __device__ __forceinline__ static double eval(double w, Phi phi, int K, const FluxConst &c) {
+    const double wq = w / c.c12;  // |w| / 12 == |w / 12| bit for bit
+    const double m2 = phi(K - 2), m1 = phi(K - 1), p0 = phi(K), p1 = phi(K + 1);
+    return wq * (7.0 * (m1 + p0) - (m2 + p1)) - fabs(wq) * (3.0 * (m1 - p0) - (m2 - p1));
+  }
+};
+template <>
+struct VFlux<TB200_FLUX_FIFTH_ORDER_UPWIND> {  // fifth_order_upwind.py:L31-L42
+  static constexpr int extent = 3;
+  template <class Phi>
+  __device__ __forceinline__ static double eval(double w, Phi phi, int K, const FluxConst &c) {
+    const double wq = w / c.c60;
+    const double m3 = phi(K - 3), m2 = phi(K - 2), m1 = phi(K - 1);
+    const double p0 = phi(K), p1 = phi(K + 1), p2 = phi(K + 2);
+    return wq * (37.0 * (m1 + p0) - 8.0 * (m2 + p1) + (m3 + p2)) -
+           fabs(wq) * (10.0 * (m1 - p0) - 5.0 * (m2 - p1) + (m3 - p2));
+  }
+};
+
+struct VAdvArgs {
+  View w, s, su, sv, qv, qc, qr;
+  View out[6];   // s, su, sv, qv, qc, qr
+  bool ow[6];
+  int nout;      // 3 dry, 6 moist
+  bool staggered;
+  double dz;
+  FluxConst fc;
+  int i0, j0, k0, di, dj, dk;
+};
+
+template <int SCHEME>
+__global__ void __launch_bounds__(256) vadv_kernel(const VAdvArgs a, int n0, int n1, int n2) {
+  using F = VFlux<SCHEME>;
+  constexpr int E = F::extent;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n0 || j >= n1) return;
+  const bool col_in = i >= a.i0 && i < a.i0 + a.di && j >= a.j0 && j < a.j0 + a.dj;
+  for (int k = blockIdx.z; k < n2; k += gridDim.z) {
+    const bool inside = col_in && k >= a.k0 + E && k < a.k0 + a.dk - E;
+    double tnd[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (inside) {
+      // vertical velocity at the interfaces k and k+1 (vertical_advection.py:L308-L320); both lie
+      // strictly inside the column, where the averaged velocity is defined
+      double w0, w1;
+      if (a.staggered) {
+        w0 = a.w.ld(i, j, k);
+        w1 = a.w.ld(i, j, k + 1);
+      } else {
+        const double wm = a.w.ld(i, j, k - 1), wc = a.w.ld(i, j, k), wp = a.w.ld(i, j, k + 1);
+        w0 = 0.5 * (wc + wm);
+        w1 = 0.5 * (wp + wc);
+      }
+      const View *dry[3] = {&a.s, &a.su, &a.sv};
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        const View &v = *dry[f];
+        auto phi = [&](int kk) { return v.ld(i, j, kk); };
+        tnd[f] = (F::eval(w1, phi, k + 1, a.fc) - F::eval(w0, phi, k, a.fc)) / a.dz;  // L341-L353
+      }
+      if (a.nout == 6) {
+        const View *q[3] = {&a.qv, &a.qc, &a.qr};
+        const double sdz = a.s.ld(i, j, k) * a.dz;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          const View &v = *q[f];
+          auto phi = [&](int kk) { return a.s.ld(i, j, kk) * v.ld(i, j, kk); };  // L323-L329
+          tnd[3 + f] = (F::eval(w1, phi, k + 1, a.fc) - F::eval(w0, phi, k, a.fc)) / sdz;  // L366-L385
+        }
+      }
+    }
+    for (int f = 0; f < a.nout; ++f) {
+      double &o = a.out[f](i, j, k);
+      o = a.ow[f] ? tnd[f] : o + tnd[f];  // generics.py:L38-L40, on the whole storage
+    }
+  }
+}
+
+template <int SCHEME>
+int run_vadv(const VAdvArgs &a, cudaStream_t st) {
+  const View &o = a.out[0];
+  if (o.n0 <= 0 || o.n1 <= 0 || o.n2 <= 0) return TB200_OK;
+  dim3 block(64, 4, 1);
+  dim3 grid((o.n0 + 63) / 64, (o.n1 + 3) / 4, o.n2 > 65535 ? 65535 : o.n2);
+  vadv_kernel<SCHEME><<<grid, block, 0, st>>>(a, o.n0, o.n1, o.n2);
+  return check_launch("vertical_advection");
+}
+
+}  // namespace
+
+extern "C" int tb200_vertical_advection(
+    int flux_scheme, int staggered_w, const tb200_field *in_w, const tb200_field *in_s,
+    const tb200_field *in_su, const tb200_field *in_sv, tb200_field *out_s, tb200_field *out_su,
+    tb200_field *out_sv, const tb200_field *in_qv, const tb200_field *in_qc,
+    const tb200_field *in_qr, tb200_field *out_qv, tb200_field *out_qc, tb200_field *out_qr,
+    double dz, uint32_t overwrite_flags, const int32_t origin[3], const int32_t domain[3],
+    void *stream) {
+  VAdvArgs a{};
+  a.w = view(in_w); a.s = view(in_s); a.su = view(in_su); a.sv = view(in_sv);
+  a.qv = view(in_qv); a.qc = view(in_qc); a.qr = view(in_qr);
+  a.out[0] = view(out_s); a.out[1] = view(out_su); a.out[2] = view(out_sv);
+  a.out[3] = view(out_qv); a.out[4] = view(out_qc); a.out[5] = view(out_qr);
+  const bool moist = a.qv.ok() || a.qc.ok() || a.qr.ok() || a.out[3].ok() || a.out[4].ok() || a.out[5].ok();
+  a.nout = moist ? 6 : 3;
+  a.staggered = staggered_w != 0;
+  a.dz = dz;
+  a.fc = make_flux_const(1.0, 1.0);
+  a.i0 = origin[0]; a.j0 = origin[1]; a.k0 = origin[2];
+  a.di = domain[0]; a.dj = domain[1]; a.dk = domain[2];
+  for (int f = 0; f < 6; ++f) a.ow[f] = (overwrite_flags >> f) & 1u;
+  int e = -1;
+  switch (flux_scheme) {
+    case TB200_FLUX_UPWIND: case TB200_FLUX_CENTERED: e = 1; break;
+    case TB200_FLUX_THIRD_ORDER_UPWIND: e = 2; break;
+    case TB200_FLUX_FIFTH_ORDER_UPWIND: e = 3; break;
+  }
+  TB200_REQUIRE(e > 0, "vertical_advection: unknown flux scheme %d", flux_scheme);
+  TB200_REQUIRE(box_inside(a.s, origin, domain) && box_inside(a.su, origin, domain) &&
+                    box_inside(a.sv, origin, domain),
+                "vertical_advection: box outside an input storage");
+  TB200_REQUIRE(a.staggered ? box_inside(a.w, origin, domain, 0, 0, 0, 0, 0, 1)
+                            : box_inside(a.w, origin, domain),
+                "vertical_advection: box outside the vertical velocity storage");
+  if (moist)
+    TB200_REQUIRE(box_inside(a.qv, origin, domain) && box_inside(a.qc, origin, domain) &&
+                      box_inside(a.qr, origin, domain),
+                  "vertical_advection: moist call needs in_qv, in_qc, in_qr covering the box");
+  for (int f = 0; f < a.nout; ++f) {
+    TB200_REQUIRE(box_inside(a.out[f], origin, domain), "vertical_advection: box outside an output storage");
+    TB200_REQUIRE(a.out[f].n0 == a.out[0].n0 && a.out[f].n1 == a.out[0].n1 && a.out[f].n2 == a.out[0].n2,
+                  "vertical_advection: the output storages must share one shape");
+    TB200_REQUIRE(a.out[f].p != a.s.p && a.out[f].p != a.su.p && a.out[f].p != a.sv.p &&
+                      a.out[f].p != a.w.p && a.out[f].p != a.qv.p && a.out[f].p != a.qc.p &&
+                      a.out[f].p != a.qr.p,
+                  "vertical_advection: outputs must not alias inputs");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (flux_scheme) {
+    case TB200_FLUX_UPWIND: return run_vadv<TB200_FLUX_UPWIND>(a, st);
+    case TB200_FLUX_CENTERED: return run_vadv<TB200_FLUX_CENTERED>(a, st);
+    case TB200_FLUX_THIRD_ORDER_UPWIND: return run_vadv<TB200_FLUX_THIRD_ORDER_UPWIND>(a, st);
+    default: return run_vadv<TB200_FLUX_FIFTH_ORDER_UPWIND>(a, st);
+  }
+}

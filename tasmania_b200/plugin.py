@@ -138,6 +138,8 @@ def _class_scoped_stencils():
          st.damping_b200),
         ("tasmania.burgers.dynamics.stepper", "BurgersStepper", "forward_euler",
          st.burgers_forward_euler_b200),
+        ("tasmania.isentropic.physics.vertical_advection", "IsentropicVerticalAdvection", "stencil",
+         st.vertical_advection_b200),
     ]
     out += [(m, c, s, getattr(st, d)) for (m, c, s, d) in st.KESSLER_CLASS_STENCILS]
     return out
@@ -146,12 +148,13 @@ def _class_scoped_stencils():
 def _class_scoped_subroutines():
     mf = "tasmania.isentropic.dynamics.subclasses.minimal_horizontal_fluxes"
     ff = "tasmania.isentropic.dynamics.subclasses.horizontal_fluxes"
+    vf = "tasmania.isentropic.dynamics.subclasses.minimal_vertical_fluxes"
     ad = "tasmania.burgers.dynamics.subclasses.advection"
     out = []
     for mod, cls, scheme in (("upwind", "Upwind", "upwind"), ("centered", "Centered", "centered"),
                              ("third_order_upwind", "ThirdOrderUpwind", "third_order_upwind"),
                              ("fifth_order_upwind", "FifthOrderUpwind", "fifth_order_upwind")):
-        for pkg in (mf, ff):
+        for pkg in (mf, ff, vf):
             for name in ("flux_dry", "flux_moist"):
                 out.append((f"{pkg}.{mod}", cls, name, _descriptor(st.FLUX[scheme], name)))
     for mod, cls in (("first_order", "FirstOrder"), ("second_order", "SecondOrder"),

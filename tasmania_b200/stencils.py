@@ -449,6 +449,34 @@ def accumulated_precipitation_b200(externals, *, in_rho, in_qr, in_vt, in_accpre
           _i3(domain), _stream())
 
 
+# ------------------------------------------------------------------ vertical advection (8f-1)
+def _vflux_code(externals):
+    d = _scheme_of(externals.get("get_flux_dry", externals.get("flux_dry")))
+    if isinstance(d, FluxScheme):
+        return d.code
+    if isinstance(d, str):
+        return lib.FLUX_SCHEMES[d]
+    raise lib.B200Error("externals['get_flux_dry'] must be a tasmania_b200 FluxScheme descriptor")
+
+
+@stencil_definition("vertical_advection")
+def vertical_advection_b200(
+    externals, *, in_w, in_s, in_su, in_sv, out_s, out_su, out_sv, in_qv=None, in_qc=None,
+    in_qr=None, out_qv=None, out_qc=None, out_qr=None, dt=0.0, dz, ow_out_s, ow_out_su, ow_out_sv,
+    ow_out_qv=True, ow_out_qc=True, ow_out_qr=True, origin, domain):
+    """IsentropicVerticalAdvection's stencil (vertical_advection.py:L271-L386); externals as set
+    by the class (L148-L160): get_flux_dry (scheme descriptor), moist, staggering."""
+    moist = bool(externals.get("moist", False))
+    if moist and any(x is None for x in (in_qv, in_qc, in_qr, out_qv, out_qc, out_qr)):
+        raise lib.B200Error("vertical_advection: moist=True needs in_q* and out_q*")
+    ows = (ow_out_s, ow_out_su, ow_out_sv, ow_out_qv, ow_out_qc, ow_out_qr)
+    flags = sum(1 << n for n, ow in enumerate(ows) if ow)
+    q = [(_f(x) if moist else None) for x in (in_qv, in_qc, in_qr, out_qv, out_qc, out_qr)]
+    _call("tb200_vertical_advection", _vflux_code(externals), int(bool(externals.get("staggering", False))),
+          _f(in_w), _f(in_s), _f(in_su), _f(in_sv), _f(out_s), _f(out_su), _f(out_sv),
+          q[0], q[1], q[2], q[3], q[4], q[5], float(dz), flags, _i3(origin), _i3(domain), _stream())
+
+
 _KE = "tasmania.physics.microphysics.kessler"
 KESSLER_CLASS_STENCILS += [
     (_KE, "KesslerMicrophysics", "kessler", "kessler_b200"),

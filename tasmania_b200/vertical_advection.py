@@ -1,0 +1,66 @@
+# -*- coding: utf-8 -*-
+"""Host-side mirror of ``tasmania.IsentropicVerticalAdvection``
+(src/tasmania/isentropic/physics/vertical_advection.py:L71-L269) at the raw-array level: same
+constructor arguments, same externals, same ``array_call`` keyword wiring; the arithmetic runs
+in ``tb200_vertical_advection`` (csrc/vertical.cu).  SURVEY.md section 8f, row 1."""
+from __future__ import annotations
+
+from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
+from tasmania_b200.stencils import FLUX
+
+S, SU, SV = "air_isentropic_density", "x_momentum_isentropic", "y_momentum_isentropic"
+MFWV = "mass_fraction_of_water_vapor_in_air"
+MFCW = "mass_fraction_of_cloud_liquid_water_in_air"
+MFPW = "mass_fraction_of_precipitation_water_in_air"
+W_ML = "tendency_of_air_potential_temperature"
+W_HL = "tendency_of_air_potential_temperature_on_interface_levels"
+
+
+class IsentropicVerticalAdvection(StencilFactory):
+    """Vertical derivative of the conservative vertical advection flux of s, su, sv (and of the
+    water species when ``moist``), by one of the minimal vertical flux schemes
+    (src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/*.py)."""
+
+    class_stencils = {"stencil": "vertical_advection"}
+
+    def __init__(self, grid, flux_scheme="upwind", moist=False,
+                 tendency_of_air_potential_temperature_on_interface_levels=False, *, backend="b200",
+                 backend_options=None, storage_shape=None, storage_options=None):
+        super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
+        if flux_scheme not in FLUX:
+            raise ValueError(f"unknown vertical flux scheme {flux_scheme!r}")
+        self.grid = grid
+        self._moist = moist
+        self._stgz = tendency_of_air_potential_temperature_on_interface_levels
+        self._vflux = FLUX[flux_scheme]
+        # vertical_advection.py:L148-L160
+        assert grid.nz >= 2 * self._vflux.extent + 1, "too few vertical levels for the flux scheme"
+        self.storage_shape = tuple(storage_shape or (grid.nx + 1, grid.ny + 1, grid.nz + 1))
+        self.backend_options.externals = {
+            "flux_end": -self._vflux.extent + 1 if self._vflux.extent > 1 else None,
+            "flux_extent": self._vflux.extent,
+            "get_flux_dry": self._vflux,
+            "get_flux_moist": self._vflux,
+            "moist": moist,
+            "set_output": self.get_subroutine_definition("set_output"),
+            "staggering": self._stgz,
+        }
+        self._stencil = self.compile_stencil("stencil")
+
+    def array_call(self, state, out_tendencies, out_diagnostics=None, overwrite_tendencies=None):
+        """vertical_advection.py:L216-L269"""
+        g = self.grid
+        ow = overwrite_tendencies or {}
+        args = {
+            "dz": g.dz,
+            "in_w": state[W_HL] if self._stgz else state[W_ML],
+            "in_s": state[S], "out_s": out_tendencies[S], "ow_out_s": ow.get(S, True),
+            "in_su": state[SU], "out_su": out_tendencies[SU], "ow_out_su": ow.get(SU, True),
+            "in_sv": state[SV], "out_sv": out_tendencies[SV], "ow_out_sv": ow.get(SV, True),
+        }
+        if self._moist:
+            for key, name in (("qv", MFWV), ("qc", MFCW), ("qr", MFPW)):
+                args["in_" + key] = state[name]
+                args["out_" + key] = out_tendencies[name]
+                args["ow_out_" + key] = ow.get(name, True)
+        self._stencil(**args, origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))

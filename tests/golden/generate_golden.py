@@ -402,6 +402,65 @@ def gen_kessler():
 
     save("kessler", dims=np.array([nx, ny, nz]), **out)
 
+# ============================================================================ vertical advection
+VFLUX_CLASSES = {"upwind": "Upwind", "centered": "Centered", "third_order_upwind": "ThirdOrderUpwind",
+                 "fifth_order_upwind": "FifthOrderUpwind"}
+
+
+def gen_vertical_advection():
+    """IsentropicVerticalAdvection._stencil_numpy
+    (src/tasmania/isentropic/physics/vertical_advection.py:L271-L386) with the four minimal
+    vertical flux schemes (src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/
+    *.py), vertical velocity on main or interface levels, dry and moist, overwrite on / off.
+    The method is run unbound on a stand-in ``self`` that carries what it reads: _vflux, _stgz,
+    _moist, get_field_storage_shape, storage_options.dtype."""
+    va = refload.load("tasmania.isentropic.physics.vertical_advection")
+    gen = refload.load("tasmania.framework.subclasses.subroutine_definitions.generics")
+    st = refload.numpy_stencil(va.IsentropicVerticalAdvection._stencil_numpy,
+                               {"set_output": gen.set_output_numpy})
+    rng = np.random.default_rng(20261020)
+    nx, ny, nz = 11, 9, 13
+    shape = (nx + 1, ny + 1, nz + 1)
+    dz = 2.5
+    ins = {
+        "w": rng.uniform(-0.02, 0.02, size=shape),
+        "s": rng.uniform(10.0, 1000.0, size=shape),
+        "su": rng.uniform(-5e4, 5e4, size=shape),
+        "sv": rng.uniform(-5e4, 5e4, size=shape),
+        "qv": rng.uniform(0.0, 5.0, size=shape),
+        "qc": rng.uniform(0.0, 5.0, size=shape),
+        "qr": rng.uniform(0.0, 5.0, size=shape),
+    }
+    ins["w"][::4, ::3, ::2] = 0.0  # zeros exercise the upwind selection
+    prev = {n: rng.uniform(-1.0, 1.0, size=shape) for n in ("s", "su", "sv", "qv", "qc", "qr")}
+    out = {"in_" + k: v for k, v in ins.items()}
+    out.update({"prev_" + k: v for k, v in prev.items()})
+    for scheme, cls in VFLUX_CLASSES.items():
+        mod = refload.load("tasmania.isentropic.dynamics.subclasses.minimal_vertical_fluxes." + scheme)
+        flux_cls = getattr(mod, cls)
+        vflux = types.SimpleNamespace(
+            extent=flux_cls.extent,
+            get_subroutine_definition=lambda name, c=flux_cls: getattr(c, name + "_numpy"))
+        for stgz in (False, True):
+            for moist in (False, True):
+                for ow in (True, False):
+                    fake = types.SimpleNamespace(
+                        _vflux=vflux, _stgz=stgz, _moist=moist,
+                        get_field_storage_shape=lambda name=None: shape,
+                        storage_options=types.SimpleNamespace(dtype=np.float64))
+                    names = ("s", "su", "sv") + (("qv", "qc", "qr") if moist else ())
+                    outs = {n: (rng.uniform(-1, 1, size=shape) if ow else prev[n].copy()) for n in names}
+                    kw = {"in_w": ins["w"], "dz": dz, "origin": (0, 0, 0), "domain": (nx, ny, nz)}
+                    for n in names:
+                        kw["in_" + n] = ins[n]
+                        kw["out_" + n] = outs[n]
+                        kw["ow_out_" + n] = ow
+                    st(fake, **kw)
+                    for n in names:
+                        out[f"{scheme}_z{int(stgz)}_m{int(moist)}_o{int(ow)}_{n}"] = outs[n]
+    save("vertical_advection", dims=np.array([nx, ny, nz]), dz=np.array([dz]), **out)
+
+
 # ============================================================================ isentropic
 def _make_domain(nx, ny, nz, hb_type, nb, hb_kwargs, topo_time=1800.0, xlim=(-176, 176),
                  topo=True):
@@ -559,6 +618,7 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
 CASES = {
     "stencils": gen_stencils,
     "kessler": gen_kessler,
+    "vertical_advection": gen_vertical_advection,
     "isen_dry_rk3_5th": lambda: gen_isentropic_dry(
         "isen_dry_rk3_5th", 25, 21, 8, "rk3ws_si", "fifth_order_upwind", 3, 6, 6, 5.0),
     "isen_dry_rk3_3rd": lambda: gen_isentropic_dry(

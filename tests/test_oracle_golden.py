@@ -227,3 +227,42 @@ def test_kessler_family_bitwise():
         np.testing.assert_array_equal(got, want, err_msg=f"{tag}:{name}")
         n += 1
     assert n >= 60
+
+
+def _vertical_advection_cases(fx):
+    """(key prefix, scheme, staggered, moist, overwrite) of tests/golden/vertical_advection.npz"""
+    from oracle import vertical_advection as va
+
+    for scheme in va.EXTENT:
+        for z in (0, 1):
+            for m in (0, 1):
+                for ow in (1, 0):
+                    yield f"{scheme}_z{z}_m{m}_o{ow}_", scheme, bool(z), bool(m), bool(ow)
+
+
+def test_vertical_advection_bitwise():
+    """the oracle's vertical advection against the reference's own numpy stencil
+    (vertical_advection.py:L271-L386) for the four flux schemes, velocity on main / interface
+    levels, dry / moist, overwrite on / off -- bit for bit, on the WHOLE output storages."""
+    from oracle import vertical_advection as va
+
+    fx = hp.load("vertical_advection")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    dz = float(fx["dz"][0])
+    n = 0
+    for prefix, scheme, stg, moist, ow in _vertical_advection_cases(fx):
+        names = ("s", "su", "sv") + (("qv", "qc", "qr") if moist else ())
+        outs = {k: (np.full(fx["in_s"].shape, 7.0) if ow else fx["prev_" + k].copy()) for k in names}
+        kw = dict(dz=dz, origin=(0, 0, 0), domain=(nx, ny, nz))
+        for k in names:
+            kw["ow_out_" + k] = ow
+        if moist:
+            for k in ("qv", "qc", "qr"):
+                kw["in_" + k] = fx["in_" + k]
+                kw["out_" + k] = outs[k]
+        va.vertical_advection(scheme, stg, fx["in_w"], fx["in_s"], fx["in_su"], fx["in_sv"],
+                              outs["s"], outs["su"], outs["sv"], **kw)
+        for k in names:
+            np.testing.assert_array_equal(outs[k], fx[prefix + k], err_msg=prefix + k)
+            n += 1
+    assert n == 4 * 2 * (3 + 6) * 2
