@@ -304,12 +304,18 @@ __global__ void __launch_bounds__(128, 2) diag_column_kernel(const DiagArgs a) {
   double pb = 0.0, eb = 0.0, thb = 0.0, m = 0.0, hk = 0.0;
   double *pe = &a.exn(i, j, k0), *pm = &a.mtg(i, j, k0), *ph = &a.h(i, j, k0);
   const double *pth = &a.theta(i, j, k0);
-  auto interface = [&](int l1, double pa, double ea) {  // interface k0 + l1, l1 < n
-    const double tha = __ldg(pth + l1 * a.theta.s2);
+  // One interface of the upward sweep: x = rd (th_a e_a + th_b e_b) (p_a - p_b) / (cp g (p_a + p_b))
+  // is the height increment (L356-L360); the increments of a group of eight interfaces are
+  // evaluated side by side (eight independent IEEE divisions in flight), only the running sums
+  // (h and the Montgomery potential) are serial.
+  auto increment = [&](double tha, double ea, double pa, double thb_, double eb_, double pb_) {
+    return a.rd * (tha * ea + thb_ * eb_) * (pa - pb_) / (cpg * (pa + pb_));
+  };
+  auto interface = [&](int l1, double pa, double ea, double tha, double x) {  // interface k0 + l1 < k0 + n
     pe[l1 * a.exn.s2] = ea;
     if (l1 < n - 1) m = m + a.dz * eb;  // mtg[k] = mtg[k+1] + dz exn[k+1]
     pm[l1 * a.mtg.s2] = m;
-    hk = hk - a.rd * (tha * ea + thb * eb) * (pa - pb) / (cpg * (pa + pb));
+    hk = hk - x;
     ph[l1 * a.h.s2] = hk;
     pb = pa; eb = ea; thb = tha;
   };
@@ -320,25 +326,44 @@ __global__ void __launch_bounds__(128, 2) diag_column_kernel(const DiagArgs a) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) x.v[c] = 8 * q + c < n ? pr[8 * q + c] / a.cpref : 1.0;
       const E8 ex = exner8_diag(x, a.kappa, a.cp);
+      // theta at the interfaces 8q+1 .. 8q+8 (those of pr[8q .. 8q+7])
+      double th[8], inc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) th[c] = 8 * q + c < n ? __ldg(pth + (8 * q + c + 1) * a.theta.s2) : 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int l = 8 * q + c;
+        if (l < n - 1) {
+          // the interface below: the next entry of this group, or the one carried from group q+1
+          const double thb_ = c < 7 ? th[c + 1] : thb, eb_ = c < 7 ? ex.v[c + 1] : eb;
+          const double pb_ = c < 7 ? pr[l + 1] : pb;
+          inc[c] = increment(th[c], ex.v[c], pr[l], thb_, eb_, pb_);
+        } else {
+          inc[c] = 0.0;
+        }
+      }
 #pragma unroll
       for (int c = 7; c >= 0; --c) {
         const int l = 8 * q + c;  // interface k0 + l + 1
         if (l == n - 1) {         // the lowest interface starts the sweep
           pb = pr[l];
           eb = ex.v[c];
-          thb = __ldg(pth + n * a.theta.s2);
+          thb = th[c];
           hk = a.hs(i, j, kt);
           const double mtg_s = thb * eb + a.g * hk;  // L347
           m = mtg_s + 0.5 * a.dz * eb;
           pe[n * a.exn.s2] = eb;
           ph[n * a.h.s2] = hk;  // L354
         } else if (l < n - 1) {
-          interface(l + 1, pr[l], ex.v[c]);
+          interface(l + 1, pr[l], ex.v[c], th[c], inc[c]);
         }
       }
     }
   }
-  interface(0, a.pt, a.cp * pow_pos(a.pt / a.cpref, a.kappa));
+  {
+    const double tha = __ldg(pth), ea = a.cp * pow_pos(a.pt / a.cpref, a.kappa);
+    interface(0, a.pt, ea, tha, increment(tha, ea, a.pt, thb, eb, pb));
+  }
 }
 
 extern "C" int tb200_montgomery(const tb200_field *in_hs, const tb200_field *in_s,
