@@ -240,6 +240,12 @@ int tb200_accumulated_precipitation(const tb200_field *in_rho, const tb200_field
                                     double rhow, const int32_t origin[3],
                                     const int32_t domain[3], void *stream);
 
+/* ---- Coriolis forcing of the momenta:
+ * src/tasmania/isentropic/physics/coriolis.py:L166-L186  tnd_su (+)= f sv, tnd_sv (+)= -f su */
+int tb200_coriolis(const tb200_field *in_su, const tb200_field *in_sv, tb200_field *tnd_su,
+                   tb200_field *tnd_sv, double f, int ow_tnd_su, int ow_tnd_sv,
+                   const int32_t origin[3], const int32_t domain[3], void *stream);
+
 /* ---- vertical advection: IsentropicVerticalAdvection._stencil
  * src/tasmania/isentropic/physics/vertical_advection.py:L271-L386 with the minimal vertical flux
  * schemes of src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/ (flux_scheme =

@@ -70,3 +70,10 @@ def vertical_advection(scheme, staggered, in_w, in_s, in_su, in_sv, out_s, out_s
         for q, out, ow in ((in_qv, out_qv, ow_out_qv), (in_qc, out_qc, ow_out_qc), (in_qr, out_qr, ow_out_qr)):
             sq = in_s[i, j, kb:ke] * q[i, j, kb:ke]
             _set_output(out, tendency(sq, s_in * dz), ow)
+
+
+def coriolis(in_su, in_sv, tnd_su, tnd_sv, *, f, ow_tnd_su, ow_tnd_sv, origin, domain):
+    """src/tasmania/isentropic/physics/coriolis.py:L166-L186 (set_output on the box)."""
+    box = tuple(slice(o, o + d) for o, d in zip(origin, domain))
+    _set_output(tnd_su[box], f * in_sv[box], ow_tnd_su)
+    _set_output(tnd_sv[box], -f * in_su[box], ow_tnd_sv)

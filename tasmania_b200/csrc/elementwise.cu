@@ -204,6 +204,31 @@ extern "C" int tb200_damping(const tb200_field *in_phi_now, const tb200_field *i
                     });
 }
 
+// ---------------------------------------------------------------------------- Coriolis (8f-3)
+// src/tasmania/isentropic/physics/coriolis.py:L166-L186: tnd_su = f sv, tnd_sv = -f su, each
+// written or accumulated (set_output) over the box; one pass over both momenta.
+extern "C" int tb200_coriolis(const tb200_field *in_su, const tb200_field *in_sv,
+                              tb200_field *tnd_su, tb200_field *tnd_sv, double f, int ow_tnd_su,
+                              int ow_tnd_sv, const int32_t origin[3], const int32_t domain[3],
+                              void *stream) {
+  View su = view(in_su), sv = view(in_sv), tu = view(tnd_su), tv = view(tnd_sv);
+  TB200_REQUIRE(box_inside(su, origin, domain) && box_inside(sv, origin, domain) &&
+                    box_inside(tu, origin, domain) && box_inside(tv, origin, domain),
+                "coriolis: box outside storage");
+  TB200_REQUIRE(tu.p != su.p && tu.p != sv.p && tv.p != su.p && tv.p != sv.p && tu.p != tv.p,
+                "coriolis: tendencies must not alias the momenta or each other");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  const bool owu = ow_tnd_su != 0, owv = ow_tnd_sv != 0;
+  const double mf = -f;
+  return launch_box("coriolis", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      const double a = f * sv(i, j, k), b = mf * su(i, j, k);
+                      tu(i, j, k) = owu ? a : tu(i, j, k) + a;
+                      tv(i, j, k) = owv ? b : tv(i, j, k) + b;
+                    });
+}
+
 // ---------------------------------------------------------------------------- K4
 extern "C" int tb200_velocity(int axis, const tb200_field *in_d, const tb200_field *in_dw,
                               tb200_field *out_w, int staggering, const int32_t origin[3],

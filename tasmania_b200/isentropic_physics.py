@@ -1,8 +1,11 @@
 # -*- coding: utf-8 -*-
-"""Host-side mirror of ``tasmania.IsentropicVerticalAdvection``
-(src/tasmania/isentropic/physics/vertical_advection.py:L71-L269) at the raw-array level: same
-constructor arguments, same externals, same ``array_call`` keyword wiring; the arithmetic runs
-in ``tb200_vertical_advection`` (csrc/vertical.cu).  SURVEY.md section 8f, row 1."""
+"""Host-side mirrors of the isentropic physics components of SURVEY.md section 8f at the
+raw-array level -- ``tasmania.IsentropicVerticalAdvection``
+(src/tasmania/isentropic/physics/vertical_advection.py:L71-L269, row 1) and
+``tasmania.IsentropicConservativeCoriolis`` (src/tasmania/isentropic/physics/coriolis.py:L44-L186,
+row 3): same constructor arguments, same externals, same ``array_call`` keyword wiring; the
+arithmetic runs in ``tb200_vertical_advection`` (csrc/vertical.cu) and ``tb200_coriolis``
+(csrc/elementwise.cu)."""
 from __future__ import annotations
 
 from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
@@ -64,3 +67,24 @@ class IsentropicVerticalAdvection(StencilFactory):
                 args["out_" + key] = out_tendencies[name]
                 args["ow_out_" + key] = ow.get(name, True)
         self._stencil(**args, origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))
+
+
+class IsentropicConservativeCoriolis(StencilFactory):
+    """Mirror of ``tasmania.IsentropicConservativeCoriolis``
+    (src/tasmania/isentropic/physics/coriolis.py:L44-L164): Coriolis forcing of the momenta on
+    the interior of the numerical grid (``nb`` boundary layers excluded)."""
+
+    def __init__(self, grid, nb, coriolis_parameter=1e-4, *, backend="b200", backend_options=None,
+                 storage_options=None):
+        super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
+        self.grid, self._nb, self._f = grid, int(nb), float(coriolis_parameter)
+        self.backend_options.externals = {"set_output": self.get_subroutine_definition("set_output")}
+        self._stencil = self.compile_stencil("coriolis")
+
+    def array_call(self, state, out_tendencies, out_diagnostics=None, overwrite_tendencies=None):
+        g, nb = self.grid, self._nb
+        ow = overwrite_tendencies or {}
+        self._stencil(in_su=state[SU], in_sv=state[SV], tnd_su=out_tendencies[SU],
+                      tnd_sv=out_tendencies[SV], f=self._f, ow_tnd_su=ow.get(SU, True),
+                      ow_tnd_sv=ow.get(SV, True), origin=(nb, nb, 0),
+                      domain=(g.nx - 2 * nb, g.ny - 2 * nb, g.nz))

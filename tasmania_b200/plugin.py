@@ -140,6 +140,8 @@ def _class_scoped_stencils():
          st.burgers_forward_euler_b200),
         ("tasmania.isentropic.physics.vertical_advection", "IsentropicVerticalAdvection", "stencil",
          st.vertical_advection_b200),
+        ("tasmania.isentropic.physics.coriolis", "IsentropicConservativeCoriolis", "coriolis",
+         st.coriolis_b200),
     ]
     out += [(m, c, s, getattr(st, d)) for (m, c, s, d) in st.KESSLER_CLASS_STENCILS]
     return out

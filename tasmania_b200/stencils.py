@@ -449,6 +449,14 @@ def accumulated_precipitation_b200(externals, *, in_rho, in_qr, in_vt, in_accpre
           _i3(domain), _stream())
 
 
+# ------------------------------------------------------------------ Coriolis (8f-3)
+@stencil_definition("coriolis")
+def coriolis_b200(externals, *, in_su, in_sv, tnd_su, tnd_sv, f, ow_tnd_su, ow_tnd_sv, origin, domain):
+    """IsentropicConservativeCoriolis's stencil (isentropic/physics/coriolis.py:L166-L186)."""
+    _call("tb200_coriolis", _f(in_su), _f(in_sv), _f(tnd_su), _f(tnd_sv), float(f),
+          int(bool(ow_tnd_su)), int(bool(ow_tnd_sv)), _i3(origin), _i3(domain), _stream())
+
+
 # ------------------------------------------------------------------ vertical advection (8f-1)
 def _vflux_code(externals):
     d = _scheme_of(externals.get("get_flux_dry", externals.get("flux_dry")))

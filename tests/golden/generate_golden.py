@@ -458,7 +458,19 @@ def gen_vertical_advection():
                     st(fake, **kw)
                     for n in names:
                         out[f"{scheme}_z{int(stgz)}_m{int(moist)}_o{int(ow)}_{n}"] = outs[n]
-    save("vertical_advection", dims=np.array([nx, ny, nz]), dz=np.array([dz]), **out)
+    # ---- Coriolis: IsentropicConservativeCoriolis._stencil_numpy,
+    # src/tasmania/isentropic/physics/coriolis.py:L166-L186, on the interior box (nb = 2)
+    co = refload.load("tasmania.isentropic.physics.coriolis")
+    cst = refload.numpy_stencil(co.IsentropicConservativeCoriolis._stencil_numpy,
+                                {"set_output": gen.set_output_numpy})
+    f = 1.2345e-4
+    for owu, owv in ((True, True), (False, True), (False, False)):
+        tu, tv = prev["su"].copy(), prev["sv"].copy()
+        cst(in_su=ins["su"], in_sv=ins["sv"], tnd_su=tu, tnd_sv=tv, f=f, ow_tnd_su=owu, ow_tnd_sv=owv,
+            origin=(2, 2, 0), domain=(nx - 4, ny - 4, nz))
+        out[f"coriolis_o{int(owu)}{int(owv)}_su"] = tu
+        out[f"coriolis_o{int(owu)}{int(owv)}_sv"] = tv
+    save("vertical_advection", dims=np.array([nx, ny, nz]), dz=np.array([dz]), f=np.array([f]), **out)
 
 
 # ============================================================================ isentropic

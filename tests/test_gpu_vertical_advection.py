@@ -52,7 +52,7 @@ def test_host_mirror_vs_oracle_bitwise(scheme, moist, stg):
     number of levels) with a sub-box origin exercised through the oracle signature."""
     import tasmania_b200 as tb
     from oracle import vertical_advection as ova
-    from tasmania_b200 import vertical_advection as va
+    from tasmania_b200 import isentropic_physics as va
     from tasmania_b200.grid import Grid
 
     nx, ny, nz = 67, 45, 60
@@ -107,3 +107,21 @@ def test_uniform_column_has_no_tendency_full_size():
        ow_out_s=True, ow_out_su=True, ow_out_sv=True, origin=(0, 0, 0), domain=(nx, ny, nz))
     for o in outs:
         assert float(o.t.abs().max()) <= 1e-12  # 60 w phi / 60 - ... cancels up to rounding of w / 60
+
+
+def test_coriolis_vs_reference_fixture_bitwise():
+    """SURVEY.md 8f-3 through the host mirror of IsentropicConservativeCoriolis (nb = 2)."""
+    import tasmania_b200 as tb
+    from tasmania_b200 import isentropic_physics as va
+    from tasmania_b200.grid import Grid
+
+    fx = hp.load("vertical_advection")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    grid = Grid((-10.0, 10.0), nx, (-7.0, 7.0), ny, (400.0, 280.0), nz, units_to_m=1e3)
+    comp = va.IsentropicConservativeCoriolis(grid, 2, coriolis_parameter=float(fx["f"][0]))
+    state = {va.SU: tb.as_storage(fx["in_su"]), va.SV: tb.as_storage(fx["in_sv"])}
+    for owu, owv in ((True, True), (False, True), (False, False)):
+        out = {va.SU: tb.as_storage(fx["prev_su"]), va.SV: tb.as_storage(fx["prev_sv"])}
+        comp.array_call(state, out, {}, {va.SU: owu, va.SV: owv})
+        np.testing.assert_array_equal(tb.to_numpy(out[va.SU]), fx[f"coriolis_o{int(owu)}{int(owv)}_su"])
+        np.testing.assert_array_equal(tb.to_numpy(out[va.SV]), fx[f"coriolis_o{int(owu)}{int(owv)}_sv"])

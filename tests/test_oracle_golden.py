@@ -266,3 +266,17 @@ def test_vertical_advection_bitwise():
             np.testing.assert_array_equal(outs[k], fx[prefix + k], err_msg=prefix + k)
             n += 1
     assert n == 4 * 2 * (3 + 6) * 2
+
+
+def test_coriolis_bitwise():
+    """coriolis.py:L166-L186 on the interior box, written and accumulated."""
+    from oracle import vertical_advection as va
+
+    fx = hp.load("vertical_advection")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    for owu, owv in ((True, True), (False, True), (False, False)):
+        tu, tv = fx["prev_su"].copy(), fx["prev_sv"].copy()
+        va.coriolis(fx["in_su"], fx["in_sv"], tu, tv, f=float(fx["f"][0]), ow_tnd_su=owu, ow_tnd_sv=owv,
+                    origin=(2, 2, 0), domain=(nx - 4, ny - 4, nz))
+        np.testing.assert_array_equal(tu, fx[f"coriolis_o{int(owu)}{int(owv)}_su"])
+        np.testing.assert_array_equal(tv, fx[f"coriolis_o{int(owu)}{int(owv)}_sv"])
