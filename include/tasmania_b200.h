@@ -246,6 +246,15 @@ int tb200_coriolis(const tb200_field *in_su, const tb200_field *in_sv, tb200_fie
                    tb200_field *tnd_sv, double f, int ow_tnd_su, int ow_tnd_sv,
                    const int32_t origin[3], const int32_t domain[3], void *stream);
 
+/* ---- Smagorinsky horizontal turbulence:
+ * src/tasmania/physics/turbulence.py:L165-L229 (in_s NULL: in_a = u, in_b = v, tendencies of u, v)
+ * src/tasmania/isentropic/physics/turbulence.py:L99-L125 (in_s, in_a = su, in_b = sv: u = su / s,
+ * v = sv / s, tendencies of su, sv).  The box needs two more points on every horizontal side. */
+int tb200_smagorinsky(const tb200_field *in_s, const tb200_field *in_a, const tb200_field *in_b,
+                      tb200_field *out_a_tnd, tb200_field *out_b_tnd, double dx, double dy,
+                      double cs, int ow_out_a_tnd, int ow_out_b_tnd, const int32_t origin[3],
+                      const int32_t domain[3], void *stream);
+
 /* ---- vertical advection: IsentropicVerticalAdvection._stencil
  * src/tasmania/isentropic/physics/vertical_advection.py:L271-L386 with the minimal vertical flux
  * schemes of src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/ (flux_scheme =

@@ -21,5 +21,5 @@ Operation order is kept exactly as in the reference (``u / 60.0 * (...)``, divid
 kernels are compared to this oracle at 1e-12 relative.
 """
 
-from oracle import (boundary, burgers, dwarfs, fluxes, isentropic, microphysics,  # noqa: F401
-                    vertical_advection)
+from oracle import (boundary, burgers, dwarfs, fluxes, isentropic, isentropic_physics,  # noqa: F401
+                    microphysics)

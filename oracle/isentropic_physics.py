@@ -1,11 +1,12 @@
 # -*- coding: utf-8 -*-
-"""Oracle (test infrastructure): vertical advection of the isentropic model, SURVEY.md 8f-1.
+"""Oracle (test infrastructure): the isentropic physics components of SURVEY.md 8f -- vertical
+advection (row 1), Coriolis forcing and Smagorinsky turbulence (row 3).
 
 Follows src/tasmania/isentropic/physics/vertical_advection.py:L271-L386 (numpy definition of
 ``IsentropicVerticalAdvection._stencil``) and the flux formulas of
 src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/{upwind.py:L31-L33,
 centered.py:L28-L30, third_order_upwind.py:L31-L38, fifth_order_upwind.py:L31-L42}.
-Pinned bit for bit on tests/golden/vertical_advection.npz (the reference's own code run in place).
+Pinned bit for bit on tests/golden/isentropic_physics.npz (the reference's own code run in place).
 """
 import numpy as np
 
@@ -77,3 +78,42 @@ def coriolis(in_su, in_sv, tnd_su, tnd_sv, *, f, ow_tnd_su, ow_tnd_sv, origin, d
     box = tuple(slice(o, o + d) for o, d in zip(origin, domain))
     _set_output(tnd_su[box], f * in_sv[box], ow_tnd_su)
     _set_output(tnd_sv[box], -f * in_su[box], ow_tnd_sv)
+
+
+def _smagorinsky_core(u, v, dx, dy, cs, ib, ie, jb, je, k):
+    """src/tasmania/physics/turbulence.py:L211-L229: strain rates on the box + 1 from centred
+    differences, eddy viscosity, divergence of the stresses on the box."""
+    def dxc(f, i0, i1, j0, j1):
+        return (f[i0 + 1:i1 + 1, j0:j1, k] - f[i0 - 1:i1 - 1, j0:j1, k]) / (2.0 * dx)
+
+    def dyc(f, i0, i1, j0, j1):
+        return (f[i0:i1, j0 + 1:j1 + 1, k] - f[i0:i1, j0 - 1:j1 - 1, k]) / (2.0 * dy)
+
+    e = (ib - 1, ie + 1, jb - 1, je + 1)
+    s00 = dxc(u, *e)
+    s01 = 0.5 * (dyc(u, *e) + dxc(v, *e))
+    s11 = dyc(v, *e)
+    nu = cs**2 * dx * dy * np.sqrt(2.0 * (s00 * s00 + 2.0 * (s01 * s01) + s11 * s11))
+    p00, p01, p11 = nu * s00, nu * s01, nu * s11
+    u_tnd = 2.0 * ((p00[2:, 1:-1] - p00[:-2, 1:-1]) / (2.0 * dx) + (p01[1:-1, 2:] - p01[1:-1, :-2]) / (2.0 * dy))
+    v_tnd = 2.0 * ((p01[2:, 1:-1] - p01[:-2, 1:-1]) / (2.0 * dx) + (p11[1:-1, 2:] - p11[1:-1, :-2]) / (2.0 * dy))
+    return u_tnd, v_tnd
+
+
+def smagorinsky(in_u, in_v, out_u_tnd, out_v_tnd, *, dx, dy, cs, ow_out_u_tnd, ow_out_v_tnd, origin,
+                domain, in_s=None):
+    """Smagorinsky2d (in_s None) / IsentropicSmagorinsky (in_u, in_v = su, sv; tendencies of them):
+    physics/turbulence.py:L165-L187, isentropic/physics/turbulence.py:L99-L125."""
+    ib, ie = origin[0], origin[0] + domain[0]
+    jb, je = origin[1], origin[1] + domain[1]
+    k = slice(origin[2], origin[2] + domain[2])
+    if in_s is not None:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u, v = in_u / in_s, in_v / in_s
+    else:
+        u, v = in_u, in_v
+    tu, tv = _smagorinsky_core(u, v, dx, dy, cs, ib, ie, jb, je, k)
+    if in_s is not None:
+        tu, tv = in_s[ib:ie, jb:je, k] * tu, in_s[ib:ie, jb:je, k] * tv
+    _set_output(out_u_tnd[ib:ie, jb:je, k], tu, ow_out_u_tnd)
+    _set_output(out_v_tnd[ib:ie, jb:je, k], tv, ow_out_v_tnd)

@@ -3,9 +3,11 @@
 raw-array level -- ``tasmania.IsentropicVerticalAdvection``
 (src/tasmania/isentropic/physics/vertical_advection.py:L71-L269, row 1) and
 ``tasmania.IsentropicConservativeCoriolis`` (src/tasmania/isentropic/physics/coriolis.py:L44-L186,
-row 3): same constructor arguments, same externals, same ``array_call`` keyword wiring; the
+row 3) and the Smagorinsky turbulence components ``tasmania.Smagorinsky2d`` /
+``tasmania.IsentropicSmagorinsky`` (src/tasmania/physics/turbulence.py:L42-L229,
+src/tasmania/isentropic/physics/turbulence.py:L38-L125, row 3): same constructor arguments, same externals, same ``array_call`` keyword wiring; the
 arithmetic runs in ``tb200_vertical_advection`` (csrc/vertical.cu) and ``tb200_coriolis``
-(csrc/elementwise.cu)."""
+(csrc/elementwise.cu) and ``tb200_smagorinsky`` (csrc/turbulence.cu)."""
 from __future__ import annotations
 
 from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
@@ -88,3 +90,46 @@ class IsentropicConservativeCoriolis(StencilFactory):
                       tnd_sv=out_tendencies[SV], f=self._f, ow_tnd_su=ow.get(SU, True),
                       ow_tnd_sv=ow.get(SV, True), origin=(nb, nb, 0),
                       domain=(g.nx - 2 * nb, g.ny - 2 * nb, g.nz))
+
+
+class Smagorinsky2d(StencilFactory):
+    """Mirror of ``tasmania.Smagorinsky2d`` (src/tasmania/physics/turbulence.py:L42-L163):
+    tendencies of x_velocity / y_velocity on the interior of the numerical grid."""
+
+    names = ("x_velocity", "y_velocity")
+
+    def __init__(self, grid, nb, smagorinsky_constant=0.18, *, backend="b200", backend_options=None,
+                 storage_options=None):
+        super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
+        assert nb >= 2, "The number of boundary layers must be greater or equal than two."
+        self.grid, self._nb, self._cs = grid, max(2, int(nb)), float(smagorinsky_constant)
+        self.backend_options.externals = {
+            "core": self.get_subroutine_definition("smagorinsky_core"),
+            "set_output": self.get_subroutine_definition("set_output"),
+        }
+        self._stencil = self.compile_stencil("smagorinsky")
+
+    def _box(self):
+        g, nb = self.grid, self._nb
+        return dict(origin=(nb, nb, 0), domain=(g.nx - 2 * nb, g.ny - 2 * nb, g.nz))
+
+    def array_call(self, state, out_tendencies, out_diagnostics=None, overwrite_tendencies=None):
+        g, ow = self.grid, overwrite_tendencies or {}
+        nu, nv = self.names
+        self._stencil(in_u=state[nu], in_v=state[nv], out_u_tnd=out_tendencies[nu],
+                      out_v_tnd=out_tendencies[nv], dx=g.dx, dy=g.dy, cs=self._cs,
+                      ow_out_u_tnd=ow.get(nu, True), ow_out_v_tnd=ow.get(nv, True), **self._box())
+
+
+class IsentropicSmagorinsky(Smagorinsky2d):
+    """Mirror of ``tasmania.IsentropicSmagorinsky``
+    (src/tasmania/isentropic/physics/turbulence.py:L38-L125): conservative form, tendencies of
+    the momenta."""
+
+    class_stencils = {"smagorinsky": "smagorinsky_isentropic"}
+
+    def array_call(self, state, out_tendencies, out_diagnostics=None, overwrite_tendencies=None):
+        g, ow = self.grid, overwrite_tendencies or {}
+        self._stencil(in_s=state[S], in_su=state[SU], in_sv=state[SV], out_su_tnd=out_tendencies[SU],
+                      out_sv_tnd=out_tendencies[SV], dx=g.dx, dy=g.dy, cs=self._cs,
+                      ow_out_su_tnd=ow.get(SU, True), ow_out_sv_tnd=ow.get(SV, True), **self._box())

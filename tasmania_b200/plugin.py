@@ -142,6 +142,9 @@ def _class_scoped_stencils():
          st.vertical_advection_b200),
         ("tasmania.isentropic.physics.coriolis", "IsentropicConservativeCoriolis", "coriolis",
          st.coriolis_b200),
+        ("tasmania.physics.turbulence", "Smagorinsky2d", "smagorinsky", st.smagorinsky_b200),
+        ("tasmania.isentropic.physics.turbulence", "IsentropicSmagorinsky", "smagorinsky",
+         st.smagorinsky_isentropic_b200),
     ]
     out += [(m, c, s, getattr(st, d)) for (m, c, s, d) in st.KESSLER_CLASS_STENCILS]
     return out
@@ -167,6 +170,8 @@ def _class_scoped_subroutines():
     for mod, cls, name in (("first_order", "FirstOrderUpwind", "first_order_upwind"),
                            ("second_order", "SecondOrderUpwind", "second_order_upwind")):
         out.append((f"{sf}.{mod}", cls, "flux", _descriptor(st.SEDIMENTATION_FLUX[name], "flux")))
+    out.append(("tasmania.physics.turbulence", "Smagorinsky2d", "smagorinsky_core",
+                _descriptor("smagorinsky_core", "smagorinsky_core")))
     return out
 
 

@@ -449,6 +449,25 @@ def accumulated_precipitation_b200(externals, *, in_rho, in_qr, in_vt, in_accpre
           _i3(domain), _stream())
 
 
+# ------------------------------------------------------------------ Smagorinsky (8f-3)
+@stencil_definition("smagorinsky")
+def smagorinsky_b200(externals, *, in_u, in_v, out_u_tnd, out_v_tnd, dx, dy, cs, ow_out_u_tnd,
+                     ow_out_v_tnd, origin, domain):
+    """Smagorinsky2d's stencil (physics/turbulence.py:L165-L187)."""
+    _call("tb200_smagorinsky", None, _f(in_u), _f(in_v), _f(out_u_tnd), _f(out_v_tnd), float(dx),
+          float(dy), float(cs), int(bool(ow_out_u_tnd)), int(bool(ow_out_v_tnd)), _i3(origin),
+          _i3(domain), _stream())
+
+
+@stencil_definition("smagorinsky_isentropic")
+def smagorinsky_isentropic_b200(externals, *, in_s, in_su, in_sv, out_su_tnd, out_sv_tnd, dx, dy, cs,
+                                ow_out_su_tnd, ow_out_sv_tnd, origin, domain):
+    """IsentropicSmagorinsky's stencil (isentropic/physics/turbulence.py:L99-L125)."""
+    _call("tb200_smagorinsky", _f(in_s), _f(in_su), _f(in_sv), _f(out_su_tnd), _f(out_sv_tnd),
+          float(dx), float(dy), float(cs), int(bool(ow_out_su_tnd)), int(bool(ow_out_sv_tnd)),
+          _i3(origin), _i3(domain), _stream())
+
+
 # ------------------------------------------------------------------ Coriolis (8f-3)
 @stencil_definition("coriolis")
 def coriolis_b200(externals, *, in_su, in_sv, tnd_su, tnd_sv, f, ow_tnd_su, ow_tnd_sv, origin, domain):
@@ -508,3 +527,4 @@ for _name, _scheme in ADVECTION.items():
 for _name, _scheme in SEDIMENTATION_FLUX.items():
     subroutine_definition(f"flux:{_name}")(_scheme)
 subroutine_definition("set_output")("set_output")
+subroutine_definition("smagorinsky_core")("smagorinsky_core")  # fused into tb200_smagorinsky

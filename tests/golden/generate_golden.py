@@ -402,7 +402,7 @@ def gen_kessler():
 
     save("kessler", dims=np.array([nx, ny, nz]), **out)
 
-# ============================================================================ vertical advection
+# ============================================================================ isentropic physics (8f)
 VFLUX_CLASSES = {"upwind": "Upwind", "centered": "Centered", "third_order_upwind": "ThirdOrderUpwind",
                  "fifth_order_upwind": "FifthOrderUpwind"}
 
@@ -470,7 +470,29 @@ def gen_vertical_advection():
             origin=(2, 2, 0), domain=(nx - 4, ny - 4, nz))
         out[f"coriolis_o{int(owu)}{int(owv)}_su"] = tu
         out[f"coriolis_o{int(owu)}{int(owv)}_sv"] = tv
-    save("vertical_advection", dims=np.array([nx, ny, nz]), dz=np.array([dz]), f=np.array([f]), **out)
+    # ---- Smagorinsky: Smagorinsky2d / IsentropicSmagorinsky _stencil_numpy with
+    # the class's own "core" subroutine (physics/turbulence.py:L165-L229,
+    # isentropic/physics/turbulence.py:L99-L125), interior box of nb = 2 and nb = 3
+    tu2 = refload.load("tasmania.physics.turbulence")
+    tui = refload.load("tasmania.isentropic.physics.turbulence")
+    ext = {"set_output": gen.set_output_numpy, "core": tu2.Smagorinsky2d._core_numpy}
+    st2 = refload.numpy_stencil(tu2.Smagorinsky2d._stencil_numpy, ext)
+    sti = refload.numpy_stencil(tui.IsentropicSmagorinsky._stencil_numpy, ext)
+    vel = {"u": rng.uniform(-50, 50, size=shape), "v": rng.uniform(-50, 50, size=shape)}
+    out.update({"in_u": vel["u"], "in_v": vel["v"]})
+    sdx, sdy, cs = 1100.0, 950.0, 0.18
+    for nb, ow in ((2, True), (3, False)):
+        box = dict(origin=(nb, nb, 0), domain=(nx - 2 * nb, ny - 2 * nb, nz))
+        a, b = prev["su"].copy(), prev["sv"].copy()
+        st2(in_u=vel["u"], in_v=vel["v"], out_u_tnd=a, out_v_tnd=b, dx=sdx, dy=sdy, cs=cs,
+            ow_out_u_tnd=ow, ow_out_v_tnd=not ow, **box)
+        out[f"smag2d_nb{nb}_u"], out[f"smag2d_nb{nb}_v"] = a, b
+        a, b = prev["su"].copy(), prev["sv"].copy()
+        sti(in_s=ins["s"], in_su=ins["su"], in_sv=ins["sv"], out_su_tnd=a, out_sv_tnd=b, dx=sdx, dy=sdy,
+            cs=cs, ow_out_su_tnd=ow, ow_out_sv_tnd=not ow, **box)
+        out[f"smagisen_nb{nb}_su"], out[f"smagisen_nb{nb}_sv"] = a, b
+    save("isentropic_physics", dims=np.array([nx, ny, nz]), dz=np.array([dz]), f=np.array([f]),
+         smag=np.array([sdx, sdy, cs]), **out)
 
 
 # ============================================================================ isentropic
@@ -630,7 +652,7 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
 CASES = {
     "stencils": gen_stencils,
     "kessler": gen_kessler,
-    "vertical_advection": gen_vertical_advection,
+    "isentropic_physics": gen_vertical_advection,
     "isen_dry_rk3_5th": lambda: gen_isentropic_dry(
         "isen_dry_rk3_5th", 25, 21, 8, "rk3ws_si", "fifth_order_upwind", 3, 6, 6, 5.0),
     "isen_dry_rk3_3rd": lambda: gen_isentropic_dry(

@@ -1,7 +1,7 @@
 # -*- coding: utf-8 -*-
 """SURVEY.md 8f-1 on the GPU: ``tb200_vertical_advection`` through the compiled b200 stencil and
 the host mirror of ``IsentropicVerticalAdvection`` against the reference's own numpy outputs
-(tests/golden/vertical_advection.npz) and, on a larger seeded case, against the oracle.  No
+(tests/golden/isentropic_physics.npz) and, on a larger seeded case, against the oracle.  No
 transcendental call in this stencil: every comparison is bit for bit."""
 import numpy as np
 import pytest
@@ -23,7 +23,7 @@ def test_stencil_vs_reference_fixture_bitwise():
     import tasmania_b200 as tb
     from tasmania_b200.stencils import FLUX
 
-    fx = hp.load("vertical_advection")
+    fx = hp.load("isentropic_physics")
     nx, ny, nz = (int(v) for v in fx["dims"])
     dz = float(fx["dz"][0])
     dev = {k: tb.as_storage(fx["in_" + k]) for k in ("w", "s", "su", "sv", "qv", "qc", "qr")}
@@ -51,7 +51,7 @@ def test_host_mirror_vs_oracle_bitwise(scheme, moist, stg):
     """The mirror of IsentropicVerticalAdvection.array_call on a 67 x 45 x 60 state (config 3's
     number of levels) with a sub-box origin exercised through the oracle signature."""
     import tasmania_b200 as tb
-    from oracle import vertical_advection as ova
+    from oracle import isentropic_physics as ova
     from tasmania_b200 import isentropic_physics as va
     from tasmania_b200.grid import Grid
 
@@ -115,7 +115,7 @@ def test_coriolis_vs_reference_fixture_bitwise():
     from tasmania_b200 import isentropic_physics as va
     from tasmania_b200.grid import Grid
 
-    fx = hp.load("vertical_advection")
+    fx = hp.load("isentropic_physics")
     nx, ny, nz = (int(v) for v in fx["dims"])
     grid = Grid((-10.0, 10.0), nx, (-7.0, 7.0), ny, (400.0, 280.0), nz, units_to_m=1e3)
     comp = va.IsentropicConservativeCoriolis(grid, 2, coriolis_parameter=float(fx["f"][0]))
@@ -125,3 +125,52 @@ def test_coriolis_vs_reference_fixture_bitwise():
         comp.array_call(state, out, {}, {va.SU: owu, va.SV: owv})
         np.testing.assert_array_equal(tb.to_numpy(out[va.SU]), fx[f"coriolis_o{int(owu)}{int(owv)}_su"])
         np.testing.assert_array_equal(tb.to_numpy(out[va.SV]), fx[f"coriolis_o{int(owu)}{int(owv)}_sv"])
+
+
+def test_smagorinsky_vs_reference_fixture_bitwise():
+    """SURVEY.md 8f-3 through the compiled b200 stencils (generic and isentropic form)."""
+    import tasmania_b200 as tb
+
+    fx = hp.load("isentropic_physics")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    dx, dy, cs = (float(v) for v in fx["smag"])
+    st2 = tb.compile_stencil("smagorinsky")
+    sti = tb.compile_stencil("smagorinsky_isentropic")
+    d = {k: tb.as_storage(fx["in_" + k]) for k in ("u", "v", "s", "su", "sv")}
+    for nb, ow in ((2, True), (3, False)):
+        box = dict(origin=(nb, nb, 0), domain=(nx - 2 * nb, ny - 2 * nb, nz))
+        a, b = tb.as_storage(fx["prev_su"]), tb.as_storage(fx["prev_sv"])
+        st2(in_u=d["u"], in_v=d["v"], out_u_tnd=a, out_v_tnd=b, dx=dx, dy=dy, cs=cs, ow_out_u_tnd=ow,
+            ow_out_v_tnd=not ow, **box)
+        np.testing.assert_array_equal(tb.to_numpy(a), fx[f"smag2d_nb{nb}_u"])
+        np.testing.assert_array_equal(tb.to_numpy(b), fx[f"smag2d_nb{nb}_v"])
+        a, b = tb.as_storage(fx["prev_su"]), tb.as_storage(fx["prev_sv"])
+        sti(in_s=d["s"], in_su=d["su"], in_sv=d["sv"], out_su_tnd=a, out_sv_tnd=b, dx=dx, dy=dy, cs=cs,
+            ow_out_su_tnd=ow, ow_out_sv_tnd=not ow, **box)
+        np.testing.assert_array_equal(tb.to_numpy(a), fx[f"smagisen_nb{nb}_su"])
+        np.testing.assert_array_equal(tb.to_numpy(b), fx[f"smagisen_nb{nb}_sv"])
+
+
+@pytest.mark.parametrize("nx,ny,nz,nb", [(131, 77, 9, 2), (64, 40, 3, 3)])
+def test_smagorinsky_mirror_vs_oracle_bitwise(nx, ny, nz, nb):
+    """Tile seams (several 32 x 8 blocks), ragged edges, several levels: host mirror of
+    IsentropicSmagorinsky against the oracle."""
+    import tasmania_b200 as tb
+    from oracle import isentropic_physics as ova
+    from tasmania_b200 import isentropic_physics as va
+    from tasmania_b200.grid import Grid
+
+    rng = np.random.default_rng(nx)
+    shape = (nx + 1, ny + 1, nz + 1)
+    grid = Grid((-100.0, 100.0), nx, (-70.0, 70.0), ny, (400.0, 280.0), nz, units_to_m=1e3)
+    s, su, sv = rng.uniform(10, 1000, shape), rng.uniform(-5e4, 5e4, shape), rng.uniform(-5e4, 5e4, shape)
+    prev = {va.SU: rng.uniform(-1, 1, shape), va.SV: rng.uniform(-1, 1, shape)}
+    comp = va.IsentropicSmagorinsky(grid, nb, smagorinsky_constant=0.21)
+    out = {k: tb.as_storage(v) for k, v in prev.items()}
+    comp.array_call({va.S: tb.as_storage(s), va.SU: tb.as_storage(su), va.SV: tb.as_storage(sv)}, out, {},
+                    {va.SU: False, va.SV: True})
+    ra, rb = prev[va.SU].copy(), prev[va.SV].copy()
+    ova.smagorinsky(su, sv, ra, rb, in_s=s, dx=grid.dx, dy=grid.dy, cs=0.21, ow_out_u_tnd=False,
+                    ow_out_v_tnd=True, origin=(nb, nb, 0), domain=(nx - 2 * nb, ny - 2 * nb, nz))
+    np.testing.assert_array_equal(tb.to_numpy(out[va.SU]), ra)
+    np.testing.assert_array_equal(tb.to_numpy(out[va.SV]), rb)

@@ -230,8 +230,8 @@ def test_kessler_family_bitwise():
 
 
 def _vertical_advection_cases(fx):
-    """(key prefix, scheme, staggered, moist, overwrite) of tests/golden/vertical_advection.npz"""
-    from oracle import vertical_advection as va
+    """(key prefix, scheme, staggered, moist, overwrite) of tests/golden/isentropic_physics.npz"""
+    from oracle import isentropic_physics as va
 
     for scheme in va.EXTENT:
         for z in (0, 1):
@@ -244,9 +244,9 @@ def test_vertical_advection_bitwise():
     """the oracle's vertical advection against the reference's own numpy stencil
     (vertical_advection.py:L271-L386) for the four flux schemes, velocity on main / interface
     levels, dry / moist, overwrite on / off -- bit for bit, on the WHOLE output storages."""
-    from oracle import vertical_advection as va
+    from oracle import isentropic_physics as va
 
-    fx = hp.load("vertical_advection")
+    fx = hp.load("isentropic_physics")
     nx, ny, nz = (int(v) for v in fx["dims"])
     dz = float(fx["dz"][0])
     n = 0
@@ -270,9 +270,9 @@ def test_vertical_advection_bitwise():
 
 def test_coriolis_bitwise():
     """coriolis.py:L166-L186 on the interior box, written and accumulated."""
-    from oracle import vertical_advection as va
+    from oracle import isentropic_physics as va
 
-    fx = hp.load("vertical_advection")
+    fx = hp.load("isentropic_physics")
     nx, ny, nz = (int(v) for v in fx["dims"])
     for owu, owv in ((True, True), (False, True), (False, False)):
         tu, tv = fx["prev_su"].copy(), fx["prev_sv"].copy()
@@ -280,3 +280,25 @@ def test_coriolis_bitwise():
                     origin=(2, 2, 0), domain=(nx - 4, ny - 4, nz))
         np.testing.assert_array_equal(tu, fx[f"coriolis_o{int(owu)}{int(owv)}_su"])
         np.testing.assert_array_equal(tv, fx[f"coriolis_o{int(owu)}{int(owv)}_sv"])
+
+
+def test_smagorinsky_bitwise():
+    """Smagorinsky2d and IsentropicSmagorinsky against the reference's own numpy
+    stencils (physics/turbulence.py:L165-L229, isentropic/physics/turbulence.py:L99-L125)."""
+    from oracle import isentropic_physics as va
+
+    fx = hp.load("isentropic_physics")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    dx, dy, cs = (float(v) for v in fx["smag"])
+    for nb, ow in ((2, True), (3, False)):
+        box = dict(origin=(nb, nb, 0), domain=(nx - 2 * nb, ny - 2 * nb, nz))
+        a, b = fx["prev_su"].copy(), fx["prev_sv"].copy()
+        va.smagorinsky(fx["in_u"], fx["in_v"], a, b, dx=dx, dy=dy, cs=cs, ow_out_u_tnd=ow,
+                       ow_out_v_tnd=not ow, **box)
+        np.testing.assert_array_equal(a, fx[f"smag2d_nb{nb}_u"])
+        np.testing.assert_array_equal(b, fx[f"smag2d_nb{nb}_v"])
+        a, b = fx["prev_su"].copy(), fx["prev_sv"].copy()
+        va.smagorinsky(fx["in_su"], fx["in_sv"], a, b, in_s=fx["in_s"], dx=dx, dy=dy, cs=cs,
+                       ow_out_u_tnd=ow, ow_out_v_tnd=not ow, **box)
+        np.testing.assert_array_equal(a, fx[f"smagisen_nb{nb}_su"])
+        np.testing.assert_array_equal(b, fx[f"smagisen_nb{nb}_sv"])
