@@ -1,6 +1,7 @@
 # -*- coding: utf-8 -*-
 """Oracle (test infrastructure): the isentropic physics components of SURVEY.md 8f -- vertical
-advection (row 1), Coriolis forcing and Smagorinsky turbulence (row 3).
+advection (row 1), Coriolis forcing and Smagorinsky turbulence (row 3), implicit vertical
+advection with the Thomas algorithm (row 4).
 
 Follows src/tasmania/isentropic/physics/vertical_advection.py:L271-L386 (numpy definition of
 ``IsentropicVerticalAdvection._stencil``) and the flux formulas of
@@ -117,3 +118,44 @@ def smagorinsky(in_u, in_v, out_u_tnd, out_v_tnd, *, dx, dy, cs, ow_out_u_tnd, o
         tu, tv = in_s[ib:ie, jb:je, k] * tu, in_s[ib:ie, jb:je, k] * tv
     _set_output(out_u_tnd[ib:ie, jb:je, k], tu, ow_out_u_tnd)
     _set_output(out_v_tnd[ib:ie, jb:je, k], tv, ow_out_v_tnd)
+
+
+def _setup_tridiagonal(gamma, w, phi):
+    """cla.py:L81-L108 on columns (third axis = the nk levels of the box); b is one."""
+    a, c, d = np.zeros_like(phi), np.zeros_like(phi), phi.copy()
+    a[:, :, 1:-1] = gamma * w[:, :, :-2]
+    c[:, :, 1:-1] = -gamma * w[:, :, 2:]
+    d[:, :, 1:-1] = phi[:, :, 1:-1] - gamma * (w[:, :, :-2] * phi[:, :, :-2] - w[:, :, 2:] * phi[:, :, 2:])
+    return a, c, d
+
+
+def _thomas(a, c, d):
+    """cla.py:L42-L78 with b = 1: forward elimination, backward substitution, level by level."""
+    nk = d.shape[2]
+    beta, delta = np.ones_like(d), d.copy()
+    for k in range(1, nk):
+        w = np.where(beta[:, :, k - 1] != 0.0, a[:, :, k] / beta[:, :, k - 1], a[:, :, k])
+        beta[:, :, k] -= w * c[:, :, k - 1]
+        delta[:, :, k] -= w * delta[:, :, k - 1]
+    out = np.empty_like(d)
+    out[:, :, -1] = np.where(beta[:, :, -1] != 0.0, delta[:, :, -1] / beta[:, :, -1], delta[:, :, -1] / 1.0)
+    for k in range(nk - 2, -1, -1):
+        r = delta[:, :, k] - c[:, :, k] * out[:, :, k + 1]
+        out[:, :, k] = np.where(beta[:, :, k] != 0.0, r / beta[:, :, k], r / 1.0)
+    return out
+
+
+def implicit_vertical_advection(staggered, in_w, in_s, in_su, in_sv, out_s, out_su, out_sv, *, gamma,
+                                origin, domain, in_qv=None, in_qc=None, in_qr=None, out_qv=None,
+                                out_qc=None, out_qr=None):
+    """implicit_vertical_advection.py:L221-L336."""
+    box = tuple(slice(o, o + d) for o, d in zip(origin, domain))
+    i, j, _ = box
+    kb, ke = origin[2], origin[2] + domain[2]
+    w = 0.5 * (in_w[i, j, kb:ke] + in_w[i, j, kb + 1:ke + 1]) if staggered else in_w[box]
+    with np.errstate(all="ignore"):
+        for src, out in ((in_s, out_s), (in_su, out_su), (in_sv, out_sv)):
+            out[box] = _thomas(*_setup_tridiagonal(gamma, w, src[box]))
+        if in_qv is not None:
+            for q, out in ((in_qv, out_qv), (in_qc, out_qc), (in_qr, out_qr)):
+                out[box] = _thomas(*_setup_tridiagonal(gamma, w, in_s[box] * q[box])) / out_s[box]

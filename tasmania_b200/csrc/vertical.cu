@@ -133,6 +133,123 @@ int run_vadv(const VAdvArgs &a, cudaStream_t st) {
 
 }  // namespace
 
+// ---------------------------------------------------------------- implicit vertical advection
+// src/tasmania/isentropic/physics/implicit_vertical_advection.py:L221-L336 with the tridiagonal
+// set-up and the Thomas algorithm of
+// src/tasmania/framework/subclasses/subroutine_definitions/cla.py:L42-L78, L81-L108.
+// Crank-Nicolson in the vertical: for every advected field phi
+//   a[k] = gamma w[k-1],  b = 1,  c[k] = -gamma w[k+1],
+//   d[k] = phi[k] - gamma (w[k-1] phi[k-1] - w[k+1] phi[k+1])        (first / last level: identity)
+// solved per column.  The matrix depends on w only, so the forward elimination factors
+// (beta[k], the multipliers) are computed once per column and shared by the three (six) fields;
+// the reference recomputes them per field with the same operations, hence the same bits.  One
+// thread per column, i along the warp; beta, c and the multipliers sit in thread-local arrays,
+// the eliminated right-hand side in the output storage itself.
+struct ImplArgs {
+  View w, in[6], out[6];  // s, su, sv, qv, qc, qr
+  int nfields;            // 3 dry, 6 moist
+  bool staggered;
+  double gamma;
+  int i0, j0, k0, di, dj, dk;
+};
+
+template <int MAXK>
+__global__ void __launch_bounds__(128) implicit_vadv_kernel(const ImplArgs a) {
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jj = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ii >= a.di || jj >= a.dj) return;
+  const int i = ii + a.i0, j = jj + a.j0, k0 = a.k0, nk = a.dk;
+  const double gamma = a.gamma, mgamma = -a.gamma;
+  double beta[MAXK], cc[MAXK], mult[MAXK], wm[MAXK];
+  // vertical velocity on the main levels, implicit_vertical_advection.py:L246-L252
+  for (int l = 0; l < nk; ++l)
+    wm[l] = a.staggered ? 0.5 * (a.w.ld(i, j, k0 + l) + a.w.ld(i, j, k0 + l + 1)) : a.w.ld(i, j, k0 + l);
+  // matrix and its elimination (cla.py:L98-L102, L60-L68): a[l] = gamma w[l-1], c[l] = -gamma w[l+1]
+  // on the inner levels, zero on the first and the last one
+  beta[0] = 1.0;
+  cc[0] = 0.0;
+  mult[0] = 0.0;
+  for (int l = 1; l < nk; ++l) {
+    const bool inner = l < nk - 1;
+    const double al = inner ? gamma * wm[l - 1] : 0.0;
+    cc[l] = inner ? mgamma * wm[l + 1] : 0.0;
+    const double m = beta[l - 1] != 0.0 ? al / beta[l - 1] : al;
+    mult[l] = m;
+    beta[l] = 1.0 - m * cc[l - 1];
+  }
+  for (int f = 0; f < a.nfields; ++f) {
+    const bool water = f >= 3;  // advected as s q, returned as (s q)_new / s_new (L255-L262, L331-L336)
+    auto phi = [&](int l) {
+      const double v = a.in[f].ld(i, j, k0 + l);
+      return water ? a.in[0].ld(i, j, k0 + l) * v : v;
+    };
+    View o = a.out[f];
+    // right-hand side (cla.py:L104-L108) and forward sweep (L64-L68), delta parked in the output
+    double delta = phi(0);
+    o(i, j, k0) = delta;
+    for (int l = 1; l < nk; ++l) {
+      double d;
+      if (l < nk - 1)
+        d = phi(l) - gamma * (wm[l - 1] * phi(l - 1) - wm[l + 1] * phi(l + 1));
+      else
+        d = phi(l);
+      delta = d - mult[l] * delta;
+      o(i, j, k0 + l) = delta;
+    }
+    // backward substitution (cla.py:L70-L78); b == 1 where beta == 0
+    double x = beta[nk - 1] != 0.0 ? delta / beta[nk - 1] : delta / 1.0;
+    o(i, j, k0 + nk - 1) = water ? x / a.out[0](i, j, k0 + nk - 1) : x;
+    for (int l = nk - 2; l >= 0; --l) {
+      const double r = o(i, j, k0 + l) - cc[l] * x;
+      x = beta[l] != 0.0 ? r / beta[l] : r / 1.0;
+      o(i, j, k0 + l) = water ? x / a.out[0](i, j, k0 + l) : x;
+    }
+  }
+}
+
+extern "C" int tb200_implicit_vertical_advection(
+    int staggered_w, const tb200_field *in_w, const tb200_field *in_s, const tb200_field *in_su,
+    const tb200_field *in_sv, tb200_field *out_s, tb200_field *out_su, tb200_field *out_sv,
+    const tb200_field *in_qv, const tb200_field *in_qc, const tb200_field *in_qr,
+    tb200_field *out_qv, tb200_field *out_qc, tb200_field *out_qr, double gamma,
+    const int32_t origin[3], const int32_t domain[3], void *stream) {
+  ImplArgs a{};
+  a.w = view(in_w);
+  const tb200_field *ins[6] = {in_s, in_su, in_sv, in_qv, in_qc, in_qr};
+  tb200_field *outs[6] = {out_s, out_su, out_sv, out_qv, out_qc, out_qr};
+  for (int f = 0; f < 6; ++f) {
+    a.in[f] = view(ins[f]);
+    a.out[f] = view(outs[f]);
+  }
+  bool moist = false;
+  for (int f = 3; f < 6; ++f) moist = moist || a.in[f].ok() || a.out[f].ok();
+  a.nfields = moist ? 6 : 3;
+  a.staggered = staggered_w != 0;
+  a.gamma = gamma;
+  a.i0 = origin[0]; a.j0 = origin[1]; a.k0 = origin[2];
+  a.di = domain[0]; a.dj = domain[1]; a.dk = domain[2];
+  TB200_REQUIRE(a.dk >= 2 && a.dk <= 256, "implicit_vertical_advection: 2 <= levels <= 256, got %d", a.dk);
+  TB200_REQUIRE(a.staggered ? box_inside(a.w, origin, domain, 0, 0, 0, 0, 0, 1)
+                            : box_inside(a.w, origin, domain),
+                "implicit_vertical_advection: box outside the vertical velocity storage");
+  for (int f = 0; f < a.nfields; ++f) {
+    TB200_REQUIRE(box_inside(a.in[f], origin, domain) && box_inside(a.out[f], origin, domain),
+                  "implicit_vertical_advection: box outside a field storage (moist needs all six)");
+    for (int g = 0; g < a.nfields; ++g)
+      TB200_REQUIRE(a.out[f].p != a.in[g].p && (f == g || a.out[f].p != a.out[g].p) && a.out[f].p != a.w.p,
+                    "implicit_vertical_advection: outputs must not alias inputs or each other");
+  }
+  if (a.di <= 0 || a.dj <= 0) return TB200_OK;
+  dim3 block(32, 4, 1);
+  dim3 grid((a.di + 31) / 32, (a.dj + 3) / 4, 1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a.dk <= 64)
+    implicit_vadv_kernel<64><<<grid, block, 0, st>>>(a);
+  else
+    implicit_vadv_kernel<256><<<grid, block, 0, st>>>(a);
+  return check_launch("implicit_vertical_advection");
+}
+
 extern "C" int tb200_vertical_advection(
     int flux_scheme, int staggered_w, const tb200_field *in_w, const tb200_field *in_s,
     const tb200_field *in_su, const tb200_field *in_sv, tb200_field *out_s, tb200_field *out_su,

@@ -7,7 +7,10 @@ row 3) and the Smagorinsky turbulence components ``tasmania.Smagorinsky2d`` /
 ``tasmania.IsentropicSmagorinsky`` (src/tasmania/physics/turbulence.py:L42-L229,
 src/tasmania/isentropic/physics/turbulence.py:L38-L125, row 3): same constructor arguments, same externals, same ``array_call`` keyword wiring; the
 arithmetic runs in ``tb200_vertical_advection`` (csrc/vertical.cu) and ``tb200_coriolis``
-(csrc/elementwise.cu) and ``tb200_smagorinsky`` (csrc/turbulence.cu)."""
+(csrc/elementwise.cu), ``tb200_smagorinsky`` (csrc/turbulence.cu) and, for
+``tasmania.IsentropicImplicitVerticalAdvectionDiagnostic``
+(src/tasmania/isentropic/physics/implicit_vertical_advection.py:L44-L336, row 4),
+``tb200_implicit_vertical_advection`` (csrc/vertical.cu)."""
 from __future__ import annotations
 
 from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
@@ -133,3 +136,39 @@ class IsentropicSmagorinsky(Smagorinsky2d):
         self._stencil(in_s=state[S], in_su=state[SU], in_sv=state[SV], out_su_tnd=out_tendencies[SU],
                       out_sv_tnd=out_tendencies[SV], dx=g.dx, dy=g.dy, cs=self._cs,
                       ow_out_su_tnd=ow.get(SU, True), ow_out_sv_tnd=ow.get(SV, True), **self._box())
+
+
+class IsentropicImplicitVerticalAdvectionDiagnostic(StencilFactory):
+    """Mirror of ``tasmania.IsentropicImplicitVerticalAdvectionDiagnostic``
+    (src/tasmania/isentropic/physics/implicit_vertical_advection.py:L44-L219): Crank-Nicolson
+    vertical advection, one tridiagonal solve per column and field."""
+
+    def __init__(self, grid, moist=False,
+                 tendency_of_air_potential_temperature_on_interface_levels=False, *, backend="b200",
+                 backend_options=None, storage_options=None):
+        super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
+        self.grid, self._moist = grid, moist
+        self._stgz = tendency_of_air_potential_temperature_on_interface_levels
+        self.backend_options.externals = {  # L112-L117
+            "moist": moist,
+            "staggering": self._stgz,
+            "setup": self.get_subroutine_definition("setup_thomas"),
+            "setup_bc": self.get_subroutine_definition("setup_thomas_bc"),
+        }
+        self._stencil = self.compile_stencil("implicit_vertical_advection")
+
+    def array_call(self, state, timestep, out_tendencies, out_diagnostics, overwrite_tendencies=None):
+        """implicit_vertical_advection.py:L172-L219"""
+        g = self.grid
+        args = {
+            "gamma": timestep.total_seconds() / (4.0 * g.dz),
+            "in_w": state[W_HL] if self._stgz else state[W_ML],
+            "in_s": state[S], "out_s": out_diagnostics[S],
+            "in_su": state[SU], "out_su": out_diagnostics[SU],
+            "in_sv": state[SV], "out_sv": out_diagnostics[SV],
+        }
+        if self._moist:
+            for key, name in (("qv", MFWV), ("qc", MFCW), ("qr", MFPW)):
+                args["in_" + key] = state[name]
+                args["out_" + key] = out_diagnostics[name]
+        self._stencil(**args, origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))

@@ -142,6 +142,9 @@ def _class_scoped_stencils():
          st.vertical_advection_b200),
         ("tasmania.isentropic.physics.coriolis", "IsentropicConservativeCoriolis", "coriolis",
          st.coriolis_b200),
+        ("tasmania.isentropic.physics.implicit_vertical_advection",
+         "IsentropicImplicitVerticalAdvectionDiagnostic", "implicit_vertical_advection",
+         st.implicit_vertical_advection_b200),
         ("tasmania.physics.turbulence", "Smagorinsky2d", "smagorinsky", st.smagorinsky_b200),
         ("tasmania.isentropic.physics.turbulence", "IsentropicSmagorinsky", "smagorinsky",
          st.smagorinsky_isentropic_b200),
@@ -220,8 +223,8 @@ def install(strict: bool = False) -> dict:
     for name in GLOBAL_STENCILS:
         ts.StencilDefinition.register(fw.get_stencil_definition(name), backend=BACKEND, stencil=name)
         report["global"].append(name)
-    ts.SubroutineDefinition.register(_descriptor("set_output", "set_output"), backend=BACKEND,
-                                     stencil="set_output")
+    for name in ("set_output", "thomas", "setup_thomas", "setup_thomas_bc"):
+        ts.SubroutineDefinition.register(_descriptor(name, name), backend=BACKEND, stencil=name)
 
     # 4. class-scoped definitions: tagged static methods on the reference classes
     def attach(modname, clsname, stencil, fn, tagger):

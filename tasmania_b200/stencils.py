@@ -504,6 +504,21 @@ def vertical_advection_b200(
           q[0], q[1], q[2], q[3], q[4], q[5], float(dz), flags, _i3(origin), _i3(domain), _stream())
 
 
+@stencil_definition("implicit_vertical_advection")
+def implicit_vertical_advection_b200(
+    externals, *, in_w, in_s, in_su, in_sv, out_s, out_su, out_sv, in_qv=None, in_qc=None,
+    in_qr=None, out_qv=None, out_qc=None, out_qr=None, gamma, origin, domain):
+    """IsentropicImplicitVerticalAdvectionDiagnostic's stencil
+    (implicit_vertical_advection.py:L221-L336); externals (L112-L117): moist, staggering."""
+    moist = bool(externals.get("moist", False))
+    if moist and any(x is None for x in (in_qv, in_qc, in_qr, out_qv, out_qc, out_qr)):
+        raise lib.B200Error("implicit_vertical_advection: moist=True needs in_q* and out_q*")
+    q = [(_f(x) if moist else None) for x in (in_qv, in_qc, in_qr, out_qv, out_qc, out_qr)]
+    _call("tb200_implicit_vertical_advection", int(bool(externals.get("staggering", False))), _f(in_w),
+          _f(in_s), _f(in_su), _f(in_sv), _f(out_s), _f(out_su), _f(out_sv), q[0], q[1], q[2], q[3],
+          q[4], q[5], float(gamma), _i3(origin), _i3(domain), _stream())
+
+
 _KE = "tasmania.physics.microphysics.kessler"
 KESSLER_CLASS_STENCILS += [
     (_KE, "KesslerMicrophysics", "kessler", "kessler_b200"),
@@ -528,3 +543,5 @@ for _name, _scheme in SEDIMENTATION_FLUX.items():
     subroutine_definition(f"flux:{_name}")(_scheme)
 subroutine_definition("set_output")("set_output")
 subroutine_definition("smagorinsky_core")("smagorinsky_core")  # fused into tb200_smagorinsky
+for _name in ("thomas", "setup_thomas", "setup_thomas_bc"):  # fused into tb200_implicit_vertical_advection
+    subroutine_definition(_name)(_name)

@@ -491,8 +491,34 @@ def gen_vertical_advection():
         sti(in_s=ins["s"], in_su=ins["su"], in_sv=ins["sv"], out_su_tnd=a, out_sv_tnd=b, dx=sdx, dy=sdy,
             cs=cs, ow_out_su_tnd=ow, ow_out_sv_tnd=not ow, **box)
         out[f"smagisen_nb{nb}_su"], out[f"smagisen_nb{nb}_sv"] = a, b
+    # ---- implicit vertical advection:
+    # IsentropicImplicitVerticalAdvectionDiagnostic._stencil_numpy
+    # (isentropic/physics/implicit_vertical_advection.py:L221-L336) with the reference's own
+    # setup_thomas / thomas subroutines (framework/subclasses/subroutine_definitions/cla.py)
+    iva = refload.load("tasmania.isentropic.physics.implicit_vertical_advection")
+    cla = refload.load("tasmania.framework.subclasses.subroutine_definitions.cla")
+    subs = {"setup_thomas": cla.setup_tridiagonal_system_numpy, "thomas": cla.thomas_numpy}
+    gamma = 7.5 / (4.0 * dz)
+    wbig = ins["w"] * 8.0  # |gamma w| up to 0.12: a diagonally dominant but non-trivial system
+    out["in_w_implicit"] = wbig
+    for stgz in (False, True):
+        for moist in (False, True):
+            ist = refload.numpy_stencil(iva.IsentropicImplicitVerticalAdvectionDiagnostic._stencil_numpy,
+                                        {"staggering": stgz, "moist": moist})
+            fake = types.SimpleNamespace(
+                zeros=lambda backend=None, *, shape, storage_options=None: np.zeros(shape),
+                ones=lambda backend=None, *, shape, storage_options=None: np.ones(shape),
+                get_subroutine_definition=lambda name: subs[name])
+            names = ("s", "su", "sv") + (("qv", "qc", "qr") if moist else ())
+            outs = {n: prev[n].copy() for n in names}
+            kw = {"in_w": wbig, "gamma": gamma, "origin": (0, 0, 0), "domain": (nx, ny, nz)}
+            for n in names:
+                kw["in_" + n], kw["out_" + n] = ins[n], outs[n]
+            ist(fake, **kw)
+            for n in names:
+                out[f"implicit_z{int(stgz)}_m{int(moist)}_{n}"] = outs[n]
     save("isentropic_physics", dims=np.array([nx, ny, nz]), dz=np.array([dz]), f=np.array([f]),
-         smag=np.array([sdx, sdy, cs]), **out)
+         smag=np.array([sdx, sdy, cs]), gamma=np.array([gamma]), **out)
 
 
 # ============================================================================ isentropic

@@ -174,3 +174,62 @@ def test_smagorinsky_mirror_vs_oracle_bitwise(nx, ny, nz, nb):
                     ow_out_v_tnd=True, origin=(nb, nb, 0), domain=(nx - 2 * nb, ny - 2 * nb, nz))
     np.testing.assert_array_equal(tb.to_numpy(out[va.SU]), ra)
     np.testing.assert_array_equal(tb.to_numpy(out[va.SV]), rb)
+
+
+def test_implicit_vertical_advection_vs_reference_fixture_bitwise():
+    """SURVEY.md 8f-4 through the compiled b200 stencil."""
+    import tasmania_b200 as tb
+
+    fx = hp.load("isentropic_physics")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    d = {k: tb.as_storage(fx["in_" + k]) for k in ("s", "su", "sv", "qv", "qc", "qr")}
+    w = tb.as_storage(fx["in_w_implicit"])
+    for z in (0, 1):
+        for m in (0, 1):
+            bo = tb.BackendOptions()
+            bo.externals = {"moist": bool(m), "staggering": bool(z)}
+            st = tb.compile_stencil("implicit_vertical_advection", backend_options=bo)
+            names = ("s", "su", "sv") + (("qv", "qc", "qr") if m else ())
+            outs = {n: tb.as_storage(fx["prev_" + n]) for n in names}
+            kw = {"in_w": w, "gamma": float(fx["gamma"][0]), "origin": (0, 0, 0), "domain": (nx, ny, nz)}
+            for n in names:
+                kw["in_" + n], kw["out_" + n] = d[n], outs[n]
+            st(**kw)
+            for n in names:
+                np.testing.assert_array_equal(tb.to_numpy(outs[n]), fx[f"implicit_z{z}_m{m}_{n}"],
+                                              err_msg=f"{z}{m}{n}")
+
+
+@pytest.mark.parametrize("nz", [60, 100])
+def test_implicit_vertical_advection_mirror_vs_oracle_bitwise(nz):
+    """Config 3's number of levels (register-sized arrays) and a taller column (the 256-level
+    instantiation) through the host mirror, moist, velocity on interface levels."""
+    from datetime import timedelta
+
+    import tasmania_b200 as tb
+    from oracle import isentropic_physics as ova
+    from tasmania_b200 import isentropic_physics as va
+    from tasmania_b200.grid import Grid
+
+    nx, ny = 45, 37
+    rng = np.random.default_rng(nz)
+    shape = (nx + 1, ny + 1, nz + 1)
+    grid = Grid((-10.0, 10.0), nx, (-7.0, 7.0), ny, (400.0, 280.0), nz, units_to_m=1e3)
+    state = {va.S: rng.uniform(10, 1000, shape), va.SU: rng.uniform(-5e4, 5e4, shape),
+             va.SV: rng.uniform(-5e4, 5e4, shape), va.W_HL: rng.uniform(-0.15, 0.15, shape),
+             va.MFWV: rng.uniform(0, 5, shape), va.MFCW: rng.uniform(0, 5, shape),
+             va.MFPW: rng.uniform(0, 5, shape)}
+    names = (va.S, va.SU, va.SV, va.MFWV, va.MFCW, va.MFPW)
+    comp = va.IsentropicImplicitVerticalAdvectionDiagnostic(
+        grid, moist=True, tendency_of_air_potential_temperature_on_interface_levels=True)
+    out = {k: tb.zeros(shape) for k in names}
+    dt = timedelta(seconds=12)
+    comp.array_call({k: tb.as_storage(v) for k, v in state.items()}, dt, {}, out)
+    ref = {k: np.zeros(shape) for k in names}
+    ova.implicit_vertical_advection(
+        True, state[va.W_HL], state[va.S], state[va.SU], state[va.SV], ref[va.S], ref[va.SU], ref[va.SV],
+        gamma=dt.total_seconds() / (4.0 * grid.dz), origin=(0, 0, 0), domain=(nx, ny, nz),
+        in_qv=state[va.MFWV], in_qc=state[va.MFCW], in_qr=state[va.MFPW], out_qv=ref[va.MFWV],
+        out_qc=ref[va.MFCW], out_qr=ref[va.MFPW])
+    for k in names:
+        np.testing.assert_array_equal(tb.to_numpy(out[k]), ref[k], err_msg=k)

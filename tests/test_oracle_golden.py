@@ -302,3 +302,25 @@ def test_smagorinsky_bitwise():
                        ow_out_u_tnd=ow, ow_out_v_tnd=not ow, **box)
         np.testing.assert_array_equal(a, fx[f"smagisen_nb{nb}_su"])
         np.testing.assert_array_equal(b, fx[f"smagisen_nb{nb}_sv"])
+
+
+def test_implicit_vertical_advection_bitwise():
+    """the Crank-Nicolson vertical advection (tridiagonal set-up + Thomas algorithm,
+    implicit_vertical_advection.py:L221-L336, cla.py:L42-L108) against the reference's own numpy
+    code: velocity on main / interface levels, dry / moist."""
+    from oracle import isentropic_physics as va
+
+    fx = hp.load("isentropic_physics")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    for z in (0, 1):
+        for m in (0, 1):
+            names = ("s", "su", "sv") + (("qv", "qc", "qr") if m else ())
+            outs = {n: fx["prev_" + n].copy() for n in names}
+            kw = dict(gamma=float(fx["gamma"][0]), origin=(0, 0, 0), domain=(nx, ny, nz))
+            if m:
+                for n in ("qv", "qc", "qr"):
+                    kw["in_" + n], kw["out_" + n] = fx["in_" + n], outs[n]
+            va.implicit_vertical_advection(bool(z), fx["in_w_implicit"], fx["in_s"], fx["in_su"],
+                                           fx["in_sv"], outs["s"], outs["su"], outs["sv"], **kw)
+            for n in names:
+                np.testing.assert_array_equal(outs[n], fx[f"implicit_z{z}_m{m}_{n}"], err_msg=f"{z}{m}{n}")
