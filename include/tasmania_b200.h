@@ -277,7 +277,9 @@ int tb200_vertical_advection(int flux_scheme, int staggered_w, const tb200_field
  * thomas of src/tasmania/framework/subclasses/subroutine_definitions/cla.py:L42-L108.
  * gamma = dt / (4 dz); staggered_w: in_w on interface levels, averaged onto the main levels.
  * in_q* / out_q* NULL = dry; the water species are advected as s q and returned as mass fractions.
- * 2 <= domain[2] <= 256. */
+ * dt_tendency = 0: the advected fields (IsentropicImplicitVerticalAdvectionDiagnostic, L221-L336);
+ * dt_tendency > 0: the tendencies (x_new - x) / dt_tendency into the same outputs
+ * (IsentropicImplicitVerticalAdvectionPrognostic, L793-L919).  2 <= domain[2] <= 256. */
 int tb200_implicit_vertical_advection(int staggered_w, const tb200_field *in_w,
                                       const tb200_field *in_s, const tb200_field *in_su,
                                       const tb200_field *in_sv, tb200_field *out_s,
@@ -285,8 +287,8 @@ int tb200_implicit_vertical_advection(int staggered_w, const tb200_field *in_w,
                                       const tb200_field *in_qv, const tb200_field *in_qc,
                                       const tb200_field *in_qr, tb200_field *out_qv,
                                       tb200_field *out_qc, tb200_field *out_qr, double gamma,
-                                      const int32_t origin[3], const int32_t domain[3],
-                                      void *stream);
+                                      double dt_tendency, const int32_t origin[3],
+                                      const int32_t domain[3], void *stream);
 
 /* ---- fused dry isentropic stage (the benchmark hot path) ---------------------------
  * One RK stage of IsentropicDynamicalCore.stage_array_call_dry

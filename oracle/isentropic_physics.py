@@ -159,3 +159,21 @@ def implicit_vertical_advection(staggered, in_w, in_s, in_su, in_sv, out_s, out_
         if in_qv is not None:
             for q, out in ((in_qv, out_qv), (in_qc, out_qc), (in_qr, out_qr)):
                 out[box] = _thomas(*_setup_tridiagonal(gamma, w, in_s[box] * q[box])) / out_s[box]
+
+
+def implicit_vertical_advection_tendency(staggered, in_w, in_s, in_su, in_sv, tnd_s, tnd_su, tnd_sv, *,
+                                         dt, gamma, origin, domain, in_qv=None, in_qc=None,
+                                         in_qr=None, tnd_qv=None, tnd_qc=None, tnd_qr=None):
+    """implicit_vertical_advection.py:L793-L919: the same solves, as tendencies (x_new - x) / dt."""
+    box = tuple(slice(o, o + d) for o, d in zip(origin, domain))
+    i, j, _ = box
+    kb, ke = origin[2], origin[2] + domain[2]
+    w = 0.5 * (in_w[i, j, kb:ke] + in_w[i, j, kb + 1:ke + 1]) if staggered else in_w[box]
+    with np.errstate(all="ignore"):
+        new_s = _thomas(*_setup_tridiagonal(gamma, w, in_s[box]))
+        tnd_s[box] = (new_s - in_s[box]) / dt
+        for src, out in ((in_su, tnd_su), (in_sv, tnd_sv)):
+            out[box] = (_thomas(*_setup_tridiagonal(gamma, w, src[box])) - src[box]) / dt
+        if in_qv is not None:
+            for q, out in ((in_qv, tnd_qv), (in_qc, tnd_qc), (in_qr, tnd_qr)):
+                out[box] = (_thomas(*_setup_tridiagonal(gamma, w, in_s[box] * q[box])) / new_s - q[box]) / dt

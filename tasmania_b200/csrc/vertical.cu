@@ -150,6 +150,7 @@ struct ImplArgs {
   int nfields;            // 3 dry, 6 moist
   bool staggered;
   double gamma;
+  double dt;  // > 0: return the tendencies (x_new - x) / dt (the prognostic component, L793-L919)
   int i0, j0, k0, di, dj, dk;
 };
 
@@ -196,22 +197,32 @@ __global__ void __launch_bounds__(128) implicit_vadv_kernel(const ImplArgs a) {
       delta = d - mult[l] * delta;
       o(i, j, k0 + l) = delta;
     }
-    // backward substitution (cla.py:L70-L78); b == 1 where beta == 0
+    // backward substitution (cla.py:L70-L78); b == 1 where beta == 0.  In tendency mode the
+    // solved s stays in its output until the water species have been divided by it.
+    const bool tend = a.dt > 0.0;
+    auto result = [&](int l, double x) {
+      double v = water ? x / a.out[0](i, j, k0 + l) : x;
+      if (tend && f > 0) v = (v - a.in[f].ld(i, j, k0 + l)) / a.dt;  // L908-L919
+      return v;
+    };
     double x = beta[nk - 1] != 0.0 ? delta / beta[nk - 1] : delta / 1.0;
-    o(i, j, k0 + nk - 1) = water ? x / a.out[0](i, j, k0 + nk - 1) : x;
+    o(i, j, k0 + nk - 1) = result(nk - 1, x);
     for (int l = nk - 2; l >= 0; --l) {
       const double r = o(i, j, k0 + l) - cc[l] * x;
       x = beta[l] != 0.0 ? r / beta[l] : r / 1.0;
-      o(i, j, k0 + l) = water ? x / a.out[0](i, j, k0 + l) : x;
+      o(i, j, k0 + l) = result(l, x);
     }
   }
+  if (a.dt > 0.0)
+    for (int l = 0; l < nk; ++l)
+      a.out[0](i, j, k0 + l) = (a.out[0](i, j, k0 + l) - a.in[0].ld(i, j, k0 + l)) / a.dt;  // L908
 }
 
 extern "C" int tb200_implicit_vertical_advection(
     int staggered_w, const tb200_field *in_w, const tb200_field *in_s, const tb200_field *in_su,
     const tb200_field *in_sv, tb200_field *out_s, tb200_field *out_su, tb200_field *out_sv,
     const tb200_field *in_qv, const tb200_field *in_qc, const tb200_field *in_qr,
-    tb200_field *out_qv, tb200_field *out_qc, tb200_field *out_qr, double gamma,
+    tb200_field *out_qv, tb200_field *out_qc, tb200_field *out_qr, double gamma, double dt_tendency,
     const int32_t origin[3], const int32_t domain[3], void *stream) {
   ImplArgs a{};
   a.w = view(in_w);
@@ -226,8 +237,10 @@ extern "C" int tb200_implicit_vertical_advection(
   a.nfields = moist ? 6 : 3;
   a.staggered = staggered_w != 0;
   a.gamma = gamma;
+  a.dt = dt_tendency;
   a.i0 = origin[0]; a.j0 = origin[1]; a.k0 = origin[2];
   a.di = domain[0]; a.dj = domain[1]; a.dk = domain[2];
+  TB200_REQUIRE(dt_tendency >= 0.0, "implicit_vertical_advection: dt_tendency must be >= 0");
   TB200_REQUIRE(a.dk >= 2 && a.dk <= 256, "implicit_vertical_advection: 2 <= levels <= 256, got %d", a.dk);
   TB200_REQUIRE(a.staggered ? box_inside(a.w, origin, domain, 0, 0, 0, 0, 0, 1)
                             : box_inside(a.w, origin, domain),

@@ -172,3 +172,40 @@ class IsentropicImplicitVerticalAdvectionDiagnostic(StencilFactory):
                 args["in_" + key] = state[name]
                 args["out_" + key] = out_diagnostics[name]
         self._stencil(**args, origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))
+
+
+class IsentropicImplicitVerticalAdvectionPrognostic(StencilFactory):
+    """Mirror of ``tasmania.IsentropicImplicitVerticalAdvectionPrognostic``
+    (src/tasmania/isentropic/physics/implicit_vertical_advection.py:L593-L919): the same solves,
+    returned as tendencies (x_new - x) / dt in storages owned by the component."""
+
+    class_stencils = {"stencil": "implicit_vertical_advection_tendency"}
+
+    def __init__(self, grid, moist=False,
+                 tendency_of_air_potential_temperature_on_interface_levels=False, *, backend="b200",
+                 backend_options=None, storage_shape=None, storage_options=None):
+        super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
+        self.grid, self._moist = grid, moist
+        self._stgz = tendency_of_air_potential_temperature_on_interface_levels
+        shape = tuple(storage_shape or (grid.nx + 1, grid.ny + 1, grid.nz + 1))
+        names = (S, SU, SV) + ((MFWV, MFCW, MFPW) if moist else ())
+        self._tnd = {n: self.zeros(shape=shape) for n in names}
+        self.backend_options.externals = {  # L665-L670
+            "moist": moist,
+            "vstaggering": self._stgz,
+            "setup": self.get_subroutine_definition("setup_thomas"),
+            "setup_bc": self.get_subroutine_definition("setup_thomas_bc"),
+        }
+        self._stencil = self.compile_stencil("stencil")
+
+    def array_call(self, state, timestep):
+        """L722-L792: returns (tendencies, diagnostics)"""
+        g = self.grid
+        dt = timestep.total_seconds()
+        args = {"dt": dt, "gamma": dt / (4.0 * g.dz), "in_w": state[W_HL] if self._stgz else state[W_ML]}
+        for key, name in (("s", S), ("su", SU), ("sv", SV)) + (
+                (("qv", MFWV), ("qc", MFCW), ("qr", MFPW)) if self._moist else ()):
+            args["in_" + key] = state[name]
+            args["tnd_" + key] = self._tnd[name]
+        self._stencil(**args, origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))
+        return dict(self._tnd), {}

@@ -145,6 +145,9 @@ def _class_scoped_stencils():
         ("tasmania.isentropic.physics.implicit_vertical_advection",
          "IsentropicImplicitVerticalAdvectionDiagnostic", "implicit_vertical_advection",
          st.implicit_vertical_advection_b200),
+        ("tasmania.isentropic.physics.implicit_vertical_advection",
+         "IsentropicImplicitVerticalAdvectionPrognostic", "stencil",
+         st.implicit_vertical_advection_tendency_b200),
         ("tasmania.physics.turbulence", "Smagorinsky2d", "smagorinsky", st.smagorinsky_b200),
         ("tasmania.isentropic.physics.turbulence", "IsentropicSmagorinsky", "smagorinsky",
          st.smagorinsky_isentropic_b200),

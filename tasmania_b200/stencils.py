@@ -516,7 +516,24 @@ def implicit_vertical_advection_b200(
     q = [(_f(x) if moist else None) for x in (in_qv, in_qc, in_qr, out_qv, out_qc, out_qr)]
     _call("tb200_implicit_vertical_advection", int(bool(externals.get("staggering", False))), _f(in_w),
           _f(in_s), _f(in_su), _f(in_sv), _f(out_s), _f(out_su), _f(out_sv), q[0], q[1], q[2], q[3],
-          q[4], q[5], float(gamma), _i3(origin), _i3(domain), _stream())
+          q[4], q[5], float(gamma), 0.0, _i3(origin), _i3(domain), _stream())
+
+
+@stencil_definition("implicit_vertical_advection_tendency")
+def implicit_vertical_advection_tendency_b200(
+    externals, *, in_w, in_s, in_su, in_sv, tnd_s, tnd_su, tnd_sv, in_qv=None, in_qc=None,
+    in_qr=None, tnd_qv=None, tnd_qc=None, tnd_qr=None, dt, gamma, origin, domain):
+    """IsentropicImplicitVerticalAdvectionPrognostic's stencil
+    (implicit_vertical_advection.py:L793-L919); externals (L665-L670): moist, vstaggering."""
+    moist = bool(externals.get("moist", False))
+    if moist and any(x is None for x in (in_qv, in_qc, in_qr, tnd_qv, tnd_qc, tnd_qr)):
+        raise lib.B200Error("implicit_vertical_advection: moist=True needs in_q* and tnd_q*")
+    if not float(dt) > 0.0:
+        raise lib.B200Error("implicit_vertical_advection: dt must be positive")
+    q = [(_f(x) if moist else None) for x in (in_qv, in_qc, in_qr, tnd_qv, tnd_qc, tnd_qr)]
+    _call("tb200_implicit_vertical_advection", int(bool(externals.get("vstaggering", False))), _f(in_w),
+          _f(in_s), _f(in_su), _f(in_sv), _f(tnd_s), _f(tnd_su), _f(tnd_sv), q[0], q[1], q[2], q[3],
+          q[4], q[5], float(gamma), float(dt), _i3(origin), _i3(domain), _stream())
 
 
 _KE = "tasmania.physics.microphysics.kessler"

@@ -517,6 +517,22 @@ def gen_vertical_advection():
             ist(fake, **kw)
             for n in names:
                 out[f"implicit_z{int(stgz)}_m{int(moist)}_{n}"] = outs[n]
+    # the prognostic variant (L793-L919): same solves, returned as tendencies
+    for stgz, moist in ((False, True), (True, False)):
+        pst = refload.numpy_stencil(iva.IsentropicImplicitVerticalAdvectionPrognostic._stencil_numpy,
+                                    {"vstaggering": stgz, "moist": moist})
+        fake = types.SimpleNamespace(
+            zeros=lambda backend=None, *, shape, storage_options=None: np.zeros(shape),
+            ones=lambda backend=None, *, shape, storage_options=None: np.ones(shape),
+            get_subroutine_definition=lambda name: subs[name])
+        names = ("s", "su", "sv") + (("qv", "qc", "qr") if moist else ())
+        outs = {n: prev[n].copy() for n in names}
+        kw = {"in_w": wbig, "dt": 7.5, "gamma": gamma, "origin": (0, 0, 0), "domain": (nx, ny, nz)}
+        for n in names:
+            kw["in_" + n], kw["tnd_" + n] = ins[n], outs[n]
+        pst(fake, **kw)
+        for n in names:
+            out[f"implicit_tnd_z{int(stgz)}_m{int(moist)}_{n}"] = outs[n]
     save("isentropic_physics", dims=np.array([nx, ny, nz]), dz=np.array([dz]), f=np.array([f]),
          smag=np.array([sdx, sdy, cs]), gamma=np.array([gamma]), **out)
 

@@ -233,3 +233,28 @@ def test_implicit_vertical_advection_mirror_vs_oracle_bitwise(nz):
         out_qc=ref[va.MFCW], out_qr=ref[va.MFPW])
     for k in names:
         np.testing.assert_array_equal(tb.to_numpy(out[k]), ref[k], err_msg=k)
+
+
+def test_implicit_vertical_advection_tendency_vs_reference_fixture_bitwise():
+    """The prognostic variant through its host mirror (tendencies in component-owned storages)."""
+    from datetime import timedelta
+
+    import tasmania_b200 as tb
+    from tasmania_b200 import isentropic_physics as va
+    from tasmania_b200.grid import Grid
+
+    fx = hp.load("isentropic_physics")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    dz = float(fx["dz"][0])
+    grid = Grid((-10.0, 10.0), nx, (-7.0, 7.0), ny, (280.0 + dz * nz, 280.0), nz, units_to_m=1e3)
+    assert grid.dz == dz
+    key = {va.S: "s", va.SU: "su", va.SV: "sv", va.MFWV: "qv", va.MFCW: "qc", va.MFPW: "qr"}
+    for z, m in ((0, 1), (1, 0)):
+        comp = va.IsentropicImplicitVerticalAdvectionPrognostic(
+            grid, moist=bool(m), tendency_of_air_potential_temperature_on_interface_levels=bool(z))
+        state = {n: tb.as_storage(fx["in_" + k]) for n, k in key.items()}
+        state[va.W_HL if z else va.W_ML] = tb.as_storage(fx["in_w_implicit"])
+        tnd, _ = comp.array_call(state, timedelta(seconds=7.5))
+        for n, arr in tnd.items():
+            got = tb.to_numpy(arr)[:nx, :ny, :nz]
+            np.testing.assert_array_equal(got, fx[f"implicit_tnd_z{z}_m{m}_{key[n]}"][:nx, :ny, :nz], err_msg=n)

@@ -324,3 +324,22 @@ def test_implicit_vertical_advection_bitwise():
                                            fx["in_sv"], outs["s"], outs["su"], outs["sv"], **kw)
             for n in names:
                 np.testing.assert_array_equal(outs[n], fx[f"implicit_z{z}_m{m}_{n}"], err_msg=f"{z}{m}{n}")
+
+
+def test_implicit_vertical_advection_tendency_bitwise():
+    """The prognostic variant (implicit_vertical_advection.py:L793-L919)."""
+    from oracle import isentropic_physics as va
+
+    fx = hp.load("isentropic_physics")
+    nx, ny, nz = (int(v) for v in fx["dims"])
+    for z, m in ((0, 1), (1, 0)):
+        names = ("s", "su", "sv") + (("qv", "qc", "qr") if m else ())
+        outs = {n: fx["prev_" + n].copy() for n in names}
+        kw = dict(dt=7.5, gamma=float(fx["gamma"][0]), origin=(0, 0, 0), domain=(nx, ny, nz))
+        if m:
+            for n in ("qv", "qc", "qr"):
+                kw["in_" + n], kw["tnd_" + n] = fx["in_" + n], outs[n]
+        va.implicit_vertical_advection_tendency(bool(z), fx["in_w_implicit"], fx["in_s"], fx["in_su"],
+                                                fx["in_sv"], outs["s"], outs["su"], outs["sv"], **kw)
+        for n in names:
+            np.testing.assert_array_equal(outs[n], fx[f"implicit_tnd_z{z}_m{m}_{n}"], err_msg=f"{z}{m}{n}")
