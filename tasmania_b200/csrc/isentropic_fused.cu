@@ -5,25 +5,31 @@
 // subclasses/prognostics/rk3ws_si.py:L105-L234):
 //   K1 step s -> irelax(s) -> montgomery(s_new) -> K2 step su, sv -> irelax(s, su, sv, u, v)
 //   -> Rayleigh damping (s, su, sv) -> velocity_x / velocity_y -> outermost layers of u, v.
-// The reference runs 13 full-domain passes for this; here:
+// The reference runs 13 full-domain passes for this; here three kernels (default path):
 //
-//   kernel S   (one thread per column, marching in k)
-//       s_pre = irelax(K1(...))                      -> scratch_s
-//       p by the downward scan on s_pre              -> scratch_exn  (pressure at interface k+1)
-//       exn = cp (p/pref)^kappa, mtg_new by the upward scan -> scratch_mtg
-//   kernel MV  (one warp per 30 columns x 64 rows of a level, marching in j)
+//   kernel A   (one warp per 31 columns x 64 rows of one level, marching in j)
+//       s_pre = irelax(K1(...))                                -> scratch_s
+//   kernel B   (one thread per column, the column in registers)
+//       pressure by the downward scan on s_pre, exn = cp (p/pref)^kappa (pow_pos_n<8>),
+//       mtg_new by the upward scan                             -> scratch_mtg
+//   kernel MV  (one warp per 60 columns x 64 rows of one level, two columns per lane, marching
+//       in j; su / sv / mtg rows staged with cp.async into warp-private shared-memory rings)
 //       su, sv = irelax(K2(...)), s = irelax(s_pre), Rayleigh damping on all three,
 //       u, v from the final s, su, sv, outermost faces from the reference state.
 //
 // The vertical scans are inherently two sweeps (pressure top-down, Montgomery bottom-up) and
-// the momentum step needs mtg_new at i+-1 / j+-1, hence the kernel boundary between S and MV.
+// the momentum step needs mtg_new at i+-1 / j+-1, hence the kernel boundaries.
 //
-// HBM traffic per point and stage (8-byte words): S reads s_now, s_int, u, v, writes s_pre,
-// p, re-reads p, writes mtg = 8 words; MV reads s_now, s_pre, mtg_now, mtg_new, u, v, su_now,
-// su_int, sv_now, sv_int, writes s, su, sv, u, v = 15 words.  Total 23 words = 184 B against
-// the algorithmic minimum of 112 B; the relaxation band and the damping
-// layer add reads of the reference fields only where gamma != 0 or R != 0.  All arithmetic
-// follows the reference's operation order (see stencil_math.cuh).
+// HBM traffic per point and stage (8-byte words): A reads s_now, s_int, u, v, writes s_pre (5);
+// B reads s_pre, writes mtg (2); MV reads s_now, s_pre, mtg_now, mtg_new, u, v, su_now, su_int,
+// sv_now, sv_int, writes s, su, sv, u, v (15).  22 words = 176 B against the algorithmic minimum
+// of 112 B; measured 206 B.  All arithmetic follows
+// the reference's operation order (see stencil_math.cuh).
+//
+// Earlier variants are kept selectable and bit-identical (tests/test_gpu_stage_variants.py):
+// TB200_S_IMPL=column (kernel S = A + B in one thread-per-column kernel, pressures parked in
+// memory), TB200_MV_IMPL=window | ring (register windows / one column per lane),
+// TB200_STAGE_IMPL=tma (isentropic_tma.cu).
 #include <stdlib.h>
 #include <string.h>
 
