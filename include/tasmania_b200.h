@@ -87,6 +87,16 @@ int tb200_elementwise(int op, tb200_field *out, const tb200_field *a, const tb20
                       const tb200_field *c, double f, const int32_t origin[3],
                       const int32_t domain[3], void *stream);
 
+/* Coupler glue: out[n] = a[n] + f * b[n] for n < nfields in ONE launch --
+ * one stage of a tendency stepper over all the fields it steps.  Replaces the per-field `fma`
+ * calls of DataArrayDictOperator.fma (src/tasmania/utils/xarrayx.py:L688-L740, stencil
+ * src/tasmania/framework/subclasses/stencil_definitions/math.py:L59-L63) issued by
+ * src/tasmania/framework/subclasses/tendency_steppers/{forward_euler,rk2,rk3ws}.py. */
+#define TB200_FMA_MAX_FIELDS 8
+int tb200_fma_fields(int nfields, tb200_field *const *out, const tb200_field *const *a,
+                     const tb200_field *const *b, double f, const int32_t origin[3],
+                     const int32_t domain[3], void *stream);
+
 /* ---- K5 lateral boundaries --------------------------------------------------------- */
 /* algorithms.py:L32-L43 (irelax; pass in_phi == NULL) and L46-L57 (relax) */
 int tb200_relax(const tb200_field *in_gamma, const tb200_field *in_phi,

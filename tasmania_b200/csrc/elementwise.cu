@@ -107,6 +107,48 @@ extern "C" int tb200_elementwise(int op, tb200_field *out, const tb200_field *a,
   }
 }
 
+// ---- coupler glue: one stage of a tendency stepper in one launch.
+// The reference's DataArrayDictOperator.fma (src/tasmania/utils/xarrayx.py:L688-L740) runs the
+// `fma` stencil once per stepped field; here every thread updates its point of all fields
+// (up to TB200_FMA_MAX_FIELDS independent load pairs in flight), out_n = a_n + f * b_n.
+namespace {
+struct FmaFields {
+  View out[TB200_FMA_MAX_FIELDS], a[TB200_FMA_MAX_FIELDS], b[TB200_FMA_MAX_FIELDS];
+  int n;
+};
+}  // namespace
+
+extern "C" int tb200_fma_fields(int nfields, tb200_field *const *out,
+                                const tb200_field *const *a, const tb200_field *const *b,
+                                double f, const int32_t origin[3], const int32_t domain[3],
+                                void *stream) {
+  TB200_REQUIRE(out != nullptr && a != nullptr && b != nullptr, "fma_fields: NULL argument");
+  TB200_REQUIRE(nfields >= 1 && nfields <= TB200_FMA_MAX_FIELDS, "fma_fields: 1..%d fields, got %d",
+                TB200_FMA_MAX_FIELDS, nfields);
+  FmaFields ff{};
+  ff.n = nfields;
+  for (int n = 0; n < nfields; ++n) {
+    ff.out[n] = view(out[n]);
+    ff.a[n] = view(a[n]);
+    ff.b[n] = view(b[n]);
+    TB200_REQUIRE(box_inside(ff.out[n], origin, domain), "fma_fields: out box outside storage %d", n);
+    TB200_REQUIRE(box_inside(ff.a[n], origin, domain), "fma_fields: a box outside storage %d", n);
+    TB200_REQUIRE(box_inside(ff.b[n], origin, domain), "fma_fields: b box outside storage %d", n);
+  }
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  return launch_box("fma_fields", domain, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      i += i0; j += j0; k += k0;
+                      double va[TB200_FMA_MAX_FIELDS], vb[TB200_FMA_MAX_FIELDS];
+#pragma unroll
+                      for (int n = 0; n < TB200_FMA_MAX_FIELDS; ++n)
+                        if (n < ff.n) { va[n] = ff.a[n](i, j, k); vb[n] = ff.b[n](i, j, k); }
+#pragma unroll
+                      for (int n = 0; n < TB200_FMA_MAX_FIELDS; ++n)
+                        if (n < ff.n) ff.out[n](i, j, k) = va[n] + f * vb[n];
+                    });
+}
+
 // ---------------------------------------------------------------------------- K5
 extern "C" int tb200_relax(const tb200_field *in_gamma, const tb200_field *in_phi,
                            const tb200_field *in_phi_ref, tb200_field *out_phi,

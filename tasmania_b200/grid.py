@@ -103,8 +103,11 @@ class Grid:
 
 def isentropic_state_from_brunt_vaisala(grid: Grid, x_velocity: float, y_velocity: float,
                                         brunt_vaisala: float, constants=STATE_CONSTANTS,
-                                        storage_shape=None) -> dict:
-    """Dry initial state (numpy arrays), src/tasmania/isentropic/state.py:L126-L230."""
+                                        storage_shape=None, moist=False, precipitation=False,
+                                        relative_humidity=0.5) -> dict:
+    """Initial state (numpy arrays), src/tasmania/isentropic/state.py:L126-L391; with ``moist``
+    also air density / temperature, the water vapour of a uniform relative humidity (Tetens,
+    src/tasmania/utils/meteo.py:L192-L274), no cloud water, no rain."""
     nx, ny, nz = grid.nx, grid.ny, grid.nz
     dz, hs, bv = grid.dz, grid.topography.profile, brunt_vaisala
     rd, g, pref, cp = constants["rd"], constants["g"], constants["pref"], constants["cp"]
@@ -144,7 +147,7 @@ def isentropic_state_from_brunt_vaisala(grid: Grid, x_velocity: float, y_velocit
     sv = np.zeros(shape)
     sv[:nx, :ny, :nz] = 0.5 * s[:nx, :ny, :nz] * (v[:nx, :ny, :nz] + v[:nx, 1 : ny + 1, :nz])
 
-    return {
+    state = {
         "air_isentropic_density": s,
         "air_pressure_on_interface_levels": p,
         "exner_function_on_interface_levels": exn,
@@ -155,3 +158,26 @@ def isentropic_state_from_brunt_vaisala(grid: Grid, x_velocity: float, y_velocit
         "y_momentum_isentropic": sv,
         "y_velocity_at_v_locations": v,
     }
+    if moist:  # state.py:L286-L389
+        rho = np.zeros(shape)
+        rho[:nx, :ny, :nz] = s[:nx, :ny, :nz] * dz / (h[:nx, :ny, :nz] - h[:nx, :ny, 1 : nz + 1])
+        temp = np.zeros(shape)
+        temp[:nx, :ny, :nz] = (
+            0.5 * (exn[:nx, :ny, :nz] + exn[:nx, :ny, 1 : nz + 1]) * theta1d[:, :, :nz] / cp
+        )
+        p_unstg = np.zeros(shape)
+        p_unstg[:nx, :ny, :nz] = 0.5 * (p[:nx, :ny, :nz] + p[:nx, :ny, 1 : nz + 1])
+        rh = np.full(shape, float(relative_humidity))
+        # meteo.py:L231-L248, L266-L272
+        p_sat = 610.78 * np.exp(17.27 * (temp - 273.16) / (temp - 35.86))
+        pw = rh * p_sat
+        with np.errstate(divide="ignore", invalid="ignore"):
+            qv = np.where(p_sat >= 0.616 * p_unstg, 0, 0.62198 * pw / (p_unstg - pw))
+        state["air_density"], state["air_temperature"] = rho, temp
+        state["mass_fraction_of_water_vapor_in_air"] = qv
+        state["mass_fraction_of_cloud_liquid_water_in_air"] = np.zeros(shape)
+        state["mass_fraction_of_precipitation_water_in_air"] = np.zeros(shape)
+        if precipitation:
+            state["precipitation"] = np.zeros((shape[0], shape[1], 1))
+            state["accumulated_precipitation"] = np.zeros((shape[0], shape[1], 1))
+    return state

@@ -54,6 +54,9 @@ class IsentropicVerticalAdvection(StencilFactory):
             "staggering": self._stgz,
         }
         self._stencil = self.compile_stencil("stencil")
+        self.tendency_names = (S, SU, SV) + ((MFWV, MFCW, MFPW) if moist else ())
+
+    kind, diagnostic_names = "tendency", ()
 
     def array_call(self, state, out_tendencies, out_diagnostics=None, overwrite_tendencies=None):
         """vertical_advection.py:L216-L269"""
@@ -86,6 +89,8 @@ class IsentropicConservativeCoriolis(StencilFactory):
         self.backend_options.externals = {"set_output": self.get_subroutine_definition("set_output")}
         self._stencil = self.compile_stencil("coriolis")
 
+    kind, tendency_names, diagnostic_names = "tendency", (SU, SV), ()
+
     def array_call(self, state, out_tendencies, out_diagnostics=None, overwrite_tendencies=None):
         g, nb = self.grid, self._nb
         ow = overwrite_tendencies or {}
@@ -100,6 +105,11 @@ class Smagorinsky2d(StencilFactory):
     tendencies of x_velocity / y_velocity on the interior of the numerical grid."""
 
     names = ("x_velocity", "y_velocity")
+    kind, diagnostic_names = "tendency", ()
+
+    @property
+    def tendency_names(self):
+        return self.names
 
     def __init__(self, grid, nb, smagorinsky_constant=0.18, *, backend="b200", backend_options=None,
                  storage_options=None):
@@ -130,6 +140,7 @@ class IsentropicSmagorinsky(Smagorinsky2d):
     the momenta."""
 
     class_stencils = {"smagorinsky": "smagorinsky_isentropic"}
+    names = (SU, SV)
 
     def array_call(self, state, out_tendencies, out_diagnostics=None, overwrite_tendencies=None):
         g, ow = self.grid, overwrite_tendencies or {}
@@ -143,11 +154,18 @@ class IsentropicImplicitVerticalAdvectionDiagnostic(StencilFactory):
     (src/tasmania/isentropic/physics/implicit_vertical_advection.py:L44-L219): Crank-Nicolson
     vertical advection, one tridiagonal solve per column and field."""
 
+    kind, tendency_names = "implicit", ()
+
+    def diagnostic_shape(self, name):
+        return self.storage_shape
+
     def __init__(self, grid, moist=False,
                  tendency_of_air_potential_temperature_on_interface_levels=False, *, backend="b200",
-                 backend_options=None, storage_options=None):
+                 backend_options=None, storage_shape=None, storage_options=None):
         super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
         self.grid, self._moist = grid, moist
+        self.storage_shape = tuple(storage_shape or (grid.nx + 1, grid.ny + 1, grid.nz + 1))
+        self.diagnostic_names = (S, SU, SV) + ((MFWV, MFCW, MFPW) if moist else ())
         self._stgz = tendency_of_air_potential_temperature_on_interface_levels
         self.backend_options.externals = {  # L112-L117
             "moist": moist,

@@ -43,6 +43,16 @@ class _Component(StencilFactory):
         self.rpc.update(physical_constants or {})
         self.storage_shape = tuple(storage_shape or (grid.nx + 1, grid.ny + 1, grid.nz + 1))
 
+    # what tasmania_b200.coupling needs to know about a component: its call convention (the
+    # sympl base class in the reference) and the keys of its tendency_properties /
+    # diagnostic_properties
+    kind = "tendency"  # "tendency" | "implicit" (takes the timestep) | "diagnostic"
+    tendency_names: tuple = ()
+    diagnostic_names: tuple = ()
+
+    def diagnostic_shape(self, name):
+        return self.storage_shape
+
     @property
     def _box(self):
         g = self.grid
@@ -72,6 +82,14 @@ class KesslerMicrophysics(_Component):
         }
         self._stencil = self.compile_stencil("kessler")
         self._placeholder = self.zeros(shape=self.storage_shape)
+        # kessler.py:L214-L253
+        self.tendency_names = (mfcw, mfpw)
+        if rain_evaporation:
+            self.tendency_names += (mfwv,)
+            if self._pttd:
+                self.diagnostic_names = ("tendency_of_air_potential_temperature",)
+            else:
+                self.tendency_names += ("air_potential_temperature",)
 
     def array_call(self, state, out_tendencies, out_diagnostics, overwrite_tendencies):
         args = {
@@ -124,6 +142,9 @@ class KesslerSaturationAdjustmentDiagnostic(_Saturation):
     """Saturation adjustment as a diagnostic (implicit-tendency) component."""
 
     class_stencils = {"saturation": "saturation_diagnostic"}
+    kind = "implicit"  # kessler.py:L588-L616
+    tendency_names = ("air_potential_temperature",)
+    diagnostic_names = (mfwv, mfcw, "air_temperature")
 
     def array_call(self, state, timestep, out_tendencies, out_diagnostics, overwrite_tendencies):
         in_p, in_exn = self._p_exn(state)
@@ -139,6 +160,7 @@ class KesslerSaturationAdjustmentPrognostic(_Saturation):
     """Saturation adjustment as a tendency component with a saturation rate."""
 
     class_stencils = {"saturation": "saturation_prognostic"}
+    tendency_names = (mfwv, mfcw, "air_potential_temperature")  # kessler.py:L917-L939
 
     def __init__(self, grid, air_pressure_on_interface_levels=True, saturation_rate=0.025,
                  physical_constants=None, **kwargs):
@@ -158,6 +180,9 @@ class KesslerSaturationAdjustmentPrognostic(_Saturation):
 class KesslerFallVelocity(_Component):
     """Raindrop fall velocity."""
 
+    kind = "diagnostic"
+    diagnostic_names = ("raindrop_fall_velocity",)
+
     def __init__(self, grid, **kwargs):
         super().__init__(grid, **kwargs)
         self._in_rho_s = self.zeros(shape=self.storage_shape)
@@ -173,6 +198,9 @@ class KesslerFallVelocity(_Component):
 
 class KesslerSedimentation(_Component):
     """Tendency of qr due to sedimentation."""
+
+    kind = "implicit"
+    tendency_names = (mfpw,)
 
     def __init__(self, grid, sedimentation_flux_scheme="first_order_upwind", **kwargs):
         super().__init__(grid, **kwargs)
@@ -195,6 +223,12 @@ class KesslerSedimentation(_Component):
 
 class Precipitation(_Component):
     """Precipitation rate and accumulated precipitation at the surface (2-D outputs)."""
+
+    kind = "implicit"
+    diagnostic_names = ("precipitation", "accumulated_precipitation")
+
+    def diagnostic_shape(self, name):  # utils.py:L236-L247: one level
+        return (self.storage_shape[0], self.storage_shape[1], 1)
 
     def __init__(self, grid, physical_constants=None, **kwargs):
         super().__init__(grid, physical_constants, **kwargs)

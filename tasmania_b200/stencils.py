@@ -193,6 +193,27 @@ def isub_b200(externals, *, inout_a, in_b, origin, domain):
     _ew("sub", inout_a, inout_a, in_b, origin=origin, domain=domain)
 
 
+FMA_MAX_FIELDS = 8
+
+
+def fma_fields(outs, ins_a, ins_b, f, *, origin, domain):
+    """out_n = a_n + f * b_n over the box for all listed fields, TB200_FMA_MAX_FIELDS per launch:
+    one stage of a tendency stepper (tasmania_b200.coupling) instead of one `fma` call per
+    field (DataArrayDictOperator.fma, src/tasmania/utils/xarrayx.py:L688-L740)."""
+    outs, ins_a, ins_b = list(outs), list(ins_a), list(ins_b)
+    if not (len(outs) == len(ins_a) == len(ins_b)):
+        raise lib.B200Error("fma_fields: the three field lists differ in length")
+    for lo in range(0, len(outs), FMA_MAX_FIELDS):
+        keep, arrs = [], []
+        for group in (outs, ins_a, ins_b):
+            k = [_f(x) for x in group[lo:lo + FMA_MAX_FIELDS]]
+            keep.append(k)
+            arrs.append((lib.FieldP * len(k))(*[C.pointer(x) for x in k]))
+        _call("tb200_fma_fields", len(keep[0]), arrs[0], arrs[1], arrs[2], float(f),
+              _i3(origin), _i3(domain), _stream())
+        del keep
+
+
 @stencil_definition("sts_rk2_0")
 def sts_rk2_0_b200(externals, *, in_field, in_field_prv, in_tnd, out_field, dt, origin, domain):
     _ew("sts_rk2_0", out_field, in_field, in_field_prv, in_tnd, f=dt, origin=origin, domain=domain)

@@ -1,0 +1,110 @@
+# -*- coding: utf-8 -*-
+"""Host-logic test double for libtasmania_b200.so (test infrastructure, CPU only).
+
+The product has no CPU path: its kernels live behind the C ABI and refuse host memory.  To test
+the *host* side (couplers, model assembly, argument marshalling) in the GPU-less container, this
+module swaps the loaded library for a stub whose entry points
+
+  * have the ctypes prototypes of ``tasmania_b200.lib.SIGNATURES`` -- every call is type-checked
+    against the declared C signature exactly as a real call would be -- and are recorded;
+  * do nothing, except ``tb200_fma_fields`` and ``tb200_elementwise`` (copy / fma), which are
+    carried out with numpy on the host buffers so that the arithmetic of the coupling layer
+    (stage factors, buffer swaps, accumulate-or-overwrite) can be followed end to end.
+
+Storages are allocated on the host for the duration (``storage.DEFAULT_DEVICE_OVERRIDE``).
+Nothing in tasmania_b200 knows about this file.
+"""
+import contextlib
+import ctypes as C
+
+import numpy as np
+
+from tasmania_b200 import lib, stencils, storage
+
+
+def _host_field(x):
+    if x is None:
+        return None
+    t = x.t if hasattr(x, "t") else x
+    shape, strides = tuple(t.shape), list(t.stride())
+    while len(shape) < 3:
+        shape, strides = shape + (1,), strides + [0]
+    f = lib.Field()
+    f.ptr = t.data_ptr()
+    f.shape[:] = shape
+    f.stride[:] = strides
+    return f
+
+
+def _as_numpy(field):
+    shape = tuple(int(n) for n in field.shape)
+    stride = tuple(int(s) for s in field.stride)
+    n = 1 + sum((a - 1) * s for a, s in zip(shape, stride))
+    flat = np.ctypeslib.as_array((C.c_double * n).from_address(field.ptr))
+    return np.lib.stride_tricks.as_strided(flat, shape, tuple(8 * s for s in stride))
+
+
+def _box(o, d):
+    return tuple(slice(int(o[n]), int(o[n]) + int(d[n])) for n in range(3))
+
+
+class AbiStub:
+    def __init__(self):
+        self.calls = []
+        self._cb = {}
+        for name, argtypes in lib.SIGNATURES.items():
+            self._cb[name] = C.CFUNCTYPE(C.c_int, *argtypes)(self._make(name))
+
+    def _make(self, name):
+        def fn(*args):
+            self.calls.append(name)
+            handler = getattr(self, "_do_" + name, None)
+            if handler is not None:
+                handler(*args)
+            return 0
+
+        return fn
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["_cb"][name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def tb200_last_error(self):
+        return b"stub"
+
+    def tb200_launch_count(self):
+        return len(self.calls)
+
+    # ---- the two entry points the stub really executes
+    def _do_tb200_fma_fields(self, n, outs, a, b, f, o, d, stream):
+        box = _box(o, d)
+        for m in range(n):
+            _as_numpy(outs[m].contents)[box] = (
+                _as_numpy(a[m].contents)[box] + f * _as_numpy(b[m].contents)[box])
+
+    def _do_tb200_elementwise(self, op, out, a, b, c, f, o, d, stream):
+        box = _box(o, d)
+        if op == lib.ELEMENTWISE_OPS["copy"]:
+            _as_numpy(out.contents)[box] = _as_numpy(a.contents)[box]
+        elif op == lib.ELEMENTWISE_OPS["fma"]:
+            _as_numpy(out.contents)[box] = _as_numpy(a.contents)[box] + f * _as_numpy(b.contents)[box]
+
+    def count(self, name):
+        return sum(1 for c in self.calls if c == name)
+
+
+@contextlib.contextmanager
+def stubbed_library():
+    """``with stubbed_library() as stub:`` -- host storages + the recording ABI stub."""
+    saved = (lib._lib, lib.as_field, lib.current_stream, stencils._f, storage.DEFAULT_DEVICE_OVERRIDE)
+    stub = AbiStub()
+    lib._lib, lib.as_field, lib.current_stream = stub, _host_field, lambda: 0
+    stencils._f = _host_field
+    storage.DEFAULT_DEVICE_OVERRIDE = "cpu"
+    try:
+        yield stub
+    finally:
+        (lib._lib, lib.as_field, lib.current_stream, stencils._f,
+         storage.DEFAULT_DEVICE_OVERRIDE) = saved
