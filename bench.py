@@ -86,51 +86,42 @@ def mountain_case(nx, ny, nz):
 
 
 class DryRun:
-    """The timed loop on b200 storages."""
+    """The timed loop on b200 storages (tasmania_b200.isentropic_dry.IsentropicDryRun on the
+    benchmark's initial condition); ``graph=True`` replays the step as CUDA graphs."""
 
-    def __init__(self, nx, ny, nz, device_index=0):
+    def __init__(self, nx, ny, nz, device_index=0, graph=False):
         import torch
 
         import tasmania_b200 as tb
-        from tasmania_b200.boundary import Relaxed
-        from tasmania_b200.isentropic import (MTG, S, SU, SV, U, V, IsentropicDiagnostics,
-                                              IsentropicDynamicalCore)
+        from tasmania_b200.isentropic import MTG, S
+        from tasmania_b200.isentropic_dry import IsentropicDryRun
 
         self.tb, self.torch = tb, torch
-        self.names = (S, SU, SV, U, V, MTG)
-        self.out_names = (S, SU, U, SV, V)
         self.S, self.MTG = S, MTG
         self.nx, self.ny, self.nz = nx, ny, nz
         self.grid, np_state = mountain_case(nx, ny, nz)
         self.np_state = np_state
-        self.pt = float(np_state[P][0, 0, 0])
-        self.dt = timedelta(seconds=5)
-        self.hb = Relaxed(nx, ny, nz, 3, nr=6)
-        self.state = {n: tb.as_storage(v) for n, v in np_state.items()}
-        self.state["time"] = datetime(2000, 1, 1)
-        self.hb.reference_state = self.state
-        self.dyc = IsentropicDynamicalCore(
-            self.grid, self.hb, time_integration_scheme="rk3ws_si",
-            horizontal_flux_scheme="fifth_order_upwind",
-            time_integration_properties={"pt": self.pt, "eps": 0.5}, damp=True, damp_depth=15,
-            damp_max=5e-4)
+        self.run = IsentropicDryRun(self.grid, np_state, timedelta(seconds=5))
+        self.out_names = self.run.out_names
+        self.names = (S,) + tuple(n for n in self.out_names if n != S) + (MTG,)
+        self.pt, self.dt, self.hb, self.dyc, self.diag = (self.run.pt, self.run.dt, self.run.hb,
+                                                          self.run.dyc, self.run.diag)
         assert self.dyc._fused
-        self.diag = IsentropicDiagnostics(self.grid)
-        self.spare = {n: tb.zeros(self.dyc.storage_shape) for n in self.out_names}
-        self.nstep = 0
+        self.loop = None
+        if graph:
+            from tasmania_b200.graphs import GraphedLoop
+
+            self.loop = GraphedLoop(self.run)
+
+    @property
+    def state(self):
+        return self.run.state
 
     def step(self):
-        """update_topography -> dycore -> diagnostics refresh; ping-pong the output buffers."""
-        self.nstep += 1
-        self.dyc.update_topography(self.nstep * self.dt)
-        out = self.dyc(self.state, {}, self.dt, out_state=self.spare)
-        new = {n: out[n] for n in self.out_names}
-        new["time"] = out["time"]
-        for n in (P, EXN, H, self.MTG):
-            new[n] = self.state[n]
-        self.spare = {n: self.state[n] for n in self.out_names}
-        self.diag.get_diagnostic_variables(new[self.S], self.pt, new[P], new[EXN], new[self.MTG], new[H])
-        self.state = new
+        if self.loop is not None:
+            self.loop.step()
+        else:
+            self.run.step()
 
 
 # ------------------------------------------------------------------ clocks sampler
@@ -281,7 +272,7 @@ def run_b200(args):
 
         run = DecomposedDryRun(nx, ny, nz, rank, world, overlap=args.overlap)
     else:
-        run = DryRun(nx, ny, nz, local_rank)
+        run = DryRun(nx, ny, nz, local_rank, graph=args.graph)
 
     def barrier():
         if distributed:
@@ -300,12 +291,15 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = tblib.launch_count()
+    replayed0 = run.loop.replayed_launches if getattr(run, "loop", None) is not None else 0
     ev0.record()
     for _ in range(args.steps):
         run.step()
     ev1.record()
     barrier()
     launches = tblib.launch_count() - launches0  # kernels of libtasmania_b200.so, this rank
+    if getattr(run, "loop", None) is not None:  # launches replayed from CUDA graphs are ours too
+        launches += run.loop.replayed_launches - replayed0
     ms = ev0.elapsed_time(ev1)
     if os.environ.get("TB200_DEBUG_RANKS"):
         print(f"[rank {rank}] {ms / args.steps:.3f} ms/step on its own clock", file=sys.stderr, flush=True)
@@ -410,8 +404,9 @@ def kernel_roofline(run, args):
 
     tblib.check(handle.tb200_stage_profile(1), "tb200_stage_profile")
     dyc._stage_fused = timed
+    eager_step = run.run.step if hasattr(run, "run") else run.step  # never through a graph replay
     for _ in range(max(2, min(args.steps, 5))):
-        run.step()
+        eager_step()
     torch.cuda.synchronize()
     dyc._stage_fused = orig
     tblib.check(handle.tb200_stage_profile(0), "tb200_stage_profile")
@@ -492,6 +487,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step as CUDA graphs (tasmania_b200.graphs): pays on the "
+                         "launch-bound grids (c2), irrelevant at c5 where a step is 8.5 ms of kernels")
     ap.add_argument("--overlap", action="store_true",
                     help="multi-GPU: run the halo exchange on a side stream under the interior "
                          "blocks of the momentum kernel (measured slower at 8 GPUs: 12.19 vs 11.94 "

@@ -304,6 +304,81 @@ __global__ void __launch_bounds__(128, 2) stage_b_kernel(const StageArgs a) {
   }
 }
 
+// Kernel B for SMALL grids.  One thread per column is the right shape when there are a million
+// columns (config 5); a 161 x 161 grid has 26 000, i.e. 1.4 warps per scheduler, each walking
+// through ~4000 dependent fp64 instructions: 45 us where the data would allow 5 (profiles/
+// README.md, round 1d).  Here a block of 32 columns x 8 threads splits the column work by what is
+// actually serial: only the two running sums are (one add per level each); the divisions by pref,
+// the Exner powers (eight levels per thread -- exactly one exner8 call) and the products entering
+// the sums are evaluated by all 256 threads out of shared memory.  Every value is produced by the
+// same operation sequence as in stage_b_kernel: bit-identical results.
+template <int NZC>
+__global__ void __launch_bounds__(256) stage_b_coop_kernel(const StageArgs a) {
+  static_assert(NZC % 8 == 0 && NZC <= 64, "eight threads per column, eight levels each");
+  __shared__ double sm[NZC][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // column within the block / level group
+  const int i = blockIdx.x * 32 + tx, j = blockIdx.y;
+  const bool live = i < a.nx;
+  const int ic = live ? i : a.nx - 1;
+  const int nz = a.nz;
+  const double kappa = a.rd / a.cp;
+  const double gdz = a.g * a.dz;
+  // increments of the pressure sum, levels ty, ty + 8, ... (rows of 32 columns: coalesced)
+  {
+    const double *ps = a.spre.p + (ic + j * a.spre.s1);
+    const long long s2 = a.spre.s2;
+#pragma unroll
+    for (int k = ty; k < NZC; k += 8) sm[k][tx] = k < nz ? gdz * __ldg(ps + k * s2) : 0.0;
+  }
+  __syncthreads();
+  if (ty == 0) {  // pressure at interface k + 1, diagnostics.py:L425-L428
+    double p = a.pt;
+#pragma unroll
+    for (int k = 0; k < NZC; ++k) {
+      if (k < nz) {
+        p = p + sm[k][tx];
+        sm[k][tx] = p;
+      }
+    }
+  }
+  __syncthreads();
+  {  // Exner function of the eight interfaces 8 ty + 1 .. 8 ty + 8 and their weight in the sum
+    D8 x;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) x.v[n] = 8 * ty + n < nz ? sm[8 * ty + n][tx] / a.cpref : 1.0;
+    if (8 * ty < nz) {
+      const D8 r = exner8(x, kappa, a.cp);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int k = 8 * ty + n;
+        // level nz - 1 keeps the Exner value itself (surface term), the others dz * exn
+        sm[k][tx] = k == nz - 1 ? r.v[n] : a.dz * r.v[n];
+      }
+    }
+  }
+  __syncthreads();
+  if (ty == 0 && live) {  // upward sweep, diagnostics.py:L433-L438
+    double *pm = a.mtg.p + (i + j * a.mtg.s1);
+    const long long m2 = a.mtg.s2;
+    const double ex_s = sm[nz - 1][tx];
+    const double mtg_s = a.theta_s * ex_s + a.g * a.hs.ld(i, j, 0);
+    double m = mtg_s + 0.5 * a.dz * ex_s;
+    pm[(nz - 1) * m2] = m;
+    for (int k = nz - 2; k >= 0; --k) {
+      m = m + sm[k][tx];
+      sm[k][tx] = m;
+    }
+  }
+  __syncthreads();
+  if (live) {  // store the levels below the surface one, rows of 32 columns
+    double *pm = a.mtg.p + (i + j * a.mtg.s1);
+    const long long m2 = a.mtg.s2;
+#pragma unroll
+    for (int k = ty; k < NZC; k += 8)
+      if (k < nz - 1) pm[k * m2] = sm[k][tx];
+  }
+}
+
 // ---------------------------------------------------------------- kernel MV
 // Momentum step + second relaxation + Rayleigh damping + velocity diagnosis in one pass.
 //
@@ -1289,22 +1364,84 @@ int launch_mv_part(const StageArgs &a, cudaStream_t st) {
   return rc;
 }
 
+// Rows per warp strip (LJ) of the j-marching kernels A and MV.  64 is the measured optimum on
+// large grids (1/64 of redundant warm-up rows; config 5), but a 161 x 161 x 60 grid (config 2)
+// then yields only 1080 / 540 warps for the 148 SMs -- 1-2 warps per scheduler marching serially
+// through 64 dependent rows, 5x slower per point than at config 5 (profiles/README.md, round 1d).
+// Shorter strips trade warm-up redundancy for parallelism: the largest LJ of {64, 16, 8} that gives
+// every scheduler TARGET warps is used.  TB200_LJ=64|16|8 forces one (experiments).
+constexpr int SM_COUNT = 148, LJ_TARGET_WARPS = SM_COUNT * 4 * 4;
+int lj_forced() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TB200_LJ");
+    v = e == nullptr ? 0 : atoi(e);
+    if (v != 64 && v != 16 && v != 8) v = 0;
+  }
+  return v;
+}
+int pick_lj(long long strips_x, int ny, int nz) {
+  if (lj_forced()) return lj_forced();
+  for (int lj : {64, 16}) {
+    if (strips_x * ((ny + lj - 1) / lj) * nz >= LJ_TARGET_WARPS) return lj;
+  }
+  return 8;
+}
+
+// TB200_B_IMPL=column|coop forces the scan kernel; by default the cooperative one runs when one
+// thread per column would leave the schedulers with fewer than four warps each
+bool b_coop(const StageArgs &a) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("TB200_B_IMPL");
+    forced = e == nullptr ? 0 : strcmp(e, "column") == 0 ? 1 : strcmp(e, "coop") == 0 ? 2 : 0;
+  }
+  if (forced) return forced == 2;
+  return (long long)a.nx * a.ny < (long long)LJ_TARGET_WARPS * 32;
+}
+
+template <int SCHEME, int LJ>
+int launch_a(const StageArgs &a, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  const int chunks = (a.nx + A_COLS - 1) / A_COLS;
+  dim3 block(32 * WARPS, 1, 1);
+  dim3 grid((chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
+  stage_a_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
+  return check_launch("isentropic_stage_dry/A");
+}
+
+template <int SCHEME>
+int launch_mv(const StageArgs &a, cudaStream_t st) {
+  const MvGeom g = mv_geom(a);
+  // the overlap parts of a decomposed run are laid out in blocks of 64-row strips
+  const int lj = a.part != 0 ? 64 : pick_lj((a.nx + g.cols - 1) / g.cols, a.ny, a.nz);
+  if (lj == 16) return launch_mv_part<SCHEME, 16>(a, st);
+  if (lj == 8) return launch_mv_part<SCHEME, 8>(a, st);
+  return launch_mv_part<SCHEME, 64>(a, st);
+}
+
 template <int SCHEME>
 int run_stage(const StageArgs &a, cudaStream_t st) {
-  if (a.part == 2) return launch_mv_part<SCHEME, 64>(a, st);  // the s-step and the scans ran with part 1
+  if (a.part == 2) return launch_mv<SCHEME>(a, st);  // the s-step and the scans ran with part 1
   prof_mark(0, st);
   if (s_impl() != 0 && a.nz <= 64) {
     {
-      constexpr int LJ = 64, WARPS = 4;
-      const int chunks = (a.nx + A_COLS - 1) / A_COLS;
-      dim3 block(32 * WARPS, 1, 1);
-      dim3 grid((chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
-      stage_a_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
-      int rc = check_launch("isentropic_stage_dry/A");
+      const int lj = pick_lj((a.nx + A_COLS - 1) / A_COLS, a.ny, a.nz);
+      const int rc = lj == 16 ? launch_a<SCHEME, 16>(a, st)
+                     : lj == 8 ? launch_a<SCHEME, 8>(a, st) : launch_a<SCHEME, 64>(a, st);
       if (rc) return rc;
       prof_mark(1, st);
     }
-    {
+    if (b_coop(a)) {
+      dim3 block(32, 8, 1);
+      dim3 grid((a.nx + 31) / 32, a.ny, 1);
+      if (a.nz <= 32)
+        stage_b_coop_kernel<32><<<grid, block, 0, st>>>(a);
+      else
+        stage_b_coop_kernel<64><<<grid, block, 0, st>>>(a);
+      int rc = check_launch("isentropic_stage_dry/B(coop)");
+      if (rc) return rc;
+    } else {
       dim3 block(32, 4, 1);
       dim3 grid((a.nx + 31) / 32, (a.ny + 3) / 4, 1);
       if (a.nz == 64)
@@ -1334,7 +1471,7 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
     }
   }
   {
-    const int rc = launch_mv_part<SCHEME, 64>(a, st);
+    const int rc = launch_mv<SCHEME>(a, st);
     prof_mark(3, st);
     g_prof.recorded = g_prof.on;
     return rc;

@@ -66,7 +66,8 @@ class IsentropicMoistSUS:
         shape = (nx + 1, ny + 1, nz + 1)
         up = lambda a: storage.as_storage(a, device=device)  # noqa: E731
         self.state = {n: up(v) for n, v in state.items()}
-        self.state["time"] = init_time or datetime(1992, 2, 20)
+        self.init_time = init_time or datetime(1992, 2, 20)
+        self.state["time"] = self.init_time
         if W not in self.state:  # driver_namelist_sus.py:L125-L132
             self.state[W] = storage.zeros(shape, device=device)
         hb = HorizontalBoundary.factory("relaxed", nx, ny, nz, nb, nr=nl["nr"])
@@ -121,11 +122,21 @@ class IsentropicMoistSUS:
         self._state_new = None
         self.nstep = 0
 
-    def step(self):
+    # ---- one step = prepare_step (host-dependent, tiny) + compute_step (a fixed kernel sequence
+    # on fixed buffers: what tasmania_b200.graphs.GraphedLoop captures) + finish_step (host)
+    def topography_consumers(self):
+        """Every IsentropicDiagnostics core holding a device copy of the terrain height."""
+        return [self.dycore._prognostic._diagnostics, self.physics._component_list[0]._core]
+
+    def prepare_step(self):
+        self.nstep += 1
+        self.dycore.update_topography(self.nstep * self.dt)
+        for d in self.topography_consumers():
+            d._set_topography()
+
+    def compute_step(self):
         """driver_namelist_sus.py:L490-L512."""
         state, dt = self.state, self.dt
-        self.nstep += 1
-        self.dycore.update_topography(self.nstep * dt)
         if self._state_new is None:
             self._state_new = {}
         out = self.dycore(state, {}, dt, out_state=self._state_new)
@@ -136,6 +147,27 @@ class IsentropicMoistSUS:
         # the arrays left in the old dict are the output buffers of the next step (L494)
         self.state, self._state_new = out, {n: v for n, v in state.items()
                                             if n in self.dycore.output_names}
+
+    def finish_step(self):
+        self.state["time"] = self.init_time + self.nstep * self.dt
+
+    def buffer_dicts(self):
+        """The dicts whose arrays are permuted by a step (update_swap / ping-pong)."""
+        if self._state_new is None:
+            self._state_new = {}
+        return ([self.state, self._state_new] + self.physics._out_diagnostics
+                + self.physics._out_state)
+
+    def set_buffer_dicts(self, dicts):
+        self.state, self._state_new = dicts[0], dicts[1]
+        n = len(self.physics._out_diagnostics)
+        self.physics._out_diagnostics[:] = dicts[2:2 + n]
+        self.physics._out_state[:] = dicts[2 + n:]
+
+    def step(self):
+        self.prepare_step()
+        self.compute_step()
+        self.finish_step()
         return self.state
 
     def run(self, nsteps):

@@ -48,22 +48,69 @@ def _box(o, d):
     return tuple(slice(int(o[n]), int(o[n]) + int(d[n])) for n in range(3))
 
 
+def _freeze(name, argtypes, args):
+    """Copy the ctypes arguments of a call so that it can be re-issued later (the marshalling
+    code frees its tb200_field structs right after the call) and describe it for traces."""
+    frozen, desc, keep = [], [], []
+    nf = {"tb200_fma_fields": lambda a: a[0], "tb200_halo_pack": lambda a: a[1],
+          "tb200_halo_unpack": lambda a: a[1]}.get(name, lambda a: 3)(args)
+    for t, v in zip(argtypes, args):
+        if t is lib.FieldP:
+            if not v:
+                frozen.append(None), desc.append(None)
+            else:
+                f = lib.Field.from_buffer_copy(v.contents)
+                keep.append(f)
+                frozen.append(C.pointer(f))
+                desc.append((f.ptr, tuple(f.shape), tuple(f.stride)))
+        elif t is C.POINTER(lib.FieldP):
+            if not v:
+                frozen.append(None), desc.append(None)
+            else:
+                fs = [lib.Field.from_buffer_copy(v[m].contents) if v[m] else None for m in range(nf)]
+                keep.append(fs)
+                arr = (lib.FieldP * nf)(*[C.pointer(f) if f is not None else None for f in fs])
+                keep.append(arr)
+                frozen.append(arr)
+                desc.append(tuple(None if f is None else (f.ptr, tuple(f.shape), tuple(f.stride))
+                                  for f in fs))
+        elif t is C.POINTER(C.c_int32):
+            vals = (C.c_int32 * 3)(v[0], v[1], v[2])
+            keep.append(vals)
+            frozen.append(vals), desc.append(tuple(vals))
+        elif t in (C.c_double, C.c_int, C.c_uint32):
+            frozen.append(v), desc.append(v)
+        else:  # stream handles, config structs, raw buffers: passed through, not traced
+            frozen.append(v), desc.append("*")
+    return frozen, tuple(desc), keep
+
+
 class AbiStub:
     def __init__(self):
         self.calls = []
+        self.trace = None      # list of (name, argument description) of every EXECUTED call
+        self.recording = None  # list of frozen calls while a fake graph capture is on
         self._cb = {}
         for name, argtypes in lib.SIGNATURES.items():
-            self._cb[name] = C.CFUNCTYPE(C.c_int, *argtypes)(self._make(name))
+            self._cb[name] = C.CFUNCTYPE(C.c_int, *argtypes)(self._make(name, argtypes))
 
-    def _make(self, name):
+    def _make(self, name, argtypes):
         def fn(*args):
             self.calls.append(name)
-            handler = getattr(self, "_do_" + name, None)
-            if handler is not None:
-                handler(*args)
+            if self.recording is not None:  # stream capture: record, do not execute
+                self.recording.append((name,) + _freeze(name, argtypes, args))
+                return 0
+            self._execute(name, args, _freeze(name, argtypes, args)[1] if self.trace is not None else None)
             return 0
 
         return fn
+
+    def _execute(self, name, args, desc):
+        if self.trace is not None:
+            self.trace.append((name, desc))
+        handler = getattr(self, "_do_" + name, None)
+        if handler is not None:
+            handler(*args)
 
     def __getattr__(self, name):
         try:
@@ -93,6 +140,42 @@ class AbiStub:
 
     def count(self, name):
         return sum(1 for c in self.calls if c == name)
+
+
+class FakeCapture:
+    """Stands in for torch.cuda.CUDAGraph in tasmania_b200.graphs.GraphedLoop: ``capture`` records
+    the ABI calls ``fn`` issues WITHOUT executing them (like stream capture), ``replay`` re-issues
+    them with the recorded arguments."""
+
+    stub = None  # set by the test
+
+    def capture(self, fn):
+        stub = self.stub
+        assert stub.recording is None
+        stub.recording = []
+        try:
+            fn()
+        finally:
+            self.recorded, stub.recording = stub.recording, None
+
+    def replay(self):
+        for name, frozen, desc, _keep in self.recorded:
+            self.stub._execute(name, frozen, desc)
+
+
+def canonical(trace):
+    """A trace with every pointer replaced by the order of its first appearance, so that runs of two
+    model instances (different allocations, same allocation order) can be compared."""
+    ids = {}
+
+    def canon(x):
+        if isinstance(x, tuple) and len(x) == 3 and isinstance(x[1], tuple) and isinstance(x[0], int):
+            return (ids.setdefault(x[0], len(ids)),) + x[1:]
+        if isinstance(x, tuple):
+            return tuple(canon(y) for y in x)
+        return x
+
+    return [(name, canon(desc)) for name, desc in trace]
 
 
 @contextlib.contextmanager

@@ -80,7 +80,7 @@ def oracle_dry_run(fx, nsteps=None):
 
 
 def moist_case(nx, ny, nz, *, topo_seconds=60.0, max_height=1000.0, relative_humidity=0.98,
-               seed=True):
+               seed=True, half_width_km=(176.0, 176.0)):
     """BASELINE config 3 scaled down: the moist mountain-flow case of namelist_sus.py on a 352 km
     square (grid spacing of a 161-point axis is kept when nx = ny = 161), with a faster-growing,
     taller mountain and -- when ``seed`` -- blobs of cloud water and rain in the initial state so
@@ -89,10 +89,11 @@ def moist_case(nx, ny, nz, *, topo_seconds=60.0, max_height=1000.0, relative_hum
     from tasmania_b200.grid import Grid, Topography as GTopography
     from tasmania_b200.grid import gaussian_profile, isentropic_state_from_brunt_vaisala
 
-    x = np.linspace(-176.0, 176.0, nx)
-    y = np.linspace(-176.0, 176.0, ny)
+    hx, hy = half_width_km
+    x = np.linspace(-hx, hx, nx)
+    y = np.linspace(-hy, hy, ny)
     topo = GTopography(gaussian_profile(x, y, max_height, 50.0, 50.0), timedelta(seconds=topo_seconds))
-    grid = Grid((-176.0, 176.0), nx, (-176.0, 176.0), ny, (400.0, 280.0), nz, units_to_m=1e3,
+    grid = Grid((-hx, hx), nx, (-hy, hy), ny, (400.0, 280.0), nz, units_to_m=1e3,
                 topography=topo)
     state = isentropic_state_from_brunt_vaisala(grid, 22.5, 0.0, 0.015, moist=True,
                                                 precipitation=True,

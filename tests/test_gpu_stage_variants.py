@@ -58,3 +58,13 @@ def test_scan_kernel_variants_are_bitwise_identical(nz):
     kernel S (thread per column, pressures parked in memory)."""
     ref = _digest("fifth_order_upwind", nz)
     assert _digest("fifth_order_upwind", nz, TB200_S_IMPL="column") == ref
+
+
+@pytest.mark.parametrize("nz", [12, 60])
+def test_small_grid_kernels_are_bitwise_identical(nz):
+    """On small grids the stage runs short strips (LJ = 16 or 8 rows per warp instead of 64) and
+    the cooperative column-scan kernel (32 columns x 8 threads per block); the default of this
+    131 x 77 case.  Same bits as the large-grid kernels."""
+    ref = _digest("fifth_order_upwind", nz)
+    assert _digest("fifth_order_upwind", nz, TB200_LJ="64", TB200_B_IMPL="column") == ref
+    assert _digest("fifth_order_upwind", nz, TB200_LJ="16", TB200_B_IMPL="coop") == ref
