@@ -102,6 +102,14 @@ int tb200_fma_fields(int nfields, tb200_field *const *out, const tb200_field *co
 int tb200_relax(const tb200_field *in_gamma, const tb200_field *in_phi,
                 const tb200_field *in_phi_ref, tb200_field *out_phi, const int32_t origin[3],
                 const int32_t domain[3], void *stream);
+/* Relaxed.enforce_raw (horizontal_boundary.py:L299-L344 over relaxed.py:L119-L137) for up to
+ * TB200_FMA_MAX_FIELDS fields in one launch restricted to the frame where gamma != 0:
+ * extents = nfields x (mi, mj, mk) of each field (staggered fields are one point larger),
+ * interior = (i_lo, i_hi, j_lo, j_hi), a box on which gamma is zero (points inside are skipped). */
+int tb200_relax_frame(int nfields, tb200_field *const *phi, const tb200_field *const *phi_ref,
+                      const tb200_field *gamma, const int32_t *extents, const int32_t interior[4],
+                      void *stream);
+
 /* Periodic.enforce_field, src/tasmania/domain/subclasses/horizontal_boundaries/
  * periodic.py:L98-L122; nx, ny = physical sizes, mx, my = nx|nx+1, ny|ny+1 (staggering) */
 int tb200_periodic_enforce(tb200_field *field, int nx, int ny, int nb, int mx, int my,

@@ -12,6 +12,8 @@ uploaded; every field operation is a CUDA kernel.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from tasmania_b200 import lib, storage
@@ -128,6 +130,7 @@ class Relaxed(HorizontalBoundary):
             g2d = storage.as_storage(g[:, :, None], device=self.storage_options.device)
             self._gamma2d = g2d
             self._gamma = storage.B200Array(g2d.t.expand(-1, -1, self._shape[2]))
+            self._free_box = self._gamma_free_box(g)
             return
         rrel = rel[::-1]
         g = np.zeros((self._shape[0], self._shape[1]))
@@ -147,6 +150,7 @@ class Relaxed(HorizontalBoundary):
         g[: nx + 1, ny : ny + 1] = 1.0
         g2d = storage.as_storage(g[:, :, None], device=self.storage_options.device)
         self._gamma2d = g2d
+        self._free_box = self._gamma_free_box(g)
         # (ni, nj, nk) view with stride 0 along k
         self._gamma = storage.B200Array(g2d.t.expand(-1, -1, self._shape[2]))
 
@@ -154,6 +158,52 @@ class Relaxed(HorizontalBoundary):
         mi, mj, mk = _extent(self.nx, self.ny, self.nz, field_name)
         self._stencil(in_gamma=self._gamma, in_phi_ref=self.reference_state[field_name],
                       inout_phi=field, origin=(0, 0, 0), domain=(mi, mj, mk))
+
+    @staticmethod
+    def _gamma_free_box(g):
+        """(i_lo, i_hi, j_lo, j_hi): a box of the (nx + 1, ny + 1) coefficient matrix on which gamma
+        vanishes -- everything but the nr outer rings and the staggered extra row / column on a
+        whole domain, everything on an interior sub-domain of a decomposed grid.  Found from the
+        matrix itself and verified; (0, 0, 0, 0) (= relax everywhere) if the zeros are not a box."""
+        nz_mask = np.asarray(g) != 0.0
+        rows = np.flatnonzero(~nz_mask.all(axis=1))  # rows with at least one zero
+        cols = np.flatnonzero(~nz_mask.all(axis=0))
+        if rows.size and cols.size:
+            # the zero set of a ring-structured matrix is the box spanned by the zeros of its
+            # middle row and column
+            im, jm = int(rows[rows.size // 2]), int(cols[cols.size // 2])
+            zi, zj = np.flatnonzero(~nz_mask[:, jm]), np.flatnonzero(~nz_mask[im, :])
+            if zi.size and zj.size:
+                cand = (int(zi[0]), int(zi[-1]) + 1, int(zj[0]), int(zj[-1]) + 1)
+                if not nz_mask[cand[0]:cand[1], cand[2]:cand[3]].any():
+                    return cand
+        return (0, 0, 0, 0)
+
+    def enforce_raw(self, state, field_properties=None):
+        """All fields with a reference value in one launch over the frame where gamma != 0
+        (``tb200_relax_frame``) instead of one full-box ``irelax`` per field; TB200_RELAX=full
+        keeps the per-field path (bit-identical, tests/test_gpu_stencils.py)."""
+        if os.environ.get("TB200_RELAX", "frame") != "frame":
+            return super().enforce_raw(state, field_properties)
+        ref = self.reference_state
+        names = [n for n in state if n != "time" and n in ref
+                 and (field_properties is None or n in field_properties)]
+        if not names:
+            return
+        import ctypes as C
+
+        box = (C.c_int32 * 4)(*self._free_box)
+        gamma = lib.as_field(self._gamma2d)
+        for lo in range(0, len(names), 8):
+            chunk = names[lo:lo + 8]
+            phi = [lib.as_field(state[n]) for n in chunk]
+            refs = [lib.as_field(ref[n]) for n in chunk]
+            ext = (C.c_int32 * (3 * len(chunk)))(
+                *[v for n in chunk for v in _extent(self.nx, self.ny, self.nz, n)])
+            lib.check(lib.load().tb200_relax_frame(
+                len(chunk), (lib.FieldP * len(chunk))(*[C.pointer(f) for f in phi]),
+                (lib.FieldP * len(chunk))(*[C.pointer(f) for f in refs]), gamma, ext, box,
+                lib.current_stream()), "tb200_relax_frame")
 
     def _outermost(self, axis, field, field_name):
         mi, mj, _ = _extent(self.nx, self.ny, self.nz, field_name)

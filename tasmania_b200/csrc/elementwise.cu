@@ -167,6 +167,102 @@ extern "C" int tb200_relax(const tb200_field *in_gamma, const tb200_field *in_ph
                     });
 }
 
+// Relaxed.enforce_raw in one launch over the boundary FRAME.  The reference relaxes every field
+// with its own full-box `irelax` call (horizontal_boundary.py:L299-L344 -> relaxed.py:L119-L137)
+// although gamma is zero -- and the point left untouched -- everywhere but on the nr outer rings
+// (and the staggered extra row / column).  Here the host passes the largest box [i_lo, i_hi) x
+// [j_lo, j_hi) on which gamma vanishes; the launch covers only its complement (west and east
+// slabs over all rows, south and north slabs between them) for all fields at once: <10 % of the
+// points, one launch instead of one per field.  Same point formula (relax_point): same bits.
+namespace {
+struct FrameFields {
+  View phi[TB200_FMA_MAX_FIELDS], ref[TB200_FMA_MAX_FIELDS];
+  int mi[TB200_FMA_MAX_FIELDS], mj[TB200_FMA_MAX_FIELDS], mk[TB200_FMA_MAX_FIELDS];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) relax_frame_kernel(const FrameFields ff, const View g, int i_lo,
+                                                          int i_hi, int j_lo, int j_hi, int mi, int mj,
+                                                          int mk) {
+  const int w_e = mi - i_hi, w_c = i_hi - i_lo, h_n = mj - j_hi;
+  const long long n_w = (long long)i_lo * mj, n_e = (long long)w_e * mj;
+  const long long n_s = (long long)w_c * j_lo, n_n = (long long)w_c * h_n;
+  const long long total = n_w + n_e + n_s + n_n;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    int i, j;
+    if (p < n_w) {
+      j = (int)(p / i_lo);
+      i = (int)(p - (long long)j * i_lo);
+    } else if (p < n_w + n_e) {
+      const long long q = p - n_w;
+      j = (int)(q / w_e);
+      i = i_hi + (int)(q - (long long)j * w_e);
+    } else if (p < n_w + n_e + n_s) {
+      const long long q = p - n_w - n_e;
+      j = (int)(q / w_c);
+      i = i_lo + (int)(q - (long long)j * w_c);
+    } else {
+      const long long q = p - n_w - n_e - n_s;
+      j = (int)(q / w_c);
+      i = i_lo + (int)(q - (long long)j * w_c);
+      j += j_hi;
+    }
+    const double gam = g(i, j, 0);
+    if (gam == 0.0) continue;
+    for (int k = blockIdx.y; k < mk; k += gridDim.y) {
+#pragma unroll
+      for (int n = 0; n < TB200_FMA_MAX_FIELDS; ++n) {
+        if (n < ff.n && i < ff.mi[n] && j < ff.mj[n] && k < ff.mk[n])
+          ff.phi[n](i, j, k) = relax_point(gam, ff.phi[n](i, j, k), ff.ref[n](i, j, k));
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int tb200_relax_frame(int nfields, tb200_field *const *phi,
+                                 const tb200_field *const *phi_ref, const tb200_field *gamma,
+                                 const int32_t *extents, const int32_t interior[4], void *stream) {
+  TB200_REQUIRE(phi != nullptr && phi_ref != nullptr && extents != nullptr && interior != nullptr,
+                "relax_frame: NULL argument");
+  TB200_REQUIRE(nfields >= 1 && nfields <= TB200_FMA_MAX_FIELDS, "relax_frame: 1..%d fields, got %d",
+                TB200_FMA_MAX_FIELDS, nfields);
+  const View g = view(gamma);
+  TB200_REQUIRE(g.ok(), "relax_frame: NULL gamma");
+  FrameFields ff{};
+  ff.n = nfields;
+  int mi = 0, mj = 0, mk = 0;
+  const int32_t o[3] = {0, 0, 0};
+  for (int n = 0; n < nfields; ++n) {
+    ff.phi[n] = view(phi[n]);
+    ff.ref[n] = view(phi_ref[n]);
+    const int32_t *d = extents + 3 * n;
+    TB200_REQUIRE(box_inside(ff.phi[n], o, d), "relax_frame: extent outside storage of field %d", n);
+    TB200_REQUIRE(box_inside(ff.ref[n], o, d), "relax_frame: extent outside reference field %d", n);
+    ff.mi[n] = d[0];
+    ff.mj[n] = d[1];
+    ff.mk[n] = d[2];
+    mi = d[0] > mi ? d[0] : mi;
+    mj = d[1] > mj ? d[1] : mj;
+    mk = d[2] > mk ? d[2] : mk;
+  }
+  TB200_REQUIRE(mi <= g.n0 && mj <= g.n1, "relax_frame: gamma smaller than the field extents");
+  // clip the gamma-free box into the launch extent
+  const int i_lo = interior[0] < 0 ? 0 : (interior[0] > mi ? mi : interior[0]);
+  const int i_hi = interior[1] < i_lo ? i_lo : (interior[1] > mi ? mi : interior[1]);
+  const int j_lo = interior[2] < 0 ? 0 : (interior[2] > mj ? mj : interior[2]);
+  const int j_hi = interior[3] < j_lo ? j_lo : (interior[3] > mj ? mj : interior[3]);
+  const long long total = (long long)(i_lo + mi - i_hi) * mj + (long long)(i_hi - i_lo) * (j_lo + mj - j_hi);
+  if (total <= 0 || mk <= 0) return TB200_OK;
+  const long long blocks = (total + 255) / 256;
+  dim3 block(256, 1, 1);
+  dim3 grid((unsigned)(blocks > 2048 ? 2048 : blocks), (unsigned)(mk > 65535 ? 65535 : mk), 1);
+  relax_frame_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(ff, g, i_lo, i_hi, j_lo,
+                                                                             j_hi, mi, mj, mk);
+  return check_launch("relax_frame");
+}
+
 // Periodic.enforce_field: x wrap on rows [nb, my+nb), then y wrap over [0, mi)
 extern "C" int tb200_periodic_enforce(tb200_field *field, int nx, int ny, int nb, int mx,
                                       int my, void *stream) {

@@ -58,6 +58,7 @@ SIGNATURES = {
     "tb200_elementwise": [_I, _F, _F, _F, _F, _D, _I3, _I3, _V],
     "tb200_fma_fields": [_I, _FPP, _FPP, _FPP, _D, _I3, _I3, _V],
     "tb200_relax": [_F, _F, _F, _F, _I3, _I3, _V],
+    "tb200_relax_frame": [_I, _FPP, _FPP, _F, _I3, _I3, _V],
     "tb200_periodic_enforce": [_F, _I, _I, _I, _I, _I, _V],
     "tb200_set_outermost_layers": [_F, _F, _I, _I, _I, _V],
     "tb200_damping": [_F, _F, _F, _F, _F, _D, _I3, _I3, _V],
