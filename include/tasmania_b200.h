@@ -290,6 +290,20 @@ int tb200_vertical_advection(int flux_scheme, int staggered_w, const tb200_field
                              double dz, uint32_t overwrite_flags, const int32_t origin[3],
                              const int32_t domain[3], void *stream);
 
+/* One stage of a tendency stepper around the vertical advection in ONE kernel:
+ * out[f] = base[f] + factor * tendency[f](in) on the whole output storage, i.e.
+ * tb200_vertical_advection followed by the stage update of
+ * src/tasmania/framework/subclasses/tendency_steppers/{forward_euler,rk2,rk3ws}.py
+ * (DataArrayDictOperator.fma, src/tasmania/utils/xarrayx.py:L688-L740) without the round trip of
+ * the tendencies through memory.  in / base / out = s, su, sv[, qv, qc, qr]; nfields 3 or 6;
+ * outputs must alias neither inputs nor base fields (base may alias in). */
+int tb200_vertical_advection_step(int flux_scheme, int staggered_w, const tb200_field *in_w,
+                                  int nfields, const tb200_field *const *in,
+                                  const tb200_field *const *base, tb200_field *const *out,
+                                  double dz, double factor, const int32_t origin[3],
+                                  const int32_t domain[3], void *stream);
+
+
 /* ---- implicit (Crank-Nicolson) vertical advection:
  * src/tasmania/isentropic/physics/implicit_vertical_advection.py:L221-L336 with setup_thomas and
  * thomas of src/tasmania/framework/subclasses/subroutine_definitions/cla.py:L42-L108.

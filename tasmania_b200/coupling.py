@@ -26,6 +26,8 @@ touches the host: the whole physics suite of the moist benchmark runs as a strea
 """
 from __future__ import annotations
 
+import os
+
 from tasmania_b200 import stencils
 from tasmania_b200.dwarfs import HorizontalSmoothing, HorizontalVelocity
 from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
@@ -296,6 +298,33 @@ class TendencyStepper(StencilFactory):
                 if self._hb is not None:
                     break
         self._increment, self._diagnostics = {}, {}
+        # b200: a lone tendency component that can apply the stage update itself
+        # (``array_call_stepped``: out = base + factor * tendency in the tendency kernel) spares
+        # the round trip of the tendencies through memory.  Stages read the previous stage's
+        # output, so a second set of stage buffers alternates with out_state (the last stage
+        # writes out_state).  TB200_FUSED_STEP=0 keeps the generic tendencies + fma path.
+        lone = components[0] if len(components) == 1 else None
+        self._fused = (lone if lone is not None and getattr(lone, "kind", None) == "tendency"
+                       and hasattr(lone, "array_call_stepped") and not lone.diagnostic_names
+                       and os.environ.get("TB200_FUSED_STEP", "1") != "0" else None)
+        self._stage_buffers = {}
+
+    def _call_fused(self, state, timestep, out_state, names):
+        dt = timestep.total_seconds()
+        if len(self._factors) > 1:
+            for n in names:
+                if n not in self._stage_buffers:
+                    self._stage_buffers[n] = self.zeros(shape=state[n].shape)
+        nst = len(self._factors)
+        cur = state
+        for stage, c in enumerate(self._factors):
+            dst = out_state if (nst - 1 - stage) % 2 == 0 else self._stage_buffers
+            self._fused.array_call_stepped(cur, state, c * dt, dst)
+            if self._hb is not None:
+                self._hb.enforce_raw(dst, {n: {} for n in names})
+            if stage < nst - 1:
+                cur = dict(state)
+                cur.update({n: dst[n] for n in names})
 
     def output_names(self, state):
         return tuple(n for n in self.prognostic.tendency_names if n in state)
@@ -307,6 +336,11 @@ class TendencyStepper(StencilFactory):
         for n in names:
             if n not in out_state:
                 out_state[n] = self.zeros(shape=state[n].shape)
+        if self._fused is not None and set(names) == set(self._fused.tendency_names):
+            self._call_fused(state, timestep, out_state, names)
+            if "time" in state:
+                out_state["time"] = state["time"] + timestep
+            return out_diagnostics, out_state
         dt = timestep.total_seconds()
         cur = state
         for stage, c in enumerate(self._factors):

@@ -65,6 +65,8 @@ struct VFlux<TB200_FLUX_FIFTH_ORDER_UPWIND> {  // fifth_order_upwind.py:L31-L42
 struct VAdvArgs {
   View w, s, su, sv, qv, qc, qr;
   View out[6];   // s, su, sv, qv, qc, qr
+  View base[6];  // stepped mode: out = base + factor * tendency (one stage of a tendency stepper)
+  double factor;
   bool ow[6];
   int nout;      // 3 dry, 6 moist
   bool staggered;
@@ -73,7 +75,7 @@ struct VAdvArgs {
   int i0, j0, k0, di, dj, dk;
 };
 
-template <int SCHEME>
+template <int SCHEME, bool STEP>
 __global__ void __launch_bounds__(256) vadv_kernel(const VAdvArgs a, int n0, int n1, int n2) {
   using F = VFlux<SCHEME>;
   constexpr int E = F::extent;
@@ -116,19 +118,25 @@ __global__ void __launch_bounds__(256) vadv_kernel(const VAdvArgs a, int n0, int
     }
     for (int f = 0; f < a.nout; ++f) {
       double &o = a.out[f](i, j, k);
-      o = a.ow[f] ? tnd[f] : o + tnd[f];  // generics.py:L38-L40, on the whole storage
+      if (STEP)  // DataArrayDictOperator.fma of the stepper stage, math.py:L59-L63, same storage box
+        o = a.base[f].ld(i, j, k) + a.factor * tnd[f];
+      else
+        o = a.ow[f] ? tnd[f] : o + tnd[f];  // generics.py:L38-L40, on the whole storage
     }
   }
 }
 
 template <int SCHEME>
-int run_vadv(const VAdvArgs &a, cudaStream_t st) {
+int run_vadv(const VAdvArgs &a, bool step, cudaStream_t st) {
   const View &o = a.out[0];
   if (o.n0 <= 0 || o.n1 <= 0 || o.n2 <= 0) return TB200_OK;
   dim3 block(64, 4, 1);
   dim3 grid((o.n0 + 63) / 64, (o.n1 + 3) / 4, o.n2 > 65535 ? 65535 : o.n2);
-  vadv_kernel<SCHEME><<<grid, block, 0, st>>>(a, o.n0, o.n1, o.n2);
-  return check_launch("vertical_advection");
+  if (step)
+    vadv_kernel<SCHEME, true><<<grid, block, 0, st>>>(a, o.n0, o.n1, o.n2);
+  else
+    vadv_kernel<SCHEME, false><<<grid, block, 0, st>>>(a, o.n0, o.n1, o.n2);
+  return check_launch(step ? "vertical_advection_step" : "vertical_advection");
 }
 
 }  // namespace
@@ -263,14 +271,16 @@ extern "C" int tb200_implicit_vertical_advection(
   return check_launch("implicit_vertical_advection");
 }
 
-extern "C" int tb200_vertical_advection(
+static int vadv_entry(
     int flux_scheme, int staggered_w, const tb200_field *in_w, const tb200_field *in_s,
     const tb200_field *in_su, const tb200_field *in_sv, tb200_field *out_s, tb200_field *out_su,
     tb200_field *out_sv, const tb200_field *in_qv, const tb200_field *in_qc,
     const tb200_field *in_qr, tb200_field *out_qv, tb200_field *out_qc, tb200_field *out_qr,
-    double dz, uint32_t overwrite_flags, const int32_t origin[3], const int32_t domain[3],
-    void *stream) {
+    double dz, uint32_t overwrite_flags, const tb200_field *const *base, double factor,
+    const int32_t origin[3], const int32_t domain[3], void *stream) {
   VAdvArgs a{};
+  const bool step = base != nullptr;
+  a.factor = factor;
   a.w = view(in_w); a.s = view(in_s); a.su = view(in_su); a.sv = view(in_sv);
   a.qv = view(in_qv); a.qc = view(in_qc); a.qr = view(in_qr);
   a.out[0] = view(out_s); a.out[1] = view(out_su); a.out[2] = view(out_sv);
@@ -301,6 +311,14 @@ extern "C" int tb200_vertical_advection(
                       box_inside(a.qr, origin, domain),
                   "vertical_advection: moist call needs in_qv, in_qc, in_qr covering the box");
   for (int f = 0; f < a.nout; ++f) {
+    if (step) {
+      a.base[f] = view(base[f]);
+      const int32_t o0[3] = {0, 0, 0};
+      const int32_t whole[3] = {a.out[f].n0, a.out[f].n1, a.out[f].n2};
+      TB200_REQUIRE(box_inside(a.base[f], o0, whole),
+                    "vertical_advection_step: a base storage is smaller than its output storage");
+      TB200_REQUIRE(a.out[f].p != a.base[f].p, "vertical_advection_step: outputs must not alias the base fields");
+    }
     TB200_REQUIRE(box_inside(a.out[f], origin, domain), "vertical_advection: box outside an output storage");
     TB200_REQUIRE(a.out[f].n0 == a.out[0].n0 && a.out[f].n1 == a.out[0].n1 && a.out[f].n2 == a.out[0].n2,
                   "vertical_advection: the output storages must share one shape");
@@ -311,9 +329,42 @@ extern "C" int tb200_vertical_advection(
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (flux_scheme) {
-    case TB200_FLUX_UPWIND: return run_vadv<TB200_FLUX_UPWIND>(a, st);
-    case TB200_FLUX_CENTERED: return run_vadv<TB200_FLUX_CENTERED>(a, st);
-    case TB200_FLUX_THIRD_ORDER_UPWIND: return run_vadv<TB200_FLUX_THIRD_ORDER_UPWIND>(a, st);
-    default: return run_vadv<TB200_FLUX_FIFTH_ORDER_UPWIND>(a, st);
+    case TB200_FLUX_UPWIND: return run_vadv<TB200_FLUX_UPWIND>(a, step, st);
+    case TB200_FLUX_CENTERED: return run_vadv<TB200_FLUX_CENTERED>(a, step, st);
+    case TB200_FLUX_THIRD_ORDER_UPWIND: return run_vadv<TB200_FLUX_THIRD_ORDER_UPWIND>(a, step, st);
+    default: return run_vadv<TB200_FLUX_FIFTH_ORDER_UPWIND>(a, step, st);
   }
+}
+
+extern "C" int tb200_vertical_advection(
+    int flux_scheme, int staggered_w, const tb200_field *in_w, const tb200_field *in_s,
+    const tb200_field *in_su, const tb200_field *in_sv, tb200_field *out_s, tb200_field *out_su,
+    tb200_field *out_sv, const tb200_field *in_qv, const tb200_field *in_qc,
+    const tb200_field *in_qr, tb200_field *out_qv, tb200_field *out_qc, tb200_field *out_qr,
+    double dz, uint32_t overwrite_flags, const int32_t origin[3], const int32_t domain[3],
+    void *stream) {
+  return vadv_entry(flux_scheme, staggered_w, in_w, in_s, in_su, in_sv, out_s, out_su, out_sv, in_qv,
+                    in_qc, in_qr, out_qv, out_qc, out_qr, dz, overwrite_flags, nullptr, 0.0, origin,
+                    domain, stream);
+}
+
+// One stage of a tendency stepper around the vertical advection in one kernel: the tendencies of
+// `in` are formed exactly as above and out[f] = base[f] + factor * tendency[f] on the whole output
+// storage -- what tb200_vertical_advection followed by DataArrayDictOperator.fma
+// (src/tasmania/utils/xarrayx.py:L688-L740) computes, without writing and re-reading the
+// tendencies.  in / base / out: s, su, sv[, qv, qc, qr] (nfields = 3 or 6).
+extern "C" int tb200_vertical_advection_step(
+    int flux_scheme, int staggered_w, const tb200_field *in_w, int nfields,
+    const tb200_field *const *in, const tb200_field *const *base, tb200_field *const *out, double dz,
+    double factor, const int32_t origin[3], const int32_t domain[3], void *stream) {
+  TB200_REQUIRE(in != nullptr && base != nullptr && out != nullptr, "vertical_advection_step: NULL argument");
+  TB200_REQUIRE(nfields == 3 || nfields == 6, "vertical_advection_step: 3 or 6 fields, got %d", nfields);
+  for (int f = 0; f < nfields; ++f)
+    TB200_REQUIRE(in[f] != nullptr && base[f] != nullptr && out[f] != nullptr,
+                  "vertical_advection_step: NULL field %d", f);
+  const bool m = nfields == 6;
+  return vadv_entry(flux_scheme, staggered_w, in_w, in[0], in[1], in[2], out[0], out[1], out[2],
+                    m ? in[3] : nullptr, m ? in[4] : nullptr, m ? in[5] : nullptr, m ? out[3] : nullptr,
+                    m ? out[4] : nullptr, m ? out[5] : nullptr, dz, 0u, base, factor, origin, domain,
+                    stream);
 }

@@ -54,6 +54,7 @@ class IsentropicVerticalAdvection(StencilFactory):
             "staggering": self._stgz,
         }
         self._stencil = self.compile_stencil("stencil")
+        self._stencil_step = self.compile_stencil("vertical_advection_step")
         self.tendency_names = (S, SU, SV) + ((MFWV, MFCW, MFPW) if moist else ())
 
     kind, diagnostic_names = "tendency", ()
@@ -75,6 +76,17 @@ class IsentropicVerticalAdvection(StencilFactory):
                 args["out_" + key] = out_tendencies[name]
                 args["ow_out_" + key] = ow.get(name, True)
         self._stencil(**args, origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))
+
+
+    def array_call_stepped(self, state, base, factor, out_state):
+        """b200 only -- one stage of a tendency stepper in one kernel: out_state[n] = base[n] +
+        factor * tendency[n](state) for the advected fields (tasmania_b200.coupling.TendencyStepper
+        uses it instead of ``array_call`` + ``fma``)."""
+        g, names = self.grid, self.tendency_names
+        self._stencil_step(in_w=state[W_HL] if self._stgz else state[W_ML],
+                           ins=[state[n] for n in names], bases=[base[n] for n in names],
+                           outs=[out_state[n] for n in names], dz=g.dz, factor=factor,
+                           origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))
 
 
 class IsentropicConservativeCoriolis(StencilFactory):

@@ -525,6 +525,25 @@ def vertical_advection_b200(
           q[0], q[1], q[2], q[3], q[4], q[5], float(dz), flags, _i3(origin), _i3(domain), _stream())
 
 
+@stencil_definition("vertical_advection_step")
+def vertical_advection_step_b200(externals, *, in_w, ins, bases, outs, dz, factor, origin, domain):
+    """b200 only: the vertical advection stencil fused with the stage update of a tendency stepper,
+    outs[f] = bases[f] + factor * tendency[f](ins) (``tb200_vertical_advection_step``).  Same
+    externals as ``vertical_advection``; ins / bases / outs = s, su, sv[, qv, qc, qr]."""
+    n = 6 if bool(externals.get("moist", False)) else 3
+    if not (len(ins) == len(bases) == len(outs) == n):
+        raise lib.B200Error(f"vertical_advection_step: {n} fields expected in ins, bases and outs")
+    keep, arrs = [], []
+    for group in (ins, bases, outs):
+        k = [_f(x) for x in group]
+        keep.append(k)
+        arrs.append((lib.FieldP * n)(*[C.pointer(x) for x in k]))
+    _call("tb200_vertical_advection_step", _vflux_code(externals),
+          int(bool(externals.get("staggering", False))), _f(in_w), n, arrs[0], arrs[1], arrs[2],
+          float(dz), float(factor), _i3(origin), _i3(domain), _stream())
+    del keep
+
+
 @stencil_definition("implicit_vertical_advection")
 def implicit_vertical_advection_b200(
     externals, *, in_w, in_s, in_su, in_sv, out_s, out_su, out_sv, in_qv=None, in_qc=None,

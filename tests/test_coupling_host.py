@@ -147,11 +147,14 @@ def test_moist_model_host_path_end_to_end():
         # (2), vertical advection rk3ws (3), sedimentation rk3ws (3)
         assert per_step["tb200_coriolis"] == 2 and per_step["tb200_smagorinsky"] == 2
         assert per_step["tb200_kessler"] == 2 and per_step["tb200_saturation_prognostic"] == 2
-        assert per_step["tb200_vertical_advection"] == 3 and per_step["tb200_sedimentation"] == 3
+        # (the vertical advection applies its stage update itself: no tendencies + fma round trip)
+        assert per_step["tb200_vertical_advection_step"] == 3 and per_step["tb200_sedimentation"] == 3
+        assert "tb200_vertical_advection" not in per_step
         assert per_step["tb200_fall_velocity"] == 4          # 3 sedimentation stages + precipitation
         assert per_step["tb200_accumulated_precipitation"] == 1
         assert per_step["tb200_smoothing"] == 6              # s, su, sv, qv, qc, qr
-        assert per_step["tb200_fma_fields"] == 14            # one per stepper stage
+        assert per_step["tb200_fma_fields"] == 11            # one per remaining stepper stage
+        assert per_step["tb200_relax_frame"] == 3            # one per dycore stage, all 8 fields
         assert per_step["tb200_diagnostic_variables"] == 1
         assert per_step["tb200_density_and_temperature"] == 1
         assert per_step["tb200_step_forward_euler"] == 3     # moist dycore, three RK stages
@@ -159,7 +162,7 @@ def test_moist_model_host_path_end_to_end():
         first = {n: calls.index(n) for n in per_step}
         order = ["tb200_step_forward_euler", "tb200_diagnostic_variables", "tb200_coriolis",
                  "tb200_smoothing", "tb200_smagorinsky", "tb200_kessler",
-                 "tb200_saturation_prognostic", "tb200_vertical_advection", "tb200_sedimentation",
+                 "tb200_saturation_prognostic", "tb200_vertical_advection_step", "tb200_sedimentation",
                  "tb200_accumulated_precipitation"]
         assert [first[n] for n in order] == sorted(first[n] for n in order)
         names1 = set(model.state)
@@ -184,3 +187,43 @@ def test_moist_model_host_path_end_to_end():
         assert set(model.state) == names1
         assert len(ids2) == len(names1) - 1                  # no array sits under two names
         assert model.state["time"] == datetime(1992, 2, 20) + 4 * timedelta(seconds=5)
+
+
+def test_fused_stage_update_alternates_stage_buffers(monkeypatch):
+    """A lone component with ``array_call_stepped`` replaces tendencies + fma; every stage reads
+    the previous stage's output and the last one writes ``out_state``; TB200_FUSED_STEP=0 turns
+    the fusion off.  Checked on numbers against the oracle scheme."""
+    import tasmania_b200 as tb
+    from tasmania_b200.coupling import TendencyStepper
+
+    class FusableDecay(Decay):
+        diagnostic_names = ()
+        stepped_calls = 0
+
+        def array_call(self, state, out_tendencies, out_diagnostics, overwrite_tendencies):
+            for n in self.tendency_names:
+                out_tendencies[n].t.copy_(-self.rate * state[n].t)
+
+        def array_call_stepped(self, state, base, factor, out_state):
+            self.stepped_calls += 1
+            for n in self.tendency_names:
+                assert out_state[n] is not state[n] and out_state[n] is not base[n]
+                out_state[n].t.copy_(base[n].t + factor * (-self.rate * state[n].t))
+
+    y0 = np.random.default_rng(9).standard_normal((4, 3, 2))
+    dt = timedelta(seconds=0.3)
+    for scheme in ("forward_euler", "rk2", "rk3ws"):
+        _, want = mm.tendency_step(scheme, {"y": y0}, lambda st: ({"y": -0.7 * st["y"]}, {}),
+                                   dt.total_seconds())
+        for fused in (True, False):
+            monkeypatch.setenv("TB200_FUSED_STEP", "1" if fused else "0")
+            with stubbed_library() as stub:
+                comp = FusableDecay(0.7)
+                stepper = TendencyStepper.factory(scheme, comp)
+                state = {"y": tb.as_storage(y0)}
+                _, out = stepper(state, dt)
+                nst = len(TendencyStepper.SCHEMES[scheme])
+                assert comp.stepped_calls == (nst if fused else 0)
+                assert stub.count("tb200_fma_fields") == (0 if fused else nst)
+                np.testing.assert_array_equal(tb.to_numpy(out["y"]), want["y"])
+                np.testing.assert_array_equal(tb.to_numpy(state["y"]), y0)

@@ -91,3 +91,59 @@ def test_moist_model_vs_oracle(dims, nsteps):
     box = (slice(0, nx), slice(0, ny), slice(0, nz))
     assert float(ost[mm.QC][box].max()) > 1e-5 and float(ost[mm.QR][box].max()) > 1e-5
     assert float(ost[mm.ACCPREC].max()) > 0.0 and float(np.abs(ost[mm.W][box]).max()) > 0.0
+
+
+@pytest.mark.parametrize("scheme", ["upwind", "centered", "third_order_upwind", "fifth_order_upwind"])
+@pytest.mark.parametrize("moist", [False, True])
+def test_vertical_advection_step_is_advection_plus_fma_bitwise(scheme, moist):
+    """``tb200_vertical_advection_step`` (tendency kernel + stage update in one) against the
+    tendencies of ``tb200_vertical_advection`` followed by ``base + factor * tendency`` in numpy."""
+    import tasmania_b200 as tb
+    from tasmania_b200.grid import Grid
+    from tasmania_b200.isentropic_physics import IsentropicVerticalAdvection, W_ML
+
+    rng = np.random.default_rng(21)
+    nx, ny, nz = 19, 11, 16
+    grid = Grid((0.0, 1.0), nx, (0.0, 1.0), ny, (340.0, 280.0), nz)
+    shape = (nx + 1, ny + 1, nz + 1)
+    comp = IsentropicVerticalAdvection(grid, flux_scheme=scheme, moist=moist)
+    names = comp.tendency_names
+    host = {n: rng.uniform(0.5, 2.0, shape) for n in names}
+    host[W_ML] = rng.standard_normal(shape) * 1e-2
+    base = {n: rng.standard_normal(shape) for n in names}
+    state = {n: tb.as_storage(v) for n, v in host.items()}
+    dbase = {n: tb.as_storage(v) for n, v in base.items()}
+    tnd = {n: tb.as_storage(rng.standard_normal(shape)) for n in names}  # garbage: overwritten
+    comp.array_call(state, tnd, {}, {n: True for n in names})
+    out = {n: tb.as_storage(rng.standard_normal(shape)) for n in names}
+    factor = 5.0 / 3.0
+    comp.array_call_stepped(state, dbase, factor, out)
+    for n in names:
+        np.testing.assert_array_equal(tb.to_numpy(out[n]), base[n] + factor * tb.to_numpy(tnd[n]),
+                                      err_msg=n)
+    with pytest.raises(tb.lib.B200Error):  # outputs must not alias the inputs
+        comp.array_call_stepped(state, dbase, factor, state)
+
+
+def test_fused_paths_equal_the_reference_shaped_paths_bitwise(monkeypatch):
+    """Moist model with the b200 fusions (stage update inside the vertical advection kernel, frame
+    relaxation of all fields in one launch) against the same model issuing the reference's call
+    sequence (tendencies + fma, one full-box irelax per field): identical bits."""
+    import tasmania_b200 as tb
+    from tasmania_b200.isentropic_moist import IsentropicMoistSUS
+    from tests import helpers as hp
+
+    nx, ny, nz, nsteps = 33, 29, 14, 5
+    res = []
+    for fused in (True, False):
+        monkeypatch.setenv("TB200_FUSED_STEP", "1" if fused else "0")
+        monkeypatch.setenv("TB200_RELAX", "frame" if fused else "full")
+        grid, np_state = hp.moist_case(nx, ny, nz)
+        model = IsentropicMoistSUS(grid, np_state, timedelta(seconds=5), damp_depth=4)
+        n0 = tb.lib.launch_count()
+        model.run(nsteps)
+        res.append(({n: tb.to_numpy(v) for n, v in model.state.items() if n != "time"},
+                    (tb.lib.launch_count() - n0) / nsteps))
+    assert res[0][1] < res[1][1] - 20  # 3 fma + 21 relax launches fewer per step
+    for n, v in res[1][0].items():
+        np.testing.assert_array_equal(res[0][0][n], v, err_msg=n)
