@@ -23,9 +23,13 @@ the reference's coupling classes do at the raw-array level:
 Deliberately written without coupler classes (the product mirrors the reference's class structure
 in tasmania_b200/coupling.py; this file spells the resulting sequence out), so that the two are
 independent statements of the same thing.  The stencils it calls are the oracle functions pinned
-bit for bit on the reference's numpy definitions (tests/test_oracle_golden.py).  PARITY OF THE
-COUPLING ORDER IS UNPINNED BY EXECUTION: the reference's couplers need sympl / xarray / pint and
-cannot run here; this file follows them by reading, line references above.
+bit for bit on the reference's numpy definitions (tests/test_oracle_golden.py), and
+``tendency_step`` is pinned bit for bit on the reference's own ForwardEuler / RK2 / RK3WS ``_call``
+methods executed in place (tests/test_coupling_reference.py, which also runs the reference's
+ConcurrentCoupling._call_serial, promoters and SequentialUpdateSplitting.__call__ against the b200
+mirrors).  UNPINNED BY EXECUTION: the component list and order of the benchmark driver (a script
+over sympl objects that cannot run here); ``physics`` follows it by reading,
+line references above.
 """
 from __future__ import annotations
 
