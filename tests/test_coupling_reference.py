@@ -253,3 +253,30 @@ def test_reference_sequential_update_splitting_equals_b200():
         np.testing.assert_array_equal(tb.to_numpy(dstate["y"]), state["y"].data)
         np.testing.assert_array_equal(tb.to_numpy(dstate["seen"]), state["seen"].data)
         assert dstate["time"] == state["time"]
+
+
+# ------------------------------------------------------------------ moist initial state
+def test_moist_initial_state_equals_reference():
+    """tasmania_b200.grid.isentropic_state_from_brunt_vaisala(moist=True) restates host-side set-up
+    (src/tasmania/isentropic/state.py:L126-L391, utils/meteo.py:L192-L274); here against the
+    reference's own function run in place: every field bit for bit."""
+    from tasmania_b200.grid import Grid, Topography, gaussian_profile, isentropic_state_from_brunt_vaisala
+    from tests.golden import generate_golden as gg
+
+    nx, ny, nz = 21, 19, 10
+    d = gg._make_domain(nx, ny, nz, "relaxed", 3, {"nr": 6}, topo_time=60.0)
+    st = ref("tasmania.isentropic.state")
+    shape = (nx + 1, ny + 1, nz + 1)
+    want = st.get_isentropic_state_from_brunt_vaisala_frequency(
+        d.numerical_grid, datetime(2000, 1, 1), gg.da(22.5, "m s^-1"), gg.da(0.0, "m s^-1"),
+        gg.da(0.015, "s^-1"), moist=True, precipitation=True, relative_humidity=0.95, backend="numpy",
+        storage_shape=shape)
+    x, y = np.linspace(-176.0, 176.0, nx), np.linspace(-176.0, 176.0, ny)
+    grid = Grid((-176.0, 176.0), nx, (-176.0, 176.0), ny, (400.0, 280.0), nz, units_to_m=1e3,
+                topography=Topography(gaussian_profile(x, y, 500.0, 50.0, 50.0), timedelta(seconds=60)))
+    got = isentropic_state_from_brunt_vaisala(grid, 22.5, 0.0, 0.015, moist=True, precipitation=True,
+                                              relative_humidity=0.95)
+    assert set(got) == set(want) - {"time"}
+    for n, v in got.items():
+        np.testing.assert_array_equal(v, np.asarray(want[n].data), err_msg=n)
+    assert float(got["mass_fraction_of_water_vapor_in_air"].max()) > 1e-3
