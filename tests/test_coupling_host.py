@@ -227,3 +227,40 @@ def test_fused_stage_update_alternates_stage_buffers(monkeypatch):
                 assert stub.count("tb200_fma_fields") == (0 if fused else nst)
                 np.testing.assert_array_equal(tb.to_numpy(out["y"]), want["y"])
                 np.testing.assert_array_equal(tb.to_numpy(state["y"]), y0)
+
+
+def test_as_parallel_policy_components_do_not_see_each_other():
+    """``as_parallel`` (concurrent_coupling.py:L376-L423): every component gets the input state,
+    diagnostics of one are not visible to the next, tendency -> diagnostic promoters are skipped."""
+    import tasmania_b200 as tb
+    from tasmania_b200.coupling import ConcurrentCoupling, FromTendencyToDiagnostic
+    from tasmania_b200.grid import Grid
+
+    class Diag:
+        kind, tendency_names, diagnostic_names = "diagnostic", (), ("d",)
+
+        def diagnostic_shape(self, name):
+            return (4, 3, 2)
+
+        def array_call(self, state, out):
+            out["d"].t.copy_(state["y"].t + 1.0)
+
+    class UsesD:
+        kind, tendency_names, diagnostic_names = "tendency", ("y",), ()
+
+        def array_call(self, state, out_tendencies, out_diagnostics, overwrite_tendencies):
+            out_tendencies["y"].t.copy_(state["d"].t)
+
+    y0 = np.ones((4, 3, 2))
+    grid = Grid((0.0, 1.0), 3, (0.0, 1.0), 2, (300.0, 280.0), 1)
+    for policy, want in (("serial", 2.0), ("as_parallel", 7.0)):
+        with stubbed_library():
+            state = {"y": tb.as_storage(y0), "d": tb.as_storage(7.0 * y0)}
+            cc = ConcurrentCoupling(Diag(), UsesD(), FromTendencyToDiagnostic(grid, "y"),
+                                    execution_policy=policy)
+            tnd, diag = cc(state, timedelta(seconds=1))
+            np.testing.assert_array_equal(tb.to_numpy(tnd["y"]), want * y0)
+            promoted = tb.to_numpy(diag["tendency_of_y"])
+            assert (promoted[:3, :2, :1] == (want if policy == "serial" else 0.0)).all()
+    with pytest.raises(ValueError):
+        ConcurrentCoupling(Diag(), execution_policy="concurrent")
