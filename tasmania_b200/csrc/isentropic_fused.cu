@@ -1413,8 +1413,9 @@ int launch_a(const StageArgs &a, cudaStream_t st) {
 template <int SCHEME>
 int launch_mv(const StageArgs &a, cudaStream_t st) {
   const MvGeom g = mv_geom(a);
-  // the overlap parts of a decomposed run are laid out in blocks of 64-row strips
-  const int lj = a.part != 0 ? 64 : pick_lj((a.nx + g.cols - 1) / g.cols, a.ny, a.nz);
+  // the overlap parts of a decomposed run are laid out in blocks of 64-row strips; the earlier
+  // momentum kernels (TB200_MV_IMPL=window|ring) are kept as they were measured, at 64 rows
+  const int lj = (a.part != 0 || g.impl != 2) ? 64 : pick_lj((a.nx + g.cols - 1) / g.cols, a.ny, a.nz);
   if (lj == 16) return launch_mv_part<SCHEME, 16>(a, st);
   if (lj == 8) return launch_mv_part<SCHEME, 8>(a, st);
   return launch_mv_part<SCHEME, 64>(a, st);
