@@ -280,3 +280,33 @@ def test_moist_initial_state_equals_reference():
     for n, v in got.items():
         np.testing.assert_array_equal(v, np.asarray(want[n].data), err_msg=n)
     assert float(got["mass_fraction_of_water_vapor_in_air"].max()) > 1e-3
+
+
+def test_smoothing_with_boundary_layers_wider_than_the_stencil_equals_reference():
+    """The benchmark smooths with nb = 3 (the boundary's) under a second-order (5-point) smoother
+    (horizontal_smoothing.py:L113-L126 with second_order.py:L48); the reference's own smoother,
+    run in place, against the call the oracle's moist model makes."""
+    from oracle import dwarfs
+
+    hsm = ref("tasmania.dwarfs.horizontal_smoothing")
+    ref("tasmania.dwarfs.subclasses.horizontal_smoothers.second_order")
+    opts = ref("tasmania.framework.options")
+    shape, nb = (19, 17, 7), 3
+    phi = np.random.default_rng(4).standard_normal(shape)
+    obj = hsm.HorizontalSmoothing.factory(
+        "second_order", shape, 1.0, 1.0, 0, nb, backend="numpy",
+        backend_options=opts.BackendOptions(), storage_options=opts.StorageOptions())
+    want = np.zeros(shape)
+    obj(phi, want)
+    gamma = np.zeros(shape)
+    gamma[...] = dwarfs.vertical_profile(1.0, 1.0, 0, shape[2])[None, None, :]
+    np.testing.assert_array_equal(gamma, np.asarray(obj._gamma))
+    got = np.zeros(shape)
+    sx, sy, sz = shape
+    dwarfs.smoothing(2, phi, gamma, got, (nb, nb, 0), (sx - 2 * nb, sy - 2 * nb, sz))
+    for o, d in (((0, 0, 0), (nb, sy, sz)), ((sx - nb, 0, 0), (nb, sy, sz)),
+                 ((nb, 0, 0), (sx - 2 * nb, nb, sz)), ((nb, sy - nb, 0), (sx - 2 * nb, nb, sz))):
+        dwarfs.copy(phi, got, o, d)
+    np.testing.assert_array_equal(got, want)
+    assert not np.array_equal(want[nb:-nb, nb:-nb], phi[nb:-nb, nb:-nb])
+    np.testing.assert_array_equal(want[:nb], phi[:nb])
