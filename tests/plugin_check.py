@@ -107,6 +107,55 @@ for modname, clsname, stencil, fn in plugin._class_scoped_stencils():
     assert theirs <= ours, (clsname, stencil, sorted(theirs - ours))
     checked += 1
 assert checked >= 14, checked
+# ---- the reference's own objects issue the b200 ABI calls (recording stub: every call is
+# type-checked against the C signature; fma / copy are carried out on the host buffers)
+sys.path.insert(0, ROOT)
+from datetime import datetime, timedelta  # noqa: E402
+import types  # noqa: E402
+
+from tests.abi_stub import stubbed_library  # noqa: E402
+
+with stubbed_library() as stub:
+    phi = ta.as_storage("b200", data=np.random.default_rng(0).standard_normal((12, 11, 6)))
+    tnd = ta.zeros("b200", shape=(12, 11, 6))
+    hd(phi, tnd)  # tasmania.HorizontalDiffusion.__call__ -> compiled b200 stencil -> C ABI
+    assert stub.calls == ["tb200_diffusion"], stub.calls
+
+    # DataArrayDictOperator.fma of the unmodified reference on b200 storages
+    from tasmania.utils.xarrayx import DataArrayDictOperator  # noqa: E402
+
+    def da(arr, units="m"):
+        return refload.DataArray(arr, None, ("x", "y", "z"), None, {"units": units})
+
+    y0 = np.random.default_rng(1).standard_normal((5, 4, 3))
+    op = DataArrayDictOperator(backend="b200", backend_options=BackendOptions(),
+                               storage_options=StorageOptions())
+    out = {"y": da(ta.zeros("b200", shape=y0.shape))}
+    op.fma({"y": da(ta.as_storage("b200", data=y0))}, {"y": da(ta.as_storage("b200", data=2.0 * y0))},
+           0.25, out=out)
+    assert stub.calls[-1] == "tb200_elementwise"
+    assert np.array_equal(to_numpy(out["y"].data), y0 + 0.25 * (2.0 * y0))
+
+    # the reference's RK3WS tendency stepper logic (its own _call, unbound) on b200 storages
+    from tasmania.framework.subclasses.tendency_steppers.rk3ws import RK3WS  # noqa: E402
+
+    class Increment:
+        def get_increment(self, st, timestep, out_increment=None, out_diagnostics=None):
+            inc = ta.as_storage("b200", data=-0.7 * to_numpy(st["y"].data))
+            return {"y": da(inc), "time": st["time"]}, {}
+
+    fake = types.SimpleNamespace(_stepper_operator=Increment(), _dict_op=op, _enforce_hb=False,
+                                 _increment=None, _diagnostics=None,
+                                 output_properties={"y": {"units": "m", "dims": ("x", "y", "z")}})
+    state = {"y": da(ta.as_storage("b200", data=y0)), "time": datetime(2000, 1, 1)}
+    _, out_state = RK3WS._call(fake, state, timedelta(seconds=0.3), {},
+                               {"y": da(ta.zeros("b200", shape=y0.shape))})
+    z = 0.7 * 0.3
+    want = y0 + 0.3 * (-0.7 * (y0 + 0.5 * 0.3 * (-0.7 * (y0 + (1.0 / 3.0 * 0.3) * (-0.7 * y0)))))
+    assert np.array_equal(to_numpy(out_state["y"].data), want), np.abs(to_numpy(out_state["y"].data) - want).max()
+    assert abs(float(want.ravel()[0] / y0.ravel()[0]) - (1 - z + z * z / 2 - z**3 / 6)) < 1e-15
+    assert stub.count("tb200_elementwise") == 4
+
 print("PLUGIN-OK", len(report["global"]), len(report["class_scoped"]), len(report["skipped"]))
 for s in report["skipped"]:
     print("skipped:", s)
