@@ -18,3 +18,13 @@ def test_plugin_registers_into_the_reference():
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "PLUGIN-OK" in res.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
+                    reason="reference tree not mounted")
+def test_reference_dycore_on_b200_issues_the_mirror_call_sequence():
+    """north_star: "IsentropicDynamicalCore ... work unchanged" on the b200 backend."""
+    res = subprocess.run([sys.executable, os.path.join(HERE, "ref_dycore_check.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "REF-DYCORE-OK 42" in res.stdout
