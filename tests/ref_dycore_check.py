@@ -1,8 +1,8 @@
 # -*- coding: utf-8 -*-
 """Run by tests/test_plugin_reference.py in a subprocess.  The UNMODIFIED reference dynamical core --
-``IsentropicDynamicalCore.stage_array_call_dry`` (src/tasmania/isentropic/dynamics/dycore.py:L641-L721)
-with the reference's own Domain, Relaxed boundary, state builder, RK3WSSI prognostic, Rayleigh damper
-and HorizontalVelocity, all constructed with backend="b200" through the plugin -- is run for a full
+``IsentropicDynamicalCore.stage_array_call_dry`` and ``stage_array_call_moist``
+(src/tasmania/isentropic/dynamics/dycore.py:L641-L843) with the reference's own Domain, Relaxed boundary, state builder, RK3WSSI prognostic, Rayleigh damper
+HorizontalVelocity and WaterConstituent, all constructed with backend="b200" through the plugin -- is run for a full
 RK3WS step against the recording C-ABI stub (tests/abi_stub.py; storages on the host), and the
 sequence of ABI calls it issues (kernel, canonical buffer ids, scalars, boxes) is compared with the
 one the b200 host mirror (tasmania_b200.isentropic.IsentropicDynamicalCore, per-stencil path)
@@ -42,18 +42,20 @@ SCHEME, FLUX = "rk3ws_si", "fifth_order_upwind"
 SHAPE = (NX + 1, NY + 1, NZ + 1)
 DT = timedelta(seconds=5)
 OUTNAMES = (S, SU, U, SV, V)
+QNAMES = (gg.MFWV, gg.MFCW, gg.MFPW)
 
 
-def reference_trace(stub):
+def reference_trace(stub, moist):
     """One RK3WS step of the reference's own dycore stage on backend b200; returns the ABI trace,
     the initial state as numpy arrays and the model-top pressure."""
     from tasmania.framework import allocators as ta
     from tasmania.framework.generic_functions import to_numpy
 
+    DataArray = refload.DataArray
     dom = refload.load("tasmania.domain.domain")
     refload.load("tasmania.domain.subclasses.horizontal_boundaries.relaxed")
     refload.load("tasmania.domain.subclasses.topographies.gaussian")
-    da, DataArray = gg.da, refload.DataArray
+    da = gg.da
     domain = dom.Domain(
         DataArray([-176, 176], dims="x", attrs={"units": "km"}), NX,
         DataArray([-176, 176], dims="y", attrs={"units": "km"}), NY,
@@ -68,6 +70,12 @@ def reference_trace(stub):
         grid, datetime(2000, 1, 1), da(22.5, "m s^-1"), da(0.0, "m s^-1"), da(0.015, "s^-1"),
         moist=False, backend="b200", storage_shape=SHAPE)
     assert all(isinstance(v.data, tb.B200Array) for k, v in state.items() if k != "time")
+    if moist:  # seeded water species (like tests/golden/generate_golden.py does for the moist fixtures)
+        rng = np.random.default_rng(12)
+        for n, scale in zip(QNAMES, (8e-3, 1e-3, 5e-4)):
+            q = scale * rng.uniform(0.0, 1.0, SHAPE)
+            q[NX:, :, :] = q[:, NY:, :] = q[:, :, NZ:] = 0.0
+            state[n] = DataArray(ta.as_storage("b200", data=q), attrs={"units": "g g^-1"})
     hb = domain.horizontal_boundary
     hb.reference_state = state
     assert isinstance(hb._gamma, tb.B200Array)
@@ -84,7 +92,7 @@ def reference_trace(stub):
     bo, so = opts.BackendOptions, opts.StorageOptions
     pt = float(to_numpy(state[P].data)[0, 0, 0])
     prognostic = prog.IsentropicPrognostic.factory(
-        SCHEME, FLUX, domain, False, backend="b200", backend_options=bo(), storage_shape=SHAPE,
+        SCHEME, FLUX, domain, moist, backend="b200", backend_options=bo(), storage_shape=SHAPE,
         storage_options=so(), pt=da(pt, "Pa"), eps=0.5)
     damper = vd.VerticalDamping.factory("rayleigh", grid, 4, 5e-4, backend="b200", backend_options=bo(),
                                         storage_shape=SHAPE, storage_options=so())
@@ -94,28 +102,36 @@ def reference_trace(stub):
     def zeros():
         return ta.zeros("b200", shape=SHAPE)
 
-    # the attributes stage_array_call_dry reads from the dycore object
+    outnames = OUTNAMES + (QNAMES if moist else ())
+    water = {}
+    if moist:
+        water["_water_constituent"] = dd.WaterConstituent(
+            grid, clipping=True, backend="b200", backend_options=bo(), storage_options=so())
+        water.update({f"_{q}_{t}": zeros() for q in ("sqv", "sqc", "sqr") for t in ("now", "int", "new")})
+    # the attributes stage_array_call_dry / _moist read from the dycore object
     me = types.SimpleNamespace(
-        horizontal_boundary=hb,
-        output_properties={k: {"units": state[k].attrs["units"]} for k in OUTNAMES},
+        horizontal_boundary=hb, **water,
+        output_properties={k: {"units": state[k].attrs["units"]} for k in outnames},
         _damp=True, _damp_at_every_stage=True, stages=prognostic.stages, _prognostic=prognostic,
         _damper=damper, _velocity_components=velocity, _s_ref=zeros(), _su_ref=zeros(),
         _sv_ref=zeros(), _s_now=None, _su_now=None, _sv_now=None)
-    cur = {k: state[k].data for k in (S, MTG, SU, U, SV, V)}
+    cur = {k: state[k].data for k in (S, MTG, SU, U, SV, V) + (QNAMES if moist else ())}
     cur["time"] = state["time"]
-    outs = [{k: zeros() for k in OUTNAMES} for _ in range(prognostic.stages)]
+    outs = [{k: zeros() for k in outnames} for _ in range(prognostic.stages)]
+    stage_call = (dyc.IsentropicDynamicalCore.stage_array_call_moist if moist
+                  else dyc.IsentropicDynamicalCore.stage_array_call_dry)
     grid.update_topography(DT)
     stub.trace = []
     st_in = cur
     for stage in range(prognostic.stages):  # stage chaining of framework/dycore.py:L455-L458
-        dyc.IsentropicDynamicalCore.stage_array_call_dry(me, stage, st_in, {}, DT, outs[stage])
+        stage_call(me, stage, st_in, {}, DT, outs[stage])
         st_in = dict(outs[stage])
         st_in.setdefault(MTG, cur[MTG])
     trace, stub.trace = stub.trace, None
     return trace, {k: to_numpy(v.data) for k, v in state.items() if k != "time"}, pt
 
 
-def mirror_trace(stub, np_state, pt):
+def mirror_trace(stub, np_state, pt, moist):
     from tasmania_b200.boundary import Relaxed
     from tasmania_b200.grid import Grid, Topography, gaussian_profile
     from tasmania_b200.isentropic import IsentropicDynamicalCore
@@ -129,7 +145,7 @@ def mirror_trace(stub, np_state, pt):
     state["time"] = datetime(2000, 1, 1)
     hb.reference_state = state
     dycore = IsentropicDynamicalCore(
-        grid, hb, time_integration_scheme=SCHEME, horizontal_flux_scheme=FLUX,
+        grid, hb, moist=moist, time_integration_scheme=SCHEME, horizontal_flux_scheme=FLUX,
         time_integration_properties={"pt": pt, "eps": 0.5}, damp=True, damp_depth=4, damp_max=5e-4,
         fused=False)
     dycore.update_topography(DT)
@@ -168,17 +184,25 @@ def reduce(trace):
     return out
 
 
-with stubbed_library() as the_stub:
-    ref_trace, initial, p_top = reference_trace(the_stub)
-    counts = collections.Counter(n for n, _ in ref_trace)
+EXPECTED = {
     # per stage: K1, irelax(s), montgomery, K2, five irelax, three dampings, two velocity diagnoses
-    assert counts == {"tb200_relax": 18, "tb200_damping": 9, "tb200_velocity": 6,
-                      "tb200_step_forward_euler": 3, "tb200_montgomery": 3,
-                      "tb200_step_forward_euler_momentum": 3}, counts
-    mir_trace = mirror_trace(the_stub, initial, p_top)
-
-a, b = reduce(ref_trace), reduce(mir_trace)
-assert len(a) == len(b) == 42, (len(a), len(b))
-for n, (p, q) in enumerate(zip(a, b)):
-    assert p == q, (n, p, q)
-print("REF-DYCORE-OK", len(a))
+    False: {"tb200_relax": 18, "tb200_damping": 9, "tb200_velocity": 6, "tb200_step_forward_euler": 3,
+            "tb200_montgomery": 3, "tb200_step_forward_euler_momentum": 3},
+    # + sq = s q of the three species before, q = sq / s after, and their three relaxations
+    True: {"tb200_relax": 27, "tb200_damping": 9, "tb200_velocity": 6, "tb200_step_forward_euler": 3,
+           "tb200_montgomery": 3, "tb200_step_forward_euler_momentum": 3, "tb200_density": 9,
+           "tb200_mass_fraction": 9},
+}
+done = []
+for moist_case in (False, True):
+    with stubbed_library() as the_stub:
+        ref_trace, initial, p_top = reference_trace(the_stub, moist_case)
+        counts = collections.Counter(n for n, _ in ref_trace)
+        assert counts == EXPECTED[moist_case], counts
+        mir_trace = mirror_trace(the_stub, initial, p_top, moist_case)
+    a, b = reduce(ref_trace), reduce(mir_trace)
+    assert len(a) == len(b) == sum(EXPECTED[moist_case].values()), (len(a), len(b))
+    for n, (p, q) in enumerate(zip(a, b)):
+        assert p == q, (moist_case, n, p, q)
+    done.append(len(a))
+print("REF-DYCORE-OK", *done)

@@ -27,7 +27,7 @@ def test_reference_dycore_on_b200_issues_the_mirror_call_sequence():
     res = subprocess.run([sys.executable, os.path.join(HERE, "ref_dycore_check.py")],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "REF-DYCORE-OK 42" in res.stdout
+    assert "REF-DYCORE-OK 42 69" in res.stdout  # dry and moist stage sequences
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
