@@ -234,4 +234,33 @@ with stubbed_library() as stub:
     compare("IsentropicVelocityComponents", lambda: r.array_call(sr, dr), lambda: m.array_call(sm, dm),
             keep=("tb200_velocity",))
 
+    # ---- the Burgers dwarf (BASELINE configs[0]): the reference's RK3WS stepper, third-order advection
+    bst = refload.load("tasmania.burgers.dynamics.stepper")
+    refload.load("tasmania.burgers.dynamics.subclasses.stepper.rk3ws")
+    refload.load("tasmania.burgers.dynamics.subclasses.advection.third_order")
+    from tasmania_b200.burgers import BurgersStepper  # noqa: E402
+    from tasmania_b200.grid import Grid  # noqa: E402
+
+    bnx, bny, bnb = 21, 19, 2
+    bdomain = gg._make_domain(bnx, bny, 1, "relaxed", bnb, {"nr": 6}, topo=False)
+    r = bst.BurgersStepper.factory("rk3ws", bdomain.numerical_grid.grid_xy, bnb, "third_order",
+                                   backend="b200", backend_options=opts.BackendOptions(),
+                                   storage_options=opts.StorageOptions())
+    bgrid = Grid((-176.0, 176.0), bnx, (-176.0, 176.0), bny, (400.0, 280.0), 1, units_to_m=1e3)
+    m = BurgersStepper.factory("rk3ws", bgrid, bnb, "third_order")
+    assert r.stages == m.stages == 3
+    vel = {n: rng.standard_normal((bnx, bny, 1)) for n in ("x_velocity", "y_velocity")}
+
+    def burgers_step(stepper):
+        state = {n: tb.as_storage(v) for n, v in vel.items()}
+        state["time"] = datetime(2000, 1, 1)
+        outs = [{n: tb.zeros((bnx, bny, 1)) for n in vel} for _ in range(3)]
+        cur = state
+        for stage in range(3):
+            stepper(stage, cur, {}, DT, outs[stage])
+            cur = outs[stage]
+        assert cur["time"] == datetime(2000, 1, 1) + DT
+
+    compare("BurgersStepper", lambda: burgers_step(r), lambda: burgers_step(m))
+
 print("REF-COMPONENTS-OK", len(checked), " ".join(checked))

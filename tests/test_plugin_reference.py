@@ -34,8 +34,8 @@ def test_reference_dycore_on_b200_issues_the_mirror_call_sequence():
                     reason="reference tree not mounted")
 def test_reference_physics_components_on_b200_issue_the_mirror_calls():
     """north_star: "the sympl TendencyComponent/DiagnosticComponent classes ... work unchanged":
-    all eleven components of the moist benchmark's physics chain."""
+    the eleven components of the moist benchmark's physics chain and the Burgers stepper."""
     res = subprocess.run([sys.executable, os.path.join(HERE, "ref_components_check.py")],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "REF-COMPONENTS-OK 11" in res.stdout
+    assert "REF-COMPONENTS-OK 12" in res.stdout
