@@ -14,6 +14,7 @@ host-side mirror, at the raw-array level, of
   IsentropicDiagnostics,            src/tasmania/isentropic/physics/diagnostics.py:L41-L301
     IsentropicVelocityComponents      (the sympl components around the cores of isentropic.py / dwarfs.py)
   IsentropicHorizontalSmoothing     src/tasmania/isentropic/physics/horizontal_smoothing.py:L41-L180
+  IsentropicHorizontalDiffusion     src/tasmania/isentropic/physics/horizontal_diffusion.py:L41-L253
 
 with the same class names and call signatures, minus the DataArray / units layer (every
 isentropic component already works in the same units, so ``DataArrayDictOperator``'s conversions
@@ -141,6 +142,39 @@ class IsentropicHorizontalSmoothing(_DomainComponent):
         if self._moist:
             for n in (mfwv, mfcw, mfpw):
                 self._core_moist(state[n], out[n])
+
+
+class IsentropicHorizontalDiffusion(_DomainComponent):
+    """Horizontal numerical diffusion of s, su, sv (and of the water species) as a tendency
+    component: src/tasmania/isentropic/physics/horizontal_diffusion.py:L41-L253 around the
+    HorizontalDiffusion dwarf (row K8 of SURVEY.md section 8a)."""
+
+    kind = "tendency"
+
+    def __init__(self, grid, nb, diffusion_type, diffusion_coeff, diffusion_coeff_max, diffusion_damp_depth,
+                 moist=False, diffusion_moist_coeff=None, diffusion_moist_coeff_max=None,
+                 diffusion_moist_damp_depth=None, **kwargs):
+        from tasmania_b200.dwarfs import HorizontalDiffusion
+
+        super().__init__(grid, **kwargs)
+        self._moist = moist and diffusion_moist_coeff is not None
+        make = lambda c, cmax, depth: HorizontalDiffusion.factory(  # noqa: E731
+            diffusion_type, self.storage_shape, grid.dx, grid.dy, c, cmax, depth, nb,
+            backend_options=BackendOptions(), storage_options=self.storage_options)
+        self._core = make(diffusion_coeff, diffusion_coeff_max, diffusion_damp_depth)
+        self.tendency_names = (S, SU, SV)
+        if self._moist:
+            cmax = diffusion_moist_coeff if diffusion_moist_coeff_max is None else diffusion_moist_coeff_max
+            self._core_moist = make(diffusion_moist_coeff, cmax, diffusion_moist_damp_depth or 0)
+            self.tendency_names += (mfwv, mfcw, mfpw)
+
+    def array_call(self, state, out_tendencies, out_diagnostics=None, overwrite_tendencies=None):
+        ow = overwrite_tendencies or {}
+        for n in (S, SU, SV):
+            self._core(state[n], out_tendencies[n], overwrite_output=ow.get(n, True))
+        if self._moist:
+            for n in (mfwv, mfcw, mfpw):
+                self._core_moist(state[n], out_tendencies[n], overwrite_output=ow.get(n, True))
 
 
 class FromDiagnosticToTendency(_DomainComponent):

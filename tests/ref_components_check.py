@@ -234,6 +234,26 @@ with stubbed_library() as stub:
     compare("IsentropicVelocityComponents", lambda: r.array_call(sr, dr), lambda: m.array_call(sm, dm),
             keep=("tb200_velocity",))
 
+    # ---- horizontal diffusion as a tendency component (fourth order, dry + water species)
+    hdf = refload.load("tasmania.isentropic.physics.horizontal_diffusion")
+    for mname in ("second_order", "fourth_order"):
+        refload.load("tasmania.dwarfs.subclasses.horizontal_diffusers." + mname)
+    names = (S, SU, SV, QV, QC, QR)
+    r = hdf.IsentropicHorizontalDiffusion(
+        domain, "fourth_order", da(0.4, "s^-1"), da(0.9, "s^-1"), 4, moist=True,
+        diffusion_moist_coeff=da(0.2, "s^-1"), diffusion_moist_coeff_max=da(0.5, "s^-1"),
+        diffusion_moist_damp_depth=3, **ref_kw())
+    m = coupling.IsentropicHorizontalDiffusion(grid, NB, "fourth_order", 0.4, 0.9, 4, moist=True,
+                                               diffusion_moist_coeff=0.2, diffusion_moist_coeff_max=0.5,
+                                               diffusion_moist_damp_depth=3, **mkw)
+    assert set(m.tendency_names) == set(r.tendency_properties)
+    np.testing.assert_array_equal(tb.to_numpy(m._core._gamma)[0, 0], tb.to_numpy(r._core._gamma)[0, 0])
+    np.testing.assert_array_equal(tb.to_numpy(m._core_moist._gamma)[0, 0], tb.to_numpy(r._core_moist._gamma)[0, 0])
+    ow = {n: (n != SU) for n in names}  # one accumulating field
+    tr_, tm = buffers(names), buffers(names)
+    compare("IsentropicHorizontalDiffusion", lambda: r.array_call(sr, tr_, {}, ow),
+            lambda: m.array_call(sm, tm, {}, ow), mask={"tb200_diffusion": {2}})  # gamma rank
+
     # ---- the Burgers dwarf (BASELINE configs[0]): the reference's RK3WS stepper, third-order advection
     bst = refload.load("tasmania.burgers.dynamics.stepper")
     refload.load("tasmania.burgers.dynamics.subclasses.stepper.rk3ws")

@@ -38,4 +38,4 @@ def test_reference_physics_components_on_b200_issue_the_mirror_calls():
     res = subprocess.run([sys.executable, os.path.join(HERE, "ref_components_check.py")],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "REF-COMPONENTS-OK 12" in res.stdout
+    assert "REF-COMPONENTS-OK 13" in res.stdout
