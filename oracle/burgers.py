@@ -8,7 +8,6 @@ Follows
   src/tasmania/burgers/dynamics/dycore.py:L158-L173                           (stage + boundary)
   src/tasmania/burgers/state.py:L59-L152                                      (Zhao solution)
 """
-from datetime import timedelta
 
 import numpy as np
 

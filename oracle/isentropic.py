@@ -11,7 +11,6 @@ Follows
   src/tasmania/framework/dycore.py:L455-L462                                      (stage chaining)
 """
 from copy import deepcopy
-from datetime import timedelta
 
 import numpy as np
 

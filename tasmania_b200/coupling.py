@@ -30,7 +30,7 @@ from __future__ import annotations
 import os
 
 from tasmania_b200 import stencils
-from tasmania_b200.dwarfs import HorizontalSmoothing, HorizontalVelocity
+from tasmania_b200.dwarfs import HorizontalDiffusion, HorizontalSmoothing, HorizontalVelocity
 from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
 from tasmania_b200.isentropic import MTG, S, SU, SV, U, V
 from tasmania_b200.isentropic import IsentropicDiagnostics as _DiagnosticsCore
@@ -154,8 +154,6 @@ class IsentropicHorizontalDiffusion(_DomainComponent):
     def __init__(self, grid, nb, diffusion_type, diffusion_coeff, diffusion_coeff_max, diffusion_damp_depth,
                  moist=False, diffusion_moist_coeff=None, diffusion_moist_coeff_max=None,
                  diffusion_moist_damp_depth=None, **kwargs):
-        from tasmania_b200.dwarfs import HorizontalDiffusion
-
         super().__init__(grid, **kwargs)
         self._moist = moist and diffusion_moist_coeff is not None
         make = lambda c, cmax, depth: HorizontalDiffusion.factory(  # noqa: E731

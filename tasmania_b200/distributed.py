@@ -36,7 +36,7 @@ from __future__ import annotations
 import os
 from dataclasses import dataclass
 from datetime import datetime, timedelta
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
 import numpy as np
 import torch

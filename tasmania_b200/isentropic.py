@@ -17,7 +17,6 @@ orchestration that stays in tasmania).  Two execution paths produce the same num
 """
 from __future__ import annotations
 
-from datetime import timedelta
 
 import numpy as np
 

@@ -7,7 +7,7 @@ namelist_sus.py:L33-L141).  Everything between two calls of ``step`` stays on th
 """
 from __future__ import annotations
 
-from datetime import datetime, timedelta
+from datetime import datetime
 
 from tasmania_b200 import storage
 from tasmania_b200.boundary import HorizontalBoundary

@@ -17,8 +17,7 @@ fastest -- fine for numpy, wrong for CUDA.)
 """
 from __future__ import annotations
 
-import copy as _copy
-from typing import Optional, Sequence
+from typing import Sequence
 
 import numpy as np
 import torch

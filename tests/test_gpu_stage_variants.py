@@ -3,7 +3,6 @@
 variables, read once): the s-step + scans as kernel S (thread per column) or kernels A + B,
 the momentum step as the register-window kernel, the shared-memory-ring kernels (one or two
 columns per lane) or the TMA kernel.  Every combination must give bit-identical fields."""
-import hashlib
 import os
 import subprocess
 import sys
