@@ -130,3 +130,29 @@ def test_dry_run_graphed_issues_the_eager_call_sequence():
             stub.trace = None
     assert len(traces[0]) >= 4 * nsteps
     assert traces[0] == traces[1]
+
+
+def test_graphed_loop_refuses_a_step_that_never_cycles():
+    """A model that allocates a new output array every step has no finite set of buffer
+    configurations: the loop stops capturing at ``max_graphs`` instead of leaking graphs."""
+    import pytest
+
+    import tasmania_b200 as tb
+    from tasmania_b200 import stencils
+    from tasmania_b200.graphs import GraphedLoop
+
+    class Leaky(Rotating):
+        def compute_step(self):
+            self.pool["a"] = tb.zeros(self.state["y"].shape)  # a fresh array each step
+            super().compute_step()
+
+    with stubbed_library() as stub:
+        FakeCapture.stub = stub
+        loop = GraphedLoop(Leaky(tb, stencils, np.ones((3, 2, 2))), eager_steps=0, max_graphs=4,
+                           capture_factory=FakeCapture)
+        keep = []  # hold the arrays so that the allocator cannot hand the same address out again
+        with pytest.raises(tb.lib.B200Error, match="does not cycle"):
+            for _ in range(10):
+                loop.step()
+                keep.append(dict(loop.model.pool))
+        assert loop.period == 4
