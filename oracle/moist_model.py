@@ -27,9 +27,10 @@ bit for bit on the reference's numpy definitions (tests/test_oracle_golden.py), 
 ``tendency_step`` is pinned bit for bit on the reference's own ForwardEuler / RK2 / RK3WS ``_call``
 methods executed in place (tests/test_coupling_reference.py, which also runs the reference's
 ConcurrentCoupling._call_serial, promoters and SequentialUpdateSplitting.__call__ against the b200
-mirrors).  UNPINNED BY EXECUTION: the component list and order of the benchmark driver (a script
-over sympl objects that cannot run here); ``physics`` follows it by reading,
-line references above.
+mirrors).  ``physics`` as a whole is pinned bit for bit on the reference's own component objects
+chained by the reference's own couplers and steppers (tests/test_moist_physics_reference.py).
+UNPINNED BY EXECUTION: only the component list and order, taken by reading from the benchmark
+driver (a script over sympl objects that cannot run here).
 """
 from __future__ import annotations
 
