@@ -129,19 +129,12 @@ def promoter(cls, grid, **props):
     return p
 
 
-def test_reference_physics_pass_equals_oracle():
-    from tests import helpers as hp
+def reference_physics(model, domain):
+    """The reference's physics suite of the moist benchmark as a callable ``physics(state, dt)`` on
+    a DataArray state dict (in place)."""
     from tests.golden import generate_golden as gg
-    from tests.test_moist_model_oracle import build
 
-    # ---- the oracle model and an evolved state (cloud, rain, latent heating all non-zero)
-    model, ost = build(NX, NY, NZ, max_height=500.0)  # the terrain gg._make_domain builds
-    dt = timedelta(seconds=5)
-    for _ in range(3):
-        ost = model.step(ost, dt)
     pt = model.pt
-
-    # ---- the reference's objects, numpy backend, namelist_sus.py parameters
     cc = ref("tasmania.framework.concurrent_coupling")
     ccu = ref("tasmania.framework.concurrent_coupling_utils")
     sus = ref("tasmania.framework.sequential_update_splitting")
@@ -151,11 +144,7 @@ def test_reference_physics_pass_equals_oracle():
     steppers = {"forward_euler": ref("tasmania.framework.subclasses.tendency_steppers.forward_euler").ForwardEuler,
                 "rk2": ref("tasmania.framework.subclasses.tendency_steppers.rk2").RK2,
                 "rk3ws": ref("tasmania.framework.subclasses.tendency_steppers.rk3ws").RK3WS}
-    domain = gg._make_domain(NX, NY, NZ, "relaxed", NB, {"nr": 6}, topo_time=60.0)
     grid = domain.numerical_grid
-    grid.update_topography(model.nstep * dt)  # the terrain of the oracle's current time level
-    hb = domain.horizontal_boundary
-    hb.reference_state = {n: da(v.copy(), n) for n, v in model.hb.reference_state.items()}
     opts = ref("tasmania.framework.options")
     kw = lambda: dict(enable_checks=False, backend="numpy", backend_options=opts.BackendOptions(),  # noqa: E731
                       storage_shape=SHAPE, storage_options=opts.StorageOptions())
@@ -179,7 +168,7 @@ def test_reference_physics_pass_equals_oracle():
     d2t = promoter(iu.AirPotentialTemperatureToTendency, grid, tendency_properties={mm.THETA: prop},
                    diagnostic_properties={})
     rfv = Diagnostic(ke.KesslerFallVelocity(domain, "numerical", **kw()))
-    chain = [
+    chain = [  # driver_namelist_sus.py:L184-L479 with namelist_sus.py:L33-L141
         Diagnostic(idg.IsentropicDiagnostics(domain, "numerical", True, g(pt, "Pa"), **kw())),
         ("rk2", [Tendency(co.IsentropicConservativeCoriolis(domain, grid_type="numerical",
                                                              coriolis_parameter=None, **kw()))]),
@@ -203,7 +192,6 @@ def test_reference_physics_pass_equals_oracle():
             domain, "numerical", sedimentation_flux_scheme="second_order_upwind", **kw()))]),
         ("forward_euler", [rfv, Implicit(ut.Precipitation(domain, "numerical", **kw()), sec2d)]),
     ]
-
     op = xr.DataArrayDictOperator(backend="numpy")
 
     class Stepper:
@@ -242,19 +230,108 @@ def test_reference_physics_pass_equals_oracle():
         _component_list=components, _substeps=[1] * len(components),
         _out_diagnostics=[None] * len(components), _out_state=[None] * len(components), _dict_op=op,
         allowed_diagnostic_type=sus.SequentialUpdateSplitting.allowed_diagnostic_type)
+    return lambda state, dt: sus.SequentialUpdateSplitting.__call__(me, state, dt)
 
+
+def reference_dycore(model, domain):
+    """The reference's moist dynamical core as a callable ``dycore(raw_state, dt) -> raw outputs``:
+    ``IsentropicDynamicalCore.stage_array_call_moist`` (dycore.py:L723-L843, unbound) over the
+    reference's RK3WSSI prognostic, Rayleigh damper (last stage only, namelist_sus.py:L102),
+    HorizontalVelocity and WaterConstituent, stages chained as framework/dycore.py:L455-L458."""
+    from tests.golden import generate_golden as gg
+
+    dyc = ref("tasmania.isentropic.dynamics.dycore")
+    ref("tasmania.isentropic.dynamics.subclasses.prognostics.utils")
+    ref("tasmania.isentropic.dynamics.subclasses.prognostics.rk3ws_si")
+    ref("tasmania.isentropic.dynamics.subclasses.minimal_horizontal_fluxes.fifth_order_upwind")
+    ref("tasmania.dwarfs.subclasses.vertical_dampers.rayleigh")
+    prog = ref("tasmania.isentropic.dynamics.prognostic")
+    vd = ref("tasmania.dwarfs.vertical_damping")
+    dd = ref("tasmania.dwarfs.diagnostics")
+    opts = ref("tasmania.framework.options")
+    bo, so = opts.BackendOptions, opts.StorageOptions
+    grid, hb = domain.numerical_grid, domain.horizontal_boundary
+    prognostic = prog.IsentropicPrognostic.factory(
+        "rk3ws_si", "fifth_order_upwind", domain, True, backend="numpy", backend_options=bo(),
+        storage_shape=SHAPE, storage_options=so(), pt=gg.da(model.pt, "Pa"), eps=0.5)
+    outnames = (mm.S, mm.SU, mm.U, mm.SV, mm.V, mm.QV, mm.QC, mm.QR)
+    me = types.SimpleNamespace(
+        _water_constituent=dd.WaterConstituent(grid, clipping=True, backend="numpy", backend_options=bo(),
+                                               storage_options=so()),
+        **{f"_{q}_{t}": np.zeros(SHAPE) for q in ("sqv", "sqc", "sqr") for t in ("now", "int", "new")},
+        horizontal_boundary=hb, output_properties={k: {"units": units_of(k)} for k in outnames},
+        _damp=True, _damp_at_every_stage=False, stages=prognostic.stages, _prognostic=prognostic,
+        _damper=vd.VerticalDamping.factory("rayleigh", grid, 4, 5e-4, backend="numpy", backend_options=bo(),
+                                           storage_shape=SHAPE, storage_options=so()),
+        _velocity_components=dd.HorizontalVelocity(grid, staggering=True, backend="numpy",
+                                                   backend_options=bo(), storage_options=so()),
+        _s_ref=np.zeros(SHAPE), _su_ref=np.zeros(SHAPE), _sv_ref=np.zeros(SHAPE),
+        _s_now=None, _su_now=None, _sv_now=None)
+    outs = [{k: np.zeros(SHAPE) for k in outnames} for _ in range(prognostic.stages)]
+
+    def call(cur, dt):
+        st_in = cur
+        for stage in range(prognostic.stages):
+            dyc.IsentropicDynamicalCore.stage_array_call_moist(me, stage, st_in, {}, dt, outs[stage])
+            st_in = dict(outs[stage])
+            st_in.setdefault(mm.MTG, cur[mm.MTG])
+        return {k: outs[-1][k].copy() for k in outnames}
+
+    return call
+
+
+def _setup(nsteps_before):
+    from tests.golden import generate_golden as gg
+    from tests.test_moist_model_oracle import build
+
+    model, ost = build(NX, NY, NZ, max_height=500.0)  # the terrain gg._make_domain builds
+    dt = timedelta(seconds=5)
+    for _ in range(nsteps_before):
+        ost = model.step(ost, dt)
+    domain = gg._make_domain(NX, NY, NZ, "relaxed", NB, {"nr": 6}, topo_time=60.0)
+    domain.numerical_grid.update_topography(model.nstep * dt)
+    domain.horizontal_boundary.reference_state = {
+        n: da(v.copy(), n) for n, v in model.hb.reference_state.items()}
+    return model, ost, domain, dt
+
+
+def test_reference_physics_pass_equals_oracle():
+    """One pass of the physics suite on an evolved state (cloud, rain, latent heating non-zero)."""
+    model, ost, domain, dt = _setup(3)
+    physics = reference_physics(model, domain)
     rstate = {n: da(v.copy(), n) for n, v in ost.items() if n != "time"}
     rstate["time"] = ost["time"]
+    want = dict(ost)
     with np.errstate(divide="ignore", invalid="ignore"):
-        sus.SequentialUpdateSplitting.__call__(me, rstate, dt)
-        want = dict(ost)
+        physics(rstate, dt)
         model.physics(want, dt)
-
-    assert rstate["time"] == want["time"]
-    assert set(rstate) == set(want)
+    assert rstate["time"] == want["time"] and set(rstate) == set(want)
     for n, v in want.items():
         if n != "time":
             np.testing.assert_array_equal(rstate[n].data, v, err_msg=n)
     box = (slice(0, NX), slice(0, NY), slice(0, NZ))
     assert float(want[mm.QR][box].max()) > 1e-5 and float(np.abs(want[mm.W][box]).max()) > 0.0
     assert float(want[mm.ACCPREC].max()) > 0.0
+
+
+def test_reference_model_steps_equal_oracle():
+    """Five full steps of the benchmark loop (driver_namelist_sus.py:L490-L512): the reference's
+    moist dynamical core and physics suite, run in place, against ``MoistIsentropicModel.step``."""
+    model, ost, domain, dt = _setup(0)
+    physics, dycore = reference_physics(model, domain), reference_dycore(model, domain)
+    grid = domain.numerical_grid
+    rstate = {n: da(v.copy(), n) for n, v in ost.items() if n != "time"}
+    rstate["time"] = ost["time"]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for step in range(5):
+            grid.update_topography((step + 1) * dt)
+            out = dycore(raw(rstate), dt)
+            for n, v in out.items():  # the fields the dycore does not return are carried over (L503)
+                rstate[n] = da(v, n)
+            physics(rstate, dt)
+            ost = model.step(ost, dt)
+            assert rstate["time"] == ost["time"]
+            for n, v in ost.items():
+                if n != "time":
+                    np.testing.assert_array_equal(rstate[n].data, v, err_msg=f"step {step}: {n}")
+    assert float(np.abs(ost[mm.SV]).max()) > 1.0
