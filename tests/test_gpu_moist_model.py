@@ -147,3 +147,38 @@ def test_fused_paths_equal_the_reference_shaped_paths_bitwise(monkeypatch):
     assert res[0][1] < res[1][1] - 20  # 3 fma + 21 relax launches fewer per step
     for n, v in res[1][0].items():
         np.testing.assert_array_equal(res[0][0][n], v, err_msg=n)
+
+
+def test_moist_model_vs_reference_fixture():
+    """The GPU model against tests/golden/moist_model.npz: five steps of the moist benchmark loop
+    computed by the REFERENCE ITSELF (its moist dynamical core and physics suite run in place, numpy
+    backend; tests/golden/generate_moist_model.py).  Same tolerances as against the oracle, which
+    reproduces this fixture bit for bit (tests/test_moist_model_oracle.py)."""
+    import tasmania_b200 as tb
+    from oracle import moist_model as mm
+    from tasmania_b200.isentropic_moist import IsentropicMoistSUS
+    from tests import helpers as hp
+
+    fx = hp.load("moist_model")
+    nx, ny, nz, nb, nr, nsteps, damp_depth = (int(v) for v in fx["dims"])
+    dt_s, max_height, topo_seconds, rh = (float(v) for v in fx["params"])
+    grid, np_state = hp.moist_case(nx, ny, nz, max_height=max_height, topo_seconds=topo_seconds,
+                                   relative_humidity=rh)
+    for n, v in np_state.items():
+        np.testing.assert_array_equal(v, fx["init_" + n], err_msg=n)
+    model = IsentropicMoistSUS(grid, np_state, timedelta(seconds=dt_s), nb=nb, nr=nr,
+                               damp_depth=damp_depth)
+    final = model.run(nsteps)
+    worst = {}
+    for key in fx.files:
+        if not key.startswith("final_"):
+            continue
+        n = key[6:]
+        ref = fx[key]
+        box = (slice(0, nx), slice(0, ny), slice(0, nz if ref.shape[2] > 1 else 1))
+        worst[n] = hp.relerr(tb.to_numpy(final[n])[box], ref[box])
+    print("moist model vs the reference's own run, relative errors:",
+          {k: float(f"{v:.2e}") for k, v in worst.items()})
+    assert len(worst) >= 18
+    assert worst.pop(mm.W) <= RTOL_HEATING
+    assert max(worst.values()) <= RTOL, worst

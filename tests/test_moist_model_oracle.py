@@ -88,3 +88,23 @@ def test_physics_leaves_untouched_what_no_component_outputs():
         dwarfs.smoothing(2, before[n], model2.gamma, out, (3, 3, 0), (sx - 6, sy - 6, sz))
         sm[n] = out
         np.testing.assert_array_equal(st4[n][3:-3, 3:-3], out[3:-3, 3:-3])
+
+
+def test_oracle_moist_model_reproduces_the_reference_fixture():
+    """tests/golden/moist_model.npz was produced by the reference itself (five steps of the moist
+    benchmark loop, tests/golden/generate_moist_model.py); the oracle reproduces every field of it
+    bit for bit from the fixture's initial state."""
+    fx = hp.load("moist_model")
+    nx, ny, nz, nb, nr, nsteps, damp_depth = (int(v) for v in fx["dims"])
+    dt_s, max_height, topo_seconds, rh = (float(v) for v in fx["params"])
+    model, st = build(nx, ny, nz, max_height=max_height, topo_seconds=topo_seconds,
+                      relative_humidity=rh)
+    names = [k[5:] for k in fx.files if k.startswith("init_")]
+    for n in names:  # the case builder gives the fixture's initial state
+        np.testing.assert_array_equal(st[n], fx["init_" + n], err_msg=n)
+    for _ in range(nsteps):
+        st = model.step(st, timedelta(seconds=dt_s))
+    assert {k[6:] for k in fx.files if k.startswith("final_")} == set(st) - {"time"}
+    for n in st:
+        if n != "time":
+            np.testing.assert_array_equal(st[n], fx["final_" + n], err_msg=n)
