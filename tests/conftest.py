@@ -13,6 +13,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # docstrings of the reference tree (imported in place by tests/golden/refload.py) carry
+    # invalid escape sequences
+    config.addinivalue_line("filterwarnings", "ignore::SyntaxWarning")
 
 
 def golden(name):
