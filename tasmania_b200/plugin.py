@@ -188,7 +188,53 @@ GLOBAL_STENCILS = (
 )
 
 
-def install(strict: bool = False) -> dict:
+def _batch_dict_operator_fma():
+    """Give the reference's ``DataArrayDictOperator.fma`` (src/tasmania/utils/xarrayx.py:L688-L740)
+    the one-launch-per-stage form on backend b200: same dictionary / units logic, but the per-field
+    ``fma`` stencil calls are collected and issued as one ``tb200_fma_fields`` launch.  Every other
+    backend goes through the original method.  Returns what was replaced (for the report)."""
+    from tasmania.utils import xarrayx
+    from tasmania.utils.storage import deepcopy_dataarray
+
+    original = xarrayx.DataArrayDictOperator.fma
+    if getattr(original, "__tasmania_b200__", False):
+        return None
+
+    def fma(self, dict1, dict2, factor, out=None, field_properties=None):
+        if getattr(self, "backend", None) != BACKEND:
+            return original(self, dict1, dict2, factor, out=out, field_properties=field_properties)
+        field_properties = field_properties or {}
+        out = out or {}
+        if "time" in dict1 or "time" in dict2:
+            out["time"] = dict1.get("time", dict2.get("time", None))
+        shared_keys = set(dict1.keys()).intersection(dict2.keys()).difference(("time",))
+        outs, ins_a, ins_b = [], [], []
+        for key in shared_keys:
+            props = field_properties.get(key, {})
+            units = props.get("units", dict1[key].attrs["units"])
+            field1 = dict1[key].to_units(units)
+            rfield2 = dict2[key].to_units(units).data
+            if key in out:
+                out[key].attrs["units"] = units
+            else:
+                out[key] = deepcopy_dataarray(field1)
+            outs.append(out[key].data)
+            ins_a.append(field1.data)
+            ins_b.append(rfield2)
+        by_shape = {}
+        for o, a, b in zip(outs, ins_a, ins_b):
+            by_shape.setdefault(tuple(o.shape), []).append((o, a, b))
+        for shape, group in by_shape.items():
+            st.fma_fields([g[0] for g in group], [g[1] for g in group], [g[2] for g in group], factor,
+                           origin=(0, 0, 0), domain=shape)
+        return out
+
+    fma.__tasmania_b200__ = True
+    xarrayx.DataArrayDictOperator.fma = fma
+    return "DataArrayDictOperator.fma"
+
+
+def install(strict: bool = False, batch_fma: bool = True) -> dict:
     """Register the b200 backend into the importable ``tasmania`` package.  Returns a report
     ``{"global": [...], "class_scoped": [...], "skipped": [...]}``; with ``strict`` a reference
     class that cannot be imported raises instead of being skipped (sub-packages pulling
@@ -246,6 +292,17 @@ def install(strict: bool = False) -> dict:
         attach(modname, clsname, stencil, fn, tt.stencil_definition)
     for modname, clsname, stencil, fn in _class_scoped_subroutines():
         attach(modname, clsname, stencil, fn, tt.subroutine_definition)
+
+    # 5. the stage update of the reference's tendency steppers in one launch (bit-identical)
+    if batch_fma:
+        try:
+            patched = _batch_dict_operator_fma()
+            if patched:
+                report["batched"] = [patched]
+        except Exception as exc:  # pragma: no cover - depends on optional deps of the reference
+            if strict:
+                raise
+            report["skipped"].append(("DataArrayDictOperator.fma", repr(exc)))
 
     _installed = True
     return report

@@ -133,8 +133,21 @@ with stubbed_library() as stub:
     out = {"y": da(ta.zeros("b200", shape=y0.shape))}
     op.fma({"y": da(ta.as_storage("b200", data=y0))}, {"y": da(ta.as_storage("b200", data=2.0 * y0))},
            0.25, out=out)
-    assert stub.calls[-1] == "tb200_elementwise"
+    # (the plugin batches the per-field fma calls of the operator into one launch)
+    assert report["batched"] == ["DataArrayDictOperator.fma"] and stub.calls[-1] == "tb200_fma_fields"
     assert np.array_equal(to_numpy(out["y"].data), y0 + 0.25 * (2.0 * y0))
+    two = {n: da(ta.as_storage("b200", data=y0 * k)) for k, n in enumerate(("a", "b"), 1)}
+    inc = {n: da(ta.as_storage("b200", data=y0 + k)) for k, n in enumerate(("a", "b"), 1)}
+    res = {n: da(ta.zeros("b200", shape=y0.shape)) for n in ("a", "b")}
+    n0 = stub.count("tb200_fma_fields")
+    op.fma(two, inc, -0.5, out=res)
+    assert stub.count("tb200_fma_fields") == n0 + 1        # two fields, one launch
+    for k, n in enumerate(("a", "b"), 1):
+        assert np.array_equal(to_numpy(res[n].data), y0 * k + -0.5 * (y0 + k))
+    # other backends keep the reference's own method
+    nop = DataArrayDictOperator(backend="numpy")
+    nres = nop.fma({"y": da(y0.copy())}, {"y": da(2.0 * y0)}, 0.25, out={"y": da(np.zeros_like(y0))})
+    assert np.array_equal(nres["y"].data, y0 + 0.25 * (2.0 * y0))
 
     # the reference's RK3WS tendency stepper logic (its own _call, unbound) on b200 storages
     from tasmania.framework.subclasses.tendency_steppers.rk3ws import RK3WS  # noqa: E402
@@ -154,7 +167,7 @@ with stubbed_library() as stub:
     want = y0 + 0.3 * (-0.7 * (y0 + 0.5 * 0.3 * (-0.7 * (y0 + (1.0 / 3.0 * 0.3) * (-0.7 * y0)))))
     assert np.array_equal(to_numpy(out_state["y"].data), want), np.abs(to_numpy(out_state["y"].data) - want).max()
     assert abs(float(want.ravel()[0] / y0.ravel()[0]) - (1 - z + z * z / 2 - z**3 / 6)) < 1e-15
-    assert stub.count("tb200_elementwise") == 4
+    assert stub.count("tb200_elementwise") == 0 and stub.count("tb200_fma_fields") >= 3 + 2
 
 print("PLUGIN-OK", len(report["global"]), len(report["class_scoped"]), len(report["skipped"]))
 for s in report["skipped"]:
