@@ -93,6 +93,23 @@ def relaxed_gamma_window(global_extent, offset, shape, rel):
     return g
 
 
+def relax_frame(fields, refs, extents, gamma, free_box):
+    """``tb200_relax_frame``: relax all ``fields`` towards ``refs`` on the frame outside
+    ``free_box`` (a box on which ``gamma`` vanishes), eight fields per launch."""
+    import ctypes as C
+
+    box = (C.c_int32 * 4)(*free_box)
+    g = lib.as_field(gamma)
+    for lo in range(0, len(fields), 8):
+        phi = [lib.as_field(f) for f in fields[lo:lo + 8]]
+        ref = [lib.as_field(f) for f in refs[lo:lo + 8]]
+        ext = (C.c_int32 * (3 * len(phi)))(*[int(v) for e in extents[lo:lo + 8] for v in e])
+        lib.check(lib.load().tb200_relax_frame(
+            len(phi), (lib.FieldP * len(phi))(*[C.pointer(f) for f in phi]),
+            (lib.FieldP * len(phi))(*[C.pointer(f) for f in ref]), g, ext, box,
+            lib.current_stream()), "tb200_relax_frame")
+
+
 class Relaxed(HorizontalBoundary):
     """Relaxed boundary conditions (``ni = nx``, ``nj = ny``)."""
 
@@ -190,20 +207,8 @@ class Relaxed(HorizontalBoundary):
                  and (field_properties is None or n in field_properties)]
         if not names:
             return
-        import ctypes as C
-
-        box = (C.c_int32 * 4)(*self._free_box)
-        gamma = lib.as_field(self._gamma2d)
-        for lo in range(0, len(names), 8):
-            chunk = names[lo:lo + 8]
-            phi = [lib.as_field(state[n]) for n in chunk]
-            refs = [lib.as_field(ref[n]) for n in chunk]
-            ext = (C.c_int32 * (3 * len(chunk)))(
-                *[v for n in chunk for v in _extent(self.nx, self.ny, self.nz, n)])
-            lib.check(lib.load().tb200_relax_frame(
-                len(chunk), (lib.FieldP * len(chunk))(*[C.pointer(f) for f in phi]),
-                (lib.FieldP * len(chunk))(*[C.pointer(f) for f in refs]), gamma, ext, box,
-                lib.current_stream()), "tb200_relax_frame")
+        relax_frame([state[n] for n in names], [ref[n] for n in names],
+                    [_extent(self.nx, self.ny, self.nz, n) for n in names], self._gamma2d, self._free_box)
 
     def _outermost(self, axis, field, field_name):
         mi, mj, _ = _extent(self.nx, self.ny, self.nz, field_name)

@@ -234,7 +234,49 @@ def _batch_dict_operator_fma():
     return "DataArrayDictOperator.fma"
 
 
-def install(strict: bool = False, batch_fma: bool = True) -> dict:
+def _frame_relaxed_enforce_raw():
+    """Give the reference's ``Relaxed`` boundary the one-launch form of ``enforce_raw``
+    (src/tasmania/domain/horizontal_boundary.py:L299-L344 over relaxed.py:L119-L160) on backend
+    b200: the same selection of fields, units and extents, relaxed by ``tb200_relax_frame`` on the
+    frame where the object's own coefficient matrix is non-zero instead of one full-box ``irelax``
+    per field.  Other backends go through the original method."""
+    from tasmania.domain.subclasses.horizontal_boundaries.relaxed import Relaxed
+    from tasmania_b200 import boundary as b200_boundary
+
+    original = Relaxed.enforce_raw
+    if getattr(original, "__tasmania_b200__", False):
+        return None
+
+    def enforce_raw(self, state, field_properties=None):
+        if getattr(self, "backend", None) != BACKEND:
+            return original(self, state, field_properties)
+        rfps = {name: {"units": self.reference_state[name].attrs["units"]}
+                for name in self.reference_state if name != "time"}
+        fps = rfps if field_properties is None else {
+            key: val for key, val in field_properties.items() if key in rfps}
+        names = [name for name in state if name != "time" and name in fps]
+        if not names:
+            return
+        box = getattr(self, "_b200_free_box", None)
+        if box is None:  # once per object: where its own gamma vanishes
+            box = b200_boundary.Relaxed._gamma_free_box(storage.to_numpy(self._gamma)[:, :, 0])
+            self._b200_free_box = box
+        refs, extents = [], []
+        for name in names:
+            units = fps[name].get("units", rfps[name]["units"])
+            refs.append(self.reference_state[name].to_units(units).data)
+            extents.append((
+                self.ni + 1 if "at_u_locations" in name or "at_uv_locations" in name else self.ni,
+                self.nj + 1 if "at_v_locations" in name or "at_uv_locations" in name else self.nj,
+                self.physical_grid.nz + 1 if "on_interface_levels" in name else self.physical_grid.nz))
+        b200_boundary.relax_frame([state[n] for n in names], refs, extents, self._gamma, box)
+
+    enforce_raw.__tasmania_b200__ = True
+    Relaxed.enforce_raw = enforce_raw
+    return "Relaxed.enforce_raw"
+
+
+def install(strict: bool = False, batch_fma: bool = True, frame_relax: bool = True) -> dict:
     """Register the b200 backend into the importable ``tasmania`` package.  Returns a report
     ``{"global": [...], "class_scoped": [...], "skipped": [...]}``; with ``strict`` a reference
     class that cannot be imported raises instead of being skipped (sub-packages pulling
@@ -303,6 +345,16 @@ def install(strict: bool = False, batch_fma: bool = True) -> dict:
             if strict:
                 raise
             report["skipped"].append(("DataArrayDictOperator.fma", repr(exc)))
+
+    if frame_relax:
+        try:
+            patched = _frame_relaxed_enforce_raw()
+            if patched:
+                report.setdefault("batched", []).append(patched)
+        except Exception as exc:  # pragma: no cover - depends on optional deps of the reference
+            if strict:
+                raise
+            report["skipped"].append(("Relaxed.enforce_raw", repr(exc)))
 
     _installed = True
     return report

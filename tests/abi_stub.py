@@ -7,9 +7,10 @@ module swaps the loaded library for a stub whose entry points
 
   * have the ctypes prototypes of ``tasmania_b200.lib.SIGNATURES`` -- every call is type-checked
     against the declared C signature exactly as a real call would be -- and are recorded;
-  * do nothing, except ``tb200_fma_fields`` and ``tb200_elementwise`` (copy / fma), which are
-    carried out with numpy on the host buffers so that the arithmetic of the coupling layer
-    (stage factors, buffer swaps, accumulate-or-overwrite) can be followed end to end.
+  * do nothing, except ``tb200_fma_fields``, ``tb200_elementwise`` (copy / fma) and
+    ``tb200_relax_frame``, which are carried out with numpy on the host buffers so that the
+    arithmetic of the coupling layer (stage factors, buffer swaps, accumulate-or-overwrite) and of
+    the boundary glue can be followed end to end.
 
 Storages are allocated on the host for the duration (``storage.DEFAULT_DEVICE_OVERRIDE``).
 Nothing in tasmania_b200 knows about this file.
@@ -75,7 +76,10 @@ def _freeze(name, argtypes, args):
                 desc.append(tuple(None if f is None else (f.ptr, tuple(f.shape), tuple(f.stride))
                                   for f in fs))
         elif t is C.POINTER(C.c_int32):
-            vals = (C.c_int32 * 3)(v[0], v[1], v[2])
+            n = 3  # origin / domain triplets, except the two arrays of tb200_relax_frame
+            if name == "tb200_relax_frame":
+                n = 3 * args[0] if len(frozen) == 4 else 4
+            vals = (C.c_int32 * n)(*[v[m] for m in range(n)])
             keep.append(vals)
             frozen.append(vals), desc.append(tuple(vals))
         elif t in (C.c_double, C.c_int, C.c_uint32):
@@ -137,6 +141,20 @@ class AbiStub:
             _as_numpy(out.contents)[box] = _as_numpy(a.contents)[box]
         elif op == lib.ELEMENTWISE_OPS["fma"]:
             _as_numpy(out.contents)[box] = _as_numpy(a.contents)[box] + f * _as_numpy(b.contents)[box]
+
+    def _do_tb200_relax_frame(self, n, phi, ref, gamma, extents, interior, stream):
+        """Relaxed.enforce_raw on the frame outside ``interior`` (algorithms.py:L32-L43 per point)."""
+        g2d = _as_numpy(gamma.contents)[:, :, 0]
+        i_lo, i_hi, j_lo, j_hi = (int(interior[m]) for m in range(4))
+        for m in range(n):
+            mi, mj, mk = (int(extents[3 * m + c]) for c in range(3))
+            frame = np.ones((mi, mj), dtype=bool)
+            frame[i_lo:i_hi, j_lo:j_hi] = False
+            g = g2d[:mi, :mj, None]
+            a = _as_numpy(phi[m].contents)[:mi, :mj, :mk]
+            r = _as_numpy(ref[m].contents)[:mi, :mj, :mk]
+            relaxed = np.where(g == 1.0, r, a - g * (a - r))
+            a[...] = np.where(frame[:, :, None] & (g != 0.0), relaxed, a)
 
     def count(self, name):
         return sum(1 for c in self.calls if c == name)

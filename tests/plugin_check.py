@@ -134,7 +134,8 @@ with stubbed_library() as stub:
     op.fma({"y": da(ta.as_storage("b200", data=y0))}, {"y": da(ta.as_storage("b200", data=2.0 * y0))},
            0.25, out=out)
     # (the plugin batches the per-field fma calls of the operator into one launch)
-    assert report["batched"] == ["DataArrayDictOperator.fma"] and stub.calls[-1] == "tb200_fma_fields"
+    assert report["batched"] == ["DataArrayDictOperator.fma", "Relaxed.enforce_raw"]
+    assert stub.calls[-1] == "tb200_fma_fields"
     assert np.array_equal(to_numpy(out["y"].data), y0 + 0.25 * (2.0 * y0))
     two = {n: da(ta.as_storage("b200", data=y0 * k)) for k, n in enumerate(("a", "b"), 1)}
     inc = {n: da(ta.as_storage("b200", data=y0 + k)) for k, n in enumerate(("a", "b"), 1)}
@@ -168,6 +169,39 @@ with stubbed_library() as stub:
     assert np.array_equal(to_numpy(out_state["y"].data), want), np.abs(to_numpy(out_state["y"].data) - want).max()
     assert abs(float(want.ravel()[0] / y0.ravel()[0]) - (1 - z + z * z / 2 - z**3 / 6)) < 1e-15
     assert stub.count("tb200_elementwise") == 0 and stub.count("tb200_fma_fields") >= 3 + 2
+
+    # Relaxed.enforce_raw of the unmodified reference on b200 storages: one frame launch for all
+    # fields (carried out on the host by the stub), equal to the reference's numpy backend
+    import generate_golden as gg  # noqa: E402
+
+    names = ("air_isentropic_density", "x_velocity_at_u_locations", "y_velocity_at_v_locations",
+             "air_pressure_on_interface_levels")
+    nx, ny, nz = 19, 17, 5
+    rng = np.random.default_rng(3)
+    fields = {n: rng.standard_normal((nx + 1, ny + 1, nz + 1)) for n in names}
+    refs = {n: rng.standard_normal((nx + 1, ny + 1, nz + 1)) for n in names}
+    results = {}
+    for backend in ("numpy", "b200"):
+        dom = gg._make_domain(nx, ny, nz, "relaxed", 3, {"nr": 6}, topo=False)
+        if backend == "b200":  # _make_domain builds numpy objects: rebuild the boundary on b200
+            hbm = refload.load("tasmania.domain.horizontal_boundary")
+            hb_ = hbm.HorizontalBoundary.factory("relaxed", dom.physical_grid, 3, backend="b200",
+                                                 storage_options=StorageOptions(), nr=6)
+        else:
+            hb_ = dom.horizontal_boundary
+        conv = (lambda a: ta.as_storage("b200", data=a)) if backend == "b200" else (lambda a: a.copy())
+        hb_.reference_state = {n: refload.DataArray(conv(v), attrs={"units": "1"}) for n, v in refs.items()}
+        state = {n: conv(v) for n, v in fields.items()}
+        n0 = stub.count("tb200_relax_frame")
+        hb_.enforce_raw(state, {n: {"units": "1"} for n in names[:3]})
+        if backend == "b200":
+            assert stub.count("tb200_relax_frame") == n0 + 1 and stub.count("tb200_relax") == 0
+            assert hb_._b200_free_box == (6, nx - 6, 6, ny - 6)
+        results[backend] = {n: np.array(to_numpy(v)) for n, v in state.items()}
+    for n in names:
+        assert np.array_equal(results["b200"][n], results["numpy"][n]), n
+    assert np.array_equal(results["b200"][names[3]], fields[names[3]])       # not selected: untouched
+    assert not np.array_equal(results["b200"][names[0]], fields[names[0]])
 
 print("PLUGIN-OK", len(report["global"]), len(report["class_scoped"]), len(report["skipped"]))
 for s in report["skipped"]:
