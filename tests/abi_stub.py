@@ -53,7 +53,8 @@ def _freeze(name, argtypes, args):
     """Copy the ctypes arguments of a call so that it can be re-issued later (the marshalling
     code frees its tb200_field structs right after the call) and describe it for traces."""
     frozen, desc, keep = [], [], []
-    nf = {"tb200_fma_fields": lambda a: a[0], "tb200_halo_pack": lambda a: a[1],
+    nf = {"tb200_fma_fields": lambda a: a[0], "tb200_relax_frame": lambda a: a[0],
+          "tb200_vertical_advection_step": lambda a: a[3], "tb200_halo_pack": lambda a: a[1],
           "tb200_halo_unpack": lambda a: a[1]}.get(name, lambda a: 3)(args)
     for t, v in zip(argtypes, args):
         if t is lib.FieldP:

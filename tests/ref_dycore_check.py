@@ -32,7 +32,7 @@ import tasmania_b200 as tb  # noqa: E402
 from tasmania_b200 import plugin  # noqa: E402
 from tests.abi_stub import stubbed_library  # noqa: E402
 
-plugin.install()
+plugin.install(frame_relax=False)  # the reference-shaped boundary path on both sides
 
 S, SU, SV = gg.S, gg.SU, gg.SV
 U, V, MTG = "x_velocity_at_u_locations", "y_velocity_at_v_locations", "montgomery_potential"
