@@ -83,6 +83,10 @@ def _freeze(name, argtypes, args):
             vals = (C.c_int32 * n)(*[v[m] for m in range(n)])
             keep.append(vals)
             frozen.append(vals), desc.append(tuple(vals))
+        elif t is C.POINTER(C.c_double):  # the four physical constants of the column scans
+            vals = (C.c_double * 4)(*[v[m] for m in range(4)]) if v else None
+            keep.append(vals)
+            frozen.append(vals), desc.append(tuple(vals) if vals is not None else None)
         elif t in (C.c_double, C.c_int, C.c_uint32):
             frozen.append(v), desc.append(v)
         else:  # stream handles, config structs, raw buffers: passed through, not traced
@@ -164,7 +168,8 @@ class AbiStub:
 class FakeCapture:
     """Stands in for torch.cuda.CUDAGraph in tasmania_b200.graphs.GraphedLoop: ``capture`` records
     the ABI calls ``fn`` issues WITHOUT executing them (like stream capture), ``replay`` re-issues
-    them with the recorded arguments."""
+    them with the recorded arguments.  Slice assignments on storages (torch copy kernels on the
+    device, which stream capture records as well) are deferred in the same way."""
 
     stub = None  # set by the test
 
@@ -172,14 +177,24 @@ class FakeCapture:
         stub = self.stub
         assert stub.recording is None
         stub.recording = []
+        setitem = storage.B200Array.__setitem__
+
+        def deferred_setitem(array, idx, value):
+            stub.recording.append(("<setitem>", lambda: setitem(array, idx, value), None, None))
+
+        storage.B200Array.__setitem__ = deferred_setitem
         try:
             fn()
         finally:
+            storage.B200Array.__setitem__ = setitem
             self.recorded, stub.recording = stub.recording, None
 
     def replay(self):
         for name, frozen, desc, _keep in self.recorded:
-            self.stub._execute(name, frozen, desc)
+            if name == "<setitem>":
+                frozen()
+            else:
+                self.stub._execute(name, frozen, desc)
 
 
 def canonical(trace):
@@ -198,10 +213,11 @@ def canonical(trace):
 
 
 @contextlib.contextmanager
-def stubbed_library():
-    """``with stubbed_library() as stub:`` -- host storages + the recording ABI stub."""
+def stubbed_library(stub_cls=None):
+    """``with stubbed_library() as stub:`` -- host storages + the recording ABI stub (or a subclass
+    of it, e.g. tests/abi_oracle.py:OracleStub, which carries every call out with the oracle)."""
     saved = (lib._lib, lib.as_field, lib.current_stream, stencils._f, storage.DEFAULT_DEVICE_OVERRIDE)
-    stub = AbiStub()
+    stub = (stub_cls or AbiStub)()
     lib._lib, lib.as_field, lib.current_stream = stub, _host_field, lambda: 0
     stencils._f = _host_field
     storage.DEFAULT_DEVICE_OVERRIDE = "cpu"

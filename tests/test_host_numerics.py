@@ -1,0 +1,103 @@
+# -*- coding: utf-8 -*-
+"""The host side of the product run NUMERICALLY without a GPU: the library is replaced by
+tests/abi_oracle.py:OracleStub, which decodes every C-ABI call like the C side does and carries it
+out with the oracle on host buffers.  Mirrors, coupling layer, model assembly, marshalling of
+strides / flags / boxes, buffer rotation and CUDA-graph bookkeeping are thereby compared with the
+oracle's own models bit for bit (both sides are numpy).  The CUDA code itself is what the
+``-m gpu`` tests hold to the same oracle."""
+from datetime import datetime, timedelta
+
+import numpy as np
+
+from oracle import boundary as ob
+from oracle import isentropic as oi
+from oracle import moist_model as mm
+from tests import helpers as hp
+from tests.abi_oracle import OracleStub
+from tests.abi_stub import FakeCapture, stubbed_library
+
+
+def _oracle_moist(nx, ny, nz, grid, np_state):
+    ogrid = oi.Grid(nx, ny, nz, grid.dx, grid.dy, grid.dz, grid.z_on_interface_levels, grid.z)
+    ohb = ob.Relaxed(nx, ny, nz, 3, 6)
+    ohb.reference_state = {n: v.copy() for n, v in np_state.items()}
+    otopo = hp.Topography(grid.topography.steady_profile, 60.0)
+    model = mm.MoistIsentropicModel(ogrid, ohb, otopo, float(np_state[mm.P][0, 0, 0]), damp_depth=3)
+    st = {n: v.copy() for n, v in np_state.items()}
+    st[mm.W] = np.zeros_like(st[mm.S])
+    st["time"] = datetime(1992, 2, 20)
+    return model, st
+
+
+def test_moist_model_host_path_equals_oracle_numerically():
+    import tasmania_b200 as tb
+    from tasmania_b200.graphs import GraphedLoop
+    from tasmania_b200.isentropic_moist import IsentropicMoistSUS
+
+    nx, ny, nz, nsteps = 17, 15, 8, 4
+    dt = timedelta(seconds=5)
+    grid, np_state = hp.moist_case(nx, ny, nz)
+    omodel, ost = _oracle_moist(nx, ny, nz, grid, np_state)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for _ in range(nsteps):
+            ost = omodel.step(ost, dt)
+        for graphed in (False, True):
+            grid.topography._fact = 0.0
+            with stubbed_library(OracleStub) as stub:
+                FakeCapture.stub = stub
+                model = IsentropicMoistSUS(grid, np_state, dt, damp_depth=3)
+                if graphed:  # captured steps are replayed from the recorded calls
+                    loop = GraphedLoop(model, eager_steps=1, capture_factory=FakeCapture)
+                    loop.run(nsteps)
+                    assert loop.period == nsteps - 1
+                else:
+                    model.run(nsteps)
+                assert model.state["time"] == ost["time"]
+                assert set(model.state) == set(ost)
+                for n, v in ost.items():
+                    if n != "time":
+                        np.testing.assert_array_equal(tb.to_numpy(model.state[n]), v,
+                                                      err_msg=f"{n} (graphed={graphed})")
+    box = (slice(0, nx), slice(0, ny), slice(0, nz))
+    assert float(ost[mm.QR][box].max()) > 1e-5 and float(ost[mm.ACCPREC].max()) > 0.0
+
+
+def test_dry_run_host_path_equals_oracle_numerically():
+    """configs[1]'s loop through the per-stencil path of the dycore mirror."""
+    import tasmania_b200 as tb
+    from tasmania_b200.grid import Grid, Topography, gaussian_profile, isentropic_state_from_brunt_vaisala
+    from tasmania_b200.isentropic_dry import IsentropicDryRun
+
+    nx, ny, nz, nsteps = 19, 17, 6, 5
+    dt = timedelta(seconds=5)
+    x, y = np.linspace(-176.0, 176.0, nx), np.linspace(-176.0, 176.0, ny)
+    steady = gaussian_profile(x, y, 500.0, 50.0, 50.0)
+    grid = Grid((-176.0, 176.0), nx, (-176.0, 176.0), ny, (400.0, 280.0), nz, units_to_m=1e3,
+                topography=Topography(steady, timedelta(seconds=30)))
+    np_state = isentropic_state_from_brunt_vaisala(grid, 22.5, 0.0, 0.015)
+    pt = float(np_state[hp.P][0, 0, 0])
+    ogrid = oi.Grid(nx, ny, nz, grid.dx, grid.dy, grid.dz, grid.z_on_interface_levels, grid.z)
+    ohb = ob.Relaxed(nx, ny, nz, 3, 6)
+    ohb.reference_state = {n: v.copy() for n, v in np_state.items()}
+    otopo = hp.Topography(steady, 30.0)
+    odyc = oi.IsentropicDycore(ogrid, ohb, otopo, scheme="rk3ws_si", flux="fifth_order_upwind", pt=pt,
+                               eps=0.5, damp=True, damp_depth=2, damp_max=5e-4)
+    ost = {n: v.copy() for n, v in np_state.items()}
+    ost["time"] = datetime(2000, 1, 1)
+    for step in range(nsteps):
+        otopo.update((step + 1) * dt)
+        out = odyc(ost, {}, dt)
+        new = {n: out[n].copy() for n in (hp.S, hp.SU, hp.U, hp.SV, hp.V)}
+        new["time"] = out["time"]
+        for n in (hp.P, hp.EXN, hp.H, hp.MTG):
+            new[n] = ost[n].copy()
+        oi.refresh_diagnostics(ogrid, otopo(), new[hp.S], pt, new[hp.P], new[hp.EXN], new[hp.MTG], new[hp.H])
+        ost = new
+    with stubbed_library(OracleStub):
+        run = IsentropicDryRun(grid, np_state, dt, damp_depth=2)
+        run.dyc._fused = False  # the fused stage is one opaque ABI call: take the per-stencil path
+        for _ in range(nsteps):
+            run.step()
+        for n in (hp.S, hp.SU, hp.SV, hp.U, hp.V, hp.MTG, hp.P, hp.EXN, hp.H):
+            np.testing.assert_array_equal(tb.to_numpy(run.state[n]), ost[n], err_msg=n)
+    assert float(np.abs(ost[hp.SV]).max()) > 1e-6
