@@ -3,10 +3,14 @@
 ``IsentropicDynamicalCore.stage_array_call_dry`` and ``stage_array_call_moist``
 (src/tasmania/isentropic/dynamics/dycore.py:L641-L843) with the reference's own Domain, Relaxed boundary, state builder, RK3WSSI prognostic, Rayleigh damper
 HorizontalVelocity and WaterConstituent, all constructed with backend="b200" through the plugin -- is run for a full
-RK3WS step against the recording C-ABI stub (tests/abi_stub.py; storages on the host), and the
-sequence of ABI calls it issues (kernel, canonical buffer ids, scalars, boxes) is compared with the
-one the b200 host mirror (tasmania_b200.isentropic.IsentropicDynamicalCore, per-stencil path)
-issues from the same initial state.  Two representational differences are masked: the mirror
+RK3WS step against the oracle-backed C-ABI stub (tests/abi_oracle.py; storages on the host, every
+kernel call carried out by the oracle), from the initial state of the golden fixtures
+isen_{dry,moist}_rk3_5th.npz.  Two things are checked: (1) numerically, the first-stage outputs equal
+the fixtures' -- which the reference's numpy backend wrote -- bit for bit, i.e. the unmodified
+reference on backend b200 reproduces its own numpy backend through the plugin, the b200 stencil
+wrappers and their marshalling; (2) the sequence of ABI calls it issues (kernel, canonical buffer
+ids, scalars, boxes) is the one the b200 host mirror (tasmania_b200.isentropic.IsentropicDynamicalCore,
+per-stencil path) issues from the same initial state.  Two representational differences are masked: the mirror
 damps against the boundary's reference fields directly (the reference keeps copies) and stores
 the Rayleigh coefficient at rank 1.  The mirror's extra launches (outermost layers and topography
 factor as kernels instead of host-side slice assignments) are dropped from the comparison.
@@ -30,6 +34,7 @@ refload.install_framework()
 import generate_golden as gg  # noqa: E402
 import tasmania_b200 as tb  # noqa: E402
 from tasmania_b200 import plugin  # noqa: E402
+from tests.abi_oracle import OracleStub  # noqa: E402
 from tests.abi_stub import stubbed_library  # noqa: E402
 
 plugin.install(frame_relax=False)  # the reference-shaped boundary path on both sides
@@ -37,17 +42,30 @@ plugin.install(frame_relax=False)  # the reference-shaped boundary path on both 
 S, SU, SV = gg.S, gg.SU, gg.SV
 U, V, MTG = "x_velocity_at_u_locations", "y_velocity_at_v_locations", "montgomery_potential"
 P = gg.P
-NX, NY, NZ, NB, NR = 25, 21, 8, 3, 6
+NB, NR = 3, 6
 SCHEME, FLUX = "rk3ws_si", "fifth_order_upwind"
-SHAPE = (NX + 1, NY + 1, NZ + 1)
+# the golden fixtures of these very configurations, written by the reference's numpy backend
+# (tests/golden/generate_golden.py): their initial states are used, their first-stage outputs
+# are what the b200-backend run must reproduce numerically
+FIXTURES = {False: "isen_dry_rk3_5th", True: "isen_moist_rk3_5th"}
+NX = NY = NZ = SHAPE = None  # set per case from the fixture
+
+
+def set_case(moist):
+    global NX, NY, NZ, SHAPE
+    fx = np.load(os.path.join(ROOT, "tests", "golden", FIXTURES[moist] + ".npz"))
+    NX, NY, NZ = (int(v) for v in fx["dims"][:3])
+    assert tuple(int(v) for v in fx["dims"][3:5]) == (NB, NR) and int(fx["dims"][6]) == 4
+    SHAPE = (NX + 1, NY + 1, NZ + 1)
+    return fx
 DT = timedelta(seconds=5)
 OUTNAMES = (S, SU, U, SV, V)
 QNAMES = (gg.MFWV, gg.MFCW, gg.MFPW)
 
 
-def reference_trace(stub, moist):
+def reference_trace(stub, moist, fx):
     """One RK3WS step of the reference's own dycore stage on backend b200; returns the ABI trace,
-    the initial state as numpy arrays and the model-top pressure."""
+    the initial state as numpy arrays, the model-top pressure and the first-stage outputs."""
     from tasmania.framework import allocators as ta
     from tasmania.framework.generic_functions import to_numpy
 
@@ -70,12 +88,12 @@ def reference_trace(stub, moist):
         grid, datetime(2000, 1, 1), da(22.5, "m s^-1"), da(0.0, "m s^-1"), da(0.015, "s^-1"),
         moist=False, backend="b200", storage_shape=SHAPE)
     assert all(isinstance(v.data, tb.B200Array) for k, v in state.items() if k != "time")
-    if moist:  # seeded water species (like tests/golden/generate_golden.py does for the moist fixtures)
-        rng = np.random.default_rng(12)
-        for n, scale in zip(QNAMES, (8e-3, 1e-3, 5e-4)):
-            q = scale * rng.uniform(0.0, 1.0, SHAPE)
-            q[NX:, :, :] = q[:, NY:, :] = q[:, :, NZ:] = 0.0
-            state[n] = DataArray(ta.as_storage("b200", data=q), attrs={"units": "g g^-1"})
+    for n in list(state):  # the builder's own state equals the fixture's initial state
+        if n != "time":
+            assert np.array_equal(to_numpy(state[n].data), fx["init_" + n]), n
+    if moist:  # the seeded water species of the moist fixture
+        for n in QNAMES:
+            state[n] = DataArray(ta.as_storage("b200", data=fx["init_" + n]), attrs={"units": "g g^-1"})
     hb = domain.horizontal_boundary
     hb.reference_state = state
     assert isinstance(hb._gamma, tb.B200Array)
@@ -128,7 +146,8 @@ def reference_trace(stub, moist):
         st_in = dict(outs[stage])
         st_in.setdefault(MTG, cur[MTG])
     trace, stub.trace = stub.trace, None
-    return trace, {k: to_numpy(v.data) for k, v in state.items() if k != "time"}, pt
+    stage0 = {k: to_numpy(v) for k, v in outs[0].items() if k != "time"}
+    return trace, {k: to_numpy(v.data) for k, v in state.items() if k != "time"}, pt, stage0
 
 
 def mirror_trace(stub, np_state, pt, moist):
@@ -195,11 +214,16 @@ EXPECTED = {
 }
 done = []
 for moist_case in (False, True):
-    with stubbed_library() as the_stub:
-        ref_trace, initial, p_top = reference_trace(the_stub, moist_case)
+    fixture = set_case(moist_case)
+    # the oracle carries the kernels out on the host buffers: the run is numerical
+    with stubbed_library(OracleStub) as the_stub:
+        ref_trace, initial, p_top, first_stage = reference_trace(the_stub, moist_case, fixture)
         counts = collections.Counter(n for n, _ in ref_trace)
         assert counts == EXPECTED[moist_case], counts
         mir_trace = mirror_trace(the_stub, initial, p_top, moist_case)
+    # the unmodified reference dycore on backend b200 reproduces its own numpy backend
+    for name, got in first_stage.items():
+        assert np.array_equal(got, fixture["stage0_" + name]), (moist_case, name)
     a, b = reduce(ref_trace), reduce(mir_trace)
     assert len(a) == len(b) == sum(EXPECTED[moist_case].values()), (len(a), len(b))
     for n, (p, q) in enumerate(zip(a, b)):
