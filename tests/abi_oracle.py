@@ -13,6 +13,7 @@ what this cannot check is the CUDA code, which the ``-m gpu`` tests hold to the 
 import numpy as np
 
 from oracle import boundary as ob
+from oracle import burgers as obu
 from oracle import dwarfs
 from oracle import isentropic as oi
 from oracle import isentropic_physics as op
@@ -75,6 +76,18 @@ class OracleStub(AbiStub):
         else:  # L177-L191
             f[:mi, 0] = r[:mi, 0]
             f[:mi, mj - 1] = r[:mi, mj - 1]
+
+    def _do_tb200_periodic_enforce(self, field, nx, ny, nb, mx, my, stream):
+        stag = {(True, True): "at_uv_locations", (True, False): "at_u_locations",
+                (False, True): "at_v_locations", (False, False): ""}[(mx > nx, my > ny)]
+        ob.Periodic(nx, ny, 1, nb).enforce_field(arr(field), stag)
+
+    # ---- K10
+    def _do_tb200_burgers_forward_euler(self, order, u, v, u_tmp, v_tmp, out_u, out_v, u_tnd, v_tnd, dt, dx, dy,
+                                        o, d, stream):
+        origin, domain = box(o, d)
+        obu.forward_euler(order, arr(u), arr(v), arr(u_tmp), arr(v_tmp), arr(out_u), arr(out_v), dt=dt, dx=dx,
+                          dy=dy, origin=origin, domain=domain, u_tnd=arr(u_tnd), v_tnd=arr(v_tnd))
 
     # ---- K6, K4, K7
     def _do_tb200_damping(self, now, new, ref, rmat, out, dt, o, d, stream):

@@ -101,3 +101,77 @@ def test_dry_run_host_path_equals_oracle_numerically():
         for n in (hp.S, hp.SU, hp.SV, hp.U, hp.V, hp.MTG, hp.P, hp.EXN, hp.H):
             np.testing.assert_array_equal(tb.to_numpy(run.state[n]), ost[n], err_msg=n)
     assert float(np.abs(ost[hp.SV]).max()) > 1e-6
+
+
+def test_burgers_host_path_equals_oracle_numerically():
+    """configs[0]: the Burgers mirror (stepper, dycore, Dirichlet boundary with the Zhao core)."""
+    import tasmania_b200 as tb
+    from oracle import burgers as obu
+    from tasmania_b200.boundary import Dirichlet
+    from tasmania_b200.burgers import BurgersDynamicalCore, ZhaoSolutionFactory
+    from tasmania_b200.grid import Grid
+
+    nx = ny = 41
+    eps, nb, nsteps = 0.01, 2, 30
+    t0, dt = datetime(2000, 1, 1), timedelta(seconds=0.001)
+    grid = Grid((0.0, 1.0), nx, (0.0, 1.0), ny, (0.0, 1.0), 1)
+    zsf = ZhaoSolutionFactory(t0, eps)
+    host = {n: np.array(zsf(t0, grid, field_name=n)) for n in ("x_velocity", "y_velocity")}
+    odyc = obu.BurgersDycore(
+        nx, ny, grid.dx, grid.dy, nb, scheme="rk3ws", flux="third_order",
+        dirichlet=lambda time, sx, sy, name: obu.zhao_solution((time - t0).total_seconds(), grid.x[sx],
+                                                                grid.y[sy], eps, name))
+    ost = {n: a.copy() for n, a in host.items()}
+    ost["time"] = t0
+    for _ in range(nsteps):
+        out = odyc(ost, {}, dt)
+        ost = {"x_velocity": out["x_velocity"].copy(), "y_velocity": out["y_velocity"].copy(),
+               "time": out["time"]}
+    with stubbed_library(OracleStub) as stub:
+        hb = Dirichlet(nx, ny, 1, nb, core=zsf, grid=grid)
+        state = {n: tb.as_storage(a) for n, a in host.items()}
+        state["time"] = t0
+        hb.reference_state = state
+        dyc = BurgersDynamicalCore(grid, hb, "rk3ws", "third_order")
+        for _ in range(nsteps):
+            out = dyc(state, {}, dt)
+            state = {"x_velocity": out["x_velocity"].copy(), "y_velocity": out["y_velocity"].copy(),
+                     "time": out["time"]}
+        assert stub.count("tb200_burgers_forward_euler") == 3 * nsteps
+        assert state["time"] == ost["time"]
+        for n in ("x_velocity", "y_velocity"):
+            np.testing.assert_array_equal(tb.to_numpy(state[n]), ost[n], err_msg=n)
+
+
+def test_diffusion_dwarf_with_periodic_boundaries_equals_oracle_numerically():
+    """configs[3] in miniature: fourth-order horizontal diffusion, periodic halo, phi <- phi + dt tnd."""
+    import tasmania_b200 as tb
+    from oracle import dwarfs
+    from tasmania_b200 import stencils
+    from tasmania_b200.boundary import Periodic
+    from tasmania_b200.dwarfs import HorizontalDiffusion
+
+    nx, ny, nz, nb, dt, napp = 24, 20, 6, 2, 0.05, 5
+    phi0 = np.random.default_rng(20261018).standard_normal((nx, ny, nz))
+    ohb = ob.Periodic(nx, ny, nz, nb)
+    ophi = ohb.get_numerical_field(phi0.copy())
+    shape = ophi.shape
+    gamma = np.zeros(shape)
+    gamma[...] = dwarfs.vertical_profile(0.5, 1.0, 3, nz)[None, None, :]
+    for _ in range(napp):
+        tnd = np.zeros(shape)
+        dwarfs.diffusion(4, ophi, gamma, tnd, 1.0, 1.0, True, (nb, nb, 0), (nx, ny, nz))
+        ophi = ophi + dt * tnd
+        ohb.enforce_field(ophi)
+    with stubbed_library(OracleStub) as stub:
+        hb = Periodic(nx, ny, nz, nb)
+        phi = tb.as_storage(np.array(hb.get_numerical_field(tb.as_storage(phi0))))
+        assert phi.shape == shape
+        diff = HorizontalDiffusion.factory("fourth_order", shape, 1.0, 1.0, 0.5, 1.0, 3, nb)
+        tnd = tb.zeros(shape)
+        for _ in range(napp):
+            diff(phi, tnd, overwrite_output=True)
+            stencils.fma_fields([phi], [phi], [tnd], dt, origin=(0, 0, 0), domain=shape)
+            hb.enforce_field(phi)
+        assert stub.count("tb200_diffusion") == napp and stub.count("tb200_periodic_enforce") >= napp
+        np.testing.assert_array_equal(tb.to_numpy(phi), ophi)
