@@ -153,6 +153,42 @@ class OracleStub(AbiStub):
         oi.density_and_temperature(arr(theta), arr(s), arr(exn), arr(h), arr(rho), arr(t), origin=origin,
                                    domain=domain, constants=dict(oi.CONSTANTS, cp=cp))
 
+    # ---- the fused dry RK stage (csrc/isentropic_fused.cu): what dycore.py:L641-L721 over
+    # rk3ws_si.py:L105-L234 computes for one stage, from the same arguments the kernels get
+    def _do_tb200_isentropic_stage_dry(self, cfg, s_now, su_now, sv_now, mtg_now, s_int, su_int, sv_int, u_int,
+                                       v_int, s_new, su_new, sv_new, u_new, v_new, s_ref, su_ref, sv_ref,
+                                       u_ref, v_ref, gamma2d, rmat, topo2d, scr0, scr1, scr2, stream):
+        c = cfg.contents
+        assert c.part == 0, "the overlap parts of a decomposed run are not emulated"
+        nx, ny, nz, nb = c.nx, c.ny, c.nz, c.nb
+        flux = FLUX_NAMES[c.flux_scheme]
+        out = {n: arr(x) for n, x in (("s", s_new), ("su", su_new), ("sv", sv_new), ("u", u_new), ("v", v_new))}
+        shape = out["s"].shape
+        gamma = np.broadcast_to(arr(gamma2d)[:, :, :1], shape)
+        origin, domain = (nb, nb, 0), (nx - 2 * nb, ny - 2 * nb, nz)
+        oi.step_forward_euler(flux, arr(s_now), arr(s_int), out["s"], arr(u_int), arr(v_int), dt=c.dt,
+                              dx=c.dx, dy=c.dy, origin=origin, domain=domain)
+        ob.irelax(gamma, arr(s_ref), out["s"], (0, 0, 0), (nx, ny, nz))
+        hs = np.zeros(shape)
+        hs[:, :, nz] = arr(topo2d)[: shape[0], : shape[1], 0]
+        mtg_new = np.zeros(shape)
+        oi.montgomery(hs, out["s"], mtg_new, dz=c.dz, pt=c.pt, theta_s=c.theta_s, origin=(0, 0, 0),
+                      domain=(nx, ny, nz + 1), constants=constants(c.constants))
+        oi.step_forward_euler_momentum(
+            flux, arr(s_now), out["s"], arr(u_int), arr(v_int), arr(su_now), arr(su_int), out["su"], arr(sv_now),
+            arr(sv_int), out["sv"], arr(mtg_now), mtg_new, dt=c.dt, dx=c.dx, dy=c.dy, eps=c.eps, origin=origin,
+            domain=domain)
+        for n, ref in (("s", s_ref), ("su", su_ref), ("sv", sv_ref)):  # enforce_raw (u, v are re-diagnosed)
+            ob.irelax(gamma, arr(ref), out[n], (0, 0, 0), (nx, ny, nz))
+        if c.damp:
+            r = np.broadcast_to(arr(rmat)[:1, :1, :], shape)
+            for n, now, ref in (("s", s_now, s_ref), ("su", su_now, su_ref), ("sv", sv_now, sv_ref)):
+                dwarfs.damping(arr(now), out[n], arr(ref), r, out[n], c.dt_full, (0, 0, 0), shape)
+        dwarfs.get_velocity_components(nx, ny, nz, out["s"], out["su"], out["sv"], out["u"], out["v"])
+        ur, vr = arr(u_ref), arr(v_ref)
+        out["u"][0, :ny], out["u"][nx, :ny] = ur[0, :ny], ur[nx, :ny]        # relaxed.py:L161-L175
+        out["v"][:nx, 0], out["v"][:nx, ny] = vr[:nx, 0], vr[:nx, ny]        # L177-L191
+
     # ---- K11
     def _do_tb200_kessler(self, rho, p, t, exn, qc, qr, qv, t_qc, t_qr, t_qv, t_th, a, k1, k2, beta, lhvw, flags,
                           o, d, stream):

@@ -83,6 +83,12 @@ def _freeze(name, argtypes, args):
             vals = (C.c_int32 * n)(*[v[m] for m in range(n)])
             keep.append(vals)
             frozen.append(vals), desc.append(tuple(vals))
+        elif t is C.POINTER(lib.StageCfg):  # configuration block of the fused stage
+            cfg = lib.StageCfg.from_buffer_copy(v.contents)
+            keep.append(cfg)
+            frozen.append(C.pointer(cfg))
+            desc.append(tuple(getattr(cfg, f) if not hasattr(getattr(cfg, f), "__len__")
+                              else tuple(getattr(cfg, f)) for f, _ in lib.StageCfg._fields_))
         elif t is C.POINTER(C.c_double):  # the four physical constants of the column scans
             vals = (C.c_double * 4)(*[v[m] for m in range(4)]) if v else None
             keep.append(vals)

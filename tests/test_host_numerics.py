@@ -175,3 +175,65 @@ def test_diffusion_dwarf_with_periodic_boundaries_equals_oracle_numerically():
             hb.enforce_field(phi)
         assert stub.count("tb200_diffusion") == napp and stub.count("tb200_periodic_enforce") >= napp
         np.testing.assert_array_equal(tb.to_numpy(phi), ophi)
+
+
+def test_fused_stage_host_path_equals_oracle_numerically():
+    """The headline path's host side: IsentropicDryRun with the fused stage (one ABI call per RK
+    stage carrying 25 fields and the stage configuration), emulated stage by stage with the oracle."""
+    import tasmania_b200 as tb
+    from tasmania_b200.graphs import GraphedLoop
+    from tasmania_b200.grid import Grid, Topography, gaussian_profile, isentropic_state_from_brunt_vaisala
+    from tasmania_b200.isentropic_dry import IsentropicDryRun
+
+    nx, ny, nz, nsteps = 19, 17, 6, 5
+    dt = timedelta(seconds=5)
+    x, y = np.linspace(-176.0, 176.0, nx), np.linspace(-176.0, 176.0, ny)
+    steady = gaussian_profile(x, y, 500.0, 50.0, 50.0)
+
+    def case():
+        grid = Grid((-176.0, 176.0), nx, (-176.0, 176.0), ny, (400.0, 280.0), nz, units_to_m=1e3,
+                    topography=Topography(steady, timedelta(seconds=30)))
+        return grid, isentropic_state_from_brunt_vaisala(grid, 22.5, 0.0, 0.015)
+
+    results = {}
+    for mode in ("stencils", "fused", "fused+graphs"):
+        grid, np_state = case()
+        with stubbed_library(OracleStub) as stub:
+            FakeCapture.stub = stub
+            run = IsentropicDryRun(grid, np_state, dt, damp_depth=2)
+            assert run.dyc._fused
+            if mode == "stencils":
+                run.dyc._fused = False
+            stepper = GraphedLoop(run, eager_steps=1, capture_factory=FakeCapture) if "graphs" in mode else run
+            for _ in range(nsteps):
+                stepper.step()
+            if mode == "fused":
+                assert stub.count("tb200_isentropic_stage_dry") == 3 * nsteps
+            if mode == "fused+graphs":  # two buffer configurations captured, the rest replayed
+                assert stepper.period == 2 and stepper.replayed_launches >= 4 * (nsteps - 1)
+            results[mode] = {n: tb.to_numpy(v) for n, v in run.state.items() if n != "time"}
+    for mode in ("fused", "fused+graphs"):
+        for n, v in results["stencils"].items():
+            np.testing.assert_array_equal(results[mode][n], v, err_msg=f"{mode}: {n}")
+    assert float(np.abs(results["fused"][hp.SV]).max()) > 1e-6
+
+
+def test_decomposed_run_host_path_equals_single_domain_numerically():
+    """SURVEY.md section 8e on the host: a 2 x 2 (and 3 x 1) decomposition stepped sub-domain by sub-domain
+    with halo exchanges equals the single-domain run bit for bit (kernels emulated by the oracle)."""
+    from tasmania_b200.distributed import InProcessDecomposedRun
+
+    nxg, nyg, nz, nsteps = 37, 31, 5, 3
+    kw = dict(damp_depth=2, topo_seconds=15.0, device="cpu")
+    with stubbed_library(OracleStub):
+        single = InProcessDecomposedRun(nxg, nyg, nz, 1, 1, **kw)
+        for _ in range(nsteps):
+            single.step()
+        want = {n: single.gather(n) for n in single.subs[0].names}
+        for px, py in ((2, 2), (3, 1)):
+            run = InProcessDecomposedRun(nxg, nyg, nz, px, py, **kw)
+            for _ in range(nsteps):
+                run.step()
+            for n, v in want.items():
+                np.testing.assert_array_equal(run.gather(n), v, err_msg=f"{px}x{py}: {n}")
+    assert float(np.abs(want["y_momentum_isentropic"]).max()) > 1e-6
