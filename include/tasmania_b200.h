@@ -158,6 +158,22 @@ int tb200_smoothing(int order, const tb200_field *in_phi, const tb200_field *in_
                     tb200_field *out_phi, int rim_copy, const int32_t origin[3],
                     const int32_t domain[3], void *stream);
 
+/* ---- K8 / K9, one-dimensional variants: SecondOrder1DX / 1DY (second_order.py:L150-L219,
+ * L261-L330), FourthOrder1DX / 1DY (fourth_order.py:L196-L277, L333-L414) of the diffusers and
+ * FirstOrder1DX / 1DY (first_order.py:L141-L218, L233-L310), SecondOrder1DX / 1DY
+ * (second_order.py:L163-L247, L267-L351), ThirdOrder1DX / 1DY (third_order.py:L175-L263,
+ * L285-L373) of the smoothers.  axis = 0 (x) | 1 (y) is the axis the stencil runs along; h is
+ * the grid spacing along it (the reference's definitions receive dx and dy and use one).
+ * Same k-range and rim_copy conventions as the two-dimensional entry points (a 1-D smoother
+ * copies the two rim slabs across its axis: first_order.py:L187-L204). */
+int tb200_diffusion_1d(int order, int axis, const tb200_field *in_phi,
+                       const tb200_field *in_gamma, tb200_field *out_phi, double h,
+                       int ow_out_phi, const int32_t origin[3], const int32_t domain[3],
+                       void *stream);
+int tb200_smoothing_1d(int order, int axis, const tb200_field *in_phi,
+                       const tb200_field *in_gamma, tb200_field *out_phi, int rim_copy,
+                       const int32_t origin[3], const int32_t domain[3], void *stream);
+
 /* ---- K1 / K2 isentropic prognostic step: src/tasmania/isentropic/dynamics/subclasses/
  * prognostics/utils.py:L43-L134 and L137-L204.  The moist tracers are passed as arrays of
  * three field pointers (qv, qc, qr order); NULL arrays = dry. */

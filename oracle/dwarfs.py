@@ -6,6 +6,7 @@ Follows
   src/tasmania/dwarfs/diagnostics.py:L175-L272 (momenta, velocity_x/y), L400-L450 (density, mass_fraction)
   src/tasmania/dwarfs/horizontal_diffusion.py:L89-L109, subclasses/horizontal_diffusers/{second,fourth}_order.py
   src/tasmania/dwarfs/horizontal_smoothing.py:L83-L94, subclasses/horizontal_smoothers/{first,second,third}_order.py
+  (the one-dimensional ..._1dx / ..._1dy variants of both included)
   src/tasmania/framework/subclasses/stencil_definitions/{copy,math,algorithms}.py
 """
 import math
@@ -178,6 +179,67 @@ def horizontal_smoothing(order, phi, gamma, out, shape=None):
         ((nb, ny - nb, 0), (nx - 2 * nb, nb, nz)),
     ):
         copy(phi, out, o, d)
+
+
+# ------------------------------------------------------------------ K8 / K9, 1-D variants
+def diffusion_1d(order, axis, phi, gamma, out, h, overwrite, origin, domain):
+    """SecondOrder1DX / 1DY (horizontal_diffusers/second_order.py:L210-L219, L321-L330) and
+    FourthOrder1DX / 1DY (fourth_order.py:L256-L277, L393-L414): the stencil along one axis,
+    ``gamma * (...) / (h * h)`` with the product first; every k present is processed."""
+    i0, j0 = origin[0], origin[1]
+    i1, j1 = i0 + domain[0], j0 + domain[1]
+
+    def at(m):
+        di, dj = (m, 0) if axis == 0 else (0, m)
+        return phi[i0 + di : i1 + di, j0 + dj : j1 + dj]
+
+    g = gamma[i0:i1, j0:j1]
+    if order == 2:
+        tmp = g * (at(-1) - 2.0 * at(0) + at(1)) / (h * h)
+    elif order == 4:
+        tmp = g * (-at(-2) + 16.0 * at(-1) - 30.0 * at(0) + 16.0 * at(1) - at(2)) / (12.0 * h * h)
+    else:
+        raise ValueError(order)
+    out[i0:i1, j0:j1] = tmp if overwrite else out[i0:i1, j0:j1] + tmp
+
+
+def smoothing_1d(order, axis, phi, gamma, out, origin, domain):
+    """FirstOrder1DX / 1DY (horizontal_smoothers/first_order.py:L209-L218, L301-L310),
+    SecondOrder1DX / 1DY (second_order.py:L231-L247, L335-L351), ThirdOrder1DX / 1DY
+    (third_order.py:L243-L263, L353-L373)."""
+    c = _sh(origin, domain)
+
+    def at(m):
+        return phi[_sh(origin, domain, m, 0) if axis == 0 else _sh(origin, domain, 0, m)]
+
+    g = gamma[c]
+    if order == 1:
+        out[c] = (1.0 - 0.5 * g) * phi[c] + 0.25 * g * (at(-1) + at(1))
+    elif order == 2:
+        out[c] = (1.0 - 0.375 * g) * phi[c] + 0.0625 * g * (
+            -at(-2) + 4.0 * at(-1) - at(2) + 4.0 * at(1)
+        )
+    elif order == 3:
+        out[c] = (1.0 - 0.3125 * g) * phi[c] + 0.015625 * g * (
+            at(-3) - 6.0 * at(-2) + 15.0 * at(-1) + at(3) - 6.0 * at(2) + 15.0 * at(1)
+        )
+    else:
+        raise ValueError(order)
+
+
+def horizontal_smoothing_1d(order, axis, phi, gamma, out, shape=None):
+    """The 1-D smoothers' ``__call__`` (e.g. first_order.py:L170-L205, L262-L297): smoothing
+    on the interior along the axis + the two rim copies across it."""
+    nx, ny, nz = shape or phi.shape
+    nb = order
+    if axis == 0:
+        smoothing_1d(order, 0, phi, gamma, out, (nb, 0, 0), (nx - 2 * nb, ny, nz))
+        copy(phi, out, (0, 0, 0), (nb, ny, nz))
+        copy(phi, out, (nx - nb, 0, 0), (nb, ny, nz))
+    else:
+        smoothing_1d(order, 1, phi, gamma, out, (0, nb, 0), (nx, ny - 2 * nb, nz))
+        copy(phi, out, (0, 0, 0), (nx, nb, nz))
+        copy(phi, out, (0, ny - nb, 0), (nx, nb, nz))
 
 
 # ------------------------------------------------------------------ K12 elementwise

@@ -120,6 +120,83 @@ int launch_cross(const char *what, View phi, View gam, View out, double dx, doub
   return check_launch(what);
 }
 
+
+// ---- one-dimensional variants (second_order_1dx / _1dy, fourth_order_1dx / _1dy of the
+// diffusers, first..third_order_1dx / _1dy of the smoothers): the stencil runs along ONE
+// horizontal axis, for grids that are a single row or column of points.  Such grids are small
+// (n x 1 x nz), so there is nothing to stage: one thread per point, neighbours straight from
+// L1/L2.  The association of the reference's 1-D formulas differs from the 2-D ones
+// (`gamma * (...) / (dx * dx)`: the product first), hence separate code rather than a flag.
+template <int OP>
+struct LineOp {
+  View phi, gam, out;
+  CDiv den;
+  int si, sj;  // unit step along the stencil axis
+  int overwrite, rim;
+  int bi, bj, i0, j0, k0, di, dj;
+  __device__ __forceinline__ double at(int i, int j, int k, int m) const {
+    return phi.ld(i + m * si, j + m * sj, k);
+  }
+  __device__ void operator()(int ri, int rj, int rk) const {
+    const int i = bi + ri, j = bj + rj, k = k0 + rk;
+    const double c = phi.ld(i, j, k);
+    const bool inside = i >= i0 && i < i0 + di && j >= j0 && j < j0 + dj;
+    if (!inside) {
+      if (rim) out(i, j, k) = c;  // the two `copy` launches of the 1-D smoothers' __call__
+      return;
+    }
+    const double g = gam.ld(i, j, k);
+    double r;
+    if (OP == 2) {  // diffusers/second_order.py:L218, L329
+      r = g * (at(i, j, k, -1) - 2.0 * c + at(i, j, k, 1)) / den;
+    } else if (OP == 4) {  // diffusers/fourth_order.py:L265-L275, L402-L412
+      r = g * (-at(i, j, k, -2) + 16.0 * at(i, j, k, -1) - 30.0 * c + 16.0 * at(i, j, k, 1) -
+               at(i, j, k, 2)) / den;
+    } else if (OP == 11) {  // smoothers/first_order.py:L216-L218, L308-L310
+      r = (1.0 - 0.5 * g) * c + 0.25 * g * (at(i, j, k, -1) + at(i, j, k, 1));
+    } else if (OP == 12) {  // smoothers/second_order.py:L240-L247, L344-L351
+      r = (1.0 - 0.375 * g) * c +
+          0.0625 * g * (-at(i, j, k, -2) + 4.0 * at(i, j, k, -1) - at(i, j, k, 2) + 4.0 * at(i, j, k, 1));
+    } else {  // smoothers/third_order.py:L254-L263, L364-L373
+      r = (1.0 - 0.3125 * g) * c +
+          0.015625 * g * (at(i, j, k, -3) - 6.0 * at(i, j, k, -2) + 15.0 * at(i, j, k, -1) +
+                          at(i, j, k, 3) - 6.0 * at(i, j, k, 2) + 15.0 * at(i, j, k, 1));
+    }
+    if ((OP == 2 || OP == 4) && !overwrite) r = out(i, j, k) + r;  // generics.py:L38-L40
+    out(i, j, k) = r;
+  }
+};
+
+template <int OP>
+int launch_line(const char *what, View phi, View gam, View out, int axis, double h,
+                int overwrite, int rim, const int32_t o[3], const int32_t d[3], cudaStream_t st) {
+  // rim box = the smoother's shape along the stencil axis: nb + (n - 2 nb) + nb points
+  const int ri = 2 * o[0] + d[0], rj = 2 * o[1] + d[1];
+  LineOp<OP> op;
+  op.phi = phi; op.gam = gam; op.out = out;
+  // full denominators, evaluated as the reference does: h * h and 12.0 * h * h
+  op.den = make_cdiv(OP == 4 ? 12.0 * h * h : (OP == 2 ? h * h : 1.0));
+  op.si = axis == 0; op.sj = axis == 1;
+  op.overwrite = overwrite; op.rim = rim;
+  op.bi = rim ? 0 : o[0]; op.bj = rim ? 0 : o[1];
+  op.i0 = o[0]; op.j0 = o[1]; op.k0 = o[2]; op.di = d[0]; op.dj = d[1];
+  const int32_t ext[3] = {rim ? ri : d[0], rim ? rj : d[1], d[2]};
+  return launch_box(what, ext, st, op);
+}
+
+// argument checks shared by the two 1-D entry points: halo h along `axis` only
+int check_line(const char *what, const View &phi, const View &gam, const View &out, int axis,
+               int h, const int32_t origin[3], const int32_t domain[3]) {
+  TB200_REQUIRE(axis == 0 || axis == 1, "%s: axis must be 0 (x) or 1 (y) (got %d)", what, axis);
+  const int hx = axis == 0 ? h : 0, hy = axis == 1 ? h : 0;
+  TB200_REQUIRE(box_inside(phi, origin, domain, hx, hx, hy, hy),
+                "%s: in_phi box + halo %d along axis %d outside storage", what, h, axis);
+  TB200_REQUIRE(box_inside(gam, origin, domain) && box_inside(out, origin, domain),
+                "%s: gamma/out box outside storage", what);
+  TB200_REQUIRE(phi.p != out.p, "%s: in_phi and out_phi must not alias", what);
+  return TB200_OK;
+}
+
 }  // namespace
 
 extern "C" int tb200_diffusion(int order, const tb200_field *in_phi,
@@ -161,4 +238,35 @@ extern "C" int tb200_smoothing(int order, const tb200_field *in_phi,
   if (order == 2)
     return launch_cross<12>("smoothing2", phi, gam, out, 0, 0, 1, rim_copy, origin, domain, st);
   return launch_cross<13>("smoothing3", phi, gam, out, 0, 0, 1, rim_copy, origin, domain, st);
+}
+
+extern "C" int tb200_diffusion_1d(int order, int axis, const tb200_field *in_phi,
+                                  const tb200_field *in_gamma, tb200_field *out_phi, double h,
+                                  int ow_out_phi, const int32_t origin[3],
+                                  const int32_t domain[3], void *stream) {
+  View phi = view(in_phi), gam = view(in_gamma), out = view(out_phi);
+  TB200_REQUIRE(order == 2 || order == 4, "diffusion_1d: order must be 2 or 4 (got %d)", order);
+  if (int rc = check_line("diffusion_1d", phi, gam, out, axis, order / 2, origin, domain)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (order == 2)
+    return launch_line<2>("diffusion2_1d", phi, gam, out, axis, h, ow_out_phi, 0, origin, domain, st);
+  return launch_line<4>("diffusion4_1d", phi, gam, out, axis, h, ow_out_phi, 0, origin, domain, st);
+}
+
+extern "C" int tb200_smoothing_1d(int order, int axis, const tb200_field *in_phi,
+                                  const tb200_field *in_gamma, tb200_field *out_phi,
+                                  int rim_copy, const int32_t origin[3],
+                                  const int32_t domain[3], void *stream) {
+  View phi = view(in_phi), gam = view(in_gamma), out = view(out_phi);
+  TB200_REQUIRE(order >= 1 && order <= 3, "smoothing_1d: order must be 1..3 (got %d)", order);
+  if (int rc = check_line("smoothing_1d", phi, gam, out, axis, order, origin, domain)) return rc;
+  TB200_REQUIRE(!rim_copy || (2 * origin[0] + domain[0] <= phi.n0 && 2 * origin[0] + domain[0] <= out.n0 &&
+                              2 * origin[1] + domain[1] <= phi.n1 && 2 * origin[1] + domain[1] <= out.n1),
+                "smoothing_1d: rim box outside storage");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (order == 1)
+    return launch_line<11>("smoothing1_1d", phi, gam, out, axis, 0, 1, rim_copy, origin, domain, st);
+  if (order == 2)
+    return launch_line<12>("smoothing2_1d", phi, gam, out, axis, 0, 1, rim_copy, origin, domain, st);
+  return launch_line<13>("smoothing3_1d", phi, gam, out, axis, 0, 1, rim_copy, origin, domain, st);
 }

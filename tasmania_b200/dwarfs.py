@@ -4,6 +4,8 @@ class and method names:
 
   HorizontalDiffusion (second_order, fourth_order)  src/tasmania/dwarfs/horizontal_diffusion.py:L41-L175
   HorizontalSmoothing (first..third_order)          src/tasmania/dwarfs/horizontal_smoothing.py:L41-L134
+  (both with the one-dimensional ``..._1dx`` / ``..._1dy`` variants of the reference's
+  subclasses/horizontal_diffusers/*.py and subclasses/horizontal_smoothers/*.py)
   VerticalDamping (rayleigh)                        src/tasmania/dwarfs/vertical_damping.py:L46-L175
   HorizontalVelocity, WaterConstituent              src/tasmania/dwarfs/diagnostics.py:L44-L466
 
@@ -37,10 +39,26 @@ def vertical_profile(coeff, coeff_max, damp_depth, nk):
     return gamma
 
 
-class HorizontalDiffusion(StencilFactory):
-    """Tendency due to horizontal diffusion; ``factory("second_order" | "fourth_order", ...)``."""
+def _one_dimensional(orders):
+    """name -> (order, axis): the 2-D schemes (axis None) and their _1dx / _1dy variants"""
+    out = {name: (order, None) for name, order in orders.items()}
+    for name, order in orders.items():
+        out[name + "_1dx"], out[name + "_1dy"] = (order, 0), (order, 1)
+    return out
 
-    ORDERS = {"second_order": 2, "fourth_order": 4}
+
+def _interior(shape, nb, axis):
+    """origin and domain of the interior: nb points off both ends of the stencil axis (or axes)"""
+    nx, ny, nz = shape
+    bx, by = (nb if axis in (None, 0) else 0), (nb if axis in (None, 1) else 0)
+    return (bx, by, 0), (nx - 2 * bx, ny - 2 * by, nz)
+
+
+class HorizontalDiffusion(StencilFactory):
+    """Tendency due to horizontal diffusion; ``factory("second_order" | "fourth_order" |
+    "second_order_1dx" | ... | "fourth_order_1dy", ...)``."""
+
+    ORDERS = _one_dimensional({"second_order": 2, "fourth_order": 4})
 
     def __init__(self, diffusion_type, shape, dx, dy, diffusion_coeff, diffusion_coeff_max,
                  diffusion_damp_depth, nb=None, *, backend="b200", backend_options=None,
@@ -48,17 +66,18 @@ class HorizontalDiffusion(StencilFactory):
         super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
         if diffusion_type not in self.ORDERS:
             raise ValueError(f"unknown (or out-of-scope) diffusion type {diffusion_type!r}")
-        self.order = self.ORDERS[diffusion_type]
+        self.order, self.axis = self.ORDERS[diffusion_type]
         min_nb = self.order // 2
         nb = min_nb if (nb is None or nb < min_nb) else nb
         lb = 2 * nb + 1
-        assert shape[0] >= lb and shape[1] >= lb
+        assert all(shape[a] >= lb for a in (0, 1) if self.axis in (None, a))
         self._shape, self._nb, self._dx, self._dy = tuple(shape), nb, dx, dy
         gamma = vertical_profile(diffusion_coeff, diffusion_coeff_max, diffusion_damp_depth, shape[2])
         self._gamma1d, self._gamma = _profile_storage(gamma, shape, self.storage_options.device)
         self.backend_options.externals = {
             "set_output": self.get_subroutine_definition("set_output"),
             "diffusion_order": self.order,
+            "diffusion_axis": self.axis,
         }
         self._stencil = self.compile_stencil("diffusion")
 
@@ -67,32 +86,33 @@ class HorizontalDiffusion(StencilFactory):
         return cls(diffusion_type, *args, **kwargs)
 
     def __call__(self, phi, phi_tnd, *, overwrite_output=True):
-        nb = self._nb
-        nx, ny, nz = self._shape
+        origin, domain = _interior(self._shape, self._nb, self.axis)
         self._stencil(in_phi=phi, in_gamma=self._gamma, out_phi=phi_tnd, dx=self._dx, dy=self._dy,
-                      ow_out_phi=overwrite_output, origin=(nb, nb, 0),
-                      domain=(nx - 2 * nb, ny - 2 * nb, nz))
+                      ow_out_phi=overwrite_output, origin=origin, domain=domain)
 
 
 class HorizontalSmoothing(StencilFactory):
-    """Horizontal numerical smoothing; ``factory("first_order" | ... | "third_order", ...)``.
-    The reference's five launches (smoothing + four rim copies) are one kernel here."""
+    """Horizontal numerical smoothing; ``factory("first_order" | ... | "third_order" |
+    "first_order_1dx" | ... | "third_order_1dy", ...)``.
+    The reference's five launches (smoothing + four rim copies; three for a 1-D smoother) are
+    one kernel here."""
 
-    ORDERS = {"first_order": 1, "second_order": 2, "third_order": 3}
+    ORDERS = _one_dimensional({"first_order": 1, "second_order": 2, "third_order": 3})
 
     def __init__(self, smooth_type, shape, smooth_coeff, smooth_coeff_max, smooth_damp_depth,
                  nb=None, *, backend="b200", backend_options=None, storage_options=None):
         super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
         if smooth_type not in self.ORDERS:
             raise ValueError(f"unknown (or out-of-scope) smoothing type {smooth_type!r}")
-        self.order = self.ORDERS[smooth_type]
+        self.order, self.axis = self.ORDERS[smooth_type]
         nb = self.order if (nb is None or nb < self.order) else nb
         lb = 2 * nb + 1
-        assert shape[0] >= lb and shape[1] >= lb
+        assert all(shape[a] >= lb for a in (0, 1) if self.axis in (None, a))
         self._shape, self._nb = tuple(shape), nb
         gamma = vertical_profile(smooth_coeff, smooth_coeff_max, smooth_damp_depth, shape[2])
         self._gamma1d, self._gamma = _profile_storage(gamma, shape, self.storage_options.device)
-        self.backend_options.externals = {"smoothing_order": self.order, "rim_copy": True}
+        self.backend_options.externals = {"smoothing_order": self.order, "rim_copy": True,
+                                          "smoothing_axis": self.axis}
         self._stencil_smooth = self.compile_stencil("smoothing")
 
     @classmethod
@@ -100,10 +120,9 @@ class HorizontalSmoothing(StencilFactory):
         return cls(smooth_type, *args, **kwargs)
 
     def __call__(self, phi, phi_out):
-        nb = self._nb
-        nx, ny, nz = self._shape
+        origin, domain = _interior(self._shape, self._nb, self.axis)
         self._stencil_smooth(in_phi=phi, in_gamma=self._gamma, out_phi=phi_out,
-                             origin=(nb, nb, 0), domain=(nx - 2 * nb, ny - 2 * nb, nz))
+                             origin=origin, domain=domain)
 
 
 def rayleigh_coefficient(z_main, z_top, damp_depth, damp_max, nk):

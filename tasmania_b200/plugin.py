@@ -95,12 +95,14 @@ def _descriptor(scheme, name):
     return subroutine
 
 
-def _order_bound(definition, key, value, name):
-    """A class-scoped b200 definition with the class's order baked into the externals."""
+def _order_bound(definition, key, value, name, **more):
+    """A class-scoped b200 definition with the class's order (and, for the one-dimensional
+    variants, its axis) baked into the externals."""
 
     def bound(externals, **kwargs):
         ext = dict(externals)
         ext[key] = value
+        ext.update(more)
         return definition(ext, **kwargs)
 
     bound.__name__ = name
@@ -124,16 +126,20 @@ def _class_scoped_stencils():
         (dw, "HorizontalVelocity", "velocity_y", st.velocity_y_b200),
         (dw, "WaterConstituent", "density", st.density_b200),
         (dw, "WaterConstituent", "mass_fraction", st.mass_fraction_b200),
-        (hd + ".second_order", "SecondOrder", "diffusion",
-         _order_bound(st.diffusion_b200, "diffusion_order", 2, "diffusion_second_order_b200")),
-        (hd + ".fourth_order", "FourthOrder", "diffusion",
-         _order_bound(st.diffusion_b200, "diffusion_order", 4, "diffusion_fourth_order_b200")),
-        (hs + ".first_order", "FirstOrder", "smoothing",
-         _order_bound(st.smoothing_b200, "smoothing_order", 1, "smoothing_first_order_b200")),
-        (hs + ".second_order", "SecondOrder", "smoothing",
-         _order_bound(st.smoothing_b200, "smoothing_order", 2, "smoothing_second_order_b200")),
-        (hs + ".third_order", "ThirdOrder", "smoothing",
-         _order_bound(st.smoothing_b200, "smoothing_order", 3, "smoothing_third_order_b200")),
+    ]
+    # the 2-D schemes and their ..._1dx / ..._1dy variants (same modules)
+    for mod, cls, order in (("second_order", "SecondOrder", 2), ("fourth_order", "FourthOrder", 4)):
+        for sfx, axis in (("", None), ("1DX", 0), ("1DY", 1)):
+            out.append((f"{hd}.{mod}", cls + sfx, "diffusion",
+                        _order_bound(st.diffusion_b200, "diffusion_order", order,
+                                     f"diffusion_{mod}{'_' + sfx.lower() if sfx else ''}_b200", diffusion_axis=axis)))
+    for mod, cls, order in (("first_order", "FirstOrder", 1), ("second_order", "SecondOrder", 2),
+                            ("third_order", "ThirdOrder", 3)):
+        for sfx, axis in (("", None), ("1DX", 0), ("1DY", 1)):
+            out.append((f"{hs}.{mod}", cls + sfx, "smoothing",
+                        _order_bound(st.smoothing_b200, "smoothing_order", order,
+                                     f"smoothing_{mod}{'_' + sfx.lower() if sfx else ''}_b200", smoothing_axis=axis)))
+    out += [
         ("tasmania.dwarfs.subclasses.vertical_dampers.rayleigh", "Rayleigh", "damping",
          st.damping_b200),
         ("tasmania.burgers.dynamics.stepper", "BurgersStepper", "forward_euler",

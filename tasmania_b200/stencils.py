@@ -289,8 +289,15 @@ def diffusion_b200(externals, *, in_phi, in_gamma, out_phi, dx, dy, ow_out_phi, 
     if order not in (2, 4):
         raise lib.B200Error("externals['diffusion_order'] must be 2 or 4")
     o, d = _full_k(in_phi, origin, domain)
-    _call("tb200_diffusion", order, _f(in_phi), _f(in_gamma), _f(out_phi), float(dx), float(dy),
-          int(bool(ow_out_phi)), _i3(o), _i3(d), _stream())
+    axis = externals.get("diffusion_axis")  # None: both axes; 0 / 1: the ..._1dx / ..._1dy variants
+    if axis is None:
+        _call("tb200_diffusion", order, _f(in_phi), _f(in_gamma), _f(out_phi), float(dx), float(dy),
+              int(bool(ow_out_phi)), _i3(o), _i3(d), _stream())
+    elif axis in (0, 1):
+        _call("tb200_diffusion_1d", order, axis, _f(in_phi), _f(in_gamma), _f(out_phi),
+              float(dy if axis else dx), int(bool(ow_out_phi)), _i3(o), _i3(d), _stream())
+    else:
+        raise lib.B200Error("externals['diffusion_axis'] must be None, 0 or 1")
 
 
 @stencil_definition("smoothing")
@@ -298,8 +305,16 @@ def smoothing_b200(externals, *, in_phi, in_gamma, out_phi, origin, domain):
     order = externals.get("smoothing_order")
     if order not in (1, 2, 3):
         raise lib.B200Error("externals['smoothing_order'] must be 1, 2 or 3")
-    _call("tb200_smoothing", order, _f(in_phi), _f(in_gamma), _f(out_phi),
-          int(bool(externals.get("rim_copy", False))), _i3(origin), _i3(domain), _stream())
+    rim = int(bool(externals.get("rim_copy", False)))
+    axis = externals.get("smoothing_axis")
+    if axis is None:
+        _call("tb200_smoothing", order, _f(in_phi), _f(in_gamma), _f(out_phi), rim,
+              _i3(origin), _i3(domain), _stream())
+    elif axis in (0, 1):
+        _call("tb200_smoothing_1d", order, axis, _f(in_phi), _f(in_gamma), _f(out_phi), rim,
+              _i3(origin), _i3(domain), _stream())
+    else:
+        raise lib.B200Error("externals['smoothing_axis'] must be None, 0 or 1")
 
 
 # ------------------------------------------------------------------ K1 / K2

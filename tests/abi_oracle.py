@@ -107,6 +107,20 @@ class OracleStub(AbiStub):
     def _do_tb200_diffusion(self, order, phi, gamma, out, dx, dy, ow, o, d, stream):
         dwarfs.diffusion(order, arr(phi), arr(gamma), arr(out), dx, dy, bool(ow), *box(o, d))
 
+    def _do_tb200_diffusion_1d(self, order, axis, phi, gamma, out, h, ow, o, d, stream):
+        dwarfs.diffusion_1d(order, axis, arr(phi), arr(gamma), arr(out), h, bool(ow), *box(o, d))
+
+    def _do_tb200_smoothing_1d(self, order, axis, phi, gamma, out, rim_copy, o, d, stream):
+        origin, domain = box(o, d)
+        vin, vout = arr(phi), arr(out)
+        dwarfs.smoothing_1d(order, axis, vin, arr(gamma), vout, origin, domain)
+        if rim_copy:  # the two copies of a 1-D smoother's __call__, first_order.py:L187-L204
+            (i0, j0, k0), (di, dj, dk) = origin, domain
+            ni, nj, k = 2 * i0 + di, 2 * j0 + dj, slice(k0, k0 + dk)
+            rim = np.ones((ni, nj), dtype=bool)
+            rim[i0:i0 + di, j0:j0 + dj] = False
+            vout[:ni, :nj, k] = np.where(rim[:, :, None], vin[:ni, :nj, k], vout[:ni, :nj, k])
+
     def _do_tb200_smoothing(self, order, phi, gamma, out, rim_copy, o, d, stream):
         origin, domain = box(o, d)
         vin, vout = arr(phi), arr(out)

@@ -27,3 +27,8 @@ def golden(name):
 @pytest.fixture(scope="session")
 def stencils_golden():
     return golden("stencils")
+
+
+@pytest.fixture(scope="session")
+def stencils_1d_golden():
+    return golden("stencils_1d")

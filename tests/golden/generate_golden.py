@@ -54,6 +54,44 @@ def da(x, units):
     return DataArray(x, attrs={"units": units})
 
 
+# ============================================================================ 1-D dwarfs
+def gen_stencils_1d():
+    """K8 / K9, one-dimensional variants: the reference's SecondOrder1DX/1DY, FourthOrder1DX/1DY
+    diffusers and First/Second/ThirdOrder1DX/1DY smoothers, on a row (n x 1) and a column
+    (1 x n) of points and -- the classes accept it -- on a 2-D grid swept along one axis."""
+    rng = np.random.default_rng(20261019)
+    opts = refload.load("tasmania.framework.options")
+    for name in ("second_order", "fourth_order"):
+        refload.load("tasmania.dwarfs.subclasses.horizontal_diffusers." + name)
+    for name in ("first_order", "second_order", "third_order"):
+        refload.load("tasmania.dwarfs.subclasses.horizontal_smoothers." + name)
+    hd = refload.load("tasmania.dwarfs.horizontal_diffusion")
+    hsm = refload.load("tasmania.dwarfs.horizontal_smoothing")
+    dx, dy = 1100.0, 900.0
+    out = {"scalars": np.array([dx, dy])}
+    shapes = {"x": {"row": (19, 1, 5), "grid": (14, 6, 4)}, "y": {"row": (1, 21, 5), "grid": (7, 13, 4)}}
+    kw = dict(backend="numpy", backend_options=opts.BackendOptions(),
+              storage_options=opts.StorageOptions())
+    for ax in ("x", "y"):
+        for tag, shape in shapes[ax].items():
+            phi = rng.uniform(-5, 5, size=shape)
+            base = rng.uniform(-5, 5, size=shape)
+            out[f"{ax}_{tag}_phi"], out[f"{ax}_{tag}_base"] = phi, base
+            for order, name in ((2, "second_order"), (4, "fourth_order")):
+                obj = hd.HorizontalDiffusion.factory(f"{name}_1d{ax}", shape, dx, dy, 0.5, 1.0, 3, **kw)
+                tnd = np.zeros(shape)
+                obj(phi, tnd, overwrite_output=True)
+                acc = base.copy()
+                obj(phi, acc, overwrite_output=False)
+                out[f"k8_{order}_{ax}_{tag}_tnd"], out[f"k8_{order}_{ax}_{tag}_acc"] = tnd, acc
+            for order, name in ((1, "first_order"), (2, "second_order"), (3, "third_order")):
+                obj = hsm.HorizontalSmoothing.factory(f"{name}_1d{ax}", shape, 0.03, 0.24, 3, **kw)
+                sm = np.zeros(shape)
+                obj(phi, sm)
+                out[f"k9_{order}_{ax}_{tag}_out"] = sm
+    save("stencils_1d", **out)
+
+
 # ============================================================================ stencils
 def gen_stencils():
     """Per-stencil fixtures: K1, K2 (4 flux schemes), K3, K4, K5, K6, K7, K8, K9, K12."""
@@ -709,6 +747,9 @@ CASES = {
         "isen_moist_fe_3rd", 17, 21, 6, "forward_euler_si", "third_order_upwind", 2, 5, 3, 4.0,
         moist=True),
 }
+
+
+CASES["stencils_1d"] = gen_stencils_1d
 
 
 if __name__ == "__main__":

@@ -52,7 +52,8 @@ except FactoryRegistryError:
 # ---- class-scoped definitions on the reference's classes
 must = {"IsentropicDiagnostics:montgomery", "IsentropicDiagnostics:diagnostic_variables",
         "HorizontalVelocity:velocity_x", "WaterConstituent:density", "FourthOrder:diffusion",
-        "SecondOrder:smoothing", "Rayleigh:damping", "BurgersStepper:forward_euler",
+        "SecondOrder:smoothing", "SecondOrder1DX:diffusion", "FourthOrder1DY:diffusion",
+        "FirstOrder1DX:smoothing", "ThirdOrder1DY:smoothing", "Rayleigh:damping", "BurgersStepper:forward_euler",
         "FifthOrderUpwind:flux_dry", "ThirdOrder:advection"}
 missing = must - set(report["class_scoped"])
 assert not missing, (missing, report["skipped"])
@@ -202,6 +203,41 @@ with stubbed_library() as stub:
         assert np.array_equal(results["b200"][n], results["numpy"][n]), n
     assert np.array_equal(results["b200"][names[3]], fields[names[3]])       # not selected: untouched
     assert not np.array_equal(results["b200"][names[0]], fields[names[0]])
+
+# ---- the reference's one-dimensional diffusers / smoothers on backend b200 (their own __call__:
+# the stencil + the rim copies), carried out by the oracle behind the C ABI, against the same
+# classes on the numpy backend
+from tests.abi_oracle import OracleStub  # noqa: E402
+from tasmania.dwarfs.horizontal_smoothing import HorizontalSmoothing  # noqa: E402
+from tasmania.dwarfs.subclasses.horizontal_smoothers import first_order as _f1, third_order as _f3  # noqa: E402,F401
+from tasmania.dwarfs.subclasses.horizontal_smoothers import second_order as _f2  # noqa: E402,F401
+
+with stubbed_library(OracleStub) as stub:
+    rng = np.random.default_rng(5)
+    for ax, shape in (("x", (15, 1, 4)), ("y", (1, 16, 4)), ("x", (13, 5, 3)), ("y", (6, 14, 3))):
+        phi = rng.standard_normal(shape)
+        for name in ("second_order", "fourth_order"):
+            res = {}
+            for backend in ("numpy", "b200"):
+                obj = HorizontalDiffusion.factory(
+                    f"{name}_1d{ax}", shape, 1100.0, 900.0, 0.5, 1.0, 2, backend=backend,
+                    backend_options=BackendOptions(), storage_options=StorageOptions())
+                tnd = ta.zeros(backend, shape=shape)
+                obj(ta.as_storage(backend, data=phi), tnd)
+                res[backend] = np.array(to_numpy(tnd))
+            assert np.array_equal(res["b200"], res["numpy"]) and np.abs(res["numpy"]).max() > 0, (name, ax)
+        for name in ("first_order", "second_order", "third_order"):
+            res = {}
+            for backend in ("numpy", "b200"):
+                obj = HorizontalSmoothing.factory(
+                    f"{name}_1d{ax}", shape, 0.03, 0.24, 2, backend=backend,
+                    backend_options=BackendOptions(), storage_options=StorageOptions())
+                out = ta.zeros(backend, shape=shape)
+                obj(ta.as_storage(backend, data=phi), out)
+                res[backend] = np.array(to_numpy(out))
+            assert np.array_equal(res["b200"], res["numpy"]), (name, ax)
+    assert stub.count("tb200_diffusion_1d") == 8 and stub.count("tb200_smoothing_1d") == 12
+    assert stub.count("tb200_diffusion") == 0 and stub.count("tb200_smoothing") == 0
 
 print("PLUGIN-OK", len(report["global"]), len(report["class_scoped"]), len(report["skipped"]))
 for s in report["skipped"]:

@@ -1,0 +1,95 @@
+# -*- coding: utf-8 -*-
+"""Parity of the one-dimensional diffusers and smoothers (``..._1dx`` / ``..._1dy``;
+``tb200_diffusion_1d`` / ``tb200_smoothing_1d``, csrc/horizontal.cu) against (a) the fixture the
+reference's own classes wrote (tests/golden/stencils_1d.npz) and (b) the oracle on ragged sizes.
+No libm calls: BIT-EXACT.
+
+The file sorts last on purpose: these kernels were added at the end of round 1, after the
+round's GPU minutes were spent (built and checked with cuobjdump here, host path checked
+numerically through the oracle-backed ABI stub), so their first run on a B200 is the driver's.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import tasmania_b200 as tb  # noqa: E402
+from oracle import dwarfs as od  # noqa: E402
+from tasmania_b200.dwarfs import HorizontalDiffusion, HorizontalSmoothing  # noqa: E402
+from tests import helpers as hp  # noqa: E402
+
+DIFFUSERS = ((2, "second_order"), (4, "fourth_order"))
+SMOOTHERS = ((1, "first_order"), (2, "second_order"), (3, "third_order"))
+
+
+def dev(a):
+    return tb.as_storage(np.asarray(a))
+
+
+def eq(a, b):
+    np.testing.assert_array_equal(tb.to_numpy(a), b)
+
+
+@pytest.mark.parametrize("ax", ("x", "y"))
+@pytest.mark.parametrize("tag", ("row", "grid"))
+def test_one_dimensional_dwarfs_golden(ax, tag):
+    fx = hp.load("stencils_1d")
+    dx, dy = fx["scalars"]
+    phi = fx[f"{ax}_{tag}_phi"]
+    shape = phi.shape
+    for order, name in DIFFUSERS:
+        diff = HorizontalDiffusion.factory(f"{name}_1d{ax}", shape, dx, dy, 0.5, 1.0, 3)
+        tnd = tb.zeros(shape)
+        diff(dev(phi), tnd, overwrite_output=True)
+        eq(tnd, fx[f"k8_{order}_{ax}_{tag}_tnd"])
+        acc = dev(fx[f"{ax}_{tag}_base"])
+        diff(dev(phi), acc, overwrite_output=False)
+        eq(acc, fx[f"k8_{order}_{ax}_{tag}_acc"])
+    for order, name in SMOOTHERS:
+        out = tb.zeros(shape)
+        HorizontalSmoothing.factory(f"{name}_1d{ax}", shape, 0.03, 0.24, 3)(dev(phi), out)
+        eq(out, fx[f"k9_{order}_{ax}_{tag}_out"])
+
+
+@pytest.mark.parametrize("shape", ((7, 1, 1), (1, 7, 1), (131, 3, 4), (5, 203, 2), (1025, 1, 64)))
+def test_one_dimensional_dwarfs_oracle_ragged(shape):
+    rng = np.random.default_rng(11 + shape[0] + shape[1])
+    phi = rng.standard_normal(shape)
+    depth = min(2, shape[2])
+    for axis, ax in enumerate("xy"):
+        if shape[axis] < 7:
+            continue
+        for order, name in DIFFUSERS:
+            nb = order // 2
+            g = np.zeros(shape)
+            g[...] = od.vertical_profile(0.5, 1.0, depth, shape[2])[None, None, :]
+            origin = tuple(nb if a == axis else 0 for a in range(3))
+            domain = tuple(n - 2 * nb if a == axis else n for a, n in enumerate(shape))
+            exp = np.zeros(shape)
+            od.diffusion_1d(order, axis, phi, g, exp, (0.7, 1.3)[axis], True, origin, domain)
+            out = tb.zeros(shape)
+            HorizontalDiffusion.factory(f"{name}_1d{ax}", shape, 0.7, 1.3, 0.5, 1.0, depth)(dev(phi), out)
+            eq(out, exp)
+        for order, name in SMOOTHERS:
+            g = np.zeros(shape)
+            g[...] = od.vertical_profile(0.03, 0.24, depth, shape[2])[None, None, :]
+            exp = np.zeros(shape)
+            od.horizontal_smoothing_1d(order, axis, phi, g, exp)
+            out = tb.zeros(shape)
+            HorizontalSmoothing.factory(f"{name}_1d{ax}", shape, 0.03, 0.24, depth)(dev(phi), out)
+            eq(out, exp)
+
+
+def test_one_dimensional_entry_points_reject_bad_arguments():
+    from tasmania_b200 import lib
+
+    shape = (9, 1, 2)
+    phi, out = dev(np.ones(shape)), tb.zeros(shape)
+    diff = HorizontalDiffusion.factory("fourth_order_1dx", shape, 1.0, 1.0, 0.5, 1.0, 0)
+    with pytest.raises(lib.B200Error):  # halo 2 along x does not fit around origin 1
+        diff._stencil(in_phi=phi, in_gamma=diff._gamma, out_phi=out, dx=1.0, dy=1.0,
+                      ow_out_phi=True, origin=(1, 0, 0), domain=(7, 1, 2))
+    with pytest.raises(lib.B200Error):  # in place
+        diff._stencil(in_phi=phi, in_gamma=diff._gamma, out_phi=phi, dx=1.0, dy=1.0,
+                      ow_out_phi=True, origin=(2, 0, 0), domain=(5, 1, 2))

@@ -177,6 +177,37 @@ def test_diffusion_dwarf_with_periodic_boundaries_equals_oracle_numerically():
         np.testing.assert_array_equal(tb.to_numpy(phi), ophi)
 
 
+def test_one_dimensional_dwarfs_host_path_equals_reference_fixture(stencils_1d_golden):
+    """The ..._1dx / ..._1dy diffusers and smoothers through the b200 mirrors and the marshalling
+    of tb200_diffusion_1d / tb200_smoothing_1d reproduce what the reference's own classes wrote
+    (tests/golden/stencils_1d.npz), bit for bit."""
+    import tasmania_b200 as tb
+    from tasmania_b200.dwarfs import HorizontalDiffusion, HorizontalSmoothing
+
+    fx = stencils_1d_golden
+    dx, dy = fx["scalars"]
+    with stubbed_library(OracleStub) as stub:
+        for ax in ("x", "y"):
+            for tag in ("row", "grid"):
+                phi = fx[f"{ax}_{tag}_phi"]
+                shape = phi.shape
+                for order, name in ((2, "second_order"), (4, "fourth_order")):
+                    diff = HorizontalDiffusion.factory(f"{name}_1d{ax}", shape, dx, dy, 0.5, 1.0, 3)
+                    tnd = tb.zeros(shape)
+                    diff(tb.as_storage(phi), tnd, overwrite_output=True)
+                    np.testing.assert_array_equal(tb.to_numpy(tnd), fx[f"k8_{order}_{ax}_{tag}_tnd"])
+                    acc = tb.as_storage(fx[f"{ax}_{tag}_base"])
+                    diff(tb.as_storage(phi), acc, overwrite_output=False)
+                    np.testing.assert_array_equal(tb.to_numpy(acc), fx[f"k8_{order}_{ax}_{tag}_acc"])
+                for order, name in ((1, "first_order"), (2, "second_order"), (3, "third_order")):
+                    smooth = HorizontalSmoothing.factory(f"{name}_1d{ax}", shape, 0.03, 0.24, 3)
+                    out = tb.zeros(shape)
+                    smooth(tb.as_storage(phi), out)
+                    np.testing.assert_array_equal(tb.to_numpy(out), fx[f"k9_{order}_{ax}_{tag}_out"])
+        assert stub.count("tb200_diffusion_1d") == 16 and stub.count("tb200_smoothing_1d") == 12
+        assert stub.count("tb200_diffusion") == 0 and stub.count("tb200_smoothing") == 0
+
+
 def test_fused_stage_host_path_equals_oracle_numerically():
     """The headline path's host side: IsentropicDryRun with the fused stage (one ABI call per RK
     stage carrying 25 fields and the stage configuration), emulated stage by stage with the oracle."""

@@ -151,6 +151,35 @@ def test_k9_smoothing(stencils_golden, order):
     eq(out, fx[f"k9_{order}_out"])
 
 
+@pytest.mark.parametrize("ax", ("x", "y"))
+@pytest.mark.parametrize("tag", ("row", "grid"))
+def test_k8_k9_one_dimensional_variants(stencils_1d_golden, ax, tag):
+    """The reference's ..._1dx / ..._1dy diffusers and smoothers (run in place by
+    golden/generate_golden.py stencils_1d) against the oracle, bit for bit."""
+    fx = stencils_1d_golden
+    axis = 0 if ax == "x" else 1
+    phi = fx[f"{ax}_{tag}_phi"]
+    shape = phi.shape
+    h = fx["scalars"][axis]
+    gamma = np.zeros(shape)
+    gamma[...] = od.vertical_profile(0.5, 1.0, 3, shape[2])[None, None, :]
+    for order in (2, 4):
+        nb = order // 2
+        origin = (nb, 0, 0) if axis == 0 else (0, nb, 0)
+        domain = tuple(n - 2 * nb if a == axis else n for a, n in enumerate(shape))
+        tnd = np.zeros(shape)
+        od.diffusion_1d(order, axis, phi, gamma, tnd, h, True, origin, domain)
+        eq(tnd, fx[f"k8_{order}_{ax}_{tag}_tnd"])
+        acc = fx[f"{ax}_{tag}_base"].copy()
+        od.diffusion_1d(order, axis, phi, gamma, acc, h, False, origin, domain)
+        eq(acc, fx[f"k8_{order}_{ax}_{tag}_acc"])
+    gamma[...] = od.vertical_profile(0.03, 0.24, 3, shape[2])[None, None, :]
+    for order in (1, 2, 3):
+        out = np.zeros(shape)
+        od.horizontal_smoothing_1d(order, axis, phi, gamma, out)
+        eq(out, fx[f"k9_{order}_{ax}_{tag}_out"])
+
+
 def test_k12_elementwise(stencils_golden):
     fx = stencils_golden
     nx, ny, nz = (int(v) for v in fx["dims"])
