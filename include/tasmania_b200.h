@@ -338,6 +338,15 @@ int tb200_implicit_vertical_advection(int staggered_w, const tb200_field *in_w,
                                       double dt_tendency, const int32_t origin[3],
                                       const int32_t domain[3], void *stream);
 
+/* ---- the global `thomas` stencil: src/tasmania/framework/subclasses/stencil_definitions/
+ * cla.py:L33-L62 -- tridiagonal systems a[k] x[k-1] + b[k] x[k] + c[k] x[k+1] = d[k] solved per
+ * column over k in [origin[2], origin[2]+domain[2]) with the reference's zero-pivot rule
+ * (divide by b[k] where the eliminated diagonal vanishes).  out may alias d (the reference works
+ * on a copy of d) but not a, b or c.  At most 256 levels. */
+int tb200_thomas(const tb200_field *a, const tb200_field *b, const tb200_field *c,
+                 const tb200_field *d, tb200_field *out, const int32_t origin[3],
+                 const int32_t domain[3], void *stream);
+
 /* ---- fused dry isentropic stage (the benchmark hot path) ---------------------------
  * One RK stage of IsentropicDynamicalCore.stage_array_call_dry
  * (src/tasmania/isentropic/dynamics/dycore.py:L641-L721) with the relaxed lateral boundary:

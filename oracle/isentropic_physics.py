@@ -129,6 +129,24 @@ def _setup_tridiagonal(gamma, w, phi):
     return a, c, d
 
 
+def thomas(a, b, c, d, out, origin, domain):
+    """The global ``thomas`` stencil, framework/subclasses/stencil_definitions/cla.py:L33-L62:
+    general diagonal b, the reference's zero-pivot rule, on copies of b and d."""
+    i, j = (slice(o, o + n) for o, n in zip(origin[:2], domain[:2]))
+    k0, k1 = origin[2], origin[2] + domain[2]
+    beta, delta = b.copy(), d.copy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for k in range(k0 + 1, k1):
+            w = np.where(beta[i, j, k - 1] != 0.0, a[i, j, k] / beta[i, j, k - 1], a[i, j, k])
+            beta[i, j, k] -= w * c[i, j, k - 1]
+            delta[i, j, k] -= w * delta[i, j, k - 1]
+        out[i, j, k1 - 1] = np.where(beta[i, j, k1 - 1] != 0.0, delta[i, j, k1 - 1] / beta[i, j, k1 - 1],
+                                     delta[i, j, k1 - 1] / b[i, j, k1 - 1])
+        for k in range(k1 - 2, k0 - 1, -1):
+            r = delta[i, j, k] - c[i, j, k] * out[i, j, k + 1]
+            out[i, j, k] = np.where(beta[i, j, k] != 0.0, r / beta[i, j, k], r / b[i, j, k])
+
+
 def _thomas(a, c, d):
     """cla.py:L42-L78 with b = 1: forward elimination, backward substitution, level by level."""
     nk = d.shape[2]

@@ -271,6 +271,73 @@ extern "C" int tb200_implicit_vertical_advection(
   return check_launch("implicit_vertical_advection");
 }
 
+// ---------------------------------------------------------------- Thomas algorithm (stand-alone)
+// src/tasmania/framework/subclasses/stencil_definitions/cla.py:L33-L62 (the global `thomas`
+// stencil): per column, forward elimination
+//   w = beta[k-1] != 0 ? a[k] / beta[k-1] : a[k];  beta[k] = b[k] - w c[k-1];  delta[k] = d[k] - w delta[k-1]
+// and back substitution  x[k] = (delta[k] - c[k] x[k+1]) / (beta[k] != 0 ? beta[k] : b[k]).
+// One thread per column, i along the warp (every level a coalesced row access); beta in a
+// thread-local array, the eliminated right-hand side parked in the output storage (the
+// reference works on deep copies of b and d).  24 + 16 B/pt: a, b, c, d read once, out written
+// and re-read once.
+struct ThomasArgs {
+  View a, b, c, d, out;
+  int i0, j0, k0, di, dj, dk;
+};
+
+template <int MAXK>
+__global__ void __launch_bounds__(128) thomas_kernel(const ThomasArgs t) {
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jj = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ii >= t.di || jj >= t.dj) return;
+  const int i = ii + t.i0, j = jj + t.j0, k0 = t.k0, nk = t.dk;
+  double beta[MAXK];
+  // d through plain loads: out may alias it (never the read-only path for memory this kernel writes)
+  double bk = t.b.ld(i, j, k0), delta = t.d(i, j, k0);
+  beta[0] = bk;
+  t.out(i, j, k0) = delta;
+  for (int l = 1; l < nk; ++l) {
+    const double al = t.a.ld(i, j, k0 + l);
+    const double w = beta[l - 1] != 0.0 ? al / beta[l - 1] : al;
+    bk = t.b.ld(i, j, k0 + l) - w * t.c.ld(i, j, k0 + l - 1);
+    beta[l] = bk;
+    delta = t.d(i, j, k0 + l) - w * delta;
+    t.out(i, j, k0 + l) = delta;
+  }
+  double x = delta / (bk != 0.0 ? bk : t.b.ld(i, j, k0 + nk - 1));
+  t.out(i, j, k0 + nk - 1) = x;
+  for (int l = nk - 2; l >= 0; --l) {
+    const double r = t.out(i, j, k0 + l) - t.c.ld(i, j, k0 + l) * x;
+    x = r / (beta[l] != 0.0 ? beta[l] : t.b.ld(i, j, k0 + l));
+    t.out(i, j, k0 + l) = x;
+  }
+}
+
+extern "C" int tb200_thomas(const tb200_field *a, const tb200_field *b, const tb200_field *c,
+                            const tb200_field *d, tb200_field *out, const int32_t origin[3],
+                            const int32_t domain[3], void *stream) {
+  ThomasArgs t{};
+  t.a = view(a); t.b = view(b); t.c = view(c); t.d = view(d); t.out = view(out);
+  t.i0 = origin[0]; t.j0 = origin[1]; t.k0 = origin[2];
+  t.di = domain[0]; t.dj = domain[1]; t.dk = domain[2];
+  TB200_REQUIRE(box_inside(t.a, origin, domain) && box_inside(t.b, origin, domain) &&
+                    box_inside(t.c, origin, domain) && box_inside(t.d, origin, domain) &&
+                    box_inside(t.out, origin, domain),
+                "thomas: box outside a storage");
+  TB200_REQUIRE(t.dk >= 1 && t.dk <= 256, "thomas: 1 <= levels <= 256, got %d", t.dk);
+  TB200_REQUIRE(t.out.p != t.a.p && t.out.p != t.b.p && t.out.p != t.c.p,
+                "thomas: out must not alias a, b or c");
+  if (t.di <= 0 || t.dj <= 0) return TB200_OK;
+  dim3 block(32, 4, 1);
+  dim3 grid((t.di + 31) / 32, (t.dj + 3) / 4, 1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (t.dk <= 64)
+    thomas_kernel<64><<<grid, block, 0, st>>>(t);
+  else
+    thomas_kernel<256><<<grid, block, 0, st>>>(t);
+  return check_launch("thomas");
+}
+
 static int vadv_entry(
     int flux_scheme, int staggered_w, const tb200_field *in_w, const tb200_field *in_s,
     const tb200_field *in_su, const tb200_field *in_sv, tb200_field *out_s, tb200_field *out_su,

@@ -190,7 +190,7 @@ def _class_scoped_subroutines():
 GLOBAL_STENCILS = (
     "copy", "copychange", "abs", "iabs", "add", "iadd", "addsub", "iaddsub", "clip", "iclip", "fma",
     "mul", "imul", "scale", "iscale", "sub", "isub", "sts_rk2_0", "sts_rk3ws_0", "irelax", "relax",
-    "step_forward_euler", "step_forward_euler_momentum",
+    "step_forward_euler", "step_forward_euler_momentum", "thomas",
 )
 
 

@@ -118,6 +118,12 @@ def copychange_b200(externals, *, src, dst, origin, domain):
     _ew("copychange", dst, src, origin=origin, domain=domain)
 
 
+@stencil_definition("thomas")
+def thomas_b200(externals, *, a, b, c, d, out, origin, domain):
+    """The global ``thomas`` stencil, framework/subclasses/stencil_definitions/cla.py:L33-L62."""
+    _call("tb200_thomas", _f(a), _f(b), _f(c), _f(d), _f(out), _i3(origin), _i3(domain), _stream())
+
+
 @stencil_definition("abs")
 def abs_b200(externals, *, in_field, out_field, origin, domain):
     _ew("abs", out_field, in_field, origin=origin, domain=domain)

@@ -103,6 +103,9 @@ class OracleStub(AbiStub):
     def _do_tb200_mass_fraction(self, dens, dq, q, clipping, o, d, stream):
         dwarfs.mass_fraction(arr(dens), arr(dq), arr(q), *box(o, d), clipping=bool(clipping))
 
+    def _do_tb200_thomas(self, a, b, c, d, out, o, dm, stream):
+        op.thomas(arr(a), arr(b), arr(c), arr(d), arr(out), *box(o, dm))
+
     # ---- K8, K9
     def _do_tb200_diffusion(self, order, phi, gamma, out, dx, dy, ow, o, d, stream):
         dwarfs.diffusion(order, arr(phi), arr(gamma), arr(out), dx, dy, bool(ow), *box(o, d))

@@ -89,6 +89,23 @@ def gen_stencils_1d():
                 sm = np.zeros(shape)
                 obj(phi, sm)
                 out[f"k9_{order}_{ax}_{tag}_out"] = sm
+    # ---- the global `thomas` stencil (stencil_definitions/cla.py): diagonally dominant random
+    # systems, plus columns engineered to hit the zero-pivot branch (eliminated diagonal == 0
+    # at level 1: b = 2, a = 1, beta[0] = 1, c[0] = 2)
+    cla = refload.load("tasmania.framework.subclasses.stencil_definitions.cla")
+    shape = (6, 5, 9)
+    a, c, d = (rng.uniform(-1, 1, size=shape) for _ in range(3))
+    b = rng.uniform(2.5, 4, size=shape) * rng.choice([-1.0, 1.0], size=shape)
+    for (i, j) in ((1, 1), (3, 2), (4, 4)):
+        b[i, j, 1], c[i, j, 1] = 1.0, 2.0
+        a[i, j, 2], b[i, j, 2] = 1.0, 2.0
+    x = np.zeros(shape)
+    origin, domain = (1, 0, 1), (5, 5, 7)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cla.thomas_numpy(a, b, c, d, x, origin=origin, domain=domain)
+    assert np.isfinite(x).all()
+    out.update(thomas_a=a, thomas_b=b, thomas_c=c, thomas_d=d, thomas_x=x,
+               thomas_box=np.array(origin + domain))
     save("stencils_1d", **out)
 
 

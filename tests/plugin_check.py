@@ -44,8 +44,10 @@ for name in plugin.GLOBAL_STENCILS:
 compiled = ts.StencilCompiler("irelax", "b200", backend_options=BackendOptions())
 assert callable(compiled) and compiled.externals == {}
 try:
-    ts.StencilDefinition("b200", "thomas")  # out of scope: must fail like any unknown backend
-    raise SystemExit("thomas should not be registered for b200")
+    # the class-less hyperdiffusion demo stencil (stencil_definitions/diffusion.py) is out of
+    # scope: must fail like any unknown backend
+    ts.StencilDefinition("b200", "diffusion")
+    raise SystemExit("the global diffusion stencil should not be registered for b200")
 except FactoryRegistryError:
     pass
 
@@ -236,6 +238,14 @@ with stubbed_library(OracleStub) as stub:
                 obj(ta.as_storage(backend, data=phi), out)
                 res[backend] = np.array(to_numpy(out))
             assert np.array_equal(res["b200"], res["numpy"]), (name, ax)
+    # the reference's global `thomas` stencil compiled for b200 by the reference's own compiler
+    fx1 = np.load(os.path.join(ROOT, "tests", "golden", "stencils_1d.npz"))
+    tbox = [int(v) for v in fx1["thomas_box"]]
+    thomas = ts.StencilCompiler("thomas", "b200", backend_options=BackendOptions())
+    xs = ta.zeros("b200", shape=fx1["thomas_a"].shape)
+    thomas(**{n: ta.as_storage("b200", data=fx1["thomas_" + n]) for n in "abcd"}, out=xs,
+           origin=tuple(tbox[:3]), domain=tuple(tbox[3:]))
+    assert np.array_equal(to_numpy(xs), fx1["thomas_x"]) and stub.count("tb200_thomas") == 1
     assert stub.count("tb200_diffusion_1d") == 8 and stub.count("tb200_smoothing_1d") == 12
     assert stub.count("tb200_diffusion") == 0 and stub.count("tb200_smoothing") == 0
 

@@ -1,6 +1,7 @@
 # -*- coding: utf-8 -*-
 """Parity of the one-dimensional diffusers and smoothers (``..._1dx`` / ``..._1dy``;
-``tb200_diffusion_1d`` / ``tb200_smoothing_1d``, csrc/horizontal.cu) against (a) the fixture the
+``tb200_diffusion_1d`` / ``tb200_smoothing_1d``, csrc/horizontal.cu) and of the global ``thomas``
+stencil (``tb200_thomas``, csrc/vertical.cu) against (a) the fixture the
 reference's own classes wrote (tests/golden/stencils_1d.npz) and (b) the oracle on ragged sizes.
 No libm calls: BIT-EXACT.
 
@@ -93,3 +94,41 @@ def test_one_dimensional_entry_points_reject_bad_arguments():
     with pytest.raises(lib.B200Error):  # in place
         diff._stencil(in_phi=phi, in_gamma=diff._gamma, out_phi=phi, dx=1.0, dy=1.0,
                       ow_out_phi=True, origin=(2, 0, 0), domain=(5, 1, 2))
+
+
+def test_thomas_golden_and_views():
+    from tasmania_b200.framework import BackendOptions
+
+    fx = hp.load("stencils_1d")
+    box = [int(v) for v in fx["thomas_box"]]
+    thomas = tb.compile_stencil("thomas", backend_options=BackendOptions())
+    a, b, c, d = (dev(fx["thomas_" + n]) for n in "abcd")
+    x = tb.zeros(fx["thomas_a"].shape)
+    thomas(a=a, b=b, c=c, d=d, out=x, origin=tuple(box[:3]), domain=tuple(box[3:]))
+    eq(x, fx["thomas_x"])
+    sl = (slice(1, 6), slice(0, 5), slice(1, 8))
+    dd = dev(fx["thomas_d"])  # views of the storages, solved in place of d
+    thomas(a=a[sl], b=b[sl], c=c[sl], d=dd[sl], out=dd[sl], origin=(0, 0, 0), domain=(5, 5, 7))
+    np.testing.assert_array_equal(tb.to_numpy(dd)[sl], fx["thomas_x"][sl])
+
+
+@pytest.mark.parametrize("shape", ((3, 2, 1), (37, 21, 60), (130, 5, 100)))
+def test_thomas_oracle_ragged(shape):
+    from oracle import isentropic_physics as op
+    from tasmania_b200.framework import BackendOptions
+
+    rng = np.random.default_rng(shape[2])
+    a, c, d = (rng.uniform(-1, 1, size=shape) for _ in range(3))
+    b = rng.uniform(2.5, 4, size=shape) * rng.choice([-1.0, 1.0], size=shape)
+    exp = np.zeros(shape)
+    op.thomas(a, b, c, d, exp, (0, 0, 0), shape)
+    x = tb.zeros(shape)
+    tb.compile_stencil("thomas", backend_options=BackendOptions())(
+        a=dev(a), b=dev(b), c=dev(c), d=dev(d), out=x, origin=(0, 0, 0), domain=shape)
+    eq(x, exp)
+    # the solution solves the system (size-independent property, rtol from the conditioning)
+    x = tb.to_numpy(x)
+    res = b * x
+    res[:, :, 1:] += a[:, :, 1:] * x[:, :, :-1]
+    res[:, :, :-1] += c[:, :, :-1] * x[:, :, 1:]
+    np.testing.assert_allclose(res, d, rtol=0, atol=1e-12)

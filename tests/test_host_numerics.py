@@ -208,6 +208,28 @@ def test_one_dimensional_dwarfs_host_path_equals_reference_fixture(stencils_1d_g
         assert stub.count("tb200_diffusion") == 0 and stub.count("tb200_smoothing") == 0
 
 
+def test_thomas_stencil_host_path_equals_reference_fixture(stencils_1d_golden):
+    """compile_stencil("thomas") -> tb200_thomas marshalling (sliced, non-contiguous views
+    included) reproduces the reference's thomas_numpy output."""
+    import tasmania_b200 as tb
+    from tasmania_b200.framework import BackendOptions
+
+    fx = stencils_1d_golden
+    box = [int(v) for v in fx["thomas_box"]]
+    with stubbed_library(OracleStub) as stub:
+        thomas = tb.compile_stencil("thomas", backend_options=BackendOptions())
+        a, b, c, d = (tb.as_storage(fx["thomas_" + n]) for n in "abcd")
+        x = tb.zeros(fx["thomas_a"].shape)
+        thomas(a=a, b=b, c=c, d=d, out=x, origin=tuple(box[:3]), domain=tuple(box[3:]))
+        np.testing.assert_array_equal(tb.to_numpy(x), fx["thomas_x"])
+        # the same systems through views of the storages, solved in place of d
+        sl = (slice(1, 6), slice(0, 5), slice(1, 8))
+        dd = tb.as_storage(fx["thomas_d"])
+        thomas(a=a[sl], b=b[sl], c=c[sl], d=dd[sl], out=dd[sl], origin=(0, 0, 0), domain=(5, 5, 7))
+        np.testing.assert_array_equal(tb.to_numpy(dd)[sl], fx["thomas_x"][sl])
+        assert stub.count("tb200_thomas") == 2
+
+
 def test_fused_stage_host_path_equals_oracle_numerically():
     """The headline path's host side: IsentropicDryRun with the fused stage (one ABI call per RK
     stage carrying 25 fields and the stage configuration), emulated stage by stage with the oracle."""

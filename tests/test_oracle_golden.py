@@ -180,6 +180,23 @@ def test_k8_k9_one_dimensional_variants(stencils_1d_golden, ax, tag):
         eq(out, fx[f"k9_{order}_{ax}_{tag}_out"])
 
 
+def test_thomas_global_stencil(stencils_1d_golden):
+    """stencil_definitions/cla.py:thomas_numpy run in place (zero-pivot columns included)."""
+    from oracle import isentropic_physics as op
+
+    fx = stencils_1d_golden
+    box = [int(v) for v in fx["thomas_box"]]
+    x = np.zeros(fx["thomas_a"].shape)
+    op.thomas(fx["thomas_a"], fx["thomas_b"], fx["thomas_c"], fx["thomas_d"], x, box[:3], box[3:])
+    eq(x, fx["thomas_x"])
+    # the specialised solver of the implicit vertical advection (b == 1) agrees with it
+    a, c, d = fx["thomas_a"][1:, :, 1:8], fx["thomas_c"][1:, :, 1:8], fx["thomas_d"][1:, :, 1:8]
+    y = np.zeros(fx["thomas_a"].shape)
+    op.thomas(fx["thomas_a"], np.ones_like(fx["thomas_b"]), fx["thomas_c"], fx["thomas_d"], y,
+              box[:3], box[3:])
+    eq(op._thomas(a, c, d), y[1:, :, 1:8])
+
+
 def test_k12_elementwise(stencils_golden):
     fx = stencils_golden
     nx, ny, nz = (int(v) for v in fx["dims"])
