@@ -249,6 +249,41 @@ with stubbed_library(OracleStub) as stub:
     assert stub.count("tb200_diffusion_1d") == 8 and stub.count("tb200_smoothing_1d") == 12
     assert stub.count("tb200_diffusion") == 0 and stub.count("tb200_smoothing") == 0
 
+# ---- the reference's one-dimensional boundary classes (Relaxed1DX / 1DY, Periodic1DX / 1DY:
+# picked by its factory on grids with ny == 1 / nx == 1) run unchanged on backend b200 -- the
+# `irelax` stencil through the C ABI, the slab copies as slice assignments on b200 storages
+with stubbed_library(OracleStub) as stub:
+    for hb_type, kw, nb in (("relaxed", {"nr": 5}, 2), ("periodic", {}, 2)):
+        for nx, ny in ((17, 1), (1, 15)):
+            nz = 4
+            dom = gg._make_domain(nx, ny, nz, hb_type, nb, kw, topo=False)
+            res = {}
+            for backend in ("numpy", "b200"):
+                hb1 = hbm.HorizontalBoundary.factory(
+                    hb_type, dom.physical_grid, nb, backend=backend, backend_options=BackendOptions(),
+                    storage_options=StorageOptions(), **kw)
+                assert type(hb1).__name__.endswith("1DX" if ny == 1 else "1DY")
+                shape = (hb1.ni + 1, hb1.nj + 1, nz + 1)
+                r2 = np.random.default_rng(nx)
+                fields = {n: r2.standard_normal(shape) for n in names}
+                refs = {n: r2.standard_normal(shape) for n in names}
+                conv = (lambda a: ta.as_storage("b200", data=a)) if backend == "b200" else (lambda a: a.copy())
+                hb1.reference_state = {n: refload.DataArray(conv(v), attrs={"units": "1"})
+                                       for n, v in refs.items()}
+                got = {}
+                for n in names:
+                    f = conv(fields[n])
+                    hb1.enforce_field(f, field_name=n, field_units="1")
+                    hb1.set_outermost_layers_x(f, field_name=n, field_units="1")
+                    hb1.set_outermost_layers_y(f, field_name=n, field_units="1")
+                    got[n] = np.array(to_numpy(f))
+                phys = r2.standard_normal((nx, ny, nz))
+                got["numerical"] = np.array(to_numpy(hb1.get_numerical_field(conv(phys), field_name=names[0])))
+                res[backend] = got
+            for n in res["numpy"]:
+                assert np.array_equal(res["numpy"][n], res["b200"][n]), (hb_type, nx, ny, n)
+    assert stub.count("tb200_relax") == 8  # 2 relaxed boundaries x 4 fields
+
 print("PLUGIN-OK", len(report["global"]), len(report["class_scoped"]), len(report["skipped"]))
 for s in report["skipped"]:
     print("skipped:", s)
