@@ -10,7 +10,8 @@ relaxed lateral boundaries (nb=3, nr=6), RK3WS + fifth-order upwind, Rayleigh da
 quoted on: 1024x1024x64 per GPU (config 5; weak scaling over a 2-D decomposition), which also
 keeps every field (0.56 GB) far larger than the 126 MB L2, so no L2 flush is needed between
 timed steps.  ``--workload c2`` runs the 161x161x60 case of config 2 (L2-resident,
-launch-latency regime).
+launch-latency regime); ``--workload c4`` runs configs[3], the fourth-order diffusion dwarf at
+4096x4096x64 with periodic boundaries (its own loop and JSON line: ``run_c4``).
 
 One *step* = ``dycore.update_topography`` + one full RK3WS step (3 fused stages) + the
 ``IsentropicDiagnostics`` refresh of p / exn / mtg / h.
@@ -42,6 +43,10 @@ WORKLOADS = {
     "c5halo": (1028, 1024, 64),  # local grid of a rank of the 2x1 decomposition (timing experiments)
     "c2": (161, 161, 60),
     "small": (256, 256, 64),
+    # configs[3]: the fourth-order horizontal-diffusion dwarf on a doubly periodic grid (a different
+    # loop: run_c4 below); c4small is the same loop at a size for quick checks
+    "c4": (4096, 4096, 64),
+    "c4small": (512, 512, 64),
 }
 # algorithmic HBM bytes per grid point (SURVEY.md section 8d / BASELINE.md section 4):
 # dry RK3WS step 3 x 112 B + diagnostics refresh 40 B
@@ -255,6 +260,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload.startswith("c4"):
+        return run_reference_c4(args)
     nx, ny, nz = WORKLOADS["c2"]
     pts = nx * ny * nz
     budget = min(60.0, 4.0 * max(1, args.steps))
@@ -283,6 +290,44 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Mpts*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def run_reference_c4(args):
+    """--impl reference --workload c4: the numpy oracle port of the diffusion-dwarf loop (one
+    thread: numpy element-wise code) on a 512x512x64 sample of the same workload."""
+    from oracle import boundary as ob
+    from oracle import dwarfs
+
+    nx, ny, nz, nb, dt = 512, 512, 64, 2, 0.05
+    hb = ob.Periodic(nx, ny, nz, nb)
+    phi = hb.get_numerical_field(np.random.default_rng(20261018).standard_normal((nx, ny, nz)))
+    gamma = np.zeros(phi.shape)
+    gamma[...] = dwarfs.vertical_profile(0.5, 1.0, 15, nz)[None, None, :]
+    tnd = np.zeros(phi.shape)
+    budget = min(60.0, 4.0 * max(1, args.steps))
+    t0, steps = time.perf_counter(), 0
+    while True:
+        dwarfs.diffusion(4, phi, gamma, tnd, 1.0, 1.0, True, (nb, nb, 0), (nx, ny, nz))
+        phi = phi + dt * tnd
+        hb.enforce_field(phi)
+        steps += 1
+        if time.perf_counter() - t0 > budget or steps >= 200:
+            break
+    el = time.perf_counter() - t0
+    val = nx * ny * nz * steps / el / 1e6
+    base = {"value": val, "unit": "Mpts*steps/s", "cores": 1, "kind": "port",
+            "sample": f"{steps} applications (diffusion + update + periodic halo) on {nx}x{ny}x{nz}, "
+                      f"numpy oracle, 1 thread, {el:.1f} s"}
+    print(json.dumps({
+        "impl": "reference", "metric": "grid-point updates/sec", "value": val, "unit": "Mpts*steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 0, "ms_per_step": el / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "fourth-order horizontal diffusion dwarf, periodic BC, fp64",
+                   "sample_grid": [nx, ny, nz]},
+        "cpu_baseline": base,
+        "e2e": {"value": val, "unit": "Mpts*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
 
 
 def workload_name(key):
@@ -413,6 +458,74 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ configs[3]: diffusion dwarf
+def run_c4(args):
+    """``--workload c4``: BASELINE.json configs[3], the pure-bandwidth stencil.  One step = one
+    application of the fourth-order diffusion (16 B/pt), phi <- phi + dt * tnd (24 B/pt) and the
+    periodic halo refresh (tasmania_b200.diffusion_dwarf.DiffusionDwarfRun); the roofline object
+    is the diffusion kernel timed alone.  Single GPU (under torchrun every rank runs its own
+    replica: the periodic wrap is not decomposed)."""
+    import torch
+
+    from tasmania_b200 import lib as tblib
+    from tasmania_b200.diffusion_dwarf import DiffusionDwarfRun
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the b200 backend has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    nx, ny, nz = WORKLOADS[args.workload]
+    run = DiffusionDwarfRun(nx, ny, nz)
+    for _ in range(args.warmup):
+        run.step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    launches0 = tblib.launch_count()
+    ev[0].record()
+    for _ in range(args.steps):
+        run.step()
+    ev[1].record()
+    torch.cuda.synchronize()
+    launches = tblib.launch_count() - launches0
+    ms = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop() if rank == 0 else None
+    if not bool(torch.isfinite(run.phi.t).all()):
+        raise RuntimeError("bench: phi is not finite")
+    # the diffusion kernel alone (phi and tnd are 8.6 GB each at c4: far larger than L2)
+    for _ in range(2):
+        run.diffusion(run.phi, run.tnd)
+    ev[2].record()
+    for _ in range(args.steps):
+        run.diffusion(run.phi, run.tnd)
+    ev[3].record()
+    torch.cuda.synchronize()
+    k_ms = ev[2].elapsed_time(ev[3]) / args.steps
+    pts = nx * ny * nz
+    peak, how = measured_peak_gbs()
+    gbs = 16 * pts / (k_ms * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": "grid-point updates/sec", "value": pts * args.steps / (ms * 1e-3) / 1e6,
+            "unit": "Mpts*steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"fourth-order horizontal diffusion dwarf, periodic BC, {nx}x{ny}x{nz}, "
+                                   "fp64; step = diffusion + phi update + halo refresh",
+                       "l2": "inputs larger than L2" if pts * 8 > 126e6 else "L2-resident grid"},
+            "clocks": clocks, "e2e": None, "gpu_launches": launches,
+            "hbm_frac_step": (16 + 24) * pts / (ms / args.steps * 1e-3) / 1e9 / peak,
+            "roofline": {"bound": "hbm", "kernel": "diffusion (cross_kernel<4>)", "achieved": gbs,
+                         "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                         "peak_source": how, "ms_per_launch": k_ms,
+                         "algorithmic_bytes_per_launch": 16 * pts},
+        }))
+
+
 # algorithmic HBM bytes per grid point of each kernel of the fused stage (every distinct array
 # read once, every output written once; DESIGN.md section 4) and their DRAM traffic per launch at
 # 1024x1024x64 from the ncu --set full captures under profiles/ (dram__bytes_read + write)
@@ -538,6 +651,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload.startswith("c4"):
+        run_c4(args)
     else:
         run_b200(args)
 

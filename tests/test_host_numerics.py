@@ -175,6 +175,16 @@ def test_diffusion_dwarf_with_periodic_boundaries_equals_oracle_numerically():
             hb.enforce_field(phi)
         assert stub.count("tb200_diffusion") == napp and stub.count("tb200_periodic_enforce") >= napp
         np.testing.assert_array_equal(tb.to_numpy(phi), ophi)
+        # the same loop as bench.py --workload c4 runs it
+        from tasmania_b200.diffusion_dwarf import DiffusionDwarfRun
+
+        run = DiffusionDwarfRun(nx, ny, nz, phi0, diffusion_damp_depth=3, dt=dt)
+        n0 = stub.count("tb200_diffusion")
+        for _ in range(napp):
+            run.step()
+        assert stub.count("tb200_diffusion") == n0 + napp
+        np.testing.assert_array_equal(tb.to_numpy(run.phi), ophi)
+        np.testing.assert_array_equal(tb.to_numpy(run.physical_field()), ophi[nb:-nb, nb:-nb])
 
 
 def test_one_dimensional_dwarfs_host_path_equals_reference_fixture(stencils_1d_golden):
