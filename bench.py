@@ -519,7 +519,8 @@ def run_c4(args):
                        "l2": "inputs larger than L2" if pts * 8 > 126e6 else "L2-resident grid"},
             "clocks": clocks, "e2e": None, "gpu_launches": launches,
             "hbm_frac_step": (16 + 24) * pts / (ms / args.steps * 1e-3) / 1e9 / peak,
-            "roofline": {"bound": "hbm", "kernel": "diffusion (cross_kernel<4>)", "achieved": gbs,
+            "roofline": {"bound": "hbm", "kernel": "diffusion (" + ("march_kernel<4>" if os.environ.get(
+                "TB200_DIFF_IMPL") == "march" else "cross_kernel<4>") + ")", "achieved": gbs,
                          "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
                          "peak_source": how, "ms_per_launch": k_ms,
                          "algorithmic_bytes_per_launch": 16 * pts},

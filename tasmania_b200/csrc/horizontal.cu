@@ -7,6 +7,9 @@
 // fetched from L2/HBM once per CTA; threads keep i as the fast axis (coalesced 128-byte
 // rows), gamma comes through the read-only path.  Grid = (tiles_i, tiles_j, nk) is far
 // larger than 148 SMs x resident CTAs for the sizes of interest, so tail effects vanish.
+#include <stdlib.h>
+#include <string.h>
+
 #include "stencil_math.cuh"
 
 using namespace tb200;
@@ -102,6 +105,77 @@ __global__ void __launch_bounds__(TX *TY)
   }
 }
 
+// ---- diffusion, marching variant (TB200_DIFF_IMPL=march; experimental, not yet measured).
+// One thread per column i, marching along j over a strip of LJ rows with the 2H+1 rows of its
+// own column in registers: every phi value is requested from L2/HBM once per strip (+ 2H halo
+// rows per strip, 6 % at LJ = 64) and once more per x-neighbour from L1 (the neighbouring lanes'
+// lines of the same row); no shared memory, no barrier, one running pointer per array.  Same
+// point formulas, hence the same bits, as the tiled kernel.
+template <int OP, int LJ>
+__global__ void __launch_bounds__(128)
+    march_kernel(View phi, View gam, View out, CDiv dx, CDiv dy, int overwrite, int i0, int j0,
+                 int k0, int di, int dj, int dk) {
+  constexpr int H = Halo<OP>::value;
+  static_assert(OP == 2 || OP == 4, "diffusion only");
+  const int i = i0 + blockIdx.x * 128 + threadIdx.x;
+  if (i >= i0 + di) return;  // no shuffles and no barriers below
+  const int js = j0 + blockIdx.y * LJ, je = min(js + LJ, j0 + dj);
+  const long long s0 = phi.s0, s1 = phi.s1;
+  for (int k = k0 + blockIdx.z; k < k0 + dk; k += gridDim.z) {
+    const double *pr = phi.p + (i * s0 + js * s1 + k * phi.s2);  // (i, j, k), j running
+    const double *pg = gam.p + (i * gam.s0 + js * gam.s1 + k * gam.s2);
+    double *po = out.p + (i * out.s0 + js * out.s1 + k * out.s2);
+    double w[2 * H + 1];  // rows j-H .. j+H of the own column
+#pragma unroll
+    for (int m = 0; m < 2 * H; ++m) w[m + 1] = __ldg(pr + (m - H) * s1);
+    for (int j = js; j < je; ++j) {
+#pragma unroll
+      for (int m = 0; m < 2 * H; ++m) w[m] = w[m + 1];
+      w[2 * H] = __ldg(pr + H * s1);
+      const double g = __ldg(pg);
+      double r;
+      if (OP == 2) {
+        r = lap2(g, w[H], __ldg(pr - s0), __ldg(pr + s0), w[H - 1], w[H + 1], dx, dy);
+      } else {
+        r = lap4(g, w[H], __ldg(pr - 2 * s0), __ldg(pr - s0), __ldg(pr + s0), __ldg(pr + 2 * s0),
+                 w[H - 2], w[H - 1], w[H + 1], w[H + 2], dx, dy);
+      }
+      if (!overwrite) r = *po + r;  // generics.py:L38-L40
+      *po = r;
+      pr += s1;
+      pg += gam.s1;
+      po += out.s1;
+    }
+  }
+}
+
+// TB200_DIFF_IMPL: "tile" (default, shared-memory tiles) or "march" (register windows along j)
+int diff_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("TB200_DIFF_IMPL");
+    impl = (e != nullptr && strcmp(e, "march") == 0) ? 1 : 0;
+  }
+  return impl;
+}
+
+template <int OP>
+int launch_march(const char *what, View phi, View gam, View out, const CDiv &cdx, const CDiv &cdy,
+                 int overwrite, const int32_t o[3], const int32_t d[3], cudaStream_t st) {
+  const int gz = d[2] > 65535 ? 65535 : d[2];
+  const long long blocks64 = (long long)((d[0] + 127) / 128) * ((d[1] + 63) / 64) * gz;
+  if (blocks64 >= 148 * 8) {  // enough 64-row strips to fill the machine
+    dim3 grid((d[0] + 127) / 128, (d[1] + 63) / 64, gz);
+    march_kernel<OP, 64><<<grid, 128, 0, st>>>(phi, gam, out, cdx, cdy, overwrite, o[0], o[1], o[2],
+                                                d[0], d[1], d[2]);
+  } else {
+    dim3 grid((d[0] + 127) / 128, (d[1] + 15) / 16, gz);
+    march_kernel<OP, 16><<<grid, 128, 0, st>>>(phi, gam, out, cdx, cdy, overwrite, o[0], o[1], o[2],
+                                                d[0], d[1], d[2]);
+  }
+  return check_launch(what);
+}
+
 template <int OP>
 int launch_cross(const char *what, View phi, View gam, View out, double dx, double dy,
                  int overwrite, int rim, const int32_t o[3], const int32_t d[3],
@@ -115,6 +189,9 @@ int launch_cross(const char *what, View phi, View gam, View out, double dx, doub
   // full denominators, evaluated as the reference does: dx * dx and 12.0 * dx * dx
   const CDiv cdx = make_cdiv(OP == 4 ? 12.0 * dx * dx : (OP == 2 ? dx * dx : 1.0));
   const CDiv cdy = make_cdiv(OP == 4 ? 12.0 * dy * dy : (OP == 2 ? dy * dy : 1.0));
+  if constexpr (OP == 2 || OP == 4) {
+    if (!rim && diff_impl() == 1) return launch_march<OP>(what, phi, gam, out, cdx, cdy, overwrite, o, d, st);
+  }
   cross_kernel<OP><<<grid, block, 0, st>>>(phi, gam, out, cdx, cdy, overwrite, rim, o[0], o[1],
                                            o[2], d[0], d[1], d[2], ri, rj);
   return check_launch(what);

@@ -132,3 +132,44 @@ def test_thomas_oracle_ragged(shape):
     res[:, :, 1:] += a[:, :, 1:] * x[:, :, :-1]
     res[:, :, :-1] += c[:, :, :-1] * x[:, :, 1:]
     np.testing.assert_allclose(res, d, rtol=0, atol=1e-12)
+
+
+MARCH_SCRIPT = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+import tasmania_b200 as tb
+from oracle import dwarfs as od
+from tasmania_b200.dwarfs import HorizontalDiffusion
+for shape in ((9, 9, 1), (66, 21, 4), (131, 75, 3), (300, 200, 70)):
+    rng = np.random.default_rng(7 + shape[0])
+    phi = rng.standard_normal(shape)
+    base = rng.standard_normal(shape)
+    depth = min(2, shape[2])
+    for order, name in ((2, "second_order"), (4, "fourth_order")):
+        nb = order // 2
+        g = np.zeros(shape)
+        g[...] = od.vertical_profile(0.5, 1.0, depth, shape[2])[None, None, :]
+        box = ((nb, nb, 0), (shape[0] - 2 * nb, shape[1] - 2 * nb, shape[2]))
+        hd = HorizontalDiffusion.factory(name, shape, 0.7, 1.3, 0.5, 1.0, depth)
+        for overwrite in (True, False):
+            exp = base.copy()
+            od.diffusion(order, phi, g, exp, 0.7, 1.3, overwrite, *box)
+            out = tb.as_storage(base)
+            hd(tb.as_storage(phi), out, overwrite_output=overwrite)
+            np.testing.assert_array_equal(tb.to_numpy(out), exp)
+print("MARCH-OK")
+""" % __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+
+
+def test_marching_diffusion_variant_equals_oracle():
+    """TB200_DIFF_IMPL=march (csrc/horizontal.cu:march_kernel, experimental): same bits as the
+    oracle -- and hence as the default tiled kernel -- on ragged sizes, both output modes."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, TB200_DIFF_IMPL="march")
+    res = subprocess.run([sys.executable, "-c", MARCH_SCRIPT], capture_output=True, text=True,
+                         env=env, timeout=300)
+    assert res.returncode == 0 and "MARCH-OK" in res.stdout, res.stdout + res.stderr
