@@ -174,6 +174,12 @@ int tb200_smoothing_1d(int order, int axis, const tb200_field *in_phi,
                        const tb200_field *in_gamma, tb200_field *out_phi, int rim_copy,
                        const int32_t origin[3], const int32_t domain[3], void *stream);
 
+/* ---- the class-less `diffusion` stencil (a hyperdiffusion filter):
+ * src/tasmania/framework/subclasses/stencil_definitions/diffusion.py:L31-L55.
+ * out = phi + alpha * div(grad(lap(lap(phi)))) on [origin, origin+domain); reads a halo of 3. */
+int tb200_hyperdiffusion(const tb200_field *in_phi, tb200_field *out_phi, double alpha,
+                         const int32_t origin[3], const int32_t domain[3], void *stream);
+
 /* ---- K1 / K2 isentropic prognostic step: src/tasmania/isentropic/dynamics/subclasses/
  * prognostics/utils.py:L43-L134 and L137-L204.  The moist tracers are passed as arrays of
  * three field pointers (qv, qc, qr order); NULL arrays = dry. */

@@ -181,6 +181,25 @@ def horizontal_smoothing(order, phi, gamma, out, shape=None):
         copy(phi, out, o, d)
 
 
+def hyperdiffusion(phi, out, alpha, origin, domain):
+    """The class-less ``diffusion`` stencil, framework/subclasses/stencil_definitions/
+    diffusion.py:L31-L55: phi + alpha * (differences of the fluxes of the bilaplacian)."""
+    ib, jb, kb = origin
+    ie, je, ke = (o + d for o, d in zip(origin, domain))
+    k = slice(kb, ke)
+
+    def sh(lo_i, hi_i, lo_j, hi_j):
+        return phi[ib + lo_i : ie + hi_i, jb + lo_j : je + hi_j, k]
+
+    lap = -4 * sh(-2, 2, -2, 2) + sh(-3, 1, -2, 2) + sh(-1, 3, -2, 2) + sh(-2, 2, -3, 1) + sh(-2, 2, -1, 3)
+    bilap = -4 * lap[1:-1, 1:-1] + lap[:-2, 1:-1] + lap[2:, 1:-1] + lap[1:-1, :-2] + lap[1:-1, 2:]
+    flux_x = bilap[1:, 1:-1] - bilap[:-1, 1:-1]
+    flux_y = bilap[1:-1, 1:] - bilap[1:-1, :-1]
+    out[ib:ie, jb:je, k] = phi[ib:ie, jb:je, k] + alpha * (
+        flux_x[1:, :] - flux_x[:-1, :] + flux_y[:, 1:] - flux_y[:, :-1]
+    )
+
+
 # ------------------------------------------------------------------ K8 / K9, 1-D variants
 def diffusion_1d(order, axis, phi, gamma, out, h, overwrite, origin, domain):
     """SecondOrder1DX / 1DY (horizontal_diffusers/second_order.py:L210-L219, L321-L330) and

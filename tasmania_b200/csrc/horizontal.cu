@@ -105,6 +105,32 @@ __global__ void __launch_bounds__(TX *TY)
   }
 }
 
+// ---- the class-less `diffusion` stencil of the reference (a hyperdiffusion filter:
+// framework/subclasses/stencil_definitions/diffusion.py:L31-L55): laplacian of the laplacian,
+// its x / y differences as fluxes, phi + alpha * divergence of the fluxes.  A radius-3 diamond
+// per point; not used by any component of the benchmark models, so it is written for clarity
+// (every intermediate recomputed per thread from L1-resident loads, in the reference's order of
+// operations), not for speed.
+struct HyperOp {
+  View phi, out;
+  double alpha;
+  int i0, j0, k0;
+  __device__ __forceinline__ double lap(int i, int j, int k) const {
+    return -4.0 * phi.ld(i, j, k) + phi.ld(i - 1, j, k) + phi.ld(i + 1, j, k) + phi.ld(i, j - 1, k) +
+           phi.ld(i, j + 1, k);
+  }
+  __device__ __forceinline__ double bilap(int i, int j, int k) const {
+    return -4.0 * lap(i, j, k) + lap(i - 1, j, k) + lap(i + 1, j, k) + lap(i, j - 1, k) + lap(i, j + 1, k);
+  }
+  __device__ void operator()(int ri, int rj, int rk) const {
+    const int i = i0 + ri, j = j0 + rj, k = k0 + rk;
+    const double bc = bilap(i, j, k);
+    const double fx_hi = bilap(i + 1, j, k) - bc, fx_lo = bc - bilap(i - 1, j, k);
+    const double fy_hi = bilap(i, j + 1, k) - bc, fy_lo = bc - bilap(i, j - 1, k);
+    out(i, j, k) = phi.ld(i, j, k) + alpha * (fx_hi - fx_lo + fy_hi - fy_lo);
+  }
+};
+
 // ---- diffusion, marching variant (TB200_DIFF_IMPL=march; experimental, not yet measured).
 // One thread per column i, marching along j over a strip of LJ rows with the 2H+1 rows of its
 // own column in registers: every phi value is requested from L2/HBM once per strip (+ 2H halo
@@ -346,4 +372,18 @@ extern "C" int tb200_smoothing_1d(int order, int axis, const tb200_field *in_phi
   if (order == 2)
     return launch_line<12>("smoothing2_1d", phi, gam, out, axis, 0, 1, rim_copy, origin, domain, st);
   return launch_line<13>("smoothing3_1d", phi, gam, out, axis, 0, 1, rim_copy, origin, domain, st);
+}
+
+extern "C" int tb200_hyperdiffusion(const tb200_field *in_phi, tb200_field *out_phi, double alpha,
+                                    const int32_t origin[3], const int32_t domain[3],
+                                    void *stream) {
+  View phi = view(in_phi), out = view(out_phi);
+  TB200_REQUIRE(box_inside(phi, origin, domain, 3, 3, 3, 3),
+                "hyperdiffusion: in_phi box + halo 3 outside storage");
+  TB200_REQUIRE(box_inside(out, origin, domain), "hyperdiffusion: out box outside storage");
+  TB200_REQUIRE(phi.p != out.p, "hyperdiffusion: in_phi and out_phi must not alias");
+  HyperOp op;
+  op.phi = phi; op.out = out; op.alpha = alpha;
+  op.i0 = origin[0]; op.j0 = origin[1]; op.k0 = origin[2];
+  return launch_box("hyperdiffusion", domain, static_cast<cudaStream_t>(stream), op);
 }

@@ -68,6 +68,7 @@ SIGNATURES = {
     "tb200_mass_fraction": [_F, _F, _F, _I, _I3, _I3, _V],
     "tb200_diffusion": [_I, _F, _F, _F, _D, _D, _I, _I3, _I3, _V],
     "tb200_smoothing": [_I, _F, _F, _F, _I, _I3, _I3, _V],
+    "tb200_hyperdiffusion": [_F, _F, _D, _I3, _I3, _V],
     "tb200_thomas": [_F, _F, _F, _F, _F, _I3, _I3, _V],
     "tb200_diffusion_1d": [_I, _I, _F, _F, _F, _D, _I, _I3, _I3, _V],
     "tb200_smoothing_1d": [_I, _I, _F, _F, _F, _I, _I3, _I3, _V],

@@ -320,6 +320,12 @@ def install(strict: bool = False, batch_fma: bool = True, frame_relax: bool = Tr
     for name in GLOBAL_STENCILS:
         ts.StencilDefinition.register(fw.get_stencil_definition(name), backend=BACKEND, stencil=name)
         report["global"].append(name)
+    # the reference's class-less `diffusion` (a hyperdiffusion filter) is `hyperdiffusion` in the
+    # mirrors' flat registry; class-scoped `diffusion` definitions (the dwarfs) take precedence on
+    # their instances exactly as they do for the numpy backend
+    ts.StencilDefinition.register(fw.get_stencil_definition("hyperdiffusion"), backend=BACKEND,
+                                  stencil="diffusion")
+    report["global"].append("diffusion")
     for name in ("set_output", "thomas", "setup_thomas", "setup_thomas_bc"):
         ts.SubroutineDefinition.register(_descriptor(name, name), backend=BACKEND, stencil=name)
 

@@ -118,6 +118,15 @@ def copychange_b200(externals, *, src, dst, origin, domain):
     _ew("copychange", dst, src, origin=origin, domain=domain)
 
 
+@stencil_definition("hyperdiffusion")
+def hyperdiffusion_b200(externals, *, in_phi, out_phi, alpha, origin, domain):
+    """The reference's class-less ``diffusion`` stencil (stencil_definitions/diffusion.py:L31-L55);
+    registered under that name by the plugin, under ``hyperdiffusion`` here because the mirrors'
+    registry is flat and ``diffusion`` is the dwarfs' class-scoped stencil."""
+    _call("tb200_hyperdiffusion", _f(in_phi), _f(out_phi), float(alpha), _i3(origin), _i3(domain),
+          _stream())
+
+
 @stencil_definition("thomas")
 def thomas_b200(externals, *, a, b, c, d, out, origin, domain):
     """The global ``thomas`` stencil, framework/subclasses/stencil_definitions/cla.py:L33-L62."""

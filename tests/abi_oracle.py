@@ -110,6 +110,9 @@ class OracleStub(AbiStub):
     def _do_tb200_diffusion(self, order, phi, gamma, out, dx, dy, ow, o, d, stream):
         dwarfs.diffusion(order, arr(phi), arr(gamma), arr(out), dx, dy, bool(ow), *box(o, d))
 
+    def _do_tb200_hyperdiffusion(self, phi, out, alpha, o, d, stream):
+        dwarfs.hyperdiffusion(arr(phi), arr(out), alpha, *box(o, d))
+
     def _do_tb200_diffusion_1d(self, order, axis, phi, gamma, out, h, ow, o, d, stream):
         dwarfs.diffusion_1d(order, axis, arr(phi), arr(gamma), arr(out), h, bool(ow), *box(o, d))
 

@@ -106,6 +106,14 @@ def gen_stencils_1d():
     assert np.isfinite(x).all()
     out.update(thomas_a=a, thomas_b=b, thomas_c=c, thomas_d=d, thomas_x=x,
                thomas_box=np.array(origin + domain))
+    # ---- the class-less `diffusion` stencil (hyperdiffusion filter, stencil_definitions/diffusion.py)
+    dif = refload.load("tasmania.framework.subclasses.stencil_definitions.diffusion")
+    shape = (15, 13, 5)
+    hphi = rng.uniform(-5, 5, size=shape)
+    hout = np.zeros(shape)
+    dif.diffusion_numpy(hphi, hout, alpha=1.0 / 32.0, origin=(3, 3, 1), domain=(9, 7, 3))
+    out.update(hyper_phi=hphi, hyper_out=hout, hyper_box=np.array([3, 3, 1, 9, 7, 3]),
+               hyper_alpha=np.array(1.0 / 32.0))
     save("stencils_1d", **out)
 
 

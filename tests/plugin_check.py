@@ -44,10 +44,8 @@ for name in plugin.GLOBAL_STENCILS:
 compiled = ts.StencilCompiler("irelax", "b200", backend_options=BackendOptions())
 assert callable(compiled) and compiled.externals == {}
 try:
-    # the class-less hyperdiffusion demo stencil (stencil_definitions/diffusion.py) is out of
-    # scope: must fail like any unknown backend
-    ts.StencilDefinition("b200", "diffusion")
-    raise SystemExit("the global diffusion stencil should not be registered for b200")
+    ts.StencilDefinition("b200", "no_such_stencil")  # must fail like any unknown name
+    raise SystemExit("an unknown stencil resolved for b200")
 except FactoryRegistryError:
     pass
 
@@ -238,6 +236,14 @@ with stubbed_library(OracleStub) as stub:
                 obj(ta.as_storage(backend, data=phi), out)
                 res[backend] = np.array(to_numpy(out))
             assert np.array_equal(res["b200"], res["numpy"]), (name, ax)
+    # the reference's class-less `diffusion` stencil (hyperdiffusion filter) on b200
+    hbox = [int(v) for v in np.load(os.path.join(ROOT, "tests", "golden", "stencils_1d.npz"))["hyper_box"]]
+    hfx = np.load(os.path.join(ROOT, "tests", "golden", "stencils_1d.npz"))
+    hyper = ts.StencilCompiler("diffusion", "b200", backend_options=BackendOptions())
+    hout = ta.zeros("b200", shape=hfx["hyper_phi"].shape)
+    hyper(in_phi=ta.as_storage("b200", data=hfx["hyper_phi"]), out_phi=hout,
+          alpha=float(hfx["hyper_alpha"]), origin=tuple(hbox[:3]), domain=tuple(hbox[3:]))
+    assert np.array_equal(to_numpy(hout), hfx["hyper_out"]) and stub.count("tb200_hyperdiffusion") == 1
     # the reference's global `thomas` stencil compiled for b200 by the reference's own compiler
     fx1 = np.load(os.path.join(ROOT, "tests", "golden", "stencils_1d.npz"))
     tbox = [int(v) for v in fx1["thomas_box"]]

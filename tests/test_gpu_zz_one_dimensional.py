@@ -134,6 +134,25 @@ def test_thomas_oracle_ragged(shape):
     np.testing.assert_allclose(res, d, rtol=0, atol=1e-12)
 
 
+def test_hyperdiffusion_golden_and_oracle():
+    from tasmania_b200.framework import BackendOptions
+
+    fx = hp.load("stencils_1d")
+    box = [int(v) for v in fx["hyper_box"]]
+    hyper = tb.compile_stencil("hyperdiffusion", backend_options=BackendOptions())
+    out = tb.zeros(fx["hyper_phi"].shape)
+    hyper(in_phi=dev(fx["hyper_phi"]), out_phi=out, alpha=float(fx["hyper_alpha"]),
+          origin=tuple(box[:3]), domain=tuple(box[3:]))
+    eq(out, fx["hyper_out"])
+    shape = (141, 67, 5)
+    phi = np.random.default_rng(3).standard_normal(shape)
+    exp = np.zeros(shape)
+    od.hyperdiffusion(phi, exp, 0.01, (3, 3, 0), (135, 61, 5))
+    out = tb.zeros(shape)
+    hyper(in_phi=dev(phi), out_phi=out, alpha=0.01, origin=(3, 3, 0), domain=(135, 61, 5))
+    eq(out, exp)
+
+
 MARCH_SCRIPT = r"""
 import sys
 sys.path.insert(0, %r)

@@ -240,6 +240,21 @@ def test_thomas_stencil_host_path_equals_reference_fixture(stencils_1d_golden):
         assert stub.count("tb200_thomas") == 2
 
 
+def test_hyperdiffusion_stencil_host_path_equals_reference_fixture(stencils_1d_golden):
+    import tasmania_b200 as tb
+    from tasmania_b200.framework import BackendOptions
+
+    fx = stencils_1d_golden
+    box = [int(v) for v in fx["hyper_box"]]
+    with stubbed_library(OracleStub) as stub:
+        hyper = tb.compile_stencil("hyperdiffusion", backend_options=BackendOptions())
+        out = tb.zeros(fx["hyper_phi"].shape)
+        hyper(in_phi=tb.as_storage(fx["hyper_phi"]), out_phi=out, alpha=float(fx["hyper_alpha"]),
+              origin=tuple(box[:3]), domain=tuple(box[3:]))
+        np.testing.assert_array_equal(tb.to_numpy(out), fx["hyper_out"])
+        assert stub.count("tb200_hyperdiffusion") == 1
+
+
 def test_fused_stage_host_path_equals_oracle_numerically():
     """The headline path's host side: IsentropicDryRun with the fused stage (one ABI call per RK
     stage carrying 25 fields and the stage configuration), emulated stage by stage with the oracle."""

@@ -197,6 +197,15 @@ def test_thomas_global_stencil(stencils_1d_golden):
     eq(op._thomas(a, c, d), y[1:, :, 1:8])
 
 
+def test_hyperdiffusion_global_stencil(stencils_1d_golden):
+    """stencil_definitions/diffusion.py:diffusion_numpy run in place."""
+    fx = stencils_1d_golden
+    box = [int(v) for v in fx["hyper_box"]]
+    out = np.zeros(fx["hyper_phi"].shape)
+    od.hyperdiffusion(fx["hyper_phi"], out, float(fx["hyper_alpha"]), box[:3], box[3:])
+    eq(out, fx["hyper_out"])
+
+
 def test_k12_elementwise(stencils_golden):
     fx = stencils_golden
     nx, ny, nz = (int(v) for v in fx["dims"])
