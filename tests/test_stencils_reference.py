@@ -1,0 +1,101 @@
+# -*- coding: utf-8 -*-
+"""The prognostic-step stencils K1 / K2 of the oracle against the REFERENCE's own numpy definitions
+run in place (``step_forward_euler_numpy``, ``step_forward_euler_momentum_numpy``:
+isentropic/dynamics/subclasses/prognostics/utils.py:L43-L204 with the four minimal flux classes) on
+sizes the committed fixture (one 17x15x6 grid) does not cover: the smallest grid every scheme
+accepts (nx = ny = 2 extent + 1: a single computed point), a single level, ragged extents, and a
+compute box narrower than the storage -- bit for bit.  Skipped where /root/reference is absent."""
+import numpy as np
+import pytest
+
+from oracle import isentropic as oi
+from oracle.fluxes import EXTENT
+from tests.golden import refload
+
+pytestmark = pytest.mark.skipif(not refload.available(), reason="reference tree not mounted")
+
+CLASSES = {"upwind": "Upwind", "centered": "Centered", "third_order_upwind": "ThirdOrderUpwind",
+           "fifth_order_upwind": "FifthOrderUpwind"}
+
+
+def _reference_stencils(scheme, moist):
+    refload.install_framework()
+    utils = refload.load("tasmania.isentropic.dynamics.subclasses.prognostics.utils")
+    mod = refload.load("tasmania.isentropic.dynamics.subclasses.minimal_horizontal_fluxes." + scheme)
+    hflux = getattr(mod, CLASSES[scheme])(backend="numpy")
+    if scheme == "centered":  # the numpy Centered flux looks its helpers up as globals
+        full = refload.load("tasmania.isentropic.dynamics.subclasses.horizontal_fluxes.centered")
+        mod.get_centered_flux_x = full.Centered.get_centered_flux_x_numpy
+        mod.get_centered_flux_y = full.Centered.get_centered_flux_y_numpy
+    ext = dict(hflux.externals or {})
+    ext.update(extent=hflux.extent, moist=moist,
+               flux_dry=hflux.get_subroutine_definition("flux_dry"),
+               flux_moist=hflux.get_subroutine_definition("flux_moist"))
+    assert hflux.extent == EXTENT[scheme]
+    return (refload.numpy_stencil(utils.step_forward_euler_numpy, ext),
+            refload.numpy_stencil(utils.step_forward_euler_momentum_numpy, ext))
+
+
+def _cases(e):
+    n = 2 * e + 1
+    # (storage-defining nx, ny, nz), origin, domain
+    yield (n, n, 1), (e, e, 0), (1, 1, 1)                      # one computed point, one level
+    yield (n + 1, n + 4, 3), (e, e, 0), (1, 4, 3)              # one column of points
+    yield (23, 9, 2), (e, e, 0), (23 - 2 * e, 9 - 2 * e, 2)    # ragged
+    yield (19, 21, 4), (e + 2, e + 1, 1), (5, 7, 2)            # box strictly inside the storage
+
+
+@pytest.mark.parametrize("scheme", list(CLASSES))
+@pytest.mark.parametrize("moist", (False, True))
+def test_k1_k2_equal_reference_on_minimal_and_ragged_grids(scheme, moist):
+    k1, k2 = _reference_stencils(scheme, moist)
+    e = EXTENT[scheme]
+    for n, ((nx, ny, nz), origin, domain) in enumerate(_cases(e)):
+        rng = np.random.default_rng(1000 * e + 10 * n + moist)
+        shape = (nx + 1, ny + 1, nz + 1)
+
+        def field(lo, hi):
+            return rng.uniform(lo, hi, size=shape)
+
+        s_now, s_int, s_new_in = field(10, 1000), field(10, 1000), field(10, 1000)
+        u, v = field(-50, 50), field(-50, 50)
+        su_now, su_int, sv_now, sv_int = (field(-5e3, 5e3) for _ in range(4))
+        mtg_now, mtg_new = field(2.9e5, 3.1e5), field(2.9e5, 3.1e5)
+        s_tnd, su_tnd, sv_tnd = field(-1, 1), field(-10, 10), field(-10, 10)
+        sq_now, sq_int = [field(0, 5) for _ in range(3)], [field(0, 5) for _ in range(3)]
+        q_tnd = [field(-1e-3, 1e-3) for _ in range(3)]
+        dt, dx, dy, eps = 1.5 + n, 1100.0, 900.0, 0.3
+        for tnd in (False, True):
+            ref_s, ora_s = field(0, 1), None
+            ora_s = ref_s.copy()
+            ref_q = [field(0, 1) for _ in range(3)]
+            ora_q = [q.copy() for q in ref_q]
+            kw_ref, kw_ora = {}, {}
+            if moist:
+                for i, t in enumerate(("qv", "qc", "qr")):
+                    kw_ref.update({f"s{t}_now": sq_now[i], f"s{t}_int": sq_int[i], f"s{t}_new": ref_q[i]})
+                    if tnd:
+                        kw_ref[f"{t}_tnd"] = q_tnd[i]
+                kw_ora = dict(moist=True, sq_now=sq_now, sq_int=sq_int, sq_new=ora_q,
+                              q_tnd=q_tnd if tnd else (None, None, None))
+            k1(s_now=s_now, s_int=s_int, s_new=ref_s, u_int=u, v_int=v, su_int=su_int, sv_int=sv_int,
+               s_tnd=s_tnd if tnd else None, dt=dt, dx=dx, dy=dy, origin=origin, domain=domain, **kw_ref)
+            oi.step_forward_euler(scheme, s_now, s_int, ora_s, u, v, dt=dt, dx=dx, dy=dy, origin=origin,
+                                  domain=domain, s_tnd=s_tnd if tnd else None, **kw_ora)
+            np.testing.assert_array_equal(ora_s, ref_s, err_msg=f"s case {n} tnd {tnd}")
+            for a, b in zip(ora_q, ref_q):  # untouched outside the box, equal inside
+                np.testing.assert_array_equal(a, b, err_msg=f"sq case {n} tnd {tnd}")
+            if moist:
+                continue
+            ref_su, ref_sv = field(0, 1), field(0, 1)
+            ora_su, ora_sv = ref_su.copy(), ref_sv.copy()
+            k2(s_now=s_now, s_int=s_int, s_new=s_new_in, u_int=u, v_int=v, su_now=su_now, su_int=su_int,
+               su_new=ref_su, sv_now=sv_now, sv_int=sv_int, sv_new=ref_sv, mtg_now=mtg_now,
+               mtg_new=mtg_new, su_tnd=su_tnd if tnd else None, sv_tnd=sv_tnd if tnd else None,
+               dt=dt, dx=dx, dy=dy, eps=eps, origin=origin, domain=domain)
+            oi.step_forward_euler_momentum(
+                scheme, s_now, s_new_in, u, v, su_now, su_int, ora_su, sv_now, sv_int, ora_sv, mtg_now,
+                mtg_new, dt=dt, dx=dx, dy=dy, eps=eps, origin=origin, domain=domain,
+                su_tnd=su_tnd if tnd else None, sv_tnd=sv_tnd if tnd else None)
+            np.testing.assert_array_equal(ora_su, ref_su, err_msg=f"su case {n} tnd {tnd}")
+            np.testing.assert_array_equal(ora_sv, ref_sv, err_msg=f"sv case {n} tnd {tnd}")
