@@ -99,3 +99,61 @@ def test_k1_k2_equal_reference_on_minimal_and_ragged_grids(scheme, moist):
                 su_tnd=su_tnd if tnd else None, sv_tnd=sv_tnd if tnd else None)
             np.testing.assert_array_equal(ora_su, ref_su, err_msg=f"su case {n} tnd {tnd}")
             np.testing.assert_array_equal(ora_sv, ref_sv, err_msg=f"sv case {n} tnd {tnd}")
+
+
+@pytest.mark.parametrize("shape", ((3, 3, 1), (5, 5, 1), (7, 7, 2), (9, 31, 3), (40, 7, 5)))
+def test_diffusers_and_smoothers_equal_reference_on_minimal_and_ragged_grids(shape):
+    """The reference's HorizontalDiffusion / HorizontalSmoothing classes (2-D and 1-D variants,
+    their own __call__: stencil + rim copies) against the oracle down to the smallest shape each
+    scheme accepts (2 nb + 1 points along its axes)."""
+    from oracle import dwarfs as od
+
+    refload.install_framework()
+    opts = refload.load("tasmania.framework.options")
+    for name in ("second_order", "fourth_order"):
+        refload.load("tasmania.dwarfs.subclasses.horizontal_diffusers." + name)
+    for name in ("first_order", "second_order", "third_order"):
+        refload.load("tasmania.dwarfs.subclasses.horizontal_smoothers." + name)
+    hd = refload.load("tasmania.dwarfs.horizontal_diffusion")
+    hsm = refload.load("tasmania.dwarfs.horizontal_smoothing")
+    kw = dict(backend="numpy", backend_options=opts.BackendOptions(), storage_options=opts.StorageOptions())
+    rng = np.random.default_rng(sum(shape))
+    phi, base = rng.standard_normal(shape), rng.standard_normal(shape)
+    depth = min(2, shape[2])
+    checked = 0
+    for sfx, axis in (("", None), ("_1dx", 0), ("_1dy", 1)):
+        axes = (0, 1) if axis is None else (axis,)
+        for order, name in ((2, "second_order"), (4, "fourth_order")):
+            nb = order // 2
+            if any(shape[a] < 2 * nb + 1 for a in axes):
+                continue
+            g = np.zeros(shape)
+            g[...] = od.vertical_profile(0.5, 1.0, depth, shape[2])[None, None, :]
+            origin = tuple(nb if a in axes else 0 for a in range(3))
+            domain = tuple(n - 2 * nb if a in axes else n for a, n in enumerate(shape))
+            obj = hd.HorizontalDiffusion.factory(name + sfx, shape, 0.7, 1.3, 0.5, 1.0, depth, **kw)
+            np.testing.assert_array_equal(np.asarray(obj._gamma), g)
+            for overwrite in (True, False):
+                ref, ora = base.copy(), base.copy()
+                obj(phi, ref, overwrite_output=overwrite)
+                if axis is None:
+                    od.diffusion(order, phi, g, ora, 0.7, 1.3, overwrite, origin, domain)
+                else:
+                    od.diffusion_1d(order, axis, phi, g, ora, (0.7, 1.3)[axis], overwrite, origin, domain)
+                np.testing.assert_array_equal(ora, ref, err_msg=f"{name}{sfx} overwrite={overwrite}")
+                checked += 1
+        for order, name in ((1, "first_order"), (2, "second_order"), (3, "third_order")):
+            if any(shape[a] < 2 * order + 1 for a in axes):
+                continue
+            g = np.zeros(shape)
+            g[...] = od.vertical_profile(0.03, 0.24, depth, shape[2])[None, None, :]
+            obj = hsm.HorizontalSmoothing.factory(name + sfx, shape, 0.03, 0.24, depth, **kw)
+            ref, ora = base.copy(), base.copy()
+            obj(phi, ref)
+            if axis is None:
+                od.horizontal_smoothing(order, phi, g, ora)
+            else:
+                od.horizontal_smoothing_1d(order, axis, phi, g, ora)
+            np.testing.assert_array_equal(ora, ref, err_msg=f"{name}{sfx}")
+            checked += 1
+    assert checked >= 3
