@@ -157,3 +157,56 @@ def test_diffusers_and_smoothers_equal_reference_on_minimal_and_ragged_grids(sha
             np.testing.assert_array_equal(ora, ref, err_msg=f"{name}{sfx}")
             checked += 1
     assert checked >= 3
+
+
+@pytest.mark.parametrize("dims", ((1, 1, 1), (2, 3, 1), (9, 4, 2), (5, 7, 64), (12, 10, 70)))
+def test_k3_column_scans_equal_reference_from_one_level_to_deep_columns(dims):
+    """IsentropicDiagnostics' numpy stencils (isentropic/dynamics/diagnostics.py:L319-L570:
+    diagnostic_variables, montgomery, height, density_and_temperature) run in place against the
+    oracle on a single column / single level and on columns deeper than the 64 levels the
+    register-resident GPU scan covers -- bit for bit (both sides are numpy + glibc pow)."""
+    refload.install_framework()
+    diag = refload.load("tasmania.isentropic.dynamics.diagnostics")
+    consts = {"pref": 1.0e5, "rd": 287.05, "g": 9.80665, "cp": 1004.0}
+    D = diag.IsentropicDiagnostics
+    mont = refload.numpy_stencil(D._montgomery_numpy, consts)
+    dvar = refload.numpy_stencil(D._diagnostic_variables_numpy, consts)
+    hgt = refload.numpy_stencil(D._height_numpy, consts)
+    dat = refload.numpy_stencil(D._density_and_temperature_numpy, consts)
+    nx, ny, nz = dims
+    shape = (nx + 1, ny + 1, nz + 1)
+    rng = np.random.default_rng(nx * 100 + nz)
+    theta1d = np.linspace(400.0, 280.0, nz + 1)
+    theta = np.zeros(shape)
+    theta[:nx, :ny, :] = theta1d[None, None, :]
+    hs = np.zeros(shape)
+    hs[:nx, :ny, nz] = rng.uniform(0, 800, size=(nx, ny))
+    s = rng.uniform(5, 60, size=shape)
+    dz, pt = 120.0 / nz, 11868.9
+    box = dict(origin=(0, 0, 0), domain=(nx, ny, nz + 1))
+
+    ref, ora = np.zeros(shape), np.zeros(shape)
+    mont(in_hs=hs, in_s=s, inout_mtg=ref, dz=dz, pt=pt, theta_s=theta1d[-1], **box)
+    oi.montgomery(hs, s, ora, dz=dz, pt=pt, theta_s=theta1d[-1], **box)
+    np.testing.assert_array_equal(ora, ref)
+
+    r = [np.zeros(shape) for _ in range(4)]
+    o = [np.zeros(shape) for _ in range(4)]
+    dvar(in_theta=theta, in_hs=hs, in_s=s, inout_p=r[0], out_exn=r[1], inout_mtg=r[2], inout_h=r[3],
+         dz=dz, pt=pt, **box)
+    oi.diagnostic_variables(theta, hs, s, *o, dz=dz, pt=pt, **box)
+    for a, b, n in zip(o, r, ("p", "exn", "mtg", "h")):
+        np.testing.assert_array_equal(a, b, err_msg=n)
+    np.testing.assert_array_equal(o[2], ora)  # the two Montgomery scans agree
+
+    ref, ora = np.zeros(shape), np.zeros(shape)
+    hgt(in_theta=theta, in_hs=hs, in_s=s, inout_h=ref, dz=dz, pt=pt, **box)
+    oi.height(theta, hs, s, ora, dz=dz, pt=pt, **box)
+    np.testing.assert_array_equal(ora, ref)
+
+    rr, rt, orho, ot = (np.zeros(shape) for _ in range(4))
+    dat(in_theta=theta, in_s=s, in_exn=r[1], in_h=r[3], out_rho=rr, out_t=rt, origin=(0, 0, 0),
+        domain=(nx, ny, nz))
+    oi.density_and_temperature(theta, s, o[1], o[3], orho, ot, origin=(0, 0, 0), domain=(nx, ny, nz))
+    np.testing.assert_array_equal(orho, rr)
+    np.testing.assert_array_equal(ot, rt)
