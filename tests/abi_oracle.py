@@ -168,6 +168,11 @@ class OracleStub(AbiStub):
         oi.diagnostic_variables(arr(theta), arr(hs), arr(s), arr(p), arr(exn), arr(mtg), arr(h), dz=dz, pt=pt,
                                 origin=origin, domain=domain, constants=constants(c))
 
+    def _do_tb200_height(self, theta, hs, s, h, dz, pt, c, o, d, stream):
+        origin, domain = box(o, d)
+        oi.height(arr(theta), arr(hs), arr(s), arr(h), dz=dz, pt=pt, origin=origin, domain=domain,
+                  constants=constants(c))
+
     def _do_tb200_density_and_temperature(self, theta, s, exn, h, rho, t, cp, o, d, stream):
         origin, domain = box(o, d)
         oi.density_and_temperature(arr(theta), arr(s), arr(exn), arr(h), arr(rho), arr(t), origin=origin,

@@ -153,6 +153,47 @@ def test_hyperdiffusion_golden_and_oracle():
     eq(out, exp)
 
 
+@pytest.mark.parametrize("dims", ((1, 1, 1), (2, 3, 1), (33, 9, 2), (40, 7, 64), (37, 10, 70)))
+def test_k3_column_scans_from_one_level_to_deep_columns(dims):
+    """The stand-alone K3 stencils at depths the golden grid (6 levels) does not reach: one
+    level, and columns beyond the 64 levels of the register-resident scan (the generic kernel).
+    Pressure is bit-exact (no libm call); the pow-based outputs within 1e-13 like
+    tests/test_gpu_stencils.py."""
+    from oracle import isentropic as oi
+    from tasmania_b200.framework import BackendOptions
+
+    def stencil(name):
+        return tb.compile_stencil(name, backend_options=BackendOptions(externals=dict(oi.CONSTANTS)))
+
+    nx, ny, nz = dims
+    shape = (nx + 1, ny + 1, nz + 1)
+    rng = np.random.default_rng(nx * 100 + nz)
+    theta1d = np.linspace(400.0, 280.0, nz + 1)
+    theta = np.zeros(shape)
+    theta[:nx, :ny, :] = theta1d[None, None, :]
+    hs = np.zeros(shape)
+    hs[:nx, :ny, nz] = rng.uniform(0, 800, size=(nx, ny))
+    s = rng.uniform(5, 60, size=shape)
+    dz, pt = 120.0 / nz, 11868.9
+    box = dict(origin=(0, 0, 0), domain=(nx, ny, nz + 1))
+    want = [np.zeros(shape) for _ in range(4)]
+    oi.diagnostic_variables(theta, hs, s, *want, dz=dz, pt=pt, **box)
+    got = [tb.zeros(shape) for _ in range(4)]
+    stencil("diagnostic_variables")(in_theta=dev(theta), in_hs=dev(hs), in_s=dev(s), inout_p=got[0],
+                                    out_exn=got[1], inout_mtg=got[2], inout_h=got[3], dz=dz, pt=pt, **box)
+    eq(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        assert hp.relerr(tb.to_numpy(a), b) <= 1e-13
+    mtg = tb.zeros(shape)
+    stencil("montgomery")(in_hs=dev(hs), in_s=dev(s), inout_mtg=mtg, dz=dz, pt=pt,
+                          theta_s=float(theta1d[-1]), **box)
+    assert hp.relerr(tb.to_numpy(mtg), want[2]) <= 1e-13
+    h, want_h = tb.zeros(shape), np.zeros(shape)  # the stand-alone height scan has its own formula
+    oi.height(theta, hs, s, want_h, dz=dz, pt=pt, **box)
+    stencil("height")(in_theta=dev(theta), in_hs=dev(hs), in_s=dev(s), inout_h=h, dz=dz, pt=pt, **box)
+    assert hp.relerr(tb.to_numpy(h), want_h) <= 1e-13
+
+
 MARCH_SCRIPT = r"""
 import sys
 sys.path.insert(0, %r)
