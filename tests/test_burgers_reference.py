@@ -69,7 +69,12 @@ def reference_run(nx, ny, nb, scheme, flux, eps, dt, nsteps, t0):
 
 @pytest.mark.parametrize("scheme,flux,nb,nsteps", [("rk3ws", "third_order", 2, 100),
                                                    ("rk2", "fifth_order", 3, 15),
-                                                   ("forward_euler", "first_order", 1, 15)])
+                                                   ("forward_euler", "first_order", 1, 15),
+                                                   # the even orders, so that all six advection
+                                                   # schemes are pinned by execution
+                                                   ("rk3ws", "second_order", 1, 10),
+                                                   ("rk2", "fourth_order", 2, 10),
+                                                   ("forward_euler", "sixth_order", 3, 10)])
 def test_reference_burgers_dycore_equals_oracle(scheme, flux, nb, nsteps):
     nx = ny = 101
     eps, t0, dt = 0.01, datetime(2000, 1, 1), timedelta(seconds=0.001)
