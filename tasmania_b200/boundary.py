@@ -5,6 +5,7 @@ operations of the reference's ``HorizontalBoundary`` subclasses
   Relaxed    src/tasmania/domain/subclasses/horizontal_boundaries/relaxed.py:L34-L247
   Periodic   src/tasmania/domain/subclasses/horizontal_boundaries/periodic.py:L32-L122
   Dirichlet  src/tasmania/domain/subclasses/horizontal_boundaries/dirichlet.py:L40-L160
+  Identity   src/tasmania/domain/subclasses/horizontal_boundaries/identity.py:L30-L79
   enforce_raw  src/tasmania/domain/horizontal_boundary.py:L299-L344
 
 with the same method names.  Coefficients are built once on the host (numpy, O(nx ny)) and
@@ -55,7 +56,8 @@ class HorizontalBoundary(StencilFactory):
 
     @staticmethod
     def factory(boundary_type, nx, ny, nz, nb, **kwargs):
-        classes = {"relaxed": Relaxed, "periodic": Periodic, "dirichlet": Dirichlet}
+        classes = {"relaxed": Relaxed, "periodic": Periodic, "dirichlet": Dirichlet,
+                   "identity": Identity}
         if boundary_type not in classes:
             raise ValueError(f"unknown (or out-of-scope) horizontal boundary type {boundary_type!r}")
         return classes[boundary_type](nx, ny, nz, nb, **kwargs)
@@ -299,3 +301,30 @@ class Dirichlet(HorizontalBoundary):
 
     def get_physical_field(self, field, field_name=None):
         return field
+
+
+class Identity(HorizontalBoundary):
+    """No-op conditions: the numerical grid is the physical grid and no field is touched
+    (identity.py:L30-L79) -- no kernel, no launch."""
+
+    type = "identity"
+
+    def __init__(self, nx, ny, nz, nb, backend_options=None, storage_options=None):
+        assert nx > 1 and ny > 1 and nb <= nx / 2 and nb <= ny / 2
+        super().__init__(nx, ny, nz, nb, backend_options, storage_options)
+        self.ni, self.nj = self.nx, self.ny
+
+    def get_numerical_field(self, field, field_name=None):
+        return field
+
+    def get_physical_field(self, field, field_name=None):
+        return field
+
+    def enforce_field(self, field, field_name=None, field_units=None, time=None):
+        pass
+
+    def set_outermost_layers_x(self, field, field_name=None, field_units=None, time=None):
+        pass
+
+    def set_outermost_layers_y(self, field, field_name=None, field_units=None, time=None):
+        pass

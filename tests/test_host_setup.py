@@ -163,3 +163,24 @@ def test_exner_power_restatement_accuracy():
             ref = (Decimal(float(x)).ln() * Decimal(kappa)).exp()
             worst = max(worst, float(abs(Decimal(got) - ref) / ref))
     assert worst <= 1.7e-16, worst
+
+
+def test_identity_boundary_mirror_touches_nothing():
+    """identity.py:L30-L79: numerical grid == physical grid, every operation a no-op (and no
+    library call: the recording stub stays empty)."""
+    import numpy as np
+
+    from tasmania_b200.boundary import HorizontalBoundary
+    from tests.abi_stub import stubbed_library
+
+    with stubbed_library() as stub:
+        hb = HorizontalBoundary.factory("identity", 9, 7, 3, 2)
+        assert (hb.ni, hb.nj, hb.type) == (9, 7, "identity")
+        a = np.arange(9 * 7 * 3, dtype=float).reshape(9, 7, 3)
+        b = a.copy()
+        assert hb.get_numerical_field(a) is a and hb.get_physical_field(a) is a
+        hb.enforce_field(a, "air_isentropic_density")
+        hb.set_outermost_layers_x(a)
+        hb.set_outermost_layers_y(a)
+        hb.enforce_raw({"air_isentropic_density": a})
+        assert (a == b).all() and stub.calls == []
