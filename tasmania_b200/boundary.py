@@ -6,6 +6,8 @@ operations of the reference's ``HorizontalBoundary`` subclasses
   Periodic   src/tasmania/domain/subclasses/horizontal_boundaries/periodic.py:L32-L122
   Dirichlet  src/tasmania/domain/subclasses/horizontal_boundaries/dirichlet.py:L40-L160
   Identity   src/tasmania/domain/subclasses/horizontal_boundaries/identity.py:L30-L79
+  Relaxed1DX / 1DY   relaxed.py:L250-L461, L463-L678  (grids with ny == 1 / nx == 1)
+  Periodic1DX / 1DY  periodic.py:L125-L214, L217-L306
   enforce_raw  src/tasmania/domain/horizontal_boundary.py:L299-L344
 
 with the same method names.  Coefficients are built once on the host (numpy, O(nx ny)) and
@@ -60,6 +62,10 @@ class HorizontalBoundary(StencilFactory):
                    "identity": Identity}
         if boundary_type not in classes:
             raise ValueError(f"unknown (or out-of-scope) horizontal boundary type {boundary_type!r}")
+        # the reference's dispatch on degenerate grids (relaxed.py:L680-L710, periodic.py:L309-L322)
+        one_d = {"relaxed": (Relaxed1DX, Relaxed1DY), "periodic": (Periodic1DX, Periodic1DY)}
+        if boundary_type in one_d and (nx == 1 or ny == 1):
+            return one_d[boundary_type][0 if ny == 1 else 1](nx, ny, nz, nb, **kwargs)
         return classes[boundary_type](nx, ny, nz, nb, **kwargs)
 
     def enforce_raw(self, state, field_properties=None):
@@ -328,3 +334,169 @@ class Identity(HorizontalBoundary):
 
     def set_outermost_layers_y(self, field, field_name=None, field_units=None, time=None):
         pass
+
+
+# ---------------------------------------------------------------- one-dimensional grids
+class _OneDimensional(HorizontalBoundary):
+    """Shared by the ...1DX (ny == 1) and ...1DY (nx == 1) variants: ``axis`` is the axis the
+    grid extends along; the degenerate axis carries 2 nb + 1 copies of its single point on the
+    numerical grid.  The slab copies are slice assignments on b200 storages (device-to-device
+    copies), exactly what the reference's own classes do on this backend through the plugin."""
+
+    axis = 0
+
+    def _n(self):
+        return self.nx if self.axis == 0 else self.ny
+
+    def _ix(self, along, across, k=None):
+        """index tuple with ``along`` on the grid's axis and ``across`` on the degenerate one"""
+        ij = (along, across) if self.axis == 0 else (across, along)
+        return ij if k is None else ij + (k,)
+
+    def _staggered(self, name):
+        """(staggered along the axis, staggered across it)"""
+        name = name or ""
+        u = "at_u_locations" in name or "at_uv_locations" in name
+        v = "at_v_locations" in name or "at_uv_locations" in name
+        return (u, v) if self.axis == 0 else (v, u)
+
+
+class _Relaxed1D(_OneDimensional):
+    type = "relaxed"
+
+    def __init__(self, nx, ny, nz, nb, nr=8, backend_options=None, storage_options=None,
+                 storage_shape=None):
+        super().__init__(nx, ny, nz, nb, backend_options, storage_options)
+        n = self._n()
+        assert n > 1 and (ny if self.axis == 0 else nx) == 1
+        assert nr <= n / 2 and nr <= 8 and nb <= nr
+        self.nr = nr
+        self.ni, self.nj = (self.nx, 2 * nb + 1) if self.axis == 0 else (2 * nb + 1, self.ny)
+        self._shape = tuple(storage_shape or (self.ni + 1, self.nj + 1, nz + 1))
+        # relaxed.py:L424-L461 / L641-L678: the coefficients on the two middle lines only
+        rel = np.array([1.0] + [1.0 - np.tanh(0.5 * m) for m in range(1, 8)])[:nr]
+        rel[:nb] = 1.0
+        g = np.zeros(self._shape[:2])
+        mid = slice(nb, nb + 2)
+        g[self._ix(slice(0, nr), mid)] = rel[:, None] if self.axis == 0 else rel[None, :]
+        g[self._ix(slice(n - nr, n), mid)] = rel[::-1][:, None] if self.axis == 0 else rel[::-1][None, :]
+        g[self._ix(slice(n, n + 1), mid)] = 1.0
+        self._gamma2d = storage.as_storage(g[:, :, None], device=self.storage_options.device)
+        self._gamma = storage.B200Array(self._gamma2d.t.expand(-1, -1, self._shape[2]))
+        self._stencil = self.compile_stencil("irelax")
+
+    def _extents(self, name):
+        return _extent(self.ni, self.nj, self.nz, name)
+
+    def get_numerical_field(self, field, field_name=None):
+        nb = self.nb
+        src = storage.as_storage(field, device=self.storage_options.device)
+        shape = list(src.shape)
+        shape[1 - self.axis] += 2 * nb
+        trg = self.zeros(shape=tuple(shape))
+        trg[self._ix(slice(None), slice(None, nb + 1))] = src[self._ix(slice(None), slice(0, 1))]
+        trg[self._ix(slice(None), slice(nb + 1, None))] = src[self._ix(slice(None), slice(-1, None))]
+        return trg
+
+    def enforce_field(self, field, field_name=None, field_units=None, time=None):
+        nb = self.nb
+        m = self._extents(field_name)
+        ma, mo, mk = m[self.axis], m[1 - self.axis], m[2]
+        origin, domain = [0, 0, 0], [m[0], m[1], mk]
+        origin[1 - self.axis], domain[1 - self.axis] = nb, mo - nb
+        self._stencil(in_gamma=self._gamma, in_phi_ref=self.reference_state[field_name],
+                      inout_phi=field, origin=tuple(origin), domain=tuple(domain))
+        # repeat the innermost line(s) across the degenerate direction
+        k, al = slice(0, mk), slice(0, ma)
+        field[self._ix(al, slice(0, nb), k)] = field[self._ix(al, slice(nb, nb + 1), k)]
+        field[self._ix(al, slice(mo - nb, mo), k)] = field[self._ix(al, slice(mo - nb - 1, mo - nb), k)]
+
+    def get_physical_field(self, field, field_name=None):
+        return field[self._ix(slice(None), slice(self.nb, -self.nb))]
+
+    def _outermost(self, x_layers, field, field_name):
+        mi, mj, _ = self._extents(field_name)
+        ref = self.reference_state[field_name]
+        if x_layers:
+            field[0, :mj] = ref[0, :mj]
+            field[mi - 1, :mj] = ref[mi - 1, :mj]
+        else:
+            field[:mi, 0] = ref[:mi, 0]
+            field[:mi, mj - 1] = ref[:mi, mj - 1]
+
+    def set_outermost_layers_x(self, field, field_name=None, field_units=None, time=None):
+        self._outermost(True, field, field_name)
+
+    def set_outermost_layers_y(self, field, field_name=None, field_units=None, time=None):
+        self._outermost(False, field, field_name)
+
+
+class Relaxed1DX(_Relaxed1D):
+    """relaxed.py:L250-L461 (ny == 1)."""
+
+    axis = 0
+
+
+class Relaxed1DY(_Relaxed1D):
+    """relaxed.py:L463-L678 (nx == 1)."""
+
+    axis = 1
+
+
+class _Periodic1D(_OneDimensional):
+    type = "periodic"
+
+    def __init__(self, nx, ny, nz, nb, backend_options=None, storage_options=None):
+        super().__init__(nx, ny, nz, nb, backend_options, storage_options)
+        n = self._n()
+        assert n > 1 and (ny if self.axis == 0 else nx) == 1 and nb <= n / 2
+        self.ni, self.nj = (self.nx + 2 * nb, 2 * nb + 1) if self.axis == 0 else (2 * nb + 1, self.ny + 2 * nb)
+
+    def enforce_field(self, field, field_name=None, field_units=None, time=None):
+        """periodic.py:L190-L206 / L282-L298: wrap along the axis (period n - 1 intervals), then
+        repeat across it."""
+        n, nb = self._n(), self.nb
+        st_a, st_o = self._staggered(field_name)
+        mx, my = n + int(st_a), 1 + int(st_o)
+        mi, mid = mx + 2 * nb, slice(nb, my + nb)
+        field[self._ix(slice(0, nb), mid)] = field[self._ix(slice(n - 1, n - 1 + nb), mid)]
+        lo = nb + 1 if mx == n else nb + 2
+        field[self._ix(slice(mx + nb, mx + 2 * nb), mid)] = field[self._ix(slice(lo, lo + nb), mid)]
+        al = slice(0, mi)
+        field[self._ix(al, slice(0, nb))] = field[self._ix(al, slice(nb, nb + 1))]
+        src = slice(nb, nb + 1) if my == 1 else slice(nb + 1, nb + 2)
+        field[self._ix(al, slice(my + nb, my + 2 * nb))] = field[self._ix(al, src)]
+
+    def get_numerical_field(self, field, field_name=None):
+        """periodic.py:L156-L185 / L248-L277"""
+        n, nb = self._n(), self.nb
+        st_a, st_o = self._staggered(field_name)
+        mx, my = n + int(st_a), 1 + int(st_o)
+        src = storage.as_storage(field, device=self.storage_options.device)
+        trg = self.zeros(shape=(src.shape[0] + 2 * nb, src.shape[1] + 2 * nb) + tuple(src.shape[2:]))
+        trg[self._ix(slice(nb, mx + nb), slice(nb, my + nb))] = src[self._ix(slice(0, mx), slice(0, my))]
+        self.enforce_field(trg, field_name)
+        return trg
+
+    def get_physical_field(self, field, field_name=None):
+        return field[self.nb : -self.nb, self.nb : -self.nb]
+
+    def set_outermost_layers_x(self, field, field_name=None, field_units=None, time=None):
+        field[0, :] = field[-2, :]
+        field[-1, :] = field[1, :]
+
+    def set_outermost_layers_y(self, field, field_name=None, field_units=None, time=None):
+        field[:, 0] = field[:, -2]
+        field[:, -1] = field[:, 1]
+
+
+class Periodic1DX(_Periodic1D):
+    """periodic.py:L125-L214 (ny == 1)."""
+
+    axis = 0
+
+
+class Periodic1DY(_Periodic1D):
+    """periodic.py:L217-L306 (nx == 1)."""
+
+    axis = 1

@@ -76,3 +76,51 @@ def test_relaxed_boundary_equals_reference(nb, nr):
         ref_fn(a, field_name=name, field_units="1")
         ora_fn(b, name)
         np.testing.assert_array_equal(b, a, err_msg=name)
+
+
+@pytest.mark.parametrize("kind,kw,nb", [("relaxed", {"nr": 5}, 2), ("relaxed", {"nr": 3}, 3),
+                                        ("periodic", {}, 2), ("periodic", {}, 1)])
+@pytest.mark.parametrize("nx,ny", [(17, 1), (1, 15)])
+def test_one_dimensional_boundary_mirrors_equal_reference(kind, kw, nb, nx, ny):
+    """The b200 mirrors of Relaxed1DX / 1DY and Periodic1DX / 1DY (tasmania_b200/boundary.py), run
+    numerically through the oracle-backed ABI stub, against the reference's own classes (picked by
+    its factory on ny == 1 / nx == 1 grids): numerical <-> physical fields, enforce_field on
+    unstaggered / staggered / interface-level fields, outermost layers -- bit for bit."""
+    import tasmania_b200 as tb
+    from tasmania_b200.boundary import HorizontalBoundary
+    from tests.abi_oracle import OracleStub
+    from tests.abi_stub import stubbed_library
+
+    nz = 4
+    names = FIELDS + ("air_pressure_on_interface_levels",)
+    hb = _domain(nx, ny, nz, kind, nb, **kw).horizontal_boundary
+    assert type(hb).__name__.endswith("1DX" if ny == 1 else "1DY")
+    rng = np.random.default_rng(nx + nb)
+    shape = (hb.ni + 1, hb.nj + 1, nz + 1)
+    fields = {n: rng.standard_normal(shape) for n in names}
+    refs = {n: rng.standard_normal(shape) for n in names}
+    phys = rng.standard_normal((nx, ny, nz))
+    hb.reference_state = {n: refload.DataArray(v.copy(), attrs={"units": "1"}) for n, v in refs.items()}
+    want = {}
+    for n in names:
+        f = fields[n].copy()
+        hb.enforce_field(f, field_name=n, field_units="1")
+        hb.set_outermost_layers_x(f, field_name=n, field_units="1")
+        hb.set_outermost_layers_y(f, field_name=n, field_units="1")
+        want[n] = f
+    want_num = np.asarray(hb.get_numerical_field(phys.copy(), field_name=FIELDS[0]))
+    with stubbed_library(OracleStub):
+        mhb = HorizontalBoundary.factory(kind, nx, ny, nz, nb, **kw)
+        assert type(mhb).__name__ == type(hb).__name__ and (mhb.ni, mhb.nj) == (hb.ni, hb.nj)
+        mhb.reference_state = {n: tb.as_storage(v) for n, v in refs.items()}
+        for n in names:
+            f = tb.as_storage(fields[n])
+            mhb.enforce_field(f, field_name=n)
+            mhb.set_outermost_layers_x(f, field_name=n)
+            mhb.set_outermost_layers_y(f, field_name=n)
+            np.testing.assert_array_equal(tb.to_numpy(f), want[n], err_msg=n)
+        num = mhb.get_numerical_field(tb.as_storage(phys), field_name=FIELDS[0])
+        np.testing.assert_array_equal(tb.to_numpy(num), want_num)
+        np.testing.assert_array_equal(
+            tb.to_numpy(mhb.get_physical_field(num)),
+            np.asarray(hb.get_physical_field(want_num, field_name=FIELDS[0])))
