@@ -114,6 +114,28 @@ def gen_stencils_1d():
     dif.diffusion_numpy(hphi, hout, alpha=1.0 / 32.0, origin=(3, 3, 1), domain=(9, 7, 3))
     out.update(hyper_phi=hphi, hyper_out=hout, hyper_box=np.array([3, 3, 1, 9, 7, 3]),
                hyper_alpha=np.array(1.0 / 32.0))
+    # ---- the 1-D lateral boundaries (Relaxed1DX / 1DY, Periodic1DX / 1DY of the reference)
+    bnames = ("air_isentropic_density", "x_velocity_at_u_locations", "y_velocity_at_v_locations",
+              "air_pressure_on_interface_levels")
+    for kind, kw, nb in (("relaxed", {"nr": 5}, 2), ("periodic", {}, 2)):
+        for ax, (bnx, bny) in (("x", (17, 1)), ("y", (1, 15))):
+            bnz = 4
+            hb = _make_domain(bnx, bny, bnz, kind, nb, kw, topo=False).horizontal_boundary
+            bshape = (hb.ni + 1, hb.nj + 1, bnz + 1)
+            tag = f"hb_{kind}_{ax}"
+            out[tag + "_dims"] = np.array([bnx, bny, bnz, nb, kw.get("nr", 0)])
+            phys = rng.standard_normal((bnx, bny, bnz))
+            out[tag + "_phys"] = phys
+            out[tag + "_num"] = np.asarray(hb.get_numerical_field(phys.copy(), field_name=bnames[0]))
+            refs = {n: rng.standard_normal(bshape) for n in bnames}
+            hb.reference_state = {n: DataArray(v.copy(), attrs={"units": "1"}) for n, v in refs.items()}
+            for m, n in enumerate(bnames):
+                f = rng.standard_normal(bshape)
+                out[f"{tag}_ref{m}"], out[f"{tag}_in{m}"] = refs[n], f.copy()
+                hb.enforce_field(f, field_name=n, field_units="1")
+                hb.set_outermost_layers_x(f, field_name=n, field_units="1")
+                hb.set_outermost_layers_y(f, field_name=n, field_units="1")
+                out[f"{tag}_out{m}"] = f
     save("stencils_1d", **out)
 
 

@@ -106,3 +106,31 @@ def moist_case(nx, ny, nz, *, topo_seconds=60.0, max_height=1000.0, relative_hum
         state[oi.MFCW] = 8e-4 * blob
         state[oi.MFPW] = 3e-4 * np.roll(blob, 2, axis=0) * (blob > 0)
     return grid, state
+
+
+BOUNDARY_1D_NAMES = ("air_isentropic_density", "x_velocity_at_u_locations", "y_velocity_at_v_locations",
+                     "air_pressure_on_interface_levels")
+
+
+def check_one_dimensional_boundaries(fx, tb):
+    """The b200 mirrors of Relaxed1DX / 1DY and Periodic1DX / 1DY against what the reference's own
+    classes wrote into tests/golden/stencils_1d.npz (shared by the host test, which runs it through
+    the oracle-backed ABI stub, and the GPU test)."""
+    from tasmania_b200.boundary import HorizontalBoundary
+
+    for kind in ("relaxed", "periodic"):
+        for ax in "xy":
+            tag = f"hb_{kind}_{ax}"
+            nx, ny, nz, nb, nr = (int(v) for v in fx[tag + "_dims"])
+            hb = HorizontalBoundary.factory(kind, nx, ny, nz, nb, **({"nr": nr} if kind == "relaxed" else {}))
+            num = hb.get_numerical_field(tb.as_storage(fx[tag + "_phys"]), field_name=BOUNDARY_1D_NAMES[0])
+            np.testing.assert_array_equal(tb.to_numpy(num), fx[tag + "_num"], err_msg=tag)
+            np.testing.assert_array_equal(tb.to_numpy(hb.get_physical_field(num)), fx[tag + "_phys"])
+            hb.reference_state = {n: tb.as_storage(fx[f"{tag}_ref{m}"])
+                                  for m, n in enumerate(BOUNDARY_1D_NAMES)}
+            for m, n in enumerate(BOUNDARY_1D_NAMES):
+                f = tb.as_storage(fx[f"{tag}_in{m}"])
+                hb.enforce_field(f, field_name=n)
+                hb.set_outermost_layers_x(f, field_name=n)
+                hb.set_outermost_layers_y(f, field_name=n)
+                np.testing.assert_array_equal(tb.to_numpy(f), fx[f"{tag}_out{m}"], err_msg=f"{tag} {n}")

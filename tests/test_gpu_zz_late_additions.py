@@ -194,6 +194,12 @@ def test_k3_column_scans_from_one_level_to_deep_columns(dims):
     assert hp.relerr(tb.to_numpy(h), want_h) <= 1e-13
 
 
+def test_one_dimensional_boundary_mirrors_golden():
+    """Relaxed1DX / 1DY (irelax kernel + slab copies on device storages) and Periodic1DX / 1DY
+    against the fixture the reference's own classes wrote."""
+    hp.check_one_dimensional_boundaries(hp.load("stencils_1d"), tb)
+
+
 MARCH_SCRIPT = r"""
 import sys
 sys.path.insert(0, %r)

@@ -255,6 +255,14 @@ def test_hyperdiffusion_stencil_host_path_equals_reference_fixture(stencils_1d_g
         assert stub.count("tb200_hyperdiffusion") == 1
 
 
+def test_one_dimensional_boundary_mirrors_equal_reference_fixture(stencils_1d_golden):
+    import tasmania_b200 as tb
+
+    with stubbed_library(OracleStub) as stub:
+        hp.check_one_dimensional_boundaries(stencils_1d_golden, tb)
+        assert stub.count("tb200_relax") == 8
+
+
 def test_fused_stage_host_path_equals_oracle_numerically():
     """The headline path's host side: IsentropicDryRun with the fused stage (one ABI call per RK
     stage carrying 25 fields and the stage configuration), emulated stage by stage with the oracle."""
