@@ -284,8 +284,10 @@ def run_reference(args):
         "unit": "Mpts*steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
         "ms_per_step": pts / (val * 1e6) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "sample_grid": [nx, ny, nz],
-                   "replicas": cores},
+        "config": {"workload": workload_name("c2").replace(" per GPU", "") + " -- the bounded sample of the "
+                               "headline workload (same physics and schemes, config 2's grid; the "
+                               f"b200 arm runs {'x'.join(str(v) for v in WORKLOADS[args.workload])} per GPU)",
+                   "sample_grid": [nx, ny, nz], "replicas": cores},
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": "Mpts*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -403,6 +405,14 @@ def run_b200(args):
 
     pts = nx * ny * nz
     value = pts * args.steps * world / (ms * 1e-3) / 1e6
+    decomposition = getattr(run, "decomposition", "1x1")
+    halo_mode = ("overlapped with the interior blocks of the momentum kernel"
+                 if getattr(run, "overlap", None) is not None else ("after each stage" if distributed else "none"))
+    api = ("tasmania_b200.distributed.DecomposedDryRun.step" if distributed else
+           "tasmania_b200.isentropic_dry.IsentropicDryRun.step") + \
+        " -> tasmania_b200.isentropic.IsentropicDynamicalCore.__call__ (mirror of the reference class; " \
+        "fused stage tb200_isentropic_stage_dry, lazy velocities)"
+    halo_bytes = run.sub.halo.bytes_per_exchange if distributed else None
 
     # ---- halo exchange share (device time of pack + send/recv + unpack + seam fix-up per stage)
     exchange_ms = None
@@ -426,6 +436,12 @@ def run_b200(args):
         roof = None
     # ---- end to end through the public API with host buffers
     e2e = end_to_end(run, args, world, barrier, distributed)
+    aux = None
+    if not distributed and not args.no_aux and args.workload == "c5":
+        del run  # release the headline's fields first
+        torch.cuda.empty_cache()
+        aux = aux_measurements(args)
+        run = None
 
     if rank == 0:
         base = None
@@ -438,19 +454,19 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "l2": "inputs larger than L2"
                        if pts * 8 > 126e6 else "L2-resident grid (no flush: launch-latency regime)",
-                       "decomposition": getattr(run, "decomposition", "1x1"),
-                       "halo_exchange": ("overlapped with the interior blocks of the momentum kernel"
-                                         if getattr(run, "overlap", None) is not None else
-                                         ("after each stage" if distributed else "none"))},
+                       "decomposition": decomposition,
+                       "halo_exchange": halo_mode, "api": api},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world,
             "hbm_frac_step": BYTES_PER_POINT_STEP * pts / (ms / args.steps * 1e-3) / 1e9
             / measured_peak_gbs()[0],
         }
         if roof is not None:
             line["roofline"] = roof
+        if aux is not None:
+            line["aux"] = aux
         if exchange_ms is not None:
             line["halo_exchange_ms_per_stage"] = exchange_ms
-            line["halo_exchange_bytes_per_stage"] = run.sub.halo.bytes_per_exchange
+            line["halo_exchange_bytes_per_stage"] = halo_bytes
         if base is not None:
             line["cpu_baseline"] = base
         print(json.dumps(line))
@@ -519,21 +535,51 @@ def run_c4(args):
                        "l2": "inputs larger than L2" if pts * 8 > 126e6 else "L2-resident grid"},
             "clocks": clocks, "e2e": None, "gpu_launches": launches,
             "hbm_frac_step": (16 + 24) * pts / (ms / args.steps * 1e-3) / 1e9 / peak,
-            "roofline": {"bound": "hbm", "kernel": "diffusion (" + ("march_kernel<4>" if os.environ.get(
-                "TB200_DIFF_IMPL") == "march" else "cross_kernel<4>") + ")", "achieved": gbs,
+            "roofline": {"bound": "hbm", "kernel": "diffusion (" + {"march": "march_kernel<4>", "tile": "cross_kernel<4>"}.get(
+                os.environ.get("TB200_DIFF_IMPL", ""), "march2_kernel<4>") + ")", "achieved": gbs,
                          "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
                          "peak_source": how, "ms_per_launch": k_ms,
                          "algorithmic_bytes_per_launch": 16 * pts},
         }))
 
 
-# algorithmic HBM bytes per grid point of each kernel of the fused stage (every distinct array
-# read once, every output written once) and their DRAM traffic per launch at
-# 1024x1024x64 from the ncu --set full captures under profiles/ (dram__bytes_read + write)
-KERNEL_BYTES_PER_POINT = {"s_step (stage_a_kernel)": 40, "column_scan (stage_b_kernel)": 16,
-                          "momentum (stage_mv2_kernel)": 120}
-NCU_TRAFFIC_C5 = {"s_step (stage_a_kernel)": 2.96e9, "column_scan (stage_b_kernel)": 1.03e9,
-                  "momentum (stage_mv2_kernel)": 9.41e9}  # MV: 8.51 GB at stage 0 (now == int), 9.86 GB at stages 1, 2
+# Algorithmic HBM bytes per grid point of each kernel of the fused stage, per RK stage (every
+# distinct array read once, every output written once).  With lazy velocities
+# (tb200_isentropic_stage.derive_uv_in / skip_uv_out) the three stages of a step differ:
+#   s-step     stage 0: s (now == int), u, v -> s_pre = 32; stages 1, 2: s_now, s_int, su_int, sv_int -> s_pre = 40
+#   scans      s_pre -> mtg_new = 16
+#   momentum   stage 0: s, s_pre, mtg_now, mtg_new, u, v, su, sv -> su, sv (+ s in the relaxation band
+#              / damping layer only) = 80; stage 1: s_now, s_int, s_pre, mtg_now, mtg_new, su_now, su_int,
+#              sv_now, sv_int -> su, sv = 88; stage 2: the same reads -> s, su, sv, u, v = 112
+KERNEL_NAMES = ("s_step (stage_a_kernel)", "column_scan (stage_b_kernel)", "momentum (stage_mv2_kernel)")
+KERNEL_BYTES_PER_POINT_LAZY = {0: (32, 16, 80), 1: (40, 16, 88), 2: (40, 16, 112)}
+KERNEL_BYTES_PER_POINT_EAGER = {0: (32, 16, 104), 1: (40, 16, 120), 2: (40, 16, 120)}
+NCU_KERNEL_KEYS = ("stage_a_kernel", "stage_b_kernel", "stage_mv2_kernel")
+# DRAM traffic per launch: read from the ncu --set full capture of THIS round's build of the same
+# command (profiles/README.md says which commit), never typed in
+NCU_TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r02_c5_ncu_full_raw.csv")
+
+
+def ncu_traffic(kernel_key, path=NCU_TRAFFIC_CSV):
+    """Mean dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels whose name
+    contains ``kernel_key`` in an ``ncu --page raw --csv`` export; (None, None) if unavailable."""
+    import csv
+
+    if not os.path.exists(path):
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    try:
+        with open(path, newline="") as f:
+            rows = list(csv.reader(f))
+        head, units = rows[0], rows[1]
+        kn, rd, wr = head.index("Kernel Name"), head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+        vals = [float(r[rd].replace(",", "")) * unit[units[rd]] + float(r[wr].replace(",", "")) * unit[units[wr]]
+                for r in rows[2:] if len(r) > max(kn, rd, wr) and kernel_key in r[kn]]
+    except (ValueError, KeyError, IndexError, OSError):
+        return None, None
+    if not vals:
+        return None, None
+    return float(np.mean(vals)), f"profiles/{os.path.basename(path)} ({len(vals)} launches, mean per launch)"
 
 
 def kernel_roofline(run, args):
@@ -549,13 +595,13 @@ def kernel_roofline(run, args):
     handle = tblib.load()
     dyc = run.dyc
     orig = dyc._stage_fused
-    samples = []
+    samples = {}
 
     def timed(stage, state, timestep, out_state):
         orig(stage, state, timestep, out_state)
         ms = (C.c_double * 3)()
         tblib.check(handle.tb200_stage_profile_read(ms), "tb200_stage_profile_read")
-        samples.append(tuple(ms))
+        samples.setdefault(stage, []).append(tuple(ms))
 
     tblib.check(handle.tb200_stage_profile(1), "tb200_stage_profile")
     dyc._stage_fused = timed
@@ -565,31 +611,128 @@ def kernel_roofline(run, args):
     torch.cuda.synchronize()
     dyc._stage_fused = orig
     tblib.check(handle.tb200_stage_profile(0), "tb200_stage_profile")
-    t = np.mean(np.array(samples), axis=0)  # ms: s-step, scan, momentum
+    per_stage = {st: np.mean(np.array(v), axis=0) for st, v in samples.items()}  # ms: s-step, scan, momentum
+    nst = len(per_stage)
+    bpp = KERNEL_BYTES_PER_POINT_LAZY if dyc.lazy_velocities else KERNEL_BYTES_PER_POINT_EAGER
     pts = run.nx * run.ny * run.nz
     peak, how = measured_peak_gbs()
-    names = list(KERNEL_BYTES_PER_POINT)
     kernels = {}
-    for n, ms in zip(names, t):
-        if ms > 0:
-            gbs = KERNEL_BYTES_PER_POINT[n] * pts / (ms * 1e-3) / 1e9
-            kernels[n] = {"ms_per_launch": float(ms), "achieved": gbs, "frac": gbs / peak,
-                          "algorithmic_bytes_per_launch": KERNEL_BYTES_PER_POINT[n] * pts}
-    dom = names[int(np.argmax(t))]
-    stage_ms = float(np.sum(t))
+    for ki, n in enumerate(KERNEL_NAMES):
+        ms = float(np.mean([per_stage[st][ki] for st in per_stage]))
+        if ms <= 0:
+            continue
+        bytes_pt = float(np.mean([bpp[min(st, 2)][ki] for st in per_stage]))
+        gbs = bytes_pt * pts / (ms * 1e-3) / 1e9
+        kernels[n] = {"ms_per_launch": ms, "achieved": gbs, "frac": gbs / peak,
+                      "algorithmic_bytes_per_launch": bytes_pt * pts,
+                      "algorithmic_bytes_per_point_by_stage": [bpp[min(st, 2)][ki] for st in sorted(per_stage)],
+                      "ms_by_stage": [float(per_stage[st][ki]) for st in sorted(per_stage)]}
+        traffic, src = ncu_traffic(NCU_KERNEL_KEYS[ki])
+        if traffic is not None and (run.nx, run.ny, run.nz) == WORKLOADS["c5"]:
+            kernels[n]["traffic"], kernels[n]["traffic_source"] = traffic, src
+    dom = max(kernels, key=lambda n: kernels[n]["ms_per_launch"])
+    stage_ms = float(sum(k["ms_per_launch"] for k in kernels.values()))
     stage_gbs = BYTES_PER_POINT_STAGE * pts / (stage_ms * 1e-3) / 1e9
-    c5 = (run.nx, run.ny, run.nz) == WORKLOADS["c5"]
     return {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved"], "peak": peak,
             "unit": "GB/s", "frac": kernels[dom]["frac"],
-            "traffic": NCU_TRAFFIC_C5[dom] if c5 else None,
-            "traffic_source": "ncu --set full capture of the same command, profiles/ (per launch)"
-            if c5 else None,
+            "traffic": kernels[dom].get("traffic"), "traffic_source": kernels[dom].get("traffic_source"),
             "peak_source": how, "ms_per_launch": kernels[dom]["ms_per_launch"],
             "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"],
+            "launches_averaged": f"the {nst} RK stages of a step (their compulsory traffic differs: "
+                                 "intermediate stages neither read nor write u, v)",
             "kernels": kernels,
             "fused_stage": {"ms": stage_ms, "algorithmic_bytes": BYTES_PER_POINT_STAGE * pts,
                             "achieved": stage_gbs, "frac": stage_gbs / peak,
-                            "note": "112 B/pt (SURVEY.md 8d) over the three kernels of one RK stage"}}
+                            "note": "112 B/pt (SURVEY.md 8d) over the three kernels of one RK stage, mean of the stages"}}
+
+
+# ------------------------------------------------------------------ the other configurations, briefly
+def aux_measurements(args):
+    """Short measurements of BASELINE configs[1], [2], [3] after the timed headline region, so
+    that one driver run carries every configuration.  Each entry:
+    ms/step on the device (CUDA events), launches per step, fraction of the HBM roofline where a
+    per-point traffic figure exists.  A failure is reported in place, never raised."""
+    import torch
+
+    from tasmania_b200 import lib as tblib
+
+    peak, _ = measured_peak_gbs()
+    out = {}
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = tblib.launch_count()
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / steps, (tblib.launch_count() - n0) / steps
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as exc:  # noqa: BLE001  (reported, the headline line must still print)
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        torch.cuda.empty_cache()
+
+    def c2():
+        nx, ny, nz = WORKLOADS["c2"]
+        res = {"workload": workload_name("c2").replace(" per GPU", "")}
+        for graph in (False, True):
+            run = DryRun(nx, ny, nz, graph=graph)
+            ms, launches = timed(run.step, 50, 8)
+            for n in run.out_names:
+                if not bool(torch.isfinite(run.state[n].t).all()):
+                    raise RuntimeError(f"{n} is not finite")
+            key = "cuda_graphs" if graph else "eager"
+            res[key] = {"ms_per_step": ms, "Mpts_steps_per_s": nx * ny * nz / ms / 1e3,
+                        "hbm_frac_step": BYTES_PER_POINT_STEP * nx * ny * nz / (ms * 1e-3) / 1e9 / peak,
+                        "launches_per_step": launches if not graph else None}
+            del run
+        return res
+
+    def c3():
+        from tasmania_b200.isentropic_moist import IsentropicMoistSUS, moist_mountain_case
+
+        nx, ny, nz = 256, 256, 60
+        grid, np_state = moist_mountain_case(nx, ny, nz, topo_seconds=1800.0, max_height=500.0,
+                                             relative_humidity=0.95, seed=True,
+                                             half_width_km=(1.1 * (nx - 1), 1.1 * (ny - 1)))
+        model = IsentropicMoistSUS(grid, np_state, timedelta(seconds=5))
+        ms, launches = timed(model.step, 20, 5)
+        for n, v in model.state.items():
+            if n != "time" and not bool(torch.isfinite(v.t).all()):
+                raise RuntimeError(f"{n} is not finite")
+        return {"workload": "moist isentropic + Kessler + sedimentation, sequential-update splitting, "
+                            f"{nx}x{ny}x{nz}, fp64", "ms_per_step": ms,
+                "Mpts_steps_per_s": nx * ny * nz / ms / 1e3, "launches_per_step": launches}
+
+    def c4():
+        from tasmania_b200.diffusion_dwarf import DiffusionDwarfRun
+
+        nx, ny, nz = WORKLOADS["c4"]
+        run = DiffusionDwarfRun(nx, ny, nz)
+        ms, launches = timed(run.step, 5, 3)
+        k_ms, _ = timed(lambda: run.diffusion(run.phi, run.tnd), 5, 2)
+        if not bool(torch.isfinite(run.phi.t).all()):
+            raise RuntimeError("phi is not finite")
+        pts = nx * ny * nz
+        return {"workload": f"fourth-order horizontal diffusion dwarf, periodic BC, {nx}x{ny}x{nz}, fp64",
+                "ms_per_step": ms, "launches_per_step": launches,
+                "step": "diffusion (16 B/pt) + phi update (24 B/pt) + periodic halo",
+                "hbm_frac_step": 40 * pts / (ms * 1e-3) / 1e9 / peak,
+                "diffusion_kernel": {"ms_per_launch": k_ms, "achieved": 16 * pts / (k_ms * 1e-3) / 1e9,
+                                     "frac": 16 * pts / (k_ms * 1e-3) / 1e9 / peak, "unit": "GB/s",
+                                     "kernel": os.environ.get("TB200_DIFF_IMPL", "march2")}}
+
+    guarded("c2_dry_161x161x60", c2)
+    guarded("c3_moist_256x256x60", c3)
+    guarded("c4_diffusion_4096x4096x64", c4)
+    return out
 
 
 def end_to_end(run, args, world, barrier, distributed):
@@ -631,7 +774,8 @@ def end_to_end(run, args, world, barrier, distributed):
     pts = run.nx * run.ny * run.nz
     return {"value": pts * steps * world / (ms * 1e-3) / 1e6, "unit": "Mpts*steps/s",
             "h2d_bytes_per_step": nbytes(host_in), "d2h_bytes_per_step": nbytes(host_out),
-            "steps": steps, "api": "tasmania_b200.pipeline.HostStreamedDryCore.step"}
+            "steps": steps, "api": "tasmania_b200.pipeline.HostStreamedDryCore.step (prognostic fields "
+                                   "s, su, sv over PCIe; Montgomery potential and velocities diagnosed on the device)"}
 
 
 def main():
@@ -642,6 +786,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true",
+                    help="skip the short measurements of configs[1..3] after the headline (JSON key 'aux')")
     ap.add_argument("--graph", action="store_true",
                     help="replay the step as CUDA graphs (tasmania_b200.graphs): pays on the "
                          "launch-bound grids (c2), irrelevant at c5 where a step is 8.5 ms of kernels")

@@ -377,6 +377,19 @@ typedef struct tb200_isentropic_stage {
    * must be final after part 1 (0 for an edge without a neighbour). */
   int32_t part;
   int32_t rim[4];
+  /* Velocity round trips between the stages of one time step (both default to 0 = the
+   * reference's data flow, dycore.py:L702-L721: every stage writes u_new / v_new and the next
+   * one reads them as u_int / v_int).
+   * derive_uv_in != 0: the advecting velocities are re-diagnosed inside the kernels from s_int,
+   *   su_int, sv_int with the formula of velocity_x / velocity_y (dwarfs/diagnostics.py:L219-L272)
+   *   instead of being read -- bit-identical whenever u_int / v_int ARE that diagnosis (true for
+   *   the output of a previous stage; not for an arbitrary initial state), u_int / v_int are not
+   *   touched and may be stale.
+   * skip_uv_out != 0: u_new / v_new are not written (an intermediate stage whose consumer sets
+   *   derive_uv_in).  With skip_uv_out, scratch_s may be the SAME storage as s_new: the stage then
+   *   updates s in place and stores it only where relaxation / damping changed it. */
+  int32_t derive_uv_in;
+  int32_t skip_uv_out;
 } tb200_isentropic_stage;
 
 int tb200_isentropic_stage_dry(

@@ -116,6 +116,85 @@ struct FmaFields {
   View out[TB200_FMA_MAX_FIELDS], a[TB200_FMA_MAX_FIELDS], b[TB200_FMA_MAX_FIELDS];
   int n;
 };
+
+// The generic box_kernel instantiation of this op needed 115 registers (eight predicated field
+// slots per thread) and ran two 256-thread blocks per SM with two 8-byte loads per thread in
+// flight: 1.0 TB/s, a quarter of the moist step and most of the diffusion dwarf's
+// (profiles/README.md, round 2a).  Specialised on the number of fields instead; the vector
+// variant gives a thread an aligned PAIR of columns (LDG.128 / STG.128, 2 N independent 16-byte
+// loads in flight per thread).  out may alias a or b: a thread reads its own points first.
+template <int N, bool VEC>
+__global__ void __launch_bounds__(256) fma_fields_kernel(const FmaFields ff, double f, int i0, int j0,
+                                                         int k0, int di, int dj, int dk) {
+  const int j = j0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= j0 + dj) return;
+  if (VEC) {
+    const int c0 = (i0 & ~1) + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (c0 >= i0 + di) return;
+    const bool m0 = c0 >= i0, m1 = c0 + 1 < i0 + di;
+    for (int k = k0 + blockIdx.z; k < k0 + dk; k += gridDim.z) {
+      double2 va[N], vb[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        va[n] = *reinterpret_cast<const double2 *>(ff.a[n].p + (c0 + j * ff.a[n].s1 + k * ff.a[n].s2));
+        vb[n] = *reinterpret_cast<const double2 *>(ff.b[n].p + (c0 + j * ff.b[n].s1 + k * ff.b[n].s2));
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double *po = ff.out[n].p + (c0 + j * ff.out[n].s1 + k * ff.out[n].s2);
+        const double r0 = va[n].x + f * vb[n].x, r1 = va[n].y + f * vb[n].y;
+        if (m0 && m1)
+          *reinterpret_cast<double2 *>(po) = make_double2(r0, r1);
+        else if (m0)
+          po[0] = r0;
+        else if (m1)
+          po[1] = r1;
+      }
+    }
+  } else {
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i0 + di) return;
+    for (int k = k0 + blockIdx.z; k < k0 + dk; k += gridDim.z) {
+      double va[N], vb[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        va[n] = ff.a[n](i, j, k);
+        vb[n] = ff.b[n](i, j, k);
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) ff.out[n](i, j, k) = va[n] + f * vb[n];
+    }
+  }
+}
+
+// pairs may be read beyond the box (never beyond a row of the allocation: even pitches)
+bool fma_vec_ok(const FmaFields &ff) {
+  for (int n = 0; n < ff.n; ++n)
+    for (const View *v : {&ff.out[n], &ff.a[n], &ff.b[n]})
+      if (v->s0 != 1 || (v->s1 & 1) != 0 || (v->s2 & 1) != 0 || v->s1 < 2 ||
+          (reinterpret_cast<uintptr_t>(v->p) & 15) != 0)
+        return false;
+  return true;
+}
+
+template <int N>
+int launch_fma_fields(const FmaFields &ff, double f, const int32_t o[3], const int32_t d[3], cudaStream_t st) {
+  if (d[0] <= 0 || d[1] <= 0 || d[2] <= 0) return TB200_OK;  // empty box: nothing to do
+  const int gz = d[2] > 65535 ? 65535 : d[2];
+  if (fma_vec_ok(ff)) {
+    const int pairs = (o[0] + d[0] - (o[0] & ~1) + 1) / 2;
+    dim3 block(pairs >= 128 ? 128 : (pairs > 32 ? 64 : 32), 1, 1);
+    block.y = 256 / block.x;
+    dim3 grid((pairs + block.x - 1) / block.x, (d[1] + block.y - 1) / block.y, gz);
+    fma_fields_kernel<N, true><<<grid, block, 0, st>>>(ff, f, o[0], o[1], o[2], d[0], d[1], d[2]);
+  } else {
+    dim3 block(d[0] <= 32 ? 32 : 64, 1, 1);
+    block.y = 256 / block.x;
+    dim3 grid((d[0] + block.x - 1) / block.x, (d[1] + block.y - 1) / block.y, gz);
+    fma_fields_kernel<N, false><<<grid, block, 0, st>>>(ff, f, o[0], o[1], o[2], d[0], d[1], d[2]);
+  }
+  return check_launch("fma_fields");
+}
 }  // namespace
 
 extern "C" int tb200_fma_fields(int nfields, tb200_field *const *out,
@@ -135,18 +214,17 @@ extern "C" int tb200_fma_fields(int nfields, tb200_field *const *out,
     TB200_REQUIRE(box_inside(ff.a[n], origin, domain), "fma_fields: a box outside storage %d", n);
     TB200_REQUIRE(box_inside(ff.b[n], origin, domain), "fma_fields: b box outside storage %d", n);
   }
-  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
-  return launch_box("fma_fields", domain, static_cast<cudaStream_t>(stream),
-                    [=] __device__(int i, int j, int k) {
-                      i += i0; j += j0; k += k0;
-                      double va[TB200_FMA_MAX_FIELDS], vb[TB200_FMA_MAX_FIELDS];
-#pragma unroll
-                      for (int n = 0; n < TB200_FMA_MAX_FIELDS; ++n)
-                        if (n < ff.n) { va[n] = ff.a[n](i, j, k); vb[n] = ff.b[n](i, j, k); }
-#pragma unroll
-                      for (int n = 0; n < TB200_FMA_MAX_FIELDS; ++n)
-                        if (n < ff.n) ff.out[n](i, j, k) = va[n] + f * vb[n];
-                    });
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (nfields) {
+    case 1: return launch_fma_fields<1>(ff, f, origin, domain, st);
+    case 2: return launch_fma_fields<2>(ff, f, origin, domain, st);
+    case 3: return launch_fma_fields<3>(ff, f, origin, domain, st);
+    case 4: return launch_fma_fields<4>(ff, f, origin, domain, st);
+    case 5: return launch_fma_fields<5>(ff, f, origin, domain, st);
+    case 6: return launch_fma_fields<6>(ff, f, origin, domain, st);
+    case 7: return launch_fma_fields<7>(ff, f, origin, domain, st);
+    default: return launch_fma_fields<8>(ff, f, origin, domain, st);
+  }
 }
 
 // ---------------------------------------------------------------------------- K5

@@ -131,7 +131,7 @@ struct HyperOp {
   }
 };
 
-// ---- diffusion, marching variant (TB200_DIFF_IMPL=march; experimental, not yet measured).
+// ---- diffusion, marching variant (TB200_DIFF_IMPL=march; 4.2 ms at 4096 x 4096 x 64, 0.62 of HBM).
 // One thread per column i, marching along j over a strip of LJ rows with the 2H+1 rows of its
 // own column in registers: every phi value is requested from L2/HBM once per strip (+ 2H halo
 // rows per strip, 6 % at LJ = 64) and once more per x-neighbour from L1 (the neighbouring lanes'
@@ -175,14 +175,128 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// TB200_DIFF_IMPL: "tile" (default, shared-memory tiles) or "march" (register windows along j)
+// ---- diffusion, two columns per lane (default whenever the layout allows it).
+// The one-column marching kernel above leaves the memory system idle: its only first-touch load
+// per row is consumed in the same iteration, so a warp has 256 bytes in flight and the launch
+// sits at 4.2 TB/s / 61 % warps active (profiles/r02_c4_ncu.md).  Here
+//   * a lane owns TWO adjacent columns (an aligned pair): every access is LDG.128 / STG.128;
+//   * the new row of the own pair (row j + H + 1) is requested one iteration before it enters
+//     the window, and its line is pulled DRAM -> L2 PF2 rows earlier (prefetch.global.L2), so
+//     the window load sees L2 latency and several rows per warp are in flight;
+//   * the x-neighbours are the pairs of the lanes to the left and right: two more LDG.128 on
+//     lines that entered L1 H + 1 rows ago;
+//   * a block is eight warps SIDE BY SIDE (512 columns = 4 KB contiguous per row), no shared
+//     memory, no barrier, no shuffle.
+// Every phi value leaves HBM once per strip (+ 2H halo rows per LJ-row strip).  Same point
+// formulas as the other kernels, hence the same bits.
+// Requirements (checked on the host, else the one-column kernels run): unit i-stride, 16-byte
+// aligned bases, even row / plane pitches of phi and out.
+constexpr int M2_WARPS = 8, M2_PF = 4;
+
+__device__ __forceinline__ double2 ldg2(const double *p) {
+  return __ldg(reinterpret_cast<const double2 *>(p));
+}
+
+template <int OP, int LJ>
+__global__ void __launch_bounds__(32 * M2_WARPS, 4)
+    march2_kernel(View phi, View gam, View out, CDiv dx, CDiv dy, int overwrite, int i0, int j0,
+                  int k0, int di, int dj, int dk) {
+  constexpr int H = Halo<OP>::value;
+  static_assert(OP == 2 || OP == 4, "diffusion only");
+  const int ib = i0 & ~1;  // pairs start at even columns
+  const int c0 = ib + 2 * (blockIdx.x * (32 * M2_WARPS) + threadIdx.x);
+  if (c0 >= i0 + di) return;  // no shuffles and no barriers below
+  const bool m0 = c0 >= i0, m1 = c0 + 1 < i0 + di;
+  const int js = j0 + blockIdx.y * LJ, je = min(js + LJ, j0 + dj);
+  const long long s1 = phi.s1;
+  const int pmax = (int)((s1 - 2) & ~1LL);         // last aligned pair inside a row
+  const int cl = max(c0 - 2, 0), cr = min(c0 + 2, pmax);  // neighbour pairs (clamped: only
+                                                          // masked points see clamped values)
+  const int jlast = phi.n1 - 1;
+  for (int k = k0 + blockIdx.z; k < k0 + dk; k += gridDim.z) {
+    const double *pc = phi.p + (c0 + k * phi.s2);  // row 0 of the own pair
+    const double *pg = gam.p + (c0 * gam.s0 + js * gam.s1 + k * gam.s2);
+    double *po = out.p + (c0 + js * out.s1 + k * out.s2);
+    double2 w[2 * H + 1];  // rows j-H .. j+H of the own pair
+#pragma unroll
+    for (int m = 0; m < 2 * H; ++m) w[m + 1] = ldg2(pc + (js + m - H) * s1);
+    double2 nxt = ldg2(pc + min(js + H, jlast) * s1);
+    for (int j = js; j < je; ++j) {
+#pragma unroll
+      for (int m = 0; m < 2 * H; ++m) w[m] = w[m + 1];
+      w[2 * H] = nxt;
+      nxt = ldg2(pc + min(j + 1 + H, jlast) * s1);
+      if (j + H + M2_PF < je + H)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + (j + H + M2_PF) * s1));
+      const double *pr = phi.p + (j * s1 + k * phi.s2);
+      const double2 l = ldg2(pr + cl), r = ldg2(pr + cr);
+      const double g0 = __ldg(pg), g1 = __ldg(pg + gam.s0);
+      double r0, r1;
+      if (OP == 2) {
+        r0 = lap2(g0, w[H].x, l.y, w[H].y, w[H - 1].x, w[H + 1].x, dx, dy);
+        r1 = lap2(g1, w[H].y, w[H].x, r.x, w[H - 1].y, w[H + 1].y, dx, dy);
+      } else {
+        r0 = lap4(g0, w[H].x, l.x, l.y, w[H].y, r.x, w[0].x, w[H - 1].x, w[H + 1].x, w[2 * H].x, dx, dy);
+        r1 = lap4(g1, w[H].y, l.y, w[H].x, r.x, r.y, w[0].y, w[H - 1].y, w[H + 1].y, w[2 * H].y, dx, dy);
+      }
+      if (m0 && m1) {
+        if (!overwrite) {  // generics.py:L38-L40
+          const double2 o = *reinterpret_cast<const double2 *>(po);
+          r0 = o.x + r0;
+          r1 = o.y + r1;
+        }
+        *reinterpret_cast<double2 *>(po) = make_double2(r0, r1);
+      } else if (m0) {
+        if (!overwrite) r0 = po[0] + r0;
+        po[0] = r0;
+      } else if (m1) {
+        if (!overwrite) r1 = po[1] + r1;
+        po[1] = r1;
+      }
+      pg += gam.s1;
+      po += out.s1;
+    }
+  }
+}
+
+bool march2_ok(const View &phi, const View &out) {
+  const View *vs[] = {&phi, &out};
+  for (const View *v : vs)
+    if (v->s0 != 1 || (v->s1 & 1) != 0 || (v->s2 & 1) != 0 || (reinterpret_cast<uintptr_t>(v->p) & 15) != 0 ||
+        v->s1 < 4)
+      return false;
+  return true;
+}
+
+// TB200_DIFF_IMPL: "march2" (default: two columns per lane), "march" (one column per lane,
+// register windows along j) or "tile" (shared-memory tiles)
 int diff_impl() {
   static int impl = -1;
   if (impl < 0) {
     const char *e = getenv("TB200_DIFF_IMPL");
-    impl = (e != nullptr && strcmp(e, "march") == 0) ? 1 : 0;
+    impl = e == nullptr ? 2 : strcmp(e, "march") == 0 ? 1 : strcmp(e, "tile") == 0 ? 0 : 2;
   }
   return impl;
+}
+
+template <int OP>
+int launch_march2(const char *what, View phi, View gam, View out, const CDiv &cdx, const CDiv &cdy,
+                  int overwrite, const int32_t o[3], const int32_t d[3], cudaStream_t st) {
+  const int gz = d[2] > 65535 ? 65535 : d[2];
+  const int cols = 2 * 32 * M2_WARPS;                       // columns per block
+  const int span = o[0] + d[0] - (o[0] & ~1);               // columns from the first even one
+  const int gx = (span + cols - 1) / cols;
+  const long long blocks64 = (long long)gx * ((d[1] + 63) / 64) * gz;
+  if (blocks64 >= 148 * 4) {  // enough 64-row strips to fill the machine
+    dim3 grid(gx, (d[1] + 63) / 64, gz);
+    march2_kernel<OP, 64><<<grid, 32 * M2_WARPS, 0, st>>>(phi, gam, out, cdx, cdy, overwrite, o[0], o[1],
+                                                          o[2], d[0], d[1], d[2]);
+  } else {
+    dim3 grid(gx, (d[1] + 7) / 8, gz);
+    march2_kernel<OP, 8><<<grid, 32 * M2_WARPS, 0, st>>>(phi, gam, out, cdx, cdy, overwrite, o[0], o[1],
+                                                         o[2], d[0], d[1], d[2]);
+  }
+  return check_launch(what);
 }
 
 template <int OP>
@@ -216,7 +330,9 @@ int launch_cross(const char *what, View phi, View gam, View out, double dx, doub
   const CDiv cdx = make_cdiv(OP == 4 ? 12.0 * dx * dx : (OP == 2 ? dx * dx : 1.0));
   const CDiv cdy = make_cdiv(OP == 4 ? 12.0 * dy * dy : (OP == 2 ? dy * dy : 1.0));
   if constexpr (OP == 2 || OP == 4) {
-    if (!rim && diff_impl() == 1) return launch_march<OP>(what, phi, gam, out, cdx, cdy, overwrite, o, d, st);
+    if (!rim && diff_impl() == 2 && march2_ok(phi, out))
+      return launch_march2<OP>(what, phi, gam, out, cdx, cdy, overwrite, o, d, st);
+    if (!rim && diff_impl() >= 1) return launch_march<OP>(what, phi, gam, out, cdx, cdy, overwrite, o, d, st);
   }
   cross_kernel<OP><<<grid, block, 0, st>>>(phi, gam, out, cdx, cdy, overwrite, rim, o[0], o[1],
                                            o[2], d[0], d[1], d[2], ri, rj);

@@ -145,7 +145,11 @@ __global__ void __launch_bounds__(128) stage_s_kernel(const StageArgs a) {
 // Arithmetic and results are bit-identical to kernel S.
 constexpr int A_COLS = 31;
 
-template <int SCHEME, int LJ>
+// DERIVE: the advecting velocities are re-diagnosed from s_int, su_int, sv_int (velocity_x /
+// velocity_y, dwarfs/diagnostics.py:L219-L272) instead of read from u_int / v_int: the previous
+// stage then need not write them (tb200_isentropic_stage.derive_uv_in).  Same traffic for this
+// kernel (su_int, sv_int instead of u, v), two IEEE divisions more per point.
+template <int SCHEME, int LJ, bool DERIVE>
 __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
   using F = Flux<SCHEME>;
   constexpr int E = F::extent;
@@ -176,16 +180,25 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
   unsigned o_cc = plane + (unsigned)j0 * row + (unsigned)cc * 8u;
   unsigned o_cm = plane + (unsigned)j0 * row + (unsigned)cm * 8u;
   unsigned o_g = (unsigned)j0 * grow + (unsigned)cm * 8u;
-  double fy = F::eval_v(F::prep(ldo(a.v_int.p, o_cc), a.fc), ws);
+  // v at the y-face j is (sv[j-1] + sv[j]) / (s[j-1] + s[j]); sv_lo carries sv_int of the row below
+  double sv_lo = 0.0;
+  double fy;
+  if (DERIVE) {
+    sv_lo = ldo(a.sv_int.p, o_cc);
+    const double sv_m = ldo(a.sv_int.p, plane + (unsigned)max(j0 - 1, 0) * row + (unsigned)cc * 8u);
+    fy = F::eval_v(F::prep((sv_m + sv_lo) / (ws[E - 1] + ws[E]), a.fc), ws);
+  } else {
+    fy = F::eval_v(F::prep(ldo(a.v_int.p, o_cc), a.fc), ws);
+  }
 
   struct Row {
-    double s_w, v_n, u_c, s_now, gam;
+    double s_w, v_n, u_c, s_now, gam;  // DERIVE: v_n = sv_int at row r+1, u_c = su_int at row r
   };
   auto load_row = [&](unsigned occ, unsigned ocm, unsigned og) {
     Row L;
     L.s_w = ldo(a.s_int.p, occ + E * row);
-    L.v_n = ldo(a.v_int.p, occ + row);
-    L.u_c = ldo(a.u_int.p, occ);
+    L.v_n = ldo(DERIVE ? a.sv_int.p : a.v_int.p, occ + row);
+    L.u_c = ldo(DERIVE ? a.su_int.p : a.u_int.p, occ);
     L.s_now = ldo(a.s_now.p, ocm);
     L.gam = ldo(a.gamma.p, og);
     return L;
@@ -196,21 +209,37 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     nxt = load_row(o_cc + row, o_cm + row, o_g + grow);
     if (r + 4 < jend) {  // DRAM -> L2 a few rows ahead
       prefetch_l2(a.s_int.p, o_cc + (E + 4) * row);
-      prefetch_l2(a.v_int.p, o_cc + 5 * row);
-      prefetch_l2(a.u_int.p, o_cc + 4 * row);
+      prefetch_l2(DERIVE ? a.sv_int.p : a.v_int.p, o_cc + 5 * row);
+      prefetch_l2(DERIVE ? a.su_int.p : a.u_int.p, o_cc + 4 * row);
       prefetch_l2(a.s_now.p, o_cm + 4 * row);
     }
 #pragma unroll
     for (int m = 0; m < NW - 1; ++m) ws[m] = ws[m + 1];
-    ws[NW - 1] = cur.s_w;
-    const double fy_p = F::eval_v(F::prep(cur.v_n, a.fc), ws);
+    ws[NW - 1] = cur.s_w;  // ws[m] = s_int at row r - E + 1 + m
+    double vq;
+    if (DERIVE) {
+      vq = F::prep((sv_lo + cur.v_n) / (ws[E - 1] + ws[E]), a.fc);
+      sv_lo = cur.v_n;
+    } else {
+      vq = F::prep(cur.v_n, a.fc);
+    }
+    const double fy_p = F::eval_v(vq, ws);
     double xs[NW];
     {
       const double *ps = ptr_at(a.s_int.p, o_cc);
 #pragma unroll
       for (int m = 0; m < NW; ++m) xs[m] = m == E ? ws[E - 1] : __ldg(ps + (m - E));
     }
-    const double fx = F::eval_v(F::prep(cur.u_c, a.fc), xs);
+    double uq;
+    if (DERIVE) {  // u at the left face of the column: (su[c-1] + su[c]) / (s[c-1] + s[c])
+      // (the left column from L1 like the s_int neighbours: a shuffle would hand over the
+      // CLAMPED column of a lane next to the domain edge)
+      const double su_l = ldo(a.su_int.p, o_cc - 8u);
+      uq = F::prep((su_l + cur.u_c) / (xs[E - 1] + xs[E]), a.fc);
+    } else {
+      uq = F::prep(cur.u_c, a.fc);
+    }
+    const double fx = F::eval_v(uq, xs);
     const double fx_p = __shfl_down_sync(0xffffffffu, fx, 1);
 
     const bool interior = col_int && r >= nb && r < ny - nb;
@@ -927,11 +956,15 @@ constexpr int RW2 = 72;
 constexpr int SU_RING2 = 8, MT_RING2 = 4;
 constexpr int REF_RING2 = 2;  // rows r (in use) and r+1 (in flight) of s_ref, su_ref, sv_ref
 constexpr int WARP_DOUBLES2 = (2 * SU_RING2 + 2 * MT_RING2) * RW2 + 3 * REF_RING2 * 64;
-constexpr int MV2_WX = 2, MV2_WY = 2;
+constexpr int MV2_BLOCK_DEFAULT = 1, MV2_DEF_WX = 3, MV2_DEF_WY = 1;  // TB200_MV_BLOCK: 0 = 2x2, 1 = 3x1, 2 = 6x1
 constexpr int MV2_PF = 2;  // rows of DRAM -> L2 prefetch ahead of the loads (measured: 0 -> 2.00 ms, 2 -> 1.79, 3 -> 1.82, 6 -> 2.22)
 
 __device__ __forceinline__ double2 ldo2(const double *base, unsigned off) {
   return __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + off));
+}
+// predicated: lanes that do not need the value issue no request (no sector is fetched for them)
+__device__ __forceinline__ double2 ldo2_if(bool p, const double *base, unsigned off) {
+  return p ? ldo2(base, off) : make_double2(0.0, 0.0);
 }
 __device__ __forceinline__ void sto2(double *base, unsigned off, double2 v) {
   *reinterpret_cast<double2 *>(reinterpret_cast<char *>(base) + off) = v;
@@ -950,18 +983,32 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 struct OwnLoads2 {
-  double2 v_n, u_c, s_pre, s_now, su_now, sv_now;
+  double2 v_n, u_c;  // v_int at row r+1, u_int at row r (not DERIVE)
+  double2 s_i2;      // s_int at row r+2 (DERIVE)
+  double2 s_pre, s_now, su_now, sv_now;
 };
 
-template <int SCHEME, int LJ>
-__global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(const StageArgs a) {
+// Template flags (tb200_isentropic_stage.derive_uv_in / .skip_uv_out):
+//   DERIVE  the advecting velocities are re-diagnosed from s_int and the su_int / sv_int rows
+//           already in the rings (velocity_x / velocity_y, dwarfs/diagnostics.py:L219-L272)
+//           instead of read from u_int / v_int: one stream (s_int) instead of two;
+//   UVOUT   u_new, v_new are diagnosed and written.  Without it (an intermediate stage) lane 0
+//           has nothing to recompute, the warm-up row disappears, and -- what matters most --
+//           only the 30 owner lanes touch the streams without reuse, i.e. exactly the 15
+//           32-byte sectors of the warp's 60 columns: the two-column shift of lane 0 used to cost
+//           two more sectors per row and stream (17 / 15), because the x-neighbour warp runs far
+//           enough away in time for the shared sectors to have left L2 (profiles/README.md,
+//           round 2).  For the same reason the halo pairs nobody reads are not fetched any more.
+// WX x WY warps per block: WX side by side, WY strips of LJ rows.
+template <int SCHEME, int LJ, int WX, int WY, bool DERIVE, bool UVOUT>
+__global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_kernel(const StageArgs a) {
   using F = Flux<SCHEME>;
   constexpr int E = F::extent;
   constexpr int NW = 2 * E;
   extern __shared__ __align__(16) double ring_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int xw = (blockIdx.x + a.bx0) * MV2_WX + warp % MV2_WX;
-  const int j0 = ((blockIdx.y + a.by0) * MV2_WY + warp / MV2_WX) * LJ;
+  const int xw = (blockIdx.x + a.bx0) * WX + warp % WX;
+  const int j0 = ((blockIdx.y + a.by0) * WY + warp / WX) * LJ;
   if (xw * MV2_COLS >= a.nx || j0 >= a.ny) return;  // warp-uniform (no block-wide barrier in this kernel)
   double *r_su = ring_smem + warp * WARP_DOUBLES2;
   const int c0 = xw * MV2_COLS + 2 * lane - 2;  // first of the lane's two columns (even)
@@ -974,9 +1021,16 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
   const bool col_int0 = c0 >= nb && c0 < nx - nb, col_int1 = c0 + 1 >= nb && c0 + 1 < nx - nb;
   const int pmax = (nx - 1) & ~1;        // last pair start inside the row
   const int cm = min(max(c0, 0), pmax);  // own pair, clamped into the row
-  // halo pairs of lanes 0, 1 (ring columns 0-1, 2-3) and 2 (ring columns 68-69)
-  const bool halo_lane = lane < 3;
-  const int th = lane < 2 ? 2 * lane : 68;
+  // who reads the streams without reuse: the owners, plus lane 0 when it recomputes the two
+  // columns to the left for u_new; u_int also feeds lane 31's left face
+  const bool ld_own = own_lane || (UVOUT && lane == 0);
+  const bool ld_u = lane > 0 || UVOUT;
+  // halo pairs of the su / sv rings: ring columns 2-3 (lane 1) and 68-69 (lane 2); of the mtg
+  // rings: ring columns 2-3, only for lane 0's recomputation.  Ring columns 0-1 and 70-71 feed
+  // nothing that is used (lane 0's left face); they are zeroed once.
+  const bool halo_su = lane == 1 || lane == 2;
+  const bool halo_mt = UVOUT && lane == 1;
+  const int th = lane == 1 ? 2 : 68;
   const int ch = min(max(xw * MV2_COLS - 6 + th, 0), pmax);
   const int t = 2 * lane + 4;  // ring column of c0
 
@@ -985,8 +1039,11 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
   const unsigned grow = (unsigned)a.gamma.s1 * 8u;
   const double r_damp = a.damp ? a.rmat.ld(0, 0, k) : 0.0;
   const double one_m_eps = 1.0 - a.eps;
-  const int r0 = j0 > 0 ? j0 - 1 : 0;  // first row computed (warm-up row unless j0 == 0)
+  // first row computed: the warm-up row j0-1 seeds the v_new diagnosis
+  const int r0 = (UVOUT && j0 > 0) ? j0 - 1 : j0;
   const double2 zero2 = make_double2(0.0, 0.0);
+  // s is updated in place (scratch_s is s_new): stored only where relaxation / damping change it
+  const bool s_inplace = !UVOUT && a.spre.p == a.s_new.p;
 
   // shared-memory byte addresses of this lane's own / halo entry of ring row 0
   constexpr unsigned SLOT = RW2 * 8u;                       // bytes per ring row
@@ -1000,12 +1057,22 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
   const unsigned sm_ref = (unsigned)__cvta_generic_to_shared(w_ref);
   const unsigned col_o = (unsigned)cm * 8u, col_h = (unsigned)ch * 8u;
 
+  if (lane < 2 * SU_RING2 + 2 * MT_RING2) {  // ring columns nobody fetches (ring row = lane)
+    *reinterpret_cast<double2 *>(r_su + lane * RW2) = zero2;
+    *reinterpret_cast<double2 *>(r_su + lane * RW2 + 70) = zero2;
+    if (lane >= 2 * SU_RING2) {
+      *reinterpret_cast<double2 *>(r_su + lane * RW2 + 68) = zero2;
+      if (!UVOUT) *reinterpret_cast<double2 *>(r_su + lane * RW2 + 2) = zero2;
+    }
+  }
+  __syncwarp();
+
   // grid row rr of su_int / sv_int -> ring slot q_su & 7; of mtg_now / mtg_new -> slot q_mt & 3
   auto fetch_su = [&](int q_su, int rr) {
     const unsigned o = plane + (unsigned)max(rr, 0) * row, d = (unsigned)(q_su & (SU_RING2 - 1)) * SLOT;
     cp_async16(sm_own + d, a.su_int.p, o + col_o);
     cp_async16(sm_own + d + SV_OFF, a.sv_int.p, o + col_o);
-    if (halo_lane) {
+    if (halo_su) {
       cp_async16(sm_halo + d, a.su_int.p, o + col_h);
       cp_async16(sm_halo + d + SV_OFF, a.sv_int.p, o + col_h);
     }
@@ -1014,7 +1081,7 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
     const unsigned o = plane + (unsigned)max(rr, 0) * row, d = (unsigned)(q_mt & (MT_RING2 - 1)) * SLOT;
     cp_async16(sm_own + d + MN_OFF, a.mtg_now.p, o + col_o);
     cp_async16(sm_own + d + MW_OFF, a.mtg.p, o + col_o);
-    if (halo_lane) {
+    if (halo_mt) {
       cp_async16(sm_halo + d + MN_OFF, a.mtg_now.p, o + col_h);
       cp_async16(sm_halo + d + MW_OFF, a.mtg.p, o + col_h);
     }
@@ -1033,19 +1100,25 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
 
   auto load_own = [&](unsigned oc) {
     OwnLoads2 L;
-    L.v_n = ldo2(a.v_int.p, oc + row);
-    L.u_c = ldo2(a.u_int.p, oc);
-    L.s_pre = ldo2(a.spre.p, oc);
-    L.s_now = ldo2(a.s_now.p, oc);
-    L.su_now = ldo2(a.su_now.p, oc);
-    L.sv_now = ldo2(a.sv_now.p, oc);
+    if (DERIVE) {
+      L.v_n = L.u_c = zero2;
+      L.s_i2 = ldo2(a.s_int.p, oc + 2 * row);  // every lane: lane l + 1 takes s_int[c0 - 1] from lane l
+    } else {
+      L.v_n = ldo2_if(ld_own, a.v_int.p, oc + row);
+      L.u_c = ldo2_if(ld_u, a.u_int.p, oc);
+      L.s_i2 = zero2;
+    }
+    L.s_pre = ldo2_if(ld_own, a.spre.p, oc);
+    L.s_now = ldo2_if(ld_own, a.s_now.p, oc);
+    L.su_now = ldo2_if(ld_own, a.su_now.p, oc);
+    L.sv_now = ldo2_if(ld_own, a.sv_now.p, oc);
     return L;
   };
   // The reference fields of the relaxation band / damping layer are requested one row ahead of
   // their use like everything else (cp.async into a two-row ring; the relaxation coefficients
   // run two rows ahead to decide where).  Row rr -> slot rr & 1.
   auto fetch_ref = [&](int rr, unsigned oc, double2 gam) {
-    if (gam.x != 0.0 || gam.y != 0.0 || r_damp != 0.0) {
+    if (ld_own && (gam.x != 0.0 || gam.y != 0.0 || r_damp != 0.0)) {
       const unsigned d = sm_ref + (unsigned)(rr & 1) * 512u;
       cp_async16(d, a.s_ref.p, oc);
       cp_async16(d + REF_RING2 * 512u, a.su_ref.p, oc);
@@ -1056,7 +1129,16 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
     return ldo2(a.gamma.p, (unsigned)min(rr, ny - 1) * grow + col_o);
   };
   double2 gam_a = load_gamma(r0), gam_b = load_gamma(r0 + 1);  // rows r and r+1
-  const double2 v_first = ldo2(a.v_int.p, o_c);
+  // DERIVE: s_int rows r (si_a) and r+1 (si_b) ride along in registers; the prologue also needs
+  // row r0-1 for the y-face r0
+  double2 si_a = zero2, si_b = zero2, v_first = zero2;
+  if (DERIVE) {
+    v_first = ldo2(a.s_int.p, plane + (unsigned)max(r0 - 1, 0) * row + col_o);  // s_int at row r0-1
+    si_a = ldo2(a.s_int.p, o_c);
+    si_b = ldo2(a.s_int.p, o_c + row);
+  } else {
+    v_first = ldo2_if(ld_own, a.v_int.p, o_c);
+  }
   OwnLoads2 nxt = load_own(o_c);
   fetch_su(NW, r0 + E);
   fetch_mt(2, r0 + 1);
@@ -1073,22 +1155,33 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
       const double2 vu = lds2(r_su + m * RW2 + t), vv = lds2(r_su + (SU_RING2 + m) * RW2 + t);
       ysu0[m] = vu.x; ysu1[m] = vu.y; ysv0[m] = vv.x; ysv1[m] = vv.y;
     }
-    const double vq0 = F::prep(v_first.x, a.fc), vq1 = F::prep(v_first.y, a.fc);
+    double vq0, vq1;
+    if (DERIVE) {  // window entry m holds row r0 - E + m: rows r0-1, r0 are entries E-1, E
+      vq0 = F::prep((ysv0[E - 1] + ysv0[E]) / (v_first.x + si_a.x), a.fc);
+      vq1 = F::prep((ysv1[E - 1] + ysv1[E]) / (v_first.y + si_a.y), a.fc);
+    } else {
+      vq0 = F::prep(v_first.x, a.fc);
+      vq1 = F::prep(v_first.y, a.fc);
+    }
     fy_su0 = F::eval_v(vq0, ysu0); fy_su1 = F::eval_v(vq1, ysu1);
     fy_sv0 = F::eval_v(vq0, ysv0); fy_sv1 = F::eval_v(vq1, ysv1);
   }
   double sv_prev0 = 0.0, sv_prev1 = 0.0, s_prev0 = 0.0, s_prev1 = 0.0;
 
-  // DRAM -> L2 MV2_PF rows ahead with two instructions per row for all ten streams: lane
-  // 10 l + f takes the 128-byte lines 2 l and 2 l + 1 of stream f (the warp's 70 columns of a
-  // row span at most six lines)
+  // DRAM -> L2 MV2_PF rows ahead with two instructions per row for all streams: lane
+  // 10 l + f takes the 128-byte lines 2 l and 2 l + 1 of stream f, counted from the line that
+  // holds the warp's first owned column, as far as they overlap the owned columns (the halo
+  // sectors beyond are left to the loads: prefetching whole neighbour lines is what the
+  // neighbour warp, far away in time, would do again)
   const double *pf_base;
   unsigned pf_off;
+  bool pf_a, pf_b;
   {
     const int f = lane % 10, line = lane / 10;
-    const double *bases[10] = {a.su_int.p, a.sv_int.p, a.v_int.p, a.u_int.p,  a.spre.p,
+    const double *bases[10] = {a.su_int.p, a.sv_int.p, DERIVE ? a.s_int.p : a.v_int.p,
+                               DERIVE ? nullptr : a.u_int.p, a.spre.p,
                                a.s_now.p,  a.su_now.p, a.sv_now.p, a.mtg_now.p, a.mtg.p};
-    const int ahead[10] = {E, E, 1, 0, 0, 0, 0, 0, 1, 1};
+    const int ahead[10] = {E, E, DERIVE ? 2 : 1, 0, 0, 0, 0, 0, 1, 1};
     pf_base = bases[0];
     int ah = 0;
 #pragma unroll
@@ -1097,8 +1190,12 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
         pf_base = bases[n];
         ah = ahead[n];
       }
-    const int cfirst = max(xw * MV2_COLS - 6, 0);
-    pf_off = plane + (unsigned)(r0 + MV2_PF + ah) * row + (unsigned)((cfirst * 8 & ~127) + 256 * line);
+    const int b_lo = xw * MV2_COLS * 8, b_hi = min(b_lo + MV2_COLS * 8, (int)row);
+    const int l0 = (b_lo & ~127) + 256 * line;
+    pf_a = lane < 30 && pf_base != nullptr && l0 < b_hi;
+    pf_b = lane < 30 && pf_base != nullptr && l0 + 128 < b_hi;
+    if (pf_base == nullptr) pf_base = bases[0];
+    pf_off = plane + (unsigned)(r0 + MV2_PF + ah) * row + (unsigned)l0;
   }
 
   const double *w_su = r_su + t;  // this lane's entry of su ring row 0
@@ -1115,8 +1212,8 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
     nxt = load_own(o_c + row);
     const double2 gam_c = load_gamma(r + 2);
     if (r + MV2_PF < jend) {
-      prefetch_l2(pf_base, pf_off);
-      if (lane < 30) prefetch_l2(pf_base, pf_off + 128u);
+      if (pf_a) prefetch_l2(pf_base, pf_off);
+      if (pf_b) prefetch_l2(pf_base, pf_off + 128u);
     }
     pf_off += row;
 
@@ -1130,13 +1227,19 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
       const double2 vu = lds2(pr), vv = lds2(pr + SU_RING2 * RW2);
       ysu0[m] = vu.x; ysu1[m] = vu.y; ysv0[m] = vv.x; ysv1[m] = vv.y;
     }
-    const double vq0 = F::prep(cur.v_n.x, a.fc), vq1 = F::prep(cur.v_n.y, a.fc);
+    double vq0, vq1;
+    if (DERIVE) {  // v at the y-face r+1: window entries E-1 (row r) and E (row r+1)
+      vq0 = F::prep((ysv0[E - 1] + ysv0[E]) / (si_a.x + si_b.x), a.fc);
+      vq1 = F::prep((ysv1[E - 1] + ysv1[E]) / (si_a.y + si_b.y), a.fc);
+    } else {
+      vq0 = F::prep(cur.v_n.x, a.fc);
+      vq1 = F::prep(cur.v_n.y, a.fc);
+    }
     const double fy_su0_p = F::eval_v(vq0, ysu0), fy_su1_p = F::eval_v(vq1, ysu1);
     const double fy_sv0_p = F::eval_v(vq0, ysv0), fy_sv1_p = F::eval_v(vq1, ysv1);
 
     // ---- x-faces at row r: left face of c0, face between c0 and c1; the right face of c1 is
     // the left face of the next lane's c0.  lsu[n] = su_int[c0 - E + n]
-    const double uq0 = F::prep(cur.u_c.x, a.fc), uq1 = F::prep(cur.u_c.y, a.fc);
     double lsu[NW + 1], lsv[NW + 1];
     {
       const double *psu = row_r, *psv = row_r + SU_RING2 * RW2;
@@ -1156,6 +1259,15 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
       }
       lsu[E] = ysu0[E - 1]; lsu[E + 1] = ysu1[E - 1];
       lsv[E] = ysv0[E - 1]; lsv[E + 1] = ysv1[E - 1];
+    }
+    double uq0, uq1;
+    if (DERIVE) {  // u at the left face of c0 and at the face between c0 and c1
+      const double si_l = __shfl_up_sync(0xffffffffu, si_a.y, 1);  // s_int[c0 - 1] (lane 0: unused face)
+      uq0 = F::prep((lsu[E - 1] + lsu[E]) / (si_l + si_a.x), a.fc);
+      uq1 = F::prep((lsu[E] + lsu[E + 1]) / (si_a.x + si_a.y), a.fc);
+    } else {
+      uq0 = F::prep(cur.u_c.x, a.fc);
+      uq1 = F::prep(cur.u_c.y, a.fc);
     }
     const double fx_su0 = F::eval_v(uq0, lsu), fx_su1 = F::eval_v(uq1, lsu + 1);
     const double fx_sv0 = F::eval_v(uq0, lsv), fx_sv1 = F::eval_v(uq1, lsv + 1);
@@ -1204,14 +1316,15 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
       if (!int1) { su1 = 0.0; sv1 = 0.0; }
     }
     const double gam0 = gam_a.x, gam1 = gam_a.y;
+    const bool touched = gam0 != 0.0 || gam1 != 0.0 || r_damp != 0.0;
     double2 s_ref = zero2, su_ref = zero2, sv_ref = zero2;
-    if (gam0 != 0.0 || gam1 != 0.0 || r_damp != 0.0) {
+    if (touched && ld_own) {
       const double *pr = w_ref + (r & 1) * 64;
       s_ref = lds2(pr);
       su_ref = lds2(pr + REF_RING2 * 64);
       sv_ref = lds2(pr + 2 * REF_RING2 * 64);
     }
-    if ((!int0 && gam0 != 1.0) || (!int1 && gam1 != 1.0)) {  // not reached with a Relaxed boundary
+    if (ld_own && ((!int0 && gam0 != 1.0) || (!int1 && gam1 != 1.0))) {  // not reached with a Relaxed boundary
       const double2 ou = ldo2(a.su_new.p, o_c), ov = ldo2(a.sv_new.p, o_c);
       if (!int0 && gam0 != 1.0) { su0 = ou.x; sv0 = ov.x; }
       if (!int1 && gam1 != 1.0) { su1 = ou.y; sv1 = ov.y; }
@@ -1235,44 +1348,61 @@ __global__ void __launch_bounds__(32 * MV2_WX * MV2_WY, 3) stage_mv2_kernel(cons
       sv1 = damp_point(cur.sv_now.y, sv1, sv_ref.y, r_damp, a.dt_full);
     }
 
-    // ---- velocity diagnosis (dwarfs/diagnostics.py:L219-L272) and stores
-    const double su_l = __shfl_up_sync(0xffffffffu, su1, 1);
-    const double s_l = __shfl_up_sync(0xffffffffu, s1, 1);
-    if (out0 && r >= j0) {
-      const int c1 = c0 + 1;
-      const double u0 = c0 == 0 ? ldo(a.u_ref.p, o_c) : (su_l + su0) / (s_l + s0);
-      double v0, v1;
-      if (r == 0) {
-        const double2 vr = ldo2(a.v_ref.p, o_c);
-        v0 = vr.x; v1 = vr.y;
-      } else {
-        v0 = (sv_prev0 + sv0) / (s_prev0 + s0);
-        v1 = (sv_prev1 + sv1) / (s_prev1 + s1);
+    if (UVOUT) {
+      // ---- velocity diagnosis (dwarfs/diagnostics.py:L219-L272) and stores
+      const double su_l = __shfl_up_sync(0xffffffffu, su1, 1);
+      const double s_l = __shfl_up_sync(0xffffffffu, s1, 1);
+      if (out0 && r >= j0) {
+        const int c1 = c0 + 1;
+        const double u0 = c0 == 0 ? ldo(a.u_ref.p, o_c) : (su_l + su0) / (s_l + s0);
+        double v0, v1;
+        if (r == 0) {
+          const double2 vr = ldo2(a.v_ref.p, o_c);
+          v0 = vr.x; v1 = vr.y;
+        } else {
+          v0 = (sv_prev0 + sv0) / (s_prev0 + s0);
+          v1 = (sv_prev1 + sv1) / (s_prev1 + s1);
+        }
+        if (out1) {
+          const double u1 = (su0 + su1) / (s0 + s1);
+          sto2(a.s_new.p, o_c, make_double2(s0, s1));
+          sto2(a.su_new.p, o_c, make_double2(su0, su1));
+          sto2(a.sv_new.p, o_c, make_double2(sv0, sv1));
+          sto2(a.u_new.p, o_c, make_double2(u0, u1));
+          sto2(a.v_new.p, o_c, make_double2(v0, v1));
+          if (c1 == nx - 1) sto(a.u_new.p, o_c + 16u, ldo(a.u_ref.p, o_c + 16u));  // relaxed.py:L161-L175
+          if (r == ny - 1) sto2(a.v_new.p, o_c + row, ldo2(a.v_ref.p, o_c + row));  // relaxed.py:L177-L191
+        } else {  // c0 is the last column of an odd-sized row
+          sto(a.s_new.p, o_c, s0);
+          sto(a.su_new.p, o_c, su0);
+          sto(a.sv_new.p, o_c, sv0);
+          sto(a.u_new.p, o_c, u0);
+          sto(a.v_new.p, o_c, v0);
+          sto(a.u_new.p, o_c + 8u, ldo(a.u_ref.p, o_c + 8u));
+          if (r == ny - 1) sto(a.v_new.p, o_c + row, ldo(a.v_ref.p, o_c + row));
+        }
       }
+      sv_prev0 = sv0; sv_prev1 = sv1;
+      s_prev0 = s0; s_prev1 = s1;
+    } else if (out0) {  // intermediate stage: s, su, sv only (r >= j0 always: no warm-up row)
+      const bool put_s = !s_inplace || touched;
       if (out1) {
-        const double u1 = (su0 + su1) / (s0 + s1);
-        sto2(a.s_new.p, o_c, make_double2(s0, s1));
+        if (put_s) sto2(a.s_new.p, o_c, make_double2(s0, s1));
         sto2(a.su_new.p, o_c, make_double2(su0, su1));
         sto2(a.sv_new.p, o_c, make_double2(sv0, sv1));
-        sto2(a.u_new.p, o_c, make_double2(u0, u1));
-        sto2(a.v_new.p, o_c, make_double2(v0, v1));
-        if (c1 == nx - 1) sto(a.u_new.p, o_c + 16u, ldo(a.u_ref.p, o_c + 16u));  // relaxed.py:L161-L175
-        if (r == ny - 1) sto2(a.v_new.p, o_c + row, ldo2(a.v_ref.p, o_c + row));  // relaxed.py:L177-L191
-      } else {  // c0 is the last column of an odd-sized row
-        sto(a.s_new.p, o_c, s0);
+      } else {
+        if (put_s) sto(a.s_new.p, o_c, s0);
         sto(a.su_new.p, o_c, su0);
         sto(a.sv_new.p, o_c, sv0);
-        sto(a.u_new.p, o_c, u0);
-        sto(a.v_new.p, o_c, v0);
-        sto(a.u_new.p, o_c + 8u, ldo(a.u_ref.p, o_c + 8u));
-        if (r == ny - 1) sto(a.v_new.p, o_c + row, ldo(a.v_ref.p, o_c + row));
       }
     }
-    sv_prev0 = sv0; sv_prev1 = sv1;
-    s_prev0 = s0; s_prev1 = s1;
     fy_su0 = fy_su0_p; fy_su1 = fy_su1_p;
     fy_sv0 = fy_sv0_p; fy_sv1 = fy_sv1_p;
     gam_a = gam_b; gam_b = gam_c;
+    if (DERIVE) {
+      si_a = si_b;
+      si_b = cur.s_i2;
+    }
     o_c += row;
   }
   cp_async_wait<0>();  // nothing may still be in flight into this block's shared memory
@@ -1287,6 +1417,20 @@ int mv_impl() {
     impl = e == nullptr ? 2 : strcmp(e, "window") == 0 ? 0 : strcmp(e, "ring") == 0 ? 1 : 2;
   }
   return impl;
+}
+
+// TB200_MV_BLOCK = 2x2 | 3x1 | 6x1: warps per block of the two-column kernel (side by side x
+// strips).  Warps of one block start together and stay close in time, so the halo sectors two
+// x-neighbours share are still in L2 when the second one asks; across blocks they are not.
+// The alternatives to the default are instantiated for the benchmark configuration only
+// (fifth-order fluxes, 64-row strips).
+int mv_block() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TB200_MV_BLOCK");
+    v = e == nullptr ? MV2_BLOCK_DEFAULT : strcmp(e, "2x2") == 0 ? 0 : strcmp(e, "3x1") == 0 ? 1 : strcmp(e, "6x1") == 0 ? 2 : MV2_BLOCK_DEFAULT;
+  }
+  return v;
 }
 
 // the two-column kernel moves 16-byte pairs: aligned bases, even pitches, one spare column
@@ -1304,10 +1448,47 @@ bool mv2_ok(const StageArgs &a) {
 struct MvGeom {
   int impl, wx, wy, cols;  // kernel, warps per block along x / along y, owned columns per warp
 };
-MvGeom mv_geom(const StageArgs &a) {
+template <int SCHEME, int LJ>
+constexpr bool mv2_has_blocks() {  // are the non-default block shapes instantiated?
+  return SCHEME == TB200_FLUX_FIFTH_ORDER_UPWIND && LJ == 64;
+}
+MvGeom mv_geom(const StageArgs &a, bool alt_blocks) {
   int impl = mv_impl();
   if (impl == 2 && !mv2_ok(a)) impl = 1;
-  return impl == 2 ? MvGeom{2, MV2_WX, MV2_WY, MV2_COLS} : MvGeom{impl, 4, 1, MV_COLS};
+  if (impl != 2) return MvGeom{impl, 4, 1, MV_COLS};
+  const int b = alt_blocks ? mv_block() : MV2_BLOCK_DEFAULT;
+  return b == 0 ? MvGeom{2, 2, 2, MV2_COLS} : b == 1 ? MvGeom{2, 3, 1, MV2_COLS} : MvGeom{2, 6, 1, MV2_COLS};
+}
+// is the default path (kernels A + B + two-column MV) in charge?  Only it honours derive_uv_in /
+// skip_uv_out; every other variant reads u_int / v_int and writes u_new / v_new like the
+// reference, which is consistent as long as ALL stages of a run use the same variant (the
+// selection depends on the process environment and on the storages' layout only).
+bool lazy_uv_path(const StageArgs &a) {
+  return s_impl() != 0 && a.nz <= 64 && stage_impl() == 0 && mv_impl() == 2 && mv2_ok(a);
+}
+
+template <int SCHEME, int LJ, int WX, int WY, bool DERIVE, bool UVOUT>
+int launch_mv2(const StageArgs &a, dim3 grid, cudaStream_t st) {
+  const size_t smem = (size_t)WX * WY * WARP_DOUBLES2 * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(stage_mv2_kernel<SCHEME, LJ, WX, WY, DERIVE, UVOUT>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("isentropic_stage_dry/MV2: %s", cudaGetErrorString(cudaGetLastError()));
+      return TB200_ERR_CUDA;
+    }
+    configured = true;
+  }
+  stage_mv2_kernel<SCHEME, LJ, WX, WY, DERIVE, UVOUT><<<grid, dim3(32 * WX * WY, 1, 1), smem, st>>>(a);
+  return check_launch("isentropic_stage_dry/MV(2 columns)");
+}
+template <int SCHEME, int LJ, int WX, int WY>
+int launch_mv2_flags(const StageArgs &a, dim3 grid, cudaStream_t st) {
+  if (a.derive_uv)
+    return a.skip_uv ? launch_mv2<SCHEME, LJ, WX, WY, true, false>(a, grid, st)
+                     : launch_mv2<SCHEME, LJ, WX, WY, true, true>(a, grid, st);
+  return a.skip_uv ? launch_mv2<SCHEME, LJ, WX, WY, false, false>(a, grid, st)
+                   : launch_mv2<SCHEME, LJ, WX, WY, false, true>(a, grid, st);
 }
 
 // The momentum kernel over a rectangle of its block grid.
@@ -1319,18 +1500,11 @@ int launch_mv_rect(StageArgs a, const MvGeom &g, int bx0, int bx1, int by0, int 
   dim3 block(32 * g.wx * g.wy, 1, 1);
   dim3 grid(bx1 - bx0, by1 - by0, a.nz);
   if (g.impl == 2) {
-    const size_t smem = (size_t)g.wx * g.wy * WARP_DOUBLES2 * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(stage_mv2_kernel<SCHEME, LJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem) != cudaSuccess) {
-        set_error("isentropic_stage_dry/MV2: %s", cudaGetErrorString(cudaGetLastError()));
-        return TB200_ERR_CUDA;
-      }
-      configured = true;
+    if constexpr (mv2_has_blocks<SCHEME, LJ>()) {
+      if (g.wx == 2) return launch_mv2_flags<SCHEME, LJ, 2, 2>(a, grid, st);
+      if (g.wx == 6) return launch_mv2_flags<SCHEME, LJ, 6, 1>(a, grid, st);
     }
-    stage_mv2_kernel<SCHEME, LJ><<<grid, block, smem, st>>>(a);
-    return check_launch("isentropic_stage_dry/MV(2 columns)");
+    return launch_mv2_flags<SCHEME, LJ, MV2_DEF_WX, MV2_DEF_WY>(a, grid, st);
   }
   if (g.impl == 1) {
     stage_mv_ring_kernel<SCHEME, LJ><<<grid, block, g.wx * WARP_DOUBLES * sizeof(double), st>>>(a);
@@ -1345,7 +1519,7 @@ int launch_mv_rect(StageArgs a, const MvGeom &g, int bx0, int bx1, int by0, int 
 // remaining strips); part 2: the interior rectangle.
 template <int SCHEME, int LJ>
 int launch_mv_part(const StageArgs &a, cudaStream_t st) {
-  const MvGeom g = mv_geom(a);
+  const MvGeom g = mv_geom(a, mv2_has_blocks<SCHEME, LJ>());
   const int cols = g.wx * g.cols, rows = g.wy * LJ;  // columns / rows per block
   const int gx = (a.nx + cols - 1) / cols, gy = (a.ny + rows - 1) / rows;
   if (a.part == 0) return launch_mv_rect<SCHEME, LJ>(a, g, 0, gx, 0, gy, st);
@@ -1406,13 +1580,16 @@ int launch_a(const StageArgs &a, cudaStream_t st) {
   const int chunks = (a.nx + A_COLS - 1) / A_COLS;
   dim3 block(32 * WARPS, 1, 1);
   dim3 grid((chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
-  stage_a_kernel<SCHEME, LJ><<<grid, block, 0, st>>>(a);
+  if (a.derive_uv)
+    stage_a_kernel<SCHEME, LJ, true><<<grid, block, 0, st>>>(a);
+  else
+    stage_a_kernel<SCHEME, LJ, false><<<grid, block, 0, st>>>(a);
   return check_launch("isentropic_stage_dry/A");
 }
 
 template <int SCHEME>
 int launch_mv(const StageArgs &a, cudaStream_t st) {
-  const MvGeom g = mv_geom(a);
+  const MvGeom g = mv_geom(a, false);
   // the overlap parts of a decomposed run are laid out in blocks of 64-row strips; the earlier
   // momentum kernels (TB200_MV_IMPL=window|ring) are kept as they were measured, at 64 rows
   const int lj = (a.part != 0 || g.impl != 2) ? 64 : pick_lj((a.nx + g.cols - 1) / g.cols, a.ny, a.nz);
@@ -1536,6 +1713,8 @@ extern "C" int tb200_isentropic_stage_dry(
   a.exn = view(scratch_exn); a.mtg = view(scratch_mtg); a.spre = view(scratch_s);
   a.nx = cfg->nx; a.ny = cfg->ny; a.nz = cfg->nz; a.nb = cfg->nb; a.damp = cfg->damp;
   a.part = cfg->part;
+  a.derive_uv = cfg->derive_uv_in != 0;
+  a.skip_uv = cfg->skip_uv_out != 0;
   for (int n = 0; n < 4; ++n) a.rim[n] = cfg->rim[n];
   TB200_REQUIRE(a.part >= 0 && a.part <= 2, "isentropic_stage_dry: part must be 0, 1 or 2");
   a.dt = cfg->dt; a.dt_full = cfg->dt_full; a.dx = cfg->dx; a.dy = cfg->dy; a.dz = cfg->dz;
@@ -1599,6 +1778,16 @@ extern "C" int tb200_isentropic_stage_dry(
       }
     }
   }
+  if (!lazy_uv_path(a)) {
+    // the other kernel variants keep the reference's data flow (see lazy_uv_path)
+    TB200_REQUIRE(a.spre.p != a.s_new.p,
+                  "isentropic_stage_dry: scratch_s may alias s_new only on the default kernel path");
+    a.derive_uv = a.skip_uv = 0;
+  }
+  TB200_REQUIRE(a.spre.p != a.s_new.p || a.skip_uv,
+                "isentropic_stage_dry: scratch_s may alias s_new only with skip_uv_out");
+  TB200_REQUIRE(a.spre.p != a.s_new.p || a.part == 0,
+                "isentropic_stage_dry: scratch_s may alias s_new only for an unsplit stage (part 0)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (cfg->flux_scheme) {
     case TB200_FLUX_UPWIND: return run_stage<TB200_FLUX_UPWIND>(a, st);

@@ -15,6 +15,7 @@ struct StageArgs {
   int nx, ny, nz, nb, damp;
   int bx0, by0;    // block offsets of a partial launch of the momentum kernel
   int part, rim[4];  // tb200_isentropic_stage.part / .rim
+  int derive_uv, skip_uv;  // tb200_isentropic_stage.derive_uv_in / .skip_uv_out
   double dt, dt_full, dx, dy, dz, eps, pt, theta_s, pref, rd, g, cp;
   FluxConst fc;
   CDiv two_dx, two_dy, cpref;

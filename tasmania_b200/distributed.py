@@ -209,30 +209,37 @@ class HaloExchange:
                 self.recv[s.name] = torch.empty(n, dtype=torch.float64, device=device)
         self.bytes_per_exchange = 8 * sum(b.numel() for b in self.send.values())
 
+    def message(self, buf, s, count):
+        """The leading part of a persistent buffer that holds ``count`` fields of side ``s``
+        (message layout [field][k][j][i]: fewer fields = a prefix)."""
+        return buf[: count * self.nz * s.extent[0] * s.extent[1]]
+
     def pack(self, phase, fields):
         for s in self.plan[phase]:
-            _pack(fields, self.send[s.name], s.send_origin, s.extent, self.nz)
+            _pack(fields, self.message(self.send[s.name], s, len(fields)), s.send_origin, s.extent, self.nz)
 
     def unpack(self, phase, fields):
         for s in self.plan[phase]:
-            _unpack(fields, self.recv[s.name], s.recv_origin, s.extent, self.nz)
+            _unpack(fields, self.message(self.recv[s.name], s, len(fields)), s.recv_origin, s.extent, self.nz)
 
-    def transfer(self, phase):
+    def transfer(self, phase, count=None):
         import torch.distributed as dist
 
+        count = self.nfields if count is None else count
         ops = []
         for s in self.plan[phase]:
-            ops.append(dist.P2POp(dist.isend, self.send[s.name], s.neighbour))
-            ops.append(dist.P2POp(dist.irecv, self.recv[s.name], s.neighbour))
+            ops.append(dist.P2POp(dist.isend, self.message(self.send[s.name], s, count), s.neighbour))
+            ops.append(dist.P2POp(dist.irecv, self.message(self.recv[s.name], s, count), s.neighbour))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
     def exchange(self, fields: Sequence):
-        assert len(fields) == self.nfields
+        """Two-phase exchange of up to ``nfields`` fields (every rank passes the same number)."""
+        assert 1 <= len(fields) <= self.nfields
         for phase in (0, 1):
             self.pack(phase, fields)
-            self.transfer(phase)
+            self.transfer(phase, len(fields))
             self.unpack(phase, fields)
 
 
@@ -248,7 +255,7 @@ def exchange_in_process(exchangers: Sequence[HaloExchange], fields_per_rank: Seq
         for ex, fields in zip(exchangers, fields_per_rank):
             for s in ex.plan[phase]:
                 src = exchangers[s.neighbour].send[_OPPOSITE[s.name]]
-                _unpack(fields, src, s.recv_origin, s.extent, ex.nz)
+                _unpack(fields, ex.message(src, s, len(fields)), s.recv_origin, s.extent, ex.nz)
 
 
 # ------------------------------------------------------------------ the decomposed dry core
@@ -327,12 +334,21 @@ class SubdomainDryCore:
         self.nstep = 0
 
     # ---- pieces of a step (driven stage by stage so that sub-domains can interleave)
-    def exchange_fields(self, out):
-        return [out[n] for n in (self.S, self.SU, self.SV, self.U, self.V)]
+    def velocities_written(self, stage):
+        """Does this stage's output hold u, v?  (Intermediate stages of the fused core do not
+        write them: their successor re-diagnoses them from the exchanged s, su, sv.)"""
+        return not self.dyc.lazy_velocities or stage is None or stage == self.dyc.stages - 1
 
-    def fix_seam_velocities(self, out):
+    def exchange_fields(self, out, stage=None):
+        names = (self.S, self.SU, self.SV, self.U, self.V) if self.velocities_written(stage) \
+            else (self.S, self.SU, self.SV)
+        return [out[n] for n in names]
+
+    def fix_seam_velocities(self, out, stage=None):
         """u on the faces between owned and halo columns, v likewise in y, from the exchanged
         s, su, sv (dwarfs/diagnostics.py:L219-L272, same formula as the fused kernel)."""
+        if not self.velocities_written(stage):
+            return
         vc = self.dyc._velocity_components
         for i in self.u_faces:
             vc._stencil_diagnosing_velocity_x(in_d=out[self.S], in_du=out[self.SU], out_u=out[self.U],
@@ -391,8 +407,8 @@ class Overlap:
             if self.events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            self.sub.halo.exchange(self.sub.exchange_fields(out))
-            self.sub.fix_seam_velocities(out)
+            self.sub.halo.exchange(self.sub.exchange_fields(out, stage))
+            self.sub.fix_seam_velocities(out, stage)
             if self.events is not None:
                 e1.record()
                 self.events.append((e0, e1))
@@ -433,8 +449,8 @@ class DecomposedDryRun:
         if self.exchange_events is not None:  # optional device timing of the exchange
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.sub.halo.exchange(self.sub.exchange_fields(out))
-        self.sub.fix_seam_velocities(out)
+        self.sub.halo.exchange(self.sub.exchange_fields(out, stage))
+        self.sub.fix_seam_velocities(out, stage)
         if self.exchange_events is not None:
             e1.record()
             self.exchange_events.append((e0, e1))
@@ -467,13 +483,13 @@ class InProcessDecomposedRun:
     def step(self):
         iters = [s.begin_step() for s in self.subs]
         outs = [None] * len(self.subs)
-        for _ in range(self.subs[0].dyc.stages):
+        for stage in range(self.subs[0].dyc.stages):
             for r, it in enumerate(iters):
                 outs[r] = next(it)[1]
             exchange_in_process([s.halo for s in self.subs],
-                                [s.exchange_fields(o) for s, o in zip(self.subs, outs)])
+                                [s.exchange_fields(o, stage) for s, o in zip(self.subs, outs)])
             for s, o in zip(self.subs, outs):
-                s.fix_seam_velocities(o)
+                s.fix_seam_velocities(o, stage)
         for it in iters:  # exhaust the generators (sets the time label)
             for _ in it:
                 pass

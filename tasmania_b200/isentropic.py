@@ -264,10 +264,22 @@ class IsentropicDynamicalCore(StencilFactory):
                 storage_options=self.storage_options)
             z = lambda: self.zeros(shape=self.storage_shape)  # noqa: E731
             self._sq = {(t, n): z() for t in ("now", "int", "new") for n in (SQV, SQC, SQR)}
-        fusable = (not moist) and horizontal_boundary.type == "relaxed"
+        from tasmania_b200.boundary import Relaxed
+
+        # the 2-D class only: Relaxed1DX / 1DY also report type "relaxed", but their gamma is
+        # non-zero on the middle line alone and they repeat that line across the degenerate axis,
+        # which the fused kernels do not do
+        fusable = (not moist) and type(horizontal_boundary) is Relaxed
         if fused and not fusable:
             raise ValueError("the fused stage covers the dry core with relaxed boundaries only")
         self._fused = fusable if fused is None else bool(fused)
+        # fused path only: intermediate RK stages neither write nor read u, v (see _stage_fused);
+        # set to False to get every stage's velocities like the reference's stage_array_call
+        self.lazy_velocities = True
+        # ... and stage 0 too re-diagnoses them instead of reading the state's u, v.  Only for
+        # callers who know that those ARE the diagnosis of the state's s, su, sv (true for every
+        # state this core produced, not for an initial state given in terms of u, v)
+        self.derive_stage0_velocities = False
         self._raw_stage_states = None
         self._s_now = self._su_now = self._sv_now = None
         self._ref = None
@@ -357,6 +369,15 @@ class IsentropicDynamicalCore(StencilFactory):
         cfg.constants[:] = [rpc["pref"], rpc["rd"], rpc["g"], rpc["cp"]]
         cfg.part = part
         cfg.rim[:] = list(rim)
+        # velocities between the stages of one step: an intermediate stage does not write u, v,
+        # its successor re-diagnoses them from s, su, sv (same formula, same bits: the reference
+        # computes them exactly so at the end of every stage, dycore.py:L702-L721); the stage
+        # outputs of intermediate stages therefore hold STALE u, v (``lazy_velocities``)
+        lazy = self.lazy_velocities
+        cfg.derive_uv_in = int(lazy and (stage > 0 or self.derive_stage0_velocities))
+        cfg.skip_uv_out = int(lazy and stage < self.stages - 1)
+        # ... and then nobody re-reads s before it is final: the stage updates it in place
+        scratch_s = out_state[S] if (cfg.skip_uv_out and part == 0) else self._scratch[2]
         pr._diagnostics._set_topography()
         ref, now = hb.reference_state, pr._now
         f = lib.as_field
@@ -367,7 +388,7 @@ class IsentropicDynamicalCore(StencilFactory):
             f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
             f(ref[S]), f(ref[SU]), f(ref[SV]), f(ref[U]), f(ref[V]),
             f(hb._gamma2d), f(rmat), f(pr._diagnostics._topo2d),
-            f(self._scratch[0]), f(self._scratch[1]), f(self._scratch[2]), lib.current_stream())
+            f(self._scratch[0]), f(self._scratch[1]), f(scratch_s), lib.current_stream())
         lib.check(rc, "tb200_isentropic_stage_dry")
         if "time" in state and part != 1:
             out_state["time"] = state["time"] + dtr

@@ -40,6 +40,7 @@ class StageCfg(C.Structure):
         ("pt", C.c_double), ("theta_s", C.c_double),
         ("constants", C.c_double * 4),
         ("part", C.c_int32), ("rim", C.c_int32 * 4),
+        ("derive_uv_in", C.c_int32), ("skip_uv_out", C.c_int32),
     ]
 
 

@@ -2,10 +2,16 @@
 """Host-resident states through the device: the end-to-end entry point of the dry dynamical core.
 
 A caller whose model state lives in host memory (the reference's numpy world) hands one state
-per step to ``HostStreamedDryCore.step``: the stage inputs (s, su, sv, u, v, Montgomery
-potential) are uploaded from pinned host buffers, one full RK step plus the diagnostics refresh
-runs on the device, and the stepped fields (s, su, sv, u, v) are downloaded into pinned host
-buffers.  The device side is double-buffered and the three activities run on three CUDA
+per step to ``HostStreamedDryCore.step``: the PROGNOSTIC fields (s, su, sv) are uploaded from
+pinned host buffers, one full RK step plus the diagnostics refresh runs on the device, and the
+stepped prognostic fields are downloaded into pinned host buffers.  Everything else the step
+needs is a diagnosis of those three and is made on the device, where it costs a fraction of its
+PCIe transfer: the Montgomery potential by the column-scan kernel (40 B/pt of HBM traffic against
+8 B/pt over PCIe, i.e. 0.5 ms against 10 ms at 1024 x 1024 x 64), the advecting velocities inside
+the stage kernels (``derive_uv_in``: u = (su[i-1] + su[i]) / (s[i-1] + s[i]), the formula every
+stage of the reference ends with).  ``prognostic_only=False`` restores the round-1 behaviour
+(upload s, su, sv, u, v, mtg; download s, su, u, sv, v), for callers whose velocities are NOT that
+diagnosis (an initial state given in terms of u, v).  The device side is double-buffered and the three activities run on three CUDA
 streams, so the upload of step i+1 and the download of step i-1 overlap the computation of step
 i (PCIe is full duplex): the sustained rate is max(upload, compute + download-of-previous) per
 step instead of their sum.  ``bench.py`` reports this path as ``e2e``.
@@ -31,16 +37,20 @@ def flat(arr):
 
 
 class HostStreamedDryCore:
-    names_in = (S, SU, SV, U, V, MTG)
-    names_out = (S, SU, U, SV, V)
-
-    def __init__(self, dycore, diagnostics, pt, timestep, start_time=None):
+    def __init__(self, dycore, diagnostics, pt, timestep, start_time=None, prognostic_only=True):
         self.dyc, self.diag, self.pt, self.dt = dycore, diagnostics, pt, timestep
+        self.prognostic_only = bool(prognostic_only)
+        if self.prognostic_only and not (dycore._fused and dycore.lazy_velocities):
+            raise ValueError("prognostic_only needs the fused dynamical core with lazy velocities")
+        self.names_in = (S, SU, SV) if self.prognostic_only else (S, SU, SV, U, V, MTG)
+        self.names_out = (S, SU, SV) if self.prognostic_only else (S, SU, U, SV, V)
+        self.device_names_in = (S, SU, SV, U, V, MTG)   # what a device-side state dict holds
+        self.device_names_out = (S, SU, U, SV, V)
         shape = dycore.storage_shape
         dev = dycore.storage_options.device
         z = lambda: storage.zeros(shape, device=dev)  # noqa: E731
-        self.sets = [{"in": {n: z() for n in self.names_in + (P, EXN, H)},
-                      "out": {n: z() for n in self.names_out}} for _ in range(2)]
+        self.sets = [{"in": {n: z() for n in self.device_names_in + (P, EXN, H)},
+                      "out": {n: z() for n in self.device_names_out}} for _ in range(2)]
         self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
         ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]  # noqa: E731
         self.uploaded, self.in_free, self.computed, self.out_free = ev(), ev(), ev(), ev()
@@ -68,7 +78,18 @@ class HostStreamedDryCore:
         self.dyc.update_topography(self.nstep * self.dt)
         state = dict(dev["in"])
         state["time"] = self.time
-        out = self.dyc(state, {}, self.dt, out_state=dev["out"])
+        if self.prognostic_only:
+            # Montgomery potential of the uploaded s (and p, exn, h with it); the velocities of
+            # stage 0 are diagnosed inside the kernels (u, v of this set are never read)
+            self.diag.get_diagnostic_variables(state[S], self.pt, state[P], state[EXN], state[MTG], state[H])
+            saved = self.dyc.derive_stage0_velocities
+            self.dyc.derive_stage0_velocities = True
+            try:
+                out = self.dyc(state, {}, self.dt, out_state=dev["out"])
+            finally:
+                self.dyc.derive_stage0_velocities = saved
+        else:
+            out = self.dyc(state, {}, self.dt, out_state=dev["out"])
         self.time = out["time"]
         self.diag.get_diagnostic_variables(out[S], self.pt, dev["in"][P], dev["in"][EXN],
                                            dev["in"][MTG], dev["in"][H])

@@ -191,7 +191,13 @@ class OracleStub(AbiStub):
         shape = out["s"].shape
         gamma = np.broadcast_to(arr(gamma2d)[:, :, :1], shape)
         origin, domain = (nb, nb, 0), (nx - 2 * nb, ny - 2 * nb, nz)
-        oi.step_forward_euler(flux, arr(s_now), arr(s_int), out["s"], arr(u_int), arr(v_int), dt=c.dt,
+        u_i, v_i = arr(u_int), arr(v_int)
+        if c.derive_uv_in:  # the kernels re-diagnose the advecting velocities; u_int / v_int may be stale
+            u_i, v_i = np.full(shape, np.nan), np.full(shape, np.nan)
+            dwarfs.get_velocity_components(nx, ny, nz, arr(s_int), arr(su_int), arr(sv_int), u_i, v_i)
+        assert arr(scr2) is not None  # may BE s_new (in-place update with skip_uv_out)
+        assert c.skip_uv_out or arr(scr2).ctypes.data != out["s"].ctypes.data
+        oi.step_forward_euler(flux, arr(s_now), arr(s_int), out["s"], u_i, v_i, dt=c.dt,
                               dx=c.dx, dy=c.dy, origin=origin, domain=domain)
         ob.irelax(gamma, arr(s_ref), out["s"], (0, 0, 0), (nx, ny, nz))
         hs = np.zeros(shape)
@@ -200,7 +206,7 @@ class OracleStub(AbiStub):
         oi.montgomery(hs, out["s"], mtg_new, dz=c.dz, pt=c.pt, theta_s=c.theta_s, origin=(0, 0, 0),
                       domain=(nx, ny, nz + 1), constants=constants(c.constants))
         oi.step_forward_euler_momentum(
-            flux, arr(s_now), out["s"], arr(u_int), arr(v_int), arr(su_now), arr(su_int), out["su"], arr(sv_now),
+            flux, arr(s_now), out["s"], u_i, v_i, arr(su_now), arr(su_int), out["su"], arr(sv_now),
             arr(sv_int), out["sv"], arr(mtg_now), mtg_new, dt=c.dt, dx=c.dx, dy=c.dy, eps=c.eps, origin=origin,
             domain=domain)
         for n, ref in (("s", s_ref), ("su", su_ref), ("sv", sv_ref)):  # enforce_raw (u, v are re-diagnosed)
@@ -209,6 +215,10 @@ class OracleStub(AbiStub):
             r = np.broadcast_to(arr(rmat)[:1, :1, :], shape)
             for n, now, ref in (("s", s_now, s_ref), ("su", su_now, su_ref), ("sv", sv_now, sv_ref)):
                 dwarfs.damping(arr(now), out[n], arr(ref), r, out[n], c.dt_full, (0, 0, 0), shape)
+        if c.skip_uv_out:  # not written by the kernels: poison, so that any consumer shows up
+            out["u"][...] = np.nan
+            out["v"][...] = np.nan
+            return
         dwarfs.get_velocity_components(nx, ny, nz, out["s"], out["su"], out["sv"], out["u"], out["v"])
         ur, vr = arr(u_ref), arr(v_ref)
         out["u"][0, :ny], out["u"][nx, :ny] = ur[0, :ny], ur[nx, :ny]        # relaxed.py:L161-L175

@@ -79,33 +79,12 @@ def oracle_dry_run(fx, nsteps=None):
     return state, stage0, (grid, hb, topo, dyc)
 
 
-def moist_case(nx, ny, nz, *, topo_seconds=60.0, max_height=1000.0, relative_humidity=0.98,
-               seed=True, half_width_km=(176.0, 176.0)):
-    """BASELINE config 3 scaled down: the moist mountain-flow case of namelist_sus.py on a 352 km
-    square (grid spacing of a 161-point axis is kept when nx = ny = 161), with a faster-growing,
-    taller mountain and -- when ``seed`` -- blobs of cloud water and rain in the initial state so
-    that autoconversion, accretion, evaporation, sedimentation and precipitation are all active
-    within a few steps.  Returns (tasmania_b200 Grid, numpy state)."""
-    from tasmania_b200.grid import Grid, Topography as GTopography
-    from tasmania_b200.grid import gaussian_profile, isentropic_state_from_brunt_vaisala
+def moist_case(nx, ny, nz, **kwargs):
+    """The moist mountain-flow case (BASELINE config 3, scalable): see
+    tasmania_b200.isentropic_moist.moist_mountain_case, which builds it (bench.py uses it too)."""
+    from tasmania_b200.isentropic_moist import moist_mountain_case
 
-    hx, hy = half_width_km
-    x = np.linspace(-hx, hx, nx)
-    y = np.linspace(-hy, hy, ny)
-    topo = GTopography(gaussian_profile(x, y, max_height, 50.0, 50.0), timedelta(seconds=topo_seconds))
-    grid = Grid((-hx, hx), nx, (-hy, hy), ny, (400.0, 280.0), nz, units_to_m=1e3,
-                topography=topo)
-    state = isentropic_state_from_brunt_vaisala(grid, 22.5, 0.0, 0.015, moist=True,
-                                                precipitation=True,
-                                                relative_humidity=relative_humidity)
-    if seed:
-        i, j, k = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
-        blob = np.exp(-(((i - nx // 2) / (0.2 * nx)) ** 2 + ((j - ny // 2) / (0.2 * ny)) ** 2
-                        + ((k - 0.7 * nz) / (0.2 * nz)) ** 2))
-        blob[nx:, :, :] = blob[:, ny:, :] = blob[:, :, nz:] = 0.0
-        state[oi.MFCW] = 8e-4 * blob
-        state[oi.MFPW] = 3e-4 * np.roll(blob, 2, axis=0) * (blob > 0)
-    return grid, state
+    return moist_mountain_case(nx, ny, nz, **kwargs)
 
 
 BOUNDARY_1D_NAMES = ("air_isentropic_density", "x_velocity_at_u_locations", "y_velocity_at_v_locations",

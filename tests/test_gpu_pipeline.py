@@ -10,6 +10,53 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def test_host_streamed_prognostic_only_steps_equal_direct_steps():
+    """The default of the streaming API: only s, su, sv cross PCIe, the Montgomery potential and
+    the velocities are diagnosed on the device.  Equal, bit for bit, to stepping a device-resident
+    state whose initial u, v are the diagnosis of its s, su, sv (which every later state's are)."""
+    import torch
+
+    from tasmania_b200.distributed import InProcessDecomposedRun
+    from tasmania_b200.pipeline import HostStreamedDryCore, flat
+
+    kw = dict(damp_depth=4, topo_seconds=20.0)
+    direct = InProcessDecomposedRun(67, 45, 12, 1, 1, **kw)
+    piped = InProcessDecomposedRun(67, 45, 12, 1, 1, **kw)
+    dsub, sub = direct.subs[0], piped.subs[0]
+    nx, ny, nz = dsub.nx, dsub.ny, dsub.nz
+    vc = dsub.dyc._velocity_components
+    st = dsub.state
+    vc._stencil_diagnosing_velocity_x(in_d=st[dsub.S], in_du=st[dsub.SU], out_u=st[dsub.U],
+                                      origin=(1, 0, 0), domain=(nx - 1, ny, nz))
+    vc._stencil_diagnosing_velocity_y(in_d=st[dsub.S], in_dv=st[dsub.SV], out_v=st[dsub.V],
+                                      origin=(0, 1, 0), domain=(nx, ny - 1, nz))
+    pipe = HostStreamedDryCore(sub.dyc, sub.diag, sub.pt, sub.dt)
+    assert pipe.names_in == pipe.names_out == (dsub.S, dsub.SU, dsub.SV)
+    host_in = pipe.host_buffers(pipe.names_in)
+    host_out = pipe.host_buffers(pipe.names_out)
+    for n in pipe.names_in:
+        host_in[n].copy_(flat(sub.state[n]))
+    nsteps = 5
+    for step in range(nsteps):
+        direct.step()
+        pipe.step(host_in, host_out)
+        pipe.join()
+        torch.cuda.synchronize()
+        for n in pipe.names_out:  # feed the downloaded state back as the next input
+            host_in[n].copy_(host_out[n])
+    for n in pipe.names_out:
+        want = flat(dsub.state[n]).cpu().numpy()
+        np.testing.assert_array_equal(host_out[n].numpy(), want, err_msg=n)
+    # the velocities and the refreshed diagnostics of the last step are on the device
+    last = pipe.sets[(nsteps - 1) % 2]
+    for n in (dsub.U, dsub.V):
+        np.testing.assert_array_equal(flat(last["out"][n]).cpu().numpy(), flat(dsub.state[n]).cpu().numpy(),
+                                      err_msg=n)
+    np.testing.assert_array_equal(flat(last["in"][dsub.MTG]).cpu().numpy(),
+                                  flat(dsub.state[dsub.MTG]).cpu().numpy())
+    assert np.isfinite(host_out[pipe.names_out[0]].numpy()).all()
+
+
 def test_host_streamed_steps_equal_direct_steps():
     import torch
 
@@ -20,7 +67,7 @@ def test_host_streamed_steps_equal_direct_steps():
     direct = InProcessDecomposedRun(67, 45, 12, 1, 1, **kw)
     piped = InProcessDecomposedRun(67, 45, 12, 1, 1, **kw)
     sub = piped.subs[0]
-    pipe = HostStreamedDryCore(sub.dyc, sub.diag, sub.pt, sub.dt)
+    pipe = HostStreamedDryCore(sub.dyc, sub.diag, sub.pt, sub.dt, prognostic_only=False)
     host_in = pipe.host_buffers(pipe.names_in)
     host_out = pipe.host_buffers(pipe.names_out)
     for n in pipe.names_in:
