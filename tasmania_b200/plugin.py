@@ -282,7 +282,121 @@ def _frame_relaxed_enforce_raw():
     return "Relaxed.enforce_raw"
 
 
-def install(strict: bool = False, batch_fma: bool = True, frame_relax: bool = True) -> dict:
+def _fused_stage_dry():
+    """Put the fused RK stage (``tb200_isentropic_stage_dry``: three kernels instead of the 13
+    stencil launches of a stage) behind the reference's own
+    ``IsentropicDynamicalCore.stage_array_call_dry`` (src/tasmania/isentropic/dynamics/
+    dycore.py:L641-L721) on backend b200.  The patched method keeps the reference's bookkeeping
+    (current-solution pointers of the dycore and of its prognostic object, topography upload,
+    time label) and hands everything else to the library; it falls back to the original method
+    -- the per-stencil b200 kernels -- whenever the configuration is outside the fused kernels'
+    scope: slow or fast tendencies, a boundary other than the 2-D ``Relaxed``, a prognostic scheme
+    other than RK3WSSI / ForwardEulerSI, reference fields in non-canonical units, foreign storages.
+
+    Intermediate stages neither write nor read u, v (``skip_uv_out`` / ``derive_uv_in``: their
+    successor re-diagnoses them with the formula ``get_velocity_components`` ends every stage with,
+    so the step's result is bit-identical) unless the dycore has a fast tendency or diagnostic
+    component, which may look at an intermediate state's velocities."""
+    from tasmania.isentropic.dynamics.dycore import IsentropicDynamicalCore
+    from tasmania_b200 import lib
+
+    original = IsentropicDynamicalCore.stage_array_call_dry
+    if getattr(original, "__tasmania_b200__", False):
+        return None
+
+    S, SU, SV = "air_isentropic_density", "x_momentum_isentropic", "y_momentum_isentropic"
+    U, V, MTG = "x_velocity_at_u_locations", "y_velocity_at_v_locations", "montgomery_potential"
+    UNITS = {S: "kg m^-2 K^-1", SU: "kg m^-1 K^-1 s^-1", SV: "kg m^-1 K^-1 s^-1", U: "m s^-1", V: "m s^-1"}
+    SUBSTEPS = {  # stage -> (increment of the time label, stage time step), the reference's own
+        # timedelta arithmetic (rk3ws_si.py:L115-L123, forward_euler_si.py:L106-L111)
+        "rk3ws_si": (lambda t: (t / 3.0, t / 3.0), lambda t: (t / 6.0, 0.5 * t), lambda t: (0.5 * t, t)),
+        "forward_euler_si": (lambda t: (t, t),),
+    }
+
+    def plan(self, tendencies):
+        """The static part of the decision, cached on the object; None = not fusable."""
+        cached = getattr(self, "_b200_fused_plan", None)
+        if cached is not None:
+            return cached or None
+        ok = getattr(self, "backend", None) == BACKEND and not getattr(self, "_moist", True)
+        hb, pr = self.horizontal_boundary, self._prognostic
+        ok = ok and type(hb).__name__ == "Relaxed" and getattr(type(pr), "name", None) in SUBSTEPS
+        scheme = getattr(getattr(pr, "_hflux", None), "name", None)
+        ok = ok and scheme in lib.FLUX_SCHEMES and hasattr(pr, "_diagnostics")
+        if ok:
+            ref = hb.reference_state
+            ok = all(n in ref and ref[n].attrs.get("units") == UNITS[n] for n in UNITS)
+        if not ok:
+            self._b200_fused_plan = False
+            return None
+        diag = pr._diagnostics
+        g = self.grid
+        rpc = diag.rpc
+        shape = tuple(diag._topo.shape)
+        self._b200_fused_plan = {
+            "scheme": lib.FLUX_SCHEMES[scheme], "substeps": SUBSTEPS[type(pr).name],
+            "dx": g.dx.to_units("m").values.item(), "dy": g.dy.to_units("m").values.item(),
+            "dz": g.dz.to_units("K").values.item(),
+            "theta_s": float(g.z_on_interface_levels.to_units("K").values[-1]),
+            "constants": [rpc["air_pressure_at_sea_level"], rpc["gas_constant_of_dry_air"],
+                          rpc["gravitational_acceleration"],
+                          rpc["specific_heat_of_dry_air_at_constant_pressure"]],
+            "scratch": [storage.zeros(shape, device=_device(self.storage_options)) for _ in range(3)],
+            "lazy": self.fast_tendency_component is None and self.fast_diagnostic_component is None,
+        }
+        return self._b200_fused_plan
+
+    def stage_array_call_dry(self, stage, state, tendencies, timestep, out_state):
+        if any(k != "time" for k in (tendencies or {})):
+            return original(self, stage, state, tendencies, timestep, out_state)
+        p = plan(self, tendencies)
+        if p is None or not all(isinstance(state[n], storage.B200Array) for n in (S, SU, SV, U, V, MTG)):
+            return original(self, stage, state, tendencies, timestep, out_state)
+        hb, pr = self.horizontal_boundary, self._prognostic
+        diag = pr._diagnostics
+        g = self.grid
+        nx, ny, nz = g.nx, g.ny, g.nz
+        ref = hb.reference_state
+        if stage == 0:  # the reference's bookkeeping, dycore.py:L662-L668 and rk3ws_si.py:L126-L130
+            self._s_now, self._su_now, self._sv_now = state[S], state[SU], state[SV]
+            pr._s_now, pr._mtg_now, pr._su_now, pr._sv_now = state[S], state[MTG], state[SU], state[SV]
+        # the topography of the moment, as get_montgomery_potential uploads it (diagnostics.py:L216-L219)
+        diag._topo[:nx, :ny, nz] = diag.as_storage(data=g.topography.profile.to_units("m").values)
+        dtr, dt = p["substeps"][stage](timestep)
+        damp = bool(self._damp and (self._damp_at_every_stage or stage == self.stages - 1))
+        cfg = lib.StageCfg()
+        cfg.nx, cfg.ny, cfg.nz, cfg.nb = nx, ny, nz, hb.nb
+        cfg.flux_scheme = p["scheme"]
+        cfg.damp = int(damp)
+        cfg.dt, cfg.dt_full = dt.total_seconds(), timestep.total_seconds()
+        cfg.dx, cfg.dy, cfg.dz, cfg.eps = p["dx"], p["dy"], p["dz"], pr._eps
+        cfg.pt, cfg.theta_s = pr._pt, p["theta_s"]
+        cfg.constants[:] = p["constants"]
+        cfg.part = 0
+        cfg.rim[:] = [0, 0, 0, 0]
+        cfg.derive_uv_in = int(p["lazy"] and stage > 0)
+        cfg.skip_uv_out = int(p["lazy"] and stage < self.stages - 1)
+        scratch_s = out_state[S] if cfg.skip_uv_out else p["scratch"][2]
+        f = lib.as_field
+        rmat = self._damper._rmat if self._damp else None
+        rc = lib.load().tb200_isentropic_stage_dry(
+            cfg, f(pr._s_now), f(pr._su_now), f(pr._sv_now), f(pr._mtg_now),
+            f(state[S]), f(state[SU]), f(state[SV]), f(state[U]), f(state[V]),
+            f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
+            f(ref[S].data), f(ref[SU].data), f(ref[SV].data), f(ref[U].data), f(ref[V].data),
+            f(hb._gamma), f(rmat), f(diag._topo[:, :, nz:nz + 1]),
+            f(p["scratch"][0]), f(p["scratch"][1]), f(scratch_s), lib.current_stream())
+        lib.check(rc, "tb200_isentropic_stage_dry")
+        out_state["time"] = state["time"] + dtr
+
+    stage_array_call_dry.__tasmania_b200__ = True
+    stage_array_call_dry.__wrapped_original__ = original
+    IsentropicDynamicalCore.stage_array_call_dry = stage_array_call_dry
+    return "IsentropicDynamicalCore.stage_array_call_dry"
+
+
+def install(strict: bool = False, batch_fma: bool = True, frame_relax: bool = True,
+            fused_stage: bool = True) -> dict:
     """Register the b200 backend into the importable ``tasmania`` package.  Returns a report
     ``{"global": [...], "class_scoped": [...], "skipped": [...]}``; with ``strict`` a reference
     class that cannot be imported raises instead of being skipped (sub-packages pulling
@@ -367,6 +481,17 @@ def install(strict: bool = False, batch_fma: bool = True, frame_relax: bool = Tr
             if strict:
                 raise
             report["skipped"].append(("Relaxed.enforce_raw", repr(exc)))
+
+    # 6. the fused RK stage behind the reference's own dynamical core
+    if fused_stage:
+        try:
+            patched = _fused_stage_dry()
+            if patched:
+                report.setdefault("fused", []).append(patched)
+        except Exception as exc:  # pragma: no cover - depends on optional deps of the reference
+            if strict:
+                raise
+            report["skipped"].append(("IsentropicDynamicalCore.stage_array_call_dry", repr(exc)))
 
     _installed = True
     return report

@@ -37,7 +37,7 @@ from tasmania_b200 import plugin  # noqa: E402
 from tests.abi_oracle import OracleStub  # noqa: E402
 from tests.abi_stub import stubbed_library  # noqa: E402
 
-plugin.install(frame_relax=False)  # the reference-shaped boundary path on both sides
+plugin.install(frame_relax=False, fused_stage=False)  # the reference-shaped per-stencil path on both sides
 
 S, SU, SV = gg.S, gg.SU, gg.SV
 U, V, MTG = "x_velocity_at_u_locations", "y_velocity_at_v_locations", "montgomery_potential"
@@ -63,9 +63,10 @@ OUTNAMES = (S, SU, U, SV, V)
 QNAMES = (gg.MFWV, gg.MFCW, gg.MFPW)
 
 
-def reference_trace(stub, moist, fx):
+def reference_trace(stub, moist, fx, fused=False):
     """One RK3WS step of the reference's own dycore stage on backend b200; returns the ABI trace,
-    the initial state as numpy arrays, the model-top pressure and the first-stage outputs."""
+    the initial state as numpy arrays, the model-top pressure and the first-stage outputs (with
+    ``fused``: through the plugin's fused-stage hook; the outputs of every stage)."""
     from tasmania.framework import allocators as ta
     from tasmania.framework.generic_functions import to_numpy
 
@@ -129,6 +130,9 @@ def reference_trace(stub, moist, fx):
     # the attributes stage_array_call_dry / _moist read from the dycore object
     me = types.SimpleNamespace(
         horizontal_boundary=hb, **water,
+        # what the plugin's fused-stage hook reads in addition (attributes of the real object)
+        backend="b200", grid=grid, storage_options=so(), _moist=moist,
+        fast_tendency_component=None, fast_diagnostic_component=None,
         output_properties={k: {"units": state[k].attrs["units"]} for k in outnames},
         _damp=True, _damp_at_every_stage=True, stages=prognostic.stages, _prognostic=prognostic,
         _damper=damper, _velocity_components=velocity, _s_ref=zeros(), _su_ref=zeros(),
@@ -138,6 +142,8 @@ def reference_trace(stub, moist, fx):
     outs = [{k: zeros() for k in outnames} for _ in range(prognostic.stages)]
     stage_call = (dyc.IsentropicDynamicalCore.stage_array_call_moist if moist
                   else dyc.IsentropicDynamicalCore.stage_array_call_dry)
+    if fused:  # looked up after the patch
+        stage_call = dyc.IsentropicDynamicalCore.stage_array_call_dry
     grid.update_topography(DT)
     stub.trace = []
     st_in = cur
@@ -147,6 +153,9 @@ def reference_trace(stub, moist, fx):
         st_in.setdefault(MTG, cur[MTG])
     trace, stub.trace = stub.trace, None
     stage0 = {k: to_numpy(v) for k, v in outs[0].items() if k != "time"}
+    if fused:
+        return trace, [{k: to_numpy(v) for k, v in o.items() if k != "time"} for o in outs], \
+            [o["time"] for o in outs]
     return trace, {k: to_numpy(v.data) for k, v in state.items() if k != "time"}, pt, stage0
 
 
@@ -229,4 +238,39 @@ for moist_case in (False, True):
     for n, (p, q) in enumerate(zip(a, b)):
         assert p == q, (moist_case, n, p, q)
     done.append(len(a))
-print("REF-DYCORE-OK", *done)
+
+# ---- the fused stage behind the reference's own class (plugin.install(fused_stage=True)): the
+# unmodified reference objects, stage_array_call_dry patched for backend b200, (1) issue one
+# tb200_isentropic_stage_dry call per stage with the lazy-velocity flags, (2) reproduce the
+# reference's numpy backend on the first stage (s, su, sv: the fixture) and (3) end the step with
+# exactly the fields the per-stencil reference run ends with
+fixture = set_case(False)
+with stubbed_library(OracleStub) as the_stub:
+    assert plugin._fused_stage_dry() == "IsentropicDynamicalCore.stage_array_call_dry"
+    assert plugin._fused_stage_dry() is None  # idempotent
+    fused_trace, fused_outs, fused_times = reference_trace(the_stub, False, fixture, fused=True)
+names = [n for n, _ in fused_trace]
+assert names.count("tb200_isentropic_stage_dry") == 3, collections.Counter(names)
+assert not any(n in names for n in ("tb200_step_forward_euler", "tb200_velocity", "tb200_damping", "tb200_relax"))
+flags = [(dict(zip([f for f, _ in tb.lib.StageCfg._fields_], d[0]))["derive_uv_in"],
+          dict(zip([f for f, _ in tb.lib.StageCfg._fields_], d[0]))["skip_uv_out"])
+         for n, d in fused_trace if n == "tb200_isentropic_stage_dry"]
+assert flags == [(0, 1), (1, 1), (1, 0)], flags
+for name in (S, SU, SV):
+    assert np.array_equal(fused_outs[0][name], fixture["stage0_" + name]), name
+assert np.isnan(fused_outs[0][U]).all() and np.isnan(fused_outs[1][V]).all()  # never written (stub poison)
+# the per-stencil reference run of the same step, all stages, for the final fields
+import importlib  # noqa: E402
+
+dyc_mod = importlib.import_module("tasmania.isentropic.dynamics.dycore")
+patched = dyc_mod.IsentropicDynamicalCore.stage_array_call_dry
+dyc_mod.IsentropicDynamicalCore.stage_array_call_dry = patched.__wrapped_original__
+try:
+    with stubbed_library(OracleStub) as the_stub:
+        _, plain_outs, plain_times = reference_trace(the_stub, False, fixture, fused=True)
+finally:
+    dyc_mod.IsentropicDynamicalCore.stage_array_call_dry = patched
+for name in OUTNAMES:
+    assert np.array_equal(fused_outs[2][name], plain_outs[2][name]), name
+assert fused_times == plain_times
+print("REF-DYCORE-OK", *done, "FUSED-HOOK-OK")

@@ -28,6 +28,20 @@ def test_reference_dycore_on_b200_issues_the_mirror_call_sequence():
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "REF-DYCORE-OK 42 69" in res.stdout  # dry and moist stage sequences
+    assert "FUSED-HOOK-OK" in res.stdout        # the fused stage behind the reference's class
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
+                    reason="reference tree not mounted")
+def test_reference_dycore_time_stepped_on_b200_equals_its_numpy_backend():
+    """Four RK3WS steps of the reference's own dycore stage, Relaxed boundary, damper and
+    diagnostics on backend b200 through plugin.install(fused_stage=True) -- the oracle-backed stub
+    standing in for the library -- against the same objects on backend numpy: bit for bit.  (The
+    same script runs against the real library in tests/test_gpu_plugin_reference.py.)"""
+    res = subprocess.run([sys.executable, os.path.join(HERE, "ref_dycore_steps.py"), "--stub", "--steps", "4"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "REF-DYCORE-STEPS-OK fused 4" in res.stdout
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
