@@ -424,6 +424,45 @@ int tb200_halo_pack(const tb200_field *const *fields, int nfields, double *buffe
 int tb200_halo_unpack(const tb200_field *const *fields, int nfields, const double *buffer,
                       const int32_t origin[3], const int32_t domain[3], void *stream);
 
+/* ---- peer-to-peer halo transport over NVLink / NVSwitch (one process per GPU).  No reference
+ * counterpart (the reference is single-process; north_star: "NCCL/P2P halo exchange over NVLink").
+ * A rank allocates its receive buffers and arrival counters with tb200_p2p_alloc, exports the
+ * allocation (CUDA IPC handle, 64 bytes, passed to the neighbours by any host channel) and
+ * imports the neighbours' ones.  tb200_halo_push packs the send slabs of up to two sides of a
+ * phase STRAIGHT into the neighbours' receive buffers (peer stores) and raises their arrival
+ * counters; tb200_halo_pull waits for the own counters and unpacks.  Receive buffers hold two
+ * slots of slot_doubles (exchange q uses slot q & 1; see csrc/halo.cu for why two suffice);
+ * `channel` = TB200_P2P_CHANNEL_BYTES of zeroed device memory per phase (sequence numbers, kept
+ * on the device so that the launches can be captured in a CUDA graph).  Both sides of a pair must
+ * issue their pushes / pulls in the same order. */
+#define TB200_P2P_HANDLE_BYTES 64
+#define TB200_P2P_CHANNEL_BYTES 32
+typedef struct {
+  double *remote_buffer;    /* neighbour's receive buffer for the slab sent to it (peer-mapped) */
+  uint64_t *remote_counter; /* neighbour's arrival counter of that buffer (peer-mapped) */
+  double *local_buffer;     /* own receive buffer of this side */
+  uint64_t *local_counter;  /* own arrival counter, raised by the neighbour */
+  int64_t slot_doubles;     /* capacity of one slot */
+  int32_t send_origin[2], recv_origin[2], extent[2]; /* (i, j) of the outgoing / incoming slab */
+} tb200_halo_side;
+int tb200_halo_push(const tb200_field *const *fields, int nfields, const tb200_halo_side *sides,
+                    int nsides, void *channel, int k0, int nk, void *stream);
+int tb200_halo_pull(const tb200_field *const *fields, int nfields, const tb200_halo_side *sides,
+                    int nsides, void *channel, int k0, int nk, void *stream);
+int tb200_p2p_alloc(size_t bytes, void **ptr);   /* zero-filled, exportable device memory */
+int tb200_p2p_free(void *ptr);
+int tb200_p2p_export(void *ptr, unsigned char handle[TB200_P2P_HANDLE_BYTES]);
+int tb200_p2p_import(const unsigned char handle[TB200_P2P_HANDLE_BYTES], void **ptr);
+int tb200_p2p_release(void *ptr);                /* undo tb200_p2p_import */
+/* *error != 0: a pull gave up waiting for its peer (~20 s); the results are invalid */
+int tb200_p2p_channel_error(const void *channel, int *error);
+
+/* ---- self-test of the kernels' own correctly rounded division (csrc/common.cuh: qdiv) against
+ * the compiler's IEEE division on `count` generated operand pairs (random, guard-crossing and
+ * hard-case classes); *mismatches (device memory, zeroed by the caller) receives the number of
+ * pairs whose results differ.  Test infrastructure for tests/test_gpu_division.py. */
+int tb200_selftest_division(uint64_t count, uint64_t seed, uint64_t *mismatches, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

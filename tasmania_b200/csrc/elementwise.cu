@@ -551,3 +551,59 @@ extern "C" int tb200_unpack_box(tb200_field *field, const double *buffer,
                       f(i + i0, j + j0, k + k0) = buffer[i + di * (j + dj * k)];
                     });
 }
+
+// ---- self-test of qdiv (common.cuh) against the compiler's IEEE division: `count` operand pairs
+// from a counter-based generator, in classes that cover the fast path, its guard and the known
+// hard cases of Newton-Raphson division (divisor mantissa all ones, quotients next to a rounding
+// boundary, numerator zero / tiny / huge).  *mismatches = pairs whose results differ in any bit
+// (+0 and -0 count as equal: a zero numerator keeps the fast path, which returns +0 for -0 / b).
+namespace {
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double make_fp(unsigned long long mant, int exp2, bool neg) {
+  const unsigned long long bits = ((unsigned long long)neg << 63) | ((unsigned long long)(exp2 + 1023) << 52) |
+                                  (mant & 0xfffffffffffffull);
+  return __longlong_as_double((long long)bits);
+}
+__global__ void __launch_bounds__(256) qdiv_selftest_kernel(unsigned long long count, unsigned long long seed,
+                                                            unsigned long long *mismatches) {
+  unsigned long long bad = 0;
+  for (unsigned long long n = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; n < count;
+       n += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long r0 = mix64(seed + 3 * n), r1 = mix64(seed + 3 * n + 1), r2 = mix64(seed + 3 * n + 2);
+    const int cls = (int)(r2 & 15);
+    // defaults: the data range of the velocity diagnosis (b a sum of densities, a a sum of momenta)
+    int ea = (int)((r2 >> 8) % 41) - 20, eb = (int)((r2 >> 16) % 21) - 4;
+    unsigned long long ma = r0, mb = r1;
+    bool neg = (r2 >> 4) & 1;
+    if (cls == 1) ea = (int)((r2 >> 8) % 1200) - 760;          // wide numerators, across the guard
+    if (cls == 2) eb = (int)((r2 >> 16) % 300) - 150;          // wide divisors, across the guard
+    if (cls == 3) mb = 0xfffffffffffffull - ((r1 >> 20) & 3);  // divisor mantissa (almost) all ones
+    if (cls == 4) mb = (r1 >> 20) & 7;                         // divisor next to a power of two
+    if (cls == 5) ma = mb + ((r0 >> 20) & 7) - 3;              // quotient next to 1
+    if (cls == 6) ma = 0xfffffffffffffull - ((r0 >> 20) & 3);
+    if (cls == 7) ma = mb = 0;                                 // powers of two
+    double a = make_fp(ma, ea, neg), b = make_fp(mb, eb, false);
+    if (cls == 8) a = neg ? -0.0 : 0.0;
+    if (cls == 9) a = __longlong_as_double((long long)(r0 & 0xfffffffffffffull));  // subnormal numerator
+    if (cls == 10) b = (double)(1 + (r1 & 0xffff)) * 0.5;      // small half-integers
+    if (cls == 11) { a = (double)(long long)(r0 >> 34) * 0.25; b = (double)(1 + (r1 >> 44)); }
+    const double q = tb200::qdiv(a, b), want = a / b;
+    const bool same = __double_as_longlong(q) == __double_as_longlong(want) || (q == 0.0 && want == 0.0);
+    bad += same ? 0ull : 1ull;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+extern "C" int tb200_selftest_division(uint64_t count, uint64_t seed, uint64_t *mismatches, void *stream) {
+  TB200_REQUIRE(mismatches != nullptr, "selftest_division: NULL result pointer (device memory, zeroed)");
+  if (count == 0) return TB200_OK;
+  qdiv_selftest_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      count, seed, reinterpret_cast<unsigned long long *>(mismatches));
+  return check_launch("selftest_division");
+}

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
   if (DERIVE) {
     sv_lo = ldo(a.sv_int.p, o_cc);
     const double sv_m = ldo(a.sv_int.p, plane + (unsigned)max(j0 - 1, 0) * row + (unsigned)cc * 8u);
-    fy = F::eval_v(F::prep((sv_m + sv_lo) / (ws[E - 1] + ws[E]), a.fc), ws);
+    fy = F::eval_v(F::prep(qdiv(sv_m + sv_lo, ws[E - 1] + ws[E]), a.fc), ws);
   } else {
     fy = F::eval_v(F::prep(ldo(a.v_int.p, o_cc), a.fc), ws);
   }
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     ws[NW - 1] = cur.s_w;  // ws[m] = s_int at row r - E + 1 + m
     double vq;
     if (DERIVE) {
-      vq = F::prep((sv_lo + cur.v_n) / (ws[E - 1] + ws[E]), a.fc);
+      vq = F::prep(qdiv(sv_lo + cur.v_n, ws[E - 1] + ws[E]), a.fc);
       sv_lo = cur.v_n;
     } else {
       vq = F::prep(cur.v_n, a.fc);
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
       // (the left column from L1 like the s_int neighbours: a shuffle would hand over the
       // CLAMPED column of a lane next to the domain edge)
       const double su_l = ldo(a.su_int.p, o_cc - 8u);
-      uq = F::prep((su_l + cur.u_c) / (xs[E - 1] + xs[E]), a.fc);
+      uq = F::prep(qdiv(su_l + cur.u_c, xs[E - 1] + xs[E]), a.fc);
     } else {
       uq = F::prep(cur.u_c, a.fc);
     }
@@ -962,10 +962,6 @@ constexpr int MV2_PF = 2;  // rows of DRAM -> L2 prefetch ahead of the loads (me
 __device__ __forceinline__ double2 ldo2(const double *base, unsigned off) {
   return __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + off));
 }
-// predicated: lanes that do not need the value issue no request (no sector is fetched for them)
-__device__ __forceinline__ double2 ldo2_if(bool p, const double *base, unsigned off) {
-  return p ? ldo2(base, off) : make_double2(0.0, 0.0);
-}
 __device__ __forceinline__ void sto2(double *base, unsigned off, double2 v) {
   *reinterpret_cast<double2 *>(reinterpret_cast<char *>(base) + off) = v;
 }
@@ -1098,20 +1094,29 @@ __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_
   cp_async_commit();
   unsigned o_c = plane + (unsigned)r0 * row + col_o;  // own pair, row r
 
+  // The streams without reuse are loaded UNCONDITIONALLY, one row ahead of their use: a lane that
+  // does not need a stream (ld_own / ld_u false) reads the pair of the owner lane next to it --
+  // a sector that lane fetches anyway, so no extra traffic -- and discards the value.  A
+  // predicated load with a zero alternative (`p ? load : 0`) compiles to a branch whose merge
+  // moves CONSUME the load right after its issue: the row-ahead request then stalls the warp for
+  // a full memory latency on every row (profiles/README.md, round 2: 13 % of all stall samples on
+  // one IMAD.MOV).
+  const unsigned d_own = ld_own ? 0u : (unsigned)(min(max(c0 + (lane == 0 ? 2 : -2), 0), pmax) - cm) * 8u;
+  const unsigned d_u = ld_u ? 0u : d_own;
   auto load_own = [&](unsigned oc) {
     OwnLoads2 L;
     if (DERIVE) {
       L.v_n = L.u_c = zero2;
       L.s_i2 = ldo2(a.s_int.p, oc + 2 * row);  // every lane: lane l + 1 takes s_int[c0 - 1] from lane l
     } else {
-      L.v_n = ldo2_if(ld_own, a.v_int.p, oc + row);
-      L.u_c = ldo2_if(ld_u, a.u_int.p, oc);
+      L.v_n = ldo2(a.v_int.p, oc + d_own + row);
+      L.u_c = ldo2(a.u_int.p, oc + d_u);
       L.s_i2 = zero2;
     }
-    L.s_pre = ldo2_if(ld_own, a.spre.p, oc);
-    L.s_now = ldo2_if(ld_own, a.s_now.p, oc);
-    L.su_now = ldo2_if(ld_own, a.su_now.p, oc);
-    L.sv_now = ldo2_if(ld_own, a.sv_now.p, oc);
+    L.s_pre = ldo2(a.spre.p, oc + d_own);
+    L.s_now = ldo2(a.s_now.p, oc + d_own);
+    L.su_now = ldo2(a.su_now.p, oc + d_own);
+    L.sv_now = ldo2(a.sv_now.p, oc + d_own);
     return L;
   };
   // The reference fields of the relaxation band / damping layer are requested one row ahead of
@@ -1137,7 +1142,7 @@ __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_
     si_a = ldo2(a.s_int.p, o_c);
     si_b = ldo2(a.s_int.p, o_c + row);
   } else {
-    v_first = ldo2_if(ld_own, a.v_int.p, o_c);
+    v_first = ldo2(a.v_int.p, o_c + d_own);
   }
   OwnLoads2 nxt = load_own(o_c);
   fetch_su(NW, r0 + E);
@@ -1157,8 +1162,8 @@ __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_
     }
     double vq0, vq1;
     if (DERIVE) {  // window entry m holds row r0 - E + m: rows r0-1, r0 are entries E-1, E
-      vq0 = F::prep((ysv0[E - 1] + ysv0[E]) / (v_first.x + si_a.x), a.fc);
-      vq1 = F::prep((ysv1[E - 1] + ysv1[E]) / (v_first.y + si_a.y), a.fc);
+      vq0 = F::prep(qdiv(ysv0[E - 1] + ysv0[E], v_first.x + si_a.x), a.fc);
+      vq1 = F::prep(qdiv(ysv1[E - 1] + ysv1[E], v_first.y + si_a.y), a.fc);
     } else {
       vq0 = F::prep(v_first.x, a.fc);
       vq1 = F::prep(v_first.y, a.fc);
@@ -1229,8 +1234,8 @@ __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_
     }
     double vq0, vq1;
     if (DERIVE) {  // v at the y-face r+1: window entries E-1 (row r) and E (row r+1)
-      vq0 = F::prep((ysv0[E - 1] + ysv0[E]) / (si_a.x + si_b.x), a.fc);
-      vq1 = F::prep((ysv1[E - 1] + ysv1[E]) / (si_a.y + si_b.y), a.fc);
+      vq0 = F::prep(qdiv(ysv0[E - 1] + ysv0[E], si_a.x + si_b.x), a.fc);
+      vq1 = F::prep(qdiv(ysv1[E - 1] + ysv1[E], si_a.y + si_b.y), a.fc);
     } else {
       vq0 = F::prep(cur.v_n.x, a.fc);
       vq1 = F::prep(cur.v_n.y, a.fc);
@@ -1263,8 +1268,8 @@ __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_
     double uq0, uq1;
     if (DERIVE) {  // u at the left face of c0 and at the face between c0 and c1
       const double si_l = __shfl_up_sync(0xffffffffu, si_a.y, 1);  // s_int[c0 - 1] (lane 0: unused face)
-      uq0 = F::prep((lsu[E - 1] + lsu[E]) / (si_l + si_a.x), a.fc);
-      uq1 = F::prep((lsu[E] + lsu[E + 1]) / (si_a.x + si_a.y), a.fc);
+      uq0 = F::prep(qdiv(lsu[E - 1] + lsu[E], si_l + si_a.x), a.fc);
+      uq1 = F::prep(qdiv(lsu[E] + lsu[E + 1], si_a.x + si_a.y), a.fc);
     } else {
       uq0 = F::prep(cur.u_c.x, a.fc);
       uq1 = F::prep(cur.u_c.y, a.fc);
@@ -1354,17 +1359,17 @@ __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_
       const double s_l = __shfl_up_sync(0xffffffffu, s1, 1);
       if (out0 && r >= j0) {
         const int c1 = c0 + 1;
-        const double u0 = c0 == 0 ? ldo(a.u_ref.p, o_c) : (su_l + su0) / (s_l + s0);
+        const double u0 = c0 == 0 ? ldo(a.u_ref.p, o_c) : qdiv(su_l + su0, s_l + s0);
         double v0, v1;
         if (r == 0) {
           const double2 vr = ldo2(a.v_ref.p, o_c);
           v0 = vr.x; v1 = vr.y;
         } else {
-          v0 = (sv_prev0 + sv0) / (s_prev0 + s0);
-          v1 = (sv_prev1 + sv1) / (s_prev1 + s1);
+          v0 = qdiv(sv_prev0 + sv0, s_prev0 + s0);
+          v1 = qdiv(sv_prev1 + sv1, s_prev1 + s1);
         }
         if (out1) {
-          const double u1 = (su0 + su1) / (s0 + s1);
+          const double u1 = qdiv(su0 + su1, s0 + s1);
           sto2(a.s_new.p, o_c, make_double2(s0, s1));
           sto2(a.su_new.p, o_c, make_double2(su0, su1));
           sto2(a.sv_new.p, o_c, make_double2(sv0, sv1));

@@ -26,10 +26,14 @@ Every owned point sees bit-identical inputs and executes the same operations as 
 in tests/test_gpu_distributed.py (in-process sub-domains on one GPU) and the world_size-2
 ``gloo`` test of the exchange logic in tests/test_distributed_cpu.py.
 
-Transport.  One pack kernel per side and phase gathers the slab of all five fields into one
-message (``tb200_halo_pack``); messages travel with ``torch.distributed`` point-to-point ops
-(NCCL over NVLink / NVSwitch on the GPUs, grouped per phase); one unpack kernel per side
-scatters them.  There is no global reduction on the path.
+Transport.  Default on GPUs (``TB200_HALO=p2p``): peer stores over NVLink -- one push launch
+per phase packs the slabs of both sides straight into the neighbours' receive buffers (CUDA IPC
+mappings) and raises their arrival counters, one pull launch waits for the own counters and
+unpacks (``P2PHaloExchange``, csrc/halo.cu); no NCCL call and no host synchronisation on the
+path.  ``TB200_HALO=nccl``: one pack kernel per side and phase gathers the slab of all fields
+into one message (``tb200_halo_pack``); messages travel with ``torch.distributed``
+point-to-point ops (grouped per phase); one unpack kernel per side scatters them.  There is no
+global reduction on the path.
 """
 from __future__ import annotations
 
@@ -258,6 +262,164 @@ def exchange_in_process(exchangers: Sequence[HaloExchange], fields_per_rank: Seq
                 _unpack(fields, ex.message(src, s, len(fields)), s.recv_origin, s.extent, ex.nz)
 
 
+# ------------------------------------------------------------------ peer-to-peer transport
+class P2PHaloExchange(HaloExchange):
+    """The same two-phase plan over NVLink peer stores instead of NCCL messages (csrc/halo.cu,
+    ``tb200_halo_push`` / ``tb200_halo_pull``): a phase is ONE push launch that packs the slabs of
+    both sides straight into the neighbours' receive buffers and raises their arrival counters,
+    and ONE pull launch that waits for the own counters and unpacks -- four launches per exchange,
+    no send buffers, no host synchronisation, capturable in a CUDA graph.
+
+    A rank owns one exportable allocation: per side two receive slots (exchange q uses slot
+    q & 1), then one arrival counter per side (128 bytes apart), then the two per-phase channels
+    (sequence numbers).  ``describe()`` is what the neighbours need (CUDA IPC handle + offsets);
+    ``connect()`` takes the mapped base address and the description of every neighbour.
+    """
+
+    COUNTER_PITCH = 128
+
+    def __init__(self, decomp: Decomposition, rank: int, nz: int, nfields: int, device=None):
+        import ctypes as C
+
+        self.decomp, self.rank, self.nz, self.nfields = decomp, rank, nz, nfields
+        self.plan = [decomp.sides(rank, 0), decomp.sides(rank, 1)]
+        self.send, self.recv = {}, {}
+        self.layout, off = {}, 0
+        for phase in self.plan:
+            for s in phase:
+                slot = nfields * nz * s.extent[0] * s.extent[1]
+                self.layout[s.name] = {"buffer": off, "slot_doubles": slot}
+                off += 2 * slot * 8
+        self.bytes_per_exchange = off // 2
+        off = (off + 127) // 128 * 128
+        for name in self.layout:
+            self.layout[name]["counter"] = off
+            off += self.COUNTER_PITCH
+        self.channel_offset = [off, off + lib.P2P_CHANNEL_BYTES]
+        off += 2 * lib.P2P_CHANNEL_BYTES
+        self.nbytes = off
+        base = C.c_void_p()
+        lib.check(lib.load().tb200_p2p_alloc(self.nbytes, C.byref(base)), "tb200_p2p_alloc")
+        self.base = int(base.value)
+        self.sides_c = [None, None]
+        self._imported = []
+
+    def describe(self):
+        """What a neighbour needs to push into this rank's buffers."""
+        import ctypes as C
+
+        handle = C.create_string_buffer(lib.P2P_HANDLE_BYTES)
+        lib.check(lib.load().tb200_p2p_export(C.c_void_p(self.base), handle), "tb200_p2p_export")
+        return {"rank": self.rank, "handle": handle.raw, "layout": self.layout}
+
+    def connect(self, peers):
+        """``peers``: neighbour rank -> (base address of its allocation as seen from THIS
+        process, its ``layout``)."""
+        for phase, sides in enumerate(self.plan):
+            arr = (lib.HaloSide * max(len(sides), 1))()
+            for m, s in enumerate(sides):
+                pbase, playout = peers[s.neighbour]
+                theirs, mine = playout[_OPPOSITE[s.name]], self.layout[s.name]
+                assert theirs["slot_doubles"] == mine["slot_doubles"], "asymmetric halo plan"
+                h = arr[m]
+                h.remote_buffer = pbase + theirs["buffer"]
+                h.remote_counter = pbase + theirs["counter"]
+                h.local_buffer = self.base + mine["buffer"]
+                h.local_counter = self.base + mine["counter"]
+                h.slot_doubles = mine["slot_doubles"]
+                h.send_origin[:] = list(s.send_origin)
+                h.recv_origin[:] = list(s.recv_origin)
+                h.extent[:] = list(s.extent)
+            self.sides_c[phase] = arr
+
+    def connect_in_process(self, exchangers):
+        """All sub-domains in this process (one GPU): the neighbours' buffers are plain addresses."""
+        self.connect({ex.rank: (ex.base, ex.layout) for ex in exchangers})
+
+    def connect_ipc(self, group=None):
+        """One process per GPU: descriptions travel through ``torch.distributed`` (any backend),
+        neighbours' allocations are mapped with CUDA IPC (peer access over NVLink)."""
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        mine = self.describe()
+        everyone = [None] * dist.get_world_size(group)
+        dist.all_gather_object(everyone, mine, group=group)
+        peers = {}
+        for phase in self.plan:
+            for s in phase:
+                if s.neighbour in peers:
+                    continue
+                d = everyone[s.neighbour]
+                ptr = C.c_void_p()
+                lib.check(lib.load().tb200_p2p_import(d["handle"], C.byref(ptr)), "tb200_p2p_import")
+                self._imported.append(int(ptr.value))
+                peers[s.neighbour] = (int(ptr.value), d["layout"])
+        self.connect(peers)
+        dist.barrier(group)  # nobody pushes before every mapping exists
+
+    def _call(self, fn, what, phase, fields):
+        sides = self.plan[phase]
+        if not sides:
+            return
+        arr, keep = _field_ptrs(fields)
+        lib.check(fn(arr, len(fields), self.sides_c[phase], len(sides),
+                     self.base + self.channel_offset[phase], 0, self.nz, lib.current_stream()), what)
+        del keep
+
+    def push(self, phase, fields):
+        self._call(lib.load().tb200_halo_push, "tb200_halo_push", phase, fields)
+
+    def pull(self, phase, fields):
+        self._call(lib.load().tb200_halo_pull, "tb200_halo_pull", phase, fields)
+
+    def exchange(self, fields: Sequence):
+        assert 1 <= len(fields) <= self.nfields
+        for phase in (0, 1):
+            self.push(phase, fields)
+            self.pull(phase, fields)
+
+    def check(self):
+        """Raise if a pull ever gave up waiting for its peer (device synchronised by the copy)."""
+        import ctypes as C
+
+        for phase in (0, 1):
+            err = C.c_int(0)
+            lib.check(lib.load().tb200_p2p_channel_error(self.base + self.channel_offset[phase], C.byref(err)),
+                      "tb200_p2p_channel_error")
+            if err.value:
+                raise lib.B200Error(f"halo exchange (rank {self.rank}, phase {phase}): a neighbour's slab never "
+                                    "arrived -- the results are invalid")
+
+    def close(self):
+        for ptr in self._imported:
+            lib.load().tb200_p2p_release(ptr)
+        self._imported = []
+        if self.base:
+            lib.load().tb200_p2p_free(self.base)
+            self.base = 0
+
+
+def exchange_in_process_p2p(exchangers: Sequence[P2PHaloExchange], fields_per_rank: Sequence[Sequence]):
+    """All sub-domains in one process on one GPU: every push of a phase is enqueued before the
+    first pull, so no pull ever waits (kernels of one GPU must not wait on one another)."""
+    for phase in (0, 1):
+        for ex, fields in zip(exchangers, fields_per_rank):
+            ex.push(phase, fields)
+        for ex, fields in zip(exchangers, fields_per_rank):
+            ex.pull(phase, fields)
+
+
+def halo_transport():
+    """``TB200_HALO=p2p`` (default on GPUs) | ``nccl``: peer stores over NVLink or
+    ``torch.distributed`` point-to-point messages."""
+    v = os.environ.get("TB200_HALO", "p2p").lower()
+    if v not in ("p2p", "nccl"):
+        raise ValueError(f"TB200_HALO must be p2p or nccl, got {v!r}")
+    return v
+
+
 # ------------------------------------------------------------------ the decomposed dry core
 P, EXN, H = ("air_pressure_on_interface_levels", "exner_function_on_interface_levels",
              "height_on_interface_levels")
@@ -271,7 +433,7 @@ class SubdomainDryCore:
     def __init__(self, decomp: Decomposition, rank: int, nz: int, *, domain_x=(-176.0, 176.0),
                  domain_y=(-176.0, 176.0), nb=3, nr=6, flux="fifth_order_upwind",
                  scheme="rk3ws_si", damp_depth=15, damp_max=5e-4, dt_seconds=5.0,
-                 mountain=(500.0, 50.0, 50.0), topo_seconds=1800.0, device=None):
+                 mountain=(500.0, 50.0, 50.0), topo_seconds=1800.0, device=None, transport="nccl"):
         import tasmania_b200 as tb
         from tasmania_b200.boundary import Relaxed
         from tasmania_b200.grid import (Grid, Topography, gaussian_profile,
@@ -329,7 +491,11 @@ class SubdomainDryCore:
         self.diag = IsentropicDiagnostics(grid, storage_options=so)
         self.spare = {n: tb.zeros(self.dyc.storage_shape, device=device) for n in self.out_names}
         dev = state[S].t.device
-        self.halo = HaloExchange(decomp, rank, nz, 5, dev)
+        self.transport = transport if dev.type == "cuda" else "nccl"
+        if self.transport == "p2p":
+            self.halo = P2PHaloExchange(decomp, rank, nz, 5, dev)  # connected by the owner of the run
+        else:
+            self.halo = HaloExchange(decomp, rank, nz, 5, dev)
         self.u_faces, self.v_faces = decomp.seam_faces(rank)
         self.nstep = 0
 
@@ -425,14 +591,18 @@ class DecomposedDryRun:
     owns ``nx x ny x nz`` points; the global domain grows with the process grid so that the
     grid spacing -- and with it the physics per point -- stays the same (2.2 km, config 2)."""
 
-    def __init__(self, nx, ny, nz, rank, world, device=None, overlap=False):
+    def __init__(self, nx, ny, nz, rank, world, device=None, overlap=False, transport=None, **kwargs):
         px, py = process_grid(world)
         self.decomposition = f"{px}x{py}"
         self.decomp = Decomposition(nx * px, ny * py, px, py)
         # config 2's grid spacing (2.2 km) on the global grid: dt = 5 s stays stable at any size
         hx, hy = 1.1 * (nx * px - 1), 1.1 * (ny * py - 1)
-        self.sub = SubdomainDryCore(self.decomp, rank, nz, domain_x=(-hx, hx), domain_y=(-hy, hy),
-                                    device=device)
+        self.domain_x, self.domain_y = (-hx, hx), (-hy, hy)
+        self.transport = (transport or halo_transport()) if world > 1 else "nccl"
+        self.sub = SubdomainDryCore(self.decomp, rank, nz, domain_x=self.domain_x, domain_y=self.domain_y,
+                                    device=device, transport=self.transport, **kwargs)
+        if self.transport == "p2p":
+            self.sub.halo.connect_ipc()
         self.nx, self.ny, self.nz = nx, ny, nz
         self.names, self.out_names = self.sub.names, self.sub.out_names
         self.dyc = self.sub.dyc
@@ -475,10 +645,14 @@ class InProcessDecomposedRun:
     """All sub-domains of a decomposition in ONE process on one device -- the bitwise-parity
     harness of the decomposition (and a way to run a decomposed case without several GPUs)."""
 
-    def __init__(self, nx_global, ny_global, nz, px, py, device=None, **kwargs):
+    def __init__(self, nx_global, ny_global, nz, px, py, device=None, transport="nccl", **kwargs):
         self.decomp = Decomposition(nx_global, ny_global, px, py)
-        self.subs = [SubdomainDryCore(self.decomp, r, nz, device=device, **kwargs)
+        self.subs = [SubdomainDryCore(self.decomp, r, nz, device=device, transport=transport, **kwargs)
                      for r in range(px * py)]
+        self.transport = self.subs[0].transport
+        if self.transport == "p2p":
+            for s in self.subs:
+                s.halo.connect_in_process([t.halo for t in self.subs])
 
     def step(self):
         iters = [s.begin_step() for s in self.subs]
@@ -486,8 +660,8 @@ class InProcessDecomposedRun:
         for stage in range(self.subs[0].dyc.stages):
             for r, it in enumerate(iters):
                 outs[r] = next(it)[1]
-            exchange_in_process([s.halo for s in self.subs],
-                                [s.exchange_fields(o, stage) for s, o in zip(self.subs, outs)])
+            (exchange_in_process_p2p if self.transport == "p2p" else exchange_in_process)(
+                [s.halo for s in self.subs], [s.exchange_fields(o, stage) for s, o in zip(self.subs, outs)])
             for s, o in zip(self.subs, outs):
                 s.fix_seam_velocities(o, stage)
         for it in iters:  # exhaust the generators (sets the time label)

@@ -44,6 +44,17 @@ class StageCfg(C.Structure):
     ]
 
 
+class HaloSide(C.Structure):
+    """``tb200_halo_side``"""
+
+    _fields_ = [("remote_buffer", C.c_void_p), ("remote_counter", C.c_void_p),
+                ("local_buffer", C.c_void_p), ("local_counter", C.c_void_p),
+                ("slot_doubles", C.c_int64),
+                ("send_origin", C.c_int32 * 2), ("recv_origin", C.c_int32 * 2), ("extent", C.c_int32 * 2)]
+
+
+P2P_HANDLE_BYTES, P2P_CHANNEL_BYTES = 64, 32
+
 FLUX_SCHEMES = {"upwind": 0, "centered": 1, "third_order_upwind": 2, "fifth_order_upwind": 3}
 ELEMENTWISE_OPS = {
     "copy": 0, "copychange": 1, "abs": 2, "add": 3, "addsub": 4, "clip": 5, "fma": 6,
@@ -99,6 +110,15 @@ SIGNATURES = {
     "tb200_vertical_advection_step": [_I, _I, _F, _I, _FPP, _FPP, _FPP, _D, _D, _I3, _I3, _V],
     "tb200_halo_pack": [_FPP, _I, C.c_void_p, _I3, _I3, _V],
     "tb200_halo_unpack": [_FPP, _I, C.c_void_p, _I3, _I3, _V],
+    "tb200_halo_push": [_FPP, _I, C.c_void_p, _I, _V, _I, _I, _V],
+    "tb200_halo_pull": [_FPP, _I, C.c_void_p, _I, _V, _I, _I, _V],
+    "tb200_p2p_alloc": [C.c_size_t, C.POINTER(C.c_void_p)],
+    "tb200_p2p_free": [_V],
+    "tb200_p2p_export": [_V, C.c_char_p],
+    "tb200_p2p_import": [C.c_char_p, C.POINTER(C.c_void_p)],
+    "tb200_p2p_release": [_V],
+    "tb200_p2p_channel_error": [_V, C.POINTER(C.c_int)],
+    "tb200_selftest_division": [C.c_uint64, C.c_uint64, _V, _V],
 }
 
 KESSLER_FLAGS = {"p_on_interfaces": 1, "rain_evaporation": 2, "ow_qc": 4, "ow_qr": 8, "ow_qv": 16,

@@ -74,14 +74,17 @@ class HostStreamedDryCore:
             self.uploaded[b].record()
         main.wait_event(self.uploaded[b])
         main.wait_event(self.out_free[b])     # download i-2 has finished reading this output set
-        self.nstep += 1
-        self.dyc.update_topography(self.nstep * self.dt)
         state = dict(dev["in"])
         state["time"] = self.time
         if self.prognostic_only:
-            # Montgomery potential of the uploaded s (and p, exn, h with it); the velocities of
-            # stage 0 are diagnosed inside the kernels (u, v of this set are never read)
+            # Montgomery potential of the uploaded s (and p, exn, h with it) over the topography
+            # of the uploaded state's own time, i.e. BEFORE the topography moves on to this
+            # step's; the velocities of stage 0 are diagnosed inside the kernels (u, v of this
+            # set are never read)
             self.diag.get_diagnostic_variables(state[S], self.pt, state[P], state[EXN], state[MTG], state[H])
+        self.nstep += 1
+        self.dyc.update_topography(self.nstep * self.dt)
+        if self.prognostic_only:
             saved = self.dyc.derive_stage0_velocities
             self.dyc.derive_stage0_velocities = True
             try:

@@ -130,3 +130,56 @@ def test_exchange_two_gloo_ranks():
 
     shapes = [(18, 9, 2, 1), (9, 18, 1, 2)]
     mp.spawn(_gloo_worker, args=(2, _free_port(), shapes), nprocs=2, join=True)
+
+
+# ------------------------------------------------------------------ peer-to-peer transport: host logic
+@pytest.mark.parametrize("px,py", [(2, 1), (2, 2), (4, 2), (3, 3)])
+def test_p2p_exchange_descriptors_pair_up(monkeypatch, px, py):
+    """The tb200_halo_side descriptors of the NVLink transport, built with fake base addresses
+    (no GPU): what a rank pushes towards a side lands in the OPPOSITE side's receive buffer and
+    counter of exactly that neighbour, slot sizes and extents agree, and the geometry of the slab
+    is the one of the message-based exchange."""
+    from tasmania_b200 import distributed as D
+    from tasmania_b200 import lib
+
+    class FakeLib:
+        count = 0
+
+        def tb200_p2p_alloc(self, nbytes, ref):
+            FakeLib.count += 1
+            ref._obj.value = 0x40000000 * FakeLib.count
+            return 0
+
+    monkeypatch.setattr(lib, "_lib", FakeLib())
+    nz, nf = 6, 5
+    d = Decomposition(24 * px, 20 * py, px, py)
+    ex = [D.P2PHaloExchange(d, r, nz, nf) for r in range(d.world)]
+    for e in ex:
+        e.connect_in_process(ex)
+    seen = set()
+    for e in ex:
+        spans = []
+        for phase, sides in enumerate(e.plan):
+            assert [s.name for s in sides] == [s.name for s in d.sides(e.rank, phase)]
+            for m, s in enumerate(sides):
+                h, peer, opp = e.sides_c[phase][m], ex[s.neighbour], D._OPPOSITE[s.name]
+                assert h.remote_buffer == peer.base + peer.layout[opp]["buffer"]
+                assert h.remote_counter == peer.base + peer.layout[opp]["counter"]
+                assert h.local_buffer == e.base + e.layout[s.name]["buffer"]
+                assert h.local_counter == e.base + e.layout[s.name]["counter"]
+                assert h.slot_doubles == nf * nz * s.extent[0] * s.extent[1] == peer.layout[opp]["slot_doubles"]
+                assert (tuple(h.send_origin), tuple(h.recv_origin), tuple(h.extent)) == \
+                    (s.send_origin, s.recv_origin, s.extent)
+                # the slab sent is the window the neighbour receives (global indices)
+                peer_side = [t for t in d.sides(s.neighbour, phase) if t.name == opp][0]
+                g0, g1 = d.local(e.rank), d.local(s.neighbour)
+                assert g0[0] + s.send_origin[0] == g1[0] + peer_side.recv_origin[0]
+                assert g0[2] + s.send_origin[1] == g1[2] + peer_side.recv_origin[1]
+                assert (h.remote_buffer, h.remote_counter) not in seen  # one writer per buffer
+                seen.add((h.remote_buffer, h.remote_counter))
+                spans.append((e.layout[s.name]["buffer"], e.layout[s.name]["buffer"] + 16 * h.slot_doubles))
+                assert e.layout[s.name]["counter"] % 8 == 0
+        spans.sort()
+        assert all(a[1] <= b[0] for a, b in zip(spans[:-1], spans[1:]))  # two slots each, no overlap
+        assert spans[-1][1] <= min(e.layout[n]["counter"] for n in e.layout)
+        assert e.channel_offset[1] + lib.P2P_CHANNEL_BYTES <= e.nbytes

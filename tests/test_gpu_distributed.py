@@ -35,6 +35,59 @@ def test_decomposed_equals_single_device_bitwise(px, py):
     assert np.abs(single.gather(SV)).max() > 0.0
 
 
+@pytest.mark.parametrize("px,py", [(2, 1), (2, 2), (3, 2)])
+def test_decomposed_p2p_transport_equals_single_device_bitwise(px, py):
+    """The NVLink peer-store transport (tb200_halo_push / tb200_halo_pull) with all sub-domains in
+    one process: every push of a phase is enqueued before the first pull."""
+    from tasmania_b200.distributed import InProcessDecomposedRun
+
+    NX, NY, nz = 41, 37, 9
+    kw = dict(damp_depth=4, topo_seconds=20.0)
+    single = InProcessDecomposedRun(NX, NY, nz, 1, 1, **kw)
+    multi = InProcessDecomposedRun(NX, NY, nz, px, py, transport="p2p", **kw)
+    assert multi.transport == "p2p"
+    for _ in range(5):  # both slots of every receive buffer are reused
+        single.step()
+        multi.step()
+    for s in multi.subs:
+        s.halo.check()
+    for name in _fields():
+        np.testing.assert_array_equal(single.gather(name), multi.gather(name), err_msg=name)
+
+
+def test_p2p_push_pull_roundtrip_and_slots():
+    """Two 'ranks' side by side in one process: what rank 0 pushes east is what rank 1 pulls from
+    the west, exchange after exchange (slot q & 1), for 3 and for 5 fields."""
+    import tasmania_b200 as tb
+    from tasmania_b200.distributed import Decomposition, P2PHaloExchange, exchange_in_process_p2p
+
+    nz = 5
+    d = Decomposition(40, 21, 2, 1)
+    ex = [P2PHaloExchange(d, r, nz, 5) for r in range(2)]
+    for e in ex:
+        e.connect_in_process(ex)
+    rng = np.random.default_rng(11)
+    for it, nf in enumerate((5, 3, 5, 3, 3)):
+        src, fields = [], []
+        for r in range(2):
+            nxl, nyl = d.local_shape(r)
+            arrs = [rng.standard_normal((nxl + 1, nyl + 1, nz + 1)) for _ in range(nf)]
+            src.append(arrs)
+            fields.append([tb.as_storage(a) for a in arrs])
+        exchange_in_process_p2p(ex, fields)
+        got0 = [tb.to_numpy(f) for f in fields[0]]
+        got1 = [tb.to_numpy(f) for f in fields[1]]
+        h = d.halo
+        n0 = d.local_shape(0)[0]
+        for n in range(nf):
+            # rank 1's west halo = rank 0's last owned columns, and vice versa
+            np.testing.assert_array_equal(got1[n][0:h, :21, :nz], src[0][n][n0 - 2 * h:n0 - h, :21, :nz])
+            np.testing.assert_array_equal(got0[n][n0 - h:n0, :21, :nz], src[1][n][h:2 * h, :21, :nz])
+    for e in ex:
+        e.check()
+        e.close()
+
+
 def test_halo_pack_unpack_roundtrip():
     import torch
 
@@ -76,7 +129,8 @@ def test_two_rank_nccl_run_equals_single_device_bitwise():
         pytest.skip("needs >= 2 GPUs")
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for port, extra in ((29531, []), (29532, ["--overlap"])):
+    for port, extra in ((29531, ["--transport", "p2p"]), (29532, ["--transport", "p2p", "--overlap"]),
+                        (29533, ["--transport", "nccl"]), (29534, ["--transport", "nccl", "--overlap"])):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                "--master-addr", "127.0.0.1", "--master-port", str(port),
                os.path.join(root, "tests", "mgpu_check.py"), *extra]
