@@ -550,9 +550,10 @@ def run_c4(args):
 #   scans      s_pre -> mtg_new = 16
 #   momentum   stage 0: s, s_pre, mtg_now, mtg_new, u, v, su, sv -> su, sv (+ s in the relaxation band
 #              / damping layer only) = 80; stage 1: s_now, s_int, s_pre, mtg_now, mtg_new, su_now, su_int,
-#              sv_now, sv_int -> su, sv = 88; stage 2: the same reads -> s, su, sv, u, v = 112
+#              sv_now, sv_int -> su, sv = 88; stage 2: the same (u, v of the step's final state come from
+#              one pass of tb200_velocity_components: s, su, sv -> u, v = 40 B/pt, timed in `other_kernels`)
 KERNEL_NAMES = ("s_step (stage_a_kernel)", "column_scan (stage_b_kernel)", "momentum (stage_mv2_kernel)")
-KERNEL_BYTES_PER_POINT_LAZY = {0: (32, 16, 80), 1: (40, 16, 88), 2: (40, 16, 112)}
+KERNEL_BYTES_PER_POINT_LAZY = {0: (32, 16, 80), 1: (40, 16, 88), 2: (40, 16, 88)}
 KERNEL_BYTES_PER_POINT_EAGER = {0: (32, 16, 104), 1: (40, 16, 120), 2: (40, 16, 120)}
 NCU_KERNEL_KEYS = ("stage_a_kernel", "stage_b_kernel", "stage_mv2_kernel")
 # DRAM traffic per launch: read from the ncu --set full capture of THIS round's build of the same
@@ -630,6 +631,32 @@ def kernel_roofline(run, args):
         traffic, src = ncu_traffic(NCU_KERNEL_KEYS[ki])
         if traffic is not None and (run.nx, run.ny, run.nz) == WORKLOADS["c5"]:
             kernels[n]["traffic"], kernels[n]["traffic_source"] = traffic, src
+    # the two once-per-step kernels outside the stages, timed alone on the run's fields (0.56 GB
+    # each: far larger than L2): velocity diagnosis of the final state (s, su, sv -> u, v = 40 B/pt)
+    # and the diagnostics refresh (s -> p, exn, mtg, h = 40 B/pt)
+    other = {}
+    st = run.state
+    diag = run.diag if hasattr(run, "diag") else run.sub.diag
+    pt = run.pt if hasattr(run, "pt") else run.sub.pt
+    P, EXN, H, MTG, S = ("air_pressure_on_interface_levels", "exner_function_on_interface_levels",
+                         "height_on_interface_levels", "montgomery_potential", "air_isentropic_density")
+    calls = {"diagnostics refresh (diag_column_kernel)":
+             lambda: diag.get_diagnostic_variables(st[S], pt, st[P], st[EXN], st[MTG], st[H])}
+    if dyc.lazy_velocities:
+        calls["velocity diagnosis (velocity_xy_kernel)"] = lambda: dyc.diagnose_velocities(st)
+    for name, fn in calls.items():
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        gbs = 40 * pts / (ms * 1e-3) / 1e9
+        other[name] = {"ms_per_launch": ms, "achieved": gbs, "frac": gbs / peak,
+                       "algorithmic_bytes_per_launch": 40 * pts, "launches_per_step": 1}
     dom = max(kernels, key=lambda n: kernels[n]["ms_per_launch"])
     stage_ms = float(sum(k["ms_per_launch"] for k in kernels.values()))
     stage_gbs = BYTES_PER_POINT_STAGE * pts / (stage_ms * 1e-3) / 1e9
@@ -640,7 +667,7 @@ def kernel_roofline(run, args):
             "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"],
             "launches_averaged": f"the {nst} RK stages of a step (their compulsory traffic differs: "
                                  "intermediate stages neither read nor write u, v)",
-            "kernels": kernels,
+            "kernels": kernels, "other_kernels": other,
             "fused_stage": {"ms": stage_ms, "algorithmic_bytes": BYTES_PER_POINT_STAGE * pts,
                             "achieved": stage_gbs, "frac": stage_gbs / peak,
                             "note": "112 B/pt (SURVEY.md 8d) over the three kernels of one RK stage, mean of the stages"}}
@@ -747,7 +774,7 @@ def end_to_end(run, args, world, barrier, distributed):
     diag = run.diag if hasattr(run, "diag") else run.sub.diag
     pt = run.pt if hasattr(run, "pt") else run.sub.pt
     dt = run.dt if hasattr(run, "dt") else run.sub.dt
-    pipe = HostStreamedDryCore(run.dyc, diag, pt, dt)
+    pipe = HostStreamedDryCore(run.dyc, diag, pt, dt, prognostic_only=bool(run.dyc.lazy_velocities))
     host_in = pipe.host_buffers(pipe.names_in)
     for n in pipe.names_in:
         host_in[n].copy_(flat(run.state[n]))

@@ -129,6 +129,18 @@ int tb200_damping(const tb200_field *in_phi_now, const tb200_field *in_phi_new,
 int tb200_velocity(int axis, const tb200_field *in_d, const tb200_field *in_dw,
                    tb200_field *out_w, int staggering, const int32_t origin[3],
                    const int32_t domain[3], void *stream);
+/* Both staggered velocity components of a state and their outermost faces in one pass over
+ * [0, nx) x [0, ny) x [0, nz): HorizontalVelocity.get_velocity_components
+ * (src/tasmania/dwarfs/diagnostics.py:L219-L272, staggering=True) followed by
+ * Relaxed.set_outermost_layers_x / _y (src/tasmania/domain/subclasses/horizontal_boundaries/
+ * relaxed.py:L161-L191): u(i) = (du(i-1) + du(i)) / (d(i-1) + d(i)) for 0 < i < nx, u(0), u(nx)
+ * from u_ref; likewise v along j.  u_ref / v_ref may be NULL (outermost faces untouched).
+ * The five fields must share one b200 storage geometry (else TB200_ERR_LAYOUT: use
+ * tb200_velocity + tb200_set_outermost_layers). */
+int tb200_velocity_components(const tb200_field *in_d, const tb200_field *in_du,
+                              const tb200_field *in_dv, tb200_field *out_u, tb200_field *out_v,
+                              const tb200_field *u_ref, const tb200_field *v_ref, int nx, int ny,
+                              int nz, void *stream);
 int tb200_momenta(const tb200_field *in_d, const tb200_field *in_u, const tb200_field *in_v,
                   tb200_field *out_du, tb200_field *out_dv, int staggering,
                   const int32_t origin[3], const int32_t domain[3], void *stream);
@@ -409,6 +421,11 @@ int tb200_isentropic_stage_dry(
  * {s-step kernel (A, or S), column-scan kernel (B; 0 when S does both), momentum kernel}. */
 int tb200_stage_profile(int enable);
 int tb200_stage_profile_read(double ms[3]);
+/* 1 if the stage kernels selected by the process environment honour derive_uv_in / skip_uv_out
+ * and scratch_s == s_new for columns of nz layers (the default path), 0 if an earlier kernel
+ * variant is forced (TB200_S_IMPL, TB200_MV_IMPL, TB200_STAGE_IMPL) or nz > 64: a host then
+ * passes 0 for both flags and a separate scratch_s. */
+int tb200_stage_lazy_velocities(int nz);
 
 /* ---- halo exchange support (2-D domain decomposition) ------------
  * pack/unpack a box of a field into/from a contiguous buffer (i fastest). */

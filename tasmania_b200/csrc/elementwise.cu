@@ -469,6 +469,131 @@ extern "C" int tb200_velocity(int axis, const tb200_field *in_d, const tb200_fie
                     });
 }
 
+// Both velocity components of a stage output and their outermost faces in ONE pass
+// (HorizontalVelocity.get_velocity_components, dwarfs/diagnostics.py:L219-L272, followed by
+// Relaxed.set_outermost_layers_x / _y, relaxed.py:L161-L191): reads d, du, dv once (24 B/pt),
+// writes u, v (16 B/pt).  The fused dry stage leaves the velocities of every stage to its successor
+// (derive_uv_in); this kernel diagnoses them ONCE per time step, for the state the step returns.
+// A lane owns an aligned pair of columns (LDG.128 / STG.128) and marches along j over a strip,
+// carrying the previous row's d, dv; the column to the left comes from the neighbouring lane
+// (lane 0: one scalar load); next row requested one row ahead, its lines pulled DRAM -> L2 four
+// rows earlier.  Divisions through qdiv (common.cuh): same bits as `/`.
+namespace {
+constexpr int VXY_PF = 4;
+__global__ void __launch_bounds__(128, 5) velocity_xy_kernel(View d, View du, View dv, View u, View v,
+                                                          View ur, View vr, int nx, int ny, int lj) {
+  const int lane = threadIdx.x & 31;
+  const int w0 = 2 * (blockIdx.x * blockDim.x + (threadIdx.x & ~31));  // first column of the warp
+  if (w0 >= nx) return;  // warp-uniform
+  const int c0 = w0 + 2 * lane;
+  const int pmax = (nx - 1) & ~1;           // last aligned pair that starts inside the row
+  const int cm = min(c0, pmax);             // lanes beyond the row repeat its last pair (masked)
+  const int cl = max(cm - 1, 0);            // lane 0's left neighbour
+  const bool in0 = c0 < nx, in1 = c0 + 1 < nx;
+  const int k = blockIdx.z;
+  const int j0 = blockIdx.y * lj, j1 = min(j0 + lj, ny);
+  const long long s1 = d.s1, pl = (long long)k * d.s2;
+  auto ld2 = [](const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); };
+  const double *pd = d.p + pl + cm, *pdu = du.p + pl + cm, *pdv = dv.p + pl + cm;
+  double2 dp = make_double2(1.0, 1.0), dvp = make_double2(0.0, 0.0);  // row j - 1 (unused at j == 0)
+  if (j0 > 0) {
+    dp = ld2(pd + (j0 - 1) * s1);
+    dvp = ld2(pdv + (j0 - 1) * s1);
+  }
+  double2 nd = ld2(pd + j0 * s1), ndu = ld2(pdu + j0 * s1), ndv = ld2(pdv + j0 * s1);
+  double nl_d = 1.0, nl_du = 0.0;
+  if (lane == 0 && c0 > 0) {
+    nl_d = __ldg(d.p + pl + cl + j0 * s1);
+    nl_du = __ldg(du.p + pl + cl + j0 * s1);
+  }
+  for (int j = j0; j < j1; ++j) {
+    const double2 cd = nd, cdu = ndu, cdv = ndv;
+    const double ld_ = nl_d, ldu_ = nl_du;
+    const int jn = min(j + 1, ny - 1);  // the last iteration re-requests its own row (no overrun)
+    nd = ld2(pd + jn * s1);
+    ndu = ld2(pdu + jn * s1);
+    ndv = ld2(pdv + jn * s1);
+    if (lane == 0 && c0 > 0) {
+      nl_d = __ldg(d.p + pl + cl + jn * s1);
+      nl_du = __ldg(du.p + pl + cl + jn * s1);
+    }
+    if (j + VXY_PF < j1 && (lane & 7) == 0) {  // one request per 128-byte line and stream
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + (j + VXY_PF) * s1));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pdu + (j + VXY_PF) * s1));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pdv + (j + VXY_PF) * s1));
+    }
+    // left neighbours: the previous lane's second column
+    double dl = __shfl_up_sync(0xffffffffu, cd.y, 1), dul = __shfl_up_sync(0xffffffffu, cdu.y, 1);
+    if (lane == 0) { dl = ld_; dul = ldu_; }
+    double u0, u1, v0, v1;
+    if (c0 == 0) {
+      u0 = ur.ok() ? ur.ld(0, j, k) : u.ld(0, j, k);
+    } else {
+      u0 = qdiv(dul + cdu.x, dl + cd.x);
+    }
+    u1 = qdiv(cdu.x + cdu.y, cd.x + cd.y);
+    if (j == 0) {
+      v0 = vr.ok() ? vr.ld(min(c0, nx - 1), 0, k) : v.ld(min(c0, nx - 1), 0, k);
+      v1 = vr.ok() ? vr.ld(min(c0 + 1, nx - 1), 0, k) : v.ld(min(c0 + 1, nx - 1), 0, k);
+    } else {
+      v0 = qdiv(dvp.x + cdv.x, dp.x + cd.x);
+      v1 = qdiv(dvp.y + cdv.y, dp.y + cd.y);
+    }
+    double *pu = u.p + pl + c0 + j * s1, *pv = v.p + pl + c0 + j * s1;
+    if (in1) {
+      *reinterpret_cast<double2 *>(pu) = make_double2(u0, u1);
+      *reinterpret_cast<double2 *>(pv) = make_double2(v0, v1);
+      if (c0 + 1 == nx - 1 && ur.ok()) pu[2] = ur.ld(nx, j, k);
+      if (j == ny - 1 && vr.ok()) {
+        pv[s1] = vr.ld(c0, ny, k);
+        pv[s1 + 1] = vr.ld(c0 + 1, ny, k);
+      }
+    } else if (in0) {  // the last column of an odd-sized row
+      pu[0] = u0;
+      pv[0] = v0;
+      if (ur.ok()) pu[1] = ur.ld(nx, j, k);
+      if (j == ny - 1 && vr.ok()) pv[s1] = vr.ld(c0, ny, k);
+    }
+    dp = cd;
+    dvp = cdv;
+  }
+}
+}  // namespace
+
+extern "C" int tb200_velocity_components(const tb200_field *in_d, const tb200_field *in_du,
+                                         const tb200_field *in_dv, tb200_field *out_u,
+                                         tb200_field *out_v, const tb200_field *u_ref,
+                                         const tb200_field *v_ref, int nx, int ny, int nz,
+                                         void *stream) {
+  View d = view(in_d), du = view(in_du), dv = view(in_dv), u = view(out_u), v = view(out_v);
+  View ur = view(u_ref), vr = view(v_ref);
+  TB200_REQUIRE(nx >= 2 && ny >= 2 && nz >= 1, "velocity_components: need nx, ny >= 2, nz >= 1");
+  const int32_t o[3] = {0, 0, 0}, m[3] = {nx, ny, nz}, mu[3] = {nx + 1, ny, nz}, mv[3] = {nx, ny + 1, nz};
+  TB200_REQUIRE(box_inside(d, o, m) && box_inside(du, o, m) && box_inside(dv, o, m) &&
+                    box_inside(u, o, mu) && box_inside(v, o, mv),
+                "velocity_components: box outside storage");
+  TB200_REQUIRE((!ur.ok() || box_inside(ur, o, mu)) && (!vr.ok() || box_inside(vr, o, mv)),
+                "velocity_components: reference velocities too small");
+  const View *all[] = {&d, &du, &dv, &u, &v};
+  for (const View *f : all) {
+    if (f->s0 != 1 || f->s1 != d.s1 || f->s2 != d.s2 || (f->s1 & 1) != 0 || (f->s2 & 1) != 0 ||
+        (reinterpret_cast<uintptr_t>(f->p) & 15) != 0 || f->s1 < nx + 2) {
+      set_error("velocity_components: the five fields must share one b200 storage geometry (unit i-stride, "
+                "equal even pitches with two spare columns, 16-byte aligned)");
+      return TB200_ERR_LAYOUT;
+    }
+  }
+  const int warps_x = (nx + 63) / 64;
+  const int wpb = warps_x >= 4 ? 4 : warps_x;  // warps per block, side by side
+  const int gx = (warps_x + wpb - 1) / wpb;
+  int lj = 64;
+  if ((long long)gx * ((ny + 63) / 64) * nz < 148 * 4) lj = 8;
+  dim3 grid(gx, (ny + lj - 1) / lj, nz);
+  velocity_xy_kernel<<<grid, 32 * wpb, 0, static_cast<cudaStream_t>(stream)>>>(d, du, dv, u, v, ur, vr, nx,
+                                                                                 ny, lj);
+  return check_launch("velocity_components");
+}
+
 extern "C" int tb200_momenta(const tb200_field *in_d, const tb200_field *in_u,
                              const tb200_field *in_v, tb200_field *out_du,
                              tb200_field *out_dv, int staggering, const int32_t origin[3],

@@ -191,8 +191,14 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     fy = F::eval_v(F::prep(ldo(a.v_int.p, o_cc), a.fc), ws);
   }
 
+  // Everything row r needs from memory is requested during row r-1: the first-touch streams AND
+  // the x-neighbours of s_int (lines this warp pulled into L1 E rows earlier, but an L1 miss on a
+  // load that is consumed at once stalls the warp for an L2 round trip: 51 % of kernel A's stall
+  // samples were on the first DADD of the x-flux, profiles/README.md round 2)
   struct Row {
     double s_w, v_n, u_c, s_now, gam;  // DERIVE: v_n = sv_int at row r+1, u_c = su_int at row r
+    double xn[NW];                     // s_int at row r, columns cc-E .. cc+E-1 (entry E unused)
+    double su_l;                       // DERIVE: su_int at row r, column cc-1
   };
   auto load_row = [&](unsigned occ, unsigned ocm, unsigned og) {
     Row L;
@@ -201,6 +207,9 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     L.u_c = ldo(DERIVE ? a.su_int.p : a.u_int.p, occ);
     L.s_now = ldo(a.s_now.p, ocm);
     L.gam = ldo(a.gamma.p, og);
+#pragma unroll
+    for (int m = 0; m < NW; ++m) L.xn[m] = m == E ? 0.0 : ldo(a.s_int.p, occ + (unsigned)((m - E) * 8));
+    L.su_l = DERIVE ? ldo(a.su_int.p, occ - 8u) : 0.0;
     return L;
   };
   Row nxt = load_row(o_cc, o_cm, o_g);
@@ -225,17 +234,13 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     }
     const double fy_p = F::eval_v(vq, ws);
     double xs[NW];
-    {
-      const double *ps = ptr_at(a.s_int.p, o_cc);
 #pragma unroll
-      for (int m = 0; m < NW; ++m) xs[m] = m == E ? ws[E - 1] : __ldg(ps + (m - E));
-    }
+    for (int m = 0; m < NW; ++m) xs[m] = m == E ? ws[E - 1] : cur.xn[m];
     double uq;
     if (DERIVE) {  // u at the left face of the column: (su[c-1] + su[c]) / (s[c-1] + s[c])
       // (the left column from L1 like the s_int neighbours: a shuffle would hand over the
       // CLAMPED column of a lane next to the domain edge)
-      const double su_l = ldo(a.su_int.p, o_cc - 8u);
-      uq = F::prep(qdiv(su_l + cur.u_c, xs[E - 1] + xs[E]), a.fc);
+      uq = F::prep(qdiv(cur.su_l + cur.u_c, xs[E - 1] + xs[E]), a.fc);
     } else {
       uq = F::prep(cur.u_c, a.fc);
     }
@@ -1666,6 +1671,14 @@ bool covers(const View &v, int ni, int nj, int nk) {
 }
 
 }  // namespace
+
+// Do the kernels selected by the process environment honour derive_uv_in / skip_uv_out and the
+// in-place s (scratch_s == s_new)?  1 on the default path (kernels A + B + two-column momentum
+// kernel, columns of at most 64 layers), 0 when TB200_S_IMPL / TB200_MV_IMPL / TB200_STAGE_IMPL
+// select an earlier variant -- a host then keeps the reference's data flow.
+extern "C" int tb200_stage_lazy_velocities(int nz) {
+  return s_impl() != 0 && nz <= 64 && stage_impl() == 0 && mv_impl() == 2 ? 1 : 0;
+}
 
 extern "C" int tb200_stage_profile(int enable) {
   if (enable && g_prof.ev[0] == nullptr) {

@@ -501,9 +501,10 @@ class SubdomainDryCore:
 
     # ---- pieces of a step (driven stage by stage so that sub-domains can interleave)
     def velocities_written(self, stage):
-        """Does this stage's output hold u, v?  (Intermediate stages of the fused core do not
-        write them: their successor re-diagnoses them from the exchanged s, su, sv.)"""
-        return not self.dyc.lazy_velocities or stage is None or stage == self.dyc.stages - 1
+        """Does the stage kernel write u, v?  (With lazy velocities no stage does: a successor
+        re-diagnoses them from the exchanged s, su, sv, and the step's final state gets them from
+        one pass over the exchanged fields.)"""
+        return not self.dyc.lazy_velocities
 
     def exchange_fields(self, out, stage=None):
         names = (self.S, self.SU, self.SV, self.U, self.V) if self.velocities_written(stage) \
@@ -511,9 +512,13 @@ class SubdomainDryCore:
         return [out[n] for n in names]
 
     def fix_seam_velocities(self, out, stage=None):
-        """u on the faces between owned and halo columns, v likewise in y, from the exchanged
-        s, su, sv (dwarfs/diagnostics.py:L219-L272, same formula as the fused kernel)."""
-        if not self.velocities_written(stage):
+        """After the exchange.  Lazy velocities: u, v of the step's final state over the whole
+        local grid, halos included, from the exchanged s, su, sv.  Otherwise: u on the faces
+        between owned and halo columns, v likewise in y, which the fused kernel computed from
+        not-yet-exchanged momenta (dwarfs/diagnostics.py:L219-L272, same formula)."""
+        if self.dyc.lazy_velocities:
+            if stage is None or stage == self.dyc.stages - 1:
+                self.dyc.diagnose_velocities(out)
             return
         vc = self.dyc._velocity_components
         for i in self.u_faces:

@@ -17,6 +17,8 @@ orchestration that stays in tasmania).  Two execution paths produce the same num
 """
 from __future__ import annotations
 
+import os
+
 
 import numpy as np
 
@@ -275,7 +277,9 @@ class IsentropicDynamicalCore(StencilFactory):
         self._fused = fusable if fused is None else bool(fused)
         # fused path only: intermediate RK stages neither write nor read u, v (see _stage_fused);
         # set to False to get every stage's velocities like the reference's stage_array_call
-        self.lazy_velocities = True
+        # (TB200_LAZY_UV=0 or an earlier kernel variant forced by the environment: the reference's flow)
+        self.lazy_velocities = bool(self._fused and os.environ.get("TB200_LAZY_UV", "1") != "0"
+                                    and lib.load().tb200_stage_lazy_velocities(grid.nz))
         # ... and stage 0 too re-diagnoses them instead of reading the state's u, v.  Only for
         # callers who know that those ARE the diagnosis of the state's s, su, sv (true for every
         # state this core produced, not for an initial state given in terms of u, v)
@@ -373,9 +377,14 @@ class IsentropicDynamicalCore(StencilFactory):
         # its successor re-diagnoses them from s, su, sv (same formula, same bits: the reference
         # computes them exactly so at the end of every stage, dycore.py:L702-L721); the stage
         # outputs of intermediate stages therefore hold STALE u, v (``lazy_velocities``)
+        # The last stage does not write them either: one pass of tb200_velocity_components over the
+        # finished state (40 B/pt, ~0.5 ms at config 5) replaces the in-kernel diagnosis, which cost
+        # the momentum kernel a recomputed halo lane, a warm-up row per strip and spilled registers
+        # (2.23 ms against 1.36 ms without it, profiles/README.md round 2).
         lazy = self.lazy_velocities
+        last = stage == self.stages - 1
         cfg.derive_uv_in = int(lazy and (stage > 0 or self.derive_stage0_velocities))
-        cfg.skip_uv_out = int(lazy and stage < self.stages - 1)
+        cfg.skip_uv_out = int(lazy)
         # ... and then nobody re-reads s before it is final: the stage updates it in place
         scratch_s = out_state[S] if (cfg.skip_uv_out and part == 0) else self._scratch[2]
         pr._diagnostics._set_topography()
@@ -392,6 +401,19 @@ class IsentropicDynamicalCore(StencilFactory):
         lib.check(rc, "tb200_isentropic_stage_dry")
         if "time" in state and part != 1:
             out_state["time"] = state["time"] + dtr
+        # a decomposed run diagnoses the velocities itself, after the halo exchange of s, su, sv
+        if lazy and last and part != 1 and self.after_stage is None and self.overlap is None:
+            self.diagnose_velocities(out_state)
+
+    def diagnose_velocities(self, out_state):
+        """u, v of a finished state from its s, su, sv, outermost faces from the reference state
+        (dwarfs/diagnostics.py:L219-L272 + relaxed.py:L161-L191) in one launch."""
+        g, ref = self.grid, self.horizontal_boundary.reference_state
+        f = lib.as_field
+        rc = lib.load().tb200_velocity_components(
+            f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
+            f(ref[U]), f(ref[V]), g.nx, g.ny, g.nz, lib.current_stream())
+        lib.check(rc, "tb200_velocity_components")
 
     # ---- framework/dycore.py:L383-L462
     def stages_iter(self, state, tendencies, timestep, out_state=None):

@@ -75,6 +75,7 @@ SIGNATURES = {
     "tb200_set_outermost_layers": [_F, _F, _I, _I, _I, _V],
     "tb200_damping": [_F, _F, _F, _F, _F, _D, _I3, _I3, _V],
     "tb200_velocity": [_I, _F, _F, _F, _I, _I3, _I3, _V],
+    "tb200_velocity_components": [_F] * 7 + [_I, _I, _I, _V],
     "tb200_momenta": [_F, _F, _F, _F, _F, _I, _I3, _I3, _V],
     "tb200_density": [_F, _F, _F, _I, _I3, _I3, _V],
     "tb200_mass_fraction": [_F, _F, _F, _I, _I3, _I3, _V],
@@ -94,6 +95,7 @@ SIGNATURES = {
     "tb200_burgers_forward_euler": [_I] + [_F] * 8 + [_D, _D, _D, _I3, _I3, _V],
     "tb200_isentropic_stage_dry": [C.POINTER(StageCfg)] + [_F] * 25 + [_V],
     "tb200_stage_profile": [_I],
+    "tb200_stage_lazy_velocities": [_I],
     "tb200_stage_profile_read": [C.POINTER(C.c_double)],
     "tb200_pack_box": [_F, C.c_void_p, _I3, _I3, _V],
     "tb200_unpack_box": [_F, C.c_void_p, _I3, _I3, _V],

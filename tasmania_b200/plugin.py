@@ -342,7 +342,8 @@ def _fused_stage_dry():
                           rpc["gravitational_acceleration"],
                           rpc["specific_heat_of_dry_air_at_constant_pressure"]],
             "scratch": [storage.zeros(shape, device=_device(self.storage_options)) for _ in range(3)],
-            "lazy": self.fast_tendency_component is None and self.fast_diagnostic_component is None,
+            "lazy": (self.fast_tendency_component is None and self.fast_diagnostic_component is None
+                     and bool(lib.load().tb200_stage_lazy_velocities(int(g.nz)))),
         }
         return self._b200_fused_plan
 
@@ -375,7 +376,7 @@ def _fused_stage_dry():
         cfg.part = 0
         cfg.rim[:] = [0, 0, 0, 0]
         cfg.derive_uv_in = int(p["lazy"] and stage > 0)
-        cfg.skip_uv_out = int(p["lazy"] and stage < self.stages - 1)
+        cfg.skip_uv_out = int(p["lazy"])  # the last stage's u, v: one tb200_velocity_components pass below
         scratch_s = out_state[S] if cfg.skip_uv_out else p["scratch"][2]
         f = lib.as_field
         rmat = self._damper._rmat if self._damp else None
@@ -387,6 +388,11 @@ def _fused_stage_dry():
             f(hb._gamma), f(rmat), f(diag._topo[:, :, nz:nz + 1]),
             f(p["scratch"][0]), f(p["scratch"][1]), f(scratch_s), lib.current_stream())
         lib.check(rc, "tb200_isentropic_stage_dry")
+        if p["lazy"] and stage == self.stages - 1:
+            rc = lib.load().tb200_velocity_components(
+                f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
+                f(ref[U].data), f(ref[V].data), nx, ny, nz, lib.current_stream())
+            lib.check(rc, "tb200_velocity_components")
         out_state["time"] = state["time"] + dtr
 
     stage_array_call_dry.__tasmania_b200__ = True

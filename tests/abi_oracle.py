@@ -216,13 +216,24 @@ class OracleStub(AbiStub):
             for n, now, ref in (("s", s_now, s_ref), ("su", su_now, su_ref), ("sv", sv_now, sv_ref)):
                 dwarfs.damping(arr(now), out[n], arr(ref), r, out[n], c.dt_full, (0, 0, 0), shape)
         if c.skip_uv_out:  # not written by the kernels: poison, so that any consumer shows up
-            out["u"][...] = np.nan
-            out["v"][...] = np.nan
+            out["u"][: nx + 1, :ny, :nz] = np.nan
+            out["v"][:nx, : ny + 1, :nz] = np.nan
             return
         dwarfs.get_velocity_components(nx, ny, nz, out["s"], out["su"], out["sv"], out["u"], out["v"])
         ur, vr = arr(u_ref), arr(v_ref)
         out["u"][0, :ny], out["u"][nx, :ny] = ur[0, :ny], ur[nx, :ny]        # relaxed.py:L161-L175
         out["v"][:nx, 0], out["v"][:nx, ny] = vr[:nx, 0], vr[:nx, ny]        # L177-L191
+
+    def _do_tb200_velocity_components(self, d, du, dv, u, v, u_ref, v_ref, nx, ny, nz, stream):
+        """dwarfs/diagnostics.py:L219-L272 + relaxed.py:L161-L191 (csrc/elementwise.cu)."""
+        uo, vo = arr(u), arr(v)
+        dwarfs.get_velocity_components(nx, ny, nz, arr(d), arr(du), arr(dv), uo, vo)
+        if u_ref:
+            ur = arr(u_ref)
+            uo[0, :ny, :nz], uo[nx, :ny, :nz] = ur[0, :ny, :nz], ur[nx, :ny, :nz]
+        if v_ref:
+            vr = arr(v_ref)
+            vo[:nx, 0, :nz], vo[:nx, ny, :nz] = vr[:nx, 0, :nz], vr[:nx, ny, :nz]
 
     # ---- K11
     def _do_tb200_kessler(self, rho, p, t, exn, qc, qr, qv, t_qc, t_qr, t_qv, t_th, a, k1, k2, beta, lhvw, flags,

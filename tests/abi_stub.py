@@ -110,6 +110,9 @@ class AbiStub:
             self._cb[name] = C.CFUNCTYPE(C.c_int, *argtypes)(self._make(name, argtypes))
 
     def _make(self, name, argtypes):
+        if name == "tb200_stage_lazy_velocities":  # a query, not a launch: the default kernel path
+            return lambda nz: 1 if nz <= 64 else 0
+
         def fn(*args):
             self.calls.append(name)
             if self.recording is not None:  # stream capture: record, do not execute

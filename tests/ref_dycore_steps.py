@@ -155,7 +155,7 @@ def main():
             fused_calls = stub.count("tb200_isentropic_stage_dry")
         else:
             fused_calls = None
-            assert tb.lib.launch_count() - n0 >= (10 if not args.per_stencil else 40) * args.steps
+            assert tb.lib.launch_count() - n0 >= (10 if not args.per_stencil else 30) * args.steps
     if args.stub and not args.per_stencil:
         assert fused_calls == 3 * args.steps, fused_calls
     worst = {}

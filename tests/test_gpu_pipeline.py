@@ -52,8 +52,12 @@ def test_host_streamed_prognostic_only_steps_equal_direct_steps():
     for n in (dsub.U, dsub.V):
         np.testing.assert_array_equal(flat(last["out"][n]).cpu().numpy(), flat(dsub.state[n]).cpu().numpy(),
                                       err_msg=n)
-    np.testing.assert_array_equal(flat(last["in"][dsub.MTG]).cpu().numpy(),
-                                  flat(dsub.state[dsub.MTG]).cpu().numpy())
+    # (the refresh writes the (nx, ny, nz + 1) box; the direct run's storage also holds the
+    # initial broadcast on the unused extra row / column)
+    import tasmania_b200 as tb
+
+    np.testing.assert_array_equal(tb.to_numpy(last["in"][dsub.MTG])[:nx, :ny, :nz + 1],
+                                  tb.to_numpy(dsub.state[dsub.MTG])[:nx, :ny, :nz + 1])
     assert np.isfinite(host_out[pipe.names_out[0]].numpy()).all()
 
 
