@@ -396,6 +396,8 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    if distributed and run.transport == "p2p":
+        run.sub.halo.check()  # raises if a pull ever gave up waiting for a neighbour
 
     # the timed steps must have been a healthy simulation: a state that blew up (NaN / inf) would
     # time special-case arithmetic, not the workload
@@ -408,6 +410,10 @@ def run_b200(args):
     decomposition = getattr(run, "decomposition", "1x1")
     halo_mode = ("overlapped with the interior blocks of the momentum kernel"
                  if getattr(run, "overlap", None) is not None else ("after each stage" if distributed else "none"))
+    if distributed:
+        halo_mode += {"p2p": "; NVLink peer stores into the neighbours' receive buffers (tb200_halo_push / "
+                             "tb200_halo_pull over CUDA IPC), no NCCL on the path",
+                      "nccl": "; torch.distributed point-to-point messages (NCCL)"}[run.transport]
     api = ("tasmania_b200.distributed.DecomposedDryRun.step" if distributed else
            "tasmania_b200.isentropic_dry.IsentropicDryRun.step") + \
         " -> tasmania_b200.isentropic.IsentropicDynamicalCore.__call__ (mirror of the reference class; " \

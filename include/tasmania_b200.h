@@ -415,6 +415,28 @@ int tb200_isentropic_stage_dry(
     const tb200_field *hs, tb200_field *scratch_exn, tb200_field *scratch_mtg,
     tb200_field *scratch_s, void *stream);
 
+/* One RK stage of the MOIST dynamical core (src/tasmania/isentropic/dynamics/dycore.py:L723-L843,
+ * stage_array_call_moist, without slow tendencies): tb200_isentropic_stage_dry plus the three
+ * water constituents, whose reference path is density (dwarfs/diagnostics.py:L400-L416, now and
+ * int) -> their share of K1 (prognostics/utils.py:L101-L134) -> mass_fraction (L434-L450, with
+ * the stage's s after its first relaxation) -> Relaxed.enforce_raw -- all with clipping.  One
+ * extra kernel between the s-step and the column scans does the four for all constituents.
+ * q_now / q_int / q_new / q_ref: arrays of three field pointers (mass fractions of water vapour,
+ * cloud liquid water, precipitation water) at the start of the step / the stage input / the
+ * stage output / the reference state of the lateral boundary.  Same geometry as every other
+ * field; default kernel path and part == 0 only. */
+int tb200_isentropic_stage_moist(
+    const tb200_isentropic_stage *cfg, const tb200_field *s_now, const tb200_field *su_now,
+    const tb200_field *sv_now, const tb200_field *mtg_now, const tb200_field *s_int,
+    const tb200_field *su_int, const tb200_field *sv_int, const tb200_field *u_int,
+    const tb200_field *v_int, tb200_field *s_new, tb200_field *su_new, tb200_field *sv_new,
+    tb200_field *u_new, tb200_field *v_new, const tb200_field *s_ref,
+    const tb200_field *su_ref, const tb200_field *sv_ref, const tb200_field *u_ref,
+    const tb200_field *v_ref, const tb200_field *gamma, const tb200_field *rmat,
+    const tb200_field *hs, tb200_field *scratch_exn, tb200_field *scratch_mtg,
+    tb200_field *scratch_s, const tb200_field *const *q_now, const tb200_field *const *q_int,
+    tb200_field *const *q_new, const tb200_field *const *q_ref, void *stream);
+
 /* Per-kernel timing of the fused stage for the roofline report: with profiling enabled every
  * tb200_isentropic_stage_dry call records CUDA events on its stream around its kernels;
  * tb200_stage_profile_read waits for the last call and returns the durations [ms] of

@@ -191,14 +191,8 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     fy = F::eval_v(F::prep(ldo(a.v_int.p, o_cc), a.fc), ws);
   }
 
-  // Everything row r needs from memory is requested during row r-1: the first-touch streams AND
-  // the x-neighbours of s_int (lines this warp pulled into L1 E rows earlier, but an L1 miss on a
-  // load that is consumed at once stalls the warp for an L2 round trip: 51 % of kernel A's stall
-  // samples were on the first DADD of the x-flux, profiles/README.md round 2)
   struct Row {
     double s_w, v_n, u_c, s_now, gam;  // DERIVE: v_n = sv_int at row r+1, u_c = su_int at row r
-    double xn[NW];                     // s_int at row r, columns cc-E .. cc+E-1 (entry E unused)
-    double su_l;                       // DERIVE: su_int at row r, column cc-1
   };
   auto load_row = [&](unsigned occ, unsigned ocm, unsigned og) {
     Row L;
@@ -207,9 +201,6 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     L.u_c = ldo(DERIVE ? a.su_int.p : a.u_int.p, occ);
     L.s_now = ldo(a.s_now.p, ocm);
     L.gam = ldo(a.gamma.p, og);
-#pragma unroll
-    for (int m = 0; m < NW; ++m) L.xn[m] = m == E ? 0.0 : ldo(a.s_int.p, occ + (unsigned)((m - E) * 8));
-    L.su_l = DERIVE ? ldo(a.su_int.p, occ - 8u) : 0.0;
     return L;
   };
   Row nxt = load_row(o_cc, o_cm, o_g);
@@ -233,14 +224,21 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
       vq = F::prep(cur.v_n, a.fc);
     }
     const double fy_p = F::eval_v(vq, ws);
+    // x-neighbours of s_int from L1 (requesting them a row ahead like the first-touch streams was
+    // measured SLOWER: 0.54 / 0.80 against 0.51 / 0.73 ms, the ten extra live registers spill in
+    // the DERIVE variant; profiles/README.md round 2)
     double xs[NW];
+    {
+      const double *ps = ptr_at(a.s_int.p, o_cc);
 #pragma unroll
-    for (int m = 0; m < NW; ++m) xs[m] = m == E ? ws[E - 1] : cur.xn[m];
+      for (int m = 0; m < NW; ++m) xs[m] = m == E ? ws[E - 1] : __ldg(ps + (m - E));
+    }
     double uq;
     if (DERIVE) {  // u at the left face of the column: (su[c-1] + su[c]) / (s[c-1] + s[c])
       // (the left column from L1 like the s_int neighbours: a shuffle would hand over the
       // CLAMPED column of a lane next to the domain edge)
-      uq = F::prep(qdiv(cur.su_l + cur.u_c, xs[E - 1] + xs[E]), a.fc);
+      const double su_l = ldo(a.su_int.p, o_cc - 8u);
+      uq = F::prep(qdiv(su_l + cur.u_c, xs[E - 1] + xs[E]), a.fc);
     } else {
       uq = F::prep(cur.u_c, a.fc);
     }
@@ -261,6 +259,108 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     fy = fy_p;
     o_cc += row; o_cm += row; o_g += grow;
   }
+}
+
+// ---------------------------------------------------------------- kernel T (moist stage)
+// The water constituents of one RK stage in one pass, between kernels A and B.  The reference
+// (dycore.py:L762-L812 around rk3ws_si.py:L126-L175) runs, per constituent: density
+// (sq = s q, clipped; now and int: dwarfs/diagnostics.py:L400-L416), its share of K1
+// (prognostics/utils.py:L101-L134), mass_fraction (q = sq_new / s_new, clipped; L434-L450) and the
+// lateral relaxation (enforce_raw) -- 4 + 1/3 launches and 10 full-field passes per constituent.
+// Here one thread per point forms the products s_int q_int on the stencil's cross on the fly
+// (the three constituents share the loads of s_int and the face velocities), steps, divides by
+// the stage's s (after its first relaxation: scratch_s, which is why this kernel runs before the
+// momentum kernel updates s in place) and relaxes: reads s_now, s_int, s_pre, 2 x 3 q (+ su_int,
+// sv_int or u, v), writes 3 q = 14 words per point, against 37 in the per-stencil path.
+// Same operations in the same order, hence the same bits.  Requirement as for kernel MV:
+// gamma == 1 on the nb outermost rings (the stale sq_new the reference divides there never
+// survives the relaxation).
+template <int SCHEME, bool DERIVE>
+__global__ void __launch_bounds__(256) stage_tracers_kernel(const StageArgs a) {
+  using F = Flux<SCHEME>;
+  constexpr int E = F::extent;
+  constexpr int NW = 2 * E;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= a.nx || j >= a.ny) return;
+  const int nb = a.nb;
+  const bool interior = i >= nb && i < a.nx - nb && j >= nb && j < a.ny - nb;
+  const double gam = a.gamma.ld(i, j, 0);
+  const long long sj = a.s_int.s1;
+  const long long o = i + j * sj + (long long)k * a.s_int.s2;  // same geometry for every 3-D field
+  if (!interior) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      if (t < a.ntr) {
+        const double old = gam == 1.0 ? 0.0 : a.q_new[t].p[o];  // untouched by the step; the relaxation decides
+        a.q_new[t].p[o] = relax_point(gam, old, __ldg(a.q_ref[t].p + o));
+      }
+    }
+    return;
+  }
+  // s_int on the cross: sx[n] = s_int(i - E + n, j), sy[n] = s_int(i, j - E + n), n = 0 .. 2E
+  double sx[NW + 1], sy[NW + 1];
+  const double *ps = a.s_int.p + o;
+#pragma unroll
+  for (int n = 0; n <= NW; ++n) {
+    sx[n] = __ldg(ps + (n - E));
+    sy[n] = n == E ? sx[E] : __ldg(ps + (n - E) * sj);
+  }
+  double uq_m, uq_p, vq_m, vq_p;
+  if (DERIVE) {  // velocity_x / velocity_y, dwarfs/diagnostics.py:L219-L272
+    const double *pu = a.su_int.p + o, *pv = a.sv_int.p + o;
+    const double su_c = __ldg(pu), sv_c = __ldg(pv);
+    uq_m = F::prep(qdiv(__ldg(pu - 1) + su_c, sx[E - 1] + sx[E]), a.fc);
+    uq_p = F::prep(qdiv(su_c + __ldg(pu + 1), sx[E] + sx[E + 1]), a.fc);
+    vq_m = F::prep(qdiv(__ldg(pv - sj) + sv_c, sy[E - 1] + sy[E]), a.fc);
+    vq_p = F::prep(qdiv(sv_c + __ldg(pv + sj), sy[E] + sy[E + 1]), a.fc);
+  } else {
+    uq_m = F::prep(__ldg(a.u_int.p + o), a.fc);
+    uq_p = F::prep(__ldg(a.u_int.p + o + 1), a.fc);
+    vq_m = F::prep(__ldg(a.v_int.p + o), a.fc);
+    vq_p = F::prep(__ldg(a.v_int.p + o + sj), a.fc);
+  }
+  const double s_now = __ldg(a.s_now.p + o), s_pre = __ldg(a.spre.p + o);
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (t < a.ntr) {
+      const double *pq = a.q_int[t].p + o;
+      double qx[NW + 1], qy[NW + 1];
+#pragma unroll
+      for (int n = 0; n <= NW; ++n) {  // density of the constituent, clipped (diagnostics.py:L400-L416)
+        const double x = sx[n] * __ldg(pq + (n - E));
+        qx[n] = x > 0.0 ? x : 0.0;
+        if (n == E) {
+          qy[n] = qx[n];
+        } else {
+          const double y = sy[n] * __ldg(pq + (n - E) * sj);
+          qy[n] = y > 0.0 ? y : 0.0;
+        }
+      }
+      const double fxm = F::eval_v(uq_m, qx), fxp = F::eval_v(uq_p, qx + 1);
+      const double fym = F::eval_v(vq_m, qy), fyp = F::eval_v(vq_p, qy + 1);
+      const double div = (fxp - fxm) / a.fc.dx + (fyp - fym) / a.fc.dy;
+      double sq_now = s_now * __ldg(a.q_now[t].p + o);
+      sq_now = sq_now > 0.0 ? sq_now : 0.0;
+      const double sq_new = sq_now - a.dt * (div - 0.0);  // prognostics/utils.py:L101-L134
+      double q = qdiv(sq_new, s_pre);                      // diagnostics.py:L434-L450
+      q = q > 0.0 ? q : 0.0;
+      if (gam != 0.0) q = relax_point(gam, q, __ldg(a.q_ref[t].p + o));
+      a.q_new[t].p[o] = q;
+    }
+  }
+}
+
+template <int SCHEME>
+int launch_tracers(const StageArgs &a, cudaStream_t st) {
+  dim3 block(64, 4, 1);
+  dim3 grid((a.nx + 63) / 64, (a.ny + 3) / 4, a.nz);
+  if (a.derive_uv)
+    stage_tracers_kernel<SCHEME, true><<<grid, block, 0, st>>>(a);
+  else
+    stage_tracers_kernel<SCHEME, false><<<grid, block, 0, st>>>(a);
+  return check_launch("isentropic_stage_moist/T");
 }
 
 // The Exner function of eight levels as ONE real call: kernel B is unrolled over the levels, so
@@ -1620,6 +1720,10 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
       if (rc) return rc;
       prof_mark(1, st);
     }
+    if (a.ntr > 0) {  // the water constituents need the stage's s before kernel MV finalises it in place
+      const int rc = launch_tracers<SCHEME>(a, st);
+      if (rc) return rc;
+    }
     if (b_coop(a)) {
       dim3 block(32, 8, 1);
       dim3 grid((a.nx + 31) / 32, a.ny, 1);
@@ -1708,7 +1812,8 @@ extern "C" int tb200_stage_profile_read(double ms[3]) {
   return TB200_OK;
 }
 
-extern "C" int tb200_isentropic_stage_dry(
+namespace {
+int stage_entry(
     const tb200_isentropic_stage *cfg, const tb200_field *s_now, const tb200_field *su_now,
     const tb200_field *sv_now, const tb200_field *mtg_now, const tb200_field *s_int,
     const tb200_field *su_int, const tb200_field *sv_int, const tb200_field *u_int,
@@ -1716,9 +1821,21 @@ extern "C" int tb200_isentropic_stage_dry(
     tb200_field *u_new, tb200_field *v_new, const tb200_field *s_ref, const tb200_field *su_ref,
     const tb200_field *sv_ref, const tb200_field *u_ref, const tb200_field *v_ref,
     const tb200_field *gamma, const tb200_field *rmat, const tb200_field *hs,
-    tb200_field *scratch_exn, tb200_field *scratch_mtg, tb200_field *scratch_s, void *stream) {
+    tb200_field *scratch_exn, tb200_field *scratch_mtg, tb200_field *scratch_s,
+    const tb200_field *const *q_now, const tb200_field *const *q_int, tb200_field *const *q_new,
+    const tb200_field *const *q_ref, void *stream) {
   TB200_REQUIRE(cfg != nullptr, "isentropic_stage_dry: NULL cfg");
   StageArgs a{};
+  a.ntr = 0;
+  if (q_now != nullptr) {
+    TB200_REQUIRE(q_int != nullptr && q_new != nullptr && q_ref != nullptr,
+                  "isentropic_stage_moist: NULL tracer array");
+    a.ntr = 3;
+    for (int t = 0; t < 3; ++t) {
+      a.q_now[t] = view(q_now[t]); a.q_int[t] = view(q_int[t]);
+      a.q_new[t] = view(q_new[t]); a.q_ref[t] = view(q_ref[t]);
+    }
+  }
   a.s_now = view(s_now); a.su_now = view(su_now); a.sv_now = view(sv_now);
   a.mtg_now = view(mtg_now);
   a.s_int = view(s_int); a.su_int = view(su_int); a.sv_int = view(sv_int);
@@ -1796,6 +1913,20 @@ extern "C" int tb200_isentropic_stage_dry(
       }
     }
   }
+  for (int t = 0; t < a.ntr; ++t) {
+    const View *qs[] = {&a.q_now[t], &a.q_int[t], &a.q_new[t], &a.q_ref[t]};
+    for (const View *v : qs) {
+      TB200_REQUIRE(covers(*v, nx, ny, nz), "isentropic_stage_moist: a tracer field is NULL or too small");
+      if (v->s0 != 1 || v->s1 != a.s_now.s1 || v->s2 != a.s_now.s2) {
+        set_error("isentropic_stage_moist: the tracer fields must share the geometry of the other fields");
+        return TB200_ERR_LAYOUT;
+      }
+    }
+    TB200_REQUIRE(a.q_new[t].p != a.q_int[t].p && a.q_new[t].p != a.q_now[t].p,
+                  "isentropic_stage_moist: q_new must not alias the stage inputs");
+  }
+  TB200_REQUIRE(a.ntr == 0 || (a.part == 0 && s_impl() != 0 && a.nz <= 64),
+                "isentropic_stage_moist: needs the default kernel path (A + B), an unsplit stage and nz <= 64");
   if (!lazy_uv_path(a)) {
     // the other kernel variants keep the reference's data flow (see lazy_uv_path)
     TB200_REQUIRE(a.spre.p != a.s_new.p,
@@ -1813,4 +1944,37 @@ extern "C" int tb200_isentropic_stage_dry(
     case TB200_FLUX_THIRD_ORDER_UPWIND: return run_stage<TB200_FLUX_THIRD_ORDER_UPWIND>(a, st);
     default: return run_stage<TB200_FLUX_FIFTH_ORDER_UPWIND>(a, st);
   }
+}
+}  // namespace
+
+extern "C" int tb200_isentropic_stage_dry(
+    const tb200_isentropic_stage *cfg, const tb200_field *s_now, const tb200_field *su_now,
+    const tb200_field *sv_now, const tb200_field *mtg_now, const tb200_field *s_int,
+    const tb200_field *su_int, const tb200_field *sv_int, const tb200_field *u_int,
+    const tb200_field *v_int, tb200_field *s_new, tb200_field *su_new, tb200_field *sv_new,
+    tb200_field *u_new, tb200_field *v_new, const tb200_field *s_ref, const tb200_field *su_ref,
+    const tb200_field *sv_ref, const tb200_field *u_ref, const tb200_field *v_ref,
+    const tb200_field *gamma, const tb200_field *rmat, const tb200_field *hs,
+    tb200_field *scratch_exn, tb200_field *scratch_mtg, tb200_field *scratch_s, void *stream) {
+  return stage_entry(cfg, s_now, su_now, sv_now, mtg_now, s_int, su_int, sv_int, u_int, v_int, s_new,
+                     su_new, sv_new, u_new, v_new, s_ref, su_ref, sv_ref, u_ref, v_ref, gamma, rmat, hs,
+                     scratch_exn, scratch_mtg, scratch_s, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int tb200_isentropic_stage_moist(
+    const tb200_isentropic_stage *cfg, const tb200_field *s_now, const tb200_field *su_now,
+    const tb200_field *sv_now, const tb200_field *mtg_now, const tb200_field *s_int,
+    const tb200_field *su_int, const tb200_field *sv_int, const tb200_field *u_int,
+    const tb200_field *v_int, tb200_field *s_new, tb200_field *su_new, tb200_field *sv_new,
+    tb200_field *u_new, tb200_field *v_new, const tb200_field *s_ref, const tb200_field *su_ref,
+    const tb200_field *sv_ref, const tb200_field *u_ref, const tb200_field *v_ref,
+    const tb200_field *gamma, const tb200_field *rmat, const tb200_field *hs,
+    tb200_field *scratch_exn, tb200_field *scratch_mtg, tb200_field *scratch_s,
+    const tb200_field *const *q_now, const tb200_field *const *q_int, tb200_field *const *q_new,
+    const tb200_field *const *q_ref, void *stream) {
+  TB200_REQUIRE(q_now != nullptr && q_int != nullptr && q_new != nullptr && q_ref != nullptr,
+                "isentropic_stage_moist: NULL tracer array");
+  return stage_entry(cfg, s_now, su_now, sv_now, mtg_now, s_int, su_int, sv_int, u_int, v_int, s_new,
+                     su_new, sv_new, u_new, v_new, s_ref, su_ref, sv_ref, u_ref, v_ref, gamma, rmat, hs,
+                     scratch_exn, scratch_mtg, scratch_s, q_now, q_int, q_new, q_ref, stream);
 }

@@ -12,6 +12,9 @@ struct StageArgs {
   View s_new, su_new, sv_new, u_new, v_new;
   View s_ref, su_ref, sv_ref, u_ref, v_ref;
   View gamma, rmat, hs, exn, mtg, spre;
+  // moist stage: mass fractions of the water constituents (qv, qc, qr), ntr = 0 when dry
+  View q_now[3], q_int[3], q_new[3], q_ref[3];
+  int ntr;
   int nx, ny, nz, nb, damp;
   int bx0, by0;    // block offsets of a partial launch of the momentum kernel
   int part, rim[4];  // tb200_isentropic_stage.part / .rim

@@ -17,6 +17,7 @@ orchestration that stays in tasmania).  Two execution paths produce the same num
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 
@@ -271,9 +272,12 @@ class IsentropicDynamicalCore(StencilFactory):
         # the 2-D class only: Relaxed1DX / 1DY also report type "relaxed", but their gamma is
         # non-zero on the middle line alone and they repeat that line across the degenerate axis,
         # which the fused kernels do not do
-        fusable = (not moist) and type(horizontal_boundary) is Relaxed
+        fusable = type(horizontal_boundary) is Relaxed
+        if moist:  # the tracer kernel rides the default kernel path only (csrc/isentropic_fused.cu: kernel T)
+            fusable = (fusable and os.environ.get("TB200_MOIST_FUSED", "1") != "0"
+                       and bool(lib.load().tb200_stage_lazy_velocities(grid.nz)))
         if fused and not fusable:
-            raise ValueError("the fused stage covers the dry core with relaxed boundaries only")
+            raise ValueError("the fused stage covers the core with (2-D) relaxed boundaries only")
         self._fused = fusable if fused is None else bool(fused)
         # fused path only: intermediate RK stages neither write nor read u, v (see _stage_fused);
         # set to False to get every stage's velocities like the reference's stage_array_call
@@ -357,8 +361,9 @@ class IsentropicDynamicalCore(StencilFactory):
     # ---- the fused stage: three kernels
     def _stage_fused(self, stage, state, timestep, out_state, part=0, rim=(0, 0, 0, 0)):
         g, hb, pr = self.grid, self.horizontal_boundary, self._prognostic
+        qn = (mfwv, mfcw, mfpw) if self._moist else ()
         if stage == 0:
-            pr._now = {n: state[n] for n in (S, MTG, SU, SV)}
+            pr._now = {n: state[n] for n in (S, MTG, SU, SV) + qn}
         if self._scratch is None:
             self._scratch = tuple(self.zeros(shape=self.storage_shape) for _ in range(3))
         dtr, dt = pr.substep(stage, timestep)
@@ -391,14 +396,22 @@ class IsentropicDynamicalCore(StencilFactory):
         ref, now = hb.reference_state, pr._now
         f = lib.as_field
         rmat = self._damper._rmat if self._damp else None
-        rc = lib.load().tb200_isentropic_stage_dry(
-            cfg, f(now[S]), f(now[SU]), f(now[SV]), f(now[MTG]),
-            f(state[S]), f(state[SU]), f(state[SV]), f(state[U]), f(state[V]),
-            f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
-            f(ref[S]), f(ref[SU]), f(ref[SV]), f(ref[U]), f(ref[V]),
-            f(hb._gamma2d), f(rmat), f(pr._diagnostics._topo2d),
-            f(self._scratch[0]), f(self._scratch[1]), f(scratch_s), lib.current_stream())
-        lib.check(rc, "tb200_isentropic_stage_dry")
+        args = (cfg, f(now[S]), f(now[SU]), f(now[SV]), f(now[MTG]),
+                f(state[S]), f(state[SU]), f(state[SV]), f(state[U]), f(state[V]),
+                f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
+                f(ref[S]), f(ref[SU]), f(ref[SV]), f(ref[U]), f(ref[V]),
+                f(hb._gamma2d), f(rmat), f(pr._diagnostics._topo2d),
+                f(self._scratch[0]), f(self._scratch[1]), f(scratch_s))
+        if self._moist:
+            # the three water constituents ride along (kernel T): mass fractions in, mass fractions out
+            keep = [[lib.as_field(d[n]) for n in qn] for d in (now, state, out_state, ref)]
+            arrays = [(lib.FieldP * 3)(*[C.pointer(k) for k in ks]) for ks in keep]
+            rc = lib.load().tb200_isentropic_stage_moist(*args, *arrays, lib.current_stream())
+            lib.check(rc, "tb200_isentropic_stage_moist")
+            del keep
+        else:
+            rc = lib.load().tb200_isentropic_stage_dry(*args, lib.current_stream())
+            lib.check(rc, "tb200_isentropic_stage_dry")
         if "time" in state and part != 1:
             out_state["time"] = state["time"] + dtr
         # a decomposed run diagnoses the velocities itself, after the halo exchange of s, su, sv

@@ -94,6 +94,7 @@ SIGNATURES = {
     "tb200_density_and_temperature": [_F] * 6 + [_D, _I3, _I3, _V],
     "tb200_burgers_forward_euler": [_I] + [_F] * 8 + [_D, _D, _D, _I3, _I3, _V],
     "tb200_isentropic_stage_dry": [C.POINTER(StageCfg)] + [_F] * 25 + [_V],
+    "tb200_isentropic_stage_moist": [C.POINTER(StageCfg)] + [_F] * 25 + [_FPP] * 4 + [_V],
     "tb200_stage_profile": [_I],
     "tb200_stage_lazy_velocities": [_I],
     "tb200_stage_profile_read": [C.POINTER(C.c_double)],

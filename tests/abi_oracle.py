@@ -180,9 +180,43 @@ class OracleStub(AbiStub):
 
     # ---- the fused dry RK stage (csrc/isentropic_fused.cu): what dycore.py:L641-L721 over
     # rk3ws_si.py:L105-L234 computes for one stage, from the same arguments the kernels get
+    def _do_tb200_isentropic_stage_moist(self, cfg, s_now, su_now, sv_now, mtg_now, s_int, su_int, sv_int, u_int,
+                                         v_int, s_new, su_new, sv_new, u_new, v_new, s_ref, su_ref, sv_ref,
+                                         u_ref, v_ref, gamma2d, rmat, topo2d, scr0, scr1, scr2, q_now, q_int,
+                                         q_new, q_ref, stream):
+        """dycore.py:L723-L843: the dry stage plus, per water constituent, density (now, int) -> K1 ->
+        mass fraction over the stage's s after its first relaxation -> lateral relaxation."""
+        c = cfg.contents
+        nx, ny, nz, nb = c.nx, c.ny, c.nz, c.nb
+
+        def tracers(s_pre, u_i, v_i, gamma):
+            flux = FLUX_NAMES[c.flux_scheme]
+            origin, domain = (nb, nb, 0), (nx - 2 * nb, ny - 2 * nb, nz)
+            full = ((0, 0, 0), (nx, ny, nz))
+            for t in range(3):
+                qn, qi, qo, qr = (arr(x[t]) for x in (q_now, q_int, q_new, q_ref))
+                sq_now, sq_int, sq_new = np.zeros_like(qn), np.zeros_like(qn), np.zeros_like(qn)
+                dwarfs.density(arr(s_now), qn, sq_now, *full)
+                dwarfs.density(arr(s_int), qi, sq_int, *full)
+                with np.errstate(all="ignore"):
+                    oi.step_forward_euler(flux, arr(s_now), arr(s_int), np.zeros_like(qn), u_i, v_i, dt=c.dt,
+                                          dx=c.dx, dy=c.dy, origin=origin, domain=domain, moist=True,
+                                          sq_now=[sq_now], sq_int=[sq_int], sq_new=[sq_new], q_tnd=(None,))
+                    new = qo.copy()
+                    dwarfs.mass_fraction(s_pre, sq_new, new, *full)
+                box = (slice(nb, nx - nb), slice(nb, ny - nb), slice(0, nz))
+                qo[box] = new[box]  # outside: the reference divides stale sq_new; gamma == 1 there
+                ob.irelax(gamma, qr, qo, (0, 0, 0), (nx, ny, nz))
+
+        self._do_tb200_isentropic_stage_dry(cfg, s_now, su_now, sv_now, mtg_now, s_int, su_int, sv_int, u_int,
+                                            v_int, s_new, su_new, sv_new, u_new, v_new, s_ref, su_ref, sv_ref,
+                                            u_ref, v_ref, gamma2d, rmat, topo2d, scr0, scr1, scr2, stream,
+                                            after_s_step=tracers)
+
     def _do_tb200_isentropic_stage_dry(self, cfg, s_now, su_now, sv_now, mtg_now, s_int, su_int, sv_int, u_int,
                                        v_int, s_new, su_new, sv_new, u_new, v_new, s_ref, su_ref, sv_ref,
-                                       u_ref, v_ref, gamma2d, rmat, topo2d, scr0, scr1, scr2, stream):
+                                       u_ref, v_ref, gamma2d, rmat, topo2d, scr0, scr1, scr2, stream,
+                                       after_s_step=None):
         c = cfg.contents
         assert c.part == 0, "the overlap parts of a decomposed run are not emulated"
         nx, ny, nz, nb = c.nx, c.ny, c.nz, c.nb
@@ -200,6 +234,8 @@ class OracleStub(AbiStub):
         oi.step_forward_euler(flux, arr(s_now), arr(s_int), out["s"], u_i, v_i, dt=c.dt,
                               dx=c.dx, dy=c.dy, origin=origin, domain=domain)
         ob.irelax(gamma, arr(s_ref), out["s"], (0, 0, 0), (nx, ny, nz))
+        if after_s_step is not None:
+            after_s_step(out["s"], u_i, v_i, gamma)
         hs = np.zeros(shape)
         hs[:, :, nz] = arr(topo2d)[: shape[0], : shape[1], 0]
         mtg_new = np.zeros(shape)

@@ -92,7 +92,7 @@ def test_moist_model_graphed_issues_the_eager_call_sequence():
             traces.append(canonical(stub.trace))
             assert model.state["time"] == model.init_time + nsteps * model.dt
             stub.trace = None
-    assert len(traces[0]) == len(traces[1]) > 80 * nsteps
+    assert len(traces[0]) == len(traces[1]) > 45 * nsteps  # 53 launches per step with the fused moist stage
     for n, (a, b) in enumerate(zip(*traces)):
         assert a == b, (n, a, b)
     print("buffer-rotation period of the moist SUS model:", period)
