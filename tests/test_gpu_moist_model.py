@@ -126,8 +126,8 @@ def test_vertical_advection_step_is_advection_plus_fma_bitwise(scheme, moist):
 
 
 def test_fused_paths_equal_the_reference_shaped_paths_bitwise(monkeypatch):
-    """Moist model with the b200 fusions (stage update inside the vertical advection kernel, frame
-    relaxation of all fields in one launch) against the same model issuing the reference's call
+    """Moist model with the b200 fusions (fused moist dycore stage, stage update inside the vertical
+    advection kernel, frame relaxation of all fields in one launch) against the same model issuing the reference's call
     sequence (tendencies + fma, one full-box irelax per field): identical bits."""
     import tasmania_b200 as tb
     from tasmania_b200.isentropic_moist import IsentropicMoistSUS
@@ -138,13 +138,14 @@ def test_fused_paths_equal_the_reference_shaped_paths_bitwise(monkeypatch):
     for fused in (True, False):
         monkeypatch.setenv("TB200_FUSED_STEP", "1" if fused else "0")
         monkeypatch.setenv("TB200_RELAX", "frame" if fused else "full")
+        monkeypatch.setenv("TB200_MOIST_FUSED", "1" if fused else "0")  # the fused moist dycore stage
         grid, np_state = hp.moist_case(nx, ny, nz)
         model = IsentropicMoistSUS(grid, np_state, timedelta(seconds=5), damp_depth=4)
         n0 = tb.lib.launch_count()
         model.run(nsteps)
         res.append(({n: tb.to_numpy(v) for n, v in model.state.items() if n != "time"},
                     (tb.lib.launch_count() - n0) / nsteps))
-    assert res[0][1] < res[1][1] - 20  # 3 fma + 21 relax launches fewer per step
+    assert res[0][1] < res[1][1] - 40  # 63 against 122 launches per step
     for n, v in res[1][0].items():
         np.testing.assert_array_equal(res[0][0][n], v, err_msg=n)
 
