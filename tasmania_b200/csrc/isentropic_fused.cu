@@ -352,8 +352,124 @@ __global__ void __launch_bounds__(256) stage_tracers_kernel(const StageArgs a) {
   }
 }
 
+// Kernel T, tiled (default; TB200_T_IMPL=point selects the kernel above).  The thread-per-point
+// version evaluates every face flux twice, every product s q up to 2E+1 times and derives four
+// face velocities per point: 380 us per launch at configs[2] (21 % of the step, launch list
+// r02e_launches_c3.csv) where the traffic would allow 90.  Here a block owns a tile of 31 x 16
+// points of one level:
+//   phase 1  the densities clip(s_int q_int) of the three constituents on the tile + E halo
+//            points a side go to shared memory, each formed once (coalesced row loads);
+//   phase 2  thread (tx, ty) evaluates the flux through the LEFT face and through the BOTTOM face
+//            of its point for all three constituents, with one velocity diagnosis per face; lane
+//            31 of a row and row 16 of the block are lenders (their faces close the tile, they own
+//            no point), so every face of the tile is evaluated exactly once; x-fluxes reach the
+//            left neighbour by shuffle, y-fluxes through shared memory;
+//   phase 3  divergence, step, division by the stage's s, clipping, relaxation, store.
+// Same point formulas in the same order as the kernel above, hence the same bits.
+constexpr int TT_X = 31, TT_Y = 16;
+template <int SCHEME, bool DERIVE>
+__global__ void __launch_bounds__(32 * (TT_Y + 1)) stage_tracers_tile_kernel(const StageArgs a) {
+  using F = Flux<SCHEME>;
+  constexpr int E = F::extent;
+  constexpr int NW = 2 * E;
+  constexpr int SXW = 32 + NW, SYW = TT_Y + NW;  // cells i0 - E .. i0 + 31 + E - 1 (one spare), j0 - E .. j0 + 15 + E
+  __shared__ double sq[3][SYW][SXW + 1];
+  __shared__ double fys[3][TT_Y + 1][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = blockIdx.x * TT_X, j0 = blockIdx.y * TT_Y, k = blockIdx.z;
+  const int nx = a.nx, ny = a.ny, nb = a.nb;
+  const long long sj = a.s_int.s1;
+  const long long pl = (long long)k * a.s_int.s2;
+  // ---- phase 1: densities on the tile + halo (indices clamped into the storage: clamped
+  // values only reach faces of points outside the computational domain)
+  for (int n = ty * 32 + tx; n < SXW * SYW; n += 32 * (TT_Y + 1)) {
+    const int ly = n / SXW, lx = n - ly * SXW;
+    const int gi = min(max(i0 - E + lx, 0), nx - 1), gj = min(max(j0 - E + ly, 0), ny - 1);
+    const long long o = pl + gi + gj * sj;
+    const double sv_ = __ldg(a.s_int.p + o);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const double x = sv_ * __ldg(a.q_int[t].p + o);  // diagnostics.py:L400-L416
+      sq[t][ly][lx] = x > 0.0 ? x : 0.0;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: fluxes through the left and the bottom face of point (i, j)
+  const int i = i0 + tx, j = j0 + ty;
+  const int ic = min(i, nx - 1), jc = min(j, ny - 1);  // lenders / edge threads stay inside the storage
+  const long long o = pl + ic + jc * sj;
+  double uq, vq;
+  if (DERIVE) {  // velocity_x / velocity_y, dwarfs/diagnostics.py:L219-L272
+    const long long ol = pl + max(ic - 1, 0) + jc * sj, ob = pl + ic + max(jc - 1, 0) * sj;
+    const double s_c = __ldg(a.s_int.p + o);
+    uq = F::prep(qdiv(__ldg(a.su_int.p + ol) + __ldg(a.su_int.p + o), __ldg(a.s_int.p + ol) + s_c), a.fc);
+    vq = F::prep(qdiv(__ldg(a.sv_int.p + ob) + __ldg(a.sv_int.p + o), __ldg(a.s_int.p + ob) + s_c), a.fc);
+  } else {
+    uq = F::prep(__ldg(a.u_int.p + o), a.fc);
+    vq = F::prep(__ldg(a.v_int.p + o), a.fc);
+  }
+  double fx[3], fxp[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    // face i: cells i - E .. i + E - 1 = shared columns tx .. tx + NW - 1 of row ty + E
+    double wx[NW], wy[NW];
+    const int yr = min(ty + E, SYW - 1);  // (the lender row's x-fluxes are not used)
+#pragma unroll
+    for (int m = 0; m < NW; ++m) {
+      wx[m] = sq[t][yr][tx + m];
+      wy[m] = sq[t][ty + m][tx + E];      // face j: cells j - E .. j + E - 1 = shared rows ty .. ty + NW - 1
+    }
+    fx[t] = F::eval_v(uq, wx);
+    fys[t][ty][tx] = F::eval_v(vq, wy);
+    fxp[t] = __shfl_down_sync(0xffffffffu, fx[t], 1);
+  }
+  __syncthreads();
+  // ---- phase 3: the point update
+  if (tx >= TT_X || ty >= TT_Y || i >= nx || j >= ny) return;
+  const bool interior = i >= nb && i < nx - nb && j >= nb && j < ny - nb;
+  const double gam = a.gamma.ld(i, j, 0);
+  if (!interior) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const double old = gam == 1.0 ? 0.0 : a.q_new[t].p[o];  // untouched by the step; the relaxation decides
+      a.q_new[t].p[o] = relax_point(gam, old, __ldg(a.q_ref[t].p + o));
+    }
+    return;
+  }
+  const double s_now = __ldg(a.s_now.p + o), s_pre = __ldg(a.spre.p + o);
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const double div = (fxp[t] - fx[t]) / a.fc.dx + (fys[t][ty + 1][tx] - fys[t][ty][tx]) / a.fc.dy;
+    double sq_now = s_now * __ldg(a.q_now[t].p + o);
+    sq_now = sq_now > 0.0 ? sq_now : 0.0;
+    const double sq_new = sq_now - a.dt * (div - 0.0);  // prognostics/utils.py:L101-L134
+    double q = qdiv(sq_new, s_pre);                      // diagnostics.py:L434-L450
+    q = q > 0.0 ? q : 0.0;
+    if (gam != 0.0) q = relax_point(gam, q, __ldg(a.q_ref[t].p + o));
+    a.q_new[t].p[o] = q;
+  }
+}
+
+int t_impl() {  // TB200_T_IMPL=point|tile
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("TB200_T_IMPL");
+    impl = (e != nullptr && strcmp(e, "point") == 0) ? 0 : 1;
+  }
+  return impl;
+}
+
 template <int SCHEME>
 int launch_tracers(const StageArgs &a, cudaStream_t st) {
+  if (t_impl() == 1) {
+    dim3 block(32, TT_Y + 1, 1);
+    dim3 grid((a.nx + TT_X - 1) / TT_X, (a.ny + TT_Y - 1) / TT_Y, a.nz);
+    if (a.derive_uv)
+      stage_tracers_tile_kernel<SCHEME, true><<<grid, block, 0, st>>>(a);
+    else
+      stage_tracers_tile_kernel<SCHEME, false><<<grid, block, 0, st>>>(a);
+    return check_launch("isentropic_stage_moist/T(tile)");
+  }
   dim3 block(64, 4, 1);
   dim3 grid((a.nx + 63) / 64, (a.ny + 3) / 4, a.nz);
   if (a.derive_uv)

@@ -579,15 +579,18 @@ class Overlap:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             self.sub.halo.exchange(self.sub.exchange_fields(out, stage))
-            self.sub.fix_seam_velocities(out, stage)
             if self.events is not None:
                 e1.record()
                 self.events.append((e0, e1))
+            if not self.sub.dyc.lazy_velocities:  # seam faces: rim data only
+                self.sub.fix_seam_velocities(out, stage)
             self.exchanged.record(self.side)
 
     def after_interior(self, stage, out):
         # whatever comes next on the main stream reads the exchanged halos
         torch.cuda.current_stream().wait_event(self.exchanged)
+        if self.sub.dyc.lazy_velocities:  # u, v of the step's final state: needs the interior too
+            self.sub.fix_seam_velocities(out, stage)
 
 
 class DecomposedDryRun:
@@ -625,13 +628,14 @@ class DecomposedDryRun:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         self.sub.halo.exchange(self.sub.exchange_fields(out, stage))
-        self.sub.fix_seam_velocities(out, stage)
         if self.exchange_events is not None:
             e1.record()
             self.exchange_events.append((e0, e1))
+        self.sub.fix_seam_velocities(out, stage)
 
     def exchange_ms(self):
-        """Mean device time of one halo exchange + seam fix-up (after a synchronize)."""
+        """Mean device time of one halo exchange (after a synchronize): packing, transfer, waiting for
+        the neighbours' slabs, unpacking."""
         ev = (self.overlap.events if self.overlap is not None else self.exchange_events) or []
         return float(np.mean([a.elapsed_time(b) for a, b in ev])) if ev else None
 
