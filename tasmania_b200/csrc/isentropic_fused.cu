@@ -150,7 +150,7 @@ constexpr int A_COLS = 31;
 // stage then need not write them (tb200_isentropic_stage.derive_uv_in).  Same traffic for this
 // kernel (su_int, sv_int instead of u, v), two IEEE divisions more per point.
 template <int SCHEME, int LJ, bool DERIVE>
-__global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
+__global__ void __launch_bounds__(128, DERIVE ? 6 : 7) stage_a_kernel(const StageArgs a) {
   using F = Flux<SCHEME>;
   constexpr int E = F::extent;
   constexpr int NW = 2 * E;
@@ -258,6 +258,185 @@ __global__ void __launch_bounds__(128, 6) stage_a_kernel(const StageArgs a) {
     if (out_lane) sto(a.spre.p, o_cm, v);
     fy = fy_p;
     o_cc += row; o_cm += row; o_g += grow;
+  }
+}
+
+// ---------------------------------------------------------------- kernel A, two columns per lane
+// Same decomposition and arithmetic as stage_a_kernel (a warp marches along j over a strip of one
+// level, register window of s_int rows, every face flux evaluated once), but a lane owns an ALIGNED
+// PAIR of columns like the momentum kernel: every access is LDG.128 / STG.128, a warp has twice
+// the bytes in flight per load, and address arithmetic, loop control and the relaxation logic are
+// paid once per two points.  One warp = 64 columns, 62 of them owned (lane 31 lends the left face
+// of its pair).  The x-neighbours of the pair are the pairs at c0 - 4, c0 - 2 and c0 + 2 (L1).
+// Requirements as for the two-column momentum kernel (mv2_ok); TB200_A_IMPL=one selects the
+// one-column kernel.  Bit-identical results (tests/test_gpu_stage_variants.py).
+constexpr int A2_COLS = 62;
+__device__ __forceinline__ double2 ld2o(const double *base, unsigned off) {
+  return __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + off));
+}
+
+template <int SCHEME, int LJ, bool DERIVE>
+__global__ void __launch_bounds__(128, 4) stage_a2_kernel(const StageArgs a) {
+  using F = Flux<SCHEME>;
+  constexpr int E = F::extent;
+  constexpr int NW = 2 * E;
+  const int lane = threadIdx.x & 31;
+  const int xw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (xw * A2_COLS >= a.nx) return;  // warp-uniform
+  const int c0 = xw * A2_COLS + 2 * lane;  // even
+  const int j0 = blockIdx.y * LJ;
+  const int jend = min(j0 + LJ, a.ny);
+  const int k = blockIdx.z;
+  const int nx = a.nx, ny = a.ny, nb = a.nb;
+  const int pmax = (nx - 1) & ~1;  // last aligned pair that starts inside the row
+  const bool own = lane < 31;
+  const bool out0 = own && c0 < nx, out1 = own && c0 + 1 < nx;
+  const bool int0 = c0 >= nb && c0 < nx - nb, int1 = c0 + 1 >= nb && c0 + 1 < nx - nb;
+  // pairs: own, and the x-neighbours (clamped into the row: a clamped pair only feeds faces of
+  // points outside the computational domain)
+  const unsigned col = (unsigned)min(c0, pmax) * 8u;
+  const unsigned col_m4 = (unsigned)min(max(c0 - 4, 0), pmax) * 8u;
+  const unsigned col_m2 = (unsigned)min(max(c0 - 2, 0), pmax) * 8u;
+  const unsigned col_p2 = (unsigned)min(c0 + 2, pmax) * 8u;
+  const unsigned col_l1 = (unsigned)min(max(c0 - 1, 0), nx - 1) * 8u;  // DERIVE: su_int left of the pair
+
+  const unsigned row = (unsigned)a.s_now.s1 * 8u;
+  const unsigned plane = (unsigned)k * (unsigned)a.s_now.s2 * 8u;
+  const unsigned grow = (unsigned)a.gamma.s1 * 8u;
+  const double2 zero2 = make_double2(0.0, 0.0);
+
+  // window for the y-face j0 (rows j0-E .. j0+E-1) and its flux
+  double2 ws[NW];
+#pragma unroll
+  for (int m = 0; m < NW; ++m) ws[m] = ld2o(a.s_int.p, plane + (unsigned)max(j0 - E + m, 0) * row + col);
+  unsigned o = plane + (unsigned)j0 * row;  // row r, column 0
+  unsigned og = (unsigned)j0 * grow + col;
+  double2 sv_lo = zero2;
+  double fy0, fy1;
+  {
+    double w0[NW], w1[NW];
+#pragma unroll
+    for (int m = 0; m < NW; ++m) { w0[m] = ws[m].x; w1[m] = ws[m].y; }
+    double vq0, vq1;
+    if (DERIVE) {
+      sv_lo = ld2o(a.sv_int.p, o + col);
+      const double2 sv_m = ld2o(a.sv_int.p, plane + (unsigned)max(j0 - 1, 0) * row + col);
+      vq0 = F::prep(qdiv(sv_m.x + sv_lo.x, ws[E - 1].x + ws[E].x), a.fc);
+      vq1 = F::prep(qdiv(sv_m.y + sv_lo.y, ws[E - 1].y + ws[E].y), a.fc);
+    } else {
+      const double2 v0 = ld2o(a.v_int.p, o + col);
+      vq0 = F::prep(v0.x, a.fc);
+      vq1 = F::prep(v0.y, a.fc);
+    }
+    fy0 = F::eval_v(vq0, w0);
+    fy1 = F::eval_v(vq1, w1);
+  }
+
+  struct Row {
+    double2 s_w, v_n, u_c, s_now, gam;  // DERIVE: v_n = sv_int at row r+1, u_c = su_int at row r
+  };
+  auto load_row = [&](unsigned orow, unsigned ogam) {
+    Row L;
+    L.s_w = ld2o(a.s_int.p, orow + E * row + col);
+    L.v_n = ld2o(DERIVE ? a.sv_int.p : a.v_int.p, orow + row + col);
+    L.u_c = ld2o(DERIVE ? a.su_int.p : a.u_int.p, orow + col);
+    L.s_now = ld2o(a.s_now.p, orow + col);
+    L.gam = ld2o(a.gamma.p, ogam);
+    return L;
+  };
+  Row nxt = load_row(o, og);
+  for (int r = j0; r < jend; ++r) {
+    const Row cur = nxt;
+    nxt = load_row(o + row, og + grow);
+    if (r + 4 < jend && (lane & 7) == 0) {  // DRAM -> L2 a few rows ahead, one request per 128-byte line
+      prefetch_l2(a.s_int.p, o + (E + 4) * row + col);
+      prefetch_l2(DERIVE ? a.sv_int.p : a.v_int.p, o + 5 * row + col);
+      prefetch_l2(DERIVE ? a.su_int.p : a.u_int.p, o + 4 * row + col);
+      prefetch_l2(a.s_now.p, o + 4 * row + col);
+    }
+#pragma unroll
+    for (int m = 0; m < NW - 1; ++m) ws[m] = ws[m + 1];
+    ws[NW - 1] = cur.s_w;  // ws[m] = s_int at row r - E + 1 + m
+    // ---- y-faces r+1 of both columns
+    double vq0, vq1;
+    if (DERIVE) {
+      vq0 = F::prep(qdiv(sv_lo.x + cur.v_n.x, ws[E - 1].x + ws[E].x), a.fc);
+      vq1 = F::prep(qdiv(sv_lo.y + cur.v_n.y, ws[E - 1].y + ws[E].y), a.fc);
+      sv_lo = cur.v_n;
+    } else {
+      vq0 = F::prep(cur.v_n.x, a.fc);
+      vq1 = F::prep(cur.v_n.y, a.fc);
+    }
+    double fy0_p, fy1_p;
+    {
+      double w0[NW], w1[NW];
+#pragma unroll
+      for (int m = 0; m < NW; ++m) { w0[m] = ws[m].x; w1[m] = ws[m].y; }
+      fy0_p = F::eval_v(vq0, w0);
+      fy1_p = F::eval_v(vq1, w1);
+    }
+    // ---- x-faces at row r: xc[m] = s_int at column c0 - E + m, m = 0 .. 2E
+    double xc[NW + 1];
+    {
+      const double2 ownp = ws[E - 1];
+      const double2 n2 = ld2o(a.s_int.p, o + col_m2), p2 = ld2o(a.s_int.p, o + col_p2);
+      double2 n4 = zero2;
+      if (E >= 3) n4 = ld2o(a.s_int.p, o + col_m4);
+#pragma unroll
+      for (int m = 0; m <= NW; ++m) {
+        const int d = m - E;
+        xc[m] = d == -3 ? n4.y : d == -2 ? n2.x : d == -1 ? n2.y : d == 0 ? ownp.x : d == 1 ? ownp.y
+                : d == 2 ? p2.x : p2.y;
+      }
+    }
+    double uq0, uq1;
+    if (DERIVE) {  // u at the left face of c0 and at the face between c0 and c1
+      const double su_l = ldo(a.su_int.p, o + col_l1);
+      uq0 = F::prep(qdiv(su_l + cur.u_c.x, xc[E - 1] + xc[E]), a.fc);
+      uq1 = F::prep(qdiv(cur.u_c.x + cur.u_c.y, xc[E] + xc[E + 1]), a.fc);
+    } else {
+      uq0 = F::prep(cur.u_c.x, a.fc);
+      uq1 = F::prep(cur.u_c.y, a.fc);
+    }
+    const double fx0 = F::eval_v(uq0, xc), fx1 = F::eval_v(uq1, xc + 1);
+    const double fx2 = __shfl_down_sync(0xffffffffu, fx0, 1);
+
+    // ---- point updates (prognostics/utils.py:L95-L99) and first relaxation (rk3ws_si.py:L184-L189)
+    const bool row_int = r >= nb && r < ny - nb;
+    double v0, v1;
+    if (row_int && int0) {
+      const double div = (fx1 - fx0) / a.fc.dx + (fy0_p - fy0) / a.fc.dy;
+      v0 = cur.s_now.x - a.dt * (div - 0.0);
+    } else {
+      v0 = 0.0;
+    }
+    if (row_int && int1) {
+      const double div = (fx2 - fx1) / a.fc.dx + (fy1_p - fy1) / a.fc.dy;
+      v1 = cur.s_now.y - a.dt * (div - 0.0);
+    } else {
+      v1 = 0.0;
+    }
+    const double g0 = cur.gam.x, g1 = cur.gam.y;
+    if (own && ((!(row_int && int0) && g0 != 1.0) || (!(row_int && int1) && g1 != 1.0))) {
+      // untouched by K1 and not overwritten by the relaxation: keep what the storage holds
+      const double2 old = ld2o(a.s_new.p, o + col);
+      if (!(row_int && int0) && g0 != 1.0) v0 = old.x;
+      if (!(row_int && int1) && g1 != 1.0) v1 = old.y;
+    }
+    if (own && (g0 != 0.0 || g1 != 0.0)) {
+      const double2 ref = ld2o(a.s_ref.p, o + col);
+      if (g0 != 0.0) v0 = relax_point(g0, v0, ref.x);
+      if (g1 != 0.0) v1 = relax_point(g1, v1, ref.y);
+    }
+    if (out1) {
+      *reinterpret_cast<double2 *>(reinterpret_cast<char *>(a.spre.p) + (o + col)) = make_double2(v0, v1);
+    } else if (out0) {
+      sto(a.spre.p, o + col, v0);
+    }
+    fy0 = fy0_p;
+    fy1 = fy1_p;
+    o += row;
+    og += grow;
   }
 }
 
@@ -1803,9 +1982,28 @@ bool b_coop(const StageArgs &a) {
   return (long long)a.nx * a.ny < (long long)LJ_TARGET_WARPS * 32;
 }
 
+int a_impl() {  // TB200_A_IMPL=one|two (columns per lane)
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("TB200_A_IMPL");
+    impl = (e != nullptr && strcmp(e, "one") == 0) ? 1 : 2;
+  }
+  return impl;
+}
+
 template <int SCHEME, int LJ>
 int launch_a(const StageArgs &a, cudaStream_t st) {
   constexpr int WARPS = 4;
+  if (a_impl() == 2 && a.a2_ok) {
+    const int chunks2 = (a.nx + A2_COLS - 1) / A2_COLS;
+    dim3 block2(32 * WARPS, 1, 1);
+    dim3 grid2((chunks2 + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
+    if (a.derive_uv)
+      stage_a2_kernel<SCHEME, LJ, true><<<grid2, block2, 0, st>>>(a);
+    else
+      stage_a2_kernel<SCHEME, LJ, false><<<grid2, block2, 0, st>>>(a);
+    return check_launch("isentropic_stage_dry/A(2 columns)");
+  }
   const int chunks = (a.nx + A_COLS - 1) / A_COLS;
   dim3 block(32 * WARPS, 1, 1);
   dim3 grid((chunks + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
@@ -1833,7 +2031,8 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
   prof_mark(0, st);
   if (s_impl() != 0 && a.nz <= 64) {
     {
-      const int lj = pick_lj((a.nx + A_COLS - 1) / A_COLS, a.ny, a.nz);
+      const int acols = (a_impl() == 2 && a.a2_ok) ? A2_COLS : A_COLS;
+      const int lj = pick_lj((a.nx + acols - 1) / acols, a.ny, a.nz);
       const int rc = lj == 16 ? launch_a<SCHEME, 16>(a, st)
                      : lj == 8 ? launch_a<SCHEME, 8>(a, st) : launch_a<SCHEME, 64>(a, st);
       if (rc) return rc;
@@ -2046,6 +2245,7 @@ int stage_entry(
   }
   TB200_REQUIRE(a.ntr == 0 || (a.part == 0 && s_impl() != 0 && a.nz <= 64),
                 "isentropic_stage_moist: needs the default kernel path (A + B), an unsplit stage and nz <= 64");
+  a.a2_ok = mv2_ok(a) ? 1 : 0;
   if (!lazy_uv_path(a)) {
     // the other kernel variants keep the reference's data flow (see lazy_uv_path)
     TB200_REQUIRE(a.spre.p != a.s_new.p,

@@ -19,6 +19,7 @@ struct StageArgs {
   int bx0, by0;    // block offsets of a partial launch of the momentum kernel
   int part, rim[4];  // tb200_isentropic_stage.part / .rim
   int derive_uv, skip_uv;  // tb200_isentropic_stage.derive_uv_in / .skip_uv_out
+  int a2_ok;               // the layout allows the two-column kernels (16-byte aligned pairs)
   double dt, dt_full, dx, dy, dz, eps, pt, theta_s, pref, rd, g, cp;
   FluxConst fc;
   CDiv two_dx, two_dy, cpref;
