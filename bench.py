@@ -226,14 +226,63 @@ def cpu_baseline(seconds_budget=20.0, grid=(161, 161, 60)):
     }, steps, el
 
 
+def reference_root():
+    """Where the UNMODIFIED reference sources are, if they are around: $TASMANIA_REFERENCE, or the
+    copy staged by baseline/stage_reference.sh under the git-ignored baseline/_ref (which travels
+    to the GPU box with the snapshot).  /root/reference itself is never read here."""
+    for cand in (os.environ.get("TASMANIA_REFERENCE"), os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "src", "tasmania")):
+            return cand
+    return None
+
+
+def cpu_baseline_reference(seconds_budget=20.0, grid=(161, 161, 60)):
+    """The reference ITSELF on its numpy backend (kind "reference"): its own Domain, Relaxed
+    boundary, state builder, RK3WSSI prognostic, Rayleigh damper, HorizontalVelocity,
+    IsentropicDiagnostics and ``IsentropicDynamicalCore.stage_array_call_dry``, imported in place
+    from the staged sources and chained like framework/dycore.py does (tests/ref_dycore_steps.py;
+    only the sympl wrappers, which are not installable offline, are replaced by that driver).
+    Same workload as ``cpu_baseline``: RK3WS + fifth-order upwind steps + diagnostics refresh."""
+    os.environ["TASMANIA_REFERENCE"] = reference_root()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_dycore_steps as rds
+
+    nx, ny, nz = grid
+    clock = {"budget": seconds_budget}
+    rds.run("numpy", 50, nx, ny, nz, clock=clock, damp_depth=15, topo_seconds=1800)
+    steps, el = clock["steps"], clock["seconds"]
+    return {
+        "value": nx * ny * nz * steps / el / 1e6,
+        "unit": "Mpts*steps/s",
+        "cores": 1,
+        "kind": "reference",
+        "sample": f"{steps} RK3WS steps (+diagnostics refresh) of the same dry isentropic workload on "
+                  f"{nx}x{ny}x{nz} by the UNMODIFIED reference (stubbiali/tasmania, numpy backend, its own "
+                  f"stage_array_call_dry; sources staged under baseline/_ref), 1 thread of "
+                  f"{os.cpu_count()} host cores, {el:.1f} s; the reference's gt4py CPU backends are "
+                  f"not installable offline",
+    }, steps, el
+
+
 def _replica(job):
     """One replica of the bounded sample (runs in a spawned worker process)."""
-    seconds_budget, grid = job
-    base, steps, el = cpu_baseline(seconds_budget=seconds_budget, grid=grid)
+    seconds_budget, grid = job[:2]
+    fn = cpu_baseline_reference if (len(job) > 2 and job[2] == "reference") else cpu_baseline
+    base, steps, el = fn(seconds_budget=seconds_budget, grid=grid)
     return base["value"], steps, el
 
 
-def cpu_baseline_all_cores(seconds_budget, grid):
+def cpu_baseline_one(seconds_budget, grid, kind):
+    """One timed replica in a fresh process (the reference's loader installs import stubs for the
+    packages it cannot have offline: kept out of the benchmark process)."""
+    import multiprocessing as mp
+
+    with mp.get_context("spawn").Pool(1) as pool:
+        fn = cpu_baseline_reference if kind == "reference" else cpu_baseline
+        return pool.apply(fn, (seconds_budget, grid))
+
+
+def cpu_baseline_all_cores(seconds_budget, grid, kind="port"):
     """The reference has no threading and no domain decomposition (SURVEY.md header): one Python
     thread drives single-threaded numpy element-wise code.  The only way its code uses every host
     core is one independent replica of the workload per core, which is what is timed here: the
@@ -248,7 +297,7 @@ def cpu_baseline_all_cores(seconds_budget, grid):
     cores = min(cores, 32)  # bounds host memory (a replica holds ~0.5 GB of fields and temporaries)
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_replica, [(seconds_budget, grid)] * cores, chunksize=1)
+        res = pool.map(_replica, [(seconds_budget, grid, kind)] * cores, chunksize=1)
     return cores, res
 
 
@@ -265,17 +314,20 @@ def run_reference(args):
     nx, ny, nz = WORKLOADS["c2"]
     pts = nx * ny * nz
     budget = min(60.0, 4.0 * max(1, args.steps))
-    one, _, _ = cpu_baseline(seconds_budget=min(10.0, budget), grid=(nx, ny, nz))
-    cores, res = cpu_baseline_all_cores(budget, (nx, ny, nz))
+    kind = "reference" if reference_root() is not None else "port"
+    one, _, _ = cpu_baseline_one(min(10.0, budget), (nx, ny, nz), kind)
+    cores, res = cpu_baseline_all_cores(budget, (nx, ny, nz), kind)
     val = sum(r[0] for r in res)
     steps = sum(r[1] for r in res)
     el = max(r[2] for r in res)
     base = {
-        "value": val, "unit": "Mpts*steps/s", "cores": cores, "kind": "port",
+        "value": val, "unit": "Mpts*steps/s", "cores": cores, "kind": kind,
         "single_thread_value": one["value"],
         "sample": f"{cores} independent replicas (one per host core; the reference itself is "
-                  f"single-threaded) of the same dry isentropic workload on {nx}x{ny}x{nz}, numpy "
-                  f"oracle, {steps} RK3WS steps (+diagnostics refresh) in total in {el:.1f} s; one "
+                  f"single-threaded) of the same dry isentropic workload on {nx}x{ny}x{nz}, "
+                  + ("the UNMODIFIED reference on its numpy backend (sources staged under baseline/_ref), "
+                     if kind == "reference" else "numpy oracle (port of the reference's numpy backend), ") +
+                  f"{steps} RK3WS steps (+diagnostics refresh) in total in {el:.1f} s; one "
                   f"replica alone: {one['value']:.2f} Mpts*steps/s; the reference's gt4py CPU "
                   f"backends are not installable offline",
     }
@@ -452,7 +504,8 @@ def run_b200(args):
     if rank == 0:
         base = None
         if world == 1 and not args.no_cpu_baseline:
-            base, _, _ = cpu_baseline()
+            base, _, _ = cpu_baseline_one(20.0, WORKLOADS["c2"],
+                                          "reference" if reference_root() is not None else "port")
         line = {
             "metric": "grid-point updates/sec", "value": value, "unit": "Mpts*steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -268,8 +268,11 @@ __global__ void __launch_bounds__(128, DERIVE ? 6 : 7) stage_a_kernel(const Stag
 // the bytes in flight per load, and address arithmetic, loop control and the relaxation logic are
 // paid once per two points.  One warp = 64 columns, 62 of them owned (lane 31 lends the left face
 // of its pair).  The x-neighbours of the pair are the pairs at c0 - 4, c0 - 2 and c0 + 2 (L1).
-// Requirements as for the two-column momentum kernel (mv2_ok); TB200_A_IMPL=one selects the
-// one-column kernel.  Bit-identical results (tests/test_gpu_stage_variants.py).
+// Requirements as for the two-column momentum kernel (mv2_ok).  NOT the default
+// (TB200_A_IMPL=two selects it): measured SLOWER than the one-column kernel at config 5 -- 0.575 /
+// 0.87 ms against 0.51 / 0.735 ms per launch (round 2): 118-126 registers leave 16 warps per SM
+// where the one-column kernel has 28, and this kernel lives on warps in flight, not on
+// instruction count.  Kept as a tested variant (bit-identical, tests/test_gpu_stage_variants.py).
 constexpr int A2_COLS = 62;
 __device__ __forceinline__ double2 ld2o(const double *base, unsigned off) {
   return __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + off));
@@ -545,8 +548,12 @@ __global__ void __launch_bounds__(256) stage_tracers_kernel(const StageArgs a) {
 //            left neighbour by shuffle, y-fluxes through shared memory;
 //   phase 3  divergence, step, division by the stage's s, clipping, relaxation, store.
 // Same point formulas in the same order as the kernel above, hence the same bits.
-constexpr int TT_X = 31, TT_Y = 16;
-template <int SCHEME, bool DERIVE>
+// Tile height TT_Y (TB200_T_ROWS=4|8|16, default 8): the phases of a block are separated by
+// barriers, so loads and arithmetic only overlap ACROSS blocks; 16-row tiles (544 threads, two
+// blocks per SM) ran at 29 % of the DRAM bandwidth (profiles/README.md, round 2), shorter tiles
+// trade y-halo work for more resident blocks.
+constexpr int TT_X = 31;
+template <int SCHEME, bool DERIVE, int TT_Y>
 __global__ void __launch_bounds__(32 * (TT_Y + 1)) stage_tracers_tile_kernel(const StageArgs a) {
   using F = Flux<SCHEME>;
   constexpr int E = F::extent;
@@ -641,12 +648,21 @@ int t_impl() {  // TB200_T_IMPL=point|tile
 template <int SCHEME>
 int launch_tracers(const StageArgs &a, cudaStream_t st) {
   if (t_impl() == 1) {
-    dim3 block(32, TT_Y + 1, 1);
-    dim3 grid((a.nx + TT_X - 1) / TT_X, (a.ny + TT_Y - 1) / TT_Y, a.nz);
-    if (a.derive_uv)
-      stage_tracers_tile_kernel<SCHEME, true><<<grid, block, 0, st>>>(a);
-    else
-      stage_tracers_tile_kernel<SCHEME, false><<<grid, block, 0, st>>>(a);
+    static int rows = -1;
+    if (rows < 0) {
+      const char *e = getenv("TB200_T_ROWS");
+      rows = e == nullptr ? 8 : atoi(e);
+      if (rows != 4 && rows != 8 && rows != 16) rows = 8;
+    }
+    dim3 block(32, rows + 1, 1);
+    dim3 grid((a.nx + TT_X - 1) / TT_X, (a.ny + rows - 1) / rows, a.nz);
+#define TB200_T_LAUNCH(R)                                                     \
+    if (a.derive_uv)                                                          \
+      stage_tracers_tile_kernel<SCHEME, true, R><<<grid, block, 0, st>>>(a);  \
+    else                                                                      \
+      stage_tracers_tile_kernel<SCHEME, false, R><<<grid, block, 0, st>>>(a);
+    if (rows == 4) { TB200_T_LAUNCH(4) } else if (rows == 16) { TB200_T_LAUNCH(16) } else { TB200_T_LAUNCH(8) }
+#undef TB200_T_LAUNCH
     return check_launch("isentropic_stage_moist/T(tile)");
   }
   dim3 block(64, 4, 1);
@@ -1982,11 +1998,11 @@ bool b_coop(const StageArgs &a) {
   return (long long)a.nx * a.ny < (long long)LJ_TARGET_WARPS * 32;
 }
 
-int a_impl() {  // TB200_A_IMPL=one|two (columns per lane)
+int a_impl() {  // TB200_A_IMPL=one|two (columns per lane; default one)
   static int impl = -1;
   if (impl < 0) {
     const char *e = getenv("TB200_A_IMPL");
-    impl = (e != nullptr && strcmp(e, "one") == 0) ? 1 : 2;
+    impl = (e != nullptr && strcmp(e, "two") == 0) ? 2 : 1;
   }
   return impl;
 }

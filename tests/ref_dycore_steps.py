@@ -43,9 +43,11 @@ DT = timedelta(seconds=5)
 OUTNAMES = (S, SU, U, SV, V)
 
 
-def run(backend, nsteps, nx, ny, nz):
+def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20):
     """``nsteps`` RK3WS + fifth-order-upwind steps of the mountain-flow case on ``backend``;
-    returns the final state as numpy arrays."""
+    returns the final state as numpy arrays.  ``clock`` (a dict with a "budget" in seconds): the
+    step loop is timed (set-up excluded) and stops once the budget is spent -- how ``bench.py
+    --impl reference`` times the reference's own numpy backend; "steps" and "seconds" are set."""
     from tasmania.framework import allocators as ta
     from tasmania.framework.generic_functions import to_numpy
 
@@ -60,7 +62,7 @@ def run(backend, nsteps, nx, ny, nz):
         DataArray([400, 280], dims="z", attrs={"units": "K"}), nz,
         horizontal_boundary_type="relaxed", nb=NB, horizontal_boundary_kwargs={"nr": NR},
         backend=backend, topography_type="gaussian",
-        topography_kwargs={"time": timedelta(seconds=20), "max_height": da(0.5, "km"),
+        topography_kwargs={"time": timedelta(seconds=topo_seconds), "max_height": da(0.5, "km"),
                            "width_x": da(50.0, "km"), "width_y": da(50.0, "km"), "smooth": False})
     grid = domain.numerical_grid
     st = refload.load("tasmania.isentropic.state")
@@ -84,7 +86,7 @@ def run(backend, nsteps, nx, ny, nz):
     prognostic = prog.IsentropicPrognostic.factory(
         "rk3ws_si", "fifth_order_upwind", domain, False, backend=backend, backend_options=bo(),
         storage_shape=shape, storage_options=so(), pt=da(pt, "Pa"), eps=0.5)
-    damper = vd.VerticalDamping.factory("rayleigh", grid, 4, 5e-4, backend=backend, backend_options=bo(),
+    damper = vd.VerticalDamping.factory("rayleigh", grid, damp_depth, 5e-4, backend=backend, backend_options=bo(),
                                         storage_shape=shape, storage_options=so())
     velocity = dd.HorizontalVelocity(grid, staggering=True, backend=backend, backend_options=bo(),
                                      storage_options=so())
@@ -106,6 +108,9 @@ def run(backend, nsteps, nx, ny, nz):
     stage_outs = [{k: zeros() for k in OUTNAMES} for _ in range(prognostic.stages - 1)]
     spare = {k: zeros() for k in OUTNAMES}
     stage_call = dyc.IsentropicDynamicalCore.stage_array_call_dry
+    import time as _time
+
+    t_start = _time.perf_counter()
     for step in range(nsteps):
         grid.update_topography((step + 1) * DT)
         outs = stage_outs + [spare]
@@ -122,6 +127,10 @@ def run(backend, nsteps, nx, ny, nz):
         # the role dv plays in driver_namelist_sus.py:L188-L199
         diagnostics.get_diagnostic_variables(new[S], pt, new[P], new[EXN], new[MTG], new[H])
         cur = new
+        if clock is not None:
+            clock["steps"], clock["seconds"] = step + 1, _time.perf_counter() - t_start
+            if clock["seconds"] > clock["budget"]:
+                break
     return {k: np.array(to_numpy(v)) for k, v in cur.items() if k != "time"}
 
 

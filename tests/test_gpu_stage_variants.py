@@ -49,11 +49,11 @@ def test_stage_kernel_variants_are_bitwise_identical(flux):
     assert _digest(flux, TB200_S_IMPL="column", TB200_STAGE_IMPL="tma") == ref
     assert _digest(flux, TB200_MV_IMPL="window") == ref
     assert _digest(flux, TB200_MV_IMPL="ring") == ref
-    # the s-step with one column per lane (the default has two), the velocities read instead of
+    # the s-step with two columns per lane (the default has one), the velocities read instead of
     # re-diagnosed in the kernels, and the three block shapes of the momentum kernel
-    assert _digest(flux, TB200_A_IMPL="one") == ref
+    assert _digest(flux, TB200_A_IMPL="two") == ref
     assert _digest(flux, TB200_LAZY_UV="0") == ref
-    assert _digest(flux, TB200_A_IMPL="one", TB200_LAZY_UV="0", TB200_LJ="64") == ref
+    assert _digest(flux, TB200_A_IMPL="two", TB200_LAZY_UV="0", TB200_LJ="64") == ref
     assert _digest(flux, TB200_LJ="64", TB200_MV_BLOCK="3x1") == _digest(flux, TB200_LJ="64", TB200_MV_BLOCK="6x1") == ref
 
 
