@@ -302,6 +302,22 @@ class Dirichlet(HorizontalBoundary):
             vals = np.asarray(core(time, g, sx, sy, field_name, field_units))
             field[sx, sy, : vals.shape[2]] = vals
 
+    def set_outermost_layers_x(self, field, field_name=None, field_units=None, time=None):
+        """dirichlet.py:L161-L190: the two outermost x-layers from the core (host code, uploaded)."""
+        core, g = self.core, self.grid
+        mi, mj, _ = _extent(self.nx, self.ny, self.nz, field_name)
+        for sx in (slice(0, 1), slice(mi - 1, mi)):
+            vals = np.asarray(core(time, g, sx, slice(0, mj), field_name, field_units))
+            field[sx, slice(0, mj), : vals.shape[2]] = vals
+
+    def set_outermost_layers_y(self, field, field_name=None, field_units=None, time=None):
+        """dirichlet.py:L192-L220."""
+        core, g = self.core, self.grid
+        mi, mj, _ = _extent(self.nx, self.ny, self.nz, field_name)
+        for sy in (slice(0, 1), slice(mj - 1, mj)):
+            vals = np.asarray(core(time, g, slice(0, mi), sy, field_name, field_units))
+            field[slice(0, mi), sy, : vals.shape[2]] = vals
+
     def get_numerical_field(self, field, field_name=None):
         return field
 

@@ -379,11 +379,15 @@ class TendencyStepper(StencilFactory):
             # the diagnostics returned are those of the first stage (rk2.py:L62-L71)
             diags = out_diagnostics if stage == 0 else self._diagnostics
             self.prognostic(cur, timestep, out_tendencies=self._increment, out_diagnostics=diags)
-            if names:
-                outs = [out_state[n] for n in names]
-                stencils.fma_fields(outs, [state[n] for n in names],
-                                    [self._increment[n] for n in names], c * dt,
-                                    origin=(0, 0, 0), domain=outs[0].shape)
+            # one launch per storage shape (a stepped field may be a one-level 2-D field), like
+            # plugin._batch_dict_operator_fma does for the reference's DataArrayDictOperator.fma
+            groups = {}
+            for n in names:
+                groups.setdefault(tuple(out_state[n].shape), []).append(n)
+            for shape, ns in groups.items():
+                stencils.fma_fields([out_state[n] for n in ns], [state[n] for n in ns],
+                                    [self._increment[n] for n in ns], c * dt,
+                                    origin=(0, 0, 0), domain=shape)
             if self._hb is not None:
                 self._hb.enforce_raw(out_state, {n: {} for n in names})
             if stage < len(self._factors) - 1:
