@@ -464,7 +464,8 @@ def run_b200(args):
                  if getattr(run, "overlap", None) is not None else ("after each stage" if distributed else "none"))
     if distributed:
         halo_mode += {"p2p": "; NVLink peer stores into the neighbours' receive buffers (tb200_halo_push / "
-                             "tb200_halo_pull over CUDA IPC), no NCCL on the path",
+                             "tb200_halo_pull over CUDA IPC), no NCCL on the path, "
+                             f"{getattr(run.sub.halo, 'phases', 2)} phase(s) per exchange",
                       "nccl": "; torch.distributed point-to-point messages (NCCL)"}[run.transport]
     api = ("tasmania_b200.distributed.DecomposedDryRun.step" if distributed else
            "tasmania_b200.isentropic_dry.IsentropicDryRun.step") + \
@@ -860,7 +861,8 @@ def end_to_end(run, args, world, barrier, distributed):
     pts = run.nx * run.ny * run.nz
     return {"value": pts * steps * world / (ms * 1e-3) / 1e6, "unit": "Mpts*steps/s",
             "h2d_bytes_per_step": nbytes(host_in), "d2h_bytes_per_step": nbytes(host_out),
-            "steps": steps, "api": "tasmania_b200.pipeline.HostStreamedDryCore.step (prognostic fields "
+            "steps": steps, "pinned_buffers_numa_node": getattr(pipe, "numa_node", None),
+            "api": "tasmania_b200.pipeline.HostStreamedDryCore.step (prognostic fields "
                                    "s, su, sv over PCIe; Montgomery potential and velocities diagnosed on the device)"}
 
 

@@ -467,13 +467,14 @@ int tb200_halo_unpack(const tb200_field *const *fields, int nfields, const doubl
  * counterpart (the reference is single-process; north_star: "NCCL/P2P halo exchange over NVLink").
  * A rank allocates its receive buffers and arrival counters with tb200_p2p_alloc, exports the
  * allocation (CUDA IPC handle, 64 bytes, passed to the neighbours by any host channel) and
- * imports the neighbours' ones.  tb200_halo_push packs the send slabs of up to two sides of a
- * phase STRAIGHT into the neighbours' receive buffers (peer stores) and raises their arrival
- * counters; tb200_halo_pull waits for the own counters and unpacks.  Receive buffers hold two
+ * imports the neighbours' ones.  tb200_halo_push packs the send slabs of up to
+ * TB200_HALO_MAX_SIDES sides STRAIGHT into the neighbours' receive buffers (peer stores) and raises
+ * their arrival counters; tb200_halo_pull waits for the own counters and unpacks.  Receive buffers hold two
  * slots of slot_doubles (exchange q uses slot q & 1; see csrc/halo.cu for why two suffice);
  * `channel` = TB200_P2P_CHANNEL_BYTES of zeroed device memory per phase (sequence numbers, kept
  * on the device so that the launches can be captured in a CUDA graph).  Both sides of a pair must
  * issue their pushes / pulls in the same order. */
+#define TB200_HALO_MAX_SIDES 8 /* four faces + four corner blocks in one launch */
 #define TB200_P2P_HANDLE_BYTES 64
 #define TB200_P2P_CHANNEL_BYTES 32
 typedef struct {

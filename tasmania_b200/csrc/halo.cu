@@ -85,7 +85,9 @@ extern "C" int tb200_halo_unpack(const tb200_field *const *fields, int nfields,
 // neighbour's memory and then raises the neighbour's arrival counter (system-scope release); the
 // neighbour's unpack kernel waits for the counter (system-scope acquire) and scatters the slab
 // into its halo.  No send buffer, no NCCL call, no host synchronisation: one `push` and one
-// `pull` launch per phase for BOTH sides of the phase, capturable in a CUDA graph.
+// `pull` launch for ALL sides of an exchange (the four faces and the four corner blocks of a
+// single-phase exchange, or the two faces of one phase of a two-phase one), capturable in a CUDA
+// graph.
 //
 // Flow control without acknowledgements: a receive buffer has two slots, exchange number q goes
 // to slot q & 1.  A rank can only push exchange q + 2 after it has pulled exchange q + 1 from the
@@ -113,7 +115,7 @@ struct SideDev {
   int si0, sj0, ri0, rj0, di, dj;      // send / receive origin and extent in (i, j)
 };
 struct Sides {
-  SideDev s[2];
+  SideDev s[TB200_HALO_MAX_SIDES];
   int n;
 };
 
@@ -192,7 +194,8 @@ int run_p2p(const tb200_field *const *fields, int nfields, const tb200_halo_side
   TB200_REQUIRE(fields != nullptr && sides != nullptr && channel != nullptr, "%s: NULL argument", what);
   TB200_REQUIRE(nfields >= 1 && nfields <= TB200_HALO_MAX_FIELDS, "%s: 1..%d fields, got %d", what,
                 TB200_HALO_MAX_FIELDS, nfields);
-  TB200_REQUIRE(nsides >= 0 && nsides <= 2, "%s: 0..2 sides per phase, got %d", what, nsides);
+  TB200_REQUIRE(nsides >= 0 && nsides <= TB200_HALO_MAX_SIDES, "%s: 0..%d sides per launch, got %d", what,
+                TB200_HALO_MAX_SIDES, nsides);
   if (nsides == 0 || dk <= 0) return TB200_OK;
   HaloFields hf{};
   hf.n = nfields;

@@ -12,7 +12,9 @@
 //
 // All are point-wise in (i, j) with at most k+1 / k-1 / k-2 neighbours: one thread per point,
 // i along the warp, pure streams (88 / 64 / 24 / 40 B per point).  Operation order is the
-// reference's; the transcendental calls (exp, pow) are CUDA libm (<= 2 ulp, glibc/numpy <= 1 ulp),
+// reference's; exp is CUDA libm (<= 2 ulp, glibc/numpy <= 1 ulp), the powers of positive arguments
+// go through the kernels' own pow_pos (stencil_math.cuh: <= 1.7e-16 relative, a third of the
+// instructions of CUDA's generic pow; anything outside its domain falls back to that),
 // so these stencils are held to 1e-13 relative instead of bit-exactness.  x ** 0.5 and x ** 2.0
 // are sqrt and x * x in numpy (scalar-power fast paths) and here.
 #include "stencil_math.cuh"
@@ -77,7 +79,7 @@ extern "C" int tb200_kessler(const tb200_field *in_rho, const tb200_field *in_p,
                       main_level(p, exn, i, j, k, apoil, pm, em);
                       const double c = qc(i, j, k), r = qr(i, j, k);
                       const double ar = k1 * (c > a ? c - a : 0.0);
-                      const double cr = k2 * c * (r > 0.0 ? pow(r, 0.875) : 0.0);
+                      const double cr = k2 * c * (r > 0.0 ? pow_pos(r, 0.875) : 0.0);
                       if (!evap) {
                         set_output(tqc(i, j, k), -(ar + cr), ow_qc);
                         set_output(tqr(i, j, k), ar + cr, ow_qr);
@@ -85,7 +87,7 @@ extern "C" int tb200_kessler(const tb200_field *in_rho, const tb200_field *in_p,
                       }
                       const double qvs = saturation_mixing_ratio(t(i, j, k), pm, beta);
                       const double er =
-                          r > 0.0 ? 0.0484794 * (qvs - qv(i, j, k)) * pow(rho(i, j, k) * r, 13.0 / 20.0)
+                          r > 0.0 ? 0.0484794 * (qvs - qv(i, j, k)) * pow_pos(rho(i, j, k) * r, 13.0 / 20.0)
                                   : 0.0;
                       set_output(tqv(i, j, k), er, ow_qv);
                       set_output(tqc(i, j, k), -(ar + cr), ow_qc);
@@ -176,7 +178,7 @@ extern "C" int tb200_fall_velocity(const tb200_field *in_rho, const tb200_field 
                       i += i0; j += j0; k += k0;
                       const double r = qr(i, j, k), d = rho(i, j, k);
                       const double w = 1.0e-3 * d * (r > 0.0 ? r : 0.0);
-                      vt(i, j, k) = 36.34 * (w > 0.0 ? pow(w, 0.1346) : 0.0) * sqrt(rho_s(i, j, k) / d);
+                      vt(i, j, k) = 36.34 * (w > 0.0 ? pow_pos(w, 0.1346) : 0.0) * sqrt(rho_s(i, j, k) / d);
                     });
 }
 

@@ -146,6 +146,34 @@ class Decomposition:
                                 (nxl, h)))
         return out
 
+    def sides_single_phase(self, rank) -> List[Side]:
+        """The same halo in ONE phase: x faces over the owned rows, y faces over the owned columns
+        and the four corner blocks from the diagonal neighbours (what the two-phase plan routes
+        through an x- and a y-neighbour).  Same final halo contents, half the synchronisations."""
+        cx, cy = self.coords(rank)
+        nxl, nyl = self.local_shape(rank)
+        hw, he, hs, hn = self.halos(rank)
+        h = self.halo
+        ox0, ox1, oy0, oy1 = hw, nxl - he, hs, nyl - hn  # owned block, local indices
+        out = []
+        if hw:
+            out.append(Side("west", self.rank_of(cx - 1, cy), (hw, oy0), (0, oy0), (h, oy1 - oy0)))
+        if he:
+            out.append(Side("east", self.rank_of(cx + 1, cy), (ox1 - h, oy0), (ox1, oy0), (h, oy1 - oy0)))
+        if hs:
+            out.append(Side("south", self.rank_of(cx, cy - 1), (ox0, hs), (ox0, 0), (ox1 - ox0, h)))
+        if hn:
+            out.append(Side("north", self.rank_of(cx, cy + 1), (ox0, oy1 - h), (ox0, oy1), (ox1 - ox0, h)))
+        if hw and hs:
+            out.append(Side("sw", self.rank_of(cx - 1, cy - 1), (hw, hs), (0, 0), (h, h)))
+        if he and hs:
+            out.append(Side("se", self.rank_of(cx + 1, cy - 1), (ox1 - h, hs), (ox1, 0), (h, h)))
+        if hw and hn:
+            out.append(Side("nw", self.rank_of(cx - 1, cy + 1), (hw, oy1 - h), (0, oy1), (h, h)))
+        if he and hn:
+            out.append(Side("ne", self.rank_of(cx + 1, cy + 1), (ox1 - h, oy1 - h), (ox1, oy1), (h, h)))
+        return out
+
     def seam_faces(self, rank):
         """Staggered faces between an owned and a halo point, whose velocity must be
         re-diagnosed after the exchange: ([u face columns], [v face rows]), local indices."""
@@ -247,7 +275,8 @@ class HaloExchange:
             self.unpack(phase, fields)
 
 
-_OPPOSITE = {"west": "east", "east": "west", "south": "north", "north": "south"}
+_OPPOSITE = {"west": "east", "east": "west", "south": "north", "north": "south",
+             "sw": "ne", "ne": "sw", "se": "nw", "nw": "se"}
 
 
 def exchange_in_process(exchangers: Sequence[HaloExchange], fields_per_rank: Sequence[Sequence]):
@@ -278,11 +307,17 @@ class P2PHaloExchange(HaloExchange):
 
     COUNTER_PITCH = 128
 
-    def __init__(self, decomp: Decomposition, rank: int, nz: int, nfields: int, device=None):
+    def __init__(self, decomp: Decomposition, rank: int, nz: int, nfields: int, device=None, phases=None):
         import ctypes as C
 
         self.decomp, self.rank, self.nz, self.nfields = decomp, rank, nz, nfields
-        self.plan = [decomp.sides(rank, 0), decomp.sides(rank, 1)]
+        # one phase (faces + corner blocks from the diagonal neighbours: one push, one pull, one
+        # wait per exchange; default) or the two phases of the message-based exchange
+        # (TB200_HALO_PHASES=2)
+        self.phases = int(phases or os.environ.get("TB200_HALO_PHASES", "1"))
+        assert self.phases in (1, 2)
+        self.plan = ([decomp.sides_single_phase(rank), []] if self.phases == 1
+                     else [decomp.sides(rank, 0), decomp.sides(rank, 1)])
         self.send, self.recv = {}, {}
         self.layout, off = {}, 0
         for phase in self.plan:

@@ -24,6 +24,8 @@ from tasmania_b200.distributed import DecomposedDryRun, InProcessDecomposedRun  
 def main():
     overlap = "--overlap" in sys.argv
     transport = sys.argv[sys.argv.index("--transport") + 1] if "--transport" in sys.argv else None
+    if "--phases" in sys.argv:  # peer-store transport: 1 (faces + corners, default) or 2 phases
+        os.environ["TB200_HALO_PHASES"] = sys.argv[sys.argv.index("--phases") + 1]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
@@ -54,7 +56,8 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MGPU-OK" if int(flag.item()) == 1 else "MGPU-FAIL",
-              f"world={world} decomposition={run.decomposition} overlap={overlap} transport={run.transport}",
+              f"world={world} decomposition={run.decomposition} overlap={overlap} transport={run.transport} "
+              f"phases={getattr(run.sub.halo, 'phases', 2)}",
               flush=True)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)

@@ -133,8 +133,33 @@ def test_exchange_two_gloo_ranks():
 
 
 # ------------------------------------------------------------------ peer-to-peer transport: host logic
+@pytest.mark.parametrize("NX,NY,px,py", [(16, 9, 2, 1), (9, 16, 1, 2), (19, 17, 2, 2), (40, 23, 4, 2), (27, 30, 3, 3)])
+def test_single_phase_plan_fills_all_halos(NX, NY, px, py):
+    """The one-phase plan of the peer-store transport (faces over the owned rows / columns + corner
+    blocks from the diagonal neighbours) leaves exactly the halo contents of the two-phase plan."""
+    from tasmania_b200.distributed import _OPPOSITE
+
+    nz = 3
+    d = Decomposition(NX, NY, px, py)
+    fields = [_local_fields(d, r, nz, fill_halo=False) for r in range(d.world)]
+    plans = [d.sides_single_phase(r) for r in range(d.world)]
+    for r, plan in enumerate(plans):
+        names = [s.name for s in plan]
+        assert len(names) == len(set(names)) <= 8
+        for s in plan:
+            peer = [t for t in plans[s.neighbour] if t.name == _OPPOSITE[s.name]]
+            assert len(peer) == 1 and peer[0].neighbour == r and peer[0].extent == s.extent
+            (si, sj), (di, dj) = peer[0].send_origin, s.extent
+            ri, rj = s.recv_origin
+            for dst, src in zip(fields[r], fields[s.neighbour]):
+                dst.t[ri:ri + di, rj:rj + dj, :nz] = src.t[si:si + di, sj:sj + dj, :nz]
+    for r in range(d.world):
+        _check(d, r, fields[r], nz)
+
+
+@pytest.mark.parametrize("phases", [1, 2])
 @pytest.mark.parametrize("px,py", [(2, 1), (2, 2), (4, 2), (3, 3)])
-def test_p2p_exchange_descriptors_pair_up(monkeypatch, px, py):
+def test_p2p_exchange_descriptors_pair_up(monkeypatch, px, py, phases):
     """The tb200_halo_side descriptors of the NVLink transport, built with fake base addresses
     (no GPU): what a rank pushes towards a side lands in the OPPOSITE side's receive buffer and
     counter of exactly that neighbour, slot sizes and extents agree, and the geometry of the slab
@@ -153,14 +178,20 @@ def test_p2p_exchange_descriptors_pair_up(monkeypatch, px, py):
     monkeypatch.setattr(lib, "_lib", FakeLib())
     nz, nf = 6, 5
     d = Decomposition(24 * px, 20 * py, px, py)
-    ex = [D.P2PHaloExchange(d, r, nz, nf) for r in range(d.world)]
+    ex = [D.P2PHaloExchange(d, r, nz, nf, phases=phases) for r in range(d.world)]
     for e in ex:
         e.connect_in_process(ex)
+
+    def plan_of(rank, phase):
+        if phases == 2:
+            return d.sides(rank, phase)
+        return d.sides_single_phase(rank) if phase == 0 else []
+
     seen = set()
     for e in ex:
         spans = []
         for phase, sides in enumerate(e.plan):
-            assert [s.name for s in sides] == [s.name for s in d.sides(e.rank, phase)]
+            assert [s.name for s in sides] == [s.name for s in plan_of(e.rank, phase)]
             for m, s in enumerate(sides):
                 h, peer, opp = e.sides_c[phase][m], ex[s.neighbour], D._OPPOSITE[s.name]
                 assert h.remote_buffer == peer.base + peer.layout[opp]["buffer"]
@@ -171,7 +202,7 @@ def test_p2p_exchange_descriptors_pair_up(monkeypatch, px, py):
                 assert (tuple(h.send_origin), tuple(h.recv_origin), tuple(h.extent)) == \
                     (s.send_origin, s.recv_origin, s.extent)
                 # the slab sent is the window the neighbour receives (global indices)
-                peer_side = [t for t in d.sides(s.neighbour, phase) if t.name == opp][0]
+                peer_side = [t for t in plan_of(s.neighbour, phase) if t.name == opp][0]
                 g0, g1 = d.local(e.rank), d.local(s.neighbour)
                 assert g0[0] + s.send_origin[0] == g1[0] + peer_side.recv_origin[0]
                 assert g0[2] + s.send_origin[1] == g1[2] + peer_side.recv_origin[1]

@@ -35,11 +35,15 @@ def test_decomposed_equals_single_device_bitwise(px, py):
     assert np.abs(single.gather(SV)).max() > 0.0
 
 
+@pytest.mark.parametrize("phases", ["1", "2"])
 @pytest.mark.parametrize("px,py", [(2, 1), (2, 2), (3, 2)])
-def test_decomposed_p2p_transport_equals_single_device_bitwise(px, py):
+def test_decomposed_p2p_transport_equals_single_device_bitwise(monkeypatch, px, py, phases):
     """The NVLink peer-store transport (tb200_halo_push / tb200_halo_pull) with all sub-domains in
-    one process: every push of a phase is enqueued before the first pull."""
+    one process: every push of a phase is enqueued before the first pull.  One-phase plan (faces +
+    corner blocks, the default) and the two-phase plan of the message-based exchange."""
     from tasmania_b200.distributed import InProcessDecomposedRun
+
+    monkeypatch.setenv("TB200_HALO_PHASES", phases)
 
     NX, NY, nz = 41, 37, 9
     kw = dict(damp_depth=4, topo_seconds=20.0)
@@ -130,6 +134,7 @@ def test_two_rank_nccl_run_equals_single_device_bitwise():
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for port, extra in ((29531, ["--transport", "p2p"]), (29532, ["--transport", "p2p", "--overlap"]),
+                        (29535, ["--transport", "p2p", "--phases", "2"]),
                         (29533, ["--transport", "nccl"]), (29534, ["--transport", "nccl", "--overlap"])):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                "--master-addr", "127.0.0.1", "--master-port", str(port),
