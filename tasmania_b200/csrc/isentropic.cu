@@ -9,6 +9,9 @@
 // K3 runs one thread per (i, j) column with i along the warp, so every level is a
 // coalesced row access; the scans are sequential in k exactly as in the reference (no tree
 // reduction) to keep the summation order.
+#include <stdlib.h>
+#include <string.h>
+
 #include "stencil_math.cuh"
 
 using namespace tb200;
@@ -366,6 +369,110 @@ __global__ void __launch_bounds__(128, 2) diag_column_kernel(const DiagArgs a) {
   }
 }
 
+// diagnostic_variables for SMALL grids (same idea as stage_b_coop_kernel of the fused stage): one
+// thread per column leaves a 161 x 161 grid with 0.7 warps per scheduler walking through ~5000
+// dependent instructions (68 us where the traffic would allow 5).  A block of 32 columns x 8
+// threads keeps only what is serial serial -- the pressure prefix sum and the two suffix sums
+// (Montgomery potential, height), one add per level each -- and spreads the divisions, the Exner
+// powers (eight interfaces per thread: exactly one exner8_diag call) and the height increments
+// over all 256 threads through shared memory.  Every value is produced by the operation sequence
+// of diag_column_kernel, hence the same bits.
+__global__ void __launch_bounds__(256) diag_coop_kernel(const DiagArgs a) {
+  constexpr int NC = 64;
+  __shared__ double P[NC + 1][33];   // pressure at interface l; later the heights
+  __shared__ double EX[NC + 1][33];  // Exner function at interface l; later the Montgomery potential
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ii = blockIdx.x * 32 + tx, jj = blockIdx.y;
+  const bool live = ii < a.di;
+  const int i = (live ? ii : a.di - 1) + a.i0, j = jj + a.j0, k0 = a.k0;
+  const int n = a.n;
+  const double gdz = a.g * a.dz, cpg = a.cp * a.g;
+  // increments of the pressure sum (rows of 32 columns: coalesced)
+  {
+    const double *ps = &a.s(i, j, k0);
+#pragma unroll
+    for (int l = ty; l < NC; l += 8) P[l + 1][tx] = l < n ? gdz * __ldg(ps + l * a.s.s2) : 0.0;
+  }
+  __syncthreads();
+  if (ty == 0) {  // diagnostics.py:L339-L342
+    double pk = a.pt;
+    P[0][tx] = pk;
+#pragma unroll
+    for (int l = 0; l < NC; ++l) {
+      if (l < n) {
+        pk = pk + P[l + 1][tx];
+        P[l + 1][tx] = pk;
+      }
+    }
+  }
+  __syncthreads();
+  {  // Exner function of the interfaces 8 ty + 1 .. 8 ty + 8 (and of the top one), p and exn out
+    E8 x;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x.v[c] = 8 * ty + c < n ? P[8 * ty + c + 1][tx] / a.cpref : 1.0;
+    if (8 * ty < n) {
+      const E8 ex = exner8_diag(x, a.kappa, a.cp);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (8 * ty + c < n) EX[8 * ty + c + 1][tx] = ex.v[c];
+    }
+    if (ty == 7) EX[0][tx] = a.cp * pow_pos(a.pt / a.cpref, a.kappa);
+  }
+  __syncthreads();
+  double inc[8];  // height increments of the interfaces 8 ty + c (diagnostics.py:L356-L360)
+  {
+    const double *pth = &a.theta(i, j, k0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int l1 = 8 * ty + c;
+      inc[c] = 0.0;
+      if (l1 < n) {
+        const double tha = __ldg(pth + l1 * a.theta.s2), thb = __ldg(pth + (l1 + 1) * a.theta.s2);
+        const double pa = P[l1][tx], pb = P[l1 + 1][tx];
+        inc[c] = a.rd * (tha * EX[l1][tx] + thb * EX[l1 + 1][tx]) * (pa - pb) / (cpg * (pa + pb));
+      }
+    }
+    if (live) {  // p and exn are final: store them (rows of 32 columns)
+      double *pp = &a.p(i, j, k0), *pe = &a.exn(i, j, k0);
+#pragma unroll
+      for (int l = ty; l < NC + 1; l += 8) {
+        if (l <= n) {
+          pp[l * a.p.s2] = P[l][tx];
+          pe[l * a.exn.s2] = EX[l][tx];
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (8 * ty + c < n) P[8 * ty + c][tx] = inc[c];  // the pressures are no longer needed
+  __syncthreads();
+  if (ty == 0) {  // upward sums, diagnostics.py:L345-L360
+    const double eb_s = EX[n][tx];
+    double hk = a.hs(i, j, k0 + n);
+    const double thb = __ldg(&a.theta(i, j, k0) + n * a.theta.s2);
+    const double mtg_s = thb * eb_s + a.g * hk;  // L347
+    double m = mtg_s + 0.5 * a.dz * eb_s;
+    P[n][tx] = hk;  // L354
+    for (int l1 = n - 1; l1 >= 0; --l1) {
+      if (l1 < n - 1) m = m + a.dz * EX[l1 + 1][tx];  // mtg[k] = mtg[k+1] + dz exn[k+1]
+      EX[l1 + 1][tx] = m;                               // parked one slot up (exn[l1+1] is spent)
+      hk = hk - P[l1][tx];
+      P[l1][tx] = hk;
+    }
+  }
+  __syncthreads();
+  if (live) {
+    double *pm = &a.mtg(i, j, k0), *ph = &a.h(i, j, k0);
+#pragma unroll
+    for (int l = ty; l < NC + 1; l += 8) {
+      if (l <= n) ph[l * a.h.s2] = P[l][tx];
+      if (l < n) pm[l * a.mtg.s2] = EX[l + 1][tx];
+    }
+  }
+}
+
 extern "C" int tb200_montgomery(const tb200_field *in_hs, const tb200_field *in_s,
                                 tb200_field *inout_mtg, double dz, double pt, double theta_s,
                                 const double constants[4], const int32_t origin[3],
@@ -399,6 +506,20 @@ extern "C" int tb200_diagnostic_variables(const tb200_field *in_theta, const tb2
     DiagArgs a{th, hs, s, p, exn, mtg, h, dz, pt, constants[1], constants[2], constants[3],
                constants[1] / constants[3], make_cdiv(constants[0]), origin[0], origin[1], origin[2],
                domain[0], domain[1], domain[2] - 1};
+    // fewer than four warps per scheduler with one thread per column: the cooperative kernel
+    // (TB200_DIAG_IMPL=column|coop forces one)
+    static int forced = -1;
+    if (forced < 0) {
+      const char *e = getenv("TB200_DIAG_IMPL");
+      forced = e == nullptr ? 0 : strcmp(e, "column") == 0 ? 1 : strcmp(e, "coop") == 0 ? 2 : 0;
+    }
+    const bool coop = forced ? forced == 2 : (long long)domain[0] * domain[1] < 148LL * 4 * 4 * 32;
+    if (coop) {
+      dim3 block(32, 8, 1);
+      dim3 grid((domain[0] + 31) / 32, domain[1], 1);
+      diag_coop_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(a);
+      return check_launch("diagnostic_variables(coop)");
+    }
     dim3 block(32, 4, 1);
     dim3 grid((domain[0] + 31) / 32, (domain[1] + 3) / 4, 1);
     if (a.n == 64)

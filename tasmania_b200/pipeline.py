@@ -18,6 +18,7 @@ step instead of their sum.  ``bench.py`` reports this path as ``e2e``.
 """
 from __future__ import annotations
 
+import os
 from datetime import datetime
 
 import torch
@@ -31,36 +32,38 @@ P, EXN, H = ("air_pressure_on_interface_levels", "exner_function_on_interface_le
 
 def gpu_numa_node(device_index=None):
     """NUMA node of the host memory closest to a GPU (sysfs ``numa_node`` of its PCI function), or
-    None when it cannot be told (no NVML, single-node host, container without sysfs)."""
+    None when it cannot be told (single-node host, virtualised PCI topology, no sysfs)."""
+    cands = []
+    try:
+        idx = torch.cuda.current_device() if device_index is None else device_index
+        pr = torch.cuda.get_device_properties(idx)
+        dom, bus, dev = (getattr(pr, "pci_domain_id", None), getattr(pr, "pci_bus_id", None),
+                         getattr(pr, "pci_device_id", None))
+        if bus is not None and dev is not None:
+            cands.append(f"{(dom or 0):04x}:{bus:02x}:{dev:02x}.0")
+    except Exception:  # noqa: BLE001  (best effort: placement is an optimisation)
+        pass
     try:
         import pynvml
 
         pynvml.nvmlInit()
         idx = torch.cuda.current_device() if device_index is None else device_index
-        # NVML enumerates all GPUs of the box: go through the UUID torch reports for this device
-        uuid = str(torch.cuda.get_device_properties(idx).uuid)
-        handle = None
-        for n in range(pynvml.nvmlDeviceGetCount()):
-            h = pynvml.nvmlDeviceGetHandleByIndex(n)
-            u = pynvml.nvmlDeviceGetUUID(h)
-            u = u.decode() if isinstance(u, bytes) else u
-            if uuid in u:
-                handle = h
-                break
-        if handle is None:
-            return None
-        bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            idx = int(vis.split(",")[idx])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
         bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
-        for cand in (bus, bus[4:] if len(bus) > 12 else bus):  # NVML pads the PCI domain to 8 digits
-            path = f"/sys/bus/pci/devices/{cand}/numa_node"
-            try:
-                with open(path) as f:
-                    node = int(f.read().strip())
-                return node if node >= 0 else None
-            except OSError:
-                continue
-    except Exception:  # noqa: BLE001  (best effort: placement is an optimisation)
-        return None
+        cands += [bus, bus[4:] if len(bus) > 12 else bus]  # NVML pads the PCI domain to 8 digits
+    except Exception:  # noqa: BLE001
+        pass
+    for cand in cands:
+        try:
+            with open(f"/sys/bus/pci/devices/{cand}/numa_node") as f:
+                node = int(f.read().strip())
+            if node >= 0:
+                return node
+        except (OSError, ValueError):
+            continue
     return None
 
 

@@ -73,3 +73,6 @@ def test_small_grid_kernels_are_bitwise_identical(nz):
     ref = _digest("fifth_order_upwind", nz)
     assert _digest("fifth_order_upwind", nz, TB200_LJ="64", TB200_B_IMPL="column") == ref
     assert _digest("fifth_order_upwind", nz, TB200_LJ="16", TB200_B_IMPL="coop") == ref
+    # the diagnostics refresh: cooperative kernel (default at this size) vs one thread per column
+    assert _digest("fifth_order_upwind", nz, TB200_DIAG_IMPL="column") == ref
+    assert _digest("fifth_order_upwind", nz, TB200_DIAG_IMPL="coop") == ref
