@@ -8,7 +8,8 @@ N=${1:-2}
 mkdir -p gpurun_out
 T=gpurun_out/r02_mgpu${N}
 port=29540
-for extra in "--transport p2p" "--transport p2p --overlap" "--transport p2p --phases 2" "--transport nccl" ${MGPU_MORE:+"--transport nccl --overlap"}; do
+for extra in "--transport p2p" "--transport p2p --overlap" "--transport p2p --phases 2" ${MGPU_SKIP_NCCL:-"--transport nccl"} ${MGPU_MORE:+"--transport nccl --overlap"}; do
+  [ "$extra" = "1" ] && continue
   port=$((port + 1))
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
       tests/mgpu_check.py $extra >> ${T}_check.log 2>&1
@@ -28,7 +29,7 @@ print('$1', 'ms/step', round(d['ms_per_step'],3), 'value', round(d['value'],1), 
 run_bench p2p "TB200_HALO=p2p" ""
 run_bench p2p_2phase "TB200_HALO=p2p TB200_HALO_PHASES=2" ""
 if [ -n "${MGPU_MORE:-}" ]; then run_bench p2p_overlap "TB200_HALO=p2p" "--overlap"; fi
-run_bench nccl "TB200_HALO=nccl" ""
+if [ -z "${MGPU_SKIP_NCCL:-}" ]; then run_bench nccl "TB200_HALO=nccl" ""; fi
 python bench.py --gpus 1 --steps 20 --warmup 3 --no-aux --no-cpu-baseline > ${T}_bench_1gpu.log 2>&1
 tail -n 1 ${T}_bench_1gpu.log | python -c "
 import json,sys

@@ -282,7 +282,7 @@ def _frame_relaxed_enforce_raw():
     return "Relaxed.enforce_raw"
 
 
-def _fused_stage_dry():
+def _fused_stage(moist=False):
     """Put the fused RK stage (``tb200_isentropic_stage_dry``: three kernels instead of the 13
     stencil launches of a stage) behind the reference's own
     ``IsentropicDynamicalCore.stage_array_call_dry`` (src/tasmania/isentropic/dynamics/
@@ -293,6 +293,10 @@ def _fused_stage_dry():
     scope: slow or fast tendencies, a boundary other than the 2-D ``Relaxed``, a prognostic scheme
     other than RK3WSSI / ForwardEulerSI, reference fields in non-canonical units, foreign storages.
 
+    ``moist=True`` does the same for ``stage_array_call_moist`` (dycore.py:L723-L843) with
+    ``tb200_isentropic_stage_moist``: the dry kernels plus one kernel for the three water
+    constituents (density, K1 share, mass fraction, lateral relaxation), no sq* storages.
+
     Intermediate stages neither write nor read u, v (``skip_uv_out`` / ``derive_uv_in``: their
     successor re-diagnoses them with the formula ``get_velocity_components`` ends every stage with,
     so the step's result is bit-identical) unless the dycore has a fast tendency or diagnostic
@@ -300,13 +304,18 @@ def _fused_stage_dry():
     from tasmania.isentropic.dynamics.dycore import IsentropicDynamicalCore
     from tasmania_b200 import lib
 
-    original = IsentropicDynamicalCore.stage_array_call_dry
+    method = "stage_array_call_moist" if moist else "stage_array_call_dry"
+    original = getattr(IsentropicDynamicalCore, method)
     if getattr(original, "__tasmania_b200__", False):
         return None
 
     S, SU, SV = "air_isentropic_density", "x_momentum_isentropic", "y_momentum_isentropic"
     U, V, MTG = "x_velocity_at_u_locations", "y_velocity_at_v_locations", "montgomery_potential"
+    QN = ("mass_fraction_of_water_vapor_in_air", "mass_fraction_of_cloud_liquid_water_in_air",
+          "mass_fraction_of_precipitation_water_in_air")
     UNITS = {S: "kg m^-2 K^-1", SU: "kg m^-1 K^-1 s^-1", SV: "kg m^-1 K^-1 s^-1", U: "m s^-1", V: "m s^-1"}
+    if moist:
+        UNITS.update({q: "g g^-1" for q in QN})
     SUBSTEPS = {  # stage -> (increment of the time label, stage time step), the reference's own
         # timedelta arithmetic (rk3ws_si.py:L115-L123, forward_euler_si.py:L106-L111)
         "rk3ws_si": (lambda t: (t / 3.0, t / 3.0), lambda t: (t / 6.0, 0.5 * t), lambda t: (0.5 * t, t)),
@@ -318,7 +327,7 @@ def _fused_stage_dry():
         cached = getattr(self, "_b200_fused_plan", None)
         if cached is not None:
             return cached or None
-        ok = getattr(self, "backend", None) == BACKEND and not getattr(self, "_moist", True)
+        ok = getattr(self, "backend", None) == BACKEND and bool(getattr(self, "_moist", not moist)) == moist
         hb, pr = self.horizontal_boundary, self._prognostic
         ok = ok and type(hb).__name__ == "Relaxed" and getattr(type(pr), "name", None) in SUBSTEPS
         scheme = getattr(getattr(pr, "_hflux", None), "name", None)
@@ -347,11 +356,12 @@ def _fused_stage_dry():
         }
         return self._b200_fused_plan
 
-    def stage_array_call_dry(self, stage, state, tendencies, timestep, out_state):
+    def stage_array_call(self, stage, state, tendencies, timestep, out_state):
         if any(k != "time" for k in (tendencies or {})):
             return original(self, stage, state, tendencies, timestep, out_state)
         p = plan(self, tendencies)
-        if p is None or not all(isinstance(state[n], storage.B200Array) for n in (S, SU, SV, U, V, MTG)):
+        needed = (S, SU, SV, U, V, MTG) + (QN if moist else ())
+        if p is None or not all(isinstance(state[n], storage.B200Array) for n in needed):
             return original(self, stage, state, tendencies, timestep, out_state)
         hb, pr = self.horizontal_boundary, self._prognostic
         diag = pr._diagnostics
@@ -361,6 +371,8 @@ def _fused_stage_dry():
         if stage == 0:  # the reference's bookkeeping, dycore.py:L662-L668 and rk3ws_si.py:L126-L130
             self._s_now, self._su_now, self._sv_now = state[S], state[SU], state[SV]
             pr._s_now, pr._mtg_now, pr._su_now, pr._sv_now = state[S], state[MTG], state[SU], state[SV]
+            if moist:  # the step-start mass fractions: the kernel forms s q itself (dycore.py:L762-L779)
+                self._b200_q_now = [state[q] for q in QN]
         # the topography of the moment, as get_montgomery_potential uploads it (diagnostics.py:L216-L219)
         diag._topo[:nx, :ny, nz] = diag.as_storage(data=g.topography.profile.to_units("m").values)
         dtr, dt = p["substeps"][stage](timestep)
@@ -380,14 +392,24 @@ def _fused_stage_dry():
         scratch_s = out_state[S] if cfg.skip_uv_out else p["scratch"][2]
         f = lib.as_field
         rmat = self._damper._rmat if self._damp else None
-        rc = lib.load().tb200_isentropic_stage_dry(
-            cfg, f(pr._s_now), f(pr._su_now), f(pr._sv_now), f(pr._mtg_now),
-            f(state[S]), f(state[SU]), f(state[SV]), f(state[U]), f(state[V]),
-            f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
-            f(ref[S].data), f(ref[SU].data), f(ref[SV].data), f(ref[U].data), f(ref[V].data),
-            f(hb._gamma), f(rmat), f(diag._topo[:, :, nz:nz + 1]),
-            f(p["scratch"][0]), f(p["scratch"][1]), f(scratch_s), lib.current_stream())
-        lib.check(rc, "tb200_isentropic_stage_dry")
+        args = (cfg, f(pr._s_now), f(pr._su_now), f(pr._sv_now), f(pr._mtg_now),
+                f(state[S]), f(state[SU]), f(state[SV]), f(state[U]), f(state[V]),
+                f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
+                f(ref[S].data), f(ref[SU].data), f(ref[SV].data), f(ref[U].data), f(ref[V].data),
+                f(hb._gamma), f(rmat), f(diag._topo[:, :, nz:nz + 1]),
+                f(p["scratch"][0]), f(p["scratch"][1]), f(scratch_s))
+        if moist:
+            import ctypes as C
+
+            keep = [[f(x) for x in xs] for xs in (self._b200_q_now, [state[q] for q in QN],
+                                                   [out_state[q] for q in QN], [ref[q].data for q in QN])]
+            arrays = [(lib.FieldP * 3)(*[C.pointer(k) for k in ks]) for ks in keep]
+            rc = lib.load().tb200_isentropic_stage_moist(*args, *arrays, lib.current_stream())
+            lib.check(rc, "tb200_isentropic_stage_moist")
+            del keep
+        else:
+            rc = lib.load().tb200_isentropic_stage_dry(*args, lib.current_stream())
+            lib.check(rc, "tb200_isentropic_stage_dry")
         if p["lazy"] and stage == self.stages - 1:
             rc = lib.load().tb200_velocity_components(
                 f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
@@ -395,10 +417,20 @@ def _fused_stage_dry():
             lib.check(rc, "tb200_velocity_components")
         out_state["time"] = state["time"] + dtr
 
-    stage_array_call_dry.__tasmania_b200__ = True
-    stage_array_call_dry.__wrapped_original__ = original
-    IsentropicDynamicalCore.stage_array_call_dry = stage_array_call_dry
-    return "IsentropicDynamicalCore.stage_array_call_dry"
+    stage_array_call.__name__ = method
+    stage_array_call.__tasmania_b200__ = True
+    stage_array_call.__wrapped_original__ = original
+    setattr(IsentropicDynamicalCore, method, stage_array_call)
+    return "IsentropicDynamicalCore." + method
+
+
+def _fused_stage_dry():
+    return _fused_stage(False)
+
+
+def _fused_stage_moist():
+    return _fused_stage(True)
+
 
 
 def install(strict: bool = False, batch_fma: bool = True, frame_relax: bool = True,
@@ -491,13 +523,13 @@ def install(strict: bool = False, batch_fma: bool = True, frame_relax: bool = Tr
     # 6. the fused RK stage behind the reference's own dynamical core
     if fused_stage:
         try:
-            patched = _fused_stage_dry()
-            if patched:
-                report.setdefault("fused", []).append(patched)
+            for patched in (_fused_stage_dry(), _fused_stage_moist()):
+                if patched:
+                    report.setdefault("fused", []).append(patched)
         except Exception as exc:  # pragma: no cover - depends on optional deps of the reference
             if strict:
                 raise
-            report["skipped"].append(("IsentropicDynamicalCore.stage_array_call_dry", repr(exc)))
+            report["skipped"].append(("IsentropicDynamicalCore.stage_array_call_dry / _moist", repr(exc)))
 
     _installed = True
     return report

@@ -143,7 +143,8 @@ def reference_trace(stub, moist, fx, fused=False):
     stage_call = (dyc.IsentropicDynamicalCore.stage_array_call_moist if moist
                   else dyc.IsentropicDynamicalCore.stage_array_call_dry)
     if fused:  # looked up after the patch
-        stage_call = dyc.IsentropicDynamicalCore.stage_array_call_dry
+        stage_call = (dyc.IsentropicDynamicalCore.stage_array_call_moist if moist
+                      else dyc.IsentropicDynamicalCore.stage_array_call_dry)
     grid.update_topography(DT)
     stub.trace = []
     st_in = cur
@@ -275,4 +276,29 @@ finally:
 for name in OUTNAMES:
     assert np.array_equal(fused_outs[2][name], plain_outs[2][name]), name
 assert fused_times == plain_times
-print("REF-DYCORE-OK", *done, "FUSED-HOOK-OK")
+# ---- the same for the moist stage: stage_array_call_moist patched -> one
+# tb200_isentropic_stage_moist per stage, no density / mass_fraction / relax launches, and the step
+# ends with exactly the fields of the per-stencil reference run (water constituents included)
+fixture = set_case(True)
+with stubbed_library(OracleStub) as the_stub:
+    assert plugin._fused_stage_moist() == "IsentropicDynamicalCore.stage_array_call_moist"
+    assert plugin._fused_stage_moist() is None  # idempotent
+    fused_trace, fused_outs, fused_times = reference_trace(the_stub, True, fixture, fused=True)
+names = [n for n, _ in fused_trace]
+assert names.count("tb200_isentropic_stage_moist") == 3 and names[-1] == "tb200_velocity_components", \
+    collections.Counter(names)
+assert not any(n in names for n in ("tb200_step_forward_euler", "tb200_density", "tb200_mass_fraction",
+                                    "tb200_damping", "tb200_relax", "tb200_isentropic_stage_dry"))
+for name in (S, SU, SV) + QNAMES:
+    assert np.array_equal(fused_outs[0][name], fixture["stage0_" + name]), name
+patched = dyc_mod.IsentropicDynamicalCore.stage_array_call_moist
+dyc_mod.IsentropicDynamicalCore.stage_array_call_moist = patched.__wrapped_original__
+try:
+    with stubbed_library(OracleStub) as the_stub:
+        _, plain_outs, plain_times = reference_trace(the_stub, True, fixture, fused=True)
+finally:
+    dyc_mod.IsentropicDynamicalCore.stage_array_call_moist = patched
+for name in OUTNAMES + QNAMES:
+    assert np.array_equal(fused_outs[2][name], plain_outs[2][name]), name
+assert fused_times == plain_times
+print("REF-DYCORE-OK", *done, "FUSED-HOOK-OK", "FUSED-MOIST-HOOK-OK")

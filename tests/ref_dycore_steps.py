@@ -148,7 +148,7 @@ def main():
     from tasmania_b200 import plugin
 
     report = plugin.install(fused_stage=not args.per_stencil)
-    assert args.per_stencil or report.get("fused") == ["IsentropicDynamicalCore.stage_array_call_dry"], report
+    assert args.per_stencil or "IsentropicDynamicalCore.stage_array_call_dry" in report.get("fused", []), report
     want = run("numpy", args.steps, args.nx, args.ny, args.nz)
     if args.stub:
         from tests.abi_oracle import OracleStub
