@@ -43,7 +43,11 @@ DT = timedelta(seconds=5)
 OUTNAMES = (S, SU, U, SV, V)
 
 
-def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20):
+QNAMES = ("mass_fraction_of_water_vapor_in_air", "mass_fraction_of_cloud_liquid_water_in_air",
+          "mass_fraction_of_precipitation_water_in_air")
+
+
+def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20, moist=False):
     """``nsteps`` RK3WS + fifth-order-upwind steps of the mountain-flow case on ``backend``;
     returns the final state as numpy arrays.  ``clock`` (a dict with a "budget" in seconds): the
     step loop is timed (set-up excluded) and stops once the budget is spent -- how ``bench.py
@@ -68,7 +72,13 @@ def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20):
     st = refload.load("tasmania.isentropic.state")
     state = st.get_isentropic_state_from_brunt_vaisala_frequency(
         grid, datetime(2000, 1, 1), da(22.5, "m s^-1"), da(0.0, "m s^-1"), da(0.015, "s^-1"),
-        moist=False, backend=backend, storage_shape=shape)
+        moist=moist, relative_humidity=0.95, backend=backend, storage_shape=shape)
+    if moist:  # seed cloud water and rain so that all three constituents are advected (same bits on every backend)
+        i, j, k = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+        blob = np.exp(-((i - 0.4 * nx) ** 2 + (j - 0.5 * ny) ** 2) / (0.02 * nx * ny) - ((k - 0.7 * nz) / (0.2 * nz)) ** 2)
+        blob[nx:, :, :] = blob[:, ny:, :] = blob[:, :, nz:] = 0.0
+        for n, amp in ((QNAMES[1], 8e-4), (QNAMES[2], 3e-4)):
+            state[n] = DataArray(ta.as_storage(backend, data=amp * blob), attrs={"units": "g g^-1"})
     hb = domain.horizontal_boundary
     hb.reference_state = state
     dyc = refload.load("tasmania.isentropic.dynamics.dycore")
@@ -84,7 +94,7 @@ def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20):
     bo, so = opts.BackendOptions, opts.StorageOptions
     pt = float(to_numpy(state[P].data)[0, 0, 0])
     prognostic = prog.IsentropicPrognostic.factory(
-        "rk3ws_si", "fifth_order_upwind", domain, False, backend=backend, backend_options=bo(),
+        "rk3ws_si", "fifth_order_upwind", domain, moist, backend=backend, backend_options=bo(),
         storage_shape=shape, storage_options=so(), pt=da(pt, "Pa"), eps=0.5)
     damper = vd.VerticalDamping.factory("rayleigh", grid, damp_depth, 5e-4, backend=backend, backend_options=bo(),
                                         storage_shape=shape, storage_options=so())
@@ -96,18 +106,25 @@ def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20):
     def zeros():
         return ta.zeros(backend, shape=shape)
 
-    me = types.SimpleNamespace(  # the attributes stage_array_call_dry reads from the dycore object
-        horizontal_boundary=hb, backend=backend, grid=grid, storage_options=so(), _moist=False,
+    outnames = OUTNAMES + (QNAMES if moist else ())
+    water = {}
+    if moist:
+        water["_water_constituent"] = dd.WaterConstituent(
+            grid, clipping=True, backend=backend, backend_options=bo(), storage_options=so())
+        water.update({f"_{q}_{t}": zeros() for q in ("sqv", "sqc", "sqr") for t in ("now", "int", "new")})
+    me = types.SimpleNamespace(  # the attributes stage_array_call_dry / _moist read from the dycore object
+        horizontal_boundary=hb, backend=backend, grid=grid, storage_options=so(), _moist=moist, **water,
         fast_tendency_component=None, fast_diagnostic_component=None,
-        output_properties={k: {"units": state[k].attrs["units"]} for k in OUTNAMES},
+        output_properties={k: {"units": state[k].attrs["units"]} for k in outnames},
         _damp=True, _damp_at_every_stage=True, stages=prognostic.stages, _prognostic=prognostic,
         _damper=damper, _velocity_components=velocity, _s_ref=zeros(), _su_ref=zeros(),
         _sv_ref=zeros(), _s_now=None, _su_now=None, _sv_now=None)
-    cur = {k: state[k].data for k in (S, MTG, SU, U, SV, V, P, EXN, H)}
+    cur = {k: state[k].data for k in (S, MTG, SU, U, SV, V, P, EXN, H) + (QNAMES if moist else ())}
     cur["time"] = state["time"]
-    stage_outs = [{k: zeros() for k in OUTNAMES} for _ in range(prognostic.stages - 1)]
-    spare = {k: zeros() for k in OUTNAMES}
-    stage_call = dyc.IsentropicDynamicalCore.stage_array_call_dry
+    stage_outs = [{k: zeros() for k in outnames} for _ in range(prognostic.stages - 1)]
+    spare = {k: zeros() for k in outnames}
+    stage_call = (dyc.IsentropicDynamicalCore.stage_array_call_moist if moist
+                  else dyc.IsentropicDynamicalCore.stage_array_call_dry)
     import time as _time
 
     t_start = _time.perf_counter()
@@ -119,11 +136,11 @@ def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20):
             stage_call(me, stage, st_in, {}, DT, outs[stage])
             st_in = dict(outs[stage])
             st_in.setdefault(MTG, cur[MTG])
-        new = {k: spare[k] for k in OUTNAMES}
+        new = {k: spare[k] for k in outnames}
         new["time"] = cur["time"] + DT
         for k in (P, EXN, H, MTG):
             new[k] = cur[k]
-        spare = {k: cur[k] for k in OUTNAMES}
+        spare = {k: cur[k] for k in outnames}
         # the role dv plays in driver_namelist_sus.py:L188-L199
         diagnostics.get_diagnostic_variables(new[S], pt, new[P], new[EXN], new[MTG], new[H])
         cur = new
@@ -139,6 +156,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--stub", action="store_true")
     ap.add_argument("--per-stencil", action="store_true")
+    ap.add_argument("--moist", action="store_true", help="the moist dycore stage (stage_array_call_moist)")
     ap.add_argument("--nx", type=int, default=41)
     ap.add_argument("--ny", type=int, default=37)
     ap.add_argument("--nz", type=int, default=12)
@@ -149,7 +167,9 @@ def main():
 
     report = plugin.install(fused_stage=not args.per_stencil)
     assert args.per_stencil or "IsentropicDynamicalCore.stage_array_call_dry" in report.get("fused", []), report
-    want = run("numpy", args.steps, args.nx, args.ny, args.nz)
+    if args.moist and not args.per_stencil:
+        assert "IsentropicDynamicalCore.stage_array_call_moist" in report.get("fused", []), report
+    want = run("numpy", args.steps, args.nx, args.ny, args.nz, moist=args.moist)
     if args.stub:
         from tests.abi_oracle import OracleStub
         from tests.abi_stub import stubbed_library
@@ -159,9 +179,9 @@ def main():
         ctx = contextlib.nullcontext()
     with ctx as stub:
         n0 = None if args.stub else tb.lib.launch_count()
-        got = run("b200", args.steps, args.nx, args.ny, args.nz)
+        got = run("b200", args.steps, args.nx, args.ny, args.nz, moist=args.moist)
         if args.stub:
-            fused_calls = stub.count("tb200_isentropic_stage_dry")
+            fused_calls = stub.count("tb200_isentropic_stage_moist" if args.moist else "tb200_isentropic_stage_dry")
         else:
             fused_calls = None
             assert tb.lib.launch_count() - n0 >= (10 if not args.per_stencil else 30) * args.steps
@@ -169,7 +189,7 @@ def main():
         assert fused_calls == 3 * args.steps, fused_calls
     worst = {}
     nx, ny, nz = args.nx, args.ny, args.nz
-    for k in (S, SU, SV, U, V, MTG, P, EXN, H):
+    for k in (S, SU, SV, U, V, MTG, P, EXN, H) + (QNAMES if args.moist else ()):
         a, b = got[k][: nx + 1, : ny + 1, : nz + 1], want[k][: nx + 1, : ny + 1, : nz + 1]
         scale = float(np.max(np.abs(b)))
         worst[k] = float(np.max(np.abs(a - b))) / scale if scale > 0 else float(np.max(np.abs(a - b)))
@@ -177,7 +197,10 @@ def main():
     tol = 0.0 if args.stub else 1e-12
     assert max(worst.values()) <= tol, worst
     assert float(np.max(np.abs(want[SV]))) > 1e-6  # the flow developed
-    print("REF-DYCORE-STEPS-OK", "per-stencil" if args.per_stencil else "fused", args.steps)
+    if args.moist:
+        assert all(float(np.max(np.abs(want[q]))) > 0.0 for q in QNAMES)
+    print("REF-DYCORE-STEPS-OK", ("per-stencil" if args.per_stencil else "fused") + ("-moist" if args.moist else ""),
+          args.steps)
 
 
 if __name__ == "__main__":

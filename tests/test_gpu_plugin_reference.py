@@ -26,14 +26,16 @@ def _reference_root():
     return None
 
 
-@pytest.mark.parametrize("mode", ["fused", "per-stencil"])
+@pytest.mark.parametrize("mode", ["fused", "per-stencil", "fused-moist", "per-stencil-moist"])
 def test_reference_dycore_on_b200_equals_its_numpy_backend(mode):
     ref = _reference_root()
     if ref is None:
         pytest.skip("reference sources not staged (bash baseline/stage_reference.sh)")
     cmd = [sys.executable, os.path.join(ROOT, "tests", "ref_dycore_steps.py"), "--steps", "10"]
-    if mode == "per-stencil":
+    if mode.startswith("per-stencil"):
         cmd.append("--per-stencil")
+    if mode.endswith("moist"):
+        cmd.append("--moist")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
                          env=dict(os.environ, TASMANIA_REFERENCE=ref))
     print(res.stdout[-2000:])
