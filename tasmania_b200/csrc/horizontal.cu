@@ -259,6 +259,137 @@ __global__ void __launch_bounds__(32 * M2_WARPS, 4)
   }
 }
 
+// ---- smoothing, two columns per lane: the marching structure of march2_kernel for the smoothers
+// (OP 11 / 12 / 13 = first / second / third order, halo 1 / 2 / 3).  The tiled kernel the smoothers
+// used to run pays two block barriers per level and reached 0.27 of the HBM peak on fields larger
+// than L2 (profiles/README.md, round 2); the diffusion dwarf's marching kernel reaches 0.905.  Same
+// point formulas in the same order as cross_kernel, hence the same bits.  The rim copy of
+// HorizontalSmoothing.__call__ (rim_copy) is a separate frame launch.
+// xm[d-1] / xp[d-1] = phi at i -/+ d, ym / yp likewise along j
+template <int OP>
+__device__ __forceinline__ double smooth_point(double g, double c, const double *xm, const double *xp,
+                                               const double *ym, const double *yp) {
+  if (OP == 11) {  // first_order.py:L124-L126
+    return (1.0 - g) * c + 0.25 * g * (xm[0] + xp[0] + ym[0] + yp[0]);
+  } else if (OP == 12) {  // second_order.py:L126-L139
+    return (1.0 - 0.75 * g) * c +
+           0.0625 * g * (-xm[1] + 4.0 * xm[0] - xp[1] + 4.0 * xp[0] - ym[1] + 4.0 * ym[0] - yp[1] + 4.0 * yp[0]);
+  } else {  // third_order.py:L133-L150
+    return (1.0 - 0.625 * g) * c +
+           0.015625 * g *
+               (xm[2] - 6.0 * xm[1] + 15.0 * xm[0] + xp[2] - 6.0 * xp[1] + 15.0 * xp[0] + ym[2] -
+                6.0 * ym[1] + 15.0 * ym[0] + yp[2] - 6.0 * yp[1] + 15.0 * yp[0]);
+  }
+}
+
+template <int OP, int LJ>
+__global__ void __launch_bounds__(32 * M2_WARPS, 4)
+    smooth2_kernel(View phi, View gam, View out, int i0, int j0, int k0, int di, int dj, int dk) {
+  constexpr int H = Halo<OP>::value;
+  static_assert(OP == 11 || OP == 12 || OP == 13, "smoothing only");
+  const int ib = i0 & ~1;  // pairs start at even columns
+  const int c0 = ib + 2 * (blockIdx.x * (32 * M2_WARPS) + threadIdx.x);
+  if (c0 >= i0 + di) return;  // no shuffles and no barriers below
+  const bool m0 = c0 >= i0, m1 = c0 + 1 < i0 + di;
+  const int js = j0 + blockIdx.y * LJ, je = min(js + LJ, j0 + dj);
+  const long long s1 = phi.s1;
+  const int pmax = (int)((s1 - 2) & ~1LL);  // last aligned pair inside a row
+  // neighbour pairs (clamped into the row: only masked points see clamped values)
+  const int cl = max(c0 - 2, 0), cr = min(c0 + 2, pmax);
+  const int cll = max(c0 - 4, 0), crr = min(c0 + 4, pmax);
+  const int jlast = phi.n1 - 1;
+  for (int k = k0 + blockIdx.z; k < k0 + dk; k += gridDim.z) {
+    const double *pc = phi.p + (c0 + k * phi.s2);  // row 0 of the own pair
+    const double *pg = gam.p + (c0 * gam.s0 + js * gam.s1 + k * gam.s2);
+    double *po = out.p + (c0 + js * out.s1 + k * out.s2);
+    double2 w[2 * H + 1];  // rows j-H .. j+H of the own pair
+#pragma unroll
+    for (int m = 0; m < 2 * H; ++m) w[m + 1] = ldg2(pc + max(js + m - H, 0) * s1);
+    double2 nxt = ldg2(pc + min(js + H, jlast) * s1);
+    for (int j = js; j < je; ++j) {
+#pragma unroll
+      for (int m = 0; m < 2 * H; ++m) w[m] = w[m + 1];
+      w[2 * H] = nxt;
+      nxt = ldg2(pc + min(j + 1 + H, jlast) * s1);
+      if (j + H + M2_PF < je + H)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + (j + H + M2_PF) * s1));
+      const double *pr = phi.p + (j * s1 + k * phi.s2);
+      const double2 l = ldg2(pr + cl), r = ldg2(pr + cr);
+      double2 ll = make_double2(0.0, 0.0), rr = ll;
+      if (H == 3) {
+        ll = ldg2(pr + cll);
+        rr = ldg2(pr + crr);
+      }
+      const double g0 = __ldg(pg), g1 = __ldg(pg + gam.s0);
+      // column c0: x offsets -1, -2, -3 = l.y, l.x, ll.y; +1, +2, +3 = own.y, r.x, r.y
+      // column c1: x offsets -1, -2, -3 = own.x, l.y, l.x; +1, +2, +3 = r.x, r.y, rr.x
+      const double xm0[3] = {l.y, l.x, ll.y}, xp0[3] = {w[H].y, r.x, r.y};
+      const double xm1[3] = {w[H].x, l.y, l.x}, xp1[3] = {r.x, r.y, rr.x};
+      double ym0[3], yp0[3], ym1[3], yp1[3];
+#pragma unroll
+      for (int d = 1; d <= 3; ++d) {
+        if (d <= H) {
+          ym0[d - 1] = w[H - d].x; yp0[d - 1] = w[H + d].x;
+          ym1[d - 1] = w[H - d].y; yp1[d - 1] = w[H + d].y;
+        } else {
+          ym0[d - 1] = yp0[d - 1] = ym1[d - 1] = yp1[d - 1] = 0.0;
+        }
+      }
+      const double r0 = smooth_point<OP>(g0, w[H].x, xm0, xp0, ym0, yp0);
+      const double r1 = smooth_point<OP>(g1, w[H].y, xm1, xp1, ym1, yp1);
+      if (m0 && m1) {
+        *reinterpret_cast<double2 *>(po) = make_double2(r0, r1);
+      } else if (m0) {
+        po[0] = r0;
+      } else if (m1) {
+        po[1] = r1;
+      }
+      pg += gam.s1;
+      po += out.s1;
+    }
+  }
+}
+
+template <int OP>
+int launch_smooth2(const char *what, View phi, View gam, View out, const int32_t o[3], const int32_t d[3],
+                   cudaStream_t st) {
+  const int gz = d[2] > 65535 ? 65535 : d[2];
+  const int cols = 2 * 32 * M2_WARPS;
+  const int span = o[0] + d[0] - (o[0] & ~1);
+  const int gx = (span + cols - 1) / cols;
+  const long long blocks64 = (long long)gx * ((d[1] + 63) / 64) * gz;
+  if (blocks64 >= 148 * 4) {
+    dim3 grid(gx, (d[1] + 63) / 64, gz);
+    smooth2_kernel<OP, 64><<<grid, 32 * M2_WARPS, 0, st>>>(phi, gam, out, o[0], o[1], o[2], d[0], d[1], d[2]);
+  } else {
+    dim3 grid(gx, (d[1] + 7) / 8, gz);
+    smooth2_kernel<OP, 8><<<grid, 32 * M2_WARPS, 0, st>>>(phi, gam, out, o[0], o[1], o[2], d[0], d[1], d[2]);
+  }
+  return check_launch(what);
+}
+
+// the frame of the smoother's box around [o, o + d): out = phi (the four `copy` launches of
+// HorizontalSmoothing.__call__); threads of interior points leave at once
+int launch_rim_copy(View phi, View out, const int32_t o[3], const int32_t d[3], cudaStream_t st) {
+  const int ri = 2 * o[0] + d[0], rj = 2 * o[1] + d[1];
+  const int i0 = o[0], j0 = o[1], k0 = o[2], di = d[0], dj = d[1];
+  const int32_t ext[3] = {ri, rj, d[2]};
+  return launch_box("smoothing_rim", ext, st, [=] __device__(int i, int j, int k) {
+    if (i >= i0 && i < i0 + di && j >= j0 && j < j0 + dj) return;
+    out(i, j, k + k0) = phi.ld(i, j, k + k0);
+  });
+}
+
+// TB200_SMOOTH_IMPL: "march2" (default) or "tile"
+int smooth_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("TB200_SMOOTH_IMPL");
+    impl = (e != nullptr && strcmp(e, "tile") == 0) ? 0 : 2;
+  }
+  return impl;
+}
+
 bool march2_ok(const View &phi, const View &out) {
   const View *vs[] = {&phi, &out};
   for (const View *v : vs)
@@ -333,6 +464,15 @@ int launch_cross(const char *what, View phi, View gam, View out, double dx, doub
     if (!rim && diff_impl() == 2 && march2_ok(phi, out))
       return launch_march2<OP>(what, phi, gam, out, cdx, cdy, overwrite, o, d, st);
     if (!rim && diff_impl() >= 1) return launch_march<OP>(what, phi, gam, out, cdx, cdy, overwrite, o, d, st);
+  }
+  if constexpr (OP == 11 || OP == 12 || OP == 13) {
+    // the marching kernel reads gamma with unit i-stride or as a broadcast; phi / out as pairs
+    if (smooth_impl() == 2 && march2_ok(phi, out) && d[0] > 0 && d[1] > 0 && d[2] > 0 &&
+        o[1] - Halo<OP>::value >= 0) {
+      int rc = launch_smooth2<OP>(what, phi, gam, out, o, d, st);
+      if (rc == TB200_OK && rim) rc = launch_rim_copy(phi, out, o, d, st);
+      return rc;
+    }
   }
   cross_kernel<OP><<<grid, block, 0, st>>>(phi, gam, out, cdx, cdy, overwrite, rim, o[0], o[1],
                                            o[2], d[0], d[1], d[2], ri, rj);

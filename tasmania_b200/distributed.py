@@ -381,18 +381,29 @@ class P2PHaloExchange(HaloExchange):
         mine = self.describe()
         everyone = [None] * dist.get_world_size(group)
         dist.all_gather_object(everyone, mine, group=group)
-        peers = {}
+        peers, failure = {}, None
         for phase in self.plan:
             for s in phase:
-                if s.neighbour in peers:
+                if s.neighbour in peers or failure is not None:
                     continue
                 d = everyone[s.neighbour]
                 ptr = C.c_void_p()
-                lib.check(lib.load().tb200_p2p_import(d["handle"], C.byref(ptr)), "tb200_p2p_import")
+                try:
+                    lib.check(lib.load().tb200_p2p_import(d["handle"], C.byref(ptr)), "tb200_p2p_import")
+                except lib.B200Error as exc:  # no peer access between the two devices
+                    failure = exc
+                    continue
                 self._imported.append(int(ptr.value))
                 peers[s.neighbour] = (int(ptr.value), d["layout"])
+        # every rank learns whether every rank could map its neighbours (a collective, so that no
+        # rank is left waiting at the barrier below), then nobody pushes before every mapping exists
+        verdicts = [None] * dist.get_world_size(group)
+        dist.all_gather_object(verdicts, None if failure is None else str(failure), group=group)
+        bad = [v for v in verdicts if v is not None]
+        if bad:
+            raise lib.B200Error(f"peer-store halo transport unavailable: {bad[0]}")
         self.connect(peers)
-        dist.barrier(group)  # nobody pushes before every mapping exists
+        dist.barrier(group)
 
     def _call(self, fn, what, phase, fields):
         sides = self.plan[phase]
@@ -645,7 +656,16 @@ class DecomposedDryRun:
         self.sub = SubdomainDryCore(self.decomp, rank, nz, domain_x=self.domain_x, domain_y=self.domain_y,
                                     device=device, transport=self.transport, **kwargs)
         if self.transport == "p2p":
-            self.sub.halo.connect_ipc()
+            try:
+                self.sub.halo.connect_ipc()
+            except lib.B200Error as exc:
+                # raised on EVERY rank together (connect_ipc): fall back to the message transport
+                import warnings
+
+                warnings.warn(f"{exc}; falling back to TB200_HALO=nccl")
+                self.sub.halo.close()
+                self.transport = self.sub.transport = "nccl"
+                self.sub.halo = HaloExchange(self.decomp, rank, nz, 5, self.sub.state[self.sub.S].t.device)
         self.nx, self.ny, self.nz = nx, ny, nz
         self.names, self.out_names = self.sub.names, self.sub.out_names
         self.dyc = self.sub.dyc

@@ -87,6 +87,7 @@ class NetCDFMonitor:
         self._write_on_store = bool(write_on_store)
         self._aliases = dict(aliases or {})
         self._pending = []   # (time, {name: (pinned host tensor, like, grid shape, dims)}, event)
+        self._host_pool = {}  # (name, shape, pinned) -> host buffers free for reuse
         self._staging = [None, None]   # device staging sets: {name: flat tensor}
         self._staging_free = [None, None]  # event: the D2H copy out of the set has finished
         self._nstored = 0
@@ -115,8 +116,12 @@ class NetCDFMonitor:
         host, meta = {}, {}
         for n in names:
             flat = _flat(state[n])
-            host[n] = torch.empty(flat.shape, dtype=flat.dtype, device="cpu",
-                                  pin_memory=bool(on_device))
+            assert flat.is_contiguous(), "host copies mirror the padded allocation: it must be contiguous"
+            # pinned buffers are recycled once write() has consumed them: allocating pinned memory
+            # synchronises with the device, which would stall the step loop on every store()
+            pool = self._host_pool.setdefault((n, tuple(flat.shape), bool(on_device)), [])
+            host[n] = pool.pop() if pool else torch.empty(flat.shape, dtype=flat.dtype, device="cpu",
+                                                          pin_memory=bool(on_device))
             t = state[n].t
             view = (tuple(t.shape), tuple(t.stride()), t.storage_offset()) if t._base is not None else None
             meta[n] = (view, ) + grid_shape(self.grid, n, state[n].shape)
@@ -200,6 +205,10 @@ class NetCDFMonitor:
         finally:
             nc.close()
         self._created = True
+        for _, host, _, event in self._pending:  # written: the host buffers go back to the pool
+            on_device = event is not None
+            for n, flat in host.items():
+                self._host_pool.setdefault((n, tuple(flat.shape), on_device), []).append(flat)
         self._pending = []
 
 
