@@ -369,15 +369,39 @@ int launch_smooth2(const char *what, View phi, View gam, View out, const int32_t
 }
 
 // the frame of the smoother's box around [o, o + d): out = phi (the four `copy` launches of
-// HorizontalSmoothing.__call__); threads of interior points leave at once
+// HorizontalSmoothing.__call__).  One thread per FRAME point: full rows below and above the box,
+// then the left and right margins of the rows in between.
+__global__ void __launch_bounds__(256) rim_copy_kernel(View phi, View out, int i0, int j0, int k0, int di,
+                                                       int dj, int dk, int ri, int rj) {
+  const long long low = (long long)j0 * ri, high = (long long)(rj - j0 - dj) * ri;
+  const int margin = ri - di;  // points per middle row outside the box
+  const long long total = low + high + (long long)dj * margin;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int i, j;
+  if (t < low) {
+    j = (int)(t / ri); i = (int)(t - (long long)j * ri);
+  } else if (t < low + high) {
+    const long long u = t - low;
+    j = (int)(u / ri); i = (int)(u - (long long)j * ri);
+    j += j0 + dj;
+  } else {
+    const long long u = t - low - high;
+    j = (int)(u / margin);
+    const int m = (int)(u - (long long)j * margin);
+    i = m < i0 ? m : m + di;
+    j += j0;
+  }
+  for (int k = k0 + blockIdx.y; k < k0 + dk; k += gridDim.y) out(i, j, k) = phi.ld(i, j, k);
+}
+
 int launch_rim_copy(View phi, View out, const int32_t o[3], const int32_t d[3], cudaStream_t st) {
   const int ri = 2 * o[0] + d[0], rj = 2 * o[1] + d[1];
-  const int i0 = o[0], j0 = o[1], k0 = o[2], di = d[0], dj = d[1];
-  const int32_t ext[3] = {ri, rj, d[2]};
-  return launch_box("smoothing_rim", ext, st, [=] __device__(int i, int j, int k) {
-    if (i >= i0 && i < i0 + di && j >= j0 && j < j0 + dj) return;
-    out(i, j, k + k0) = phi.ld(i, j, k + k0);
-  });
+  const long long total = (long long)ri * rj - (long long)d[0] * d[1];
+  if (total <= 0 || d[2] <= 0) return TB200_OK;
+  dim3 grid((unsigned)((total + 255) / 256), (unsigned)(d[2] > 65535 ? 65535 : d[2]), 1);
+  rim_copy_kernel<<<grid, 256, 0, st>>>(phi, out, o[0], o[1], o[2], d[0], d[1], d[2], ri, rj);
+  return check_launch("smoothing_rim");
 }
 
 // TB200_SMOOTH_IMPL: "march2" (default) or "tile"
