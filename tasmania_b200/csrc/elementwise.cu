@@ -461,10 +461,10 @@ extern "C" int tb200_velocity(int axis, const tb200_field *in_d, const tb200_fie
                     [=] __device__(int i, int j, int k) {
                       i += i0; j += j0; k += k0;
                       if (staggering) {
-                        w(i, j, k) = (dw(i - hi, j - hj, k) + dw(i, j, k)) /
-                                     (d(i - hi, j - hj, k) + d(i, j, k));
+                        w(i, j, k) = qdiv(dw(i - hi, j - hj, k) + dw(i, j, k),
+                                          d(i - hi, j - hj, k) + d(i, j, k));
                       } else {
-                        w(i, j, k) = dw(i, j, k) / d(i, j, k);
+                        w(i, j, k) = qdiv(dw(i, j, k), d(i, j, k));
                       }
                     });
 }
@@ -646,7 +646,7 @@ extern "C" int tb200_mass_fraction(const tb200_field *in_d, const tb200_field *i
   return launch_box("mass_fraction", domain, static_cast<cudaStream_t>(stream),
                     [=] __device__(int i, int j, int k) {
                       i += i0; j += j0; k += k0;
-                      const double x = dq(i, j, k) / d(i, j, k);
+                      const double x = qdiv(dq(i, j, k), d(i, j, k));
                       q(i, j, k) = clipping ? (x > 0.0 ? x : 0.0) : x;
                     });
 }

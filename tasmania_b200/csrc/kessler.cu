@@ -207,7 +207,7 @@ static int run_sedimentation(View rho, View h, View qr, View vt, View tnd, bool 
       dfdz = a * f0 * qr(i, j, k) * vt(i, j, k) + b * f1 * qr(i, j, k - 1) * vt(i, j, k - 1) +
              c * rho(i, j, k - 2) * qr(i, j, k - 2) * vt(i, j, k - 2);
     }
-    set_output(tnd(i, j, k), dfdz / f0, ow);
+    set_output(tnd(i, j, k), qdiv(dfdz, f0), ow);  // (same bits as `/`; zero wherever there is no rain)
   });
 }
 

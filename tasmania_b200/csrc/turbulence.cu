@@ -12,7 +12,8 @@
 // in three steps -- velocities on the tile + 2, nu s00 / nu s01 / nu s11 on the tile + 1,
 // tendencies on the tile -- so every division of su / s and every square root is evaluated once
 // per point (plus the halo), and global memory is read once: 24 + 16 B/point (isentropic).
-// Operation order is the reference's, divisions and the square root are IEEE: bit-identical.
+// Operation order is the reference's, divisions (by 2 dx / 2 dy through CDiv, by s through qdiv:
+// both correctly rounded, common.cuh) and the square root are IEEE: bit-identical.
 #include <math.h>
 
 #include "common.cuh"
@@ -28,7 +29,8 @@ constexpr int PX = TX + 2, PY = TY + 2;    // products:   tile + 1
 struct SmagArgs {
   View s, a, b;        // isentropic: s, su, sv; otherwise a = u, b = v
   View out_a, out_b;
-  double two_dx, two_dy, coeff;  // 2 dx, 2 dy, cs^2 dx dy
+  CDiv two_dx, two_dy;  // 2 dx, 2 dy (correctly rounded division by a constant: same bits as `/`)
+  double coeff;         // cs^2 dx dy
   bool ow_a, ow_b;
   int i0, j0, k0, di, dj, dk;
 };
@@ -49,8 +51,8 @@ __global__ void __launch_bounds__(TX *TY) smagorinsky_kernel(const SmagArgs a) {
       if (i < ie + 2 && j < je + 2) {
         if (ISEN) {  // isentropic/physics/turbulence.py:L119-L120
           const double sd = a.s.ld(i, j, k);
-          uu = a.a.ld(i, j, k) / sd;
-          vv = a.b.ld(i, j, k) / sd;
+          uu = qdiv(a.a.ld(i, j, k), sd);  // same bits as `/` (zero momenta keep the fast path)
+          vv = qdiv(a.b.ld(i, j, k), sd);
         } else {
           uu = a.a.ld(i, j, k);
           vv = a.b.ld(i, j, k);
@@ -108,7 +110,7 @@ extern "C" int tb200_smagorinsky(const tb200_field *in_s, const tb200_field *in_
   a.s = view(in_s); a.a = view(in_a); a.b = view(in_b);
   a.out_a = view(out_a_tnd); a.out_b = view(out_b_tnd);
   const bool isen = a.s.ok();
-  a.two_dx = 2.0 * dx; a.two_dy = 2.0 * dy;
+  a.two_dx = make_cdiv(2.0 * dx); a.two_dy = make_cdiv(2.0 * dy);
   a.coeff = pow(cs, 2.0) * dx * dy;  // cs**2 * dx * dy exactly as Python evaluates it (libm pow)
   a.ow_a = ow_out_a_tnd != 0; a.ow_b = ow_out_b_tnd != 0;
   a.i0 = origin[0]; a.j0 = origin[1]; a.k0 = origin[2];

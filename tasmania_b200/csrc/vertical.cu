@@ -71,6 +71,7 @@ struct VAdvArgs {
   int nout;      // 3 dry, 6 moist
   bool staggered;
   double dz;
+  CDiv cdz;  // division by dz as a correctly rounded reciprocal-multiply (same bits as `/`)
   FluxConst fc;
   int i0, j0, k0, di, dj, dk;
 };
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) vadv_kernel(const VAdvArgs a, int n0, int
       for (int f = 0; f < 3; ++f) {
         const View &v = *dry[f];
         auto phi = [&](int kk) { return v.ld(i, j, kk); };
-        tnd[f] = (F::eval(w1, phi, k + 1, a.fc) - F::eval(w0, phi, k, a.fc)) / a.dz;  // L341-L353
+        tnd[f] = (F::eval(w1, phi, k + 1, a.fc) - F::eval(w0, phi, k, a.fc)) / a.cdz;  // L341-L353
       }
       if (a.nout == 6) {
         const View *q[3] = {&a.qv, &a.qc, &a.qr};
@@ -112,7 +113,9 @@ __global__ void __launch_bounds__(256) vadv_kernel(const VAdvArgs a, int n0, int
         for (int f = 0; f < 3; ++f) {
           const View &v = *q[f];
           auto phi = [&](int kk) { return a.s.ld(i, j, kk) * v.ld(i, j, kk); };  // L323-L329
-          tnd[3 + f] = (F::eval(w1, phi, k + 1, a.fc) - F::eval(w0, phi, k, a.fc)) / sdz;  // L366-L385
+          // (qdiv: same bits as `/`; the flux difference of a water constituent is ZERO wherever there
+          // is no cloud or rain, and the compiler's division takes its slow path for a zero numerator)
+          tnd[3 + f] = qdiv(F::eval(w1, phi, k + 1, a.fc) - F::eval(w0, phi, k, a.fc), sdz);  // L366-L385
         }
       }
     }
@@ -356,6 +359,7 @@ static int vadv_entry(
   a.nout = moist ? 6 : 3;
   a.staggered = staggered_w != 0;
   a.dz = dz;
+  a.cdz = make_cdiv(dz);
   a.fc = make_flux_const(1.0, 1.0);
   a.i0 = origin[0]; a.j0 = origin[1]; a.k0 = origin[2];
   a.di = domain[0]; a.dj = domain[1]; a.dk = domain[2];
