@@ -497,6 +497,23 @@ int tb200_p2p_release(void *ptr);                /* undo tb200_p2p_import */
 /* *error != 0: a pull gave up waiting for its peer (~20 s); the results are invalid */
 int tb200_p2p_channel_error(const void *channel, int *error);
 
+/* ---- Coriolis / Smagorinsky fused with the stage update of a tendency stepper (b200 only; the
+ * reference runs the component's stencil into tendency storages and then the `fma` stencil over the
+ * whole storages: src/tasmania/framework/subclasses/tendency_steppers/{forward_euler,rk2,rk3ws}.py
+ * over src/tasmania/utils/xarrayx.py:L688-L740):
+ *   out = base + factor * tendency on [origin, origin + domain),  out = base + factor * 0 on the rest
+ * of the `full` box [0, full) (the storages' shape).  Tendency formulas and argument meaning as in
+ * tb200_coriolis / tb200_smagorinsky (in_s NULL = the non-isentropic Smagorinsky2d). */
+int tb200_coriolis_step(const tb200_field *in_su, const tb200_field *in_sv,
+                        const tb200_field *base_su, const tb200_field *base_sv, tb200_field *out_su,
+                        tb200_field *out_sv, double f, double factor, const int32_t origin[3],
+                        const int32_t domain[3], const int32_t full[3], void *stream);
+int tb200_smagorinsky_step(const tb200_field *in_s, const tb200_field *in_a, const tb200_field *in_b,
+                           const tb200_field *base_a, const tb200_field *base_b, tb200_field *out_a,
+                           tb200_field *out_b, double dx, double dy, double cs, double factor,
+                           const int32_t origin[3], const int32_t domain[3], const int32_t full[3],
+                           void *stream);
+
 /* ---- self-test of the kernels' own correctly rounded division (csrc/common.cuh: qdiv) against
  * the compiler's IEEE division on `count` generated operand pairs (random, guard-crossing and
  * hard-case classes); *mismatches (device memory, zeroed by the caller) receives the number of

@@ -445,6 +445,45 @@ extern "C" int tb200_coriolis(const tb200_field *in_su, const tb200_field *in_sv
                     });
 }
 
+// Coriolis forcing fused with the stage update of a tendency stepper (b200 only; the reference
+// runs the stencil above into a tendency storage and then `fma` over the whole storage,
+// framework/subclasses/tendency_steppers/*.py over utils/xarrayx.py:L688-L740):
+//   out = base + factor * tendency,  tendency = f sv / -f su on [origin, origin + domain), 0 elsewhere
+// over the `full` box (the storages' shape) in one pass: 4 reads + 2 writes per point instead of
+// 2 + 2 (tendencies) and 4 + 2 (fma).  Same operations in the same order, hence the same bits.
+extern "C" int tb200_coriolis_step(const tb200_field *in_su, const tb200_field *in_sv,
+                                   const tb200_field *base_su, const tb200_field *base_sv,
+                                   tb200_field *out_su, tb200_field *out_sv, double f, double factor,
+                                   const int32_t origin[3], const int32_t domain[3],
+                                   const int32_t full[3], void *stream) {
+  View su = view(in_su), sv = view(in_sv), bu = view(base_su), bv = view(base_sv);
+  View ou = view(out_su), ov = view(out_sv);
+  const int32_t zero[3] = {0, 0, 0};
+  TB200_REQUIRE(box_inside(su, origin, domain) && box_inside(sv, origin, domain),
+                "coriolis_step: box outside an input storage");
+  TB200_REQUIRE(box_inside(bu, zero, full) && box_inside(bv, zero, full) && box_inside(ou, zero, full) &&
+                    box_inside(ov, zero, full),
+                "coriolis_step: full box outside a base / output storage");
+  TB200_REQUIRE(origin[0] >= 0 && origin[1] >= 0 && origin[2] >= 0 && origin[0] + domain[0] <= full[0] &&
+                    origin[1] + domain[1] <= full[1] && origin[2] + domain[2] <= full[2],
+                "coriolis_step: the tendency box must lie inside the full box");
+  TB200_REQUIRE(ou.p != su.p && ou.p != sv.p && ov.p != su.p && ov.p != sv.p && ou.p != ov.p,
+                "coriolis_step: outputs must not alias the inputs or each other");
+  const int i0 = origin[0], j0 = origin[1], k0 = origin[2];
+  const int i1 = i0 + domain[0], j1 = j0 + domain[1], k1 = k0 + domain[2];
+  const double mf = -f;
+  return launch_box("coriolis_step", full, static_cast<cudaStream_t>(stream),
+                    [=] __device__(int i, int j, int k) {
+                      double a = 0.0, b = 0.0;  // the tendency storages of the reference path hold 0 outside the box
+                      if (i >= i0 && i < i1 && j >= j0 && j < j1 && k >= k0 && k < k1) {
+                        a = f * sv(i, j, k);
+                        b = mf * su(i, j, k);
+                      }
+                      ou(i, j, k) = bu(i, j, k) + factor * a;
+                      ov(i, j, k) = bv(i, j, k) + factor * b;
+                    });
+}
+
 // ---------------------------------------------------------------------------- K4
 extern "C" int tb200_velocity(int axis, const tb200_field *in_d, const tb200_field *in_dw,
                               tb200_field *out_w, int staggering, const int32_t origin[3],

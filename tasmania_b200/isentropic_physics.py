@@ -111,6 +111,17 @@ class IsentropicConservativeCoriolis(StencilFactory):
                       ow_tnd_sv=ow.get(SV, True), origin=(nb, nb, 0),
                       domain=(g.nx - 2 * nb, g.ny - 2 * nb, g.nz))
 
+    def array_call_stepped(self, state, base, factor, out_state):
+        """b200 only -- one stage of a tendency stepper in one kernel: out_state = base + factor *
+        tendency(state) over the whole storages (tasmania_b200.coupling.TendencyStepper uses it
+        instead of ``array_call`` + ``fma``)."""
+        g, nb = self.grid, self._nb
+        if not hasattr(self, "_stencil_step"):
+            self._stencil_step = self.compile_stencil("coriolis_step")
+        self._stencil_step(in_su=state[SU], in_sv=state[SV], base_su=base[SU], base_sv=base[SV],
+                           out_su=out_state[SU], out_sv=out_state[SV], f=self._f, factor=factor,
+                           origin=(nb, nb, 0), domain=(g.nx - 2 * nb, g.ny - 2 * nb, g.nz))
+
 
 class Smagorinsky2d(StencilFactory):
     """Mirror of ``tasmania.Smagorinsky2d`` (src/tasmania/physics/turbulence.py:L42-L163):
@@ -159,6 +170,16 @@ class IsentropicSmagorinsky(Smagorinsky2d):
         self._stencil(in_s=state[S], in_su=state[SU], in_sv=state[SV], out_su_tnd=out_tendencies[SU],
                       out_sv_tnd=out_tendencies[SV], dx=g.dx, dy=g.dy, cs=self._cs,
                       ow_out_su_tnd=ow.get(SU, True), ow_out_sv_tnd=ow.get(SV, True), **self._box())
+
+    def array_call_stepped(self, state, base, factor, out_state):
+        """b200 only -- one stage of a tendency stepper without the round trip of the tendencies
+        through memory: out_state = base + factor * tendency(state) over the whole storages."""
+        g = self.grid
+        if not hasattr(self, "_stencil_step"):
+            self._stencil_step = self.compile_stencil("smagorinsky_isentropic_step")
+        self._stencil_step(in_s=state[S], in_su=state[SU], in_sv=state[SV], base_su=base[SU],
+                           base_sv=base[SV], out_su=out_state[SU], out_sv=out_state[SV], dx=g.dx, dy=g.dy,
+                           cs=self._cs, factor=factor, **self._box())
 
 
 class IsentropicImplicitVerticalAdvectionDiagnostic(StencilFactory):

@@ -108,6 +108,8 @@ SIGNATURES = {
     "tb200_accumulated_precipitation": [_F] * 6 + [_D, _D, _I3, _I3, _V],
     "tb200_smagorinsky": [_F] * 5 + [_D, _D, _D, _I, _I, _I3, _I3, _V],
     "tb200_coriolis": [_F] * 4 + [_D, _I, _I, _I3, _I3, _V],
+    "tb200_coriolis_step": [_F] * 6 + [_D, _D, _I3, _I3, _I3, _V],
+    "tb200_smagorinsky_step": [_F] * 7 + [_D, _D, _D, _D, _I3, _I3, _I3, _V],
     "tb200_implicit_vertical_advection": [_I] + [_F] * 13 + [_D, _D, _I3, _I3, _V],
     "tb200_vertical_advection": [_I, _I] + [_F] * 13 + [_D, C.c_uint32, _I3, _I3, _V],
     "tb200_vertical_advection_step": [_I, _I, _F, _I, _FPP, _FPP, _FPP, _D, _D, _I3, _I3, _V],

@@ -527,6 +527,24 @@ def coriolis_b200(externals, *, in_su, in_sv, tnd_su, tnd_sv, f, ow_tnd_su, ow_t
           int(bool(ow_tnd_su)), int(bool(ow_tnd_sv)), _i3(origin), _i3(domain), _stream())
 
 
+@stencil_definition("coriolis_step")
+def coriolis_step_b200(externals, *, in_su, in_sv, base_su, base_sv, out_su, out_sv, f, factor, origin, domain):
+    """b200 only: Coriolis forcing fused with the stage update of a tendency stepper
+    (``tb200_coriolis_step``): out = base + factor * tendency over the whole storages."""
+    _call("tb200_coriolis_step", _f(in_su), _f(in_sv), _f(base_su), _f(base_sv), _f(out_su), _f(out_sv),
+          float(f), float(factor), _i3(origin), _i3(domain), _i3(out_su.shape), _stream())
+
+
+@stencil_definition("smagorinsky_isentropic_step")
+def smagorinsky_isentropic_step_b200(externals, *, in_s, in_su, in_sv, base_su, base_sv, out_su, out_sv, dx, dy,
+                                     cs, factor, origin, domain):
+    """b200 only: IsentropicSmagorinsky fused with the stage update of a tendency stepper
+    (``tb200_smagorinsky_step``)."""
+    _call("tb200_smagorinsky_step", _f(in_s), _f(in_su), _f(in_sv), _f(base_su), _f(base_sv), _f(out_su),
+          _f(out_sv), float(dx), float(dy), float(cs), float(factor), _i3(origin), _i3(domain),
+          _i3(out_su.shape), _stream())
+
+
 # ------------------------------------------------------------------ vertical advection (8f-1)
 def _vflux_code(externals):
     d = _scheme_of(externals.get("get_flux_dry", externals.get("flux_dry")))

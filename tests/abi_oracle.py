@@ -318,6 +318,26 @@ class OracleStub(AbiStub):
             op.smagorinsky(arr(a), arr(b), arr(t_a), arr(t_b), dx=dx, dy=dy, cs=cs, ow_out_u_tnd=bool(ow_a),
                            ow_out_v_tnd=bool(ow_b), origin=origin, domain=domain, in_s=arr(s))
 
+    def _do_tb200_coriolis_step(self, su, sv, b_su, b_sv, o_su, o_sv, f, factor, o, d, full, stream):
+        origin, domain = box(o, d)
+        shape = tuple(int(full[n]) for n in range(3))
+        t_su, t_sv = np.zeros(arr(o_su).shape), np.zeros(arr(o_sv).shape)
+        op.coriolis(arr(su), arr(sv), t_su, t_sv, f=f, ow_tnd_su=True, ow_tnd_sv=True, origin=origin, domain=domain)
+        fb = tuple(slice(0, n) for n in shape)
+        arr(o_su)[fb] = arr(b_su)[fb] + factor * t_su[fb]
+        arr(o_sv)[fb] = arr(b_sv)[fb] + factor * t_sv[fb]
+
+    def _do_tb200_smagorinsky_step(self, s, a, b, b_a, b_b, o_a, o_b, dx, dy, cs, factor, o, d, full, stream):
+        origin, domain = box(o, d)
+        shape = tuple(int(full[n]) for n in range(3))
+        t_a, t_b = np.zeros(arr(o_a).shape), np.zeros(arr(o_b).shape)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            op.smagorinsky(arr(a), arr(b), t_a, t_b, dx=dx, dy=dy, cs=cs, ow_out_u_tnd=True, ow_out_v_tnd=True,
+                           origin=origin, domain=domain, in_s=arr(s))
+        fb = tuple(slice(0, n) for n in shape)
+        arr(o_a)[fb] = arr(b_a)[fb] + factor * t_a[fb]
+        arr(o_b)[fb] = arr(b_b)[fb] + factor * t_b[fb]
+
     def _vadv(self, flux, staggered, w, ins, outs, dz, ows, o, d):
         origin, domain = box(o, d)
         moist = len(ins) == 6

@@ -145,7 +145,9 @@ def test_moist_model_host_path_end_to_end():
         per_step = {n: calls.count(n) for n in set(calls)}
         # physics stages: Coriolis rk2 (2), Smagorinsky rk2 (2), Kessler rk2 (2), saturation rk2
         # (2), vertical advection rk3ws (3), sedimentation rk3ws (3)
-        assert per_step["tb200_coriolis"] == 2 and per_step["tb200_smagorinsky"] == 2
+        # (Coriolis and Smagorinsky apply their stage update themselves: no tendencies + fma round trip)
+        assert per_step["tb200_coriolis_step"] == 2 and per_step["tb200_smagorinsky_step"] == 2
+        assert "tb200_coriolis" not in per_step and "tb200_smagorinsky" not in per_step
         assert per_step["tb200_kessler"] == 2 and per_step["tb200_saturation_prognostic"] == 2
         # (the vertical advection applies its stage update itself: no tendencies + fma round trip)
         assert per_step["tb200_vertical_advection_step"] == 3 and per_step["tb200_sedimentation"] == 3
@@ -153,7 +155,7 @@ def test_moist_model_host_path_end_to_end():
         assert per_step["tb200_fall_velocity"] == 4          # 3 sedimentation stages + precipitation
         assert per_step["tb200_accumulated_precipitation"] == 1
         assert per_step["tb200_smoothing"] == 6              # s, su, sv, qv, qc, qr
-        assert per_step["tb200_fma_fields"] == 11            # one per remaining stepper stage
+        assert per_step["tb200_fma_fields"] == 7             # one per remaining stepper stage
         assert per_step["tb200_diagnostic_variables"] == 1
         assert per_step["tb200_density_and_temperature"] == 1
         # moist dycore: one fused call per RK stage (s-step, tracers, scans, momentum, relaxation,
@@ -164,8 +166,8 @@ def test_moist_model_host_path_end_to_end():
                     "tb200_density", "tb200_mass_fraction", "tb200_damping"} & set(per_step)
         # order: dynamics first, then the physics in the driver's order
         first = {n: calls.index(n) for n in per_step}
-        order = ["tb200_isentropic_stage_moist", "tb200_diagnostic_variables", "tb200_coriolis",
-                 "tb200_smoothing", "tb200_smagorinsky", "tb200_kessler",
+        order = ["tb200_isentropic_stage_moist", "tb200_diagnostic_variables", "tb200_coriolis_step",
+                 "tb200_smoothing", "tb200_smagorinsky_step", "tb200_kessler",
                  "tb200_saturation_prognostic", "tb200_vertical_advection_step", "tb200_sedimentation",
                  "tb200_accumulated_precipitation"]
         assert [first[n] for n in order] == sorted(first[n] for n in order)
