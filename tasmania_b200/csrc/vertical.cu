@@ -14,6 +14,9 @@
 // The reference's set_output works on WHOLE storages (generics.py:L38-L40): with `overwrite` the
 // output is zero outside the computed levels -- and outside the box -- so the kernel covers the
 // full output storage.  Operation order is the reference's: bit-identical results.
+#include <stdlib.h>
+#include <string.h>
+
 #include "stencil_math.cuh"
 
 using namespace tb200;
@@ -129,10 +132,124 @@ __global__ void __launch_bounds__(256) vadv_kernel(const VAdvArgs a, int n0, int
   }
 }
 
+// Marching variant (TB200_VADV_IMPL=march): one thread per column and chunk of KC levels, marching along k with
+// the 2E+1 levels around k of every advected field in registers (the water constituents as the
+// products s q the reference advects).  The kernel above evaluates every interface flux twice
+// (once from either side) and re-reads each level 2E+1 times from L1 / L2 (75 loads per point in
+// the moist model: 187 us per launch at configs[2], the top kernel of its step, profiles/
+// README.md round 2); here every level is read once per chunk (+ 2E warm-up levels) and every
+// flux evaluated once.  Same flux functions on the same operands in the same order: same bits.
+constexpr int VADV_KC = 16;
+template <int SCHEME, bool STEP, int NF>
+__global__ void __launch_bounds__(128) vadv_march_kernel(const VAdvArgs a, int n0, int n1, int n2) {
+  using F = VFlux<SCHEME>;
+  constexpr int E = F::extent;
+  constexpr int NWIN = 2 * E + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n0 || j >= n1) return;
+  const bool col_in = i >= a.i0 && i < a.i0 + a.di && j >= a.j0 && j < a.j0 + a.dj;
+  const int kb = blockIdx.z * VADV_KC, ke = min(kb + VADV_KC, n2);
+  const int klo = a.k0 + E, khi = a.k0 + a.dk - E;  // levels with a tendency: [klo, khi)
+  const View *fld[6] = {&a.s, &a.su, &a.sv, &a.qv, &a.qc, &a.qr};
+  // level kk of field f as the reference advects it (clamped into the storage: clamped levels are
+  // only ever part of windows of levels without a tendency)
+  auto level = [&](int f, int kk, double s_at) {
+    const double x = fld[f]->ld(i, j, kk);
+    return f < 3 ? x : s_at * x;  // vertical_advection.py:L323-L329
+  };
+  double win[NF][NWIN];  // win[f][m] = field f at level k - E + m
+  if (col_in) {
+#pragma unroll
+    for (int m = 0; m < NWIN - 1; ++m) {  // levels kb - E .. kb + E - 1 go to slots 1 .. 2E (shifted below)
+      const int kk = min(max(kb - E + m, 0), n2 - 1);
+      const double s_at = a.s.ld(i, j, kk);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) win[f][m + 1] = f == 0 ? s_at : level(f, kk, s_at);
+    }
+  }
+  double flo[NF];
+  bool have_lo = false;
+  for (int k = kb; k < ke; ++k) {
+    double tnd[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) tnd[f] = 0.0;
+    if (col_in) {
+      const int kk = min(k + E, n2 - 1);
+      const double s_at = a.s.ld(i, j, kk);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+#pragma unroll
+        for (int m = 0; m < NWIN - 1; ++m) win[f][m] = win[f][m + 1];
+        win[f][NWIN - 1] = f == 0 ? s_at : level(f, kk, s_at);
+      }
+      if (k >= klo && k < khi) {
+        double w0, w1;  // vertical velocity at the interfaces k and k + 1 (vertical_advection.py:L308-L320)
+        if (a.staggered) {
+          w0 = a.w.ld(i, j, k);
+          w1 = a.w.ld(i, j, k + 1);
+        } else {
+          const double wm = a.w.ld(i, j, k - 1), wc = a.w.ld(i, j, k), wp = a.w.ld(i, j, k + 1);
+          w0 = 0.5 * (wc + wm);
+          w1 = 0.5 * (wp + wc);
+        }
+        const double sdz = win[0][E] * a.dz;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          auto phi = [&](int q) { return win[f][q - k + E]; };  // q in [k - E, k + E]
+          if (!have_lo) flo[f] = F::eval(w0, phi, k, a.fc);
+          const double fhi = F::eval(w1, phi, k + 1, a.fc);
+          if (f < 3)
+            tnd[f] = (fhi - flo[f]) / a.cdz;  // L341-L353
+          else
+            tnd[f] = qdiv(fhi - flo[f], sdz);  // L366-L385
+          flo[f] = fhi;
+        }
+        have_lo = true;
+      } else {
+        have_lo = false;
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      double &o = a.out[f](i, j, k);
+      if (STEP)  // DataArrayDictOperator.fma of the stepper stage, math.py:L59-L63, same storage box
+        o = a.base[f].ld(i, j, k) + a.factor * tnd[f];
+      else
+        o = a.ow[f] ? tnd[f] : o + tnd[f];  // generics.py:L38-L40, on the whole storage
+    }
+  }
+}
+
+int vadv_impl() {  // TB200_VADV_IMPL=point (default) | march
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("TB200_VADV_IMPL");
+    impl = (e != nullptr && strcmp(e, "march") == 0) ? 1 : 0;
+  }
+  return impl;
+}
+
 template <int SCHEME>
 int run_vadv(const VAdvArgs &a, bool step, cudaStream_t st) {
   const View &o = a.out[0];
   if (o.n0 <= 0 || o.n1 <= 0 || o.n2 <= 0) return TB200_OK;
+  if (vadv_impl() == 1) {
+    dim3 block(32, 4, 1);
+    dim3 grid((o.n0 + 31) / 32, (o.n1 + 3) / 4, (o.n2 + VADV_KC - 1) / VADV_KC);
+    if (a.nout == 6) {
+      if (step)
+        vadv_march_kernel<SCHEME, true, 6><<<grid, block, 0, st>>>(a, o.n0, o.n1, o.n2);
+      else
+        vadv_march_kernel<SCHEME, false, 6><<<grid, block, 0, st>>>(a, o.n0, o.n1, o.n2);
+    } else {
+      if (step)
+        vadv_march_kernel<SCHEME, true, 3><<<grid, block, 0, st>>>(a, o.n0, o.n1, o.n2);
+      else
+        vadv_march_kernel<SCHEME, false, 3><<<grid, block, 0, st>>>(a, o.n0, o.n1, o.n2);
+    }
+    return check_launch(step ? "vertical_advection_step(march)" : "vertical_advection(march)");
+  }
   dim3 block(64, 4, 1);
   dim3 grid((o.n0 + 63) / 64, (o.n1 + 3) / 4, o.n2 > 65535 ? 65535 : o.n2);
   if (step)
