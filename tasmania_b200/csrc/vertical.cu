@@ -139,6 +139,9 @@ __global__ void __launch_bounds__(256) vadv_kernel(const VAdvArgs a, int n0, int
 // the moist model: 187 us per launch at configs[2], the top kernel of its step, profiles/
 // README.md round 2); here every level is read once per chunk (+ 2E warm-up levels) and every
 // flux evaluated once.  Same flux functions on the same operands in the same order: same bits.
+// NOT the default: measured slower (configs[2]: 4.18 against 3.89 ms per step, 640 x 640 x 64: 22.8
+// against 22.2 ms) -- six windows of 2E+1 levels cost 192 registers in the moist third-order
+// variant, i.e. 8 warps per SM with every level's loads exposed; the point kernel's re-reads hit L1.
 constexpr int VADV_KC = 16;
 template <int SCHEME, bool STEP, int NF>
 __global__ void __launch_bounds__(128) vadv_march_kernel(const VAdvArgs a, int n0, int n1, int n2) {

@@ -258,3 +258,22 @@ def test_implicit_vertical_advection_tendency_vs_reference_fixture_bitwise():
         for n, arr in tnd.items():
             got = tb.to_numpy(arr)[:nx, :ny, :nz]
             np.testing.assert_array_equal(got, fx[f"implicit_tnd_z{z}_m{m}_{key[n]}"][:nx, :ny, :nz], err_msg=n)
+
+
+def test_marching_vertical_advection_variant_bitwise():
+    """``TB200_VADV_IMPL=march`` (thread per column and chunk of levels, register windows; measured
+    slower than the default at configs[2], kept as a variant): the vertical-advection tests of this
+    file and the fused advection step of the moist model give the same bits.  The switch is read
+    once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           os.path.join(root, "tests", "test_gpu_isentropic_physics.py"), "-k",
+           "stencil_vs_reference_fixture or host_mirror_vs_oracle or uniform_column",
+           os.path.join(root, "tests", "test_gpu_moist_model.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root,
+                         env=dict(os.environ, TB200_VADV_IMPL="march"))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
