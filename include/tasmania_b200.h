@@ -397,9 +397,12 @@ typedef struct tb200_isentropic_stage {
    *   instead of being read -- bit-identical whenever u_int / v_int ARE that diagnosis (true for
    *   the output of a previous stage; not for an arbitrary initial state), u_int / v_int are not
    *   touched and may be stale.
-   * skip_uv_out != 0: u_new / v_new are not written (an intermediate stage whose consumer sets
-   *   derive_uv_in).  With skip_uv_out, scratch_s may be the SAME storage as s_new: the stage then
-   *   updates s in place and stores it only where relaxation / damping changed it. */
+   * skip_uv_out != 0: u_new / v_new are not written: an intermediate stage whose consumer sets
+   *   derive_uv_in, or the last stage of a step when the caller diagnoses the velocities of the
+   *   final state with one tb200_velocity_components pass (what the hosts of this repository do:
+   *   cheaper than the in-kernel diagnosis).  With skip_uv_out, scratch_s may be the SAME storage
+   *   as s_new: the stage then updates s in place and stores it only where relaxation / damping
+   *   changed it. */
   int32_t derive_uv_in;
   int32_t skip_uv_out;
 } tb200_isentropic_stage;
