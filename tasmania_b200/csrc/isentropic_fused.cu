@@ -8,28 +8,38 @@
 // The reference runs 13 full-domain passes for this; here three kernels (default path):
 //
 //   kernel A   (one warp per 31 columns x 64 rows of one level, marching in j)
-//       s_pre = irelax(K1(...))                                -> scratch_s
+//       s_pre = irelax(K1(...))                                -> scratch_s (= s_new: in place)
 //   kernel B   (one thread per column, the column in registers)
 //       pressure by the downward scan on s_pre, exn = cp (p/pref)^kappa (pow_pos_n<8>),
 //       mtg_new by the upward scan                             -> scratch_mtg
 //   kernel MV  (one warp per 60 columns x 64 rows of one level, two columns per lane, marching
 //       in j; su / sv / mtg rows staged with cp.async into warp-private shared-memory rings)
-//       su, sv = irelax(K2(...)), s = irelax(s_pre), Rayleigh damping on all three,
-//       u, v from the final s, su, sv, outermost faces from the reference state.
+//       su, sv = irelax(K2(...)), s = irelax(s_pre), Rayleigh damping on all three.
 //
 // The vertical scans are inherently two sweeps (pressure top-down, Montgomery bottom-up) and
 // the momentum step needs mtg_new at i+-1 / j+-1, hence the kernel boundaries.
 //
-// HBM traffic per point and stage (8-byte words): A reads s_now, s_int, u, v, writes s_pre (5);
-// B reads s_pre, writes mtg (2); MV reads s_now, s_pre, mtg_now, mtg_new, u, v, su_now, su_int,
-// sv_now, sv_int, writes s, su, sv, u, v (15).  22 words = 176 B against the algorithmic minimum
-// of 112 B; measured 206 B.  All arithmetic follows
-// the reference's operation order (see stencil_math.cuh).
+// Velocities (round 2).  The reference ends every stage with the diagnosis of u, v and starts the
+// next one by reading them.  With derive_uv_in / skip_uv_out (tb200_isentropic_stage) no stage
+// writes them: kernels A and MV re-diagnose the advecting velocities from s_int, su_int, sv_int
+// with the same formula (same bits; the division is common.cuh:qdiv, which keeps zero numerators
+// off the compiler's slow path), and the velocities of the step's final state come from one pass
+// of tb200_velocity_components (elementwise.cu).  The moist stage (tb200_isentropic_stage_moist)
+// adds kernel T between A and B: the three water constituents (density, K1 share, mass fraction,
+// relaxation) in one tiled kernel.
+//
+// HBM traffic per point and stage (8-byte words), stages 1, 2: A reads s_now, s_int, su_int,
+// sv_int, writes s_pre (5); B reads s_pre, writes mtg (2); MV reads s_now, s_int, s_pre, mtg_now,
+// mtg_new, su_now, su_int, sv_now, sv_int, writes su, sv and s where relaxation / damping change
+// it (11+): 18 words = 144 B against the algorithmic minimum of 112 B (80 B
+// without the u, v round trip); measured 164 B (146 B at stage 0).  All
+// arithmetic follows the reference's operation order (see stencil_math.cuh).
 //
 // Earlier variants are kept selectable and bit-identical (tests/test_gpu_stage_variants.py):
 // TB200_S_IMPL=column (kernel S = A + B in one thread-per-column kernel, pressures parked in
-// memory), TB200_MV_IMPL=window | ring (register windows / one column per lane),
-// TB200_STAGE_IMPL=tma (isentropic_tma.cu).
+// memory), TB200_A_IMPL=two (two columns per lane), TB200_MV_IMPL=window | ring (register windows /
+// one column per lane), TB200_MV_BLOCK=3x1 | 6x1, TB200_STAGE_IMPL=tma (isentropic_tma.cu),
+// TB200_LAZY_UV=0 (the reference's velocity round trip), TB200_T_IMPL=point.
 #include <stdlib.h>
 #include <string.h>
 
