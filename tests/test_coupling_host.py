@@ -270,3 +270,28 @@ def test_as_parallel_policy_components_do_not_see_each_other():
             assert (promoted[:3, :2, :1] == (want if policy == "serial" else 0.0)).all()
     with pytest.raises(ValueError):
         ConcurrentCoupling(Diag(), execution_policy="concurrent")
+
+
+def test_fused_stage_is_for_the_two_dimensional_relaxed_boundary_only():
+    """Relaxed1DX / Relaxed1DY also report type "relaxed", but the fused kernels
+    assume the 2-D class (gamma == 1 on the nb outer rings, no repetition of the middle line): the
+    dycore must not select the fused stage for them, and must refuse it when forced."""
+    from tasmania_b200.boundary import HorizontalBoundary, Relaxed, Relaxed1DX
+    from tasmania_b200.grid import Grid
+    from tasmania_b200.isentropic import IsentropicDynamicalCore
+
+    with stubbed_library():
+        nx, nz, nb = 21, 6, 3
+        hb1 = HorizontalBoundary.factory("relaxed", nx, 1, nz, nb, nr=6)
+        assert isinstance(hb1, Relaxed1DX) and hb1.type == "relaxed"
+        grid1 = Grid((0.0, 100.0), hb1.ni, (0.0, 100.0), hb1.nj, (340.0, 280.0), nz)
+        kw = dict(time_integration_scheme="rk3ws_si", horizontal_flux_scheme="fifth_order_upwind",
+                  time_integration_properties={"pt": 1000.0, "eps": 0.5}, damp=False)
+        dyc = IsentropicDynamicalCore(grid1, hb1, **kw)
+        assert not dyc._fused and not dyc.lazy_velocities
+        with pytest.raises(ValueError):
+            IsentropicDynamicalCore(grid1, hb1, fused=True, **kw)
+        hb2 = HorizontalBoundary.factory("relaxed", nx, 19, nz, nb, nr=6)
+        assert type(hb2) is Relaxed
+        grid2 = Grid((0.0, 100.0), nx, (0.0, 100.0), 19, (340.0, 280.0), nz)
+        assert IsentropicDynamicalCore(grid2, hb2, **kw)._fused
