@@ -405,6 +405,11 @@ typedef struct tb200_isentropic_stage {
    *   changed it. */
   int32_t derive_uv_in;
   int32_t skip_uv_out;
+  /* Slow tendencies of s, su, sv (the `s_tnd`, `su_tnd`, `sv_tnd` arguments of the reference's
+   * step_forward_euler / step_forward_euler_momentum, prognostics/utils.py:L43-L204, as
+   * rk3ws_si.py:L105-L234 passes them): all three or none (NULL).  Same geometry as the other
+   * fields; dry stage, part 0 and the default kernel path only. */
+  const tb200_field *s_tnd, *su_tnd, *sv_tnd;
 } tb200_isentropic_stage;
 
 int tb200_isentropic_stage_dry(

@@ -159,8 +159,9 @@ constexpr int A_COLS = 31;
 // velocity_y, dwarfs/diagnostics.py:L219-L272) instead of read from u_int / v_int: the previous
 // stage then need not write them (tb200_isentropic_stage.derive_uv_in).  Same traffic for this
 // kernel (su_int, sv_int instead of u, v), two IEEE divisions more per point.
-template <int SCHEME, int LJ, bool DERIVE>
-__global__ void __launch_bounds__(128, DERIVE ? 6 : 7) stage_a_kernel(const StageArgs a) {
+// TND: a slow tendency of s is passed (prognostics/utils.py:L95-L99: s_now - dt (div - s_tnd))
+template <int SCHEME, int LJ, bool DERIVE, bool TND = false>
+__global__ void __launch_bounds__(128, (DERIVE || TND) ? 6 : 7) stage_a_kernel(const StageArgs a) {
   using F = Flux<SCHEME>;
   constexpr int E = F::extent;
   constexpr int NW = 2 * E;
@@ -260,7 +261,8 @@ __global__ void __launch_bounds__(128, DERIVE ? 6 : 7) stage_a_kernel(const Stag
     double v;
     if (interior) {  // prognostics/utils.py:L95-L99
       const double div = (fx_p - fx) / a.fc.dx + (fy_p - fy) / a.fc.dy;
-      v = cur.s_now - a.dt * (div - 0.0);
+      const double tnd = TND ? ldo(a.s_tnd.p, o_cm) : 0.0;
+      v = cur.s_now - a.dt * (div - tnd);
     } else {
       v = gam == 1.0 ? 0.0 : ldo(a.s_new.p, o_cm);  // untouched by K1; the relaxation decides
     }
@@ -1422,7 +1424,10 @@ struct OwnLoads2 {
 //           enough away in time for the shared sectors to have left L2 (profiles/README.md,
 //           round 2).  For the same reason the halo pairs nobody reads are not fetched any more.
 // WX x WY warps per block: WX side by side, WY strips of LJ rows.
-template <int SCHEME, int LJ, int WX, int WY, bool DERIVE, bool UVOUT>
+//   TND     slow tendencies of su, sv are passed (prognostics/utils.py:L191-L204); the reference's
+//           `- 0.0` becomes `- tnd`.  A separate instantiation, so that the kernels of a run
+//           without tendencies (the benchmark configurations) are untouched.
+template <int SCHEME, int LJ, int WX, int WY, bool DERIVE, bool UVOUT, bool TND = false>
 __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_kernel(const StageArgs a) {
   using F = Flux<SCHEME>;
   constexpr int E = F::extent;
@@ -1710,6 +1715,8 @@ __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_
     const bool int0 = col_int0 && row_int, int1 = col_int1 && row_int;
     double s0 = cur.s_pre.x, s1 = cur.s_pre.y, su0 = 0.0, su1 = 0.0, sv0 = 0.0, sv1 = 0.0;
     if (int0 || int1) {
+      // slow tendencies of the own pair (loaded at their use: not the benchmark's path)
+      const double2 tnd_su = TND ? ldo2(a.su_tnd.p, o_c) : zero2, tnd_sv = TND ? ldo2(a.sv_tnd.p, o_c) : zero2;
       // Montgomery potential: rows r-1, r, r+1 in slots (q + m) & 3
       const double *bm_m = w_su + (2 * SU_RING2 + (q & (MT_RING2 - 1))) * RW2;
       const double *bm_c = w_su + (2 * SU_RING2 + ((q + 1) & (MT_RING2 - 1))) * RW2;
@@ -1723,25 +1730,25 @@ __global__ void __launch_bounds__(32 * WX * WY, 384 / (32 * WX * WY)) stage_mv2_
         const double div = (fx_su1 - fx_su0) / a.fc.dx + (fy_su0_p - fy_su0) / a.fc.dy;
         const double pg_now = one_m_eps * cur.s_now.x * (mn_c.y - mn_l) / a.two_dx;
         const double pg_new = a.eps * s0 * (mw_c.y - mw_l) / a.two_dx;
-        su0 = cur.su_now.x - a.dt * (div + pg_now + pg_new - 0.0);
+        su0 = cur.su_now.x - a.dt * (div + pg_now + pg_new - tnd_su.x);
       }
       {
         const double div = (fx_su2 - fx_su1) / a.fc.dx + (fy_su1_p - fy_su1) / a.fc.dy;
         const double pg_now = one_m_eps * cur.s_now.y * (mn_r - mn_c.x) / a.two_dx;
         const double pg_new = a.eps * s1 * (mw_r - mw_c.x) / a.two_dx;
-        su1 = cur.su_now.y - a.dt * (div + pg_now + pg_new - 0.0);
+        su1 = cur.su_now.y - a.dt * (div + pg_now + pg_new - tnd_su.y);
       }
       {
         const double div = (fx_sv1 - fx_sv0) / a.fc.dx + (fy_sv0_p - fy_sv0) / a.fc.dy;
         const double pg_now = one_m_eps * cur.s_now.x * (mn_p.x - mn_m.x) / a.two_dy;
         const double pg_new = a.eps * s0 * (mw_p.x - mw_m.x) / a.two_dy;
-        sv0 = cur.sv_now.x - a.dt * (div + pg_now + pg_new - 0.0);
+        sv0 = cur.sv_now.x - a.dt * (div + pg_now + pg_new - tnd_sv.x);
       }
       {
         const double div = (fx_sv2 - fx_sv1) / a.fc.dx + (fy_sv1_p - fy_sv1) / a.fc.dy;
         const double pg_now = one_m_eps * cur.s_now.y * (mn_p.y - mn_m.y) / a.two_dy;
         const double pg_new = a.eps * s1 * (mw_p.y - mw_m.y) / a.two_dy;
-        sv1 = cur.sv_now.y - a.dt * (div + pg_now + pg_new - 0.0);
+        sv1 = cur.sv_now.y - a.dt * (div + pg_now + pg_new - tnd_sv.y);
       }
       if (!int0) { su0 = 0.0; sv0 = 0.0; }
       if (!int1) { su1 = 0.0; sv1 = 0.0; }
@@ -1890,7 +1897,7 @@ MvGeom mv_geom(const StageArgs &a, bool alt_blocks) {
   int impl = mv_impl();
   if (impl == 2 && !mv2_ok(a)) impl = 1;
   if (impl != 2) return MvGeom{impl, 4, 1, MV_COLS};
-  const int b = alt_blocks ? mv_block() : MV2_BLOCK_DEFAULT;
+  const int b = (alt_blocks && !a.su_tnd.ok()) ? mv_block() : MV2_BLOCK_DEFAULT;
   return b == 0 ? MvGeom{2, 2, 2, MV2_COLS} : b == 1 ? MvGeom{2, 3, 1, MV2_COLS} : MvGeom{2, 6, 1, MV2_COLS};
 }
 // is the default path (kernels A + B + two-column MV) in charge?  Only it honours derive_uv_in /
@@ -1901,23 +1908,32 @@ bool lazy_uv_path(const StageArgs &a) {
   return s_impl() != 0 && a.nz <= 64 && stage_impl() == 0 && mv_impl() == 2 && mv2_ok(a);
 }
 
-template <int SCHEME, int LJ, int WX, int WY, bool DERIVE, bool UVOUT>
+template <int SCHEME, int LJ, int WX, int WY, bool DERIVE, bool UVOUT, bool TND = false>
 int launch_mv2(const StageArgs &a, dim3 grid, cudaStream_t st) {
   const size_t smem = (size_t)WX * WY * WARP_DOUBLES2 * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(stage_mv2_kernel<SCHEME, LJ, WX, WY, DERIVE, UVOUT>,
+    if (cudaFuncSetAttribute(stage_mv2_kernel<SCHEME, LJ, WX, WY, DERIVE, UVOUT, TND>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("isentropic_stage_dry/MV2: %s", cudaGetErrorString(cudaGetLastError()));
       return TB200_ERR_CUDA;
     }
     configured = true;
   }
-  stage_mv2_kernel<SCHEME, LJ, WX, WY, DERIVE, UVOUT><<<grid, dim3(32 * WX * WY, 1, 1), smem, st>>>(a);
+  stage_mv2_kernel<SCHEME, LJ, WX, WY, DERIVE, UVOUT, TND><<<grid, dim3(32 * WX * WY, 1, 1), smem, st>>>(a);
   return check_launch("isentropic_stage_dry/MV(2 columns)");
 }
 template <int SCHEME, int LJ, int WX, int WY>
 int launch_mv2_flags(const StageArgs &a, dim3 grid, cudaStream_t st) {
+  if constexpr (WX == MV2_DEF_WX && WY == MV2_DEF_WY) {  // slow tendencies: the default block shape only (mv_geom)
+    if (a.su_tnd.ok()) {
+      if (a.derive_uv)
+        return a.skip_uv ? launch_mv2<SCHEME, LJ, WX, WY, true, false, true>(a, grid, st)
+                         : launch_mv2<SCHEME, LJ, WX, WY, true, true, true>(a, grid, st);
+      return a.skip_uv ? launch_mv2<SCHEME, LJ, WX, WY, false, false, true>(a, grid, st)
+                       : launch_mv2<SCHEME, LJ, WX, WY, false, true, true>(a, grid, st);
+    }
+  }
   if (a.derive_uv)
     return a.skip_uv ? launch_mv2<SCHEME, LJ, WX, WY, true, false>(a, grid, st)
                      : launch_mv2<SCHEME, LJ, WX, WY, true, true>(a, grid, st);
@@ -2020,6 +2036,16 @@ int a_impl() {  // TB200_A_IMPL=one|two (columns per lane; default one)
 template <int SCHEME, int LJ>
 int launch_a(const StageArgs &a, cudaStream_t st) {
   constexpr int WARPS = 4;
+  if (a.s_tnd.ok()) {  // slow tendency of s: the one-column kernel
+    const int chunks_t = (a.nx + A_COLS - 1) / A_COLS;
+    dim3 block_t(32 * WARPS, 1, 1);
+    dim3 grid_t((chunks_t + WARPS - 1) / WARPS, (a.ny + LJ - 1) / LJ, a.nz);
+    if (a.derive_uv)
+      stage_a_kernel<SCHEME, LJ, true, true><<<grid_t, block_t, 0, st>>>(a);
+    else
+      stage_a_kernel<SCHEME, LJ, false, true><<<grid_t, block_t, 0, st>>>(a);
+    return check_launch("isentropic_stage_dry/A(tendency)");
+  }
   if (a_impl() == 2 && a.a2_ok) {
     const int chunks2 = (a.nx + A2_COLS - 1) / A2_COLS;
     dim3 block2(32 * WARPS, 1, 1);
@@ -2057,7 +2083,7 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
   prof_mark(0, st);
   if (s_impl() != 0 && a.nz <= 64) {
     {
-      const int acols = (a_impl() == 2 && a.a2_ok) ? A2_COLS : A_COLS;
+      const int acols = (a_impl() == 2 && a.a2_ok && !a.s_tnd.ok()) ? A2_COLS : A_COLS;
       const int lj = pick_lj((a.nx + acols - 1) / acols, a.ny, a.nz);
       const int rc = lj == 16 ? launch_a<SCHEME, 16>(a, st)
                      : lj == 8 ? launch_a<SCHEME, 8>(a, st) : launch_a<SCHEME, 64>(a, st);
@@ -2170,6 +2196,7 @@ int stage_entry(
     const tb200_field *const *q_ref, void *stream) {
   TB200_REQUIRE(cfg != nullptr, "isentropic_stage_dry: NULL cfg");
   StageArgs a{};
+  a.s_tnd = view(cfg->s_tnd); a.su_tnd = view(cfg->su_tnd); a.sv_tnd = view(cfg->sv_tnd);
   a.ntr = 0;
   if (q_now != nullptr) {
     TB200_REQUIRE(q_int != nullptr && q_new != nullptr && q_ref != nullptr,
@@ -2272,6 +2299,22 @@ int stage_entry(
   TB200_REQUIRE(a.ntr == 0 || (a.part == 0 && s_impl() != 0 && a.nz <= 64),
                 "isentropic_stage_moist: needs the default kernel path (A + B), an unsplit stage and nz <= 64");
   a.a2_ok = mv2_ok(a) ? 1 : 0;
+  if (a.s_tnd.ok() || a.su_tnd.ok() || a.sv_tnd.ok()) {
+    // slow tendencies (rk3ws_si.py:L105-L234 passes s_tnd, su_tnd, sv_tnd to K1 / K2): all three or
+    // none, same geometry, dry stage, default kernel path
+    const View *ts[] = {&a.s_tnd, &a.su_tnd, &a.sv_tnd};
+    for (const View *v : ts) {
+      TB200_REQUIRE(covers(*v, nx, ny, nz), "isentropic_stage_dry: s_tnd, su_tnd, sv_tnd must be given together "
+                                            "and cover (nx, ny, nz)");
+      if (v->s0 != 1 || v->s1 != a.s_now.s1 || v->s2 != a.s_now.s2 ||
+          (reinterpret_cast<uintptr_t>(v->p) & 15) != 0) {
+        set_error("isentropic_stage_dry: the tendency fields must share the geometry of the other fields");
+        return TB200_ERR_LAYOUT;
+      }
+    }
+    TB200_REQUIRE(a.ntr == 0 && a.part == 0 && lazy_uv_path(a),
+                  "isentropic_stage_dry: slow tendencies need the dry stage, part 0 and the default kernel path");
+  }
   if (!lazy_uv_path(a)) {
     // the other kernel variants keep the reference's data flow (see lazy_uv_path)
     TB200_REQUIRE(a.spre.p != a.s_new.p,

@@ -12,6 +12,7 @@ struct StageArgs {
   View s_new, su_new, sv_new, u_new, v_new;
   View s_ref, su_ref, sv_ref, u_ref, v_ref;
   View gamma, rmat, hs, exn, mtg, spre;
+  View s_tnd, su_tnd, sv_tnd;  // slow tendencies (tb200_isentropic_stage.s_tnd ...), NULL = none
   // moist stage: mass fractions of the water constituents (qv, qc, qr), ntr = 0 when dry
   View q_now[3], q_int[3], q_new[3], q_ref[3];
   int ntr;

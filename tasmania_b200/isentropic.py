@@ -324,7 +324,12 @@ class IsentropicDynamicalCore(StencilFactory):
                     raise RuntimeError(
                         "Reference state not set in the object handling the horizontal boundary "
                         "conditions, but needed by the wave absorber.") from None
-        if self._fused and not tendencies:
+        slow = {n: v for n, v in (tendencies or {}).items() if n != "time"}
+        if self._fused and slow and self._tendencies_fusable(slow):
+            # slow tendencies of s, su, sv ride the fused stage (rk3ws_si.py:L105-L234 passes them to
+            # K1 / K2); a missing one is a field of zeros: x - 0.0 == x, the reference's own form
+            return self._stage_fused(stage, state, timestep, out_state, tendencies=slow)
+        if self._fused and not slow:
             if self.overlap is None:
                 return self._stage_fused(stage, state, timestep, out_state)
             # communication / computation overlap of a decomposed run: everything a neighbour
@@ -358,8 +363,15 @@ class IsentropicDynamicalCore(StencilFactory):
         hb.set_outermost_layers_x(out_state[U], field_name=U, time=out_state.get("time"))
         hb.set_outermost_layers_y(out_state[V], field_name=V, time=out_state.get("time"))
 
+    def _tendencies_fusable(self, slow):
+        return (not self._moist and self.overlap is None and set(slow) <= {S, SU, SV}
+                and all(isinstance(v, storage.B200Array) and tuple(v.shape) == self.storage_shape
+                        for v in slow.values())
+                and bool(lib.load().tb200_stage_lazy_velocities(self.grid.nz))
+                and os.environ.get("TB200_FUSED_TENDENCIES", "1") != "0")
+
     # ---- the fused stage: three kernels
-    def _stage_fused(self, stage, state, timestep, out_state, part=0, rim=(0, 0, 0, 0)):
+    def _stage_fused(self, stage, state, timestep, out_state, part=0, rim=(0, 0, 0, 0), tendencies=None):
         g, hb, pr = self.grid, self.horizontal_boundary, self._prognostic
         qn = (mfwv, mfcw, mfpw) if self._moist else ()
         if stage == 0:
@@ -392,6 +404,12 @@ class IsentropicDynamicalCore(StencilFactory):
         cfg.skip_uv_out = int(lazy)
         # ... and then nobody re-reads s before it is final: the stage updates it in place
         scratch_s = out_state[S] if (cfg.skip_uv_out and part == 0) else self._scratch[2]
+        keep_tnd = None
+        if tendencies:
+            if getattr(self, "_zero_tnd", None) is None:
+                self._zero_tnd = self.zeros(shape=self.storage_shape)
+            keep_tnd = [lib.as_field(tendencies.get(n, self._zero_tnd)) for n in (S, SU, SV)]
+            cfg.s_tnd, cfg.su_tnd, cfg.sv_tnd = (C.pointer(k) for k in keep_tnd)
         pr._diagnostics._set_topography()
         ref, now = hb.reference_state, pr._now
         f = lib.as_field

@@ -41,6 +41,7 @@ class StageCfg(C.Structure):
         ("constants", C.c_double * 4),
         ("part", C.c_int32), ("rim", C.c_int32 * 4),
         ("derive_uv_in", C.c_int32), ("skip_uv_out", C.c_int32),
+        ("s_tnd", FieldP), ("su_tnd", FieldP), ("sv_tnd", FieldP),
     ]
 
 

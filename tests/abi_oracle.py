@@ -231,8 +231,10 @@ class OracleStub(AbiStub):
             dwarfs.get_velocity_components(nx, ny, nz, arr(s_int), arr(su_int), arr(sv_int), u_i, v_i)
         assert arr(scr2) is not None  # may BE s_new (in-place update with skip_uv_out)
         assert c.skip_uv_out or arr(scr2).ctypes.data != out["s"].ctypes.data
+        s_tnd, su_tnd, sv_tnd = (arr(x) if x else None for x in (c.s_tnd, c.su_tnd, c.sv_tnd))
+        assert (s_tnd is None) == (su_tnd is None) == (sv_tnd is None)  # all three or none
         oi.step_forward_euler(flux, arr(s_now), arr(s_int), out["s"], u_i, v_i, dt=c.dt,
-                              dx=c.dx, dy=c.dy, origin=origin, domain=domain)
+                              dx=c.dx, dy=c.dy, origin=origin, domain=domain, s_tnd=s_tnd)
         ob.irelax(gamma, arr(s_ref), out["s"], (0, 0, 0), (nx, ny, nz))
         if after_s_step is not None:
             after_s_step(out["s"], u_i, v_i, gamma)
@@ -244,7 +246,7 @@ class OracleStub(AbiStub):
         oi.step_forward_euler_momentum(
             flux, arr(s_now), out["s"], u_i, v_i, arr(su_now), arr(su_int), out["su"], arr(sv_now),
             arr(sv_int), out["sv"], arr(mtg_now), mtg_new, dt=c.dt, dx=c.dx, dy=c.dy, eps=c.eps, origin=origin,
-            domain=domain)
+            domain=domain, su_tnd=su_tnd, sv_tnd=sv_tnd)
         for n, ref in (("s", s_ref), ("su", su_ref), ("sv", sv_ref)):  # enforce_raw (u, v are re-diagnosed)
             ob.irelax(gamma, arr(ref), out[n], (0, 0, 0), (nx, ny, nz))
         if c.damp:

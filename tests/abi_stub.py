@@ -87,8 +87,20 @@ def _freeze(name, argtypes, args):
             cfg = lib.StageCfg.from_buffer_copy(v.contents)
             keep.append(cfg)
             frozen.append(C.pointer(cfg))
-            desc.append(tuple(getattr(cfg, f) if not hasattr(getattr(cfg, f), "__len__")
-                              else tuple(getattr(cfg, f)) for f, _ in lib.StageCfg._fields_))
+            row = []
+            for f, ftype in lib.StageCfg._fields_:
+                val = getattr(cfg, f)
+                if ftype is lib.FieldP:  # optional fields of the block (slow tendencies): copy the struct
+                    if val:
+                        fld = lib.Field.from_buffer_copy(val.contents)
+                        keep.append(fld)
+                        setattr(cfg, f, C.pointer(fld))
+                        row.append((fld.ptr, tuple(fld.shape), tuple(fld.stride)))
+                    else:
+                        row.append(None)
+                else:
+                    row.append(tuple(val) if hasattr(val, "__len__") else val)
+            desc.append(tuple(row))
         elif t is C.POINTER(C.c_double):  # the four physical constants of the column scans
             vals = (C.c_double * 4)(*[v[m] for m in range(4)]) if v else None
             keep.append(vals)
