@@ -290,7 +290,8 @@ def _fused_stage(moist=False):
     (current-solution pointers of the dycore and of its prognostic object, topography upload,
     time label) and hands everything else to the library; it falls back to the original method
     -- the per-stencil b200 kernels -- whenever the configuration is outside the fused kernels'
-    scope: slow or fast tendencies, a boundary other than the 2-D ``Relaxed``, a prognostic scheme
+    scope: fast tendencies, slow tendencies other than those of s, su, sv (dry stage), a boundary
+    other than the 2-D ``Relaxed``, a prognostic scheme
     other than RK3WSSI / ForwardEulerSI, reference fields in non-canonical units, foreign storages.
 
     ``moist=True`` does the same for ``stage_array_call_moist`` (dycore.py:L723-L843) with
@@ -357,7 +358,14 @@ def _fused_stage(moist=False):
         return self._b200_fused_plan
 
     def stage_array_call(self, stage, state, tendencies, timestep, out_state):
-        if any(k != "time" for k in (tendencies or {})):
+        # slow tendencies of s, su, sv ride the fused DRY stage (tb200_isentropic_stage.s_tnd ...);
+        # anything else (moist stage, tendencies of the water constituents, foreign storages, an
+        # earlier kernel variant forced by the environment) takes the per-stencil kernels
+        slow = {k: v for k, v in (tendencies or {}).items() if k != "time"}
+        if slow and (moist or not set(slow) <= {S, SU, SV}
+                     or not all(isinstance(v, storage.B200Array) and tuple(v.shape) == tuple(state[S].shape)
+                                for v in slow.values())
+                     or not lib.load().tb200_stage_lazy_velocities(int(self.grid.nz))):
             return original(self, stage, state, tendencies, timestep, out_state)
         p = plan(self, tendencies)
         needed = (S, SU, SV, U, V, MTG) + (QN if moist else ())
@@ -391,6 +399,14 @@ def _fused_stage(moist=False):
         cfg.skip_uv_out = int(p["lazy"])  # the last stage's u, v: one tb200_velocity_components pass below
         scratch_s = out_state[S] if cfg.skip_uv_out else p["scratch"][2]
         f = lib.as_field
+        keep_tnd = None
+        if slow:  # a missing one is a field of zeros: x - 0.0 == x, the reference's own form
+            import ctypes as C
+
+            if "zero_tnd" not in p:
+                p["zero_tnd"] = storage.zeros(tuple(state[S].shape), device=_device(self.storage_options))
+            keep_tnd = [f(slow.get(n, p["zero_tnd"])) for n in (S, SU, SV)]
+            cfg.s_tnd, cfg.su_tnd, cfg.sv_tnd = (C.pointer(k) for k in keep_tnd)
         rmat = self._damper._rmat if self._damp else None
         args = (cfg, f(pr._s_now), f(pr._su_now), f(pr._sv_now), f(pr._mtg_now),
                 f(state[S]), f(state[SU]), f(state[SV]), f(state[U]), f(state[V]),

@@ -63,7 +63,7 @@ OUTNAMES = (S, SU, U, SV, V)
 QNAMES = (gg.MFWV, gg.MFCW, gg.MFPW)
 
 
-def reference_trace(stub, moist, fx, fused=False):
+def reference_trace(stub, moist, fx, fused=False, tendencies=None):
     """One RK3WS step of the reference's own dycore stage on backend b200; returns the ABI trace,
     the initial state as numpy arrays, the model-top pressure and the first-stage outputs (with
     ``fused``: through the plugin's fused-stage hook; the outputs of every stage)."""
@@ -149,7 +149,8 @@ def reference_trace(stub, moist, fx, fused=False):
     stub.trace = []
     st_in = cur
     for stage in range(prognostic.stages):  # stage chaining of framework/dycore.py:L455-L458
-        stage_call(me, stage, st_in, {}, DT, outs[stage])
+        tnd = {k: ta.as_storage("b200", data=v) for k, v in (tendencies or {}).items()}
+        stage_call(me, stage, st_in, tnd, DT, outs[stage])
         st_in = dict(outs[stage])
         st_in.setdefault(MTG, cur[MTG])
     trace, stub.trace = stub.trace, None
@@ -301,4 +302,31 @@ finally:
 for name in OUTNAMES + QNAMES:
     assert np.array_equal(fused_outs[2][name], plain_outs[2][name]), name
 assert fused_times == plain_times
-print("REF-DYCORE-OK", *done, "FUSED-HOOK-OK", "FUSED-MOIST-HOOK-OK")
+# ---- slow tendencies of su, sv (a subset: s gets a field of zeros) through the fused DRY hook: one
+# tb200_isentropic_stage_dry per stage carrying the three tendency pointers, same final fields as the
+# per-stencil reference run with the same tendencies
+fixture = set_case(False)
+rng = np.random.default_rng(17)
+slow = {SU: 1e-2 * rng.standard_normal(SHAPE), SV: 1e-2 * rng.standard_normal(SHAPE)}
+with stubbed_library(OracleStub) as the_stub:
+    fused_trace, fused_outs, _ = reference_trace(the_stub, False, fixture, fused=True, tendencies=slow)
+names = [n for n, _ in fused_trace]
+assert names.count("tb200_isentropic_stage_dry") == 3 and "tb200_step_forward_euler" not in names, \
+    collections.Counter(names)
+fields = [f for f, _ in tb.lib.StageCfg._fields_]
+for n, d in fused_trace:
+    if n == "tb200_isentropic_stage_dry":
+        cfg = dict(zip(fields, d[0]))
+        assert cfg["s_tnd"] is not None and cfg["su_tnd"] is not None and cfg["sv_tnd"] is not None
+patched = dyc_mod.IsentropicDynamicalCore.stage_array_call_dry
+dyc_mod.IsentropicDynamicalCore.stage_array_call_dry = patched.__wrapped_original__
+try:
+    with stubbed_library(OracleStub) as the_stub:
+        plain_trace, plain_outs, _ = reference_trace(the_stub, False, fixture, fused=True, tendencies=slow)
+finally:
+    dyc_mod.IsentropicDynamicalCore.stage_array_call_dry = patched
+assert "tb200_step_forward_euler" in [n for n, _ in plain_trace]
+for name in OUTNAMES:
+    assert np.array_equal(fused_outs[2][name], plain_outs[2][name]), name
+assert not np.array_equal(fused_outs[2][SU][3:-4, 3:-4, :-1], fixture["stage0_" + SU][3:-4, 3:-4, :-1])
+print("REF-DYCORE-OK", *done, "FUSED-HOOK-OK", "FUSED-MOIST-HOOK-OK", "FUSED-TENDENCIES-HOOK-OK")

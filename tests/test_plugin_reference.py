@@ -30,6 +30,7 @@ def test_reference_dycore_on_b200_issues_the_mirror_call_sequence():
     assert "REF-DYCORE-OK 42 69" in res.stdout  # dry and moist stage sequences
     assert "FUSED-HOOK-OK" in res.stdout        # the fused stage behind the reference's class
     assert "FUSED-MOIST-HOOK-OK" in res.stdout  # ... and the fused moist stage (stage_array_call_moist)
+    assert "FUSED-TENDENCIES-HOOK-OK" in res.stdout  # ... and slow tendencies through the fused dry stage
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
