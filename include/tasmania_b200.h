@@ -82,6 +82,17 @@ int tb200_device_count(void);
  * bench.py reports the difference over its timed region as `gpu_launches`) */
 long long tb200_launch_count(void);
 
+/* ---- scratch memory behind an explicit handle ------------------
+ * The library never owns field memory.  What the fused kernels need beyond the fields (the hand-off
+ * arrays of tb200_isentropic_stage_dry / _moist: scratch_exn, scratch_mtg, scratch_s) is requested
+ * from a context held by the host-side backend object: tb200_ctx_scratch returns `count` zero-filled
+ * fields of logical shape `shape` in the b200 storage layout (unit i-stride, rows padded to 16
+ * doubles), the same ones on every call with that shape, valid until tb200_ctx_destroy. */
+typedef struct tb200_ctx tb200_ctx;
+int tb200_ctx_create(tb200_ctx **ctx);
+int tb200_ctx_destroy(tb200_ctx *ctx);
+int tb200_ctx_scratch(tb200_ctx *ctx, const int64_t shape[3], int count, tb200_field *fields);
+
 /* ---- K12 element-wise ------------------------------------------------------------- */
 int tb200_elementwise(int op, tb200_field *out, const tb200_field *a, const tb200_field *b,
                       const tb200_field *c, double f, const int32_t origin[3],

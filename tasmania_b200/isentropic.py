@@ -292,6 +292,8 @@ class IsentropicDynamicalCore(StencilFactory):
         self._s_now = self._su_now = self._sv_now = None
         self._ref = None
         self._scratch = None
+        if self._fused:
+            self._allocate_scratch()  # now, not lazily: a raw device allocation must not fall into a graph capture
         # hook run after every stage on that stage's output fields (halo exchange of a
         # decomposed run); None on a single device
         self.after_stage = None
@@ -363,6 +365,19 @@ class IsentropicDynamicalCore(StencilFactory):
         hb.set_outermost_layers_x(out_state[U], field_name=U, time=out_state.get("time"))
         hb.set_outermost_layers_y(out_state[V], field_name=V, time=out_state.get("time"))
 
+    def _allocate_scratch(self):
+        """The hand-off arrays of the fused stage (parked pressures, new Montgomery potential, s after
+        its first relaxation) live in a library context held by this object (``tb200_ctx``, SURVEY.md
+        section 8b): allocated once, freed with the dycore.  Host storages (the CPU test double of the
+        library) keep plain storages."""
+        dev = self.storage_options.device
+        on_device = dev is None or "cuda" in str(dev)
+        if on_device and storage.DEFAULT_DEVICE_OVERRIDE is None and os.environ.get("TB200_CTX_SCRATCH", "1") != "0":
+            self._ctx = lib.Context()
+            self._scratch = self._ctx.scratch(self.storage_shape, 3)
+        else:
+            self._scratch = tuple(self.zeros(shape=self.storage_shape) for _ in range(3))
+
     def _tendencies_fusable(self, slow):
         return (not self._moist and self.overlap is None and set(slow) <= {S, SU, SV}
                 and all(isinstance(v, storage.B200Array) and tuple(v.shape) == self.storage_shape
@@ -377,7 +392,7 @@ class IsentropicDynamicalCore(StencilFactory):
         if stage == 0:
             pr._now = {n: state[n] for n in (S, MTG, SU, SV) + qn}
         if self._scratch is None:
-            self._scratch = tuple(self.zeros(shape=self.storage_shape) for _ in range(3))
+            self._allocate_scratch()
         dtr, dt = pr.substep(stage, timestep)
         cfg = lib.StageCfg()
         cfg.nx, cfg.ny, cfg.nz, cfg.nb = g.nx, g.ny, g.nz, hb.nb

@@ -125,6 +125,9 @@ SIGNATURES = {
     "tb200_p2p_release": [_V],
     "tb200_p2p_channel_error": [_V, C.POINTER(C.c_int)],
     "tb200_selftest_division": [C.c_uint64, C.c_uint64, _V, _V],
+    "tb200_ctx_create": [C.POINTER(C.c_void_p)],
+    "tb200_ctx_destroy": [_V],
+    "tb200_ctx_scratch": [_V, C.POINTER(C.c_int64), _I, FieldP],
 }
 
 KESSLER_FLAGS = {"p_on_interfaces": 1, "rain_evaporation": 2, "ow_qc": 4, "ow_qr": 8, "ow_qv": 16,
@@ -215,6 +218,46 @@ def as_field(x) -> Optional[Field]:
     f.shape[:] = shape
     f.stride[:] = strides
     return f
+
+
+class ScratchField:
+    """A library-owned scratch field (``tb200_ctx_scratch``) as a device array the marshalling code
+    accepts: ``__cuda_array_interface__`` only -- scratch is never read on the host."""
+
+    def __init__(self, field: Field, owner):
+        self.shape = tuple(int(n) for n in field.shape)
+        self._strides = tuple(int(s) * 8 for s in field.stride)
+        self._ptr = int(field.ptr)
+        self._owner = owner  # keeps the context alive
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "<f8", "data": (self._ptr, False), "version": 3,
+                "strides": self._strides}
+
+
+class Context:
+    """``tb200_ctx``: owner of the fused kernels' scratch memory, held by the host-side object that
+    issues the fused calls; freed with the object."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        check(load().tb200_ctx_create(C.byref(h)), "tb200_ctx_create")
+        self._h = h
+
+    def scratch(self, shape, count):
+        fields = (Field * count)()
+        check(load().tb200_ctx_scratch(self._h, (C.c_int64 * 3)(*[int(n) for n in shape]), count, fields),
+              "tb200_ctx_scratch")
+        return tuple(ScratchField(fields[n], self) for n in range(count))
+
+    def __del__(self):
+        try:
+            if self._h:
+                load().tb200_ctx_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
 
 def fp(x) -> Optional[FieldP]:
