@@ -421,6 +421,15 @@ typedef struct tb200_isentropic_stage {
    * rk3ws_si.py:L105-L234 passes them): all three or none (NULL).  Same geometry as the other
    * fields; dry stage, part 0 and the default kernel path only. */
   const tb200_field *s_tnd, *su_tnd, *sv_tnd;
+  /* Periodic lateral boundary (domain/subclasses/horizontal_boundaries/periodic.py:L98-L122): with
+   * periodic != 0, (nx, ny) is the numerical grid of a physical (nx - 2 nb, ny - 2 nb) one, gamma is
+   * a field of zeros, and the stage wraps s into its nb ghost layers between the s-step and the
+   * column scans -- the `hb.enforce_field(s_new)` of rk3ws_si.py:L184-L189, which with a relaxed
+   * boundary is the first relaxation.  Ghost points of su_new / sv_new keep their previous contents:
+   * the caller runs the stage with damp = 0 and applies `hb.enforce_raw` (tb200_periodic_enforce) and
+   * the damping afterwards, in the reference's order (dycore.py:L684-L700).  Dry stage, part 0,
+   * default kernel path, nx, ny >= 4 nb. */
+  int32_t periodic;
 } tb200_isentropic_stage;
 
 int tb200_isentropic_stage_dry(

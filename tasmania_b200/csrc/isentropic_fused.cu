@@ -2094,6 +2094,15 @@ int run_stage(const StageArgs &a, cudaStream_t st) {
       const int rc = launch_tracers<SCHEME>(a, st);
       if (rc) return rc;
     }
+    if (a.periodic) {  // hb.enforce_field(s_new), rk3ws_si.py:L184-L189, for periodic.py:L98-L122
+      tb200_field f;
+      f.ptr = a.spre.p;
+      f.shape[0] = a.spre.n0; f.shape[1] = a.spre.n1; f.shape[2] = a.nz;
+      f.stride[0] = a.spre.s0; f.stride[1] = a.spre.s1; f.stride[2] = a.spre.s2;
+      const int px = a.nx - 2 * a.nb, py = a.ny - 2 * a.nb;
+      const int rc = tb200_periodic_enforce(&f, px, py, a.nb, px, py, st);
+      if (rc) return rc;
+    }
     if (b_coop(a)) {
       dim3 block(32, 8, 1);
       dim3 grid((a.nx + 31) / 32, a.ny, 1);
@@ -2299,6 +2308,11 @@ int stage_entry(
   TB200_REQUIRE(a.ntr == 0 || (a.part == 0 && s_impl() != 0 && a.nz <= 64),
                 "isentropic_stage_moist: needs the default kernel path (A + B), an unsplit stage and nz <= 64");
   a.a2_ok = mv2_ok(a) ? 1 : 0;
+  a.periodic = cfg->periodic != 0;
+  TB200_REQUIRE(!a.periodic || (a.ntr == 0 && a.part == 0 && lazy_uv_path(a) && cfg->skip_uv_out != 0 &&
+                                !a.damp && nx >= 4 * a.nb && ny >= 4 * a.nb),
+                "isentropic_stage_dry: a periodic stage needs the dry stage, part 0, the default kernel path, "
+                "skip_uv_out, damp = 0 and nx, ny >= 4 nb");
   if (a.s_tnd.ok() || a.su_tnd.ok() || a.sv_tnd.ok()) {
     // slow tendencies (rk3ws_si.py:L105-L234 passes s_tnd, su_tnd, sv_tnd to K1 / K2): all three or
     // none, same geometry, dry stage, default kernel path

@@ -21,6 +21,7 @@ struct StageArgs {
   int part, rim[4];  // tb200_isentropic_stage.part / .rim
   int derive_uv, skip_uv;  // tb200_isentropic_stage.derive_uv_in / .skip_uv_out
   int a2_ok;               // the layout allows the two-column kernels (16-byte aligned pairs)
+  int periodic;            // tb200_isentropic_stage.periodic: wrap s_pre between the s-step and the scans
   double dt, dt_full, dx, dy, dz, eps, pt, theta_s, pref, rd, g, cp;
   FluxConst fc;
   CDiv two_dx, two_dy, cpref;

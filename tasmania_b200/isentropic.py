@@ -267,17 +267,24 @@ class IsentropicDynamicalCore(StencilFactory):
                 storage_options=self.storage_options)
             z = lambda: self.zeros(shape=self.storage_shape)  # noqa: E731
             self._sq = {(t, n): z() for t in ("now", "int", "new") for n in (SQV, SQC, SQR)}
-        from tasmania_b200.boundary import Relaxed
+        from tasmania_b200.boundary import Periodic, Relaxed
 
         # the 2-D class only: Relaxed1DX / 1DY also report type "relaxed", but their gamma is
         # non-zero on the middle line alone and they repeat that line across the degenerate axis,
         # which the fused kernels do not do
         fusable = type(horizontal_boundary) is Relaxed
+        # ... and the 2-D Periodic class for the dry core: same kernels with gamma = 0, the wrap of s
+        # between the s-step and the scans inside the stage call, enforce_raw and damping after it
+        self._periodic = (type(horizontal_boundary) is Periodic and not moist
+                          and os.environ.get("TB200_FUSED_PERIODIC", "1") != "0"
+                          and bool(lib.load().tb200_stage_lazy_velocities(grid.nz)))
+        fusable = fusable or self._periodic
         if moist:  # the tracer kernel rides the default kernel path only (csrc/isentropic_fused.cu: kernel T)
             fusable = (fusable and os.environ.get("TB200_MOIST_FUSED", "1") != "0"
                        and bool(lib.load().tb200_stage_lazy_velocities(grid.nz)))
         if fused and not fusable:
-            raise ValueError("the fused stage covers the core with (2-D) relaxed boundaries only")
+            raise ValueError("the fused stage covers the core with (2-D) relaxed boundaries, and the dry core "
+                             "with (2-D) periodic ones, only")
         self._fused = fusable if fused is None else bool(fused)
         # fused path only: intermediate RK stages neither write nor read u, v (see _stage_fused);
         # set to False to get every stage's velocities like the reference's stage_array_call
@@ -378,6 +385,11 @@ class IsentropicDynamicalCore(StencilFactory):
         else:
             self._scratch = tuple(self.zeros(shape=self.storage_shape) for _ in range(3))
 
+    def _periodic_gamma(self):
+        if getattr(self, "_zero_gamma2d", None) is None:
+            self._zero_gamma2d = self.zeros(shape=self.storage_shape[:2] + (1,))
+        return self._zero_gamma2d
+
     def _tendencies_fusable(self, slow):
         return (not self._moist and self.overlap is None and set(slow) <= {S, SU, SV}
                 and all(isinstance(v, storage.B200Array) and tuple(v.shape) == self.storage_shape
@@ -397,7 +409,12 @@ class IsentropicDynamicalCore(StencilFactory):
         cfg = lib.StageCfg()
         cfg.nx, cfg.ny, cfg.nz, cfg.nb = g.nx, g.ny, g.nz, hb.nb
         cfg.flux_scheme = pr._hflux.code
-        cfg.damp = int(self._damp and (self._damp_at_every_stage or stage == self.stages - 1))
+        damp = self._damp and (self._damp_at_every_stage or stage == self.stages - 1)
+        periodic = self._periodic
+        # periodic: the wrap of su, sv (enforce_raw) comes between the momentum step and the damping
+        # (dycore.py:L684-L700), so the damping cannot ride the momentum kernel
+        cfg.damp = int(damp and not periodic)
+        cfg.periodic = int(periodic)
         cfg.dt, cfg.dt_full = dt.total_seconds(), timestep.total_seconds()
         cfg.dx, cfg.dy, cfg.dz, cfg.eps = g.dx, g.dy, g.dz, pr._eps
         cfg.pt, cfg.theta_s = pr._pt, float(g.z_on_interface_levels[-1])
@@ -416,7 +433,8 @@ class IsentropicDynamicalCore(StencilFactory):
         lazy = self.lazy_velocities
         last = stage == self.stages - 1
         cfg.derive_uv_in = int(lazy and (stage > 0 or self.derive_stage0_velocities))
-        cfg.skip_uv_out = int(lazy)
+        # (a periodic stage never writes them: the wrap and the damping that follow the call come first)
+        cfg.skip_uv_out = int(lazy or periodic)
         # ... and then nobody re-reads s before it is final: the stage updates it in place
         scratch_s = out_state[S] if (cfg.skip_uv_out and part == 0) else self._scratch[2]
         keep_tnd = None
@@ -427,13 +445,16 @@ class IsentropicDynamicalCore(StencilFactory):
             cfg.s_tnd, cfg.su_tnd, cfg.sv_tnd = (C.pointer(k) for k in keep_tnd)
         pr._diagnostics._set_topography()
         ref, now = hb.reference_state, pr._now
+        gamma2d = hb._gamma2d if not periodic else self._periodic_gamma()
+        if periodic:  # no relaxation, no in-kernel damping, no velocity output: never read
+            ref = {n: ref.get(n, state[n]) for n in (S, SU, SV, U, V)}
         f = lib.as_field
         rmat = self._damper._rmat if self._damp else None
         args = (cfg, f(now[S]), f(now[SU]), f(now[SV]), f(now[MTG]),
                 f(state[S]), f(state[SU]), f(state[SV]), f(state[U]), f(state[V]),
                 f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
                 f(ref[S]), f(ref[SU]), f(ref[SV]), f(ref[U]), f(ref[V]),
-                f(hb._gamma2d), f(rmat), f(pr._diagnostics._topo2d),
+                f(gamma2d), f(rmat), f(pr._diagnostics._topo2d),
                 f(self._scratch[0]), f(self._scratch[1]), f(scratch_s))
         if self._moist:
             # the three water constituents ride along (kernel T): mass fractions in, mass fractions out
@@ -447,14 +468,29 @@ class IsentropicDynamicalCore(StencilFactory):
             lib.check(rc, "tb200_isentropic_stage_dry")
         if "time" in state and part != 1:
             out_state["time"] = state["time"] + dtr
+        if periodic:  # dycore.py:L684-L700 in the reference's order
+            hb.enforce_raw({n: out_state[n] for n in (S, SU, SV)} | {"time": out_state.get("time")})
+            if damp:
+                self._damper(timestep, self._s_now, out_state[S], self._ref[S], out_state[S])
+                self._damper(timestep, self._su_now, out_state[SU], self._ref[SU], out_state[SU])
+                self._damper(timestep, self._sv_now, out_state[SV], self._ref[SV], out_state[SV])
         # a decomposed run diagnoses the velocities itself, after the halo exchange of s, su, sv
         if lazy and last and part != 1 and self.after_stage is None and self.overlap is None:
+            self.diagnose_velocities(out_state)
+        elif periodic and not lazy:  # every stage's velocities, like the reference's stage_array_call
             self.diagnose_velocities(out_state)
 
     def diagnose_velocities(self, out_state):
         """u, v of a finished state from its s, su, sv, outermost faces from the reference state
         (dwarfs/diagnostics.py:L219-L272 + relaxed.py:L161-L191) in one launch."""
         g, ref = self.grid, self.horizontal_boundary.reference_state
+        if self._periodic:  # outermost faces by the wrap (periodic.py:L116-L122), not from a reference state
+            hb = self.horizontal_boundary
+            self._velocity_components.get_velocity_components(out_state[S], out_state[SU], out_state[SV],
+                                                              out_state[U], out_state[V])
+            hb.set_outermost_layers_x(out_state[U], field_name=U, time=out_state.get("time"))
+            hb.set_outermost_layers_y(out_state[V], field_name=V, time=out_state.get("time"))
+            return
         f = lib.as_field
         rc = lib.load().tb200_velocity_components(
             f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),

@@ -42,6 +42,7 @@ class StageCfg(C.Structure):
         ("part", C.c_int32), ("rim", C.c_int32 * 4),
         ("derive_uv_in", C.c_int32), ("skip_uv_out", C.c_int32),
         ("s_tnd", FieldP), ("su_tnd", FieldP), ("sv_tnd", FieldP),
+        ("periodic", C.c_int32),
     ]
 
 

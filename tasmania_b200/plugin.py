@@ -291,7 +291,7 @@ def _fused_stage(moist=False):
     time label) and hands everything else to the library; it falls back to the original method
     -- the per-stencil b200 kernels -- whenever the configuration is outside the fused kernels'
     scope: fast tendencies, slow tendencies other than those of s, su, sv (dry stage), a boundary
-    other than the 2-D ``Relaxed``, a prognostic scheme
+    other than the 2-D ``Relaxed`` (or, for the dry stage, the 2-D ``Periodic``), a prognostic scheme
     other than RK3WSSI / ForwardEulerSI, reference fields in non-canonical units, foreign storages.
 
     ``moist=True`` does the same for ``stage_array_call_moist`` (dycore.py:L723-L843) with
@@ -330,7 +330,8 @@ def _fused_stage(moist=False):
             return cached or None
         ok = getattr(self, "backend", None) == BACKEND and bool(getattr(self, "_moist", not moist)) == moist
         hb, pr = self.horizontal_boundary, self._prognostic
-        ok = ok and type(hb).__name__ == "Relaxed" and getattr(type(pr), "name", None) in SUBSTEPS
+        periodic = type(hb).__name__ == "Periodic" and not moist  # the dry stage wraps s itself (cfg.periodic)
+        ok = ok and (type(hb).__name__ == "Relaxed" or periodic) and getattr(type(pr), "name", None) in SUBSTEPS
         scheme = getattr(getattr(pr, "_hflux", None), "name", None)
         ok = ok and scheme in lib.FLUX_SCHEMES and hasattr(pr, "_diagnostics")
         if ok:
@@ -354,7 +355,13 @@ def _fused_stage(moist=False):
             "scratch": [storage.zeros(shape, device=_device(self.storage_options)) for _ in range(3)],
             "lazy": (self.fast_tendency_component is None and self.fast_diagnostic_component is None
                      and bool(lib.load().tb200_stage_lazy_velocities(int(g.nz)))),
+            "periodic": periodic,
         }
+        if periodic:
+            if not lib.load().tb200_stage_lazy_velocities(int(g.nz)):  # an earlier kernel variant forced by the environment
+                self._b200_fused_plan = False
+                return None
+            self._b200_fused_plan["gamma"] = storage.zeros(shape[:2] + (1,), device=_device(self.storage_options))
         return self._b200_fused_plan
 
     def stage_array_call(self, stage, state, tendencies, timestep, out_state):
@@ -397,6 +404,9 @@ def _fused_stage(moist=False):
         cfg.rim[:] = [0, 0, 0, 0]
         cfg.derive_uv_in = int(p["lazy"] and stage > 0)
         cfg.skip_uv_out = int(p["lazy"])  # the last stage's u, v: one tb200_velocity_components pass below
+        periodic = p["periodic"]
+        if periodic:  # the wrap of s, su, sv comes between the momentum step and the damping (dycore.py:L684-L700)
+            cfg.periodic, cfg.damp, cfg.skip_uv_out = 1, 0, 1
         scratch_s = out_state[S] if cfg.skip_uv_out else p["scratch"][2]
         f = lib.as_field
         keep_tnd = None
@@ -412,7 +422,7 @@ def _fused_stage(moist=False):
                 f(state[S]), f(state[SU]), f(state[SV]), f(state[U]), f(state[V]),
                 f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
                 f(ref[S].data), f(ref[SU].data), f(ref[SV].data), f(ref[U].data), f(ref[V].data),
-                f(hb._gamma), f(rmat), f(diag._topo[:, :, nz:nz + 1]),
+                f(p["gamma"] if periodic else hb._gamma), f(rmat), f(diag._topo[:, :, nz:nz + 1]),
                 f(p["scratch"][0]), f(p["scratch"][1]), f(scratch_s))
         if moist:
             import ctypes as C
@@ -426,7 +436,20 @@ def _fused_stage(moist=False):
         else:
             rc = lib.load().tb200_isentropic_stage_dry(*args, lib.current_stream())
             lib.check(rc, "tb200_isentropic_stage_dry")
-        if p["lazy"] and stage == self.stages - 1:
+        if periodic:
+            for n in (S, SU, SV):  # hb.enforce_raw: periodic.py:L98-L122
+                lib.check(lib.load().tb200_periodic_enforce(f(out_state[n]), hb.nx, hb.ny, hb.nb, hb.nx, hb.ny,
+                                                            lib.current_stream()), "tb200_periodic_enforce")
+            if damp:  # dycore.py:L694-L700
+                self._damper(timestep, self._s_now, out_state[S], ref[S].data, out_state[S])
+                self._damper(timestep, self._su_now, out_state[SU], ref[SU].data, out_state[SU])
+                self._damper(timestep, self._sv_now, out_state[SV], ref[SV].data, out_state[SV])
+            if not p["lazy"] or stage == self.stages - 1:  # dycore.py:L702-L721
+                self._velocity_components.get_velocity_components(
+                    out_state[S], out_state[SU], out_state[SV], out_state[U], out_state[V])
+                hb.set_outermost_layers_x(out_state[U], field_name=U)
+                hb.set_outermost_layers_y(out_state[V], field_name=V)
+        elif p["lazy"] and stage == self.stages - 1:
             rc = lib.load().tb200_velocity_components(
                 f(out_state[S]), f(out_state[SU]), f(out_state[SV]), f(out_state[U]), f(out_state[V]),
                 f(ref[U].data), f(ref[V].data), nx, ny, nz, lib.current_stream())

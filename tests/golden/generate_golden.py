@@ -651,15 +651,18 @@ def _make_domain(nx, ny, nz, hb_type, nb, hb_kwargs, topo_time=1800.0, xlim=(-17
 
 
 def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, damp_depth=4,
-                       damp_every=True, topo_time=60.0, moist=False):
+                       damp_every=True, topo_time=60.0, moist=False, hb_type="relaxed"):
     """Dry isentropic dycore driven through the reference's OWN classes: real Domain /
     Relaxed / RK3WSSI|ForwardEulerSI / IsentropicDiagnostics / Rayleigh / HorizontalVelocity
     and the real ``IsentropicDynamicalCore.stage_array_call_dry``, chained as
     framework/dycore.py:L455-L458 does; after each step the real
     ``get_diagnostic_variables`` refreshes p, exn, mtg, h."""
-    d = _make_domain(nx, ny, nz, "relaxed", nb, {"nr": nr}, topo_time=topo_time)
+    d = _make_domain(nx, ny, nz, hb_type, nb, {"nr": nr} if hb_type == "relaxed" else {}, topo_time=topo_time)
     g = d.numerical_grid
     st = refload.load("tasmania.isentropic.state")
+    # hb_type == "periodic": (nx, ny) is the PHYSICAL grid, everything below lives on the numerical
+    # one, nb ghost points a side (periodic.py:L44-L50); the fixture stores the numerical sizes
+    nx, ny = g.nx, g.ny
     shape = (nx + 1, ny + 1, nz + 1)
     state = st.get_isentropic_state_from_brunt_vaisala_frequency(
         g, datetime(2000, 1, 1), da(22.5, "m s^-1"), da(0.0, "m s^-1"), da(0.015, "s^-1"),
@@ -770,8 +773,8 @@ def gen_isentropic_dry(name, nx, ny, nz, scheme, flux, nb, nr, nsteps, dt_s, dam
         z=g.z.values, z_hl=g.z_on_interface_levels.values,
         x=g.x.to_units("m").values, y=g.y.to_units("m").values,
         topo_steady=g.topography.steady_profile.values,
-        gamma=np.array(hb._gamma), rmat=np.array(damper._rmat),
-        scheme=np.array([scheme, flux]),
+        gamma=np.array(hb._gamma) if hb_type == "relaxed" else np.zeros(1), rmat=np.array(damper._rmat),
+        scheme=np.array([scheme, flux]), boundary=np.array([hb_type]),
         **init, **first_stage, **final,
     )
 
@@ -790,6 +793,12 @@ CASES = {
         "isen_dry_fe_upw", 16, 18, 5, "forward_euler_si", "upwind", 1, 3, 4, 3.0),
     "isen_moist_rk3_5th": lambda: gen_isentropic_dry(
         "isen_moist_rk3_5th", 23, 19, 8, "rk3ws_si", "fifth_order_upwind", 3, 6, 4, 5.0, moist=True),
+    "isen_dry_rk3_5th_periodic": lambda: gen_isentropic_dry(
+        "isen_dry_rk3_5th_periodic", 19, 15, 7, "rk3ws_si", "fifth_order_upwind", 3, 0, 5, 5.0,
+        damp_depth=3, topo_time=20.0, hb_type="periodic"),
+    "isen_dry_rk3_3rd_periodic": lambda: gen_isentropic_dry(
+        "isen_dry_rk3_3rd_periodic", 14, 17, 5, "rk3ws_si", "third_order_upwind", 2, 0, 4, 5.0,
+        damp_every=False, topo_time=15.0, hb_type="periodic"),
     "isen_moist_fe_3rd": lambda: gen_isentropic_dry(
         "isen_moist_fe_3rd", 17, 21, 6, "forward_euler_si", "third_order_upwind", 2, 5, 3, 4.0,
         moist=True),

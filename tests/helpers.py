@@ -51,7 +51,9 @@ def oracle_dry_run(fx, nsteps=None):
     dx, dy, dz, pt, dt_s, eps, damp_max, topo_time = (float(v) for v in fx["params"])
     scheme, flux = (str(v) for v in fx["scheme"])
     grid = oi.Grid(nx, ny, nz, dx, dy, dz, fx["z_hl"], fx["z"])
-    hb = ob.Relaxed(nx, ny, nz, nb, nr)
+    # periodic fixtures store the sizes of the numerical grid (physical + nb ghost points a side)
+    periodic = "boundary" in fx.files and str(fx["boundary"][0]) == "periodic"
+    hb = ob.Periodic(nx - 2 * nb, ny - 2 * nb, nz, nb) if periodic else ob.Relaxed(nx, ny, nz, nb, nr)
     moist = ("init_" + oi.MFWV) in fx.files
     qnames = (oi.MFWV, oi.MFCW, oi.MFPW) if moist else ()
     names = (S, MTG, SU, U, SV, V, P, EXN, H) + qnames

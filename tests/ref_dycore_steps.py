@@ -47,7 +47,7 @@ QNAMES = ("mass_fraction_of_water_vapor_in_air", "mass_fraction_of_cloud_liquid_
           "mass_fraction_of_precipitation_water_in_air")
 
 
-def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20, moist=False):
+def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20, moist=False, boundary="relaxed"):
     """``nsteps`` RK3WS + fifth-order-upwind steps of the mountain-flow case on ``backend``;
     returns the final state as numpy arrays.  ``clock`` (a dict with a "budget" in seconds): the
     step loop is timed (set-up excluded) and stops once the budget is spent -- how ``bench.py
@@ -56,19 +56,24 @@ def run(backend, nsteps, nx, ny, nz, clock=None, damp_depth=4, topo_seconds=20, 
     from tasmania.framework.generic_functions import to_numpy
 
     DataArray, da = refload.DataArray, gg.da
-    shape = (nx + 1, ny + 1, nz + 1)
     dom = refload.load("tasmania.domain.domain")
     refload.load("tasmania.domain.subclasses.horizontal_boundaries.relaxed")
+    refload.load("tasmania.domain.subclasses.horizontal_boundaries.periodic")
     refload.load("tasmania.domain.subclasses.topographies.gaussian")
     domain = dom.Domain(
         DataArray([-176, 176], dims="x", attrs={"units": "km"}), nx,
         DataArray([-176, 176], dims="y", attrs={"units": "km"}), ny,
         DataArray([400, 280], dims="z", attrs={"units": "K"}), nz,
-        horizontal_boundary_type="relaxed", nb=NB, horizontal_boundary_kwargs={"nr": NR},
+        horizontal_boundary_type=boundary, nb=NB,
+        horizontal_boundary_kwargs={"nr": NR} if boundary == "relaxed" else {},
         backend=backend, topography_type="gaussian",
         topography_kwargs={"time": timedelta(seconds=topo_seconds), "max_height": da(0.5, "km"),
                            "width_x": da(50.0, "km"), "width_y": da(50.0, "km"), "smooth": False})
     grid = domain.numerical_grid
+    # ``boundary="periodic"``: (nx, ny) is the physical grid, the fields live on the numerical one
+    # (NB ghost points a side, periodic.py:L44-L50)
+    nx, ny = grid.nx, grid.ny
+    shape = (nx + 1, ny + 1, nz + 1)
     st = refload.load("tasmania.isentropic.state")
     state = st.get_isentropic_state_from_brunt_vaisala_frequency(
         grid, datetime(2000, 1, 1), da(22.5, "m s^-1"), da(0.0, "m s^-1"), da(0.015, "s^-1"),
@@ -157,6 +162,7 @@ def main():
     ap.add_argument("--stub", action="store_true")
     ap.add_argument("--per-stencil", action="store_true")
     ap.add_argument("--moist", action="store_true", help="the moist dycore stage (stage_array_call_moist)")
+    ap.add_argument("--periodic", action="store_true", help="the reference's Periodic boundary instead of Relaxed")
     ap.add_argument("--nx", type=int, default=41)
     ap.add_argument("--ny", type=int, default=37)
     ap.add_argument("--nz", type=int, default=12)
@@ -169,7 +175,8 @@ def main():
     assert args.per_stencil or "IsentropicDynamicalCore.stage_array_call_dry" in report.get("fused", []), report
     if args.moist and not args.per_stencil:
         assert "IsentropicDynamicalCore.stage_array_call_moist" in report.get("fused", []), report
-    want = run("numpy", args.steps, args.nx, args.ny, args.nz, moist=args.moist)
+    boundary = "periodic" if args.periodic else "relaxed"
+    want = run("numpy", args.steps, args.nx, args.ny, args.nz, moist=args.moist, boundary=boundary)
     if args.stub:
         from tests.abi_oracle import OracleStub
         from tests.abi_stub import stubbed_library
@@ -179,7 +186,7 @@ def main():
         ctx = contextlib.nullcontext()
     with ctx as stub:
         n0 = None if args.stub else tb.lib.launch_count()
-        got = run("b200", args.steps, args.nx, args.ny, args.nz, moist=args.moist)
+        got = run("b200", args.steps, args.nx, args.ny, args.nz, moist=args.moist, boundary=boundary)
         if args.stub:
             fused_calls = stub.count("tb200_isentropic_stage_moist" if args.moist else "tb200_isentropic_stage_dry")
         else:
@@ -188,7 +195,7 @@ def main():
     if args.stub and not args.per_stencil:
         assert fused_calls == 3 * args.steps, fused_calls
     worst = {}
-    nx, ny, nz = args.nx, args.ny, args.nz
+    nx, ny, nz = (n - 1 for n in want[S].shape)  # the numerical grid
     for k in (S, SU, SV, U, V, MTG, P, EXN, H) + (QNAMES if args.moist else ()):
         a, b = got[k][: nx + 1, : ny + 1, : nz + 1], want[k][: nx + 1, : ny + 1, : nz + 1]
         scale = float(np.max(np.abs(b)))
@@ -199,7 +206,8 @@ def main():
     assert float(np.max(np.abs(want[SV]))) > 1e-6  # the flow developed
     if args.moist:
         assert all(float(np.max(np.abs(want[q]))) > 0.0 for q in QNAMES)
-    print("REF-DYCORE-STEPS-OK", ("per-stencil" if args.per_stencil else "fused") + ("-moist" if args.moist else ""),
+    print("REF-DYCORE-STEPS-OK", ("per-stencil" if args.per_stencil else "fused") + ("-moist" if args.moist else "")
+          + ("-periodic" if args.periodic else ""),
           args.steps)
 
 

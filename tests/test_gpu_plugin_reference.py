@@ -26,7 +26,8 @@ def _reference_root():
     return None
 
 
-@pytest.mark.parametrize("mode", ["fused", "per-stencil", "fused-moist", "per-stencil-moist"])
+@pytest.mark.parametrize("mode", ["fused", "per-stencil", "fused-moist", "per-stencil-moist",
+                                  "fused-periodic", "per-stencil-periodic"])
 def test_reference_dycore_on_b200_equals_its_numpy_backend(mode):
     ref = _reference_root()
     if ref is None:
@@ -36,6 +37,8 @@ def test_reference_dycore_on_b200_equals_its_numpy_backend(mode):
         cmd.append("--per-stencil")
     if mode.endswith("moist"):
         cmd.append("--moist")
+    if mode.endswith("periodic"):  # the reference's Periodic boundary (tb200_isentropic_stage.periodic when fused)
+        cmd.append("--periodic")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
                          env=dict(os.environ, TASMANIA_REFERENCE=ref))
     print(res.stdout[-2000:])

@@ -240,11 +240,13 @@ def test_k12_elementwise(stencils_golden):
 
 
 @pytest.mark.parametrize(
-    "case", ("isen_dry_rk3_5th", "isen_dry_rk3_3rd", "isen_dry_rk3_cen", "isen_dry_fe_upw")
+    "case", ("isen_dry_rk3_5th", "isen_dry_rk3_3rd", "isen_dry_rk3_cen", "isen_dry_fe_upw",
+             "isen_dry_rk3_5th_periodic", "isen_dry_rk3_3rd_periodic")
 )
 def test_dry_dycore_orchestration(case):
     """The oracle's restated orchestration vs. the reference's own classes driving the
-    reference's own ``stage_array_call_dry`` over several steps."""
+    reference's own ``stage_array_call_dry`` over several steps (relaxed boundaries, and the
+    reference's Periodic class on its numerical grid)."""
     fx = hp.load(case)
     final, stage0, _ = hp.oracle_dry_run(fx)
     nx, ny, nz = (int(v) for v in fx["dims"][:3])

@@ -48,6 +48,19 @@ def test_reference_dycore_time_stepped_on_b200_equals_its_numpy_backend():
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
                     reason="reference tree not mounted")
+def test_reference_dycore_with_periodic_boundary_on_b200_equals_its_numpy_backend():
+    """The same with the reference's Periodic boundary: the plugin's hook runs the fused dry stage
+    with ``tb200_isentropic_stage.periodic`` (the wrap of s inside the call, enforce_raw and the
+    damping after it, dycore.py:L684-L700), three fused calls per step, the reference's bits."""
+    res = subprocess.run([sys.executable, os.path.join(HERE, "ref_dycore_steps.py"), "--stub", "--periodic",
+                          "--steps", "3", "--nx", "23", "--ny", "19", "--nz", "8"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "REF-DYCORE-STEPS-OK fused-periodic 3" in res.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
+                    reason="reference tree not mounted")
 def test_reference_physics_components_on_b200_issue_the_mirror_calls():
     """north_star: "the sympl TendencyComponent/DiagnosticComponent classes ... work unchanged":
     the eleven components of the moist benchmark's physics chain and the Burgers stepper."""
