@@ -191,7 +191,9 @@ def main():
             fused_calls = stub.count("tb200_isentropic_stage_moist" if args.moist else "tb200_isentropic_stage_dry")
         else:
             fused_calls = None
-            assert tb.lib.launch_count() - n0 >= (10 if not args.per_stencil else 30) * args.steps
+            # (the reference's Periodic class wraps by slice assignment: storage copies, not library launches)
+            floor = 10 if not args.per_stencil else 20 if args.periodic else 30
+            assert tb.lib.launch_count() - n0 >= floor * args.steps, (tb.lib.launch_count() - n0, floor)
     if args.stub and not args.per_stencil:
         assert fused_calls == 3 * args.steps, fused_calls
     worst = {}
