@@ -425,10 +425,10 @@ typedef struct tb200_isentropic_stage {
    * periodic != 0, (nx, ny) is the numerical grid of a physical (nx - 2 nb, ny - 2 nb) one, gamma is
    * a field of zeros, and the stage wraps s into its nb ghost layers between the s-step and the
    * column scans -- the `hb.enforce_field(s_new)` of rk3ws_si.py:L184-L189, which with a relaxed
-   * boundary is the first relaxation.  Ghost points of su_new / sv_new keep their previous contents:
-   * the caller runs the stage with damp = 0 and applies `hb.enforce_raw` (tb200_periodic_enforce) and
-   * the damping afterwards, in the reference's order (dycore.py:L684-L700).  Dry stage, part 0,
-   * default kernel path, nx, ny >= 4 nb. */
+   * boundary is the first relaxation.  Ghost points of su_new / sv_new (and of the water constituents
+   * of the moist stage) keep their previous contents: the caller runs the stage with damp = 0 and
+   * skip_uv_out and applies `hb.enforce_raw` (tb200_periodic_enforce) and the damping afterwards, in
+   * the reference's order (dycore.py:L684-L700).  Part 0, default kernel path, nx, ny >= 4 nb. */
   int32_t periodic;
 } tb200_isentropic_stage;
 

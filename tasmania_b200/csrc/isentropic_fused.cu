@@ -2309,10 +2309,10 @@ int stage_entry(
                 "isentropic_stage_moist: needs the default kernel path (A + B), an unsplit stage and nz <= 64");
   a.a2_ok = mv2_ok(a) ? 1 : 0;
   a.periodic = cfg->periodic != 0;
-  TB200_REQUIRE(!a.periodic || (a.ntr == 0 && a.part == 0 && lazy_uv_path(a) && cfg->skip_uv_out != 0 &&
-                                !a.damp && nx >= 4 * a.nb && ny >= 4 * a.nb),
-                "isentropic_stage_dry: a periodic stage needs the dry stage, part 0, the default kernel path, "
-                "skip_uv_out, damp = 0 and nx, ny >= 4 nb");
+  TB200_REQUIRE(!a.periodic || (a.part == 0 && lazy_uv_path(a) && cfg->skip_uv_out != 0 && !a.damp &&
+                                nx >= 4 * a.nb && ny >= 4 * a.nb),
+                "isentropic_stage_dry: a periodic stage needs part 0, the default kernel path, skip_uv_out, "
+                "damp = 0 and nx, ny >= 4 nb");
   if (a.s_tnd.ok() || a.su_tnd.ok() || a.sv_tnd.ok()) {
     // slow tendencies (rk3ws_si.py:L105-L234 passes s_tnd, su_tnd, sv_tnd to K1 / K2): all three or
     // none, same geometry, dry stage, default kernel path

@@ -273,9 +273,9 @@ class IsentropicDynamicalCore(StencilFactory):
         # non-zero on the middle line alone and they repeat that line across the degenerate axis,
         # which the fused kernels do not do
         fusable = type(horizontal_boundary) is Relaxed
-        # ... and the 2-D Periodic class for the dry core: same kernels with gamma = 0, the wrap of s
+        # ... and the 2-D Periodic class: same kernels with gamma = 0, the wrap of s
         # between the s-step and the scans inside the stage call, enforce_raw and damping after it
-        self._periodic = (type(horizontal_boundary) is Periodic and not moist
+        self._periodic = (type(horizontal_boundary) is Periodic
                           and os.environ.get("TB200_FUSED_PERIODIC", "1") != "0"
                           and bool(lib.load().tb200_stage_lazy_velocities(grid.nz)))
         fusable = fusable or self._periodic
@@ -283,8 +283,7 @@ class IsentropicDynamicalCore(StencilFactory):
             fusable = (fusable and os.environ.get("TB200_MOIST_FUSED", "1") != "0"
                        and bool(lib.load().tb200_stage_lazy_velocities(grid.nz)))
         if fused and not fusable:
-            raise ValueError("the fused stage covers the core with (2-D) relaxed boundaries, and the dry core "
-                             "with (2-D) periodic ones, only")
+            raise ValueError("the fused stage covers the core with (2-D) relaxed or periodic boundaries only")
         self._fused = fusable if fused is None else bool(fused)
         # fused path only: intermediate RK stages neither write nor read u, v (see _stage_fused);
         # set to False to get every stage's velocities like the reference's stage_array_call
@@ -447,7 +446,7 @@ class IsentropicDynamicalCore(StencilFactory):
         ref, now = hb.reference_state, pr._now
         gamma2d = hb._gamma2d if not periodic else self._periodic_gamma()
         if periodic:  # no relaxation, no in-kernel damping, no velocity output: never read
-            ref = {n: ref.get(n, state[n]) for n in (S, SU, SV, U, V)}
+            ref = {n: ref.get(n, state[n]) for n in (S, SU, SV, U, V) + qn}
         f = lib.as_field
         rmat = self._damper._rmat if self._damp else None
         args = (cfg, f(now[S]), f(now[SU]), f(now[SV]), f(now[MTG]),
@@ -469,7 +468,7 @@ class IsentropicDynamicalCore(StencilFactory):
         if "time" in state and part != 1:
             out_state["time"] = state["time"] + dtr
         if periodic:  # dycore.py:L684-L700 in the reference's order
-            hb.enforce_raw({n: out_state[n] for n in (S, SU, SV)} | {"time": out_state.get("time")})
+            hb.enforce_raw({n: out_state[n] for n in (S, SU, SV) + qn} | {"time": out_state.get("time")})
             if damp:
                 self._damper(timestep, self._s_now, out_state[S], self._ref[S], out_state[S])
                 self._damper(timestep, self._su_now, out_state[SU], self._ref[SU], out_state[SU])

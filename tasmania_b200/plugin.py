@@ -291,7 +291,7 @@ def _fused_stage(moist=False):
     time label) and hands everything else to the library; it falls back to the original method
     -- the per-stencil b200 kernels -- whenever the configuration is outside the fused kernels'
     scope: fast tendencies, slow tendencies other than those of s, su, sv (dry stage), a boundary
-    other than the 2-D ``Relaxed`` (or, for the dry stage, the 2-D ``Periodic``), a prognostic scheme
+    other than the 2-D ``Relaxed`` or the 2-D ``Periodic``, a prognostic scheme
     other than RK3WSSI / ForwardEulerSI, reference fields in non-canonical units, foreign storages.
 
     ``moist=True`` does the same for ``stage_array_call_moist`` (dycore.py:L723-L843) with
@@ -330,7 +330,7 @@ def _fused_stage(moist=False):
             return cached or None
         ok = getattr(self, "backend", None) == BACKEND and bool(getattr(self, "_moist", not moist)) == moist
         hb, pr = self.horizontal_boundary, self._prognostic
-        periodic = type(hb).__name__ == "Periodic" and not moist  # the dry stage wraps s itself (cfg.periodic)
+        periodic = type(hb).__name__ == "Periodic"  # the stage wraps s itself (cfg.periodic)
         ok = ok and (type(hb).__name__ == "Relaxed" or periodic) and getattr(type(pr), "name", None) in SUBSTEPS
         scheme = getattr(getattr(pr, "_hflux", None), "name", None)
         ok = ok and scheme in lib.FLUX_SCHEMES and hasattr(pr, "_diagnostics")
@@ -437,7 +437,7 @@ def _fused_stage(moist=False):
             rc = lib.load().tb200_isentropic_stage_dry(*args, lib.current_stream())
             lib.check(rc, "tb200_isentropic_stage_dry")
         if periodic:
-            for n in (S, SU, SV):  # hb.enforce_raw: periodic.py:L98-L122
+            for n in (S, SU, SV) + (QN if moist else ()):  # hb.enforce_raw: periodic.py:L98-L122
                 lib.check(lib.load().tb200_periodic_enforce(f(out_state[n]), hb.nx, hb.ny, hb.nb, hb.nx, hb.ny,
                                                             lib.current_stream()), "tb200_periodic_enforce")
             if damp:  # dycore.py:L694-L700

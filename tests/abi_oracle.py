@@ -237,7 +237,7 @@ class OracleStub(AbiStub):
                               dx=c.dx, dy=c.dy, origin=origin, domain=domain, s_tnd=s_tnd)
         ob.irelax(gamma, arr(s_ref), out["s"], (0, 0, 0), (nx, ny, nz))
         if c.periodic:  # the stage wraps s itself (hb.enforce_field(s_new), rk3ws_si.py:L184-L189)
-            assert not gamma.any() and not c.damp and c.skip_uv_out and after_s_step is None
+            assert not gamma.any() and not c.damp and c.skip_uv_out
             ob.Periodic(nx - 2 * nb, ny - 2 * nb, nz, nb).enforce_field(out["s"][:nx, :ny, :nz])
         if after_s_step is not None:
             after_s_step(out["s"], u_i, v_i, gamma)

@@ -27,7 +27,7 @@ def _reference_root():
 
 
 @pytest.mark.parametrize("mode", ["fused", "per-stencil", "fused-moist", "per-stencil-moist",
-                                  "fused-periodic", "per-stencil-periodic"])
+                                  "fused-periodic", "per-stencil-periodic", "fused-moist-periodic"])
 def test_reference_dycore_on_b200_equals_its_numpy_backend(mode):
     ref = _reference_root()
     if ref is None:
@@ -35,7 +35,7 @@ def test_reference_dycore_on_b200_equals_its_numpy_backend(mode):
     cmd = [sys.executable, os.path.join(ROOT, "tests", "ref_dycore_steps.py"), "--steps", "10"]
     if mode.startswith("per-stencil"):
         cmd.append("--per-stencil")
-    if mode.endswith("moist"):
+    if "moist" in mode:
         cmd.append("--moist")
     if mode.endswith("periodic"):  # the reference's Periodic boundary (tb200_isentropic_stage.periodic when fused)
         cmd.append("--periodic")

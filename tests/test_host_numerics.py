@@ -8,6 +8,7 @@ oracle's own models bit for bit (both sides are numpy).  The CUDA code itself is
 from datetime import datetime, timedelta
 
 import numpy as np
+import pytest
 
 from oracle import boundary as ob
 from oracle import isentropic as oi
@@ -472,3 +473,32 @@ def test_periodic_dry_dycore_fused_and_stencil_paths_equal_oracle_numerically():
                 np.testing.assert_array_equal(got[n][:nx + 1, :ny + 1, :nz], want[n][:nx + 1, :ny + 1, :nz],
                                               err_msg=f"fused={fused} lazy={lazy} tendencies={tendencies is not None}: {n}")
         assert float(np.abs(want[hp.SV] - np_state[hp.SV]).max()) > 1e-6
+
+
+@pytest.mark.parametrize("case", ("isen_dry_rk3_5th_periodic", "isen_dry_rk3_3rd_periodic",
+                                  "isen_moist_rk3_5th_periodic"))
+@pytest.mark.parametrize("fused,lazy", ((False, False), (True, True), (True, False)))
+def test_periodic_dycore_host_path_equals_reference_fixture(case, fused, lazy):
+    """The harness of tests/test_gpu_isentropic.py over the oracle-backed stub: the dycore mirror with
+    the Periodic boundary -- per-stencil path and fused stage (dry and moist) -- reproduces, bit for
+    bit, the fixtures written by the reference's own ``stage_array_call_dry / _moist`` on a periodic
+    domain."""
+    import tasmania_b200 as tb
+    from tests import test_gpu_isentropic as tg
+
+    fx = hp.load(case)
+    with stubbed_library(OracleStub) as stub:
+        grid, hb, dyc, diag, state, pt, dt, nsteps = tg.build_from_fixture(fx, fused)
+        assert dyc._fused == fused and (not fused or dyc._periodic)
+        dyc.lazy_velocities = lazy
+        final, stage0 = tg.run(grid, dyc, diag, state, pt, dt, nsteps)
+        entry = "tb200_isentropic_stage_moist" if dyc._moist else "tb200_isentropic_stage_dry"
+        assert stub.count(entry) == (dyc.stages * nsteps if fused else 0)
+        nx, ny, nz = grid.nx, grid.ny, grid.nz
+        qn = tg.QNAMES if dyc._moist else ()
+        for n in (hp.S, hp.SU, hp.SV) + qn + (() if lazy else (hp.U, hp.V)):
+            np.testing.assert_array_equal(stage0[n][: nx + 1, : ny + 1, :nz],
+                                          fx["stage0_" + n][: nx + 1, : ny + 1, :nz], err_msg="stage0 " + n)
+        for n in (hp.S, hp.SU, hp.SV, hp.U, hp.V, hp.MTG, hp.P, hp.EXN, hp.H) + qn:
+            np.testing.assert_array_equal(tb.to_numpy(final[n])[: nx + 1, : ny + 1, : nz + 1],
+                                          fx["final_" + n][: nx + 1, : ny + 1, : nz + 1], err_msg="final " + n)

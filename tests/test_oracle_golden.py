@@ -256,7 +256,7 @@ def test_dry_dycore_orchestration(case):
         eq(final[n], fx["final_" + n])
 
 
-@pytest.mark.parametrize("case", ("isen_moist_rk3_5th", "isen_moist_fe_3rd"))
+@pytest.mark.parametrize("case", ("isen_moist_rk3_5th", "isen_moist_fe_3rd", "isen_moist_rk3_5th_periodic"))
 def test_moist_dycore_orchestration(case):
     """Moist stage (tracer densities -> K1 with tracers -> mass fractions -> boundary -> damping
     -> velocities) against the reference's own ``stage_array_call_moist``."""

@@ -52,11 +52,12 @@ def test_reference_dycore_with_periodic_boundary_on_b200_equals_its_numpy_backen
     """The same with the reference's Periodic boundary: the plugin's hook runs the fused dry stage
     with ``tb200_isentropic_stage.periodic`` (the wrap of s inside the call, enforce_raw and the
     damping after it, dycore.py:L684-L700), three fused calls per step, the reference's bits."""
-    res = subprocess.run([sys.executable, os.path.join(HERE, "ref_dycore_steps.py"), "--stub", "--periodic",
-                          "--steps", "3", "--nx", "23", "--ny", "19", "--nz", "8"],
-                         capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout + res.stderr
-    assert "REF-DYCORE-STEPS-OK fused-periodic 3" in res.stdout
+    for extra, tag in ((), "fused-periodic"), (("--moist",), "fused-moist-periodic"):
+        res = subprocess.run([sys.executable, os.path.join(HERE, "ref_dycore_steps.py"), "--stub", "--periodic",
+                              "--steps", "3", "--nx", "23", "--ny", "19", "--nz", "8", *extra],
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert f"REF-DYCORE-STEPS-OK {tag} 3" in res.stdout
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "tasmania")),
