@@ -378,6 +378,12 @@ class IsentropicDynamicalCore(StencilFactory):
         library) keep plain storages."""
         dev = self.storage_options.device
         on_device = dev is None or "cuda" in str(dev)
+        if on_device and dev is not None and storage.DEFAULT_DEVICE_OVERRIDE is None:
+            import torch
+
+            # the context allocates on the CURRENT device; storages of another one stay with torch
+            index = torch.device(dev).index
+            on_device = index is None or index == torch.cuda.current_device()
         if on_device and storage.DEFAULT_DEVICE_OVERRIDE is None and os.environ.get("TB200_CTX_SCRATCH", "1") != "0":
             self._ctx = lib.Context()
             self._scratch = self._ctx.scratch(self.storage_shape, 3)
