@@ -376,19 +376,9 @@ class IsentropicDynamicalCore(StencilFactory):
         its first relaxation) live in a library context held by this object (``tb200_ctx``, SURVEY.md
         section 8b): allocated once, freed with the dycore.  Host storages (the CPU test double of the
         library) keep plain storages."""
-        dev = self.storage_options.device
-        on_device = dev is None or "cuda" in str(dev)
-        if on_device and dev is not None and storage.DEFAULT_DEVICE_OVERRIDE is None:
-            import torch
-
-            # the context allocates on the CURRENT device; storages of another one stay with torch
-            index = torch.device(dev).index
-            on_device = index is None or index == torch.cuda.current_device()
-        if on_device and storage.DEFAULT_DEVICE_OVERRIDE is None and os.environ.get("TB200_CTX_SCRATCH", "1") != "0":
-            self._ctx = lib.Context()
-            self._scratch = self._ctx.scratch(self.storage_shape, 3)
-        else:
-            self._scratch = tuple(self.zeros(shape=self.storage_shape) for _ in range(3))
+        ctx, self._scratch = storage.stage_scratch(self.storage_shape, 3, self.storage_options.device)
+        if ctx is not None:
+            self._ctx = ctx
 
     def _periodic_gamma(self):
         if getattr(self, "_zero_gamma2d", None) is None:

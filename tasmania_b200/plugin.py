@@ -352,11 +352,14 @@ def _fused_stage(moist=False):
             "constants": [rpc["air_pressure_at_sea_level"], rpc["gas_constant_of_dry_air"],
                           rpc["gravitational_acceleration"],
                           rpc["specific_heat_of_dry_air_at_constant_pressure"]],
-            "scratch": [storage.zeros(shape, device=_device(self.storage_options)) for _ in range(3)],
+            # the stage's hand-off arrays: a library context held by the dycore object (tb200_ctx)
+            "scratch_owner": None, "scratch": None,
             "lazy": (self.fast_tendency_component is None and self.fast_diagnostic_component is None
                      and bool(lib.load().tb200_stage_lazy_velocities(int(g.nz)))),
             "periodic": periodic,
         }
+        self._b200_fused_plan["scratch_owner"], self._b200_fused_plan["scratch"] = storage.stage_scratch(
+            shape, 3, _device(self.storage_options))
         if periodic:
             if not lib.load().tb200_stage_lazy_velocities(int(g.nz)):  # an earlier kernel variant forced by the environment
                 self._b200_fused_plan = False

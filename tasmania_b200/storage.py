@@ -279,3 +279,26 @@ def to_numpy(x) -> np.ndarray:
     if isinstance(x, B200Array):
         return x.to_numpy()
     return np.asarray(x)
+
+
+def stage_scratch(shape, count, device=None):
+    """``count`` hand-off fields of the fused RK stage for a host-side object that issues the fused
+    calls: ``(context, fields)``.  On the current CUDA device they come from a library context
+    (``tb200_ctx_create / scratch / destroy``; the caller keeps ``context``
+    alive and drops it with itself); storages of another device, the CPU test double of the
+    library (``DEFAULT_DEVICE_OVERRIDE``) and ``TB200_CTX_SCRATCH=0`` keep plain storages
+    (``context`` is None).  Call it outside any CUDA-graph capture."""
+    import os
+
+    from tasmania_b200 import lib
+
+    use_ctx = DEFAULT_DEVICE_OVERRIDE is None and os.environ.get("TB200_CTX_SCRATCH", "1") != "0"
+    if use_ctx and device is not None:
+        d = torch.device(device)
+        # the context allocates on the CURRENT device
+        use_ctx = d.type == "cuda" and (d.index is None or d.index == torch.cuda.current_device())
+    if use_ctx:
+        ctx = lib.Context()
+        return ctx, ctx.scratch(tuple(int(n) for n in shape), count)
+    return None, tuple(zeros(tuple(shape), device=device) for _ in range(count))
+
