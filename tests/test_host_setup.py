@@ -184,3 +184,17 @@ def test_identity_boundary_mirror_touches_nothing():
         hb.set_outermost_layers_y(a)
         hb.enforce_raw({"air_isentropic_density": a})
         assert (a == b).all() and stub.calls == []
+
+
+def test_stage_scratch_keeps_plain_storages_without_a_device(monkeypatch):
+    """storage.stage_scratch hands out library-context fields on the current CUDA device only; the
+    CPU test double of the library (DEFAULT_DEVICE_OVERRIDE) gets ordinary storages and no context."""
+    from tasmania_b200 import storage
+
+    monkeypatch.setattr(storage, "DEFAULT_DEVICE_OVERRIDE", "cpu")
+    ctx, fields = storage.stage_scratch((7, 5, 3), 3)
+    assert ctx is None and len(fields) == 3
+    for f in fields:
+        assert isinstance(f, storage.B200Array) and f.shape == (7, 5, 3) and f.strides == (8, 16 * 8, 16 * 5 * 8)
+        assert float(np.abs(tb.to_numpy(f)).max()) == 0.0
+    assert len({f.t.data_ptr() for f in fields}) == 3
