@@ -799,6 +799,9 @@ CASES = {
     "isen_dry_rk3_3rd_periodic": lambda: gen_isentropic_dry(
         "isen_dry_rk3_3rd_periodic", 14, 17, 5, "rk3ws_si", "third_order_upwind", 2, 0, 4, 5.0,
         damp_every=False, topo_time=15.0, hb_type="periodic"),
+    "isen_dry_fe_cen_periodic": lambda: gen_isentropic_dry(
+        "isen_dry_fe_cen_periodic", 13, 16, 5, "forward_euler_si", "centered", 1, 0, 4, 3.0,
+        damp_depth=2, topo_time=9.0, hb_type="periodic"),
     "isen_moist_rk3_5th_periodic": lambda: gen_isentropic_dry(
         "isen_moist_rk3_5th_periodic", 17, 16, 6, "rk3ws_si", "fifth_order_upwind", 3, 0, 4, 5.0,
         damp_depth=3, topo_time=20.0, moist=True, hb_type="periodic"),

@@ -476,7 +476,7 @@ def test_periodic_dry_dycore_fused_and_stencil_paths_equal_oracle_numerically():
 
 
 @pytest.mark.parametrize("case", ("isen_dry_rk3_5th_periodic", "isen_dry_rk3_3rd_periodic",
-                                  "isen_moist_rk3_5th_periodic"))
+                                  "isen_dry_fe_cen_periodic", "isen_moist_rk3_5th_periodic"))
 @pytest.mark.parametrize("fused,lazy", ((False, False), (True, True), (True, False)))
 def test_periodic_dycore_host_path_equals_reference_fixture(case, fused, lazy):
     """The harness of tests/test_gpu_isentropic.py over the oracle-backed stub: the dycore mirror with

@@ -241,7 +241,7 @@ def test_k12_elementwise(stencils_golden):
 
 @pytest.mark.parametrize(
     "case", ("isen_dry_rk3_5th", "isen_dry_rk3_3rd", "isen_dry_rk3_cen", "isen_dry_fe_upw",
-             "isen_dry_rk3_5th_periodic", "isen_dry_rk3_3rd_periodic")
+             "isen_dry_rk3_5th_periodic", "isen_dry_rk3_3rd_periodic", "isen_dry_fe_cen_periodic")
 )
 def test_dry_dycore_orchestration(case):
     """The oracle's restated orchestration vs. the reference's own classes driving the
