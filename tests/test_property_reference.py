@@ -160,3 +160,64 @@ def test_k3_column_scans_on_random_columns(dims):
     from tests import test_stencils_reference as ts
 
     ts.test_k3_column_scans_equal_reference_from_one_level_to_deep_columns(dims)
+
+
+@settings(max_examples=12, **SETTINGS)
+@given(data=st.data())
+def test_b200_mirror_components_on_random_grids(data):
+    """The reference's tests run every component on every backend; here the b200 mirrors
+    (HorizontalDiffusion, HorizontalSmoothing, Periodic, Relaxed: host marshalling + the C-ABI call,
+    carried out by the oracle-backed stub) against the reference's own classes on backend numpy, on
+    random grids -- bit for bit."""
+    import tasmania_b200 as tb
+    from tasmania_b200 import boundary as tbb
+    from tasmania_b200.dwarfs import HorizontalDiffusion, HorizontalSmoothing
+    from tests.abi_oracle import OracleStub
+    from tests.abi_stub import stubbed_library
+
+    refload.install_framework()
+    opts = refload.load("tasmania.framework.options")
+    for name in ("second_order", "fourth_order"):
+        refload.load("tasmania.dwarfs.subclasses.horizontal_diffusers." + name)
+    for name in ("first_order", "second_order", "third_order"):
+        refload.load("tasmania.dwarfs.subclasses.horizontal_smoothers." + name)
+    hd = refload.load("tasmania.dwarfs.horizontal_diffusion")
+    hsm = refload.load("tasmania.dwarfs.horizontal_smoothing")
+    kw = dict(backend="numpy", backend_options=opts.BackendOptions(), storage_options=opts.StorageOptions())
+
+    nx = data.draw(st.integers(7, 20), label="nx")
+    ny = data.draw(st.integers(7, 20), label="ny")
+    nz = data.draw(st.integers(1, 5), label="nz")
+    depth = data.draw(st.integers(0, nz), label="damp depth")
+    nb = data.draw(st.integers(1, 3), label="nb")
+    rng = np.random.default_rng(data.draw(st.integers(0, 2**31), label="seed"))
+    shape = (nx, ny, nz)
+    phi, base = rng.standard_normal(shape), rng.standard_normal(shape)
+    with stubbed_library(OracleStub):
+        for name in ("second_order", "fourth_order"):
+            ref_obj = hd.HorizontalDiffusion.factory(name, shape, 0.7, 1.3, 0.5, 1.0, depth, **kw)
+            obj = HorizontalDiffusion.factory(name, shape, 0.7, 1.3, 0.5, 1.0, depth)
+            for overwrite in (True, False):
+                ref = base.copy()
+                ref_obj(phi, ref, overwrite_output=overwrite)
+                out = tb.as_storage(base)
+                obj(tb.as_storage(phi), out, overwrite_output=overwrite)
+                np.testing.assert_array_equal(tb.to_numpy(out), ref, err_msg=f"diffusion {name} {overwrite}")
+        for name in ("first_order", "second_order", "third_order"):
+            ref_obj = hsm.HorizontalSmoothing.factory(name, shape, 0.03, 0.24, depth, **kw)
+            obj = HorizontalSmoothing.factory(name, shape, 0.03, 0.24, depth)
+            ref = base.copy()
+            ref_obj(phi, ref)
+            out = tb.as_storage(base)
+            obj(tb.as_storage(phi), out)
+            np.testing.assert_array_equal(tb.to_numpy(out), ref, err_msg=f"smoothing {name}")
+        # periodic wrap of unstaggered and staggered fields on the numerical grid
+        px, py = max(nx - 2 * nb, 2 * nb), max(ny - 2 * nb, 2 * nb)
+        hb_ref = _domain(px, py, nz, "periodic", nb).horizontal_boundary
+        hb = tbb.Periodic(px, py, nz, nb)
+        for name in FIELDS:
+            a = rng.standard_normal((px + 2 * nb + 1, py + 2 * nb + 1, nz + 1))
+            b = tb.as_storage(a)
+            hb_ref.enforce_field(a, field_name=name)
+            hb.enforce_field(b, field_name=name)
+            np.testing.assert_array_equal(tb.to_numpy(b), a, err_msg="periodic " + name)
