@@ -87,7 +87,10 @@ long long tb200_launch_count(void);
  * arrays of tb200_isentropic_stage_dry / _moist: scratch_exn, scratch_mtg, scratch_s) is requested
  * from a context held by the host-side backend object: tb200_ctx_scratch returns `count` zero-filled
  * fields of logical shape `shape` in the b200 storage layout (unit i-stride, rows padded to 16
- * doubles), the same ones on every call with that shape, valid until tb200_ctx_destroy. */
+ * doubles), the same ones on every call with that shape, valid until tb200_ctx_destroy.
+ * Reference counterpart: the temporaries its objects allocate for themselves, e.g. `_mtg_new` of
+ * the prognostic (isentropic/dynamics/subclasses/prognostics/rk3ws_si.py:L241) and the sq* / *_ref
+ * storages of the dycore (isentropic/dynamics/dycore.py:L321-L345). */
 typedef struct tb200_ctx tb200_ctx;
 int tb200_ctx_create(tb200_ctx **ctx);
 int tb200_ctx_destroy(tb200_ctx *ctx);
