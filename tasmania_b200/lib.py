@@ -252,6 +252,15 @@ class Context:
               "tb200_ctx_scratch")
         return tuple(ScratchField(fields[n], self) for n in range(count))
 
+    def __copy__(self):
+        raise TypeError("a tb200_ctx owns device memory: not copyable")
+
+    def __deepcopy__(self, memo):
+        raise TypeError("a tb200_ctx owns device memory: not copyable")
+
+    def __reduce__(self):
+        raise TypeError("a tb200_ctx owns device memory: not picklable")
+
     def __del__(self):
         try:
             if self._h:
