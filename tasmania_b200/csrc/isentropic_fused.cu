@@ -28,6 +28,13 @@
 // adds kernel T between A and B: the three water constituents (density, K1 share, mass fraction,
 // relaxation) in one tiled kernel.
 //
+// Periodic boundary (tb200_isentropic_stage.periodic).  The kernels are general in gamma: a point
+// outside the interior keeps its previous value unless gamma == 1 there.  With gamma = 0 everywhere
+// on the numerical grid of a periodic domain the same kernels therefore compute the interior and
+// leave the ghost layers alone; the stage wraps s_pre into them between kernel A and kernel B (the
+// reference's hb.enforce_field(s_new) before the Montgomery scan), and the caller wraps the outputs
+// and applies the damping after the call, in the reference's order (dycore.py:L684-L700).
+//
 // HBM traffic per point and stage (8-byte words), stages 1, 2: A reads s_now, s_int, su_int,
 // sv_int, writes s_pre (5); B reads s_pre, writes mtg (2); MV reads s_now, s_int, s_pre, mtg_now,
 // mtg_new, su_now, su_int, sv_now, sv_int, writes su, sv and s where relaxation / damping change
