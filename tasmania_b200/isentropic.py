@@ -242,10 +242,23 @@ class IsentropicDynamicalCore(StencilFactory):
                  time_integration_scheme="forward_euler_si", horizontal_flux_scheme="upwind",
                  time_integration_properties=None, damp=True, damp_at_every_stage=True,
                  damp_type="rayleigh", damp_depth=15, damp_max=0.0002, fused=None,
-                 backend="b200", backend_options=None, storage_shape=None, storage_options=None):
+                 backend="b200", backend_options=None, storage_shape=None, storage_options=None,
+                 smooth=True, smooth_at_every_stage=True, smooth_moist=False,
+                 smooth_moist_at_every_stage=True, **smoothing_options):
         super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
         self.grid, self.horizontal_boundary = grid, horizontal_boundary
         self._moist, self._damp, self._damp_at_every_stage = moist, damp, damp_at_every_stage
+        # the reference's constructor takes twelve smooth* arguments (dycore.py:L81-L92), keeps four
+        # flags (L245-L248) and never applies any smoothing in its stages (L641-L843; the benchmark
+        # drivers smooth through the IsentropicHorizontalSmoothing component): accepted and kept
+        # likewise, so that a reference call site carries over; anything else is a mistake
+        unknown = set(smoothing_options) - {
+            "smooth_type", "smooth_coeff", "smooth_coeff_max", "smooth_damp_depth", "smooth_moist_type",
+            "smooth_moist_coeff", "smooth_moist_coeff_max", "smooth_moist_damp_depth"}
+        if unknown:
+            raise TypeError(f"IsentropicDynamicalCore: unexpected keyword argument(s) {sorted(unknown)}")
+        self._smooth, self._smooth_at_every_stage = smooth, smooth_at_every_stage
+        self._smooth_moist, self._smooth_moist_at_every_stage = smooth_moist, smooth_moist_at_every_stage
         g = grid
         self.storage_shape = tuple(storage_shape or (g.nx + 1, g.ny + 1, g.nz + 1))
         kwargs = time_integration_properties or {}

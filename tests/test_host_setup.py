@@ -198,3 +198,24 @@ def test_stage_scratch_keeps_plain_storages_without_a_device(monkeypatch):
         assert isinstance(f, storage.B200Array) and f.shape == (7, 5, 3) and f.strides == (8, 16 * 8, 16 * 5 * 8)
         assert float(np.abs(tb.to_numpy(f)).max()) == 0.0
     assert len({f.t.data_ptr() for f in fields}) == 3
+
+
+def test_dycore_mirror_accepts_the_reference_smoothing_arguments(monkeypatch):
+    """A reference call site passes smooth* keywords (dycore.py:L81-L92); the reference keeps the
+    flags and never smooths inside a stage, and so does the mirror.  Unknown keywords still raise."""
+    from tasmania_b200 import storage
+    from tasmania_b200.boundary import Relaxed
+    from tasmania_b200.isentropic import IsentropicDynamicalCore
+
+    monkeypatch.setattr(storage, "DEFAULT_DEVICE_OVERRIDE", "cpu")
+    x = np.linspace(-176.0, 176.0, 19)
+    grid = Grid((-176.0, 176.0), 19, (-176.0, 176.0), 17, (400.0, 280.0), 6, units_to_m=1e3,
+                topography=Topography(gaussian_profile(x, np.linspace(-176.0, 176.0, 17), 500.0, 50.0, 50.0),
+                                      timedelta(seconds=30)))
+    kw = dict(time_integration_scheme="rk3ws_si", horizontal_flux_scheme="fifth_order_upwind",
+              time_integration_properties={"pt": 100.0, "eps": 0.5}, damp_depth=2, fused=False)
+    dyc = IsentropicDynamicalCore(grid, Relaxed(19, 17, 6, 3, nr=6), smooth=False, smooth_type="second_order",
+                                  smooth_coeff=0.2, smooth_moist=False, smooth_moist_damp_depth=0, **kw)
+    assert dyc._smooth is False and dyc._smooth_moist is False
+    with pytest.raises(TypeError):
+        IsentropicDynamicalCore(grid, Relaxed(19, 17, 6, 3, nr=6), smoooth=False, **kw)
