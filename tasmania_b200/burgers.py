@@ -18,7 +18,7 @@ from __future__ import annotations
 import numpy as np
 
 from tasmania_b200.dwarfs import HorizontalDiffusion
-from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
+from tasmania_b200.framework import BackendOptions, GridComponent, StencilFactory, StorageOptions
 from tasmania_b200.stencils import ADVECTION
 
 
@@ -115,7 +115,7 @@ class BurgersStepper(StencilFactory):
         out_state["time"] = state["time"] + dtr
 
 
-class BurgersDynamicalCore(StencilFactory):
+class BurgersDynamicalCore(GridComponent, StencilFactory):
     """Stage = stepper + lateral boundary (dycore.py:L158-L173), chained as in
     ``DynamicalCore.__call__`` (src/tasmania/framework/dycore.py:L383-L462)."""
 

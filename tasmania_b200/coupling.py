@@ -31,7 +31,7 @@ import os
 
 from tasmania_b200 import stencils
 from tasmania_b200.dwarfs import HorizontalDiffusion, HorizontalSmoothing, HorizontalVelocity
-from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
+from tasmania_b200.framework import BackendOptions, GridComponent, StencilFactory, StorageOptions
 from tasmania_b200.isentropic import MTG, S, SU, SV, U, V
 from tasmania_b200.isentropic import IsentropicDiagnostics as _DiagnosticsCore
 
@@ -67,7 +67,7 @@ def update_swap(dst, src):
 
 
 # ------------------------------------------------------------------------------ components
-class _DomainComponent(StencilFactory):
+class _DomainComponent(GridComponent, StencilFactory):
     kind = "diagnostic"
     tendency_names: tuple = ()
     diagnostic_names: tuple = ()

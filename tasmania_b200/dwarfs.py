@@ -20,7 +20,7 @@ import math
 import numpy as np
 
 from tasmania_b200 import storage
-from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
+from tasmania_b200.framework import BackendOptions, GridComponent, StencilFactory, StorageOptions
 
 
 def _profile_storage(profile, shape, device):
@@ -136,7 +136,7 @@ def rayleigh_coefficient(z_main, z_top, damp_depth, damp_max, nk):
     return r
 
 
-class VerticalDamping(StencilFactory):
+class VerticalDamping(GridComponent, StencilFactory):
     """Rayleigh wave absorber: ``out = new - dt R(k) (now - ref)``."""
 
     def __init__(self, damp_type, grid, damp_depth=15, damp_coeff_max=0.0002, time_units="s", *,
@@ -145,6 +145,7 @@ class VerticalDamping(StencilFactory):
         if damp_type != "rayleigh":
             raise ValueError(f"unknown vertical damping type {damp_type!r}")
         assert damp_depth <= grid.nz
+        self._grid = grid
         self._damp_depth = damp_depth
         self._shape = tuple(storage_shape or (grid.nx + 1, grid.ny + 1, grid.nz + 1))
         r = rayleigh_coefficient(grid.z, grid.z_on_interface_levels[0], damp_depth, damp_coeff_max,
@@ -162,7 +163,7 @@ class VerticalDamping(StencilFactory):
                            origin=(0, 0, 0), domain=self._shape)
 
 
-class HorizontalVelocity(StencilFactory):
+class HorizontalVelocity(GridComponent, StencilFactory):
     """Momenta <-> velocity components, dwarfs/diagnostics.py:L44-L272."""
 
     def __init__(self, grid, staggering=True, *, backend="b200", backend_options=None,
@@ -187,7 +188,7 @@ class HorizontalVelocity(StencilFactory):
                                             domain=(g.nx, g.ny - dn, g.nz))
 
 
-class WaterConstituent(StencilFactory):
+class WaterConstituent(GridComponent, StencilFactory):
     """Density <-> mass fraction of a water species, dwarfs/diagnostics.py:L275-L466."""
 
     def __init__(self, grid, clipping=False, *, backend="b200", backend_options=None,

@@ -141,6 +141,12 @@ def compiler_b200(definition: Callable, *, backend_options: Optional[BackendOpti
     return stencil
 
 
+def subroutine_compiler_b200(definition, *, backend_options: Optional[BackendOptions] = None):
+    """The b200 ``subroutine_compiler``: a b200 subroutine is a scheme descriptor read by the fused
+    kernels' marshalling code, never a callable to inline -- nothing to compile."""
+    return definition
+
+
 def compile_stencil(stencil: str, backend: Optional[str] = None, *,
                     backend_options: Optional[BackendOptions] = None) -> Callable:
     return compiler_b200(get_stencil_definition(stencil, backend), backend_options=backend_options)
@@ -185,6 +191,20 @@ class StencilFactory:
     def get_subroutine_definition(self, stencil, backend=None):
         return get_subroutine_definition(stencil, backend)
 
+    # framework/stencil.py:L286-L297, L356-L427: one compiler per kind for the one backend
+    def get_stencil_compiler(self, backend=None, stencil=None):
+        _check_backend(backend)
+        return compiler_b200
+
+    def get_subroutine_compiler(self, backend=None, stencil=None):
+        _check_backend(backend)
+        return subroutine_compiler_b200
+
+    def compile_subroutine(self, stencil: str, backend: Optional[str] = None, *,
+                           backend_options: Optional[BackendOptions] = None):
+        return subroutine_compiler_b200(self.get_subroutine_definition(stencil, backend),
+                                        backend_options=backend_options or self.backend_options)
+
     def _so(self, storage_options):
         return storage_options or self.storage_options
 
@@ -209,3 +229,42 @@ class StencilFactory:
         _check_backend(backend)
         so = self._so(storage_options)
         return storage.as_storage(data, device=so.device)
+
+
+class GridComponent:
+    """Shape helpers of the reference's components over a grid
+    (src/tasmania/framework/base_components.py:L55-L135): the extent of a named field on the grid --
+    one more point along an axis it is staggered on, one level for a surface field, nz + 1 on the
+    interface levels -- and the storage shape that holds it."""
+
+    @property
+    def grid(self):
+        return self._grid
+
+    @grid.setter
+    def grid(self, value):
+        self._grid = value
+
+    def get_field_grid_shape(self, name: str):
+        g = self.grid
+        stag_x = "at_u_locations" in name or "at_uv_locations" in name
+        stag_y = "at_v_locations" in name or "at_uv_locations" in name
+        nk = 1 if "at_surface_level" in name else g.nz + 1 if "on_interface_levels" in name else g.nz
+        return g.nx + int(stag_x), g.ny + int(stag_y), nk
+
+    def get_field_storage_shape(self, name: str, default_storage_shape):
+        return self.get_shape(default_storage_shape, min_shape=self.get_field_grid_shape(name))
+
+    def get_storage_shape(self, shape, min_shape=None, max_shape=None):
+        g = self.grid
+        return self.get_shape(shape, min_shape or (g.nx, g.ny, g.nz), max_shape)
+
+    @staticmethod
+    def get_shape(in_shape, min_shape, max_shape=None):
+        """``in_shape`` (or ``min_shape`` when none is given) clamped from below by ``min_shape`` and,
+        if given, from above by ``max_shape``."""
+        out = in_shape or min_shape
+        if max_shape is None:
+            return [max(a, lo) for a, lo in zip(out, min_shape)]
+        return [lo if a < lo else (hi if a > hi else a) for a, lo, hi in zip(out, min_shape, max_shape)]
+

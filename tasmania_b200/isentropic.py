@@ -25,7 +25,7 @@ import numpy as np
 
 from tasmania_b200 import lib, storage
 from tasmania_b200.dwarfs import HorizontalVelocity, VerticalDamping, WaterConstituent
-from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
+from tasmania_b200.framework import BackendOptions, GridComponent, StencilFactory, StorageOptions
 from tasmania_b200.grid import CONSTANTS
 from tasmania_b200.stencils import FLUX
 
@@ -40,7 +40,7 @@ SQC = "isentropic_density_of_cloud_liquid_water"
 SQR = "isentropic_density_of_precipitation_water"
 
 
-class IsentropicDiagnostics(StencilFactory):
+class IsentropicDiagnostics(GridComponent, StencilFactory):
     """Pressure, Exner function, Montgomery potential and height of the interface levels by
     per-column vertical scans (K3)."""
 
@@ -119,7 +119,7 @@ class IsentropicDiagnostics(StencilFactory):
             origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))
 
 
-class IsentropicPrognostic(StencilFactory):
+class IsentropicPrognostic(GridComponent, StencilFactory):
     """Prognostic stage (K1 -> boundary(s) -> Montgomery -> K2); ``factory`` by scheme name."""
 
     name = None
@@ -234,7 +234,7 @@ class RK3WSSI(IsentropicPrognostic):
         return 0.5 * timestep, timestep
 
 
-class IsentropicDynamicalCore(StencilFactory):
+class IsentropicDynamicalCore(GridComponent, StencilFactory):
     """Raw-array dynamical core: ``stage_array_call`` (dry and moist) + the stage chaining of
     ``DynamicalCore.__call__`` (src/tasmania/framework/dycore.py:L383-L462)."""
 

@@ -13,7 +13,7 @@ arithmetic runs in ``tb200_vertical_advection`` (csrc/vertical.cu) and ``tb200_c
 ``tb200_implicit_vertical_advection`` (csrc/vertical.cu)."""
 from __future__ import annotations
 
-from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
+from tasmania_b200.framework import BackendOptions, GridComponent, StencilFactory, StorageOptions
 from tasmania_b200.stencils import FLUX
 
 S, SU, SV = "air_isentropic_density", "x_momentum_isentropic", "y_momentum_isentropic"
@@ -24,7 +24,7 @@ W_ML = "tendency_of_air_potential_temperature"
 W_HL = "tendency_of_air_potential_temperature_on_interface_levels"
 
 
-class IsentropicVerticalAdvection(StencilFactory):
+class IsentropicVerticalAdvection(GridComponent, StencilFactory):
     """Vertical derivative of the conservative vertical advection flux of s, su, sv (and of the
     water species when ``moist``), by one of the minimal vertical flux schemes
     (src/tasmania/isentropic/dynamics/subclasses/minimal_vertical_fluxes/*.py)."""
@@ -89,7 +89,7 @@ class IsentropicVerticalAdvection(StencilFactory):
                            origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))
 
 
-class IsentropicConservativeCoriolis(StencilFactory):
+class IsentropicConservativeCoriolis(GridComponent, StencilFactory):
     """Mirror of ``tasmania.IsentropicConservativeCoriolis``
     (src/tasmania/isentropic/physics/coriolis.py:L44-L164): Coriolis forcing of the momenta on
     the interior of the numerical grid (``nb`` boundary layers excluded)."""
@@ -123,7 +123,7 @@ class IsentropicConservativeCoriolis(StencilFactory):
                            origin=(nb, nb, 0), domain=(g.nx - 2 * nb, g.ny - 2 * nb, g.nz))
 
 
-class Smagorinsky2d(StencilFactory):
+class Smagorinsky2d(GridComponent, StencilFactory):
     """Mirror of ``tasmania.Smagorinsky2d`` (src/tasmania/physics/turbulence.py:L42-L163):
     tendencies of x_velocity / y_velocity on the interior of the numerical grid."""
 
@@ -182,7 +182,7 @@ class IsentropicSmagorinsky(Smagorinsky2d):
                            cs=self._cs, factor=factor, **self._box())
 
 
-class IsentropicImplicitVerticalAdvectionDiagnostic(StencilFactory):
+class IsentropicImplicitVerticalAdvectionDiagnostic(GridComponent, StencilFactory):
     """Mirror of ``tasmania.IsentropicImplicitVerticalAdvectionDiagnostic``
     (src/tasmania/isentropic/physics/implicit_vertical_advection.py:L44-L219): Crank-Nicolson
     vertical advection, one tridiagonal solve per column and field."""
@@ -225,7 +225,7 @@ class IsentropicImplicitVerticalAdvectionDiagnostic(StencilFactory):
         self._stencil(**args, origin=(0, 0, 0), domain=(g.nx, g.ny, g.nz))
 
 
-class IsentropicImplicitVerticalAdvectionPrognostic(StencilFactory):
+class IsentropicImplicitVerticalAdvectionPrognostic(GridComponent, StencilFactory):
     """Mirror of ``tasmania.IsentropicImplicitVerticalAdvectionPrognostic``
     (src/tasmania/isentropic/physics/implicit_vertical_advection.py:L593-L919): the same solves,
     returned as tendencies (x_new - x) / dt in storages owned by the component."""

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from tasmania_b200.framework import BackendOptions, StencilFactory, StorageOptions
+from tasmania_b200.framework import BackendOptions, GridComponent, StencilFactory, StorageOptions
 from tasmania_b200.stencils import SEDIMENTATION_FLUX
 
 mfwv = "mass_fraction_of_water_vapor_in_air"
@@ -34,7 +34,7 @@ DEFAULT_CONSTANTS = {
 }
 
 
-class _Component(StencilFactory):
+class _Component(GridComponent, StencilFactory):
     def __init__(self, grid, physical_constants=None, *, backend="b200", backend_options=None,
                  storage_shape=None, storage_options=None):
         super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())

@@ -75,9 +75,7 @@ def as_storage_b200(data, *, storage_options=None):
     return storage.as_storage(data, device=_device(storage_options))
 
 
-def subroutine_compiler_b200(definition, *, backend_options=None):
-    """Subroutines are descriptors for b200: nothing to compile."""
-    return definition
+subroutine_compiler_b200 = fw.subroutine_compiler_b200  # descriptors: nothing to compile
 
 
 # ------------------------------------------------------------------ descriptors as functions

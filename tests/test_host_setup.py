@@ -219,3 +219,17 @@ def test_dycore_mirror_accepts_the_reference_smoothing_arguments(monkeypatch):
     assert dyc._smooth is False and dyc._smooth_moist is False
     with pytest.raises(TypeError):
         IsentropicDynamicalCore(grid, Relaxed(19, 17, 6, 3, nr=6), smoooth=False, **kw)
+
+
+def test_stencil_factory_compiler_accessors():
+    """framework/stencil.py:L286-L297, L356-L427: get_stencil_compiler / get_subroutine_compiler /
+    compile_subroutine exist on every mirror (one compiler per kind: there is one backend)."""
+    from tasmania_b200 import framework as fw
+
+    f = fw.StencilFactory()
+    assert f.get_stencil_compiler("b200") is fw.compiler_b200
+    assert f.get_subroutine_compiler("b200", "flux_dry") is fw.subroutine_compiler_b200
+    with pytest.raises(tb.FactoryRegistryError):
+        f.get_stencil_compiler("numpy")
+    desc = f.get_subroutine_definition("set_output")
+    assert f.compile_subroutine("set_output") is desc

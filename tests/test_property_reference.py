@@ -221,3 +221,36 @@ def test_b200_mirror_components_on_random_grids(data):
             hb_ref.enforce_field(a, field_name=name)
             hb.enforce_field(b, field_name=name)
             np.testing.assert_array_equal(tb.to_numpy(b), a, err_msg="periodic " + name)
+
+
+@settings(max_examples=40, **SETTINGS)
+@given(data=st.data())
+def test_grid_component_shape_helpers(data):
+    """framework.GridComponent (the shape helpers every grid-based mirror inherits) against the
+    reference's GridComponent methods run in place (framework/base_components.py:L55-L135)."""
+    import types
+
+    from tasmania_b200.framework import GridComponent
+
+    refload.install_framework()
+    ref_cls = refload.load("tasmania.framework.base_components").GridComponent
+    grid = types.SimpleNamespace(nx=data.draw(st.integers(1, 20)), ny=data.draw(st.integers(1, 20)),
+                                 nz=data.draw(st.integers(1, 20)))
+    ref_self = types.SimpleNamespace(grid=grid, get_field_grid_shape=None, get_shape=ref_cls.get_shape)
+    ref_self.get_field_grid_shape = lambda name: ref_cls.get_field_grid_shape(ref_self, name)
+    mine = GridComponent()
+    mine.grid = grid
+    stem = data.draw(st.sampled_from(("air_density", "x_velocity", "precipitation", "height")))
+    stag = data.draw(st.sampled_from(("", "_at_u_locations", "_at_v_locations", "_at_uv_locations")))
+    lev = data.draw(st.sampled_from(("", "_on_interface_levels", "_at_surface_level")))
+    name = stem + stag + lev
+    assert tuple(mine.get_field_grid_shape(name)) == tuple(ref_cls.get_field_grid_shape(ref_self, name))
+    triple = st.tuples(st.integers(1, 24), st.integers(1, 24), st.integers(1, 24))
+    shape = data.draw(st.one_of(st.none(), triple), label="shape")
+    lo = data.draw(triple, label="min")
+    hi = data.draw(st.one_of(st.none(), triple.map(lambda t: tuple(max(a, b) for a, b in zip(t, lo)))), label="max")
+    assert list(mine.get_shape(shape, lo, hi)) == list(ref_cls.get_shape(shape, lo, hi))
+    assert list(mine.get_field_storage_shape(name, shape)) == list(
+        ref_cls.get_field_storage_shape(ref_self, name, shape))
+    assert list(mine.get_storage_shape(shape, None, hi and tuple(max(a, b) for a, b in zip(hi, (grid.nx, grid.ny, grid.nz))))) == list(
+        ref_cls.get_storage_shape(ref_self, shape, None, hi and tuple(max(a, b) for a, b in zip(hi, (grid.nx, grid.ny, grid.nz)))))
