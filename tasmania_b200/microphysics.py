@@ -221,6 +221,24 @@ class KesslerSedimentation(_Component):
                       **self._box)
 
 
+class Clipping(_Component):
+    """Negative values of the water species set to zero (physics/microphysics/utils.py:L58-L141): one
+    ``clip`` launch per species over its whole storage, as the reference's ``array_call`` does."""
+
+    kind = "diagnostic"
+
+    def __init__(self, grid, water_species_names=None, **kwargs):
+        super().__init__(grid, None, **kwargs)
+        self._names = tuple(water_species_names or ())
+        self.diagnostic_names = self._names
+        self._stencil = self.compile_stencil("clip")
+
+    def array_call(self, state, out):
+        for name in self._names:
+            out_q = out[name]
+            self._stencil(in_field=state[name], out_field=out_q, origin=(0, 0, 0), domain=tuple(out_q.shape))
+
+
 class Precipitation(_Component):
     """Precipitation rate and accumulated precipitation at the surface (2-D outputs)."""
 

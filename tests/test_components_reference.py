@@ -176,3 +176,34 @@ def test_coriolis_smagorinsky_and_vertical_advection_array_calls(evolved):
     for n in names:
         np.testing.assert_array_equal(tnd[n], want[n], err_msg=n)
     assert float(np.abs(want[mm.QV][box]).max()) > 0.0
+
+
+def test_clipping_array_call(evolved):
+    """Clipping (physics/microphysics/utils.py:L58-L141): the reference's array_call with its own
+    clip_numpy stencil against the b200 mirror through the oracle-backed stub, on species with
+    negative values, bit for bit; the inputs stay untouched."""
+    import tasmania_b200 as tb
+    from tasmania_b200.microphysics import Clipping
+    from tests.abi_oracle import OracleStub
+    from tests.abi_stub import stubbed_library
+
+    model, st = evolved
+    _, ut, _ = modules()
+    math = refload.load("tasmania.framework.subclasses.stencil_definitions.math")
+    names = (mm.QV, mm.QC, mm.QR)
+    rng = np.random.default_rng(8)
+    state = {n: st[n] - 0.5 * np.abs(st[n]).mean() * rng.random(st[n].shape) for n in names}
+    assert all((v < 0).any() and (v > 0).any() for v in state.values())
+    me = stand_in(model, math.clip_numpy, {}, _names=names)
+    ref = {n: np.full(model.shape, 7.0) for n in names}
+    ut.Clipping.array_call(me, state, ref)
+    with stubbed_library(OracleStub) as stub:
+        comp = Clipping(model.g, water_species_names=names)
+        dev_state = {n: tb.as_storage(v) for n, v in state.items()}
+        out = {n: tb.as_storage(np.full(model.shape, 7.0)) for n in names}
+        comp.array_call(dev_state, out)
+        assert stub.count("tb200_elementwise") == 3
+        for n in names:
+            np.testing.assert_array_equal(tb.to_numpy(out[n]), ref[n], err_msg=n)
+            np.testing.assert_array_equal(tb.to_numpy(dev_state[n]), state[n])
+            assert float(ref[n].min()) == 0.0
