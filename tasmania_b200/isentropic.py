@@ -392,6 +392,8 @@ class IsentropicDynamicalCore(GridComponent, StencilFactory):
         ctx, self._scratch = storage.stage_scratch(self.storage_shape, 3, self.storage_options.device)
         if ctx is not None:
             self._ctx = ctx
+        if self._periodic:
+            self._periodic_gamma()  # allocated with the scratch, outside any graph capture
 
     def _periodic_gamma(self):
         if getattr(self, "_zero_gamma2d", None) is None:

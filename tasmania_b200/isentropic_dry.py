@@ -15,7 +15,7 @@ from __future__ import annotations
 from datetime import datetime
 
 from tasmania_b200 import storage
-from tasmania_b200.boundary import Relaxed
+from tasmania_b200.boundary import Periodic, Relaxed
 from tasmania_b200.isentropic import (MTG, S, SU, SV, U, V, IsentropicDiagnostics,
                                       IsentropicDynamicalCore)
 
@@ -28,12 +28,19 @@ class IsentropicDryRun:
 
     def __init__(self, grid, state, timestep, *, nb=3, nr=6, horizontal_flux_scheme="fifth_order_upwind",
                  time_integration_scheme="rk3ws_si", eps=0.5, damp=True, damp_depth=15, damp_max=5e-4,
-                 damp_at_every_stage=True, init_time=None, device=None):
+                 damp_at_every_stage=True, init_time=None, device=None, boundary="relaxed"):
         nx, ny, nz = grid.nx, grid.ny, grid.nz
         self.grid, self.dt = grid, timestep
         self.nx, self.ny, self.nz = nx, ny, nz
         self.pt = float(state[P][0, 0, 0])
-        self.hb = Relaxed(nx, ny, nz, nb, nr=nr)
+        if boundary == "relaxed":
+            self.hb = Relaxed(nx, ny, nz, nb, nr=nr)
+        elif boundary == "periodic":
+            # ``grid`` is the numerical grid (physical + nb ghost points a side, periodic.py:L44-L50)
+            # and ``state`` lives on it with wrapped ghost layers (``Periodic.get_numerical_field``)
+            self.hb = Periodic(nx - 2 * nb, ny - 2 * nb, nz, nb)
+        else:
+            raise ValueError(f"boundary must be 'relaxed' or 'periodic', got {boundary!r}")
         self.state = {n: storage.as_storage(v, device=device) for n, v in state.items()}
         self.init_time = init_time or datetime(2000, 1, 1)
         self.state["time"] = self.init_time
