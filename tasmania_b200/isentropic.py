@@ -49,7 +49,10 @@ class IsentropicDiagnostics(GridComponent, StencilFactory):
         super().__init__(backend, backend_options or BackendOptions(), storage_options or StorageOptions())
         self.grid = grid
         self.rpc = dict(CONSTANTS)
-        self.rpc.update(physical_constants or {})
+        # plain numbers under the externals' names (pref, rd, g, cp) or under the reference's long
+        # names (diagnostics.py:L56-L63), in the reference's units
+        for key, value in (physical_constants or {}).items():
+            self.rpc[self.physical_constant_names.get(key, key)] = float(getattr(value, "values", value))
         nx, ny, nz = grid.nx, grid.ny, grid.nz
         shape = tuple(storage_shape or (nx + 1, ny + 1, nz + 1))
         self._shape = shape
@@ -67,6 +70,16 @@ class IsentropicDiagnostics(GridComponent, StencilFactory):
         self._stencil_density_and_temperature = self.compile_stencil("density_and_temperature")
         self._stencil_montgomery = self.compile_stencil("montgomery")
         self._stencil_height = self.compile_stencil("height")
+
+    physical_constant_names = {
+        "air_pressure_at_sea_level": "pref", "gas_constant_of_dry_air": "rd",
+        "gravitational_acceleration": "g", "specific_heat_of_dry_air_at_constant_pressure": "cp"}
+    default_physical_constants = {long: CONSTANTS[short] for long, short in physical_constant_names.items()}
+
+    @property
+    def raw_physical_constants(self):
+        """framework/base_components.py:L46-L48, keyed by the reference's names."""
+        return {long: self.rpc[short] for long, short in self.physical_constant_names.items()}
 
     def _set_topography(self):
         """Current terrain height -> device.  The reference re-uploads the host profile on

@@ -53,6 +53,13 @@ class _Component(GridComponent, StencilFactory):
     def diagnostic_shape(self, name):
         return self.storage_shape
 
+    default_physical_constants = DEFAULT_CONSTANTS
+
+    @property
+    def raw_physical_constants(self):
+        """framework/base_components.py:L46-L48."""
+        return dict(self.rpc)
+
     @property
     def _box(self):
         g = self.grid

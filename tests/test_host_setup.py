@@ -233,3 +233,22 @@ def test_stencil_factory_compiler_accessors():
         f.get_stencil_compiler("numpy")
     desc = f.get_subroutine_definition("set_output")
     assert f.compile_subroutine("set_output") is desc
+
+
+def test_physical_constants_by_the_reference_names(monkeypatch):
+    """IsentropicDiagnostics takes its constants under the reference's names too
+    (isentropic/dynamics/diagnostics.py:L56-L63) and reports them through raw_physical_constants."""
+    from tasmania_b200 import storage
+    from tasmania_b200.isentropic import IsentropicDiagnostics
+
+    monkeypatch.setattr(storage, "DEFAULT_DEVICE_OVERRIDE", "cpu")
+    x, y = np.linspace(-1.0, 1.0, 9), np.linspace(-1.0, 1.0, 7)
+    grid = Grid((-1.0, 1.0), 9, (-1.0, 1.0), 7, (400.0, 280.0), 4, units_to_m=1e3,
+                topography=Topography(gaussian_profile(x, y, 500.0, 0.5, 0.5), timedelta(seconds=0)))
+    d = IsentropicDiagnostics(grid)
+    assert d.raw_physical_constants == d.default_physical_constants
+    assert d.raw_physical_constants["gravitational_acceleration"] == 9.80665
+    d = IsentropicDiagnostics(grid, {"gravitational_acceleration": 9.81, "cp": 1005.0})
+    assert d.rpc["g"] == 9.81 and d.rpc["cp"] == 1005.0 and d.rpc["rd"] == 287.05
+    assert d.raw_physical_constants["specific_heat_of_dry_air_at_constant_pressure"] == 1005.0
+    assert d.backend_options.externals["g"] == 9.81
